@@ -1,0 +1,45 @@
+"""Deterministic synthetic YUV 4:2:0 luma sequences: smoothed-noise texture
+panning a few pixels per frame, a moving object, gain/offset drift and sensor noise.  Used by
+tests, bench.py and the golden-vector generators so that every side sees the same input."""
+import numpy as np
+
+
+def _smooth(a, k):
+    for _ in range(k):
+        a = (a + np.roll(a, 1, 0) + np.roll(a, -1, 0) + np.roll(a, 1, 1) + np.roll(a, -1, 1)) / 5.0
+    return a
+
+
+def luma_sequence(W, H, nframes, seed=20261018, pan=(2, 1), obj=(3, 1), noise=1.5, gain=1.0, offset=0.0):
+    """Returns uint8 [nframes, H, W]."""
+    rng = np.random.default_rng(seed)
+    big = rng.normal(0, 1, (H + 64, W + 64))
+    tex = _smooth(big, 3)
+    tex = (tex - tex.min()) / (tex.max() - tex.min())
+    fine = rng.normal(0, 1, (H + 64, W + 64))
+    tex = 40 + 160 * tex + 14 * _smooth(fine, 1)
+    ob = 128 + 90 * _smooth(rng.normal(0, 1, (32, 32)), 1)
+    frames = np.zeros((nframes, H, W), np.uint8)
+    for t in range(nframes):
+        sx, sy = (pan[0] * t) % 32, (pan[1] * t) % 32
+        f = tex[16 + sy:16 + sy + H, 16 + sx:16 + sx + W].copy()
+        ox, oy = (W // 3 + obj[0] * t) % (W - 32), (H // 3 + obj[1] * t) % (H - 32)
+        f[oy:oy + 32, ox:ox + 32] = ob
+        f = (gain ** t) * f + offset * t + rng.normal(0, noise, f.shape)
+        frames[t] = np.clip(np.rint(f), 0, 255).astype(np.uint8)
+    return frames
+
+
+def predictors(W, H, nrefs, seed=1, spread=0, base=None, rmax=6):
+    """Synthetic quarter-pel MV predictors [nmb, nrefs, 41, 2] int16 and the integer search centres
+    JM derives from them (mv_search.c:931-932: ((p+2)>>2)*4).  spread=0: one predictor per
+    (MB, ref) shared by its 41 partitions; spread>0: per-partition jitter of +-spread qpel."""
+    rng = np.random.default_rng(seed)
+    nmb = (W // 16) * (H // 16)
+    p = rng.integers(-4 * rmax, 4 * rmax + 1, (nmb, nrefs, 1, 2)) if base is None else base
+    p = np.broadcast_to(p, (nmb, nrefs, 41, 2)).copy()
+    if spread:
+        p += rng.integers(-spread, spread + 1, p.shape)
+    p = p.astype(np.int16)
+    c = (((p.astype(np.int32) + 2) >> 2) * 4).astype(np.int16)
+    return p, c

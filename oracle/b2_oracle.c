@@ -1,0 +1,355 @@
+/* b2_oracle.c -- CPU restatement of the reference's block-matching hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference leg may load this; the product (libb2me.so) never does.
+ *
+ * Parity status: PINNED.  Every function here is checked (tests/test_oracle_vs_ref.py,
+ * run in the build container where /root/reference exists) against the unmodified
+ * reference objects through oracle/_ref/libjmref.so / libv1ref.so, and against the golden
+ * vectors under tests/golden/ that were generated from those objects and from a
+ * boundary-logged run of the stock `lencod` (scripts in oracle/gen_golden_*.py).
+ *
+ * Path aliases: JM/ = /root/reference/4.对比程序/jm18.5/JM/,
+ *               V1/ = /root/reference/2.论文程序/ZhangLing_Yu_version1/H264Fractal/
+ *
+ * Plain C, no dependencies beyond libc/libm.  Build: gcc -O2 -shared -fPIC (no -march=native,
+ * no FMA contraction) so the double arithmetic of the fractal part is reproducible.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
+
+#define PAD_X 32   /* IMG_PAD_SIZE_X  JM/lencod/inc/defines.h:120 */
+#define PAD_Y 20   /* IMG_PAD_SIZE_Y  JM/lencod/inc/defines.h:121 */
+#define DISTBLK_MAX_ORC (((int64_t)INT_MAX) << 5)   /* defines.h:135 */
+
+static inline int iclip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int iabs_(int v) { return v < 0 ? -v : v; }
+
+/* ------------------------------------------------------------------------------------
+ * Tables: spiral order and MV bit lengths.   JM/lencod/src/mv_search.c:406-442, :366-374
+ * ---------------------------------------------------------------------------------- */
+/* out: (2R+1)^2 (x,y) pairs in integer-pel units (the reference keeps x1, x2, x4 copies). */
+void orc_spiral(int R, int16_t *out_xy)
+{
+  int k = 1, l, i;
+  out_xy[0] = out_xy[1] = 0;
+  for (l = 1; l <= (R > 1 ? R : 1); l++) {
+    for (i = -l + 1; i < l; i++) {
+      out_xy[2*k] = (int16_t)i;  out_xy[2*k+1] = (int16_t)-l; k++;
+      out_xy[2*k] = (int16_t)i;  out_xy[2*k+1] = (int16_t) l; k++;
+    }
+    for (i = -l; i <= l; i++) {
+      out_xy[2*k] = (int16_t)-l; out_xy[2*k+1] = (int16_t)i; k++;
+      out_xy[2*k] = (int16_t) l; out_xy[2*k+1] = (int16_t)i; k++;
+    }
+  }
+}
+
+/* mvbits[d]: Exp-Golomb length of a quarter-pel MV difference (mv_search.c:366-374):
+ * 1 for d==0, else 2*floor(log2|d|)+3. */
+int orc_mvbits(int d)
+{
+  int a = iabs_(d), n = 0;
+  if (!a) return 1;
+  while (a >>= 1) n++;
+  return 2 * n + 3;
+}
+
+static inline int64_t orc_mv_cost(int lambda, int cx, int cy, int px, int py)
+{ /* JM/lencod/inc/mv_search.h:100-104 (JCOST_CALC_SCALEUP) */
+  return (int64_t)lambda * (int64_t)(orc_mvbits(cx - px) + orc_mvbits(cy - py));
+}
+
+/* ------------------------------------------------------------------------------------
+ * 16 quarter-pel planes.   JM/lencod/src/img_luma.c:611-680 (+ helpers :40-600)
+ * planes: [4][4][Hp][Wp] u8 with Hp = H+40, Wp = W+64; index [yy][xx] = (y&3, x&3).
+ * ---------------------------------------------------------------------------------- */
+static inline int clip1_255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+void orc_subpel_planes(const uint8_t *luma, int W, int H, uint8_t *planes)
+{
+  const int Wp = W + 2 * PAD_X, Hp = H + 2 * PAD_Y;
+  const size_t PS = (size_t)Wp * Hp;
+#define PL(yy, xx) (planes + ((size_t)((yy) * 4 + (xx))) * PS)
+  uint8_t *p00 = PL(0,0), *p02 = PL(0,2), *p20 = PL(2,0), *p22 = PL(2,2);
+  int32_t *tmp = (int32_t *)malloc(PS * sizeof(int32_t));
+  int x, y;
+  /* [0][0]: integer samples, edge replicated into the pad (img_luma.c:40-86) */
+  for (y = 0; y < Hp; y++) {
+    int sy = iclip3(0, H - 1, y - PAD_Y);
+    for (x = 0; x < Wp; x++)
+      p00[(size_t)y * Wp + x] = luma[(size_t)sy * W + iclip3(0, W - 1, x - PAD_X)];
+  }
+  /* [0][2]: horizontal 6-tap (20,-5,1) over the padded plane, neighbours clamped to the
+   * padded row ends; unrounded value kept in tmp (img_luma.c:151-237) */
+  for (y = 0; y < Hp; y++) {
+    const uint8_t *s = p00 + (size_t)y * Wp;
+    for (x = 0; x < Wp; x++) {
+#define CX(v) ((v) < 0 ? 0 : ((v) > Wp - 1 ? Wp - 1 : (v)))
+      int is = 20 * (s[x] + s[CX(x + 1)]) - 5 * (s[CX(x - 1)] + s[CX(x + 2)]) + (s[CX(x - 2)] + s[CX(x + 3)]);
+      tmp[(size_t)y * Wp + x] = is;
+      p02[(size_t)y * Wp + x] = (uint8_t)clip1_255((is + 16) >> 5);
+    }
+  }
+  /* [2][0]: vertical 6-tap of [0][0] (img_luma.c:257-331); [2][2]: vertical 6-tap of the
+   * unrounded horizontal intermediates, (is+512)>>10 (img_luma.c:347-422) */
+  for (y = 0; y < Hp; y++) {
+#define CY(v) ((v) < 0 ? 0 : ((v) > Hp - 1 ? Hp - 1 : (v)))
+    size_t a = (size_t)y * Wp, d = (size_t)CY(y + 1) * Wp, b = (size_t)CY(y - 1) * Wp,
+           e = (size_t)CY(y + 2) * Wp, c = (size_t)CY(y - 2) * Wp, f = (size_t)CY(y + 3) * Wp;
+    for (x = 0; x < Wp; x++) {
+      int is = 20 * (p00[a + x] + p00[d + x]) - 5 * (p00[b + x] + p00[e + x]) + (p00[c + x] + p00[f + x]);
+      int it = 20 * (tmp[a + x] + tmp[d + x]) - 5 * (tmp[b + x] + tmp[e + x]) + (tmp[c + x] + tmp[f + x]);
+      p20[a + x] = (uint8_t)clip1_255((is + 16) >> 5);
+      p22[a + x] = (uint8_t)clip1_255((it + 512) >> 10);
+    }
+  }
+  /* twelve quarter planes: (a+b+1)>>1 (img_luma.c:440-600, call list :653-678) */
+  for (y = 0; y < Hp; y++) {
+    size_t r = (size_t)y * Wp, rn = (size_t)CY(y + 1) * Wp;
+    for (x = 0; x < Wp; x++) {
+      int xn = CX(x + 1);
+#define AVG(a, b) ((uint8_t)(((int)(a) + (int)(b) + 1) >> 1))
+      PL(0,1)[r + x] = AVG(p00[r + x], p02[r + x]);
+      PL(1,0)[r + x] = AVG(p00[r + x], p20[r + x]);
+      PL(1,1)[r + x] = AVG(p02[r + x], p20[r + x]);
+      PL(1,2)[r + x] = AVG(p02[r + x], p22[r + x]);
+      PL(2,1)[r + x] = AVG(p20[r + x], p22[r + x]);
+      PL(0,3)[r + x] = AVG(p02[r + x], p00[r + xn]);
+      PL(1,3)[r + x] = AVG(p02[r + x], p20[r + xn]);
+      PL(2,3)[r + x] = AVG(p22[r + x], p20[r + xn]);
+      PL(3,0)[r + x] = AVG(p20[r + x], p00[rn + x]);
+      PL(3,1)[r + x] = AVG(p20[r + x], p02[rn + x]);
+      PL(3,2)[r + x] = AVG(p22[r + x], p02[rn + x]);
+      PL(3,3)[r + x] = AVG(p02[rn + x], p20[r + xn]);
+    }
+  }
+  free(tmp);
+#undef PL
+#undef CX
+#undef CY
+#undef AVG
+}
+
+/* UMVLine4X (JM/lencod/inc/refbuf.h:22-26): plane [y&3][x&3], block ORIGIN clamped to
+ * [-20, H+3] x [-32, W+15] (size_y_pad/size_x_pad, mbuffer.c:549-550). Returns pointer
+ * into the padded plane (row stride Wp). */
+static inline const uint8_t *orc_umv_line4x(const uint8_t *planes, int W, int H, int y, int x)
+{
+  const int Wp = W + 2 * PAD_X, Hp = H + 2 * PAD_Y;
+  const uint8_t *pl = planes + ((size_t)((y & 3) * 4 + (x & 3))) * ((size_t)Wp * Hp);
+  int yy = iclip3(-PAD_Y, H + 3, y >> 2), xx = iclip3(-PAD_X, W + 15, x >> 2);
+  return pl + (size_t)(yy + PAD_Y) * Wp + (xx + PAD_X);
+}
+
+/* computeSAD (JM/lencod/src/me_distortion.c:349-426), luma only, no early exit (the early
+ * exit is result-neutral, SURVEY Q-J1).  cand = absolute quarter-pel coordinates.
+ * Returns the plain SAD (caller shifts <<5). */
+int orc_sad(const uint8_t *planes, int W, int H, const uint8_t *cur, int cur_stride,
+            int bsx, int bsy, int cand_x, int cand_y)
+{
+  const int Wp = W + 2 * PAD_X;
+  const uint8_t *ref = orc_umv_line4x(planes, W, H, cand_y, cand_x);
+  int x, y, s = 0;
+  for (y = 0; y < bsy; y++)
+    for (x = 0; x < bsx; x++)
+      s += iabs_((int)cur[y * cur_stride + x] - (int)ref[(size_t)y * Wp + x]);
+  return s;
+}
+
+/* HadamardSAD4x4 (me_distortion.c:175-258): 2-D 4-point Hadamard, sum |coef|, (s+1)>>1.
+ * The butterfly network is sign/permutation-equivalent to H4 * D * H4; the absolute sum is
+ * invariant to row/column sign flips and permutations of the transform, so a plain
+ * separable Hadamard is used here.  diff: 16 shorts, raster. */
+int orc_hadamard4x4(const int16_t *d)
+{
+  int m[16], i, s = 0;
+  for (i = 0; i < 4; i++) {               /* rows */
+    int a = d[4*i], b = d[4*i+1], c = d[4*i+2], e = d[4*i+3];
+    m[4*i] = a + b + c + e; m[4*i+1] = a - b + c - e; m[4*i+2] = a + b - c - e; m[4*i+3] = a - b - c + e;
+  }
+  for (i = 0; i < 4; i++) {               /* columns */
+    int a = m[i], b = m[4+i], c = m[8+i], e = m[12+i];
+    s += iabs_(a + b + c + e) + iabs_(a - b + c - e) + iabs_(a + b - c - e) + iabs_(a - b - c + e);
+  }
+  return (s + 1) >> 1;
+}
+
+/* HadamardSAD8x8 (me_distortion.c:266-341): (sum|H8 D H8| + 2) >> 2 */
+int orc_hadamard8x8(const int16_t *d)
+{
+  int m[64], t[8], i, j, k, s = 0;
+  for (j = 0; j < 8; j++) {
+    for (i = 0; i < 8; i++) t[i] = d[8*j + i];
+    for (k = 1; k < 8; k <<= 1)
+      for (i = 0; i < 8; i++) if (!(i & k)) { int a = t[i], b = t[i | k]; t[i] = a + b; t[i | k] = a - b; }
+    for (i = 0; i < 8; i++) m[8*j + i] = t[i];
+  }
+  for (i = 0; i < 8; i++) {
+    for (j = 0; j < 8; j++) t[j] = m[8*j + i];
+    for (k = 1; k < 8; k <<= 1)
+      for (j = 0; j < 8; j++) if (!(j & k)) { int a = t[j], b = t[j | k]; t[j] = a + b; t[j | k] = a - b; }
+    for (j = 0; j < 8; j++) s += iabs_(t[j]);
+  }
+  return (s + 2) >> 2;
+}
+
+/* computeSATD (me_distortion.c:745-825), no early exit.  Each 4x4 (8x8) tile origin goes
+ * through UMVLine4X separately (per-tile clamp, :771 / :801). */
+int orc_satd(const uint8_t *planes, int W, int H, const uint8_t *cur, int cur_stride,
+             int bsx, int bsy, int cand_x, int cand_y, int test8x8)
+{
+  const int Wp = W + 2 * PAD_X, T = test8x8 ? 8 : 4;
+  int bx, by, i, j, s = 0; int16_t diff[64];
+  for (by = 0; by < bsy; by += T)
+    for (bx = 0; bx < bsx; bx += T) {
+      const uint8_t *ref = orc_umv_line4x(planes, W, H, cand_y + (by << 2), cand_x + (bx << 2));
+      for (j = 0; j < T; j++)
+        for (i = 0; i < T; i++)
+          diff[j * T + i] = (int16_t)((int)cur[(by + j) * cur_stride + bx + i] - (int)ref[(size_t)j * Wp + i]);
+      s += test8x8 ? orc_hadamard8x8(diff) : orc_hadamard4x4(diff);
+    }
+  return s;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Searches.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int W, H, nrefs, R;          /* frame size (multiple of 16), refs, max search range (pel) */
+  const uint8_t *cur;          /* W x H */
+  const uint8_t *planes;       /* [nrefs][16][Hp][Wp] */
+  int16_t *spiral;             /* (2R+1)^2 x 2, integer pel */
+} OrcFrame;
+
+void *orc_frame_create(int W, int H, int nrefs, int R, const uint8_t *cur, const uint8_t *refs /*[nrefs][H][W]*/)
+{
+  OrcFrame *f = (OrcFrame *)calloc(1, sizeof(OrcFrame));
+  const size_t PS = (size_t)(W + 2 * PAD_X) * (H + 2 * PAD_Y);
+  int r, np = (2 * R + 1) * (2 * R + 1); if (np < 9) np = 9;
+  uint8_t *pl = (uint8_t *)malloc(PS * 16 * nrefs);
+  uint8_t *c = (uint8_t *)malloc((size_t)W * H);
+  memcpy(c, cur, (size_t)W * H);
+  for (r = 0; r < nrefs; r++) orc_subpel_planes(refs + (size_t)r * W * H, W, H, pl + PS * 16 * r);
+  f->W = W; f->H = H; f->nrefs = nrefs; f->R = R; f->cur = c; f->planes = pl;
+  f->spiral = (int16_t *)malloc(sizeof(int16_t) * 2 * np);
+  orc_spiral(R, f->spiral);
+  return f;
+}
+void orc_frame_destroy(void *h)
+{ OrcFrame *f = (OrcFrame *)h; free((void *)f->cur); free((void *)f->planes); free(f->spiral); free(f); }
+const uint8_t *orc_frame_planes(void *h, int r)
+{ OrcFrame *f = (OrcFrame *)h; return f->planes + (size_t)r * 16 * (size_t)(f->W + 2*PAD_X) * (f->H + 2*PAD_Y); }
+
+/* full_search_motion_estimation (JM/lencod/src/me_fullsearch.c:39-103), RDO build
+ * (check_for_00 is only live when !rdopt).  mv: in = centre (relative quarter-pel MV),
+ * out = best integer MV.  search_range in pel = min(max_x,max_y)>>2 of the block's window. */
+int64_t orc_full_search(const OrcFrame *f, int ref, int pos_x, int pos_y, int bsx, int bsy,
+                        const int16_t *pred_mv, int16_t *mv, int search_range,
+                        int64_t min_mcost, int lambda_factor)
+{
+  const uint8_t *pl = orc_frame_planes((void *)f, ref);
+  const uint8_t *cur = f->cur + (size_t)pos_y * f->W + pos_x;
+  int max_pos = (2 * search_range + 1) * (2 * search_range + 1), pos, best_pos = 0;
+  int cx = (pos_x << 2) + mv[0], cy = (pos_y << 2) + mv[1];
+  int px = (pos_x << 2) + pred_mv[0], py = (pos_y << 2) + pred_mv[1];
+  for (pos = 0; pos < max_pos; pos++) {
+    int candx = cx + 4 * f->spiral[2*pos], candy = cy + 4 * f->spiral[2*pos+1];
+    int64_t mcost = orc_mv_cost(lambda_factor, candx, candy, px, py);
+    if (mcost >= min_mcost) continue;
+    mcost += ((int64_t)orc_sad(pl, f->W, f->H, cur, f->W, bsx, bsy, candx, candy)) << 5;
+    if (mcost < min_mcost) { best_pos = pos; min_mcost = mcost; }
+  }
+  if (best_pos) { mv[0] = (int16_t)(mv[0] + 4 * f->spiral[2*best_pos]); mv[1] = (int16_t)(mv[1] + 4 * f->spiral[2*best_pos+1]); }
+  return min_mcost;
+}
+
+/* sub_pel_motion_estimation (me_fullsearch.c:186-289), RDO build.  start_hp/start_qp =
+ * p_Vid->start_me_refinement_hp/_qp (mv_search.c:445-446); metric_h/q: 0 SAD, 2 SATD. */
+int64_t orc_sub_pel(const OrcFrame *f, int ref, int pos_x, int pos_y, int bsx, int bsy,
+                    const int16_t *pred_mv, int16_t *mv, int64_t min_mcost,
+                    const int *lambda /*[3]*/, int start_hp, int start_qp,
+                    int metric_h, int metric_q, int test8x8)
+{
+  const uint8_t *pl = orc_frame_planes((void *)f, ref);
+  const uint8_t *cur = f->cur + (size_t)pos_y * f->W + pos_x;
+  int pos, best_pos, lam = lambda[1];
+  int max_pos2 = 9; /* search_pos2 (init_mv_block, mv_search.c:718) ; imax(1,9) */
+  for (best_pos = 0, pos = start_hp; pos < max_pos2; pos++) {
+    int cx = mv[0] + 2 * f->spiral[2*pos], cy = mv[1] + 2 * f->spiral[2*pos+1];
+    int64_t mcost = orc_mv_cost(lam, cx, cy, pred_mv[0], pred_mv[1]);
+    int d;
+    if (mcost >= min_mcost) continue;
+    d = (metric_h == 2) ? orc_satd(pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2), test8x8)
+                        : orc_sad (pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2));
+    mcost += ((int64_t)d) << 5;
+    if (mcost < min_mcost) { min_mcost = mcost; best_pos = pos; }
+  }
+  if (best_pos) { mv[0] = (int16_t)(mv[0] + 2 * f->spiral[2*best_pos]); mv[1] = (int16_t)(mv[1] + 2 * f->spiral[2*best_pos+1]); }
+  if (!start_qp) min_mcost = DISTBLK_MAX_ORC;
+  lam = lambda[2];
+  for (best_pos = 0, pos = start_qp; pos < 9; pos++) {
+    int cx = mv[0] + f->spiral[2*pos], cy = mv[1] + f->spiral[2*pos+1];
+    int64_t mcost = orc_mv_cost(lam, cx, cy, pred_mv[0], pred_mv[1]);
+    int d;
+    if (mcost >= min_mcost) continue;
+    d = (metric_q == 2) ? orc_satd(pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2), test8x8)
+                        : orc_sad (pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2));
+    mcost += ((int64_t)d) << 5;
+    if (mcost < min_mcost) { min_mcost = mcost; best_pos = pos; }
+  }
+  if (best_pos) { mv[0] = (int16_t)(mv[0] + f->spiral[2*best_pos]); mv[1] = (int16_t)(mv[1] + f->spiral[2*best_pos+1]); }
+  return min_mcost;
+}
+
+/* partition p (0..40) -> blocktype (1..7, JM block_size[] macroblock.h:58) and offset in MB */
+static const uint8_t ORC_BS[8][2] = {{0,0},{16,16},{16,8},{8,16},{8,8},{8,4},{4,8},{4,4}};
+static const int ORC_FIRST[8] = {0, 0, 1, 3, 5, 9, 17, 25};
+void orc_partition_geometry(int p, int *bt, int *ox, int *oy, int *w, int *h)
+{
+  int t = 7, k, per_row;
+  while (ORC_FIRST[t] > p) t--;
+  k = p - ORC_FIRST[t]; *w = ORC_BS[t][0]; *h = ORC_BS[t][1]; per_row = 16 / *w;
+  *bt = t; *ox = (k % per_row) * *w; *oy = (k / per_row) * *h;
+}
+
+/* get_search_range (mv_search.c:70-92): per-block search range in pel.
+ * mode = p_Inp->full_search (RestrictSearchRange): 2 = no restriction. */
+int orc_block_search_range(int R, int mode, int ref, int blocktype)
+{
+  int q = R << 2, scale = 1;
+  if (mode == 1) scale = (ref < 1 ? ref : 1) + 1;
+  else if (mode != 2) scale = ((ref < 1 ? ref : 1) + 1) * (blocktype < 2 ? blocktype : 2);
+  return (q / scale) >> 2;
+}
+
+/* Batch form == product b2me_search_frame() semantics == jmh_search_frame().
+ * metric_f is SAD; metric_h/q SAD(0) or SATD(2). */
+void orc_search_frame(void *h, int mb_first, int mb_count, const int16_t *pred, const int16_t *center,
+                      const int *lambda_factor, int restrict_mode, int metric_h, int metric_q, int do_subpel,
+                      int16_t *mv_int, int64_t *cost_int, int16_t *mv_sub, int64_t *cost_sub)
+{
+  OrcFrame *f = (OrcFrame *)h;
+  int mbw = f->W / 16, m, r, p;
+  int start_hp = (0 != metric_h) ? 0 : 1, start_qp = (metric_h != metric_q) ? 0 : 1;
+  for (m = mb_first; m < mb_first + mb_count; m++)
+    for (r = 0; r < f->nrefs; r++)
+      for (p = 0; p < 41; p++) {
+        int bt, ox, oy, w, hh; size_t i = ((size_t)m * f->nrefs + r) * 41 + p;
+        int16_t mv[2]; int64_t c; int sr;
+        orc_partition_geometry(p, &bt, &ox, &oy, &w, &hh);
+        sr = orc_block_search_range(f->R, restrict_mode, r, bt);
+        mv[0] = center[2*i]; mv[1] = center[2*i+1];
+        c = orc_full_search(f, r, (m % mbw) * 16 + ox, (m / mbw) * 16 + oy, w, hh, pred + 2*i, mv, sr,
+                            DISTBLK_MAX_ORC, lambda_factor[0]);
+        mv_int[2*i] = mv[0]; mv_int[2*i+1] = mv[1]; cost_int[i] = c;
+        if (do_subpel) {
+          if (!start_hp) c = DISTBLK_MAX_ORC;
+          c = orc_sub_pel(f, r, (m % mbw) * 16 + ox, (m / mbw) * 16 + oy, w, hh, pred + 2*i, mv, c,
+                          lambda_factor, start_hp, start_qp, metric_h, metric_q, 0);
+          mv_sub[2*i] = mv[0]; mv_sub[2*i+1] = mv[1]; cost_sub[i] = c;
+        }
+      }
+}
