@@ -1,0 +1,170 @@
+"""Host-side mirror of the C ABI in include/b2me.h (ctypes; no torch types cross the boundary).
+
+The product path is libb2me.so (hand-written sm_100a CUDA).  There is no CPU fallback: if the
+library is missing or a call fails this module raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2me.so")
+NPART = 41
+DISTBLK_MAX = (2**31 - 1) << 5
+PAD_X, PAD_Y = 32, 20
+_vp = C.c_void_p
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("lambda_factor", C.c_int32 * 3), ("restrict_mode", C.c_int32), ("metric_h", C.c_int32),
+                ("metric_q", C.c_int32), ("do_subpel", C.c_int32), ("reserved", C.c_int32),
+                ("min_mcost", C.c_int64)]
+
+
+def make_params(lambda_factor, restrict_mode=2, metric_h=2, metric_q=2, do_subpel=True, min_mcost=DISTBLK_MAX):
+    p = SearchParams()
+    lam = [int(x) for x in np.broadcast_to(np.asarray(lambda_factor), (3,))]
+    p.lambda_factor[0], p.lambda_factor[1], p.lambda_factor[2] = lam
+    p.restrict_mode, p.metric_h, p.metric_q = restrict_mode, metric_h, metric_q
+    p.do_subpel, p.reserved, p.min_mcost = int(bool(do_subpel)), 0, int(min_mcost)
+    return p
+
+
+_lib = None
+
+
+def lib():
+    """Load libb2me.so; raises if the CUDA extension has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2Error(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                          "(make -C h264_b200/csrc). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.b2me_last_error.restype = C.c_char_p
+        L.b2me_last_error.argtypes = [_vp]
+        L.b2me_launch_count.restype = C.c_int64
+        L.b2me_launch_count.argtypes = [_vp]
+        L.b2me_destroy.argtypes = [_vp]
+        L.b2me_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_vp)
+
+
+def _dp(t):
+    """device pointer of a torch CUDA tensor (or None)"""
+    return _vp(0) if t is None else _vp(t.data_ptr())
+
+
+def ubench(kind, iters=2000, device=0):
+    g = C.c_double()
+    r = lib().b2me_ubench(C.c_int(device), C.c_int(kind), C.c_int(iters), C.byref(g))
+    if r:
+        raise B2Error(f"b2me_ubench failed: {r}")
+    return g.value
+
+
+class Searcher:
+    """One b2me context: a coded picture size, nrefs reference pictures, SearchRange R."""
+
+    def __init__(self, W, H, nrefs, R, device=0):
+        self.L = lib()
+        self.W, self.H, self.nrefs, self.R, self.device = W, H, nrefs, R, device
+        self.nmb = (W // 16) * (H // 16)
+        h = _vp()
+        r = self.L.b2me_create(C.byref(h), C.c_int(device), C.c_int(W), C.c_int(H), C.c_int(nrefs), C.c_int(R))
+        self.h = h
+        if r:
+            msg = self.L.b2me_last_error(h if h else _vp(0))
+            raise B2Error(f"b2me_create failed ({r}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b2me_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, r, what):
+        if r:
+            msg = self.L.b2me_last_error(self.h)
+            raise B2Error(f"{what} failed ({r}): {msg.decode() if msg else ''}")
+
+    # ---- pictures -----------------------------------------------------------------------
+    def set_cur(self, luma):
+        luma = np.ascontiguousarray(luma, np.uint8)
+        assert luma.shape == (self.H, self.W)
+        self._chk(self.L.b2me_set_cur(self.h, _p(luma), C.c_int(self.W)), "b2me_set_cur")
+
+    def set_ref(self, r, luma):
+        luma = np.ascontiguousarray(luma, np.uint8)
+        assert luma.shape == (self.H, self.W)
+        self._chk(self.L.b2me_set_ref(self.h, C.c_int(r), _p(luma), C.c_int(self.W)), "b2me_set_ref")
+
+    def set_cur_dev(self, t, stream=0):
+        self._chk(self.L.b2me_set_cur_dev(self.h, _dp(t), C.c_int(t.stride(0)), _vp(stream)), "b2me_set_cur_dev")
+
+    def set_ref_dev(self, r, t, stream=0):
+        self._chk(self.L.b2me_set_ref_dev(self.h, C.c_int(r), _dp(t), C.c_int(t.stride(0)), _vp(stream)), "b2me_set_ref_dev")
+
+    def subplane(self, r, yy, xx):
+        out = np.zeros((self.H + 2 * PAD_Y, self.W + 2 * PAD_X), np.uint8)
+        self._chk(self.L.b2me_get_subplane(self.h, C.c_int(r), C.c_int(yy), C.c_int(xx), _p(out)), "b2me_get_subplane")
+        return out
+
+    # ---- search -------------------------------------------------------------------------
+    def search_frame(self, pred, center, params):
+        """Host numpy in/out through the C ABI (copies inside the call)."""
+        pred = np.ascontiguousarray(pred, np.int16)
+        center = np.ascontiguousarray(center, np.int16)
+        shape = (self.nmb, self.nrefs, NPART, 2)
+        assert pred.shape == shape and center.shape == shape
+        mv_int = np.zeros(shape, np.int16)
+        mv_sub = np.zeros(shape, np.int16)
+        cost_int = np.zeros(shape[:3], np.int64)
+        cost_sub = np.zeros(shape[:3], np.int64)
+        self._chk(self.L.b2me_search_frame(self.h, _p(pred), _p(center), C.byref(params), _p(mv_int), _p(cost_int),
+                                           _p(mv_sub), _p(cost_sub)), "b2me_search_frame")
+        return mv_int, cost_int, mv_sub, cost_sub
+
+    def search_frame_dev(self, pred, center, params, mv_int, cost_int, mv_sub, cost_sub, stream=0,
+                         mb_first=0, mb_count=None):
+        """torch CUDA tensors in/out (device pointers), asynchronous on `stream`."""
+        if mb_count is None:
+            mb_count = self.nmb - mb_first
+        self._chk(self.L.b2me_search_mbs_dev(self.h, C.c_int(mb_first), C.c_int(mb_count), _dp(pred), _dp(center),
+                                             C.byref(params), _dp(mv_int), _dp(cost_int), _dp(mv_sub), _dp(cost_sub),
+                                             _vp(stream)), "b2me_search_mbs_dev")
+
+    def block_search(self, pos_x, pos_y, blocktype, ref, pred_mv, center_mv, params, search_range):
+        pm = (C.c_int16 * 2)(int(pred_mv[0]), int(pred_mv[1]))
+        cm = (C.c_int16 * 2)(int(center_mv[0]), int(center_mv[1]))
+        mi, ms = (C.c_int16 * 2)(), (C.c_int16 * 2)()
+        ci, cs = C.c_int64(), C.c_int64()
+        self._chk(self.L.b2me_block_search(self.h, pos_x, pos_y, blocktype, ref, pm, cm, C.byref(params),
+                                           C.c_int(search_range), mi, C.byref(ci), ms, C.byref(cs)), "b2me_block_search")
+        return (mi[0], mi[1]), ci.value, (ms[0], ms[1]), cs.value
+
+    # ---- instrumentation ------------------------------------------------------------------
+    def launch_count(self):
+        return self.L.b2me_launch_count(self.h)
+
+    def kernel_timing(self, enable):
+        self._chk(self.L.b2me_kernel_timing(self.h, C.c_int(int(enable))), "b2me_kernel_timing")
+
+    def kernel_time_ms(self, which):
+        ms, n = C.c_double(), C.c_int64()
+        self._chk(self.L.b2me_kernel_time_ms(self.h, C.c_int(which), C.byref(ms), C.byref(n)), "b2me_kernel_time_ms")
+        return ms.value, n.value

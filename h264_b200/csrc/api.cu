@@ -1,0 +1,310 @@
+// api.cu -- the C ABI of libb2me.so (include/b2me.h): context, picture upload, search entry
+// points.  No CPU fallback exists: every entry point either runs the CUDA path or returns an
+// error code.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "b2_common.cuh"
+#include "b2_ctx.h"
+
+using namespace b2;
+
+static char g_err[512] = "no context";
+
+extern "C" int b2me_version(void) { return 100; }
+
+extern "C" const char *b2me_last_error(b2me_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+extern "C" int b2me_create(b2me_ctx **out, int device, int width, int height, int nrefs, int search_range)
+{
+  if (!out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || nrefs < 1 || nrefs > 16 ||
+      search_range < 1 || search_range > 64) {
+    snprintf(g_err, sizeof(g_err), "b2me_create: invalid argument");
+    return B2ME_EINVAL;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) {
+    snprintf(g_err, sizeof(g_err), "b2me_create: no CUDA device %d (%s)", device, cudaGetErrorString(e));
+    return B2ME_ECUDA;
+  }
+  b2me_ctx *c = new (std::nothrow) b2me_ctx();
+  if (!c) return B2ME_ENOMEM;
+  memset(c, 0, sizeof(*c));
+  c->device = device; c->W = width; c->H = height; c->nrefs = nrefs; c->R = search_range;
+  c->Wp = width + 2 * PADX; c->Hp = height + 2 * PADY;
+  c->mbw = width / 16; c->mbh = height / 16; c->nmb = c->mbw * c->mbh;
+  c->plane_size = (size_t)c->Wp * c->Hp;
+  *out = c;
+  B2_CUDA_CHECK(c, cudaSetDevice(device));
+  B2_CUDA_CHECK(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  const size_t n = (size_t)c->nmb * nrefs * NPART;
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_cur, (size_t)width * height));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_stage, (size_t)width * height));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_planes, c->plane_size * 16 * nrefs));
+  B2_CUDA_CHECK(c, cudaMemset(c->d_planes, 0, c->plane_size * 16 * nrefs));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_pred, n * 2 * sizeof(int16_t)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_center, n * 2 * sizeof(int16_t)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_mv_int, n * 2 * sizeof(int16_t)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_mv_sub, n * 2 * sizeof(int16_t)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_cost_int, n * sizeof(long long)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_cost_sub, n * sizeof(long long)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_io16, 4 * NPART * 2 * sizeof(int16_t)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_io64, 2 * NPART * sizeof(long long)));
+  B2_CUDA_CHECK(c, cudaMallocHost(&c->h_io16, 4 * NPART * 2 * sizeof(int16_t)));
+  B2_CUDA_CHECK(c, cudaMallocHost(&c->h_io64, 2 * NPART * sizeof(long long)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_errflag, sizeof(int)));
+  B2_CUDA_CHECK(c, cudaMemset(c->d_errflag, 0, sizeof(int)));
+  B2_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  B2_CUDA_CHECK(c, cudaEventCreate(&c->ev0));
+  B2_CUDA_CHECK(c, cudaEventCreate(&c->ev1));
+  return B2ME_OK;
+}
+
+extern "C" void b2me_destroy(b2me_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_cur); cudaFree(c->d_stage); cudaFree(c->d_planes);
+  cudaFree(c->d_pred); cudaFree(c->d_center); cudaFree(c->d_mv_int); cudaFree(c->d_mv_sub);
+  cudaFree(c->d_cost_int); cudaFree(c->d_cost_sub); cudaFree(c->d_io16); cudaFree(c->d_io64);
+  cudaFreeHost(c->h_io16); cudaFreeHost(c->h_io64); cudaFree(c->d_errflag);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+// ---- timing helper: device time of one kernel family on the launching stream --------------
+struct FamilyTimer {
+  b2me_ctx *c; int which; cudaStream_t s;
+  FamilyTimer(b2me_ctx *c_, int w, cudaStream_t s_) : c(c_), which(w), s(s_) { if (c->timing) cudaEventRecord(c->ev0, s); }
+  void stop() {
+    if (!c->timing) return;
+    cudaEventRecord(c->ev1, s); cudaEventSynchronize(c->ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->t_ms[which] += ms; c->t_n[which]++;
+  }
+};
+
+extern "C" int b2me_kernel_timing(b2me_ctx *c, int enable)
+{
+  if (!c) return B2ME_EINVAL;
+  c->timing = enable;
+  for (int i = 0; i < 4; i++) { c->t_ms[i] = 0; c->t_n[i] = 0; }
+  return B2ME_OK;
+}
+extern "C" int b2me_kernel_time_ms(b2me_ctx *c, int which, double *ms, int64_t *launches)
+{
+  if (!c || which < 0 || which > 3) return B2ME_EINVAL;
+  if (ms) *ms = c->t_ms[which];
+  if (launches) *launches = c->t_n[which];
+  return B2ME_OK;
+}
+extern "C" int64_t b2me_launch_count(b2me_ctx *c) { return c ? c->launches : 0; }
+
+// ---- pictures ------------------------------------------------------------------------------
+extern "C" int b2me_set_cur_dev(b2me_ctx *c, const uint8_t *luma_dev, int stride, void *stream)
+{
+  if (!c || !luma_dev || stride < c->W) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  B2_CUDA_CHECK(c, cudaMemcpy2DAsync(c->d_cur, c->W, luma_dev, stride, c->W, c->H, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return B2ME_OK;
+}
+extern "C" int b2me_set_cur(b2me_ctx *c, const uint8_t *luma, int stride)
+{
+  if (!c || !luma || stride < c->W) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  B2_CUDA_CHECK(c, cudaMemcpy2DAsync(c->d_cur, c->W, luma, stride, c->W, c->H, cudaMemcpyHostToDevice, c->stream));
+  B2_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return B2ME_OK;
+}
+static int build_planes(b2me_ctx *c, int ref_idx, const uint8_t *luma_dev, int stride, cudaStream_t s)
+{
+  FamilyTimer t(c, 1, s);
+  B2_CUDA_CHECK(c, launch_subpel_planes(luma_dev, stride, c->W, c->H, c->d_planes + (size_t)ref_idx * 16 * c->plane_size, s));
+  c->launches += 2;
+  t.stop();
+  return B2ME_OK;
+}
+extern "C" int b2me_set_ref_dev(b2me_ctx *c, int ref_idx, const uint8_t *luma_dev, int stride, void *stream)
+{
+  if (!c || !luma_dev || stride < c->W || ref_idx < 0 || ref_idx >= c->nrefs) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  return build_planes(c, ref_idx, luma_dev, stride, (cudaStream_t)stream);
+}
+extern "C" int b2me_set_ref(b2me_ctx *c, int ref_idx, const uint8_t *luma, int stride)
+{
+  if (!c || !luma || stride < c->W || ref_idx < 0 || ref_idx >= c->nrefs) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  B2_CUDA_CHECK(c, cudaMemcpy2DAsync(c->d_stage, c->W, luma, stride, c->W, c->H, cudaMemcpyHostToDevice, c->stream));
+  int r = build_planes(c, ref_idx, c->d_stage, c->W, c->stream);
+  if (r) return r;
+  B2_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return B2ME_OK;
+}
+extern "C" int b2me_get_subplane(b2me_ctx *c, int ref_idx, int yy, int xx, uint8_t *out)
+{
+  if (!c || !out || ref_idx < 0 || ref_idx >= c->nrefs || yy < 0 || yy > 3 || xx < 0 || xx > 3) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  B2_CUDA_CHECK(c, cudaMemcpy(out, c->d_planes + ((size_t)ref_idx * 16 + yy * 4 + xx) * c->plane_size, c->plane_size, cudaMemcpyDeviceToHost));
+  return B2ME_OK;
+}
+
+// ---- search --------------------------------------------------------------------------------
+static int check_params(b2me_ctx *c, const b2me_search_params *p)
+{
+  if (!p) return B2ME_EINVAL;
+  if (p->restrict_mode < 0 || p->restrict_mode > 2) return B2ME_EINVAL;
+  if (p->do_subpel && ((p->metric_h != 0 && p->metric_h != 2) || (p->metric_q != 0 && p->metric_q != 2))) {
+    snprintf(c->err, sizeof(c->err), "sub-pel metric SSE is not implemented on this path");
+    return B2ME_EUNSUPPORTED;
+  }
+  return B2ME_OK;
+}
+
+static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, int refs_per_mb, int abs_index,
+                      unsigned long long mask, int sr_override,
+                      const int16_t *pred, const int16_t *center, const b2me_search_params *p,
+                      int16_t *mv_int, long long *cost_int, int16_t *mv_sub, long long *cost_sub, cudaStream_t s)
+{
+  FsArgs f;
+  f.cur = c->d_cur; f.cur_pitch = c->W; f.planes = c->d_planes; f.plane_size = c->plane_size;
+  f.W = c->W; f.H = c->H; f.Wp = c->Wp; f.Hp = c->Hp; f.mbw = c->mbw; f.nrefs = c->nrefs;
+  f.R = c->R; f.restrict_mode = sr_override >= 0 ? -1 : p->restrict_mode; f.sr_override = sr_override;
+  f.lambda_f = p->lambda_factor[0]; f.min_mcost = p->min_mcost;
+  f.pred = pred; f.center = center; f.mv_int = mv_int; f.cost_int = cost_int;
+  f.mb_first = mb_first; f.ref_first = ref_first; f.refs_per_mb = refs_per_mb; f.nitems = mb_count * refs_per_mb;
+  f.abs_index = abs_index; f.part_mask = mask; f.errflag = c->d_errflag;
+  {
+    FamilyTimer t(c, 0, s);
+    B2_CUDA_CHECK(c, launch_sad_fs(f, c->sm_count, s, &c->fs_smem_bytes));
+    c->launches++;
+    t.stop();
+  }
+  if (p->do_subpel) {
+    SubArgs q;
+    q.cur = c->d_cur; q.cur_pitch = c->W; q.planes = c->d_planes; q.plane_size = c->plane_size;
+    q.W = c->W; q.H = c->H; q.Wp = c->Wp; q.Hp = c->Hp; q.mbw = c->mbw; q.nrefs = c->nrefs;
+    q.lambda_h = p->lambda_factor[1]; q.lambda_q = p->lambda_factor[2]; q.metric_h = p->metric_h; q.metric_q = p->metric_q;
+    // p_Vid->start_me_refinement_hp/_qp (mv_search.c:445-446), ChromaME off, F_PEL metric = SAD
+    q.start_hp = (0 != p->metric_h) ? 0 : 1; q.start_qp = (p->metric_h != p->metric_q) ? 0 : 1;
+    q.pred = pred; q.mv_int = mv_int; q.cost_int = cost_int; q.mv_sub = mv_sub; q.cost_sub = cost_sub;
+    q.mb_first = mb_first; q.ref_first = ref_first; q.refs_per_mb = refs_per_mb; q.nitems = f.nitems;
+    q.abs_index = abs_index; q.part_mask = mask;
+    FamilyTimer t(c, 2, s);
+    B2_CUDA_CHECK(c, launch_subpel_refine(q, s));
+    c->launches++;
+    t.stop();
+  }
+  return B2ME_OK;
+}
+
+extern "C" int b2me_search_mbs_dev(b2me_ctx *c, int mb_first, int mb_count, const int16_t *pred, const int16_t *center,
+                                   const b2me_search_params *p, int16_t *mv_int, int64_t *cost_int,
+                                   int16_t *mv_sub, int64_t *cost_sub, void *stream)
+{
+  if (!c || !pred || !center || !mv_int || !cost_int) return B2ME_EINVAL;
+  int r = check_params(c, p);
+  if (r) return r;
+  if (p->do_subpel && (!mv_sub || !cost_sub)) return B2ME_EINVAL;
+  if (mb_first < 0 || mb_count < 0 || mb_first + mb_count > c->nmb) return B2ME_EINVAL;
+  if (mb_count == 0) return B2ME_OK;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  return run_search(c, mb_first, mb_count, 0, c->nrefs, 1, (1ull << NPART) - 1, -1, pred, center, p, mv_int,
+                    (long long *)cost_int, mv_sub, (long long *)cost_sub, (cudaStream_t)stream);
+}
+
+extern "C" int b2me_search_frame_dev(b2me_ctx *c, const int16_t *pred, const int16_t *center, const b2me_search_params *p,
+                                     int16_t *mv_int, int64_t *cost_int, int16_t *mv_sub, int64_t *cost_sub, void *stream)
+{
+  if (!c) return B2ME_EINVAL;
+  return b2me_search_mbs_dev(c, 0, c->nmb, pred, center, p, mv_int, cost_int, mv_sub, cost_sub, stream);
+}
+
+static int check_errflag(b2me_ctx *c, cudaStream_t s)
+{
+  int flag = 0;
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  B2_CUDA_CHECK(c, cudaStreamSynchronize(s));
+  if (flag) {
+    cudaMemsetAsync(c->d_errflag, 0, sizeof(int), s);
+    snprintf(c->err, sizeof(c->err), "search centre is not integer-pel (quarter-pel centres are not a full-search input)");
+    return B2ME_EINVAL;
+  }
+  return B2ME_OK;
+}
+
+extern "C" int b2me_search_frame(b2me_ctx *c, const int16_t *pred, const int16_t *center, const b2me_search_params *p,
+                                 int16_t *mv_int, int64_t *cost_int, int16_t *mv_sub, int64_t *cost_sub)
+{
+  if (!c || !pred || !center || !mv_int || !cost_int) return B2ME_EINVAL;
+  int r = check_params(c, p);
+  if (r) return r;
+  if (p->do_subpel && (!mv_sub || !cost_sub)) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)c->nmb * c->nrefs * NPART;
+  cudaStream_t s = c->stream;
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_pred, pred, n * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_center, center, n * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  r = run_search(c, 0, c->nmb, 0, c->nrefs, 1, (1ull << NPART) - 1, -1, c->d_pred, c->d_center, p,
+                 c->d_mv_int, c->d_cost_int, c->d_mv_sub, c->d_cost_sub, s);
+  if (r) return r;
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(mv_int, c->d_mv_int, n * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(cost_int, c->d_cost_int, n * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  if (p->do_subpel) {
+    B2_CUDA_CHECK(c, cudaMemcpyAsync(mv_sub, c->d_mv_sub, n * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA_CHECK(c, cudaMemcpyAsync(cost_sub, c->d_cost_sub, n * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  }
+  return check_errflag(c, s);
+}
+
+extern "C" int b2me_block_search(b2me_ctx *c, int pos_x, int pos_y, int blocktype, int ref_idx,
+                                 const int16_t pred_mv[2], const int16_t center_mv[2], const b2me_search_params *p,
+                                 int search_range_pel, int16_t mv_int[2], int64_t *cost_int, int16_t mv_sub[2], int64_t *cost_sub)
+{
+  if (!c || !pred_mv || !center_mv || !mv_int || !cost_int) return B2ME_EINVAL;
+  int r = check_params(c, p);
+  if (r) return r;
+  if (p->do_subpel && (!mv_sub || !cost_sub)) return B2ME_EINVAL;
+  if (blocktype < 1 || blocktype > 7 || ref_idx < 0 || ref_idx >= c->nrefs || search_range_pel < 0 || search_range_pel > c->R ||
+      pos_x < 0 || pos_y < 0 || pos_x >= c->W || pos_y >= c->H) return B2ME_EINVAL;
+  // locate the partition of this blocktype at (pos_x & 15, pos_y & 15)
+  int part = -1;
+  for (int q = part_first(blocktype); q < NPART; q++) {
+    PartGeom g = part_geom(q);
+    if (g.bt != blocktype) break;
+    if (g.ox == (pos_x & 15) && g.oy == (pos_y & 15)) { part = q; break; }
+  }
+  if (part < 0) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  int16_t *h16 = c->h_io16; long long *h64 = c->h_io64;
+  h16[part * 2] = pred_mv[0]; h16[part * 2 + 1] = pred_mv[1];
+  h16[(NPART + part) * 2] = center_mv[0]; h16[(NPART + part) * 2 + 1] = center_mv[1];
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_io16, h16, 2 * NPART * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  const int mb = (pos_y >> 4) * c->mbw + (pos_x >> 4);
+  r = run_search(c, mb, 1, ref_idx, 1, 0, 1ull << part, search_range_pel, c->d_io16, c->d_io16 + NPART * 2, p,
+                 c->d_io16 + 2 * NPART * 2, c->d_io64, c->d_io16 + 3 * NPART * 2, c->d_io64 + NPART, s);
+  if (r) return r;
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(h16 + 2 * NPART * 2, c->d_io16 + 2 * NPART * 2, 2 * NPART * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(h64, c->d_io64, 2 * NPART * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  r = check_errflag(c, s);
+  if (r) return r;
+  mv_int[0] = h16[(2 * NPART + part) * 2]; mv_int[1] = h16[(2 * NPART + part) * 2 + 1];
+  *cost_int = h64[part];
+  if (p->do_subpel) {
+    mv_sub[0] = h16[(3 * NPART + part) * 2]; mv_sub[1] = h16[(3 * NPART + part) * 2 + 1];
+    *cost_sub = h64[NPART + part];
+  }
+  return B2ME_OK;
+}
+
+extern "C" int b2me_ubench(int device, int kind, int iters, double *gops)
+{
+  if (!gops || iters <= 0) return B2ME_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return B2ME_ECUDA;
+  cudaError_t e = ubench(kind, iters, gops);
+  if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "ubench: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
+  return B2ME_OK;
+}

@@ -1,0 +1,72 @@
+// b2_ctx.h -- internal context of libb2me (not part of the C ABI).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/b2me.h"
+
+struct b2me_ctx {
+  int device;
+  int W, H, Wp, Hp, mbw, mbh, nmb, nrefs, R;
+  size_t plane_size;            // Wp*Hp
+  uint8_t *d_cur;               // [H][W]
+  uint8_t *d_planes;            // [nrefs][16][Hp][Wp]  index [yy*4+xx]
+  uint8_t *d_stage;             // [H][W] staging for host uploads
+  // device mirrors for the host-pointer batch API
+  int16_t *d_pred, *d_center, *d_mv_int, *d_mv_sub;
+  long long *d_cost_int, *d_cost_sub;
+  // pinned host staging for the single-block drop-in path
+  int16_t *h_io16;              // [4][41][2]
+  long long *h_io64;            // [2][41]
+  int16_t *d_io16;
+  long long *d_io64;
+  int *d_errflag;
+  cudaStream_t stream;          // internal stream for host-pointer calls
+  cudaEvent_t ev0, ev1;
+  int timing;
+  double t_ms[4];
+  int64_t t_n[4];
+  int64_t launches;
+  int sm_count;
+  int fs_smem_bytes;
+  char err[512];
+};
+
+namespace b2 {
+
+struct FsArgs {
+  const uint8_t *cur; int cur_pitch;
+  const uint8_t *planes; size_t plane_size;   // integer plane of ref r = planes + r*16*plane_size
+  int W, H, Wp, Hp, mbw, nrefs;
+  int R;                 // half window (pel)
+  int restrict_mode;     // get_search_range mode; -1: use sr_override for every partition
+  int sr_override;
+  int lambda_f;
+  long long min_mcost;
+  const int16_t *pred, *center;
+  int16_t *mv_int; long long *cost_int;
+  int mb_first, ref_first, refs_per_mb;   // item -> (mb, ref)
+  int nitems;
+  int abs_index;         // 1: arrays indexed ((mb*nrefs+ref)*41+p), 0: (item*41+p)
+  unsigned long long part_mask;           // active partitions
+  int *errflag;
+};
+
+struct SubArgs {
+  const uint8_t *cur; int cur_pitch;
+  const uint8_t *planes; size_t plane_size;
+  int W, H, Wp, Hp, mbw, nrefs;
+  int lambda_h, lambda_q, metric_h, metric_q;
+  int start_hp, start_qp;
+  const int16_t *pred;
+  const int16_t *mv_int; const long long *cost_int;
+  int16_t *mv_sub; long long *cost_sub;
+  int mb_first, ref_first, refs_per_mb, nitems, abs_index;
+  unsigned long long part_mask;
+};
+
+cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, cudaStream_t s);
+cudaError_t launch_sad_fs(const FsArgs &a, int sm_count, cudaStream_t s, int *smem_bytes_out);
+cudaError_t launch_subpel_refine(const SubArgs &a, cudaStream_t s);
+cudaError_t ubench(int kind, int iters, double *gops);
+
+}  // namespace b2

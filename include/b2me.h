@@ -1,0 +1,131 @@
+/* b2me.h -- C ABI of libb2me.so: the B200-native (sm_100a) block-matching hot path of the
+ * joint fractal + H.264/AVC encoder in HuddsinYuan/--h.264-by-zhaodongyu.
+ *
+ * Plain C: raw pointers, sizes and POD structs only (no JM / version1 / torch types).
+ * Every entry point returns 0 on success or a negative B2ME_E* code; nothing aborts.
+ * Pointers are HOST pointers unless the function name ends in _dev (device pointers, and a
+ * cudaStream_t passed as void*; those calls are asynchronous on that stream).
+ *
+ * Reference interfaces replaced (aliases: JM/ = 4.对比程序/jm18.5/JM, V1/ =
+ * 2.论文程序/ZhangLing_Yu_version1/H264Fractal, both under the reference root):
+ *   b2me_search_frame / b2me_block_search
+ *        <- full_search_motion_estimation   JM/lencod/src/me_fullsearch.c:39-103
+ *           sub_pel_motion_estimation       JM/lencod/src/me_fullsearch.c:186-289
+ *           computeSAD / computeSATD        JM/lencod/src/me_distortion.c:349-426 / 745-825
+ *           (the per-call sequencing of BlockMotionSearch, JM/lencod/src/mv_search.c:960-976)
+ *   b2me_set_ref (sub-pel plane build)
+ *        <- getSubImagesLuma                JM/lencod/src/img_luma.c:611-680
+ *   b2me_tq4x4
+ *        <- forward4x4 / inverse4x4         JM/lcommon/src/transform.c:20-118
+ *           quant_4x4_normal                JM/lencod/src/quant4x4_normal.c:39-115
+ *           residual_transform_quant_luma_4x4  JM/lencod/src/block.c:660-724
+ *           dct_luma (version1)             V1/src/block.c:836-1045
+ *   b2fr_*  (fractal)
+ *        <- compute_domain_Sum/compute_range_Sum  V1/src/compute.c:277,686
+ *           compute_rdSum / compute_rms           V1/src/compute.c:192,6
+ *           full_search / bound_chk               V1/src/block_enc.c:1933,2894
+ */
+#ifndef B2ME_H
+#define B2ME_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2ME_OK            0
+#define B2ME_EINVAL       -1   /* bad argument (null pointer, size not multiple of 16, ...) */
+#define B2ME_ECUDA        -2   /* CUDA runtime error; see b2me_last_error() */
+#define B2ME_ENOMEM       -3
+#define B2ME_EUNSUPPORTED -4   /* valid in the reference but not implemented on this path */
+
+#define B2ME_NPART        41   /* 1+2+2+4+8+8+16 partitions of a macroblock (JM block_size[], macroblock.h:58) */
+#define B2ME_DISTBLK_MAX  (((int64_t)0x7fffffff) << 5)   /* JM defines.h:135 */
+
+/* Partition numbering used by every array below (p = 0..40), blocktype = JM blocktype 1..7:
+ *   p 0       16x16 (bt 1)
+ *   p 1..2    16x8  (bt 2)  top, bottom
+ *   p 3..4    8x16  (bt 3)  left, right
+ *   p 5..8    8x8   (bt 4)  raster
+ *   p 9..16   8x4   (bt 5)  raster (2 per row, 4 rows)
+ *   p 17..24  4x8   (bt 6)  raster (4 per row, 2 rows)
+ *   p 25..40  4x4   (bt 7)  raster                                            */
+
+typedef struct b2me_ctx b2me_ctx;
+
+typedef struct b2me_search_params {
+  int32_t lambda_factor[3];  /* F_PEL, H_PEL, Q_PEL lambda_mf (LAMBDA_FACTOR, JM defines.h:130) */
+  int32_t restrict_mode;     /* p_Inp->full_search (RestrictSearchRange): 0,1,2 (mv_search.c:70-92) */
+  int32_t metric_h;          /* MEDistortionHPel: 0 SAD, 2 SATD */
+  int32_t metric_q;          /* MEDistortionQPel: 0 SAD, 2 SATD */
+  int32_t do_subpel;         /* !DisableSubpelME */
+  int32_t reserved;
+  int64_t min_mcost;         /* initial bound handed to the integer search (B2ME_DISTBLK_MAX) */
+} b2me_search_params;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* width/height: coded luma size, multiples of 16.  search_range: SearchRange in pel (<=64). */
+int  b2me_create(b2me_ctx **out, int device, int width, int height, int nrefs, int search_range);
+void b2me_destroy(b2me_ctx *ctx);
+const char *b2me_last_error(b2me_ctx *ctx);          /* thread-unsafe, like the reference */
+int  b2me_version(void);
+
+/* ---- pictures ----------------------------------------------------------------------- */
+/* Current (original) luma, 8-bit.  JM stores imgpel=uint16 holding 8-bit samples; the shim
+ * narrows on upload (SURVEY Q-J3). */
+int b2me_set_cur(b2me_ctx *ctx, const uint8_t *luma, int stride);
+int b2me_set_cur_dev(b2me_ctx *ctx, const uint8_t *luma_dev, int stride, void *stream);
+/* Reference picture ref_idx of list 0: uploads the reconstructed luma and builds the 16
+ * quarter-pel planes on the device (getSubImagesLuma). */
+int b2me_set_ref(b2me_ctx *ctx, int ref_idx, const uint8_t *luma, int stride);
+int b2me_set_ref_dev(b2me_ctx *ctx, int ref_idx, const uint8_t *luma_dev, int stride, void *stream);
+/* Read back sub-pel plane [yy][xx] (padded (H+40) x (W+64), tightly packed) -- parity tests. */
+int b2me_get_subplane(b2me_ctx *ctx, int ref_idx, int yy, int xx, uint8_t *out);
+
+/* ---- motion search ------------------------------------------------------------------ */
+/* Whole-frame batch: for every MB (raster), ref and partition p run the reference's integer
+ * full search and, if params->do_subpel, its half/quarter-pel refinement.
+ *   pred, center : [nmb][nrefs][41][2] int16, quarter-pel MV predictor and search centre
+ *                  (centre = relative MV, multiple of 4; JM derives it at mv_search.c:931-932)
+ *   mv_int, mv_sub : same shape, best integer / final quarter-pel MV
+ *   cost_int, cost_sub : [nmb][nrefs][41] int64 motion costs (SAD or SATD <<5 + lambda*bits)
+ * mv_sub/cost_sub may be NULL when do_subpel == 0. */
+int b2me_search_frame(b2me_ctx *ctx, const int16_t *pred, const int16_t *center,
+                      const b2me_search_params *params,
+                      int16_t *mv_int, int64_t *cost_int, int16_t *mv_sub, int64_t *cost_sub);
+int b2me_search_frame_dev(b2me_ctx *ctx, const int16_t *pred_dev, const int16_t *center_dev,
+                          const b2me_search_params *params,
+                          int16_t *mv_int_dev, int64_t *cost_int_dev,
+                          int16_t *mv_sub_dev, int64_t *cost_sub_dev, void *stream);
+/* MB sub-range variant (MB-row bands / bounded samples): MBs [mb_first, mb_first+mb_count);
+ * arrays are still indexed by absolute MB number. */
+int b2me_search_mbs_dev(b2me_ctx *ctx, int mb_first, int mb_count,
+                        const int16_t *pred_dev, const int16_t *center_dev,
+                        const b2me_search_params *params,
+                        int16_t *mv_int_dev, int64_t *cost_int_dev,
+                        int16_t *mv_sub_dev, int64_t *cost_sub_dev, void *stream);
+
+/* Drop-in for ONE call of full_search_motion_estimation (+ sub_pel_motion_estimation): block
+ * at luma (pos_x,pos_y), JM blocktype 1..7, reference ref_idx.  search_range_pel is the
+ * block's own range (min(max_x,max_y)>>2 after get_search_range). */
+int b2me_block_search(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int ref_idx,
+                      const int16_t pred_mv[2], const int16_t center_mv[2],
+                      const b2me_search_params *params, int search_range_pel,
+                      int16_t mv_int[2], int64_t *cost_int, int16_t mv_sub[2], int64_t *cost_sub);
+
+/* ---- instrumentation ---------------------------------------------------------------- */
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t b2me_launch_count(b2me_ctx *ctx);
+/* Device time (ms, CUDA events on the launching stream) accumulated per kernel family since the
+ * last reset: which = 0 integer search, 1 sub-pel planes, 2 sub-pel refinement. Enables timing
+ * when enable != 0 (adds two event records per launch). */
+int b2me_kernel_timing(b2me_ctx *ctx, int enable);
+int b2me_kernel_time_ms(b2me_ctx *ctx, int which, double *ms, int64_t *launches);
+/* Micro-benchmark of an instruction mix on the whole chip; kind: 0 VABSDIFF4.ACC only,
+ * 1 +IMAD 1:1, 2 +IADD3 1:1, 3 +LOP3 1:1, 4 IADD3 only, 5 IMAD only, 6 VIMNMX.U16x2 only,
+ * 7 VABSDIFF4+LDS.  Returns giga warp-lane-ops per second of the FIRST op of the mix. */
+int b2me_ubench(int device, int kind, int iters, double *gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2ME_H */

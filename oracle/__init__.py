@@ -48,6 +48,8 @@ def orc_lib():
         L.orc_frame_planes.restype = _vp
         L.orc_full_search.restype = C.c_int64
         L.orc_sub_pel.restype = C.c_int64
+        L.orc_call_full_search.restype = C.c_int64
+        L.orc_call_sub_pel.restype = C.c_int64
         _orc = L
     return _orc
 
@@ -117,6 +119,23 @@ class OrcFrame:
         p = self.L.orc_frame_planes(self.h, C.c_int(r))
         buf = (C.c_uint8 * (16 * Hp * Wp)).from_address(p)
         return np.frombuffer(buf, np.uint8).reshape(4, 4, Hp, Wp)
+
+    def call_full_search(self, ref, pos_x, pos_y, blocktype, pred_mv, center_mv, search_range, min_mcost, lam):
+        pm = np.array(pred_mv, np.int16)
+        mv = np.array(center_mv, np.int16)
+        c = self.L.orc_call_full_search(self.h, C.c_int(ref), C.c_int(pos_x), C.c_int(pos_y), C.c_int(blocktype),
+                                        _ptr(pm), _ptr(mv), C.c_int(search_range), C.c_int64(int(min_mcost)),
+                                        C.c_int(int(lam)))
+        return (int(mv[0]), int(mv[1])), c
+
+    def call_sub_pel(self, ref, pos_x, pos_y, blocktype, pred_mv, mv_in, min_mcost, lam_h, lam_q,
+                     metric_h=2, metric_q=2):
+        pm = np.array(pred_mv, np.int16)
+        mv = np.array(mv_in, np.int16)
+        c = self.L.orc_call_sub_pel(self.h, C.c_int(ref), C.c_int(pos_x), C.c_int(pos_y), C.c_int(blocktype),
+                                    _ptr(pm), _ptr(mv), C.c_int64(int(min_mcost)), C.c_int(int(lam_h)),
+                                    C.c_int(int(lam_q)), C.c_int(metric_h), C.c_int(metric_q))
+        return (int(mv[0]), int(mv[1])), c
 
     def search_frame(self, pred, center, lambda_factor, restrict_mode=2, metric_h=2, metric_q=2,
                      do_subpel=True, mb_first=0, mb_count=None):

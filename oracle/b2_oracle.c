@@ -3,7 +3,7 @@
  * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference leg may load this; the product (libb2me.so) never does.
  *
- * Parity status: PINNED.  Every function here is checked (tests/test_oracle_vs_ref.py,
+ * Parity status: PINNED.  Every function here is checked (tests/test_oracle_jm.py,
  * run in the build container where /root/reference exists) against the unmodified
  * reference objects through oracle/_ref/libjmref.so / libv1ref.so, and against the golden
  * vectors under tests/golden/ that were generated from those objects and from a
@@ -352,4 +352,22 @@ void orc_search_frame(void *h, int mb_first, int mb_count, const int16_t *pred, 
           mv_sub[2*i] = mv[0]; mv_sub[2*i+1] = mv[1]; cost_sub[i] = c;
         }
       }
+}
+
+/* Call-level entry points (one call of full_search_motion_estimation / sub_pel_motion_estimation)
+ * used against the boundary-logged golden vectors. */
+int64_t orc_call_full_search(void *h, int ref, int pos_x, int pos_y, int blocktype, const int16_t *pred_mv,
+                             int16_t *mv_inout, int search_range, int64_t min_mcost, int lambda_factor)
+{
+  return orc_full_search((OrcFrame *)h, ref, pos_x, pos_y, ORC_BS[blocktype][0], ORC_BS[blocktype][1], pred_mv,
+                         mv_inout, search_range, min_mcost, lambda_factor);
+}
+int64_t orc_call_sub_pel(void *h, int ref, int pos_x, int pos_y, int blocktype, const int16_t *pred_mv,
+                         int16_t *mv_inout, int64_t min_mcost, int lambda_h, int lambda_q,
+                         int metric_h, int metric_q)
+{
+  int lam[3]; int start_hp = (0 != metric_h) ? 0 : 1, start_qp = (metric_h != metric_q) ? 0 : 1;
+  lam[0] = 0; lam[1] = lambda_h; lam[2] = lambda_q;
+  return orc_sub_pel((OrcFrame *)h, ref, pos_x, pos_y, ORC_BS[blocktype][0], ORC_BS[blocktype][1], pred_mv,
+                     mv_inout, min_mcost, lam, start_hp, start_qp, metric_h, metric_q, 0);
 }

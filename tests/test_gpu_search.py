@@ -1,0 +1,136 @@
+"""GPU parity tests (through the C ABI): CUDA motion search vs the oracle / golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from h264_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(W, H, R, NR, seed):
+    fr = synth.luma_sequence(W, H, NR + 1, seed=seed)
+    cur, refs = fr[NR], fr[list(range(NR - 1, -1, -1))]
+    s = api.Searcher(W, H, NR, R)
+    s.set_cur(cur)
+    for r in range(NR):
+        s.set_ref(r, refs[r])
+    return s, cur, refs
+
+
+def test_subpel_planes_bit_exact():
+    W, H = 176, 144
+    s, cur, refs = _setup(W, H, 16, 2, seed=5)
+    for r in range(2):
+        P = oracle.subpel_planes(refs[r])
+        for yy in range(4):
+            for xx in range(4):
+                assert (s.subplane(r, yy, xx) == P[yy, xx]).all(), (r, yy, xx)
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_search_matches_reference_golden(golden_dir, name):
+    """Golden outputs of the unmodified JM objects (oracle/gen_golden_jm.py)."""
+    g = np.load(os.path.join(golden_dir, "jm_harness_qcif.npz"))
+    W, H, R, NR = 176, 144, 16, 2
+    fr = synth.luma_sequence(W, H, 3, seed=7)
+    cur, refs = fr[2], fr[[1, 0]]
+    restrict, spread, rmax, l0, l1, l2 = [int(x) for x in g[f"{name}_cfg"]]
+    pred, cen = synth.predictors(W, H, NR, seed=11, spread=spread, rmax=rmax)
+    s = api.Searcher(W, H, NR, R)
+    s.set_cur(cur)
+    for r in range(NR):
+        s.set_ref(r, refs[r])
+    mi, ci, ms, cs = s.search_frame(pred, cen, api.make_params((l0, l1, l2), restrict_mode=restrict))
+    assert (mi == g[f"{name}_mv_int"]).all()
+    assert (ci == g[f"{name}_cost_int"]).all()
+    assert (ms == g[f"{name}_mv_sub"]).all()
+    assert (cs == g[f"{name}_cost_sub"]).all()
+
+
+@pytest.mark.parametrize("W,H,R,NR,spread,rmax,lam", [
+    (64, 48, 7, 1, 0, 3, (187, 187, 187)),        # shared centre per MB
+    (64, 48, 7, 2, 6, 40, (40, 30, 30)),          # far, per-partition predictors: clamped windows
+    (96, 64, 32, 1, 2, 8, (1200, 900, 900)),      # +-32, high lambda
+    (48, 48, 16, 1, 0, 0, (4, 4, 4)),             # tiny lambda: many ties / improvements
+])
+def test_search_matches_oracle(W, H, R, NR, spread, rmax, lam):
+    s, cur, refs = _setup(W, H, R, NR, seed=W + R)
+    of = oracle.OrcFrame(cur, refs, R)
+    pred, cen = synth.predictors(W, H, NR, seed=3, spread=spread, rmax=rmax)
+    got = s.search_frame(pred, cen, api.make_params(lam))
+    exp = of.search_frame(pred, cen, lam)
+    for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+        assert (a == b).all(), (n, int((a != b).sum()))
+
+
+def test_flat_and_noise_content():
+    """Flat frames (all-zero SAD, ties decided by spiral order) and pure noise."""
+    W, H, R = 48, 32, 7
+    rng = np.random.default_rng(0)
+    for cur, ref in ((np.full((H, W), 77, np.uint8), np.full((H, W), 77, np.uint8)),
+                     (rng.integers(0, 256, (H, W), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8))):
+        s = api.Searcher(W, H, 1, R)
+        s.set_cur(cur); s.set_ref(0, ref)
+        of = oracle.OrcFrame(cur, ref[None], R)
+        pred, cen = synth.predictors(W, H, 1, seed=9, spread=5, rmax=5)
+        got = s.search_frame(pred, cen, api.make_params((90, 70, 70)))
+        exp = of.search_frame(pred, cen, (90, 70, 70))
+        for a, b in zip(got, exp):
+            assert (a == b).all()
+
+
+def test_sad_subpel_metric_and_no_subpel():
+    W, H, R = 64, 48, 7
+    s, cur, refs = _setup(W, H, R, 1, seed=21)
+    of = oracle.OrcFrame(cur, refs, R)
+    pred, cen = synth.predictors(W, H, 1, seed=4, spread=3, rmax=4)
+    got = s.search_frame(pred, cen, api.make_params((100, 100, 100), metric_h=0, metric_q=0))
+    exp = of.search_frame(pred, cen, (100, 100, 100), metric_h=0, metric_q=0)
+    for a, b in zip(got, exp):
+        assert (a == b).all()
+    got = s.search_frame(pred, cen, api.make_params((100, 100, 100), metric_h=0, metric_q=2))
+    exp = of.search_frame(pred, cen, (100, 100, 100), metric_h=0, metric_q=2)
+    for a, b in zip(got, exp):
+        assert (a == b).all()
+    got = s.search_frame(pred, cen, api.make_params((100, 100, 100), do_subpel=False))
+    exp = of.search_frame(pred, cen, (100, 100, 100), do_subpel=False)
+    assert (got[0] == exp[0]).all() and (got[1] == exp[1]).all()
+
+
+def test_block_search_dropin_matches_boundary_log(golden_dir):
+    """b2me_block_search == one full_search + sub_pel call of the stock lencod run."""
+    g = np.load(os.path.join(golden_dir, "jm_wrap_foreman.npz"))
+    ints, subs = g["int_calls"], g["sub_calls"]
+    poc = int(g["pocs"][0])
+    s = api.Searcher(176, 144, 1, 16)
+    s.set_cur(g["cur"][0]); s.set_ref(0, g["ref"][0])
+    rows_i = ints[ints[:, 0] == poc]
+    rows_s = subs[subs[:, 0] == poc]
+    idx = np.linspace(0, len(rows_i) - 1, 160).astype(int)
+    for k in idx:
+        _, px, py, bt, ref, pdx, pdy, cx, cy, sr, lam, min_in, ox, oy, cost = [int(x) for x in rows_i[k]]
+        v = [int(x) for x in rows_s[k]]
+        assert v[1:5] == [px, py, bt, ref]
+        lh, lq, sox, soy, scost = v[9], v[10], v[12], v[13], v[14]
+        p = api.make_params((lam, lh, lq), min_mcost=min_in)
+        mi, ci, ms, cs = s.block_search(px, py, bt, ref, (pdx, pdy), (cx, cy), p, sr)
+        assert (mi, ci) == ((ox, oy), cost), rows_i[k]
+        assert (ms, cs) == ((sox, soy), scost), rows_s[k]
+
+
+def test_error_codes():
+    s = api.Searcher(64, 48, 1, 7)
+    with pytest.raises(api.B2Error):
+        api.Searcher(60, 48, 1, 7)                      # not a multiple of 16
+    with pytest.raises(api.B2Error):
+        s.block_search(0, 0, 9, 0, (0, 0), (0, 0), api.make_params(100), 7)   # bad blocktype
+    with pytest.raises(api.B2Error):
+        s.search_frame(*synth.predictors(64, 48, 1), api.make_params(100, metric_h=1))  # SSE unsupported
+    pred, cen = synth.predictors(64, 48, 1)
+    cen = cen.copy(); cen[0, 0, 0, 0] = 2               # quarter-pel centre
+    s.set_cur(np.zeros((48, 64), np.uint8)); s.set_ref(0, np.zeros((48, 64), np.uint8))
+    with pytest.raises(api.B2Error):
+        s.search_frame(pred, cen, api.make_params(100))

@@ -1,0 +1,87 @@
+"""CPU tests: the restated oracle (oracle/b2_oracle.c) against (a) golden vectors captured from the
+unmodified reference and (b) the reference objects themselves when oracle/_ref exists."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from h264_b200 import synth
+
+
+def test_spiral_and_mvbits_closed_forms():
+    sp = oracle.spiral(16)
+    assert sp.shape == (33 * 33, 2) and tuple(sp[0]) == (0, 0)
+    assert [tuple(x) for x in sp[1:9]] == [(0, -1), (0, 1), (-1, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (1, 1)]
+    assert len({tuple(x) for x in sp}) == 33 * 33
+    # ring l occupies indices (2l-1)^2 .. (2l+1)^2-1
+    ring = np.maximum(np.abs(sp[:, 0]), np.abs(sp[:, 1]))
+    for l in range(1, 17):
+        assert (ring[(2 * l - 1) ** 2:(2 * l + 1) ** 2] == l).all()
+    assert [oracle.mvbits(d) for d in (0, 1, -1, 2, 3, 4, 7, 8, 255, 256, -511)] == [1, 3, 3, 5, 5, 7, 7, 9, 17, 19, 19]
+
+
+def test_oracle_reproduces_boundary_logged_lencod_run(golden_dir):
+    """Every full_search / sub_pel call of a stock lencod run on the bundled foreman clip."""
+    g = np.load(os.path.join(golden_dir, "jm_wrap_foreman.npz"))
+    pocs = list(g["pocs"])
+    ints, subs = g["int_calls"], g["sub_calls"]
+    assert len(ints) == 8118 and len(subs) == 8118       # 99 MB x 41 partitions x 2 P frames
+    for fi, poc in enumerate(pocs):
+        of = oracle.OrcFrame(g["cur"][fi], g["ref"][fi][None], 16)
+        rows = ints[ints[:, 0] == poc]
+        step = 1 if os.environ.get("B2_FULL") else 7
+        for v in rows[::step]:
+            _, px, py, bt, ref, pdx, pdy, cx, cy, sr, lam, min_in, ox, oy, cost = [int(x) for x in v]
+            mv, c = of.call_full_search(ref, px, py, bt, (pdx, pdy), (cx, cy), sr, min_in, lam)
+            assert (mv, c) == ((ox, oy), cost), v
+        rows = subs[subs[:, 0] == poc]
+        for v in rows[::step]:
+            _, px, py, bt, ref, pdx, pdy, ix, iy, lh, lq, min_in, ox, oy, cost = [int(x) for x in v]
+            mv, c = of.call_sub_pel(ref, px, py, bt, (pdx, pdy), (ix, iy), min_in, lh, lq)
+            assert (mv, c) == ((ox, oy), cost), v
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_oracle_reproduces_harness_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "jm_harness_qcif.npz"))
+    W, H, R, NR = 176, 144, 16, 2
+    fr = synth.luma_sequence(W, H, 3, seed=7)
+    cur, refs = fr[2], fr[[1, 0]]
+    restrict, spread, rmax, l0, l1, l2 = [int(x) for x in g[f"{name}_cfg"]]
+    pred, cen = synth.predictors(W, H, NR, seed=11, spread=spread, rmax=rmax)
+    of = oracle.OrcFrame(cur, refs, R)
+    nmb = 24 if not os.environ.get("B2_FULL") else 99
+    mi, ci, ms, cs = of.search_frame(pred, cen, (l0, l1, l2), restrict_mode=restrict, mb_count=nmb)
+    assert (mi[:nmb] == g[f"{name}_mv_int"][:nmb]).all()
+    assert (ci[:nmb] == g[f"{name}_cost_int"][:nmb]).all()
+    assert (ms[:nmb] == g[f"{name}_mv_sub"][:nmb]).all()
+    assert (cs[:nmb] == g[f"{name}_cost_sub"][:nmb]).all()
+
+
+@pytest.mark.skipif(not oracle.have_jmref(), reason="oracle/_ref/libjmref.so only exists where /root/reference was built")
+def test_oracle_vs_reference_objects_live():
+    """Sub-pel planes, Hadamards, tables and a whole-frame search against the reference itself."""
+    W, H, R, NR = 64, 48, 7, 1
+    fr = synth.luma_sequence(W, H, 2, seed=3)
+    jm = oracle.JMRef(W, H, R, NR)
+    jm.set_ref(0, fr[0]); jm.set_cur(fr[1])
+    of = oracle.OrcFrame(fr[1], fr[:1], R)
+    assert (jm.spiral(15 * 15) // 4 == oracle.spiral(R)).all()
+    md = jm.max_mvd()
+    assert all(jm.mvbits(d) == oracle.mvbits(d) for d in range(-md, md + 1))
+    P = of.planes(0)
+    for yy in range(4):
+        for xx in range(4):
+            assert (jm.subplane(0, yy, xx) == P[yy, xx]).all(), (yy, xx)
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        d = rng.integers(-255, 256, 16).astype(np.int16)
+        assert jm.hadamard4x4(d) == oracle.hadamard4x4(d)
+        d = rng.integers(-255, 256, 64).astype(np.int16)
+        assert jm.hadamard8x8(d) == oracle.hadamard8x8(d)
+    pred, cen = synth.predictors(W, H, NR, seed=2, spread=5, rmax=30)   # far predictors: clamped windows
+    a = jm.search_frame(pred, cen, np.array([120, 100, 100], np.int32))
+    b = of.search_frame(pred, cen, (120, 100, 100))
+    for x, y in zip(a, b):
+        assert (x == y).all()
