@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the block-matching hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE config "1080p 4:2:0, JM full-search +-32 integer + quarter-pel
+SATD refinement, 4 reference frames".  One step = the motion search of one P frame:
+  * build the 16 quarter-pel planes of the newest reference (getSubImagesLuma),
+  * integer full search +-32 (SAD) for all 8160 MBs x 4 refs x 41 partitions,
+  * half/quarter-pel SATD refinement of every partition.
+metric = Mpel-search-points/s = MBs x refs x (2R+1)^2 x 256 / time (the
+SAD-tree-algorithmic unit); MB/s is reported beside it.
+
+  value : inputs already resident in HBM (device pointers through the C ABI's *_dev calls)
+  e2e   : the same step through the host-pointer C ABI (b2me_set_cur / b2me_set_ref /
+          b2me_search_frame) with pinned HOST buffers, H2D + D2H inside the timed region.
+
+Multi-GPU (torchrun, one rank per GPU): independent closed-GOP segments, i.e. every rank runs the
+same per-frame step on its own frames -- no data-path collective (weak scaling).
+
+--impl reference: times the reference's own CPU implementation (the unmodified JM objects in
+oracle/_ref/libjmref.so, else the restated oracle) on a bounded MB sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+W, H, R, NREFS = 1920, 1088, 32, 4
+LAMBDA = (187, 187, 187)        # LAMBDA_FACTOR(lambda_me) at QP 28 (JM lambda.c:30, defines.h:130)
+UNIT = "Mpel-search-points/s"
+
+
+def workload(seed=1):
+    from h264_b200 import synth
+    fr = synth.luma_sequence(W, H, NREFS + 2, seed=seed)
+    nmb = (W // 16) * (H // 16)
+    # predictor = the clip's true pan motion per reference distance (what JM's median predictor
+    # converges to on a panning clip), shared by the 41 partitions of an MB
+    base = np.zeros((nmb, NREFS, 1, 2), np.int64)
+    for r in range(NREFS):
+        base[:, r, 0, 0] = 4 * 2 * (r + 1)
+        base[:, r, 0, 1] = 4 * 1 * (r + 1)
+    pred, cen = synth.predictors(W, H, NREFS, seed=seed, spread=0, base=base)
+    return fr, pred, cen
+
+
+def pel_sp(nmb):
+    return nmb * NREFS * (2 * R + 1) ** 2 * 256
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu):
+        self.rows, self.stop = [], False
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def finish(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def _cpu_worker(job):
+    """One process of the CPU reference arm: its own copy of the reference state, its own MB range."""
+    first, cnt, trial = job
+    import oracle
+    fr, pred, cen = workload()
+    cur, refs = fr[NREFS], fr[[NREFS - 1 - r for r in range(NREFS)]]
+    if oracle.have_jmref():
+        eng = oracle.JMRef(W, H, R, NREFS)
+        for r in range(NREFS):
+            eng.set_ref(r, refs[r])
+        eng.set_cur(cur)
+        lam = np.array(LAMBDA, np.int32)
+        run = lambda a, b: eng.search_frame(pred, cen, lam, mb_first=a, mb_count=b)
+    else:
+        eng = oracle.OrcFrame(cur, refs, R)
+        run = lambda a, b: eng.search_frame(pred, cen, LAMBDA, mb_first=a, mb_count=b)
+    t0 = time.time(); run(first, trial); t_trial = time.time() - t0
+    t0 = time.time(); run(first, cnt); dt = time.time() - t0
+    return t_trial, dt
+
+
+def cpu_reference(seconds_budget=20.0, procs=None):
+    """The reference's CPU implementation (unmodified JM objects, oracle/_ref/libjmref.so; else the
+    restated oracle) on a bounded MB sample of the same workload.  The reference is single-threaded;
+    the only parallelism it admits is independent processes, so `procs` processes each search their
+    own MB range and the aggregate is reported (cores = procs)."""
+    import multiprocessing as mp
+    import oracle
+    kind = "reference" if oracle.have_jmref() else "port"
+    nmb = (W // 16) * (H // 16)
+    procs = procs or max(1, min(os.cpu_count() or 1, 32))
+    ctx = mp.get_context("spawn")
+    # calibrate on one process, then give every process an equal MB range sized to the budget
+    t_trial, _ = _cpu_worker((nmb // 2, 2, 8))
+    per_mb = t_trial / 8
+    cnt = int(max(2, min(nmb // 2, seconds_budget / per_mb)))       # ranges may overlap across processes
+    jobs = [((nmb // 2 + i * cnt) % (nmb - cnt), cnt, 1) for i in range(procs)]
+    t0 = time.time()
+    if procs > 1:
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    else:
+        res = [_cpu_worker(jobs[0])]
+    wall = max(r[1] for r in res)            # slowest process = wall time of the parallel search
+    v = procs * cnt * NREFS * (2 * R + 1) ** 2 * 256 / wall / 1e6
+    return {"value": v, "unit": UNIT, "cores": procs, "kind": kind,
+            "sample": f"{procs} processes x {cnt} MBs of {nmb} x {NREFS} refs x 41 partitions, integer +-{R} SAD + sub-pel SATD; "
+                      f"slowest process {wall:.1f} s (launch-to-finish {time.time() - t0:.1f} s incl. per-process plane build)",
+            "mb_per_s": procs * cnt / wall, "one_core_value": cnt * NREFS * (2 * R + 1) ** 2 * 256 / (sum(r[1] for r in res) / len(res)) / 1e6}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    per_step = min(30.0, 90.0 / (steps + args.warmup))
+    res = None
+    t0 = time.time()
+    for i in range(args.warmup + steps):
+        if i == args.warmup:
+            t0 = time.time()
+        res = cpu_reference(per_step)
+    ms = (time.time() - t0) * 1e3 / steps
+    line = {"metric": UNIT, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"1080p {W}x{H} luma, JM full search +-{R} integer (SAD) + half/quarter-pel SATD, {NREFS} refs, 41 partitions/MB",
+                       "note": "reference CPU path: unmodified JM objects, one process per host core (the reference is single-threaded), bounded MB sample per step"},
+            "cpu_baseline": res, "gpu_launches": 0,
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from h264_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(3, args.warmup)
+
+    fr, pred_np, cen_np = workload(seed=1 + rank)
+    nmb = (W // 16) * (H // 16)
+    s = api.Searcher(W, H, NREFS, R, device=local)
+    params = api.make_params(LAMBDA)
+    n = nmb * NREFS * 41
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- resident inputs -------------------------------------------------------------------
+    d_frames = torch.from_numpy(fr).to(dev)                     # [NREFS+2, H, W] u8
+    d_pred = torch.from_numpy(pred_np).to(dev)
+    d_cen = torch.from_numpy(cen_np).to(dev)
+    d_mvi = torch.zeros((nmb, NREFS, 41, 2), dtype=torch.int16, device=dev)
+    d_mvs = torch.zeros_like(d_mvi)
+    d_ci = torch.zeros((nmb, NREFS, 41), dtype=torch.int64, device=dev)
+    d_cs = torch.zeros_like(d_ci)
+    for r in range(NREFS):
+        s.set_ref_dev(r, d_frames[NREFS - 1 - r], stream)
+    # L2 flush buffer (larger than the 126 MB L2), written between timed iterations
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_resident(i):
+        s.set_cur_dev(d_frames[NREFS], stream)
+        # newest reference: rebuild its 16 quarter-pel planes (slot content unchanged so that the
+        # predictors stay consistent with the clip's motion)
+        s.set_ref_dev(i % NREFS, d_frames[NREFS - 1 - (i % NREFS)], stream)
+        s.search_frame_dev(d_pred, d_cen, params, d_mvi, d_ci, d_mvs, d_cs, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step_resident(i)
+    barrier()
+    l0 = s.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    clocks = ClockSampler(local) if rank == 0 else None
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)                                     # L2 flush (untimed)
+        ev[i][0].record()
+        step_resident(i)
+        ev[i][1].record()
+    barrier()
+    launches = s.launch_count() - l0
+    ms_dev = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+    clk = clocks.finish() if clocks else None
+    value = world * pel_sp(nmb) / (ms_step * 1e-3) / 1e6
+
+    # ---- dominant kernel (integer search): live CUDA-event time per launch ------------------
+    s.kernel_timing(True)
+    for i in range(max(3, min(args.steps, 10))):
+        flush.fill_(i)
+        step_resident(i)
+    torch.cuda.synchronize()
+    k_ms, k_n = s.kernel_time_ms(0)
+    p_ms, p_n = s.kernel_time_ms(1)
+    q_ms, q_n = s.kernel_time_ms(2)
+    s.kernel_timing(False)
+    k_ms_launch = k_ms / max(k_n, 1)
+
+    # ---- e2e: host buffers through the host-pointer C ABI -----------------------------------
+    h_cur = [torch.from_numpy(fr[NREFS + j]).pin_memory() for j in range(2)]
+    h_ref = [torch.from_numpy(fr[j]).pin_memory() for j in range(NREFS + 2)]
+    h_pred = torch.from_numpy(pred_np).pin_memory(); h_cen = torch.from_numpy(cen_np).pin_memory()
+    h_mvi = torch.zeros((nmb, NREFS, 41, 2), dtype=torch.int16).pin_memory(); h_mvs = torch.zeros_like(h_mvi).pin_memory()
+    h_ci = torch.zeros((nmb, NREFS, 41), dtype=torch.int64).pin_memory(); h_cs = torch.zeros_like(h_ci).pin_memory()
+    import ctypes as C
+    L = s.L
+
+    def step_e2e(i):
+        r = L.b2me_set_cur(s.h, C.c_void_p(h_cur[0].data_ptr()), C.c_int(W))
+        r |= L.b2me_set_ref(s.h, C.c_int(i % NREFS), C.c_void_p(h_ref[NREFS - 1 - (i % NREFS)].data_ptr()), C.c_int(W))
+        r |= L.b2me_search_frame(s.h, C.c_void_p(h_pred.data_ptr()), C.c_void_p(h_cen.data_ptr()), C.byref(params),
+                                 C.c_void_p(h_mvi.data_ptr()), C.c_void_p(h_ci.data_ptr()),
+                                 C.c_void_p(h_mvs.data_ptr()), C.c_void_p(h_cs.data_ptr()))
+        if r:
+            raise RuntimeError(f"C ABI call failed: {L.b2me_last_error(s.h)}")
+
+    for i in range(warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)                                              # synchronous calls: results are on the host on return
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * pel_sp(nmb) / float(t.item()) / 1e6
+    h2d = 2 * W * H + 2 * n * 2 * 2
+    d2h = 2 * n * 2 * 2 + 2 * n * 8
+    checksum = int(h_mvs.to(torch.int64).sum().item())           # the result really is on the host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------
+    peaks, peak_src = measured_peaks()
+    sad_peak_glane = api.ubench(0, 4000, device=local)           # measured VABSDIFF4.U8.ACC issue rate (G lane-ops/s)
+    sad_peak_tpel = sad_peak_glane * 4 / 1e3                      # 4 pixel pairs per lane-op
+    achieved_tpel = pel_sp(nmb) / (k_ms_launch * 1e-3) / 1e12
+    alg_bytes = W * H + NREFS * (W + 64) * (H + 40) + 2 * n * 4 + n * (4 + 8)   # cur + int planes + pred/centre in, mv+cost out
+    roofline = {"bound": "int-alu", "kernel": "k_sad_fs (integer full search, VABSDIFF4.U8.ACC)",
+                "achieved": achieved_tpel, "peak": sad_peak_tpel, "unit": "Tpel-sp/s", "frac": achieved_tpel / sad_peak_tpel,
+                "peak_source": "measured live: b2me_ubench(kind=0) VABSDIFF4.U8.ACC lane-ops/s x 4 pixels (MEASURED_PEAKS.json has no integer figure)",
+                "kernel_ms": k_ms_launch,
+                "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (k_ms_launch * 1e-3) / 1e9,
+                        "peak_gbs": peaks["hbm_gbs"], "peak_source": peak_src,
+                        "frac": alg_bytes / (k_ms_launch * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                "traffic": None,
+                "share_of_step": {"k_sad_fs": k_ms / max(k_n, 1), "subpel_planes": p_ms / max(p_n, 1), "subpel_refine": q_ms / max(q_n, 1)}}
+    cpu = None if args.no_cpu else cpu_reference(15.0)
+    line = {"metric": UNIT, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"1080p {W}x{H} luma, JM full search +-{R} integer (SAD) + half/quarter-pel SATD refinement, {NREFS} refs, "
+                                   f"41 partitions/MB, 16 quarter-pel planes of the newest reference rebuilt per step",
+                       "predictors": "per-(MB,ref) predictor = clip pan motion, shared by the 41 partitions (search centre = rounded predictor)",
+                       "lambda_factor": LAMBDA[0], "sharding": "independent closed-GOP segments (one frame stream per GPU), no collective",
+                       "l2": "192 MB L2 flush written between timed iterations"},
+            "mb_per_s": world * nmb / (ms_step * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t.item()) * 1e3, "result_checksum": checksum},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
