@@ -161,6 +161,11 @@ class Searcher:
     def launch_count(self):
         return self.L.b2me_launch_count(self.h)
 
+    def search_stats(self, reset=True):
+        out = (C.c_int64 * 3)()
+        self._chk(self.L.b2me_search_stats(self.h, out, C.c_int(int(reset))), "b2me_search_stats")
+        return {"exact_evals": out[0], "window_passes": out[1], "items": out[2]}
+
     def kernel_timing(self, enable):
         self._chk(self.L.b2me_kernel_timing(self.h, C.c_int(int(enable))), "b2me_kernel_timing")
 

@@ -55,6 +55,8 @@ extern "C" int b2me_create(b2me_ctx **out, int device, int width, int height, in
   B2_CUDA_CHECK(c, cudaMallocHost(&c->h_io64, 2 * NPART * sizeof(long long)));
   B2_CUDA_CHECK(c, cudaMalloc(&c->d_errflag, sizeof(int)));
   B2_CUDA_CHECK(c, cudaMemset(c->d_errflag, 0, sizeof(int)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long)));
+  B2_CUDA_CHECK(c, cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
   B2_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   B2_CUDA_CHECK(c, cudaEventCreate(&c->ev0));
   B2_CUDA_CHECK(c, cudaEventCreate(&c->ev1));
@@ -68,7 +70,7 @@ extern "C" void b2me_destroy(b2me_ctx *c)
   cudaFree(c->d_cur); cudaFree(c->d_stage); cudaFree(c->d_planes);
   cudaFree(c->d_pred); cudaFree(c->d_center); cudaFree(c->d_mv_int); cudaFree(c->d_mv_sub);
   cudaFree(c->d_cost_int); cudaFree(c->d_cost_sub); cudaFree(c->d_io16); cudaFree(c->d_io64);
-  cudaFreeHost(c->h_io16); cudaFreeHost(c->h_io64); cudaFree(c->d_errflag);
+  cudaFreeHost(c->h_io16); cudaFreeHost(c->h_io64); cudaFree(c->d_errflag); cudaFree(c->d_stats);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -102,6 +104,17 @@ extern "C" int b2me_kernel_time_ms(b2me_ctx *c, int which, double *ms, int64_t *
   return B2ME_OK;
 }
 extern "C" int64_t b2me_launch_count(b2me_ctx *c) { return c ? c->launches : 0; }
+extern "C" int b2me_search_stats(b2me_ctx *c, int64_t out[3], int reset)
+{
+  if (!c || !out) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  B2_CUDA_CHECK(c, cudaDeviceSynchronize());
+  unsigned long long h[4];
+  B2_CUDA_CHECK(c, cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+  out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = (int64_t)h[2];
+  if (reset) B2_CUDA_CHECK(c, cudaMemset(c->d_stats, 0, sizeof(h)));
+  return B2ME_OK;
+}
 
 // ---- pictures ------------------------------------------------------------------------------
 extern "C" int b2me_set_cur_dev(b2me_ctx *c, const uint8_t *luma_dev, int stride, void *stream)
@@ -175,7 +188,7 @@ static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
   f.lambda_f = p->lambda_factor[0]; f.min_mcost = p->min_mcost;
   f.pred = pred; f.center = center; f.mv_int = mv_int; f.cost_int = cost_int;
   f.mb_first = mb_first; f.ref_first = ref_first; f.refs_per_mb = refs_per_mb; f.nitems = mb_count * refs_per_mb;
-  f.abs_index = abs_index; f.part_mask = mask; f.errflag = c->d_errflag;
+  f.abs_index = abs_index; f.part_mask = mask; f.errflag = c->d_errflag; f.stats = c->d_stats;
   {
     FamilyTimer t(c, 0, s);
     B2_CUDA_CHECK(c, launch_sad_fs(f, c->sm_count, s, &c->fs_smem_bytes));

@@ -20,6 +20,7 @@ struct b2me_ctx {
   int16_t *d_io16;
   long long *d_io64;
   int *d_errflag;
+  unsigned long long *d_stats;
   cudaStream_t stream;          // internal stream for host-pointer calls
   cudaEvent_t ev0, ev1;
   int timing;
@@ -49,6 +50,7 @@ struct FsArgs {
   int abs_index;         // 1: arrays indexed ((mb*nrefs+ref)*41+p), 0: (item*41+p)
   unsigned long long part_mask;           // active partitions
   int *errflag;
+  unsigned long long *stats;   // optional: [0] exact re-evaluations, [1] window passes, [2] items
 };
 
 struct SubArgs {

@@ -40,6 +40,9 @@ namespace b2 {
 
 constexpr int FS_K = 5;          // candidates per task (lock-step rows)
 constexpr int FS_NT = 128;       // threads per CTA
+constexpr int FS_QCH = 32;       // queue chunk: candidates re-evaluated per cooperative pass
+constexpr int FS_PRE = 1;        // radius of the exact pre-pass around the centres (initial bounds)
+constexpr int FS_SMAX = 8;       // partitions whose centres lie within an 8-pel box share one window pass
 
 struct FsSmemLayout {
   int wr, wpitch, copy_stride, win_bytes, total;
@@ -48,14 +51,14 @@ struct FsSmemLayout {
 __host__ __device__ inline FsSmemLayout fs_layout(int R)
 {
   FsSmemLayout L;
-  L.wr = 2 * R + 16 + FS_K - 1;                       // rows (extra rows for the partial last group)
-  L.wpitch = ((2 * R + 16 + 3) + 31) & ~31;           // bytes per row
+  L.wr = 2 * R + 16 + FS_K - 1 + FS_SMAX;             // rows (extra rows for the partial last group)
+  L.wpitch = ((2 * R + 16 + 3 + FS_SMAX) + 31) & ~31; // bytes per row
   L.copy_stride = ((L.wr * L.wpitch + 127) & ~127) + 32;
   L.win_bytes = 4 * L.copy_stride;
   L.off_cur = L.win_bytes;
   L.off_bx = L.off_cur + 256;
-  L.off_by = L.off_bx + ((2 * R + 1 + FS_K + 15) & ~15);
-  L.off_misc = L.off_by + ((2 * R + 1 + FS_K + 15) & ~15);
+  L.off_by = L.off_bx + ((2 * R + 1 + FS_SMAX + FS_K + 15) & ~15);
+  L.off_misc = L.off_by + ((2 * R + 1 + FS_SMAX + FS_K + 15) & ~15);
   L.total = L.off_misc;
   return L;
 }
@@ -68,9 +71,16 @@ struct FsShared {                 // static shared part
   short ppx[NPART], ppy[NPART];   // predictor (quarter-pel)
   short psr[NPART];               // per-partition search range (pel)
   signed char pgrp[NPART];        // centre group of the partition (-1 inactive)
-  short gcx[NPART], gcy[NPART];   // centre of group g (pel)
+  signed char pex[NPART], pey[NPART];   // centre of the partition relative to its group's box origin (pel)
+  short gx0[NPART], gy0[NPART], gx1[NPART], gy1[NPART];   // centre bounding box of group g (pel)
+  unsigned char dupx[NPART], dupy[NPART];   // predictor component already present at a lower partition of the group
+  int red[2][4];                  // per-warp centre bounding box (min x, max x, min y, max y)
   int ngroups;
   int err;
+  int nhits;
+  int qn[2];                      // survivors queued for exact re-evaluation (double-buffered by round parity)
+  unsigned short queue[FS_NT * FS_K];   // dx | dy << 8 (window coordinates)
+  unsigned short s4[FS_QCH][16];  // 4x4 SADs of the candidates of the current queue chunk
 };
 
 // index of partition p in the packed-threshold array (u16 view of Cw) or -1-s for scalar s
@@ -95,55 +105,60 @@ __device__ __forceinline__ void set_threshold(FsShared &S, int p, unsigned long 
   }
 }
 
-// Exact evaluation of candidate (dx,dy) (window coordinates, 0..2R) for every partition of
-// group g: recompute the sixteen 4x4 SADs, form each partition sum, exact mv cost, and
-// atomically lower best[p].  Slow path: runs for survivors of the packed filter only.
-__device__ __noinline__ void fs_exact_eval(FsShared &S, const uint8_t *smem, const FsSmemLayout L, int R, int g,
-                                           int dx, int dy, int lambda_f, unsigned long long mask)
+// Cooperative exact re-evaluation of the queued window candidates (survivors of the packed
+// filter, and the pre-pass neighbourhood of the centres) for every partition of group g:
+// phase A computes the sixteen 4x4 SADs of each candidate (16 threads per candidate), phase B
+// forms each partition's sum, its exact mv cost in the partition's own spiral and lowers
+// best[p] with a 64-bit atomicMin (41 threads per candidate).  Called by the whole CTA.
+__device__ __forceinline__ void fs_process_queue(FsShared &S, const uint8_t *smem, const FsSmemLayout L, int R, int g,
+                                                 int lambda_f, int par)
 {
-  const uint8_t *wb = smem + (dx & 3) * L.copy_stride + (dx >> 2) * 4 + dy * L.wpitch;
+  const int tid = threadIdx.x;
+  const int n = S.qn[par];
   const uint32_t *cur = reinterpret_cast<const uint32_t *>(smem + L.off_cur);
-  uint32_t s[16];
+  for (int c0 = 0; c0 < n; c0 += FS_QCH) {
+    const int m = min(FS_QCH, n - c0);
+    for (int idx = tid; idx < m * 16; idx += FS_NT) {
+      const int c = idx >> 4, k = idx & 15, bx = k & 3, by = k >> 2;
+      const unsigned q = S.queue[c0 + c];
+      const int col = (int)(q & 255u) + 4 * bx, row = (int)(q >> 8) + 4 * by;
+      const uint8_t *wb = smem + (col & 3) * L.copy_stride + (col >> 2) * 4 + row * L.wpitch;
+      uint32_t acc = 0;
 #pragma unroll
-  for (int b = 0; b < 4; b++) {
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const uint32_t *rw = reinterpret_cast<const uint32_t *>(wb + (b * 4 + i) * L.wpitch);
-      const uint32_t *cw = cur + (b * 4 + i) * 4;
-      a0 = sad4(cw[0], rw[0], a0); a1 = sad4(cw[1], rw[1], a1);
-      a2 = sad4(cw[2], rw[2], a2); a3 = sad4(cw[3], rw[3], a3);
+      for (int i = 0; i < 4; i++)
+        acc = sad4(cur[(by * 4 + i) * 4 + bx], *reinterpret_cast<const uint32_t *>(wb + i * L.wpitch), acc);
+      S.s4[c][k] = (unsigned short)acc;
     }
-    s[b * 4 + 0] = a0; s[b * 4 + 1] = a1; s[b * 4 + 2] = a2; s[b * 4 + 3] = a3;
-  }
-  const int ox = dx - R, oy = dy - R;                       // displacement from the group centre (pel)
-  const int ring = max(abs(ox), abs(oy));
-  const int pos = spiral_index(ox, oy);
-#pragma unroll
-  for (int p = 0; p < NPART; p++) {
-    if (!((mask >> p) & 1ull) || S.pgrp[p] != g) continue;
-    const PartGeom gm = part_geom(p);
-    uint32_t sum = 0;
-#pragma unroll
-    for (int by = 0; by < 4; by++)
-#pragma unroll
-      for (int bx = 0; bx < 4; bx++)
-        if (bx * 4 >= gm.ox && bx * 4 < gm.ox + gm.w && by * 4 >= gm.oy && by * 4 < gm.oy + gm.h) sum += s[by * 4 + bx];
-    if (ring > S.psr[p]) continue;
-    const int mvx = S.pcx[p] + 4 * ox, mvy = S.pcy[p] + 4 * oy;
-    const long long cost = ((long long)sum << 5) + (long long)lambda_f * (mvbits(mvx - S.ppx[p]) + mvbits(mvy - S.ppy[p]));
-    const unsigned long long key = ((unsigned long long)cost << 20) | (unsigned)pos;
-    if (key < *reinterpret_cast<volatile unsigned long long *>(&S.best[p])) {
-      unsigned long long old = atomicMin(&S.best[p], key);
-      set_threshold(S, p, old < key ? old : key);
+    __syncthreads();
+    for (int idx = tid; idx < m * NPART; idx += FS_NT) {
+      const int c = idx / NPART, p = idx - c * NPART;
+      if (S.pgrp[p] != g) continue;
+      const unsigned q = S.queue[c0 + c];
+      const int dx = (int)(q & 255u), dy = (int)(q >> 8);
+      const int ox = dx - R - S.pex[p], oy = dy - R - S.pey[p];   // displacement from the partition's own centre
+      if (max(abs(ox), abs(oy)) > S.psr[p]) continue;
+      const PartGeom gm = part_geom(p);
+      uint32_t sum = 0;
+      for (int by = gm.oy >> 2; by < ((gm.oy + gm.h) >> 2); by++)
+        for (int bx = gm.ox >> 2; bx < ((gm.ox + gm.w) >> 2); bx++) sum += S.s4[c][by * 4 + bx];
+      const int mvx = S.pcx[p] + 4 * ox, mvy = S.pcy[p] + 4 * oy;
+      const long long cost = ((long long)sum << 5) + (long long)lambda_f * (mvbits(mvx - S.ppx[p]) + mvbits(mvy - S.ppy[p]));
+      const unsigned long long key = ((unsigned long long)cost << 20) | (unsigned)spiral_index(ox, oy);
+      if (key < *reinterpret_cast<volatile unsigned long long *>(&S.best[p])) {
+        const unsigned long long old = atomicMin(&S.best[p], key);
+        set_threshold(S, p, old < key ? old : key);
+      }
     }
+    __syncthreads();
   }
+  if (tid == 0) { S.nhits += n; S.qn[par] = 0; }
+  __syncthreads();
 }
 
 // One task in "fine" mode: K candidates (dx, dy0..dy0+K-1), all 41 partitions filtered.
 template <int K>
 __device__ __forceinline__ void fs_task(FsShared &S, const uint8_t *smem, const FsSmemLayout L, int R, int g,
-                                        int dx, int dy0, int lambda_f, unsigned long long mask)
+                                        int dx, int dy0, int ncy, int lambda_f, int par)
 {
   const uint8_t *wb = smem + (dx & 3) * L.copy_stride + (dx >> 2) * 4 + dy0 * L.wpitch;
   const uint4 *cur = reinterpret_cast<const uint4 *>(smem + L.off_cur);
@@ -205,7 +220,7 @@ __device__ __forceinline__ void fs_task(FsShared &S, const uint8_t *smem, const 
             const volatile int *Bs = S.Bs;
             const int sf = (Bs[0] - top - m) & (Bs[1] - bot - m) & (Bs[2] - left - m) & (Bs[3] - right - m) & (Bs[4] - all - m);
             const bool allfail = ((fail[j] & 0x80008000u) == 0x80008000u) && (sf < 0);
-            if (!allfail && dy0 + j <= 2 * R) fs_exact_eval(S, smem, L, R, g, dx, dy0 + j, lambda_f, mask);
+            if (!allfail && dy0 + j < ncy) S.queue[atomicAdd(&S.qn[par], 1)] = (unsigned short)(dx | ((dy0 + j) << 8));
           }
         } else { keepA01[j] = A01; keepA23[j] = A23; keepH[j] = Hh; }
       }
@@ -218,9 +233,10 @@ __global__ void __launch_bounds__(FS_NT) k_sad_fs(const FsArgs a)
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ FsShared S;
   const FsSmemLayout L = fs_layout(a.R);
-  const int tid = threadIdx.x;
-  const int R = a.R, NC = 2 * R + 1;
-  if (tid == 0) S.err = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = a.R;
+  const int wpw = L.wpitch >> 2;                      // words per window row
+  if (tid == 0) { S.err = 0; S.nhits = 0; S.qn[0] = S.qn[1] = 0; }
 
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int mb = a.mb_first + item / a.refs_per_mb, ref = a.ref_first + item % a.refs_per_mb;
@@ -242,63 +258,126 @@ __global__ void __launch_bounds__(FS_NT) k_sad_fs(const FsArgs a)
     if (tid < 64) reinterpret_cast<uint32_t *>(smem + L.off_cur)[tid] =
         *reinterpret_cast<const uint32_t *>(a.cur + (size_t)(mby * 16 + (tid >> 2)) * a.cur_pitch + mbx * 16 + (tid & 3) * 4);
     __syncthreads();
-    if (tid == 0) {                                           // group partitions by centre
-      int ng = 0;
-      for (int p = 0; p < NPART; p++) {
-        if (S.pgrp[p] < 0) continue;
-        int g = -1;
-        for (int q = 0; q < ng; q++) if (S.gcx[q] == (S.pcx[p] >> 2) && S.gcy[q] == (S.pcy[p] >> 2)) { g = q; break; }
-        if (g < 0) { g = ng++; S.gcx[g] = S.pcx[p] >> 2; S.gcy[g] = S.pcy[p] >> 2; }
-        S.pgrp[p] = (signed char)g;
+    // ---- cluster partitions whose centres fit in one FS_SMAX box (usually all of them) ----
+    if (tid < 64) {
+      const bool act = tid < NPART && S.pgrp[tid] >= 0;
+      const int cx = act ? (S.pcx[tid] >> 2) : 0, cy = act ? (S.pcy[tid] >> 2) : 0;
+      const int x0 = __reduce_min_sync(0xffffffffu, act ? cx : 0x7fff), x1 = __reduce_max_sync(0xffffffffu, act ? cx : -0x7fff);
+      const int y0 = __reduce_min_sync(0xffffffffu, act ? cy : 0x7fff), y1 = __reduce_max_sync(0xffffffffu, act ? cy : -0x7fff);
+      if (lane == 0) { S.red[warp][0] = x0; S.red[warp][1] = x1; S.red[warp][2] = y0; S.red[warp][3] = y1; }
+    }
+    __syncthreads();
+    {
+      const int bx0 = min(S.red[0][0], S.red[1][0]), bx1 = max(S.red[0][1], S.red[1][1]);
+      const int by0 = min(S.red[0][2], S.red[1][2]), by1 = max(S.red[0][3], S.red[1][3]);
+      if (bx1 - bx0 <= FS_SMAX && by1 - by0 <= FS_SMAX) {
+        if (tid == 0) { S.gx0[0] = bx0; S.gx1[0] = bx1; S.gy0[0] = by0; S.gy1[0] = by1; S.ngroups = bx1 >= bx0 ? 1 : 0; }
+      } else if (tid == 0) {        // general case: greedy clustering (serial, rare)
+        int ng = 0;
+        for (int p = 0; p < NPART; p++) {
+          if (S.pgrp[p] < 0) continue;
+          const int cx = S.pcx[p] >> 2, cy = S.pcy[p] >> 2;
+          int g = -1;
+          for (int q = 0; q < ng; q++) {
+            const int nx0 = min((int)S.gx0[q], cx), nx1 = max((int)S.gx1[q], cx), ny0 = min((int)S.gy0[q], cy), ny1 = max((int)S.gy1[q], cy);
+            if (nx1 - nx0 <= FS_SMAX && ny1 - ny0 <= FS_SMAX) { g = q; S.gx0[q] = nx0; S.gx1[q] = nx1; S.gy0[q] = ny0; S.gy1[q] = ny1; break; }
+          }
+          if (g < 0) { g = ng++; S.gx0[g] = S.gx1[g] = cx; S.gy0[g] = S.gy1[g] = cy; }
+          S.pgrp[p] = (signed char)g;
+        }
+        S.ngroups = ng;
       }
-      S.ngroups = ng;
     }
     __syncthreads();
     const int ngroups = S.ngroups;
     const uint8_t *plane = a.planes + (size_t)ref * 16 * a.plane_size;     // integer plane [0][0]
 
     for (int g = 0; g < ngroups; g++) {
-      __syncthreads();
-      // ---- stage the window: rows y0.., cols x0.. in padded-plane coordinates, clamped ----
-      const int x0 = mbx * 16 + S.gcx[g] - R + PADX, y0 = mby * 16 + S.gcy[g] - R + PADY;
-      const int wcols = 2 * R + 16 + 3;
-      for (int i = tid; i < L.wr * L.wpitch; i += FS_NT) {
-        const int r = i / L.wpitch, c = i - r * L.wpitch;
-        uint8_t v = 0;
-        if (c < wcols) v = plane[(size_t)iclamp(y0 + r, 0, a.Hp - 1) * a.Wp + iclamp(x0 + c, 0, a.Wp - 1)];
-        smem[i] = v;
+      if (g) __syncthreads();
+      const int spanx = S.gx1[g] - S.gx0[g], spany = S.gy1[g] - S.gy0[g];
+      const int ncx = 2 * R + 1 + spanx, ncy = 2 * R + 1 + spany;
+      // ---- stage the window (4 byte-shifted copies), padded-plane coordinates ----
+      const int x0 = mbx * 16 + S.gx0[g] - R + PADX, y0 = mby * 16 + S.gy0[g] - R + PADY;
+      const int nrows = 2 * R + 16 + FS_K - 1 + spany, ncols = 2 * R + 16 + 3 + spanx;
+      uint32_t *c0 = reinterpret_cast<uint32_t *>(smem), *c1 = reinterpret_cast<uint32_t *>(smem + L.copy_stride),
+               *c2 = reinterpret_cast<uint32_t *>(smem + 2 * L.copy_stride), *c3 = reinterpret_cast<uint32_t *>(smem + 3 * L.copy_stride);
+      if (x0 >= 0 && y0 >= 0 && x0 + ncols <= a.Wp && y0 + nrows <= a.Hp) {
+        const int al = x0 & 3;
+#pragma unroll 4
+        for (int r = warp; r < nrows; r += FS_NT / 32) {
+          const uint32_t *grow = reinterpret_cast<const uint32_t *>(plane + (size_t)(y0 + r) * a.Wp + (x0 - al));
+          for (int j = lane; j < wpw; j += 32) {
+            const uint32_t g0 = grow[j], g1 = grow[j + 1], g2 = grow[j + 2];
+            // bytes al.. of (g0,g1,g2): copy c starts at byte al + c
+            const uint32_t lo = al ? __funnelshift_r(g0, g1, 8 * al) : g0;      // window word j
+            const uint32_t hi = al ? __funnelshift_r(g1, g2, 8 * al) : g1;      // window word j+1
+            c0[r * wpw + j] = lo;
+            c1[r * wpw + j] = __funnelshift_r(lo, hi, 8);
+            c2[r * wpw + j] = __funnelshift_r(lo, hi, 16);
+            c3[r * wpw + j] = __funnelshift_r(lo, hi, 24);
+          }
+        }
+      } else {                      // window leaves the padded plane: per-pixel coordinate clamp
+        for (int r = warp; r < nrows; r += FS_NT / 32) {
+          const uint8_t *grow = plane + (size_t)iclamp(y0 + r, 0, a.Hp - 1) * a.Wp;
+          for (int j = lane; j < wpw; j += 32) {
+            uint32_t b[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) b[k] = grow[iclamp(x0 + 4 * j + k, 0, a.Wp - 1)];
+            c0[r * wpw + j] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+            c1[r * wpw + j] = b[1] | (b[2] << 8) | (b[3] << 16) | (b[4] << 24);
+            c2[r * wpw + j] = b[2] | (b[3] << 8) | (b[4] << 16) | (b[5] << 24);
+            c3[r * wpw + j] = b[3] | (b[4] << 8) | (b[5] << 16) | (b[6] << 24);
+          }
+        }
       }
-      // thresholds: groups other than g never pass
+      // thresholds: partitions of other groups never pass
       if (tid < 18) S.Cw[tid] = 0x80008000u;
       if (tid < 5) S.Bs[tid] = -1;
-      // lower bound of mv bits over the partitions of the group, per window column / row
-      for (int i = tid; i < 2 * (NC + FS_K); i += FS_NT) {
-        const int isy = i >= NC + FS_K, d = isy ? i - (NC + FS_K) : i;
+      if (tid < NPART && S.pgrp[tid] == g) { S.pex[tid] = (signed char)((S.pcx[tid] >> 2) - S.gx0[g]); S.pey[tid] = (signed char)((S.pcy[tid] >> 2) - S.gy0[g]); }
+      if (tid >= 64 && tid < 64 + NPART && S.pgrp[tid - 64] == g) {     // predictor component seen at a lower partition?
+        const int p = tid - 64;
+        bool fx = false, fy = false;
+        for (int q = 0; q < p; q++)
+          if (S.pgrp[q] == g) { fx |= (S.ppx[q] == S.ppx[p]); fy |= (S.ppy[q] == S.ppy[p]); }
+        S.dupx[p] = fx; S.dupy[p] = fy;
+      }
+      __syncthreads();
+      // lower bound of the mv bits over the predictors of the group, per window column / row:
+      // every partition of the group sees the same absolute displacement 4*(g0 + d - R)
+      for (int i = tid; i < ncx + ncy + FS_K; i += FS_NT) {
+        const bool isy = i >= ncx;
+        const int d = isy ? i - ncx : i;
+        const int mv = 4 * ((isy ? S.gy0[g] : S.gx0[g]) + d - R);
+        const unsigned char *dup = isy ? S.dupy : S.dupx;
+        const short *pp = isy ? S.ppy : S.ppx;
         int mn = 255;
-        for (int p = 0; p < NPART; p++) {
-          if (S.pgrp[p] != g) continue;
-          const int v = isy ? mvbits(S.pcy[p] + 4 * (d - R) - S.ppy[p]) : mvbits(S.pcx[p] + 4 * (d - R) - S.ppx[p]);
-          mn = min(mn, v);
-        }
+        for (int q = 0; q < NPART; q++)
+          if (S.pgrp[q] == g && !dup[q]) mn = min(mn, mvbits(mv - pp[q]));
         (isy ? smem + L.off_by : smem + L.off_bx)[d] = (uint8_t)mn;
       }
-      __syncthreads();
-      // shifted copies 1..3 from copy 0
-      for (int i = tid; i < 3 * L.wr * (L.wpitch / 4); i += FS_NT) {
-        const int c = 1 + i / (L.wr * (L.wpitch / 4)), w = i % (L.wr * (L.wpitch / 4));
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(smem) + w;
-        const uint32_t lo = src[0], hi = ((w + 1) % (L.wpitch / 4)) ? src[1] : 0u;
-        reinterpret_cast<uint32_t *>(smem + c * L.copy_stride)[w] = __funnelshift_r(lo, hi, 8 * c);
+      // ---- initial bounds: exact pre-pass over the neighbourhood of the group's centres ----
+      {
+        const int xlo = max(0, R - FS_PRE), ylo = max(0, R - FS_PRE);
+        const int pw = min(ncx - 1, R + spanx + FS_PRE) - xlo + 1, ph = min(ncy - 1, R + spany + FS_PRE) - ylo + 1;
+        for (int i = tid; i < pw * ph; i += FS_NT) {
+          const int dx = xlo + i % pw, dy = ylo + i / pw;
+          S.queue[i] = (unsigned short)(dx | (dy << 8));
+        }
+        if (tid == 0) S.qn[0] = pw * ph;
       }
       __syncthreads();
-      // ---- initial thresholds: exact cost of the centre candidate (spiral pos 0) ----
-      if (tid == 0) fs_exact_eval(S, smem, L, R, g, R, R, a.lambda_f, a.part_mask);
-      __syncthreads();
-      // ---- main pass ----
-      const int ngrp = (NC + FS_K - 1) / FS_K, ntask = NC * ngrp;
-      for (int t = tid; t < ntask; t += FS_NT) {
-        const int gy = t / NC, dx = t - gy * NC;
-        fs_task<FS_K>(S, smem, L, R, g, dx, gy * FS_K, a.lambda_f, a.part_mask);
+      fs_process_queue(S, smem, L, R, g, a.lambda_f, 0);
+      // ---- main pass: rounds of FS_NT tasks, survivors re-evaluated after each round ----
+      const int ngrp = (ncy + FS_K - 1) / FS_K, ntask = ncx * ngrp;
+      for (int t0 = 0, par = 0; t0 < ntask; t0 += FS_NT, par ^= 1) {
+        const int t = t0 + tid;
+        if (t < ntask) {
+          const int gy = t / ncx, dx = t - gy * ncx;
+          fs_task<FS_K>(S, smem, L, R, g, dx, gy * FS_K, ncy, a.lambda_f, par);
+        }
+        __syncthreads();
+        if (S.qn[par]) fs_process_queue(S, smem, L, R, g, a.lambda_f, par);
       }
     }
     __syncthreads();
@@ -313,6 +392,7 @@ __global__ void __launch_bounds__(FS_NT) k_sad_fs(const FsArgs a)
       a.cost_int[base + p] = (long long)(key >> 20);
     }
     if (tid == 0 && S.err) { *a.errflag = 1; S.err = 0; }
+    if (tid == 0 && a.stats) { atomicAdd(&a.stats[0], (unsigned long long)S.nhits); atomicAdd(&a.stats[1], (unsigned long long)ngroups); atomicAdd(&a.stats[2], 1ull); S.nhits = 0; }
   }
 }
 

@@ -115,6 +115,9 @@ int b2me_block_search(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int re
 /* ---- instrumentation ---------------------------------------------------------------- */
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t b2me_launch_count(b2me_ctx *ctx);
+/* Integer-search counters accumulated since the last reset: out[0] = candidates that survived the
+ * packed filter and were re-evaluated exactly, out[1] = window passes, out[2] = (MB,ref) items. */
+int b2me_search_stats(b2me_ctx *ctx, int64_t out[3], int reset);
 /* Device time (ms, CUDA events on the launching stream) accumulated per kernel family since the
  * last reset: which = 0 integer search, 1 sub-pel planes, 2 sub-pel refinement. Enables timing
  * when enable != 0 (adds two event records per launch). */

@@ -6,7 +6,7 @@ from h264_b200 import api, synth
 
 out = {}
 names = ["vabsdiff4", "vabsdiff4+imad", "vabsdiff4+iadd3", "vabsdiff4+lop3", "iadd3", "imad", "vimnmx16x2", "vabsdiff4+lds"]
-for k, n in enumerate(names):
+for k, n in (enumerate(names) if os.environ.get("UBENCH") else []):
     out[n] = api.ubench(k, 4000)
     print(f"ubench {n}: {out[n]:.1f} G lane-ops/s", flush=True)
 
@@ -23,12 +23,13 @@ for r in range(NR):
 for spread in (0, 3):
     pred, cen = synth.predictors(W, H, NR, seed=1, spread=spread, base=base)
     p = api.make_params((187, 187, 187))
-    s.kernel_timing(True)
+    s.kernel_timing(True); s.search_stats()
     for it in range(3):
         t = time.time(); res = s.search_frame(pred, cen, p); dt = time.time() - t
     ms0, n0 = s.kernel_time_ms(0); ms2, n2 = s.kernel_time_ms(2)
     pel = s.nmb * NR * (2 * R + 1) ** 2 * 256
     print(f"spread={spread}: int search {ms0/n0:.3f} ms/launch -> {pel/(ms0/n0*1e-3)/1e12:.2f} Tpel-sp/s; subpel {ms2/n2:.3f} ms; host call {dt*1e3:.1f} ms", flush=True)
+    print('  stats', s.search_stats(), flush=True)
     mv = res[0]
     print("  mv_int mode:", np.unique(mv.reshape(-1, 2), axis=0, return_counts=True)[0][:3], flush=True)
     s.kernel_timing(False)
