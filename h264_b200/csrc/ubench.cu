@@ -11,19 +11,26 @@ namespace b2 {
 template <int KIND>
 __global__ void __launch_bounds__(256) k_ubench(uint32_t *out, int iters, uint32_t seed)
 {
-  uint32_t a[8], x[8];
+  uint32_t a[8], x[8], y[8];
   const uint32_t b = seed * 0x01010101u + threadIdx.x;
   __shared__ uint32_t sm[256];
   sm[threadIdx.x] = b;
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 8; i++) { a[i] = threadIdx.x + i; x[i] = b ^ (i * 0x9e3779b9u); }
+  for (int i = 0; i < 8; i++) { a[i] = threadIdx.x + i; x[i] = b ^ (i * 0x9e3779b9u); y[i] = x[i] + 7; }
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        if (KIND == 0 || KIND == 1 || KIND == 2 || KIND == 3 || KIND == 7) a[i] = sad4(x[i], b, a[i]);
+        if (KIND == 0 || KIND == 1 || KIND == 2 || KIND == 3 || KIND == 7 || KIND >= 8) a[i] = sad4(x[i], b, a[i]);
+        if (KIND == 8) asm volatile("shf.r.clamp.b32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(8));          // SHF (funnel shift)
+        if (KIND == 9) asm volatile("prmt.b32 %0, %0, %1, 0x4321;" : "+r"(y[i]) : "r"(b));                      // PRMT
+        if (KIND == 10) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(b), "r"(seed));        // LOP3, independent chain
+        if (KIND == 11) asm volatile("min.u16x2 %0, %0, %1;" : "+r"(y[i]) : "r"(b + i));                        // VIMNMX.U16x2
+        if (KIND == 12) y[i] = sm[(threadIdx.x + i * 32 + it) & 255];                                            // LDS.32, independent
+        if (KIND == 13) asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(b));                               // IADD, independent chain
+        if (KIND == 14) y[i] = y[i] * 5u + seed;                                                                 // IMAD, independent chain
         if (KIND == 1 || KIND == 5) x[i] = x[i] * 3u + b;                                   // IMAD
         if (KIND == 2 || KIND == 4) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(b)); // IADD3
         if (KIND == 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(b), "r"(a[(i + 1) & 7]));
@@ -34,7 +41,7 @@ __global__ void __launch_bounds__(256) k_ubench(uint32_t *out, int iters, uint32
   }
   uint32_t r = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) r += a[i] ^ x[i];
+  for (int i = 0; i < 8; i++) r += a[i] ^ x[i] ^ y[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
@@ -60,7 +67,14 @@ cudaError_t ubench(int kind, int iters, double *gops)
       case 4: k_ubench<4><<<grid, block>>>(out, iters, rep); break;
       case 5: k_ubench<5><<<grid, block>>>(out, iters, rep); break;
       case 6: k_ubench<6><<<grid, block>>>(out, iters, rep); break;
-      default: k_ubench<7><<<grid, block>>>(out, iters, rep); break;
+      case 7: k_ubench<7><<<grid, block>>>(out, iters, rep); break;
+      case 8: k_ubench<8><<<grid, block>>>(out, iters, rep); break;
+      case 9: k_ubench<9><<<grid, block>>>(out, iters, rep); break;
+      case 10: k_ubench<10><<<grid, block>>>(out, iters, rep); break;
+      case 11: k_ubench<11><<<grid, block>>>(out, iters, rep); break;
+      case 12: k_ubench<12><<<grid, block>>>(out, iters, rep); break;
+      case 13: k_ubench<13><<<grid, block>>>(out, iters, rep); break;
+      default: k_ubench<14><<<grid, block>>>(out, iters, rep); break;
     }
     cudaEventRecord(e1);
     e = cudaEventSynchronize(e1);
