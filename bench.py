@@ -56,38 +56,50 @@ def pel_sp(nmb):
 
 
 class ClockSampler:
-    """nvidia-smi clocks during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML (nvidia_ml_py) is polled
+    from a thread every ~2 ms (nvidia-smi -lms cannot resolve a region of tens of milliseconds)."""
 
     def __init__(self, gpu):
-        self.rows, self.stop = [], False
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        self.sm, self.reasons, self.stop, self.mx, self.err = [], set(), False, None, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml as N
+            N.nvmlInit()
+            # NVML indices are not remapped by CUDA_VISIBLE_DEVICES
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu]) if vis and vis.split(",")[gpu].isdigit() else gpu
+            self.N, self.h = N, N.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except Exception:
-            self.p = None
+        except Exception as e:  # noqa: BLE001
+            self.err, self.t = repr(e), None
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        N = self.N
+        names = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown if hasattr(N, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop:
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
 
     def finish(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop = True
+        if self.t:
+            self.t.join(timeout=1.0)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+               "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def measured_peaks():
