@@ -173,3 +173,90 @@ class Searcher:
         ms, n = C.c_double(), C.c_int64()
         self._chk(self.L.b2me_kernel_time_ms(self.h, C.c_int(which), C.byref(ms), C.byref(n)), "b2me_kernel_time_ms")
         return ms.value, n.value
+
+
+class FractalSearcher:
+    """One b2fr context (include/b2me.h): version1's fractal range/domain block search for one
+    picture size.  Mirrors the reference's call sequence: set_range (compute_range_Sum),
+    set_domain (compute_domain_Sum), then full_search per block or search_plane for the grid."""
+
+    def __init__(self, W, H, R, device=0):
+        self.L = lib()
+        self.L.b2fr_last_error.restype = C.c_char_p
+        self.L.b2fr_last_error.argtypes = [_vp]
+        self.L.b2fr_destroy.argtypes = [_vp]
+        self.L.b2fr_destroy.restype = None
+        self.L.b2fr_launch_count.restype = C.c_int64
+        self.L.b2fr_launch_count.argtypes = [_vp]
+        self.W, self.H, self.R = W, H, R
+        h = _vp()
+        r = self.L.b2fr_create(C.byref(h), C.c_int(device), C.c_int(W), C.c_int(H), C.c_int(R))
+        self.h = h
+        if r:
+            msg = self.L.b2fr_last_error(h if h else _vp(0))
+            raise B2Error(f"b2fr_create failed ({r}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b2fr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, r, what):
+        if r:
+            msg = self.L.b2fr_last_error(self.h)
+            raise B2Error(f"{what} failed ({r}): {msg.decode() if msg else ''}")
+
+    def _planes(self, y, u, v):
+        y = np.ascontiguousarray(y, np.uint8)
+        assert y.shape == (self.H, self.W)
+        u = None if u is None else np.ascontiguousarray(u, np.uint8)
+        v = None if v is None else np.ascontiguousarray(v, np.uint8)
+        return y, u, v
+
+    def set_range(self, y, u=None, v=None):
+        y, u, v = self._planes(y, u, v)
+        self._chk(self.L.b2fr_set_range(self.h, _p(y), _p(u) if u is not None else _vp(0), _p(v) if v is not None else _vp(0)), "b2fr_set_range")
+
+    def set_domain(self, plane_set, y, u=None, v=None, build_sums=True):
+        y, u, v = self._planes(y, u, v)
+        self._chk(self.L.b2fr_set_domain(self.h, C.c_int(plane_set), _p(y), _p(u) if u is not None else _vp(0),
+                                         _p(v) if v is not None else _vp(0), C.c_int(int(build_sums))), "b2fr_set_domain")
+
+    def grid(self, con):
+        return (self.W // 16, self.H // 16) if con == 1 else (self.W // 16 // 2, self.H // 16 // 2)
+
+    def search_plane(self, plane_set, con):
+        mbw, mbh = self.grid(con)
+        xy = np.zeros((mbw * mbh, NPART, 2), np.int32)
+        so = np.zeros((mbw * mbh, NPART, 2), np.float64)
+        rms = np.zeros((mbw * mbh, NPART), np.float64)
+        self._chk(self.L.b2fr_search_plane(self.h, C.c_int(plane_set), C.c_int(con), _p(xy), _p(so), _p(rms)), "b2fr_search_plane")
+        return xy, so, rms
+
+    def full_search(self, plane_set, bx, by, bsx, bsy, con, xy=(0, 0)):
+        v = (C.c_int32 * 2)(int(xy[0]), int(xy[1]))
+        so = (C.c_double * 2)()
+        rms = C.c_double()
+        self._chk(self.L.b2fr_full_search(self.h, C.c_int(plane_set), bx, by, bsx, bsy, con, v, so, C.byref(rms)), "b2fr_full_search")
+        return (v[0], v[1]), (so[0], so[1]), rms.value
+
+    def domain_table(self, plane_set, con, bw, bh, squares):
+        w, h = (self.W, self.H) if con == 1 else (self.W // 2, self.H // 2)
+        out = np.zeros((h, w), np.int32)
+        self._chk(self.L.b2fr_get_domain_table(self.h, C.c_int(plane_set), C.c_int(con), C.c_int(bw), C.c_int(bh), C.c_int(int(squares)), _p(out)), "b2fr_get_domain_table")
+        return out
+
+    def range_table(self, con, squares):
+        w, h = (self.W, self.H) if con == 1 else (self.W // 2, self.H // 2)
+        out = np.zeros((h // 4, w // 4), np.int32)
+        self._chk(self.L.b2fr_get_range_table(self.h, C.c_int(con), C.c_int(int(squares)), _p(out)), "b2fr_get_range_table")
+        return out
+
+    def launch_count(self):
+        return self.L.b2fr_launch_count(self.h)

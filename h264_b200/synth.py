@@ -43,3 +43,31 @@ def predictors(W, H, nrefs, seed=1, spread=0, base=None, rmax=6):
     p = p.astype(np.int16)
     c = (((p.astype(np.int32) + 2) >> 2) * 4).astype(np.int16)
     return p, c
+
+
+def yuv_pair(W, H, seed=20261018, shift=(-3, 2), gain=0.9, offset=10.0, noise=1.0):
+    """A (reference, current) 4:2:0 frame pair for the fractal search:
+    current = gain * reference displaced by `shift` + offset + noise, with a flat patch (variance 0
+    -> alpha = 0 path) and a saturated patch.  Returns ((Yr,Ur,Vr), (Yc,Uc,Vc)) uint8."""
+    rng = np.random.default_rng(seed)
+
+    def tex(h, w, k):
+        a = _smooth(rng.normal(0, 1, (h + 32, w + 32)), k)
+        a = (a - a.min()) / (a.max() - a.min())
+        return 30 + 190 * a + 10 * _smooth(rng.normal(0, 1, (h + 32, w + 32)), 1)
+
+    out = []
+    planes = [tex(H, W, 3), tex(H // 2, W // 2, 2), tex(H // 2, W // 2, 2)]
+    ref, cur = [], []
+    for i, t in enumerate(planes):
+        h, w = (H, W) if i == 0 else (H // 2, W // 2)
+        sx, sy = shift if i == 0 else (shift[0] // 2, shift[1] // 2)
+        r = t[16:16 + h, 16:16 + w]
+        c = gain * t[16 + sy:16 + sy + h, 16 + sx:16 + sx + w] + offset + rng.normal(0, noise, (h, w))
+        r = r.copy(); c = c.copy()
+        r[h // 2:h // 2 + 20, w // 4:w // 4 + 24] = 77          # flat domain area: det == 0
+        c[h // 4:h // 4 + 18, w // 2:w // 2 + 20] = 200          # flat range area
+        c[:12, :12] = 255
+        ref.append(np.clip(np.rint(r), 0, 255).astype(np.uint8))
+        cur.append(np.clip(np.rint(c), 0, 255).astype(np.uint8))
+    return tuple(ref), tuple(cur)

@@ -128,6 +128,40 @@ int b2me_kernel_time_ms(b2me_ctx *ctx, int which, double *ms, int64_t *launches)
  * 7 VABSDIFF4+LDS.  Returns giga warp-lane-ops per second of the FIRST op of the mix. */
 int b2me_ubench(int device, int kind, int iters, double *gops);
 
+/* ==== fractal range/domain block search (version1) ====================================== */
+/* One context per picture size.  Planes are 8-bit 4:2:0 (chroma planes width/2 x height/2, tightly
+ * packed); `con` follows version1: 1 = Y, 2 = U, 3 = V.  Plane sets: 0 = C (previous reconstructed
+ * frame), 1..3 = H, M, N (the "fractional-pel" sets the shipped program allocates but never
+ * fills, SURVEY Q-F3: they stay zero with zero sum tables unless the caller loads them).
+ * Results are indexed [macroblock of the component plane][p], p = the 41-partition numbering
+ * above (the 1+2+2+4+8+8+16 range blocks of a 16x16 macroblock). */
+typedef struct b2fr_ctx b2fr_ctx;
+int  b2fr_create(b2fr_ctx **out, int device, int width, int height, int search_range);
+void b2fr_destroy(b2fr_ctx *ctx);
+const char *b2fr_last_error(b2fr_ctx *ctx);
+/* range (current) frame + its block-grid sums:  <- compute_range_Sum  V1/src/compute.c:686 */
+int b2fr_set_range(b2fr_ctx *ctx, const uint8_t *y, const uint8_t *u, const uint8_t *v);
+/* domain (reference) plane set; build_sums != 0 rebuilds its sliding sum tables
+ *                                              <- compute_domain_Sum V1/src/compute.c:277 */
+int b2fr_set_domain(b2fr_ctx *ctx, int plane_set, const uint8_t *y, const uint8_t *u, const uint8_t *v, int build_sums);
+/* full_search of EVERY range block of component `con` against plane set `plane_set`:
+ *   xy [nmb][41][2] int32 displacement (0,0 when the start candidate wins),
+ *   scale_offset [nmb][41][2] double (alpha, beta after QUAN_A), rms [nmb][41] double (1e30 = rejected)
+ *                                              <- full_search V1/src/block_enc.c:1933 over the grid */
+int b2fr_search_plane(b2fr_ctx *ctx, int plane_set, int con, int32_t *xy, double *scale_offset, double *rms);
+/* Drop-in for ONE call of  double full_search(block_x, block_y, block_size_x, block_size_y, con, TRANS_NODE*)
+ * against the plane set changeReferenceFrame selected: xy is in/out (left untouched when the
+ * (0,0) start candidate wins, SURVEY Q-F11), scale_offset = {trans->scale, trans->offset}.  The
+ * first call after new pictures searches the whole (plane set, component) on the GPU; later calls
+ * are table look-ups (SURVEY Q-F10). */
+int b2fr_full_search(b2fr_ctx *ctx, int plane_set, int block_x, int block_y, int block_size_x, int block_size_y,
+                     int con, int32_t xy[2], double scale_offset[2], double *rms);
+/* parity read-back of the sum tables: domain table of block size bw x bh at every pixel offset
+ * ([h][w] int32, 0 where the block does not fit), range 4x4 table on the block grid ([h/4][w/4]) */
+int b2fr_get_domain_table(b2fr_ctx *ctx, int plane_set, int con, int bw, int bh, int squares, int32_t *out);
+int b2fr_get_range_table(b2fr_ctx *ctx, int con, int squares, int32_t *out);
+int64_t b2fr_launch_count(b2fr_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,3 +224,107 @@ class JMRef:
                                 _ptr(lam), C.c_int(int(do_subpel)), _ptr(mv_int), _ptr(cost_int),
                                 _ptr(mv_sub), _ptr(cost_sub))
         return mv_int, cost_int, mv_sub, cost_sub
+
+
+# ---------------------------------------------------------------------------------------------
+# version1 fractal search
+# ---------------------------------------------------------------------------------------------
+V1_SIZES = [(16, 16), (8, 8), (4, 4), (16, 8), (8, 16), (8, 4), (4, 8)]   # table order of compute_domain_Sum
+
+
+class V1Ref:
+    """The unmodified version1 compute.c/block_enc.c behind oracle/v1_harness.c (one per process:
+    the reference keeps its state in globals)."""
+    _made = False
+
+    def __init__(self, W, H, R, tol=(10.5, 8.0, 6.0)):
+        if V1Ref._made:
+            raise RuntimeError("V1Ref: the reference state is global; one instance per process")
+        self.L = _load(os.path.join(_HERE, "_ref", "libv1ref.so"))
+        self.L.v1h_full_search.restype = C.c_double
+        self.L.v1h_compute_rms.restype = C.c_double
+        self.W, self.H, self.R = W, H, R
+        r = self.L.v1h_init(C.c_int(W), C.c_int(H), C.c_int(R), C.c_double(tol[0]), C.c_double(tol[1]), C.c_double(tol[2]))
+        assert r == 0
+        V1Ref._made = True
+
+    def set_cur(self, y, u, v):
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        self.L.v1h_set_cur(_ptr(y), _ptr(u), _ptr(v))
+
+    def set_ref(self, which, y, u, v, build_sums=True):
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        self.L.v1h_set_ref(C.c_int(which), _ptr(y), _ptr(u), _ptr(v), C.c_int(int(build_sums)))
+
+    def full_search(self, which, bx, by, bsx, bsy, con):
+        xy = (C.c_int * 2)(0, 0)
+        so = (C.c_double * 2)()
+        rms = self.L.v1h_full_search(C.c_int(which), bx, by, bsx, bsy, con, xy, so)
+        return (xy[0], xy[1]), (so[0], so[1]), rms
+
+    def compute_rms(self, which, bx, by, m, n, bsx, bsy, con):
+        ab = (C.c_double * 2)()
+        r = self.L.v1h_compute_rms(C.c_int(which), bx, by, m, n, bsx, bsy, con, ab)
+        return r, ab[0], ab[1]
+
+    def domain_table(self, sz, con, squares):
+        """table sz (index into V1_SIZES) of plane set C as the reference holds it (double, cropped)."""
+        w, h = (self.W, self.H) if con == 1 else (self.W // 2, self.H // 2)
+        bw, bh = V1_SIZES[sz]
+        out = np.zeros((h - bh + 1, w - bw + 1), np.float64)
+        self.L.v1h_domain_table(C.c_int(sz), C.c_int(con), C.c_int(int(squares)), _ptr(out), C.c_int(out.shape[0]), C.c_int(out.shape[1]))
+        return out
+
+    def search_plane(self, which, con):
+        """full_search of every range block, in the product's [mb][41] layout."""
+        w, h = (self.W, self.H) if con == 1 else (self.W // 2, self.H // 2)
+        mbw, mbh = (self.W // 16, self.H // 16) if con == 1 else (self.W // 16 // 2, self.H // 16 // 2)
+        geo = partition_geometry()
+        xy = np.zeros((mbw * mbh, 41, 2), np.int32)
+        so = np.zeros((mbw * mbh, 41, 2), np.float64)
+        rms = np.zeros((mbw * mbh, 41), np.float64)
+        for mb in range(mbw * mbh):
+            for p, (_, ox, oy, bw, bh) in enumerate(geo):
+                a, b, r = self.full_search(which, (mb % mbw) * 16 + ox, (mb // mbw) * 16 + oy, bw, bh, con)
+                xy[mb, p], so[mb, p], rms[mb, p] = a, b, r
+        return xy, so, rms
+
+    def encode_mb(self, mb, con):
+        out = np.zeros((21, 5), np.int32)
+        outd = np.zeros((21, 2), np.float64)
+        n = self.L.v1h_encode_mb(C.c_int(mb), C.c_int(con), _ptr(out), _ptr(outd), C.c_int(21))
+        return out[:n], outd[:n]
+
+
+def v1_box_table(img, bw, bh, squares):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((h, w), np.float64)
+    orc_lib().orc_v1_box_table(_ptr(img), C.c_int(w), C.c_int(h), C.c_int(bw), C.c_int(bh), C.c_int(int(squares)), _ptr(out))
+    return out
+
+
+def v1_range_table(img, squares):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((h // 4, w // 4), np.float64)
+    orc_lib().orc_v1_range_table(_ptr(img), C.c_int(w), C.c_int(h), C.c_int(int(squares)), _ptr(out))
+    return out
+
+
+def v1_search_plane(org, ref, R, have_sums=True, chroma=False, full_wh=None):
+    """Restated full_search of every range block of one plane: (xy, scale_offset, rms) [mb][41]."""
+    org = np.ascontiguousarray(org, np.uint8)
+    ref = np.ascontiguousarray(ref, np.uint8)
+    h, w = org.shape
+    if chroma:
+        W, H = full_wh
+        mbw, mbh = W // 16 // 2, H // 16 // 2
+    else:
+        mbw, mbh = w // 16, h // 16
+    xy = np.zeros((mbw * mbh, 41, 2), np.int32)
+    so = np.zeros((mbw * mbh, 41, 2), np.float64)
+    rms = np.zeros((mbw * mbh, 41), np.float64)
+    orc_lib().orc_v1_search_plane(_ptr(org), _ptr(ref), C.c_int(w), C.c_int(h), C.c_int(mbw), C.c_int(mbh), C.c_int(R),
+                                  C.c_int(int(have_sums)), _ptr(xy), _ptr(so), _ptr(rms))
+    return xy, so, rms
