@@ -260,3 +260,39 @@ class FractalSearcher:
 
     def launch_count(self):
         return self.L.b2fr_launch_count(self.h)
+
+
+class TQParams(C.Structure):
+    """b2tq_params (include/b2me.h)"""
+    _fields_ = [("qp", C.c_int32), ("mode", C.c_int32), ("cavlc", C.c_int32), ("field_scan", C.c_int32),
+                ("disthres", C.c_int32), ("reserved", C.c_int32 * 3), ("scale", C.c_int32 * 64),
+                ("offset", C.c_int32 * 64), ("invscale", C.c_int32 * 64)]
+
+
+def tq_default_params(n, qp, intra, mode=0, cavlc=1, field_scan=0, disthres=0):
+    p = TQParams()
+    r = lib().b2tq_default_params(C.byref(p), C.c_int(int(n == 8)), C.c_int(qp), C.c_int(intra), C.c_int(mode))
+    if r:
+        raise B2Error(f"b2tq_default_params failed ({r})")
+    p.cavlc, p.field_scan, p.disthres = cavlc, field_scan, disthres
+    return p
+
+
+def tq_params_table(p, n):
+    return np.array([list(p.scale)[:n * n], list(p.offset)[:n * n], list(p.invscale)[:n * n]], np.int32)
+
+
+def tq(params, orig, pred, n, device=0):
+    """Host arrays through b2tq_4x4 / b2tq_8x8: returns level, run, recon, coeff_cost, nonzero."""
+    L = lib()
+    L.b2tq_last_error.restype = C.c_char_p
+    orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+    nblk, m = orig.shape[0], n * n
+    assert orig.shape == (nblk, m) and pred.shape == (nblk, m)
+    level = np.zeros((nblk, m), np.int16); run = np.zeros((nblk, m), np.uint8)
+    recon = np.zeros((nblk, m), np.uint8); cost = np.zeros(nblk, np.int32); nz = np.zeros(nblk, np.uint8)
+    f = L.b2tq_4x4 if n == 4 else L.b2tq_8x8
+    r = f(C.c_int(device), C.byref(params), C.c_int(nblk), _p(orig), _p(pred), _p(level), _p(run), _p(recon), _p(cost), _p(nz))
+    if r:
+        raise B2Error(f"b2tq_{n}x{n} failed ({r}): {L.b2tq_last_error().decode()}")
+    return level, run, recon, cost, nz

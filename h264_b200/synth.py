@@ -71,3 +71,19 @@ def yuv_pair(W, H, seed=20261018, shift=(-3, 2), gain=0.9, offset=10.0, noise=1.
         ref.append(np.clip(np.rint(r), 0, 255).astype(np.uint8))
         cur.append(np.clip(np.rint(c), 0, 255).astype(np.uint8))
     return tuple(ref), tuple(cur)
+
+
+def residual_blocks(nblk, n, seed=1):
+    """(orig, pred) uint8 [nblk][n*n]: a mix of smooth, noisy, identical (all-zero residual),
+    single-coefficient and saturated blocks for the transform/quant path."""
+    rng = np.random.default_rng(seed)
+    m = n * n
+    base = rng.integers(0, 256, (nblk, 1)).astype(np.int64)
+    ramp = (np.arange(m) % n)[None, :] * rng.integers(-6, 7, (nblk, 1)) + (np.arange(m) // n)[None, :] * rng.integers(-6, 7, (nblk, 1))
+    amp = rng.choice([0, 1, 2, 4, 8, 20, 60, 255], (nblk, 1))
+    orig = np.clip(base + ramp + rng.integers(-1, 2, (nblk, m)) * amp, 0, 255)
+    pred = np.clip(base + rng.integers(-1, 2, (nblk, m)) * rng.choice([0, 1, 3, 10, 255], (nblk, 1)), 0, 255)
+    same = rng.random(nblk) < 0.1
+    pred[same] = orig[same]
+    pred[::17] = 0; orig[::17] = 255          # maximal residual
+    return orig.astype(np.uint8), pred.astype(np.uint8)

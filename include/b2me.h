@@ -162,6 +162,41 @@ int b2fr_get_domain_table(b2fr_ctx *ctx, int plane_set, int con, int bw, int bh,
 int b2fr_get_range_table(b2fr_ctx *ctx, int con, int squares, int32_t *out);
 int64_t b2fr_launch_count(b2fr_ctx *ctx);
 
+/* ==== residual transform + quantisation + reconstruction ================================= */
+/* Parameter block = the reference's per-(plane, intra, qp) LevelQuantParams table
+ * (JM/lencod/inc/global.h LevelQuantParams; q_matrix.c:566-590, q_offsets.c:163-188) plus the
+ * switches residual_transform_quant_luma_4x4/_8x8 read from the slice / macroblock. */
+typedef struct b2tq_params {
+  int32_t qp;            /* qp_scaled of the plane (0..51); qp_per = qp / 6 */
+  int32_t mode;          /* 0: JM 18.5 (skip all-zero residual blocks, inverse only when a level is nonzero)
+                            1: version1 dct_luma (V1/src/block.c:836; 4x4 only, no level clip) */
+  int32_t cavlc;         /* symbol_mode == CAVLC: clip |level| to 2063 (quant4x4_normal.c:86; 4x4, mode 0) */
+  int32_t field_scan;    /* 0 zig-zag (SNGL_SCAN), 1 FIELD_SCAN */
+  int32_t disthres;      /* COEFF_COST4x4/8x8[disthres] */
+  int32_t reserved[3];
+  int32_t scale[64];     /* ScaleComp    raster [j*n+i], n = 4 or 8 */
+  int32_t offset[64];    /* OffsetComp */
+  int32_t invscale[64];  /* InvScaleComp (= dequant << 4 in mode 0; dequant_coef in mode 1) */
+} b2tq_params;
+/* flat matrices + default rounding offsets of the reference; intra: 0 inter block, 1 intra block
+ * of a P/B slice (offset 342/2048 like inter), 2 intra block of an I slice (682/2048); mode as above */
+int b2tq_default_params(b2tq_params *p, int is8x8, int qp, int intra, int mode);
+/* nblk independent blocks, tightly packed raster blocks: orig/pred/recon [nblk][16|64] u8;
+ * level [nblk][16|64] int16 and run [nblk][16|64] u8 = ACLevel/ACRun lists (zero-terminated,
+ * zero-padded); coeff_cost [nblk] int32 (the increment the reference adds to *coeff_cost);
+ * nonzero [nblk] u8 (the return value).  residual = orig - pred is formed on the device.
+ *   <- residual_transform_quant_luma_4x4  JM/lencod/src/block.c:660-724
+ *   <- residual_transform_quant_luma_8x8  JM/lencod/src/transform8x8.c:522-602 */
+int b2tq_4x4(int device, const b2tq_params *p, int nblk, const uint8_t *orig, const uint8_t *pred,
+             int16_t *level, uint8_t *run, uint8_t *recon, int32_t *coeff_cost, uint8_t *nonzero);
+int b2tq_8x8(int device, const b2tq_params *p, int nblk, const uint8_t *orig, const uint8_t *pred,
+             int16_t *level, uint8_t *run, uint8_t *recon, int32_t *coeff_cost, uint8_t *nonzero);
+int b2tq_4x4_dev(const b2tq_params *p, int nblk, const uint8_t *orig, const uint8_t *pred,
+                 int16_t *level, uint8_t *run, uint8_t *recon, int32_t *coeff_cost, uint8_t *nonzero, void *stream);
+int b2tq_8x8_dev(const b2tq_params *p, int nblk, const uint8_t *orig, const uint8_t *pred,
+                 int16_t *level, uint8_t *run, uint8_t *recon, int32_t *coeff_cost, uint8_t *nonzero, void *stream);
+const char *b2tq_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -328,3 +328,59 @@ def v1_search_plane(org, ref, R, have_sums=True, chroma=False, full_wh=None):
     orc_lib().orc_v1_search_plane(_ptr(org), _ptr(ref), C.c_int(w), C.c_int(h), C.c_int(mbw), C.c_int(mbh), C.c_int(R),
                                   C.c_int(int(have_sums)), _ptr(xy), _ptr(so), _ptr(rms))
     return xy, so, rms
+
+
+# ---------------------------------------------------------------------------------------------
+# residual transform + quantisation
+# ---------------------------------------------------------------------------------------------
+class TQParams(C.Structure):
+    """same layout as b2tq_params (include/b2me.h)"""
+    _fields_ = [("qp", C.c_int32), ("mode", C.c_int32), ("cavlc", C.c_int32), ("field_scan", C.c_int32),
+                ("disthres", C.c_int32), ("reserved", C.c_int32 * 3), ("scale", C.c_int32 * 64),
+                ("offset", C.c_int32 * 64), ("invscale", C.c_int32 * 64)]
+
+
+def tq_params(table, qp, mode=0, cavlc=1, field_scan=0, disthres=0):
+    """table: int array [3][n*n] = ScaleComp, OffsetComp, InvScaleComp."""
+    p = TQParams()
+    p.qp, p.mode, p.cavlc, p.field_scan, p.disthres = qp, mode, cavlc, field_scan, disthres
+    t = np.asarray(table, np.int64)
+    for k, name in enumerate(("scale", "offset", "invscale")):
+        arr = getattr(p, name)
+        for i, v in enumerate(t[k].ravel()):
+            arr[i] = int(v)
+    return p
+
+
+def tq(params, orig, pred, n):
+    """restated oracle: n = 4 or 8.  Returns level, run, recon, cost, nonzero."""
+    orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+    nblk = orig.shape[0]
+    level = np.zeros((nblk, n * n), np.int16); run = np.zeros((nblk, n * n), np.uint8)
+    recon = np.zeros((nblk, n * n), np.uint8); cost = np.zeros(nblk, np.int32); nz = np.zeros(nblk, np.uint8)
+    f = orc_lib().orc_tq4x4 if n == 4 else orc_lib().orc_tq8x8
+    f(C.byref(params), C.c_int(nblk), _ptr(orig), _ptr(pred), _ptr(level), _ptr(run), _ptr(recon), _ptr(cost), _ptr(nz))
+    return level, run, recon, cost, nz
+
+
+class JMQuantRef:
+    """The unmodified JM residual_transform_quant_luma_4x4/_8x8 behind oracle/jm_harness_tq.c."""
+
+    def __init__(self, slice_type=0, symbol_mode=0):
+        self.L = _load(os.path.join(_HERE, "_ref", "libjmref.so"))
+        self.L.jmq_create.restype = _vp
+        self.h = _vp(self.L.jmq_create(C.c_int(slice_type), C.c_int(symbol_mode)))
+
+    def params(self, n, qp, intra):
+        out = np.zeros((3, n * n), np.int32)
+        self.L.jmq_params(self.h, C.c_int(int(n == 8)), C.c_int(qp), C.c_int(intra), _ptr(out))
+        return out
+
+    def tq(self, n, qp, intra, orig, pred):
+        orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+        nblk, m = orig.shape[0], n * n
+        level = np.zeros((nblk, m + 1), np.int32); run = np.zeros((nblk, m + 1), np.int32)
+        recon = np.zeros((nblk, m), np.uint8); cost = np.zeros(nblk, np.int32); nz = np.zeros(nblk, np.int32)
+        f = self.L.jmq_tq4x4 if n == 4 else self.L.jmq_tq8x8
+        f(self.h, C.c_int(qp), C.c_int(intra), C.c_int(nblk), _ptr(orig), _ptr(pred), _ptr(level), _ptr(run), _ptr(recon), _ptr(cost), _ptr(nz))
+        return level[:, :m].astype(np.int16), run[:, :m].astype(np.uint8), recon, cost, nz.astype(np.uint8)

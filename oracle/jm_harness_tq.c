@@ -1,0 +1,136 @@
+/* jm_harness_tq.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Drives the UNMODIFIED JM 18.5 residual transform + quantisation path:
+ *   residual_transform_quant_luma_4x4   JM/lencod/src/block.c:660-724
+ *   residual_transform_quant_luma_8x8   JM/lencod/src/transform8x8.c:522-602
+ *     -> forward4x4 / inverse4x4 / forward8x8 / inverse8x8   JM/lcommon/src/transform.c
+ *     -> quant_4x4_normal / quant_8x8_normal                 JM/lencod/src/quant4x4_normal.c:39, quant8x8_normal.c:43
+ *     -> sample_reconstruct                                  JM/lcommon/src/blk_prediction.c:48
+ * with the quantiser tables built by the reference's own init_qmatrix / CalculateQuant4x4Param /
+ * CalculateQuant8x8Param (q_matrix.c:539,591,729) and init_qoffset / CalculateOffset4x4Param /
+ * CalculateOffset8x8Param (q_offsets.c:385,487,570).
+ */
+#include <string.h>
+#include <stdlib.h>
+#include "global.h"
+#include "memalloc.h"
+#include "mbuffer.h"
+#include "block.h"
+#include "transform8x8.h"
+#include "q_matrix.h"
+#include "q_offsets.h"
+#include "quant4x4.h"
+#include "quant8x8.h"
+
+typedef struct {
+  VideoParameters *p_Vid;
+  InputParameters *p_Inp;
+  Slice *slice;
+  Macroblock mb;
+  StorablePicture *enc;
+} JMQ;
+
+/* slice_type: P_SLICE (0) / I_SLICE (2); symbol_mode: 0 CAVLC, 1 CABAC */
+void *jmq_create(int slice_type, int symbol_mode)
+{
+  JMQ *h = (JMQ *)calloc(1, sizeof(JMQ));
+  VideoParameters *p_Vid = (VideoParameters *)calloc(1, sizeof(VideoParameters));
+  InputParameters *p_Inp = (InputParameters *)calloc(1, sizeof(InputParameters));
+  Slice *s = (Slice *)calloc(1, sizeof(Slice));
+  h->p_Vid = p_Vid; h->p_Inp = p_Inp; h->slice = s;
+  p_Vid->p_Inp = p_Inp;
+  p_Inp->output.bit_depth[0] = p_Inp->output.bit_depth[1] = 8;
+  p_Vid->bitdepth_luma = p_Vid->bitdepth_chroma = 8;
+  p_Vid->max_imgpel_value = 255;
+  p_Vid->yuv_format = YUV420;
+  p_Vid->type = slice_type;
+  p_Vid->nal_reference_idc = NALU_PRIORITY_HIGHEST;
+  p_Vid->p_Quant = (QuantParameters *)calloc(1, sizeof(QuantParameters));
+  p_Vid->p_QScale = (ScaleParameters *)calloc(1, sizeof(ScaleParameters));
+  p_Vid->active_sps = (seq_parameter_set_rbsp_t *)calloc(1, sizeof(seq_parameter_set_rbsp_t));
+  p_Vid->active_pps = (pic_parameter_set_rbsp_t *)calloc(1, sizeof(pic_parameter_set_rbsp_t));
+  init_qmatrix(p_Vid, p_Inp);
+  init_qoffset(p_Vid);
+  CalculateQuant4x4Param(p_Vid);
+  CalculateQuant8x8Param(p_Vid);
+  CalculateOffset4x4Param(p_Vid);
+  CalculateOffset8x8Param(p_Vid);
+  h->enc = alloc_storable_picture(p_Vid, FRAME, 16, 16, 8, 8);
+  h->enc->p_curr_img = h->enc->imgY;
+  p_Vid->enc_picture = h->enc;
+  s->p_Vid = p_Vid; s->p_Inp = p_Inp; s->slice_type = slice_type; s->symbol_mode = (char)symbol_mode;
+  get_mem3Dpel(&s->mb_pred, 3, 16, 16);
+  get_mem3Dint(&s->mb_ores, 3, 16, 16);
+  get_mem3Dint(&s->mb_rres, 3, 16, 16);
+  get_mem2Dint(&s->tblk16x16, 16, 16);
+  get_mem4Dint(&s->cofAC, 12, 4, 2, 65);
+  init_quant_4x4(s);
+  init_quant_8x8(s);
+  h->mb.p_Vid = p_Vid; h->mb.p_Inp = p_Inp; h->mb.p_Slice = s;
+  return h;
+}
+
+/* nblk 4x4 blocks; block k is placed at (4*(k&3), 4*((k>>2)&3)) of the macroblock.
+ * out: level[nblk][17], run[nblk][17] (ACLevel/ACRun as the reference leaves them; entries after
+ * the terminating level 0 are set to 0), recon[nblk][16], cost[nblk], nz[nblk] */
+void jmq_tq4x4(void *hh, int qp, int intra, int nblk, const unsigned char *orig, const unsigned char *pred,
+               int *level, int *run, unsigned char *recon, int *cost, int *nz)
+{
+  JMQ *h = (JMQ *)hh; Slice *s = h->slice; int k, i, j;
+  h->mb.qp_scaled[0] = qp;
+  for (k = 0; k < nblk; k++) {
+    int bx = 4 * (k & 3), by = 4 * ((k >> 2) & 3), c = 0, n;
+    int pos_x = bx >> 2, pos_y = by >> 2, b8 = 2 * (pos_y >> 1) + (pos_x >> 1), b4 = 2 * (pos_y & 1) + (pos_x & 1);
+    for (j = 0; j < 4; j++)
+      for (i = 0; i < 4; i++) {
+        s->mb_pred[0][by + j][bx + i] = pred[k * 16 + j * 4 + i];
+        s->mb_ores[0][by + j][bx + i] = (int)orig[k * 16 + j * 4 + i] - (int)pred[k * 16 + j * 4 + i];
+      }
+    memset(s->cofAC[b8][b4][0], 0, 65 * sizeof(int)); memset(s->cofAC[b8][b4][1], 0, 65 * sizeof(int));
+    nz[k] = residual_transform_quant_luma_4x4(&h->mb, PLANE_Y, bx, by, &c, intra);
+    cost[k] = c;
+    for (n = 0; n < 17; n++) { level[k * 17 + n] = s->cofAC[b8][b4][0][n]; run[k * 17 + n] = s->cofAC[b8][b4][1][n]; }
+    for (n = 0; n < 16 && level[k * 17 + n] != 0; n++) ;
+    for (; n < 17; n++) { level[k * 17 + n] = 0; run[k * 17 + n] = 0; }
+    for (j = 0; j < 4; j++)
+      for (i = 0; i < 4; i++) recon[k * 16 + j * 4 + i] = (unsigned char)h->enc->imgY[by + j][bx + i];
+  }
+}
+
+/* nblk 8x8 blocks; block k is b8 = k&3.  level/run [nblk][65], recon [nblk][64] */
+void jmq_tq8x8(void *hh, int qp, int intra, int nblk, const unsigned char *orig, const unsigned char *pred,
+               int *level, int *run, unsigned char *recon, int *cost, int *nz)
+{
+  JMQ *h = (JMQ *)hh; Slice *s = h->slice; int k, i, j;
+  h->mb.qp_scaled[0] = qp;
+  for (k = 0; k < nblk; k++) {
+    int b8 = k & 3, bx = 8 * (b8 & 1), by = 8 * (b8 >> 1), c = 0, n;
+    for (j = 0; j < 8; j++)
+      for (i = 0; i < 8; i++) {
+        s->mb_pred[0][by + j][bx + i] = pred[k * 64 + j * 8 + i];
+        s->mb_ores[0][by + j][bx + i] = (int)orig[k * 64 + j * 8 + i] - (int)pred[k * 64 + j * 8 + i];
+      }
+    memset(s->cofAC[b8][0][0], 0, 65 * sizeof(int)); memset(s->cofAC[b8][0][1], 0, 65 * sizeof(int));
+    nz[k] = residual_transform_quant_luma_8x8(&h->mb, PLANE_Y, b8, &c, intra);
+    cost[k] = c;
+    for (n = 0; n < 65; n++) { level[k * 65 + n] = s->cofAC[b8][0][0][n]; run[k * 65 + n] = s->cofAC[b8][0][1][n]; }
+    for (n = 0; n < 64 && level[k * 65 + n] != 0; n++) ;
+    for (; n < 65; n++) { level[k * 65 + n] = 0; run[k * 65 + n] = 0; }
+    for (j = 0; j < 8; j++)
+      for (i = 0; i < 8; i++) recon[k * 64 + j * 8 + i] = (unsigned char)h->enc->imgY[by + j][bx + i];
+  }
+}
+
+/* the LevelQuantParams the reference derived, for the product's parameter block:
+ * out[3][16] (or [3][64]) = ScaleComp, OffsetComp, InvScaleComp, raster [j][i] */
+void jmq_params(void *hh, int is8x8, int qp, int intra, int *out)
+{
+  JMQ *h = (JMQ *)hh; int n = is8x8 ? 8 : 4, i, j;
+  LevelQuantParams **q = is8x8 ? h->p_Vid->p_Quant->q_params_8x8[0][intra][qp] : h->p_Vid->p_Quant->q_params_4x4[0][intra][qp];
+  for (j = 0; j < n; j++)
+    for (i = 0; i < n; i++) {
+      out[0 * n * n + j * n + i] = q[j][i].ScaleComp;
+      out[1 * n * n + j * n + i] = q[j][i].OffsetComp;
+      out[2 * n * n + j * n + i] = q[j][i].InvScaleComp;
+    }
+}

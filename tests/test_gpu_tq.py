@@ -1,0 +1,54 @@
+"""GPU parity tests (through the C ABI): CUDA transform/quant/reconstruction vs golden vectors of the
+unmodified JM objects and vs the restated oracle (bit-exact: integer path)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from h264_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+NAMES = ("level", "run", "recon", "cost", "nz")
+
+
+def test_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "jm_tq.npz"))
+    for ci, (n, qp, intra, st, sm, seed, nblk) in enumerate(g["cases"]):
+        n, qp = int(n), int(qp)
+        orig, pred = synth.residual_blocks(int(nblk), n, int(seed))
+        p = api.TQParams()
+        q = oracle.tq_params(g[f"c{ci}_params"], qp, cavlc=int(sm == 0))
+        for f, _ in api.TQParams._fields_:
+            setattr(p, f, getattr(q, f))
+        out = api.tq(p, orig, pred, n)
+        for a, name in zip(out, NAMES):
+            assert (a == g[f"c{ci}_{name}"]).all(), (ci, name)
+
+
+@pytest.mark.parametrize("n,qp,intra,mode,field,dis,nblk", [
+    (4, 28, 0, 0, 0, 0, 1), (4, 28, 0, 0, 0, 0, 130),            # ragged sizes (not a multiple of the CTA)
+    (4, 33, 1, 0, 1, 1, 4097), (4, 28, 0, 1, 0, 0, 2000),        # field scan + disthres; version1 dct_luma mode
+    (4, 10, 1, 1, 0, 0, 2000), (8, 28, 0, 0, 0, 0, 1), (8, 26, 1, 0, 1, 1, 1025),
+    (4, 28, 0, 0, 0, 0, 130560), (8, 28, 0, 0, 0, 0, 32640),     # every 4x4 / 8x8 block of a 1080p luma frame
+])
+def test_matches_oracle(n, qp, intra, mode, field, dis, nblk):
+    orig, pred = synth.residual_blocks(nblk, n, seed=nblk + qp)
+    p = api.tq_default_params(n, qp, intra, mode=mode, field_scan=field, disthres=dis)
+    q = oracle.tq_params(api.tq_params_table(p, n), qp, mode=mode, cavlc=1, field_scan=field, disthres=dis)
+    got = api.tq(p, orig, pred, n)
+    exp = oracle.tq(q, orig, pred, n)
+    for a, b, name in zip(got, exp, NAMES):
+        assert (a == b).all(), name
+
+
+def test_empty_and_bad_arguments():
+    p = api.tq_default_params(4, 28, 0)
+    z = np.zeros((0, 16), np.uint8)
+    out = api.tq(p, z, z, 4)
+    assert out[0].shape == (0, 16)
+    p.qp = 99
+    with pytest.raises(api.B2Error):
+        api.tq(p, np.zeros((1, 16), np.uint8), np.zeros((1, 16), np.uint8), 4)
+    with pytest.raises(api.B2Error):
+        api.tq_default_params(8, 28, 0, mode=1)        # version1 has no 8x8 transform
