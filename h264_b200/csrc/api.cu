@@ -176,6 +176,31 @@ static int check_params(b2me_ctx *c, const b2me_search_params *p)
   return B2ME_OK;
 }
 
+static int run_subpel(b2me_ctx *c, int mb_first, int mb_count, int ref_first, int refs_per_mb, int abs_index,
+                      unsigned long long mask, const int16_t *pred, const b2me_search_params *p,
+                      const int16_t *mv_int, const long long *cost_int, int16_t *mv_sub, long long *cost_sub,
+                      int use_bound, cudaStream_t s)
+{
+  SubArgs q;
+  q.cur = c->d_cur; q.cur_pitch = c->W; q.planes = c->d_planes; q.plane_size = c->plane_size;
+  q.W = c->W; q.H = c->H; q.Wp = c->Wp; q.Hp = c->Hp; q.mbw = c->mbw; q.nrefs = c->nrefs;
+  q.lambda_h = p->lambda_factor[1]; q.lambda_q = p->lambda_factor[2]; q.metric_h = p->metric_h; q.metric_q = p->metric_q;
+  // p_Vid->start_me_refinement_hp/_qp (mv_search.c:445-446), ChromaME off, F_PEL metric = SAD
+  q.start_hp = (0 != p->metric_h) ? 0 : 1;
+  q.start_qp = (p->metric_h != p->metric_q) ? 0 : 1;
+  // BlockMotionSearch resets the bound to DISTBLK_MAX when start_me_refinement_hp == 0 (mv_search.c:971-974);
+  // the single-call drop-in receives the caller's bound instead
+  q.use_bound = use_bound >= 0 ? use_bound : q.start_hp;
+  q.pred = pred; q.mv_int = mv_int; q.cost_int = cost_int; q.mv_sub = mv_sub; q.cost_sub = cost_sub;
+  q.mb_first = mb_first; q.ref_first = ref_first; q.refs_per_mb = refs_per_mb; q.nitems = mb_count * refs_per_mb;
+  q.abs_index = abs_index; q.part_mask = mask;
+  FamilyTimer t(c, 2, s);
+  B2_CUDA_CHECK(c, launch_subpel_refine(q, s));
+  c->launches++;
+  t.stop();
+  return B2ME_OK;
+}
+
 static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, int refs_per_mb, int abs_index,
                       unsigned long long mask, int sr_override,
                       const int16_t *pred, const int16_t *center, const b2me_search_params *p,
@@ -195,21 +220,8 @@ static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
     c->launches++;
     t.stop();
   }
-  if (p->do_subpel) {
-    SubArgs q;
-    q.cur = c->d_cur; q.cur_pitch = c->W; q.planes = c->d_planes; q.plane_size = c->plane_size;
-    q.W = c->W; q.H = c->H; q.Wp = c->Wp; q.Hp = c->Hp; q.mbw = c->mbw; q.nrefs = c->nrefs;
-    q.lambda_h = p->lambda_factor[1]; q.lambda_q = p->lambda_factor[2]; q.metric_h = p->metric_h; q.metric_q = p->metric_q;
-    // p_Vid->start_me_refinement_hp/_qp (mv_search.c:445-446), ChromaME off, F_PEL metric = SAD
-    q.start_hp = (0 != p->metric_h) ? 0 : 1; q.start_qp = (p->metric_h != p->metric_q) ? 0 : 1;
-    q.pred = pred; q.mv_int = mv_int; q.cost_int = cost_int; q.mv_sub = mv_sub; q.cost_sub = cost_sub;
-    q.mb_first = mb_first; q.ref_first = ref_first; q.refs_per_mb = refs_per_mb; q.nitems = f.nitems;
-    q.abs_index = abs_index; q.part_mask = mask;
-    FamilyTimer t(c, 2, s);
-    B2_CUDA_CHECK(c, launch_subpel_refine(q, s));
-    c->launches++;
-    t.stop();
-  }
+  if (p->do_subpel)
+    return run_subpel(c, mb_first, mb_count, ref_first, refs_per_mb, abs_index, mask, pred, p, mv_int, cost_int, mv_sub, cost_sub, -1, s);
   return B2ME_OK;
 }
 
@@ -310,6 +322,43 @@ extern "C" int b2me_block_search(b2me_ctx *c, int pos_x, int pos_y, int blocktyp
     mv_sub[0] = h16[(3 * NPART + part) * 2]; mv_sub[1] = h16[(3 * NPART + part) * 2 + 1];
     *cost_sub = h64[NPART + part];
   }
+  return B2ME_OK;
+}
+
+// Drop-in for ONE call of sub_pel_motion_estimation: start MV mv_in (quarter-pel, relative), bound
+// min_mcost exactly as BlockMotionSearch hands it over (mv_search.c:967-976).
+extern "C" int b2me_block_subpel(b2me_ctx *c, int pos_x, int pos_y, int blocktype, int ref_idx,
+                                 const int16_t pred_mv[2], const int16_t mv_in[2], const b2me_search_params *p,
+                                 int64_t min_mcost, int16_t mv_out[2], int64_t *cost_out)
+{
+  if (!c || !pred_mv || !mv_in || !mv_out || !cost_out) return B2ME_EINVAL;
+  int r = check_params(c, p);
+  if (r) return r;
+  if (blocktype < 1 || blocktype > 7 || ref_idx < 0 || ref_idx >= c->nrefs || pos_x < 0 || pos_y < 0 || pos_x >= c->W || pos_y >= c->H) return B2ME_EINVAL;
+  int part = -1;
+  for (int q = part_first(blocktype); q < NPART; q++) {
+    PartGeom g = part_geom(q);
+    if (g.bt != blocktype) break;
+    if (g.ox == (pos_x & 15) && g.oy == (pos_y & 15)) { part = q; break; }
+  }
+  if (part < 0) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  int16_t *h16 = c->h_io16; long long *h64 = c->h_io64;
+  h16[part * 2] = pred_mv[0]; h16[part * 2 + 1] = pred_mv[1];
+  h16[(2 * NPART + part) * 2] = mv_in[0]; h16[(2 * NPART + part) * 2 + 1] = mv_in[1];
+  h64[part] = min_mcost;
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_io16, h16, 3 * NPART * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_io64, h64, NPART * sizeof(long long), cudaMemcpyHostToDevice, s));
+  const int mb = (pos_y >> 4) * c->mbw + (pos_x >> 4);
+  r = run_subpel(c, mb, 1, ref_idx, 1, 0, 1ull << part, c->d_io16, p, c->d_io16 + 2 * NPART * 2, c->d_io64,
+                 c->d_io16 + 3 * NPART * 2, c->d_io64 + NPART, 1, s);
+  if (r) return r;
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(h16 + 3 * NPART * 2, c->d_io16 + 3 * NPART * 2, NPART * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(h64 + NPART, c->d_io64 + NPART, NPART * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  B2_CUDA_CHECK(c, cudaStreamSynchronize(s));
+  mv_out[0] = h16[(3 * NPART + part) * 2]; mv_out[1] = h16[(3 * NPART + part) * 2 + 1];
+  *cost_out = h64[NPART + part];
   return B2ME_OK;
 }
 

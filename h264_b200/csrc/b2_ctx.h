@@ -59,6 +59,7 @@ struct SubArgs {
   int W, H, Wp, Hp, mbw, nrefs;
   int lambda_h, lambda_q, metric_h, metric_q;
   int start_hp, start_qp;
+  int use_bound;         // 1: cost_int is the initial bound of the half-pel stage, 0: DISTBLK_MAX
   const int16_t *pred;
   const int16_t *mv_int; const long long *cost_int;
   int16_t *mv_sub; long long *cost_sub;

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
       mv[tid][0] = a.mv_int[(base + tid) * 2]; mv[tid][1] = a.mv_int[(base + tid) * 2 + 1];
       prd[tid][0] = a.pred[(base + tid) * 2];  prd[tid][1] = a.pred[(base + tid) * 2 + 1];
       // BlockMotionSearch resets the bound when the metric changes between levels (mv_search.c:971-974)
-      mincost[tid] = a.start_hp ? a.cost_int[base + tid] : DMAX;
+      mincost[tid] = a.use_bound ? a.cost_int[base + tid] : DMAX;
     }
     for (int stage = 0; stage < 2; stage++) {
       const int step = stage ? 1 : 2;

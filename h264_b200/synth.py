@@ -87,3 +87,16 @@ def residual_blocks(nblk, n, seed=1):
     pred[same] = orig[same]
     pred[::17] = 0; orig[::17] = 255          # maximal residual
     return orig.astype(np.uint8), pred.astype(np.uint8)
+
+
+def yuv420_sequence(W, H, nframes, seed=20261018):
+    """Planar 4:2:0 clip as bytes (Y, U, V per frame): luma_sequence for Y, U = 128, V = a smooth
+    function of Y (SURVEY 8(d) config 1 input)."""
+    y = luma_sequence(W, H, nframes, seed=seed)
+    out = bytearray()
+    for t in range(nframes):
+        out += y[t].tobytes()
+        out += np.full((H // 2, W // 2), 128, np.uint8).tobytes()
+        v = (y[t][::2, ::2].astype(np.int32) // 4 + 96).astype(np.uint8)
+        out += v.tobytes()
+    return bytes(out)

@@ -112,6 +112,13 @@ int b2me_block_search(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int re
                       const b2me_search_params *params, int search_range_pel,
                       int16_t mv_int[2], int64_t *cost_int, int16_t mv_sub[2], int64_t *cost_sub);
 
+/* Drop-in for ONE call of sub_pel_motion_estimation: mv_in = the block's current MV (relative,
+ * quarter-pel), min_mcost = the bound exactly as the caller hands it over (BlockMotionSearch passes
+ * DISTBLK_MAX when the metric changes between levels, mv_search.c:971-974). */
+int b2me_block_subpel(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int ref_idx,
+                      const int16_t pred_mv[2], const int16_t mv_in[2], const b2me_search_params *params,
+                      int64_t min_mcost, int16_t mv_out[2], int64_t *cost_out);
+
 /* ---- instrumentation ---------------------------------------------------------------- */
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t b2me_launch_count(b2me_ctx *ctx);

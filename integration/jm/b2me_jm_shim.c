@@ -1,0 +1,193 @@
+/* b2me_jm_shim.c -- the reference-side binding: JM 18.5's motion-search entry points served by
+ * libb2me.so (hand-written sm_100a CUDA behind include/b2me.h).
+ *
+ * Link-level object replacement: JM's me_fullsearch.o is left out of the link and this
+ * file defines the two symbols the IPPP / full-search configurations reach,
+ *     distblk full_search_motion_estimation(Macroblock*, MotionVector*, MEBlock*, distblk, int)
+ *     distblk sub_pel_motion_estimation    (Macroblock*, MotionVector*, MEBlock*, distblk, int*)
+ * with the exact signatures of JM/lencod/inc/me_fullsearch.h:20-25.  The other four symbols of
+ * that object (bi-pred twins, full_sub_pel_motion_estimation) come from JM's own source compiled
+ * with the two names above renamed (integration/jm/Makefile), so every other configuration still
+ * links and runs the reference code for them.
+ *
+ * Ownership / threading follow the reference: the caller owns every buffer, the callee writes only
+ * mv_block->mv[list] and returns the cost; one thread; state hangs off a process-wide context that
+ * is created on first use from p_Vid / p_Inp and keyed on picture identity:
+ *   - the current original picture is uploaded when p_Vid->enc_picture changes,
+ *   - a reference picture is uploaded (and its 16 quarter-pel planes rebuilt on the GPU) the first
+ *     time a (StorablePicture*, poc) pair is searched; slots are recycled least-recently-used.
+ * Configurations the CUDA path does not cover (bit depth > 8, field/MBAFF pictures, weighted ME,
+ * chroma ME, list 1, SSE metrics, non-RDO (0,0) bias) stop the encoder through JM's own error()
+ * -- there is no silent CPU fallback.
+ *
+ * Built only where the JM headers are available (it includes the reference's global.h).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "global.h"
+#include "mbuffer.h"
+#include "me_fullsearch.h"
+#include "mv_search.h"
+#include "b2me.h"
+
+#define B2_MAX_SLOTS 16
+
+typedef struct {
+  StorablePicture *pic;
+  int poc;
+  long stamp;
+} B2Slot;
+
+static b2me_ctx *g_ctx;
+static int g_W, g_H, g_nslots;
+static B2Slot g_slot[B2_MAX_SLOTS];
+static long g_clock;
+static StorablePicture *g_cur_pic;
+static int g_cur_poc = -0x7fffffff;
+static unsigned char *g_stage;
+static long g_calls_int, g_calls_sub, g_uploads;
+
+static void b2_fail(const char *what)
+{
+  char msg[600];
+  snprintf(msg, sizeof(msg), "b2me shim: %s (%s)", what, g_ctx ? b2me_last_error(g_ctx) : "no context");
+  error(msg, 500);
+}
+
+static void b2_report(void)
+{
+  if (getenv("B2ME_SHIM_VERBOSE"))
+    fprintf(stderr, "b2me shim: %ld integer searches, %ld sub-pel refinements, %ld picture uploads, %lld kernel launches\n",
+            g_calls_int, g_calls_sub, g_uploads, g_ctx ? (long long)b2me_launch_count(g_ctx) : 0LL);
+  if (g_ctx) b2me_destroy(g_ctx);
+  g_ctx = NULL;
+}
+
+static void b2_check_config(Macroblock *currMB, MEBlock *mv_block)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  InputParameters *p_Inp = currMB->p_Inp;
+  Slice *currSlice = currMB->p_Slice;
+  if (p_Vid->bitdepth_luma != 8) b2_fail("only 8-bit luma is supported");
+  if (currSlice->structure != FRAME || currMB->list_offset != 0) b2_fail("field / MBAFF pictures are not supported");
+  if (mv_block->list != 0) b2_fail("only list 0 is supported");
+  if (p_Inp->ChromaMEEnable || mv_block->ChromaMEEnable) b2_fail("ChromaMEEnable is not supported");
+  if (mv_block->apply_weights) b2_fail("weighted-prediction ME is not supported");
+  if (!p_Inp->rdopt) b2_fail("RDOptimization=0 ((0,0)-bias path) is not supported");
+  if (p_Inp->MEErrorMetric[F_PEL] != ERROR_SAD) b2_fail("MEDistortionFPel must be SAD");
+  if (p_Inp->OnTheFlyFractMCP) b2_fail("OnTheFlyFractMCP must be 0");
+}
+
+static void b2_ensure_ctx(Macroblock *currMB)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  InputParameters *p_Inp = currMB->p_Inp;
+  int dev = 0, R = p_Inp->search_range[p_Vid->view_id];
+  const char *e = getenv("B2ME_DEVICE");
+  if (g_ctx) return;
+  if (e) dev = atoi(e);
+  g_W = p_Vid->width; g_H = p_Vid->height;
+  g_nslots = imin(B2_MAX_SLOTS, imax(2, p_Vid->max_num_references + 1));
+  if (b2me_create(&g_ctx, dev, g_W, g_H, g_nslots, R) != B2ME_OK) b2_fail("b2me_create failed");
+  g_stage = (unsigned char *)malloc((size_t)g_W * g_H);
+  if (!g_stage) no_mem_exit("b2me shim: staging plane");
+  memset(g_slot, 0, sizeof(g_slot));
+  atexit(b2_report);
+}
+
+/* imgpel (uint16 holding 8-bit samples, SURVEY Q-J3) -> packed bytes */
+static void b2_narrow(imgpel **src)
+{
+  int x, y;
+  for (y = 0; y < g_H; y++) {
+    const imgpel *s = src[y];
+    unsigned char *d = g_stage + (size_t)y * g_W;
+    for (x = 0; x < g_W; x++) d[x] = (unsigned char)s[x];
+  }
+}
+
+static void b2_ensure_cur(VideoParameters *p_Vid)
+{
+  StorablePicture *enc = p_Vid->enc_picture;
+  if (enc == g_cur_pic && enc->poc == g_cur_poc) return;
+  b2_narrow(p_Vid->pCurImg);
+  if (b2me_set_cur(g_ctx, g_stage, g_W) != B2ME_OK) b2_fail("b2me_set_cur failed");
+  g_cur_pic = enc; g_cur_poc = enc->poc; g_uploads++;
+  /* a new coded picture: reference slots whose picture is gone are simply aged out by the LRU */
+}
+
+static int b2_ref_slot(StorablePicture *ref)
+{
+  int i, victim = 0;
+  for (i = 0; i < g_nslots; i++)
+    if (g_slot[i].pic == ref && g_slot[i].poc == ref->poc && g_slot[i].stamp) { g_slot[i].stamp = ++g_clock; return i; }
+  for (i = 1; i < g_nslots; i++)
+    if (g_slot[i].stamp < g_slot[victim].stamp) victim = i;
+  b2_narrow(ref->imgY);                 /* reconstructed (deblocked) luma; the GPU rebuilds getSubImagesLuma's planes */
+  if (b2me_set_ref(g_ctx, victim, g_stage, g_W) != B2ME_OK) b2_fail("b2me_set_ref failed");
+  g_slot[victim].pic = ref; g_slot[victim].poc = ref->poc; g_slot[victim].stamp = ++g_clock; g_uploads++;
+  return victim;
+}
+
+static void b2_params(InputParameters *p_Inp, b2me_search_params *P, int lam_f, int lam_h, int lam_q, distblk min_mcost)
+{
+  memset(P, 0, sizeof(*P));
+  P->lambda_factor[0] = lam_f; P->lambda_factor[1] = lam_h; P->lambda_factor[2] = lam_q;
+  P->restrict_mode = p_Inp->full_search;
+  P->metric_h = p_Inp->MEErrorMetric[H_PEL]; P->metric_q = p_Inp->MEErrorMetric[Q_PEL];
+  P->do_subpel = 0;
+  P->min_mcost = (int64_t)min_mcost;
+}
+
+distblk full_search_motion_estimation(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor)
+{
+  Slice *currSlice = currMB->p_Slice;
+  MotionVector *mv = &mv_block->mv[(short)mv_block->list];
+  StorablePicture *ref_picture = currSlice->listX[mv_block->list + currMB->list_offset][mv_block->ref_idx];
+  int search_range = imin(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2;
+  b2me_search_params P;
+  int16_t pm[2], cm[2], out[2];
+  int64_t cost = 0;
+  int slot;
+
+  b2_ensure_ctx(currMB);
+  b2_check_config(currMB, mv_block);
+  b2_ensure_cur(currMB->p_Vid);
+  slot = b2_ref_slot(ref_picture);
+  b2_params(currMB->p_Inp, &P, lambda_factor, lambda_factor, lambda_factor, min_mcost);
+  pm[0] = pred_mv->mv_x; pm[1] = pred_mv->mv_y; cm[0] = mv->mv_x; cm[1] = mv->mv_y;
+  if (b2me_block_search(g_ctx, mv_block->pos_x, mv_block->pos_y, mv_block->blocktype, slot, pm, cm, &P, search_range,
+                        out, &cost, NULL, NULL) != B2ME_OK)
+    b2_fail("b2me_block_search failed");
+  g_calls_int++;
+  mv->mv_x = out[0]; mv->mv_y = out[1];       /* centre + spiral[best_pos]; unchanged when best_pos == 0 */
+  return (distblk)cost;
+}
+
+distblk sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, MEBlock *mv_block, distblk min_mcost, int *lambda)
+{
+  Slice *currSlice = currMB->p_Slice;
+  int list = mv_block->list;
+  MotionVector *mv = &mv_block->mv[list];
+  StorablePicture *ref_picture = currSlice->listX[list + currMB->list_offset][mv_block->ref_idx];
+  b2me_search_params P;
+  int16_t pm[2], in[2], out[2];
+  int64_t cost = 0;
+  int slot;
+
+  b2_ensure_ctx(currMB);
+  b2_check_config(currMB, mv_block);
+  if (mv_block->search_pos2 != 9 || mv_block->search_pos4 != 9) b2_fail("SubPelSearch position counts other than 9/9 are not supported");
+  b2_ensure_cur(currMB->p_Vid);
+  slot = b2_ref_slot(ref_picture);
+  b2_params(currMB->p_Inp, &P, lambda[F_PEL], lambda[H_PEL], lambda[Q_PEL], min_mcost);
+  P.do_subpel = 1;
+  pm[0] = pred->mv_x; pm[1] = pred->mv_y; in[0] = mv->mv_x; in[1] = mv->mv_y;
+  if (b2me_block_subpel(g_ctx, mv_block->pos_x, mv_block->pos_y, mv_block->blocktype, slot, pm, in, &P, (int64_t)min_mcost,
+                        out, &cost) != B2ME_OK)
+    b2_fail("b2me_block_subpel failed");
+  g_calls_sub++;
+  mv->mv_x = out[0]; mv->mv_y = out[1];
+  return (distblk)cost;
+}

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def run_lencod(yuv, W, H, frames, outdir, exe="lencod", search_mode=-1, search_range=16, nrefs=1, qp=28,
                subpel=True, restrict=2, rdo=1, extra=(), env=None, cfg=None):
     os.makedirs(outdir, exist_ok=True)
-    cfg = cfg or os.path.join(REF_JM, "bin", "encoder.cfg")
+    cfg = cfg or os.path.join(HERE, "_ref", "encoder.cfg")   # copied from JM/bin/encoder.cfg by Makefile.jm
     keys = {
         "InputFile": yuv, "SourceWidth": W, "SourceHeight": H, "OutputWidth": W, "OutputHeight": H,
         "FramesToBeEncoded": frames, "SearchMode": search_mode, "SearchRange": search_range,

@@ -1,0 +1,50 @@
+"""Drop-in test of the JM boundary (capture plan (i)): the stock JM 18.5 encoder and the same
+encoder with me_fullsearch.o replaced by integration/jm/b2me_jm_shim.c + libb2me.so must write
+byte-identical bitstreams and reconstructions on BASELINE config 1 (synthetic QCIF, IPPP, full search
++-16, 1 reference, QP 28, SAD integer + SATD sub-pel).  Both binaries are prebuilt by oracle/Makefile.jm
+in the build container (oracle/_ref/ travels to the GPU box)."""
+import os
+import tempfile
+
+import pytest
+
+from h264_b200 import synth
+from oracle import jm_run
+
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+have = all(os.path.exists(os.path.join(REF, f)) for f in ("lencod", "lencod_b2", "encoder.cfg"))
+
+
+def _encode(exe, yuv, W, H, frames, out, **kw):
+    log = jm_run.run_lencod(yuv, W, H, frames, out, exe=exe, **kw)
+    return open(os.path.join(out, "out.264"), "rb").read(), open(os.path.join(out, "rec.yuv"), "rb").read(), log
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have, reason="oracle/_ref/lencod{,_b2} not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("frames,nrefs,sr,qp", [(30, 1, 16, 28), (6, 2, 8, 36)])
+def test_lencod_with_cuda_motion_search_is_bit_identical(frames, nrefs, sr, qp):
+    W, H = 176, 144
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(W, H, frames, seed=20261018))
+        a = _encode("lencod", yuv, W, H, frames, os.path.join(d, "stock"), nrefs=nrefs, search_range=sr, qp=qp)
+        b = _encode("lencod_b2", yuv, W, H, frames, os.path.join(d, "b2"), nrefs=nrefs, search_range=sr, qp=qp,
+                    env={"B2ME_SHIM_VERBOSE": "1"})
+        assert len(a[0]) > 1000
+        assert a[0] == b[0], "bitstreams differ"
+        assert a[1] == b[1], "reconstructions differ"
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref/lencod_b2 not built")
+def test_dropin_fails_loudly_without_a_gpu():
+    """No CPU fallback behind the boundary: without a CUDA device the shim stops the encoder."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    W, H = 176, 144
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(W, H, 2, seed=1))
+        with pytest.raises(RuntimeError, match="b2me"):
+            jm_run.run_lencod(yuv, W, H, 2, os.path.join(d, "b2"), exe="lencod_b2")
