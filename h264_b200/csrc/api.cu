@@ -213,7 +213,7 @@ static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
   f.lambda_f = p->lambda_factor[0]; f.min_mcost = p->min_mcost;
   f.pred = pred; f.center = center; f.mv_int = mv_int; f.cost_int = cost_int;
   f.mb_first = mb_first; f.ref_first = ref_first; f.refs_per_mb = refs_per_mb; f.nitems = mb_count * refs_per_mb;
-  f.abs_index = abs_index; f.part_mask = mask; f.errflag = c->d_errflag; f.stats = c->d_stats;
+  f.abs_index = abs_index; f.part_mask = mask; f.errflag = c->d_errflag; f.stats = c->d_stats; f.one = 1;
   {
     FamilyTimer t(c, 0, s);
     B2_CUDA_CHECK(c, launch_sad_fs(f, c->sm_count, s, &c->fs_smem_bytes));

@@ -50,6 +50,7 @@ struct FsArgs {
   int abs_index;         // 1: arrays indexed ((mb*nrefs+ref)*41+p), 0: (item*41+p)
   unsigned long long part_mask;           // active partitions
   int *errflag;
+  int one;               // 1 (a run-time constant the compiler cannot fold, see sad_fs.cu addmin2)
   unsigned long long *stats;   // optional: [0] exact re-evaluations, [1] window passes, [2] items
 };
 

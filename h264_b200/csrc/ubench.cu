@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) k_ubench(uint32_t *out, int iters, uint32
     for (int u = 0; u < 4; u++) {
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        if (KIND == 0 || KIND == 1 || KIND == 2 || KIND == 3 || KIND == 7 || KIND >= 8) a[i] = sad4(x[i], b, a[i]);
+        if (KIND == 0 || KIND == 1 || KIND == 2 || KIND == 3 || KIND == 7 || (KIND >= 8 && KIND != 19)) a[i] = sad4(x[i], b, a[i]);
         if (KIND == 8) asm volatile("shf.r.clamp.b32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(8));          // SHF (funnel shift)
         if (KIND == 9) asm volatile("prmt.b32 %0, %0, %1, 0x4321;" : "+r"(y[i]) : "r"(b));                      // PRMT
         if (KIND == 10) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(b), "r"(seed));        // LOP3, independent chain
@@ -31,6 +31,14 @@ __global__ void __launch_bounds__(256) k_ubench(uint32_t *out, int iters, uint32
         if (KIND == 12) y[i] = sm[(threadIdx.x + i * 32 + it) & 255];                                            // LDS.32, independent
         if (KIND == 13) asm volatile("add.u32 %0, %0, %1;" : "+r"(y[i]) : "r"(b));                               // IADD, independent chain
         if (KIND == 14) y[i] = y[i] * 5u + seed;                                                                 // IMAD, independent chain
+        if (KIND == 15 || KIND == 19) y[i] = __viaddmin_s16x2(x[i], b, y[i]);                                     // VIADDMNMX.S16x2
+        if (KIND == 16) y[i] = __dp2a_lo(y[i], 0x0101u, b);                                                      // IDP.2A
+        if (KIND == 17) { uint2 v = *reinterpret_cast<const uint2 *>(&sm[(2 * (threadIdx.x + i * 32 + it)) & 254]); y[i] = v.x ^ v.y; }   // LDS.64 (+LOP)
+        if (KIND == 18) y[i] = x[i] * 65536u + y[i];                                                             // IMAD (pack)
+        if (KIND == 20) y[i] = __vimin3_s16x2(x[i], b + i, y[i]);                                                // VIMNMX3.S16x2
+        if (KIND == 21) asm volatile("add.s16x2 %0, %0, %1;" : "+r"(y[i]) : "r"(b));                             // VIADD.16x2
+        if (KIND == 22) asm volatile("mad.lo.u32 %0, %1, 1, %0;" : "+r"(y[i]) : "r"(b));                         // add on the FMA pipe?
+        if (KIND == 23) asm volatile("min.s16x2 %0, %0, %1;" : "+r"(y[i]) : "r"(b + i));                         // VIMNMX.S16x2
         if (KIND == 1 || KIND == 5) x[i] = x[i] * 3u + b;                                   // IMAD
         if (KIND == 2 || KIND == 4) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(b)); // IADD3
         if (KIND == 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(b), "r"(a[(i + 1) & 7]));
@@ -74,7 +82,16 @@ cudaError_t ubench(int kind, int iters, double *gops)
       case 11: k_ubench<11><<<grid, block>>>(out, iters, rep); break;
       case 12: k_ubench<12><<<grid, block>>>(out, iters, rep); break;
       case 13: k_ubench<13><<<grid, block>>>(out, iters, rep); break;
-      default: k_ubench<14><<<grid, block>>>(out, iters, rep); break;
+      case 14: k_ubench<14><<<grid, block>>>(out, iters, rep); break;
+      case 15: k_ubench<15><<<grid, block>>>(out, iters, rep); break;
+      case 16: k_ubench<16><<<grid, block>>>(out, iters, rep); break;
+      case 17: k_ubench<17><<<grid, block>>>(out, iters, rep); break;
+      case 18: k_ubench<18><<<grid, block>>>(out, iters, rep); break;
+      case 19: k_ubench<19><<<grid, block>>>(out, iters, rep); break;
+      case 20: k_ubench<20><<<grid, block>>>(out, iters, rep); break;
+      case 21: k_ubench<21><<<grid, block>>>(out, iters, rep); break;
+      case 22: k_ubench<22><<<grid, block>>>(out, iters, rep); break;
+      default: k_ubench<23><<<grid, block>>>(out, iters, rep); break;
     }
     cudaEventRecord(e1);
     e = cudaEventSynchronize(e1);

@@ -5,7 +5,7 @@ import numpy as np
 from h264_b200 import api, synth
 
 out = {}
-names = ["vabsdiff4", "vabsdiff4+imad", "vabsdiff4+iadd3", "vabsdiff4+lop3", "iadd3", "imad", "vimnmx16x2", "vabsdiff4+lds", "v+shf", "v+prmt", "v+lop3i", "v+vimnmx", "v+lds32", "v+iadd", "v+imad"]
+names = ["vabsdiff4", "vabsdiff4+imad", "vabsdiff4+iadd3", "vabsdiff4+lop3", "iadd3", "imad", "vimnmx16x2", "vabsdiff4+lds", "v+shf", "v+prmt", "v+lop3i", "v+vimnmx", "v+lds32", "v+iadd", "v+imad", "v+viaddmnmx", "v+idp2a", "v+lds64", "v+imadpack", "viaddmnmx", "v+vimnmx3_16x2", "v+viadd16x2", "v+mad1", "v+vimnmx_s16x2"]
 for k, n in (enumerate(names) if os.environ.get("UBENCH") else []):
     out[n] = api.ubench(k, 4000)
     print(f"ubench {n}: {out[n]:.1f} G lane-ops/s", flush=True)
