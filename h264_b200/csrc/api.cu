@@ -43,6 +43,27 @@ extern "C" int b2me_create(b2me_ctx **out, int device, int width, int height, in
   B2_CUDA_CHECK(c, cudaMalloc(&c->d_stage, (size_t)width * height));
   B2_CUDA_CHECK(c, cudaMalloc(&c->d_planes, c->plane_size * 16 * nrefs));
   B2_CUDA_CHECK(c, cudaMemset(c->d_planes, 0, c->plane_size * 16 * nrefs));
+  // search planes of the integer full search + their TMA descriptor (box = one window copy)
+  c->spad = ((search_range + 32) + 15) & ~15;
+  c->Wq = width + 2 * c->spad; c->Hq = height + 2 * c->spad;
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_spl, (size_t)c->Wq * c->Hq * 16 * nrefs));
+  B2_CUDA_CHECK(c, cudaMemset(c->d_spl, 0, (size_t)c->Wq * c->Hq * 16 * nrefs));
+  {
+    const FsGeom G = fs_geom_host(search_range);
+    const cuuint64_t dims[3] = {(cuuint64_t)c->Wq, (cuuint64_t)c->Hq, (cuuint64_t)nrefs * 16};
+    const cuuint64_t strides[2] = {(cuuint64_t)c->Wq, (cuuint64_t)c->Wq * c->Hq};
+    const cuuint32_t box[3] = {(cuuint32_t)G.pitch, (cuuint32_t)G.rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult cr = cuTensorMapEncodeTiled(&c->tmap_spl, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d_spl, dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+      return B2ME_ECUDA;
+    }
+    B2_CUDA_CHECK(c, cudaMalloc(&c->d_tmap_spl, sizeof(CUtensorMap)));
+    B2_CUDA_CHECK(c, cudaMemcpy(c->d_tmap_spl, &c->tmap_spl, sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  }
   B2_CUDA_CHECK(c, cudaMalloc(&c->d_pred, n * 2 * sizeof(int16_t)));
   B2_CUDA_CHECK(c, cudaMalloc(&c->d_center, n * 2 * sizeof(int16_t)));
   B2_CUDA_CHECK(c, cudaMalloc(&c->d_mv_int, n * 2 * sizeof(int16_t)));
@@ -67,7 +88,7 @@ extern "C" void b2me_destroy(b2me_ctx *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_cur); cudaFree(c->d_stage); cudaFree(c->d_planes);
+  cudaFree(c->d_cur); cudaFree(c->d_stage); cudaFree(c->d_planes); cudaFree(c->d_spl); cudaFree(c->d_tmap_spl);
   cudaFree(c->d_pred); cudaFree(c->d_center); cudaFree(c->d_mv_int); cudaFree(c->d_mv_sub);
   cudaFree(c->d_cost_int); cudaFree(c->d_cost_sub); cudaFree(c->d_io16); cudaFree(c->d_io64);
   cudaFreeHost(c->h_io16); cudaFreeHost(c->h_io64); cudaFree(c->d_errflag); cudaFree(c->d_stats);
@@ -136,7 +157,8 @@ static int build_planes(b2me_ctx *c, int ref_idx, const uint8_t *luma_dev, int s
 {
   FamilyTimer t(c, 1, s);
   B2_CUDA_CHECK(c, launch_subpel_planes(luma_dev, stride, c->W, c->H, c->d_planes + (size_t)ref_idx * 16 * c->plane_size, s));
-  c->launches += 2;
+  B2_CUDA_CHECK(c, launch_search_plane(luma_dev, stride, c->W, c->H, c->d_spl + (size_t)ref_idx * 16 * c->Wq * c->Hq, c->Wq, c->Hq, c->spad, s));
+  c->launches += 3;
   t.stop();
   return B2ME_OK;
 }
@@ -207,16 +229,17 @@ static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
                       int16_t *mv_int, long long *cost_int, int16_t *mv_sub, long long *cost_sub, cudaStream_t s)
 {
   FsArgs f;
-  f.cur = c->d_cur; f.cur_pitch = c->W; f.planes = c->d_planes; f.plane_size = c->plane_size;
-  f.W = c->W; f.H = c->H; f.Wp = c->Wp; f.Hp = c->Hp; f.mbw = c->mbw; f.nrefs = c->nrefs;
+  f.cur = c->d_cur; f.cur_pitch = c->W; f.spl = c->d_spl; f.Wq = c->Wq; f.Hq = c->Hq; f.spad = c->spad;
+  f.W = c->W; f.H = c->H; f.mbw = c->mbw; f.nrefs = c->nrefs;
   f.R = c->R; f.restrict_mode = sr_override >= 0 ? -1 : p->restrict_mode; f.sr_override = sr_override;
   f.lambda_f = p->lambda_factor[0]; f.min_mcost = p->min_mcost;
   f.pred = pred; f.center = center; f.mv_int = mv_int; f.cost_int = cost_int;
   f.mb_first = mb_first; f.ref_first = ref_first; f.refs_per_mb = refs_per_mb; f.nitems = mb_count * refs_per_mb;
   f.abs_index = abs_index; f.part_mask = mask; f.errflag = c->d_errflag; f.stats = c->d_stats; f.one = 1;
+  { const char *e = getenv("B2ME_FS_NOTMA"); f.flags = (e && e[0] == '1') ? 1 : 0; }
   {
     FamilyTimer t(c, 0, s);
-    B2_CUDA_CHECK(c, launch_sad_fs(f, c->sm_count, s, &c->fs_smem_bytes));
+    B2_CUDA_CHECK(c, launch_sad_fs(f, c->d_tmap_spl, c->sm_count, s, &c->fs_smem_bytes));
     c->launches++;
     t.stop();
   }

@@ -1,6 +1,7 @@
 // b2_ctx.h -- internal context of libb2me (not part of the C ABI).
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/b2me.h"
 
@@ -11,6 +12,10 @@ struct b2me_ctx {
   uint8_t *d_cur;               // [H][W]
   uint8_t *d_planes;            // [nrefs][16][Hp][Wp]  index [yy*4+xx]
   uint8_t *d_stage;             // [H][W] staging for host uploads
+  uint8_t *d_spl;               // [nrefs][16][Hq][Wq] search planes: integer picture with an edge-replicated pad of spad, 16 byte shifts
+  int Wq, Hq, spad;
+  CUtensorMap tmap_spl;         // 3-D tensor map over d_spl (x, y, ref), box = one window copy
+  CUtensorMap *d_tmap_spl;      // its device copy (global memory, 64-byte aligned)
   // device mirrors for the host-pointer batch API
   int16_t *d_pred, *d_center, *d_mv_int, *d_mv_sub;
   long long *d_cost_int, *d_cost_sub;
@@ -36,8 +41,8 @@ namespace b2 {
 
 struct FsArgs {
   const uint8_t *cur; int cur_pitch;
-  const uint8_t *planes; size_t plane_size;   // integer plane of ref r = planes + r*16*plane_size
-  int W, H, Wp, Hp, mbw, nrefs;
+  const uint8_t *spl; int Wq, Hq, spad;       // search planes [nrefs][16][Hq][Wq]: plane s = integer picture (edge-replicated pad of spad) shifted left by s bytes
+  int W, H, mbw, nrefs;
   int R;                 // half window (pel)
   int restrict_mode;     // get_search_range mode; -1: use sr_override for every partition
   int sr_override;
@@ -50,8 +55,18 @@ struct FsArgs {
   int abs_index;         // 1: arrays indexed ((mb*nrefs+ref)*41+p), 0: (item*41+p)
   unsigned long long part_mask;           // active partitions
   int *errflag;
+  int flags;             // bit 0: stage every window with the clamped (non-TMA) path (debug, B2ME_FS_NOTMA=1)
   int one;               // 1 (a run-time constant the compiler cannot fold, see sad_fs.cu addmin2)
   unsigned long long *stats;   // optional: [0] exact re-evaluations, [1] window passes, [2] items
+};
+
+struct FsGeom {                  // window geometry of a search range (sad_fs.cu fs_geom)
+  int pitch;                     // bytes per window row: == 32 or 96 (mod 128)
+  int rows;                      // physical rows per copy (logical rows + 3)
+  int copy_bytes;                // bytes per copy (multiple of 128)
+  int slot_bytes;                // 4 copies = one window buffer
+  int total;                     // dynamic shared memory (two buffers)
+  int threads;                   // CTA size
 };
 
 struct SubArgs {
@@ -69,7 +84,9 @@ struct SubArgs {
 };
 
 cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, cudaStream_t s);
-cudaError_t launch_sad_fs(const FsArgs &a, int sm_count, cudaStream_t s, int *smem_bytes_out);
+cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, cudaStream_t s, int *smem_bytes_out);
+FsGeom fs_geom_host(int R);
+cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, cudaStream_t s);
 cudaError_t launch_subpel_refine(const SubArgs &a, cudaStream_t s);
 cudaError_t ubench(int kind, int iters, double *gops);
 

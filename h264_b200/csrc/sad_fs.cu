@@ -20,16 +20,19 @@
 //  * Partitions may have different search centres.  Partitions are grouped by centre; each
 //    group is one pass over its own window.
 //
-// Work decomposition.  One CTA (4 warps) works on FS_NSLOT (MB, ref) items at a time, each with
-// its own window in shared memory.  A warp-task = 64 window columns x K rows of candidates of one
-// item: lane l owns the column pair (dx, dx+4), dx = 8*(l>>2) + (l&3), and walks K consecutive
-// rows dy0..dy0+K-1 in lock step with a sliding window of K reference rows in registers, so a
-// reference row costs three LDS.64 per 2K candidates and a current row one broadcast LDS.128.
-// Warps pull tasks from a shared counter and never meet at a barrier inside an item.
+// Work decomposition.  Persistent CTAs, two window buffers each.  Buffer b of CTA i walks the items
+// i + (2k+b)*gridDim; a "unit" is one (item, centre group) and lives in one buffer: its window (TMA),
+// per-partition state and filter constants.  A warp-task = 64 window columns x K rows of candidates:
+// lane l owns the column pair (dx, dx+4), dx = 8*(l>>2) + (l&3), and walks K consecutive rows
+// dy0..dy0+K-1 in lock step with a sliding window of K reference rows in registers, so a reference row
+// costs three LDS.64 per 2K candidates and a current row one broadcast LDS.128.  Warps pull tasks of
+// whichever buffer is ready from a shared counter and never meet at a CTA barrier; the warp that
+// completes the last task of a unit writes its results and sets up the buffer's next unit (parameters,
+// TMA of the window, tables, exact pre-pass) while the other warps work on the other buffer.
 //
 // Filter.  After every 4 rows the 4x4 SADs of a block row are packed two per register (IMAD on the
-// FMA pipe), tree-summed, and folded into one running minimum per candidate with one
-// VIADDMNMX.S16x2 per pair of partitions:   run = min(run, sad_p - B_p - 1),  B_p = best_p >> 5.
+// FMA pipe), tree-summed (VIADD.16x2), and folded into one running minimum per candidate:
+//        run = min(run, sad_p - B_p - 1),  B_p = best_p >> 5      (IMAD add + VIMNMX.S16x2)
 // At the end  run + m < 0  (m = floor(lambda*minbits/32), a lower bound of the candidate's mv
 // cost over the partitions' predictors) is a NECESSARY condition for (cost,pos) < best of some
 // partition, so nothing that could win is dropped.  Survivors (rare) are re-evaluated exactly by
@@ -39,28 +42,25 @@
 // Shared-memory window: 4 byte-shifted copies (copy c holds the window shifted left by c bytes) so
 // that the 16+4 pixels of a column pair are three aligned 64-bit words; copy c is stored c rows
 // lower so that, with a row pitch of 24 (mod 32) words, the four copies start 8 banks apart while
-// every copy stays 128-byte aligned (TMA destination rule).
+// every copy stays 128-byte aligned (TMA destination rule).  Each copy is one cp.async.bulk.tensor
+// box.  A TMA box must START on a 16-byte boundary in global memory (a box at an odd byte column raises
+// "illegal instruction", tools/tma_probe), so the reference's search plane (edge-replicated integer
+// picture with a pad of R+32, k_search_plane) is kept in HBM as 16 byte-shifted planes,
+// plane_s[y][x] = P[y][x+s]: copy c of a window at column x0 is the box at column (x0+c)&~15 of plane
+// (x0+c)&15.  Windows that leave the search plane (centres more than 32 pel outside the picture) are
+// staged by the setting-up warp with per-pixel clamps.
 #include "b2_common.cuh"
 #include "b2_ctx.h"
 
 namespace b2 {
 
 constexpr int FS_K = 5;          // candidate rows per task (lock step)
-constexpr int FS_NW = 4;         // warps per CTA
-constexpr int FS_NT = FS_NW * 32;
 constexpr int FS_PRE = 0;        // radius of the exact pre-pass around the centres (initial bounds)
 constexpr int FS_SMAX = 8;       // partitions whose centres lie within an 8-pel box share one window pass
 constexpr int FS_BMAX = 12;      // a trailing column block of at most this width is walked row-major (type B)
 constexpr int FS_MCAP = 2047;    // cap of each half of the mv-cost lower bound (keeps packed sums in range)
+constexpr int FS_MAXW = 12;      // max warps per CTA
 
-struct FsGeom {                  // window geometry of a search range (host + device)
-  int pitch;                     // bytes per window row: == 32 or 96 (mod 128)
-  int rows;                      // physical rows per copy (logical rows + 3)
-  int copy_bytes;                // bytes per copy (multiple of 128)
-  int slot_bytes;                // 4 copies
-  int nslot;                     // items per CTA
-  int total;                     // dynamic shared memory
-};
 __host__ __device__ inline FsGeom fs_geom(int R)
 {
   FsGeom G;
@@ -73,30 +73,35 @@ __host__ __device__ inline FsGeom fs_geom(int R)
   G.rows = FS_K * ngy + 15 + 3;
   G.copy_bytes = (G.rows * G.pitch + 127) & ~127;
   G.slot_bytes = 4 * G.copy_bytes;
-  G.nslot = G.slot_bytes <= 40 * 1024 ? 2 : 1;
-  G.total = G.nslot * G.slot_bytes;
+  G.total = 2 * G.slot_bytes;
+  G.threads = G.pitch == 96 ? 128 : 384;
   return G;
 }
 
-struct __align__(16) FsSlot {     // per-item state
+template <int PITCH>
+struct __align__(16) FsSlotT {    // per-buffer state: one (item, centre group) unit at a time
+  static constexpr int NTAB = PITCH == 96 ? 88 : 152;
   uint32_t cur[64];               // current MB, 16 rows x 4 words
   unsigned long long best[NPART]; // (cost << 20) | pos
+  unsigned long long mbar;        // TMA completion barrier of this buffer
   uint32_t Cw[20];                // packed filter constants, see cmap()
   int C16;                        // 16x16: -B-1
-  unsigned short mxs[160], mys[160];   // per window column / row: lower bound of lambda*bits >> 5
+  unsigned short mxs[NTAB], mys[NTAB];   // per window column / row: lower bound of lambda*bits >> 5 (also clustering scratch)
   short pcx[NPART], pcy[NPART];   // centre (relative MV, quarter-pel)
   short ppx[NPART], ppy[NPART];   // predictor (quarter-pel)
   short psr[NPART];               // per-partition search range (pel)
   signed char pgrp[NPART];        // centre group of the partition (-1 inactive)
   signed char pex[NPART], pey[NPART];   // centre of the partition relative to its group's box origin (pel)
-  short gx0[NPART], gy0[NPART], gx1[NPART], gy1[NPART];   // centre bounding box of group g (pel)
-  int red[2][4];
-  int ngroups;
-  int active;                     // slot holds an item
-  int mb, ref; unsigned base_lo, base_hi;
-  // current group
+  // pipeline
+  int ready_epoch;                // epoch whose window + setup are complete (written last, read first)
+  int next;                       // (epoch << 20) | tasks claimed
+  int done;                       // tasks completed in the current epoch
+  int ended;                      // no more items for this buffer
+  int epoch, tma_uses;
+  // current unit
+  int item, mb, ref, g, ngroups; unsigned base_lo, base_hi;
+  int gx0, gy0;                   // origin of the group's centre box (pel)
   int ncx, ncy, ngy, gc, ncbA, ntaskA, npb, ntask;
-  int ppxmin, ppxmax, ppymin, ppymax;
 };
 
 struct FsWarp { unsigned short sat[2][28]; };
@@ -113,7 +118,8 @@ __device__ __forceinline__ int cmap(int p)
   return -1;
 }
 
-__device__ __forceinline__ void set_threshold(FsSlot &S, int p, unsigned long long key)
+template <class SLOT>
+__device__ __forceinline__ void set_threshold(SLOT &S, int p, unsigned long long key)
 {
   const unsigned long long b = (key >> 20) >> 5;
   const int c = cmap(p);
@@ -149,8 +155,8 @@ __device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterp
 
 // Exact evaluation of two window candidates (one per half warp; the second may be absent) of slot S
 // for every partition of group g.  Called by a whole warp.
-template <int PITCH>
-__device__ __noinline__ void fs_exact2(FsSlot &S, FsWarp &ws, const uint8_t *win, int copy_bytes, const uint32_t *pgt,
+template <int PITCH, class SLOT>
+__device__ __noinline__ void fs_exact2(SLOT &S, FsWarp &ws, const uint8_t *win, int copy_bytes, const uint32_t *pgt,
                                        int dx0, int dy0, int dx1, int dy1, bool valid1, int R, int g, int lambda_f)
 {
   const int lane = threadIdx.x & 31, half = lane >> 4, k = lane & 15, bx = k & 3, by = k >> 2;
@@ -200,8 +206,8 @@ __device__ __forceinline__ void ld3(uint32_t (&r)[6], const uint8_t *p)
 
 // One lane-job: candidates (dx, dy0..dy0+K-1) and (dx+4, same rows); wb = lane address of window row dy0.
 // Returns the pass mask: bit j = column a row j, bit K+j = column b row j.
-template <int K, int PITCH>
-__device__ __forceinline__ uint32_t fs_task(const FsSlot &S, const uint8_t *wb, uint32_t mxa, uint32_t mxb, const unsigned short *mys, uint32_t one)
+template <int K, int PITCH, class SLOT>
+__device__ __forceinline__ uint32_t fs_task(const SLOT &S, const uint8_t *wb, uint32_t mxa, uint32_t mxb, const unsigned short *mys, uint32_t one)
 {
   const uint4 *cur = reinterpret_cast<const uint4 *>(S.cur);
   uint32_t rw[K][6];
@@ -275,329 +281,365 @@ __device__ __forceinline__ uint32_t fs_task(const FsSlot &S, const uint8_t *wb, 
   return pass;
 }
 
-template <int PITCH>
-__global__ void __launch_bounds__(FS_NT, 3) k_sad_fs(const FsArgs a)
+// ---- mbarrier / TMA (PTX) ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(void *bar, uint32_t parity)
 {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, void *bar, int x, int y, int z)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+struct FsCtaStats { int err, nhits, ngroups, nitems; };
+
+// Called by ONE warp when the unit of buffer S is complete (or at kernel start): writes the results of a
+// finished item, fetches the buffer's next unit (next centre group of the same item, else the next item
+// of this buffer's sequence) and sets it up: parameters, centre groups, window (TMA), filter constants,
+// mv-cost tables, exact pre-pass over the centres' box.  Publishes the unit with ready_epoch, then arms
+// the task counter.
+template <int PITCH, class SLOT>
+__device__ __noinline__ void fs_advance(SLOT &S, FsWarp &ws, uint8_t *win, const uint32_t *pgt, const FsArgs &a,
+                                        const CUtensorMap *tm, FsCtaStats *st)
+{
+  constexpr int K = FS_K;
+  const FsGeom G = fs_geom(a.R);
+  const int lane = threadIdx.x & 31, R = a.R;
+  for (;;) {
+    int g;
+    if (S.item >= 0 && S.g + 1 < S.ngroups) g = S.g + 1;
+    else {
+      if (S.item >= 0 && S.ngroups > 0) {          // ---- results of the finished item ----
+        const size_t base = ((size_t)S.base_hi << 32) | S.base_lo;
+        for (int p = lane; p < NPART; p += 32) {
+          if (!((a.part_mask >> p) & 1ull)) continue;
+          const unsigned long long key = S.best[p];
+          const int pos = (int)(key & 0xfffffull);
+          int sx, sy; spiral_xy(pos, &sx, &sy);
+          a.mv_int[(base + p) * 2]     = (int16_t)(S.pcx[p] + 4 * sx);
+          a.mv_int[(base + p) * 2 + 1] = (int16_t)(S.pcy[p] + 4 * sy);
+          long long cost = (long long)(key >> 20);
+          if (pos == 0 && cost == (1ll << 42) && a.min_mcost > (1ll << 42)) cost = a.min_mcost;   // bound never beaten
+          a.cost_int[base + p] = cost;
+        }
+        if (lane == 0) { atomicAdd(&st->ngroups, S.ngroups); atomicAdd(&st->nitems, 1); }
+      }
+      __syncwarp();
+      const int item = (S.item >= 0 ? S.item : S.item + 0x40000000) + 2 * (int)gridDim.x;   // first call: item encodes first - 2*grid - 2^30
+      if (item >= a.nitems) {
+        if (lane == 0) { S.item = -1; S.ngroups = 0; __threadfence_block(); *reinterpret_cast<volatile int *>(&S.ended) = 1; }
+        __syncwarp();
+        return;
+      }
+      // ---- per-partition parameters, current MB ----
+      const int mb = a.mb_first + item / a.refs_per_mb, ref = a.ref_first + item % a.refs_per_mb;
+      const int mbx = mb % a.mbw, mby = mb / a.mbw;
+      const size_t base = (a.abs_index ? ((size_t)mb * a.nrefs + ref) : (size_t)item) * NPART;
+      int bx0 = 0x7fff, bx1 = -0x7fff, by0 = 0x7fff, by1 = -0x7fff;
+      for (int p = lane; p < NPART; p += 32) {
+        const bool act = (a.part_mask >> p) & 1ull;
+        const PartGeom gm = part_geom(p);
+        const int cx = a.center[(base + p) * 2], cy = a.center[(base + p) * 2 + 1];
+        S.pcx[p] = (short)cx; S.pcy[p] = (short)cy;
+        S.ppx[p] = a.pred[(base + p) * 2];   S.ppy[p] = a.pred[(base + p) * 2 + 1];
+        S.psr[p] = (short)(a.restrict_mode < 0 ? a.sr_override : block_search_range(R, a.restrict_mode, ref, gm.bt));
+        S.pgrp[p] = act ? 0 : -1;
+        const long long mm = a.min_mcost < 0 ? 0 : (a.min_mcost > (1ll << 42) ? (1ll << 42) : a.min_mcost);
+        S.best[p] = ((unsigned long long)mm << 20);
+        if (act) {
+          if ((cx | cy) & 3) st->err = 1;          // sub-pel centres are not a full-search input
+          bx0 = min(bx0, cx >> 2); bx1 = max(bx1, cx >> 2); by0 = min(by0, cy >> 2); by1 = max(by1, cy >> 2);
+        }
+      }
+      for (int t = lane; t < 64; t += 32)
+        S.cur[t] = *reinterpret_cast<const uint32_t *>(a.cur + (size_t)(mby * 16 + (t >> 2)) * a.cur_pitch + mbx * 16 + (t & 3) * 4);
+      bx0 = __reduce_min_sync(0xffffffffu, bx0); bx1 = __reduce_max_sync(0xffffffffu, bx1);
+      by0 = __reduce_min_sync(0xffffffffu, by0); by1 = __reduce_max_sync(0xffffffffu, by1);
+      int ng = bx1 >= bx0 ? 1 : 0;
+      __syncwarp();
+      // ---- cluster partitions whose centres fit in one FS_SMAX box (usually all of them) ----
+      if (ng && (bx1 - bx0 > FS_SMAX || by1 - by0 > FS_SMAX)) {      // general case: greedy clustering (serial, rare)
+        if (lane == 0) {
+          short *gx0 = reinterpret_cast<short *>(S.mxs), *gx1 = gx0 + NPART, *gy0 = gx1 + NPART, *gy1 = gy0 + NPART;   // scratch
+          ng = 0;
+          for (int p = 0; p < NPART; p++) {
+            if (S.pgrp[p] < 0) continue;
+            const int cx = S.pcx[p] >> 2, cy = S.pcy[p] >> 2;
+            int gg = -1;
+            for (int q = 0; q < ng; q++) {
+              const int nx0 = min((int)gx0[q], cx), nx1 = max((int)gx1[q], cx), ny0 = min((int)gy0[q], cy), ny1 = max((int)gy1[q], cy);
+              if (nx1 - nx0 <= FS_SMAX && ny1 - ny0 <= FS_SMAX) { gg = q; gx0[q] = nx0; gx1[q] = nx1; gy0[q] = ny0; gy1[q] = ny1; break; }
+            }
+            if (gg < 0) { gg = ng++; gx0[gg] = gx1[gg] = cx; gy0[gg] = gy1[gg] = cy; }
+            S.pgrp[p] = (signed char)gg;
+          }
+        }
+        ng = __shfl_sync(0xffffffffu, ng, 0);
+      }
+      if (lane == 0) {
+        S.item = item; S.mb = mb; S.ref = ref; S.base_lo = (unsigned)base; S.base_hi = (unsigned)((unsigned long long)base >> 32);
+        S.ngroups = ng; S.g = 0;
+      }
+      __syncwarp();
+      if (ng == 0) continue;                       // no active partition: nothing to search, nothing to write
+      g = 0;
+    }
+    // ---- set up centre group g of the current item ----
+    int gx0 = 0x7fff, gx1 = -0x7fff, gy0 = 0x7fff, gy1 = -0x7fff, qx0 = 0x7fff, qx1 = -0x7fff, qy0 = 0x7fff, qy1 = -0x7fff;
+    for (int p = lane; p < NPART; p += 32) {
+      if (S.pgrp[p] != g) continue;
+      const int cx = S.pcx[p] >> 2, cy = S.pcy[p] >> 2, px = S.ppx[p], py = S.ppy[p];
+      gx0 = min(gx0, cx); gx1 = max(gx1, cx); gy0 = min(gy0, cy); gy1 = max(gy1, cy);
+      qx0 = min(qx0, px); qx1 = max(qx1, px); qy0 = min(qy0, py); qy1 = max(qy1, py);
+    }
+    gx0 = __reduce_min_sync(0xffffffffu, gx0); gx1 = __reduce_max_sync(0xffffffffu, gx1);
+    gy0 = __reduce_min_sync(0xffffffffu, gy0); gy1 = __reduce_max_sync(0xffffffffu, gy1);
+    qx0 = __reduce_min_sync(0xffffffffu, qx0); qx1 = __reduce_max_sync(0xffffffffu, qx1);
+    qy0 = __reduce_min_sync(0xffffffffu, qy0); qy1 = __reduce_max_sync(0xffffffffu, qy1);
+    const int spanx = gx1 - gx0, spany = gy1 - gy0;
+    const int ncx = 2 * R + 1 + spanx, ncy = 2 * R + 1 + spany;
+    const int ngy = (ncy + K - 1) / K;
+    const int ncb = (ncx + 63) >> 6, wlast = ncx - 64 * (ncb - 1);
+    const int ncbA = wlast <= FS_BMAX ? ncb - 1 : ncb;
+    int npb = 0;
+    if (ncbA < ncb) npb = wlast <= 4 ? wlast : (wlast <= 8 ? 4 : wlast - 4);
+    const int ntask = ncbA * ngy + (npb * ngy + 31) / 32;
+    const int mbx = S.mb % a.mbw, mby = S.mb / a.mbw;
+    const int x0 = mbx * 16 + gx0 - R + a.spad, y0 = mby * 16 + gy0 - R + a.spad;
+    const bool inside = x0 >= 0 && y0 >= 0 && x0 + ncx + 15 <= a.Wq && y0 + ncy + 15 <= a.Hq && !(a.flags & 1);
+    const int ep = S.epoch + 1;
+    if (inside) {                                  // ---- window: four TMA boxes (copy c starts c bytes right, c rows up) ----
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&S.mbar, 4u * PITCH * G.rows);
+#pragma unroll
+        for (int c = 0; c < 4; c++)      // a TMA box must start on a 16-byte boundary: take plane (x0+c)&15 at the aligned column
+          tma_load_3d(win + c * G.copy_bytes, tm, &S.mbar, (x0 + c) & ~15, y0 - c, S.ref * 16 + ((x0 + c) & 15));
+      }
+    } else {                                       // window leaves the search plane: per-pixel coordinate clamp
+      const uint8_t *plane = a.spl + (size_t)S.ref * 16 * a.Wq * a.Hq;     // shift-0 plane
+      const int nrows = K * ngy + 15, wpw = PITCH >> 2;
+      for (int r = 0; r < nrows; r++) {
+        const uint8_t *grow = plane + (size_t)iclamp(y0 + r, 0, a.Hq - 1) * a.Wq;
+        for (int j = lane; j < wpw; j += 32) {
+          uint32_t b[7];
+#pragma unroll
+          for (int k = 0; k < 7; k++) b[k] = grow[iclamp(x0 + 4 * j + k, 0, a.Wq - 1)];
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+            reinterpret_cast<uint32_t *>(win + c * G.copy_bytes + (r + c) * PITCH)[j] = b[c] | (b[c + 1] << 8) | (b[c + 2] << 16) | (b[c + 3] << 24);
+        }
+      }
+    }
+    // ---- filter constants: partitions of other groups never pass ----
+    if (lane < 20) S.Cw[lane] = 0;
+    if (lane == 20) S.C16 = 0;
+    __syncwarp();
+    for (int p = lane; p < NPART; p += 32) {
+      if (S.pgrp[p] != g) continue;
+      S.pex[p] = (signed char)((S.pcx[p] >> 2) - gx0); S.pey[p] = (signed char)((S.pcy[p] >> 2) - gy0);
+      set_threshold(S, p, S.best[p]);
+    }
+    // ---- lower bound of the mv cost per window column / row: every partition of the group sees the same
+    //      displacement 4*(g0 + d - R); bits is monotone in |mv - pred|, so the distance to the predictors'
+    //      [min,max] interval bounds every partition's term from below ----
+    for (int i = lane; i < ncx + ncy + K + 4; i += 32) {
+      const bool isy = i >= ncx + 4;
+      const int d = isy ? i - ncx - 4 : i;
+      const int mv = 4 * ((isy ? gy0 : gx0) + d - R);
+      const int lo = isy ? qy0 : qx0, hi = isy ? qy1 : qx1;
+      const int dist = max(0, max(lo - mv, mv - hi));
+      const long long v = ((long long)a.lambda_f * mvbits(dist)) >> 5;
+      (isy ? S.mys : S.mxs)[d] = (unsigned short)(v > FS_MCAP ? FS_MCAP : v);
+    }
+    if (lane == 0) {
+      S.g = g; S.gx0 = gx0; S.gy0 = gy0;
+      S.ncx = ncx; S.ncy = ncy; S.ngy = ngy; S.gc = min(ngy - 1, (R + (spany >> 1)) / K);
+      S.ncbA = ncbA; S.ntaskA = ncbA * ngy; S.npb = npb; S.ntask = ntask;
+      S.done = 0; S.epoch = ep;
+    }
+    __syncwarp();
+    if (inside) {
+      const uint32_t parity = (uint32_t)S.tma_uses & 1u;
+      while (!mbar_try_wait(&S.mbar, parity)) { }
+      __syncwarp();
+      if (lane == 0) S.tma_uses++;
+    }
+    __syncwarp();
+    // ---- initial bounds: exact pre-pass over the centres' box ----
+    {
+      const int xlo = max(0, R - FS_PRE), ylo = max(0, R - FS_PRE);
+      const int pw = min(ncx - 1, R + spanx + FS_PRE) - xlo + 1, ph = min(ncy - 1, R + spany + FS_PRE) - ylo + 1;
+      const int total = pw * ph;
+      for (int i0 = 0; i0 < total; i0 += 2) {
+        const int i1 = i0 + 1;
+        const bool v1 = i1 < total;
+        const int dx0 = xlo + i0 % pw, dy0 = ylo + i0 / pw;
+        const int dx1 = v1 ? xlo + i1 % pw : dx0, dy1 = v1 ? ylo + i1 / pw : dy0;
+        fs_exact2<PITCH>(S, ws, win, G.copy_bytes, pgt, dx0, dy0, dx1, dy1, v1, R, g, a.lambda_f);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      *reinterpret_cast<volatile int *>(&S.ready_epoch) = ep;
+      __threadfence_block();
+      atomicExch(&S.next, (ep & 0x7ff) << 20);
+    }
+    __syncwarp();
+    return;
+  }
+}
+
+template <int PITCH, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_sad_fs(const CUtensorMap *__restrict__ tmap, const FsArgs a)
+{
+  using SLOT = FsSlotT<PITCH>;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ FsSlot SS[2];
-  __shared__ FsWarp WS[FS_NW];
+  __shared__ SLOT SS[2];
+  __shared__ FsWarp WS[NT / 32];
   __shared__ uint32_t pgt[NPART];
-  __shared__ int s_next, s_err, s_nhits;
+  __shared__ FsCtaStats st;
   constexpr int K = FS_K;
   const FsGeom G = fs_geom(a.R);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = a.R;
-  const int nslot = G.nslot;
-  const int wpw = PITCH >> 2;                      // words per window row
 
   if (tid < NPART) {
     const PartGeom gm = part_geom(tid);
     pgt[tid] = (gm.ox >> 2) | ((gm.oy >> 2) << 4) | (((gm.ox + gm.w) >> 2) << 8) | (((gm.oy + gm.h) >> 2) << 12);
   }
-  for (int i = tid; i < FS_NW * 2 * 28; i += FS_NT) (&WS[0].sat[0][0])[i] = 0;
-  if (tid == 0) { s_err = 0; s_nhits = 0; }
+  for (int i = tid; i < (NT / 32) * 2 * 28; i += NT) (&WS[0].sat[0][0])[i] = 0;
+  if (tid == 0) { st.err = 0; st.nhits = 0; st.ngroups = 0; st.nitems = 0; }
+  if (tid < 2) {
+    SLOT &S = SS[tid];
+    S.ready_epoch = 0; S.next = 0; S.done = 0; S.ended = 0; S.epoch = 0; S.tma_uses = 0; S.ntask = 0;
+    S.g = 0; S.ngroups = 0;
+    S.item = (int)blockIdx.x + tid * (int)gridDim.x - 2 * (int)gridDim.x - 0x40000000;   // "before the first item"
+    mbar_init(&S.mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp < 2) fs_advance<PITCH>(SS[warp], WS[warp], smem + warp * G.slot_bytes, pgt, a, tmap, &st);
 
-  const int nunits = (a.nitems + nslot - 1) / nslot;
-  for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
-    __syncthreads();   // previous unit fully finished
-    // ---- per-partition parameters, current MB (threads 0..63 -> slot 0, 64..127 -> slot 1) ----
-    {
-      const int sl = tid >> 6, t = tid & 63;
-      FsSlot &S = SS[sl];
-      const int item = unit * nslot + sl;
-      const bool on = sl < nslot && item < a.nitems;
-      if (t == 0) { S.active = on; S.ngroups = 0; S.ntask = 0; }
-      if (on) {
-        const int mb = a.mb_first + item / a.refs_per_mb, ref = a.ref_first + item % a.refs_per_mb;
-        const int mbx = mb % a.mbw, mby = mb / a.mbw;
-        const size_t base = (a.abs_index ? ((size_t)mb * a.nrefs + ref) : (size_t)item) * NPART;
-        if (t == 0) { S.mb = mb; S.ref = ref; S.base_lo = (unsigned)base; S.base_hi = (unsigned)((unsigned long long)base >> 32); }
-        if (t < NPART) {
-          const int p = t;
-          const bool act = (a.part_mask >> p) & 1ull;
-          const PartGeom gm = part_geom(p);
-          S.pcx[p] = a.center[(base + p) * 2]; S.pcy[p] = a.center[(base + p) * 2 + 1];
-          S.ppx[p] = a.pred[(base + p) * 2];   S.ppy[p] = a.pred[(base + p) * 2 + 1];
-          S.psr[p] = (short)(a.restrict_mode < 0 ? a.sr_override : block_search_range(R, a.restrict_mode, ref, gm.bt));
-          S.pgrp[p] = act ? 0 : -1;
-          const long long mm = a.min_mcost < 0 ? 0 : (a.min_mcost > (1ll << 42) ? (1ll << 42) : a.min_mcost);
-          S.best[p] = ((unsigned long long)mm << 20);
-          if (act && ((S.pcx[p] | S.pcy[p]) & 3)) s_err = 1;       // sub-pel centres are not a full-search input
-        }
-        S.cur[t] = *reinterpret_cast<const uint32_t *>(a.cur + (size_t)(mby * 16 + (t >> 2)) * a.cur_pitch + mbx * 16 + (t & 3) * 4);
+  int ex0 = 0, ex1 = 0, nh = 0;
+  for (;;) {
+    bool any = false; int nend = 0;
+#pragma unroll 1
+    for (int b = 0; b < 2; b++) {
+      SLOT &S = SS[b];
+      const int ep0 = *reinterpret_cast<volatile int *>(&S.ready_epoch);
+      if (ep0 == (b ? ex1 : ex0)) { if (*reinterpret_cast<volatile int *>(&S.ended)) nend++; continue; }
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&S.next, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      const int ep = *reinterpret_cast<volatile int *>(&S.ready_epoch);
+      if ((c >> 20) != (ep & 0x7ff)) continue;       // counter not (yet) armed for the published epoch
+      __threadfence_block();
+      const int t = c & 0xfffff;
+      const int ntask = *reinterpret_cast<volatile int *>(&S.ntask);
+      if (t >= ntask) { if (b) ex1 = ep; else ex0 = ep; continue; }
+      any = true;
+      uint8_t *win = smem + b * G.slot_bytes;
+      const int g = S.g;
+      int dxa, dy0; bool va, vb;
+      if (t < S.ntaskA) {
+        const int cb = t / S.ngy, k = t - cb * S.ngy;
+        const int gc = S.gc, lo = gc, hi = S.ngy - 1 - gc, mn = min(lo, hi);
+        const int gy = k <= 2 * mn ? ((k & 1) ? gc + ((k + 1) >> 1) : gc - (k >> 1)) : (lo > hi ? gc - (k - hi) : gc + (k - lo));
+        dxa = 64 * cb + 8 * (lane >> 2) + (lane & 3); dy0 = gy * K;
+        va = dxa < S.ncx; vb = dxa + 4 < S.ncx;
+      } else {
+        const int job = (t - S.ntaskA) * 32 + lane;
+        const int i = job / S.ngy, gy = job - i * S.ngy;
+        dxa = 64 * S.ncbA + 8 * (i >> 2) + (i & 3); dy0 = gy * K;
+        va = i < S.npb && dxa < S.ncx; vb = va && dxa + 4 < S.ncx;
+        if (!va) dy0 = 0;
       }
-    }
-    __syncthreads();
-    // ---- cluster partitions whose centres fit in one FS_SMAX box (usually all of them) ----
-    {
-      const int sl = tid >> 6, t = tid & 63;
-      FsSlot &S = SS[sl];
-      if (S.active) {
-        const bool act = t < NPART && S.pgrp[t] >= 0;
-        const int cx = act ? (S.pcx[t] >> 2) : 0, cy = act ? (S.pcy[t] >> 2) : 0;
-        const int x0 = __reduce_min_sync(0xffffffffu, act ? cx : 0x7fff), x1 = __reduce_max_sync(0xffffffffu, act ? cx : -0x7fff);
-        const int y0 = __reduce_min_sync(0xffffffffu, act ? cy : 0x7fff), y1 = __reduce_max_sync(0xffffffffu, act ? cy : -0x7fff);
-        if (lane == 0) { S.red[t >> 5][0] = x0; S.red[t >> 5][1] = x1; S.red[t >> 5][2] = y0; S.red[t >> 5][3] = y1; }
-      }
-    }
-    __syncthreads();
-    if ((tid & 63) == 0 && SS[tid >> 6].active) {
-      FsSlot &S = SS[tid >> 6];
-      const int bx0 = min(S.red[0][0], S.red[1][0]), bx1 = max(S.red[0][1], S.red[1][1]);
-      const int by0 = min(S.red[0][2], S.red[1][2]), by1 = max(S.red[0][3], S.red[1][3]);
-      if (bx1 - bx0 <= FS_SMAX && by1 - by0 <= FS_SMAX) {
-        S.gx0[0] = bx0; S.gx1[0] = bx1; S.gy0[0] = by0; S.gy1[0] = by1; S.ngroups = bx1 >= bx0 ? 1 : 0;
-      } else {        // general case: greedy clustering (serial, rare)
-        int ng = 0;
-        for (int p = 0; p < NPART; p++) {
-          if (S.pgrp[p] < 0) continue;
-          const int cx = S.pcx[p] >> 2, cy = S.pcy[p] >> 2;
-          int g = -1;
-          for (int q = 0; q < ng; q++) {
-            const int nx0 = min((int)S.gx0[q], cx), nx1 = max((int)S.gx1[q], cx), ny0 = min((int)S.gy0[q], cy), ny1 = max((int)S.gy1[q], cy);
-            if (nx1 - nx0 <= FS_SMAX && ny1 - ny0 <= FS_SMAX) { g = q; S.gx0[q] = nx0; S.gx1[q] = nx1; S.gy0[q] = ny0; S.gy1[q] = ny1; break; }
-          }
-          if (g < 0) { g = ng++; S.gx0[g] = S.gx1[g] = cx; S.gy0[g] = S.gy1[g] = cy; }
-          S.pgrp[p] = (signed char)g;
-        }
-        S.ngroups = ng;
-      }
-    }
-    __syncthreads();
-    const int maxg = max(SS[0].ngroups, SS[1].active ? SS[1].ngroups : 0);
-
-    for (int g = 0; g < maxg; g++) {
-      if (g) __syncthreads();
-      // ---- group geometry + filter constants ----
-      {
-        const int sl = tid >> 6, t = tid & 63;
-        FsSlot &S = SS[sl];
-        const bool on = S.active && g < S.ngroups;
-        if (on) {
-          const bool ing = t < NPART && S.pgrp[t] == g;
-          const int px = ing ? S.ppx[t] : 0, py = ing ? S.ppy[t] : 0;
-          const int x0 = __reduce_min_sync(0xffffffffu, ing ? px : 0x7fff), x1 = __reduce_max_sync(0xffffffffu, ing ? px : -0x7fff);
-          const int y0 = __reduce_min_sync(0xffffffffu, ing ? py : 0x7fff), y1 = __reduce_max_sync(0xffffffffu, ing ? py : -0x7fff);
-          if (lane == 0) { S.red[t >> 5][0] = x0; S.red[t >> 5][1] = x1; S.red[t >> 5][2] = y0; S.red[t >> 5][3] = y1; }
-          if (ing) { S.pex[t] = (signed char)((S.pcx[t] >> 2) - S.gx0[g]); S.pey[t] = (signed char)((S.pcy[t] >> 2) - S.gy0[g]); }
-          if (t < 20) S.Cw[t] = 0;                 // partitions of other groups never pass
-          if (t == 20) S.C16 = 0;
-          if (t == 0) {
-            const int spanx = S.gx1[g] - S.gx0[g], spany = S.gy1[g] - S.gy0[g];
-            const int ncx = 2 * R + 1 + spanx, ncy = 2 * R + 1 + spany;
-            const int ngy = (ncy + K - 1) / K;
-            const int ncb = (ncx + 63) >> 6, wlast = ncx - 64 * (ncb - 1);
-            const int ncbA = wlast <= FS_BMAX ? ncb - 1 : ncb;
-            int npb = 0;
-            if (ncbA < ncb) npb = wlast <= 4 ? wlast : (wlast <= 8 ? 4 : wlast - 4);
-            S.ncx = ncx; S.ncy = ncy; S.ngy = ngy; S.gc = min(ngy - 1, (R + (spany >> 1)) / K);
-            S.ncbA = ncbA; S.ntaskA = ncbA * ngy; S.npb = npb;
-            S.ntask = ncbA * ngy + (npb * ngy + 31) / 32;
-          }
-        } else if (t == 0) S.ntask = 0;
-      }
-      __syncthreads();
-      {
-        const int sl = tid >> 6, t = tid & 63;
-        FsSlot &S = SS[sl];
-        const bool on = S.active && g < S.ngroups;
-        if (on) {
-          if (t < NPART && S.pgrp[t] == g) set_threshold(S, t, S.best[t]);
-          if (t == 0) {
-            S.ppxmin = min(S.red[0][0], S.red[1][0]); S.ppxmax = max(S.red[0][1], S.red[1][1]);
-            S.ppymin = min(S.red[0][2], S.red[1][2]); S.ppymax = max(S.red[0][3], S.red[1][3]);
-          }
-        }
-      }
-      // ---- stage the windows (4 byte-shifted copies, copy c stored c rows lower) ----
-      for (int sl = 0; sl < nslot; sl++) {
-        FsSlot &S = SS[sl];
-        if (!(S.active && g < S.ngroups)) continue;
-        const int mbx = S.mb % a.mbw, mby = S.mb / a.mbw;
-        const uint8_t *plane = a.planes + (size_t)S.ref * 16 * a.plane_size;     // integer plane [0][0]
-        const int x0 = mbx * 16 + S.gx0[g] - R + PADX, y0 = mby * 16 + S.gy0[g] - R + PADY;
-        const int nrows = G.rows - 3;
-        const int needw = S.ncx + 15;
-        uint8_t *wbase = smem + sl * G.slot_bytes;
-        uint32_t *c0 = reinterpret_cast<uint32_t *>(wbase), *c1 = reinterpret_cast<uint32_t *>(wbase + G.copy_bytes + PITCH),
-                 *c2 = reinterpret_cast<uint32_t *>(wbase + 2 * G.copy_bytes + 2 * PITCH), *c3 = reinterpret_cast<uint32_t *>(wbase + 3 * G.copy_bytes + 3 * PITCH);
-        if (x0 >= 0 && y0 >= 0 && x0 + needw <= a.Wp && y0 + nrows <= a.Hp) {
-          const int al = x0 & 3;
-#pragma unroll 2
-          for (int r = warp; r < nrows; r += FS_NW) {
-            const uint32_t *grow = reinterpret_cast<const uint32_t *>(plane + (size_t)(y0 + r) * a.Wp + (x0 - al));
-            for (int j = lane; j < wpw; j += 32) {
-              const uint32_t g0 = grow[j], g1 = grow[j + 1], g2 = grow[j + 2];
-              const uint32_t lo = al ? __funnelshift_r(g0, g1, 8 * al) : g0;      // window word j
-              const uint32_t hi = al ? __funnelshift_r(g1, g2, 8 * al) : g1;      // window word j+1
-              c0[r * wpw + j] = lo;
-              c1[r * wpw + j] = __funnelshift_r(lo, hi, 8);
-              c2[r * wpw + j] = __funnelshift_r(lo, hi, 16);
-              c3[r * wpw + j] = __funnelshift_r(lo, hi, 24);
-            }
-          }
-        } else {                      // window leaves the padded plane: per-pixel coordinate clamp
-          for (int r = warp; r < nrows; r += FS_NW) {
-            const uint8_t *grow = plane + (size_t)iclamp(y0 + r, 0, a.Hp - 1) * a.Wp;
-            for (int j = lane; j < wpw; j += 32) {
-              uint32_t b[7];
+      if (!va) dxa = 0;
+      const int cc = dxa & 3;
+      const uint8_t *wb = win + cc * G.copy_bytes + (dy0 + cc) * PITCH + (dxa >> 2) * 4;
+      uint32_t pass = fs_task<K, PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
+      uint32_t vm = 0;
 #pragma unroll
-              for (int k = 0; k < 7; k++) b[k] = grow[iclamp(x0 + 4 * j + k, 0, a.Wp - 1)];
-              c0[r * wpw + j] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-              c1[r * wpw + j] = b[1] | (b[2] << 8) | (b[3] << 16) | (b[4] << 24);
-              c2[r * wpw + j] = b[2] | (b[3] << 8) | (b[4] << 16) | (b[5] << 24);
-              c3[r * wpw + j] = b[3] | (b[4] << 8) | (b[5] << 16) | (b[6] << 24);
-            }
+      for (int j = 0; j < K; j++) if (dy0 + j < S.ncy) vm |= (va ? 1u << j : 0u) | (vb ? 1u << (K + j) : 0u);
+      pass &= vm;
+      if (__any_sync(0xffffffffu, pass != 0)) {
+        for (int bb = 0; bb < 2 * K; bb++) {
+          uint32_t m = __ballot_sync(0xffffffffu, (pass >> bb) & 1u);
+          while (m) {
+            const int l0 = __ffs(m) - 1; m &= m - 1;
+            const bool v1 = m != 0;
+            const int l1 = v1 ? __ffs(m) - 1 : l0; m &= m - 1;
+            const int ddx = bb >= K ? 4 : 0, ddy = bb >= K ? bb - K : bb;
+            const int ex0_ = __shfl_sync(0xffffffffu, dxa, l0) + ddx, ey0 = __shfl_sync(0xffffffffu, dy0, l0) + ddy;
+            const int ex1_ = __shfl_sync(0xffffffffu, dxa, l1) + ddx, ey1 = __shfl_sync(0xffffffffu, dy0, l1) + ddy;
+            fs_exact2<PITCH>(S, WS[warp], win, G.copy_bytes, pgt, ex0_, ey0, ex1_, ey1, v1, R, g, a.lambda_f);
+            nh += v1 ? 2 : 1;
           }
         }
       }
-      __syncthreads();
-      // ---- lower bound of the mv cost per window column / row: every partition of the group sees the
-      //      same displacement 4*(g0 + d - R); bits is monotone in |mv - pred|, so the distance to the
-      //      predictors' [min,max] interval bounds every partition's term from below ----
-      for (int sl = 0; sl < nslot; sl++) {
-        FsSlot &S = SS[sl];
-        if (!(S.active && g < S.ngroups)) continue;
-        const int ncx = S.ncx, ncy = S.ncy;
-        for (int i = tid; i < ncx + ncy + K; i += FS_NT) {
-          const bool isy = i >= ncx;
-          const int d = isy ? i - ncx : i;
-          const int mv = 4 * ((isy ? S.gy0[g] : S.gx0[g]) + d - R);
-          const int lo = isy ? S.ppymin : S.ppxmin, hi = isy ? S.ppymax : S.ppxmax;
-          const int dist = max(0, max(lo - mv, mv - hi));
-          const long long v = ((long long)a.lambda_f * mvbits(dist)) >> 5;
-          (isy ? S.mys : S.mxs)[d] = (unsigned short)(v > FS_MCAP ? FS_MCAP : v);
-        }
-      }
-      if (tid == 0) s_next = 0;
-      __syncthreads();
-      // ---- initial bounds: exact pre-pass over the centres' box ----
-      {
-        int total[2] = {0, 0}, pw[2] = {1, 1}, xlo[2] = {0, 0}, ylo[2] = {0, 0};
-        for (int sl = 0; sl < nslot; sl++) {
-          FsSlot &S = SS[sl];
-          if (!(S.active && g < S.ngroups)) continue;
-          xlo[sl] = max(0, R - FS_PRE); ylo[sl] = max(0, R - FS_PRE);
-          pw[sl] = min(S.ncx - 1, R + S.ncx - (2 * R + 1) + FS_PRE) - xlo[sl] + 1;
-          const int ph = min(S.ncy - 1, R + S.ncy - (2 * R + 1) + FS_PRE) - ylo[sl] + 1;
-          total[sl] = pw[sl] * ph;
-        }
-        const int npair0 = (total[0] + 1) >> 1, npair1 = (total[1] + 1) >> 1;
-        for (int pr = warp; pr < npair0 + npair1; pr += FS_NW) {
-          const int sl = pr >= npair0 ? 1 : 0, i0 = 2 * (pr - (sl ? npair0 : 0)), i1 = i0 + 1;
-          const bool v1 = i1 < total[sl];
-          const int dx0 = xlo[sl] + i0 % pw[sl], dy0 = ylo[sl] + i0 / pw[sl];
-          const int dx1 = v1 ? xlo[sl] + i1 % pw[sl] : dx0, dy1 = v1 ? ylo[sl] + i1 / pw[sl] : dy0;
-          fs_exact2<PITCH>(SS[sl], WS[warp], smem + sl * G.slot_bytes, G.copy_bytes, pgt, dx0, dy0, dx1, dy1, v1, R, g, a.lambda_f);
-        }
-      }
-      __syncthreads();
-      // ---- main pass: warps pull tasks until both items are exhausted ----
-      const int nt0 = SS[0].ntask, nt1 = nslot > 1 ? SS[1].ntask : 0;
-      int nh = 0;
-      for (;;) {
-        int T = 0;
-        if (lane == 0) T = atomicAdd(&s_next, 1);
-        T = __shfl_sync(0xffffffffu, T, 0);
-        if (T >= nt0 + nt1) break;
-        // interleave the two items so that both advance from their centres outwards
-        int sl, t;
-        if (T < 2 * min(nt0, nt1)) { sl = T & 1; t = T >> 1; }
-        else { sl = nt0 > nt1 ? 0 : 1; t = T - min(nt0, nt1); }
-        FsSlot &S = SS[sl];
-        const uint8_t *win = smem + sl * G.slot_bytes;
-        int dxa, dy0; bool va, vb;
-        if (t < S.ntaskA) {
-          const int cb = t / S.ngy, k = t - cb * S.ngy;
-          const int gc = S.gc, lo = gc, hi = S.ngy - 1 - gc, mn = min(lo, hi);
-          const int gy = k <= 2 * mn ? ((k & 1) ? gc + ((k + 1) >> 1) : gc - (k >> 1)) : (lo > hi ? gc - (k - hi) : gc + (k - lo));
-          dxa = 64 * cb + 8 * (lane >> 2) + (lane & 3); dy0 = gy * K;
-          va = dxa < S.ncx; vb = dxa + 4 < S.ncx;
-        } else {
-          const int job = (t - S.ntaskA) * 32 + lane;
-          const int i = job / S.ngy, gy = job - i * S.ngy;
-          dxa = 64 * S.ncbA + 8 * (i >> 2) + (i & 3); dy0 = gy * K;
-          va = i < S.npb && dxa < S.ncx; vb = va && dxa + 4 < S.ncx;
-          if (!va) dy0 = 0;
-        }
-        if (!va) dxa = 0;
-        const int c = dxa & 3;
-        const uint8_t *wb = win + c * G.copy_bytes + (dy0 + c) * PITCH + (dxa >> 2) * 4;
-        uint32_t pass = fs_task<K, PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
-        uint32_t vm = 0;
-#pragma unroll
-        for (int j = 0; j < K; j++) if (dy0 + j < S.ncy) vm |= (va ? 1u << j : 0u) | (vb ? 1u << (K + j) : 0u);
-        pass &= vm;
-        if (__any_sync(0xffffffffu, pass != 0)) {
-          for (int b = 0; b < 2 * K; b++) {
-            uint32_t m = __ballot_sync(0xffffffffu, (pass >> b) & 1u);
-            while (m) {
-              const int l0 = __ffs(m) - 1; m &= m - 1;
-              const bool v1 = m != 0;
-              const int l1 = v1 ? __ffs(m) - 1 : l0; m &= m - 1;
-              const int ddx = b >= K ? 4 : 0, ddy = b >= K ? b - K : b;
-              const int ex0 = __shfl_sync(0xffffffffu, dxa, l0) + ddx, ey0 = __shfl_sync(0xffffffffu, dy0, l0) + ddy;
-              const int ex1 = __shfl_sync(0xffffffffu, dxa, l1) + ddx, ey1 = __shfl_sync(0xffffffffu, dy0, l1) + ddy;
-              fs_exact2<PITCH>(S, WS[warp], win, G.copy_bytes, pgt, ex0, ey0, ex1, ey1, v1, R, g, a.lambda_f);
-              nh += v1 ? 2 : 1;
-            }
-          }
-        }
-      }
-      if (lane == 0 && nh) atomicAdd(&s_nhits, nh);
-    }
-    __syncthreads();
-    // ---- results ----
-    {
-      const int sl = tid >> 6, p = tid & 63;
-      FsSlot &S = SS[sl];
-      if (S.active && p < NPART && ((a.part_mask >> p) & 1ull)) {
-        const size_t base = ((size_t)S.base_hi << 32) | S.base_lo;
-        const unsigned long long key = S.best[p];
-        const int pos = (int)(key & 0xfffffull);
-        int sx, sy; spiral_xy(pos, &sx, &sy);
-        a.mv_int[(base + p) * 2]     = (int16_t)(S.pcx[p] + 4 * sx);
-        a.mv_int[(base + p) * 2 + 1] = (int16_t)(S.pcy[p] + 4 * sy);
-        long long cost = (long long)(key >> 20);
-        if (pos == 0 && cost == (1ll << 42) && a.min_mcost > (1ll << 42)) cost = a.min_mcost;   // bound never beaten
-        a.cost_int[base + p] = cost;
+      __syncwarp();
+      int d = 0;
+      if (lane == 0) { __threadfence_block(); d = atomicAdd(&S.done, 1) + 1; }
+      d = __shfl_sync(0xffffffffu, d, 0);
+      if (d == ntask) {
+        if (b) ex1 = ep; else ex0 = ep;
+        __threadfence_block();
+        fs_advance<PITCH>(S, WS[warp], win, pgt, a, tmap, &st);
       }
     }
-    if (tid == 0 && s_err) { *a.errflag = 1; s_err = 0; }
-    if (tid == 0 && a.stats) {
-      atomicAdd(&a.stats[0], (unsigned long long)s_nhits);
-      atomicAdd(&a.stats[1], (unsigned long long)(SS[0].ngroups + (SS[1].active ? SS[1].ngroups : 0)));
-      atomicAdd(&a.stats[2], (unsigned long long)(1 + (SS[1].active ? 1 : 0)));
-      s_nhits = 0;
+    if (nend == 2) break;
+    if (!any) __nanosleep(40);
+  }
+  if (lane == 0 && nh) atomicAdd(&st.nhits, nh);
+  __syncthreads();
+  if (tid == 0) {
+    if (st.err) *a.errflag = 1;
+    if (a.stats) {
+      atomicAdd(&a.stats[0], (unsigned long long)st.nhits);
+      atomicAdd(&a.stats[1], (unsigned long long)st.ngroups);
+      atomicAdd(&a.stats[2], (unsigned long long)st.nitems);
     }
   }
 }
 
-cudaError_t launch_sad_fs(const FsArgs &a, int sm_count, cudaStream_t s, int *smem_bytes_out)
+FsGeom fs_geom_host(int R) { return fs_geom(R); }
+
+cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, cudaStream_t s, int *smem_bytes_out)
 {
   const FsGeom G = fs_geom(a.R);
   static int configured96 = 0, configured160 = 0;
-  const int nunits = (a.nitems + G.nslot - 1) / G.nslot;
   cudaError_t e;
+  if (smem_bytes_out) *smem_bytes_out = G.total;
   if (G.pitch == 96) {
     if (configured96 < G.total) {
-      e = cudaFuncSetAttribute(k_sad_fs<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
+      e = cudaFuncSetAttribute(k_sad_fs<96, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
       if (e != cudaSuccess) return e;
       configured96 = G.total;
     }
-    k_sad_fs<96><<<nunits, FS_NT, G.total, s>>>(a);
+    const int grid = min((a.nitems + 1) / 2, sm_count * 3);
+    k_sad_fs<96, 128, 3><<<grid, 128, G.total, s>>>(tm, a);
   } else if (G.pitch == 160) {
     if (configured160 < G.total) {
-      e = cudaFuncSetAttribute(k_sad_fs<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
+      e = cudaFuncSetAttribute(k_sad_fs<160, 384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
       if (e != cudaSuccess) return e;
       configured160 = G.total;
     }
-    k_sad_fs<160><<<nunits, FS_NT, G.total, s>>>(a);
+    const int grid = min((a.nitems + 1) / 2, sm_count);
+    k_sad_fs<160, 384, 1><<<grid, 384, G.total, s>>>(tm, a);
   } else {
     return cudaErrorInvalidValue;
   }
-  if (smem_bytes_out) *smem_bytes_out = G.total;
-  (void)sm_count;
   return cudaGetLastError();
 }
 

@@ -96,6 +96,34 @@ __global__ void __launch_bounds__(256) k_quarter_planes(uint8_t *__restrict__ pl
     *reinterpret_cast<uint32_t *>(planes + idx[i] * PS + r + x) = o[i];   // Wp % 4 == 0
 }
 
+// Search planes of the integer full search: the reconstructed luma with an edge-replicated pad of `spad`
+// on every side (the [0][0] plane of getSubImagesLuma continued further out; UMVLine4X's clamp of the block
+// origin, refbuf.h:25, equals this replication, see sad_fs.cu), stored 16 times, plane s shifted left by s
+// bytes: out[s][y][x] = P[y][x+s].  TMA boxes must start on 16-byte boundaries; the shifted planes make
+// every byte column reachable.  HBM-bound: W*H read, 16*Wq*Hq written.
+__global__ void __launch_bounds__(256) k_search_plane(const uint8_t *__restrict__ luma, int pitch, int W, int H,
+                                                       uint8_t *__restrict__ out, int Wq, int Hq, int spad)
+{
+  const int wq4 = Wq >> 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= wq4 * Hq) return;
+  const int y = i / wq4, x = (i - y * wq4) * 4;
+  const uint8_t *row = luma + (size_t)iclamp(y - spad, 0, H - 1) * pitch;
+  uint32_t b[19];
+#pragma unroll
+  for (int k = 0; k < 19; k++) b[k] = row[iclamp(x + k - spad, 0, W - 1)];
+#pragma unroll
+  for (int s = 0; s < 16; s++)
+    reinterpret_cast<uint32_t *>(out + (size_t)s * Wq * Hq)[i] = b[s] | (b[s + 1] << 8) | (b[s + 2] << 16) | (b[s + 3] << 24);
+}
+
+cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, cudaStream_t s)
+{
+  const int n = (Wq >> 2) * Hq;
+  k_search_plane<<<(n + 255) / 256, 256, 0, s>>>(luma, pitch, W, H, out, Wq, Hq, spad);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, cudaStream_t s)
 {
   const int Wp = W + 2 * PADX, Hp = H + 2 * PADY;
