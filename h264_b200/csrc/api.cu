@@ -76,8 +76,9 @@ extern "C" int b2me_create(b2me_ctx **out, int device, int width, int height, in
   B2_CUDA_CHECK(c, cudaMallocHost(&c->h_io64, 2 * NPART * sizeof(long long)));
   B2_CUDA_CHECK(c, cudaMalloc(&c->d_errflag, sizeof(int)));
   B2_CUDA_CHECK(c, cudaMemset(c->d_errflag, 0, sizeof(int)));
-  B2_CUDA_CHECK(c, cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long)));
-  B2_CUDA_CHECK(c, cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_work, sizeof(int)));
+  B2_CUDA_CHECK(c, cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)));
+  B2_CUDA_CHECK(c, cudaMemset(c->d_stats, 0, 16 * sizeof(unsigned long long)));
   B2_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   B2_CUDA_CHECK(c, cudaEventCreate(&c->ev0));
   B2_CUDA_CHECK(c, cudaEventCreate(&c->ev1));
@@ -91,7 +92,7 @@ extern "C" void b2me_destroy(b2me_ctx *c)
   cudaFree(c->d_cur); cudaFree(c->d_stage); cudaFree(c->d_planes); cudaFree(c->d_spl); cudaFree(c->d_tmap_spl);
   cudaFree(c->d_pred); cudaFree(c->d_center); cudaFree(c->d_mv_int); cudaFree(c->d_mv_sub);
   cudaFree(c->d_cost_int); cudaFree(c->d_cost_sub); cudaFree(c->d_io16); cudaFree(c->d_io64);
-  cudaFreeHost(c->h_io16); cudaFreeHost(c->h_io64); cudaFree(c->d_errflag); cudaFree(c->d_stats);
+  cudaFreeHost(c->h_io16); cudaFreeHost(c->h_io64); cudaFree(c->d_errflag); cudaFree(c->d_work); cudaFree(c->d_stats);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -130,9 +131,11 @@ extern "C" int b2me_search_stats(b2me_ctx *c, int64_t out[3], int reset)
   if (!c || !out) return B2ME_EINVAL;
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
   B2_CUDA_CHECK(c, cudaDeviceSynchronize());
-  unsigned long long h[4];
+  unsigned long long h[16];
   B2_CUDA_CHECK(c, cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
   out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = (int64_t)h[2];
+  if (getenv("B2ME_FS_PROFILE"))
+    fprintf(stderr, "[b2me] k_sad_fs warp-cycles: task %llu exact %llu advance %llu (tma wait %llu) total %llu; CTA0 warp0: %llu cycles in %llu ns = %.0f MHz\n", h[3], h[4], h[5], h[8], h[7], h[9], h[10], h[10] ? 1e3 * (double)h[9] / (double)h[10] : 0.0);
   if (reset) B2_CUDA_CHECK(c, cudaMemset(c->d_stats, 0, sizeof(h)));
   return B2ME_OK;
 }
@@ -236,7 +239,10 @@ static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
   f.pred = pred; f.center = center; f.mv_int = mv_int; f.cost_int = cost_int;
   f.mb_first = mb_first; f.ref_first = ref_first; f.refs_per_mb = refs_per_mb; f.nitems = mb_count * refs_per_mb;
   f.abs_index = abs_index; f.part_mask = mask; f.errflag = c->d_errflag; f.stats = c->d_stats; f.one = 1;
-  { const char *e = getenv("B2ME_FS_NOTMA"); f.flags = (e && e[0] == '1') ? 1 : 0; }
+  { const char *e = getenv("B2ME_FS_NOTMA"); f.flags = (e && e[0] == '1') ? 1 : 0;
+    const char *r = getenv("B2ME_FS_REP"); if (r) f.flags |= atoi(r) << 8; }
+  f.work_counter = c->d_work;
+  B2_CUDA_CHECK(c, cudaMemsetAsync(c->d_work, 0, sizeof(int), s));
   {
     FamilyTimer t(c, 0, s);
     B2_CUDA_CHECK(c, launch_sad_fs(f, c->d_tmap_spl, c->sm_count, s, &c->fs_smem_bytes));

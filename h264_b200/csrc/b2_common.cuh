@@ -60,8 +60,9 @@ __host__ __device__ __forceinline__ int spiral_index(int x, int y)
 __host__ __device__ __forceinline__ void spiral_xy(int pos, int *x, int *y)
 {
   if (pos == 0) { *x = 0; *y = 0; return; }
-  int l = 1;
+  int l = (int)((sqrtf((float)pos) + 1.0f) * 0.5f);          // ring: (2l-1)^2 <= pos < (2l+1)^2
   while ((2 * l + 1) * (2 * l + 1) <= pos) l++;
+  while ((2 * l - 1) * (2 * l - 1) > pos) l--;
   int k = pos - (2 * l - 1) * (2 * l - 1);
   if (k < 2 * (2 * l - 1)) { *x = (k >> 1) - l + 1; *y = (k & 1) ? l : -l; }
   else { k -= 2 * (2 * l - 1); *y = (k >> 1) - l; *x = (k & 1) ? l : -l; }

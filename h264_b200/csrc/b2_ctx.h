@@ -25,6 +25,7 @@ struct b2me_ctx {
   int16_t *d_io16;
   long long *d_io64;
   int *d_errflag;
+  int *d_work;                  // k_sad_fs item counter
   unsigned long long *d_stats;
   cudaStream_t stream;          // internal stream for host-pointer calls
   cudaEvent_t ev0, ev1;
@@ -55,6 +56,7 @@ struct FsArgs {
   int abs_index;         // 1: arrays indexed ((mb*nrefs+ref)*41+p), 0: (item*41+p)
   unsigned long long part_mask;           // active partitions
   int *errflag;
+  int *work_counter;     // device int, zero at launch: next (MB, ref) item to hand out
   int flags;             // bit 0: stage every window with the clamped (non-TMA) path (debug, B2ME_FS_NOTMA=1)
   int one;               // 1 (a run-time constant the compiler cannot fold, see sad_fs.cu addmin2)
   unsigned long long *stats;   // optional: [0] exact re-evaluations, [1] window passes, [2] items

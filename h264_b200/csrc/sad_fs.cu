@@ -50,11 +50,12 @@
 // (x0+c)&15.  Windows that leave the search plane (centres more than 32 pel outside the picture) are
 // staged by the setting-up warp with per-pixel clamps.
 #include "b2_common.cuh"
+#include <cstdlib>
 #include "b2_ctx.h"
 
 namespace b2 {
 
-constexpr int FS_K = 5;          // candidate rows per task (lock step)
+constexpr int FS_K = 4;          // candidate rows per task (lock step): 4 = rolled fs_task4, 5 = fully unrolled fs_task
 constexpr int FS_PRE = 0;        // radius of the exact pre-pass around the centres (initial bounds)
 constexpr int FS_SMAX = 8;       // partitions whose centres lie within an 8-pel box share one window pass
 constexpr int FS_BMAX = 12;      // a trailing column block of at most this width is walked row-major (type B)
@@ -70,11 +71,14 @@ __host__ __device__ inline FsGeom fs_geom(int R)
   while ((p & 127) != 32 && (p & 127) != 96) p += 16;
   G.pitch = p;
   const int ngy = (ncmax + FS_K - 1) / FS_K;
-  G.rows = FS_K * ngy + 15 + 3;
+  G.rows = ncmax + 15 + 3;                         // rows that valid candidates read (+3 for the copies' row shift)
   G.copy_bytes = (G.rows * G.pitch + 127) & ~127;
   G.slot_bytes = 4 * G.copy_bytes;
-  G.total = 2 * G.slot_bytes;
-  G.threads = G.pitch == 96 ? 128 : 384;
+  // masked candidates of the last row group read up to FS_K*ngy+15+3 rows: harmless garbage from the next
+  // copy / buffer; the slack keeps those reads inside the allocation at the very end
+  const int over = (FS_K * ngy + 15 + 3 - G.rows) * G.pitch;
+  G.total = 2 * G.slot_bytes + ((over + 127) & ~127);
+  G.threads = G.pitch == 96 ? 160 : 416;    // workers + one producer warp
   return G;
 }
 
@@ -94,6 +98,7 @@ struct __align__(16) FsSlotT {    // per-buffer state: one (item, centre group) 
   signed char pex[NPART], pey[NPART];   // centre of the partition relative to its group's box origin (pel)
   // pipeline
   int ready_epoch;                // epoch whose window + setup are complete (written last, read first)
+  int finished_epoch;             // epoch whose tasks are all done (written by the worker that completed the last one)
   int next;                       // (epoch << 20) | tasks claimed
   int done;                       // tasks completed in the current epoch
   int ended;                      // no more items for this buffer
@@ -281,6 +286,94 @@ __device__ __forceinline__ uint32_t fs_task(const SLOT &S, const uint8_t *wb, ui
   return pass;
 }
 
+// K = 4 variant of fs_task with the two 8-row halves of the macroblock as a rolled loop: the register window
+// slot of reference row i+j is (i+j)&3, independent of the half, so the loop body (8 rows) is the same code
+// for both halves and the task body shrinks from ~21 KB to ~8 KB of SASS (instruction-cache pressure: 12
+// desynchronised warps per SM stream through this body).
+template <int PITCH, class SLOT>
+__device__ __forceinline__ uint32_t fs_task4(const SLOT &S, const uint8_t *wb, uint32_t mxa, uint32_t mxb, const unsigned short *mys, uint32_t one)
+{
+  constexpr int K = 4;
+  const uint4 *cur = reinterpret_cast<const uint4 *>(S.cur);
+  uint32_t rw[K][6];
+  uint32_t acc[2][K][4];
+  uint32_t run[2][K], X0[2][K], Y0[2][K], E0[2][K];
+  uint32_t pass = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++) { run[0][j] = run[1][j] = 0x7fff7fffu; E0[0][j] = E0[1][j] = 0; }
+#pragma unroll
+  for (int j = 0; j < K - 1; j++) ld3(rw[j], wb + j * PITCH);
+#pragma unroll 1
+  for (int bb = 0; bb < 2; bb++) {
+    const uint8_t *wr = wb + bb * 8 * PITCH;
+    const uint32_t *Cb = S.Cw + 6 * bb;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      ld3(rw[(r + K - 1) & 3], wr + (r + K - 1) * PITCH);
+      const uint4 c = cur[bb * 8 + r];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const int sl = (r + j) & 3;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          if ((r & 3) == 0) {
+            acc[q][j][0] = sad4(c.x, rw[sl][q + 0], 0u);
+            acc[q][j][1] = sad4(c.y, rw[sl][q + 1], 0u);
+            acc[q][j][2] = sad4(c.z, rw[sl][q + 2], 0u);
+            acc[q][j][3] = sad4(c.w, rw[sl][q + 3], 0u);
+          } else {
+            acc[q][j][0] = sad4(c.x, rw[sl][q + 0], acc[q][j][0]);
+            acc[q][j][1] = sad4(c.y, rw[sl][q + 1], acc[q][j][1]);
+            acc[q][j][2] = sad4(c.z, rw[sl][q + 2], acc[q][j][2]);
+            acc[q][j][3] = sad4(c.w, rw[sl][q + 3], acc[q][j][3]);
+          }
+        }
+      }
+      if ((r & 3) == 3) {
+        const int odd = r >> 2;                       // block row b = 2*bb + odd
+        const uint32_t cx = ld_vol(&Cb[3 * odd]), cy = ld_vol(&Cb[3 * odd + 1]), ch = ld_vol(&Cb[3 * odd + 2]);
+        uint32_t cxv = 0, cyv = 0, ce = 0;
+        if (odd) { cxv = ld_vol(&S.Cw[12 + 3 * bb]); cyv = ld_vol(&S.Cw[13 + 3 * bb]); ce = ld_vol(&S.Cw[14 + 3 * bb]); }
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const uint32_t X = acc[q][j][2] * 65536u + acc[q][j][0];
+            const uint32_t Y = acc[q][j][3] * 65536u + acc[q][j][1];
+            const uint32_t H = add2(X, Y);
+            uint32_t rr = run[q][j];
+            rr = addmin2(X, cx, rr, one);
+            rr = addmin2(Y, cy, rr, one);
+            rr = addmin2(H, ch, rr, one);
+            if (odd) {
+              const uint32_t XV = add2(X, X0[q][j]), YV = add2(Y, Y0[q][j]);
+              const uint32_t E = add2(XV, YV);
+              rr = addmin2(XV, cxv, rr, one);
+              rr = addmin2(YV, cyv, rr, one);
+              rr = addmin2(E, ce, rr, one);
+              if (bb == 0) E0[q][j] = E;
+              else {
+                const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
+                const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
+                const uint32_t top = __dp2a_lo(E0[q][j], 0x0101u, 0u), bot = __dp2a_lo(E, 0x0101u, 0u);
+                const uint32_t TB = bot * 65536u + top, LR = add2(E0[q][j], E);
+                rr = addmin2(TB, ctb, rr, one);
+                rr = addmin2(LR, clr, rr, one);
+                const uint32_t m = (q ? mxb : mxa) + mys[j];
+                const int s = (int)(top + bot) + c16 + (int)m;
+                const uint32_t t = rr + m * 0x10001u;
+                if ((t & 0x80008000u) != 0u || s < 0) pass |= 1u << (q * K + j);
+              }
+            } else { X0[q][j] = X; Y0[q][j] = Y; }
+            run[q][j] = rr;
+          }
+        }
+      }
+    }
+  }
+  return pass;
+}
+
 // ---- mbarrier / TMA (PTX) ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void *bar, int count)
@@ -300,7 +393,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, vo
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
-struct FsCtaStats { int err, nhits, ngroups, nitems; };
+struct FsCtaStats { int err, nhits, ngroups, nitems; unsigned long long cyc[6]; };   // cyc: task, exact, advance, idle, total, tma-wait (warp cycles)
 
 // Called by ONE warp when the unit of buffer S is complete (or at kernel start): writes the results of a
 // finished item, fetches the buffer's next unit (next centre group of the same item, else the next item
@@ -314,6 +407,7 @@ __device__ __noinline__ void fs_advance(SLOT &S, FsWarp &ws, uint8_t *win, const
   constexpr int K = FS_K;
   const FsGeom G = fs_geom(a.R);
   const int lane = threadIdx.x & 31, R = a.R;
+  const long long t_adv0 = clock64();
   for (;;) {
     int g;
     if (S.item >= 0 && S.g + 1 < S.ngroups) g = S.g + 1;
@@ -334,7 +428,9 @@ __device__ __noinline__ void fs_advance(SLOT &S, FsWarp &ws, uint8_t *win, const
         if (lane == 0) { atomicAdd(&st->ngroups, S.ngroups); atomicAdd(&st->nitems, 1); }
       }
       __syncwarp();
-      const int item = (S.item >= 0 ? S.item : S.item + 0x40000000) + 2 * (int)gridDim.x;   // first call: item encodes first - 2*grid - 2^30
+      int item = 0;                                // items are handed out in order by a global counter (load balance)
+      if (lane == 0) item = atomicAdd(a.work_counter, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
       if (item >= a.nitems) {
         if (lane == 0) { S.item = -1; S.ngroups = 0; __threadfence_block(); *reinterpret_cast<volatile int *>(&S.ended) = 1; }
         __syncwarp();
@@ -427,7 +523,7 @@ __device__ __noinline__ void fs_advance(SLOT &S, FsWarp &ws, uint8_t *win, const
       }
     } else {                                       // window leaves the search plane: per-pixel coordinate clamp
       const uint8_t *plane = a.spl + (size_t)S.ref * 16 * a.Wq * a.Hq;     // shift-0 plane
-      const int nrows = K * ngy + 15, wpw = PITCH >> 2;
+      const int nrows = min(K * ngy + 15, G.rows - 3), wpw = PITCH >> 2;
       for (int r = 0; r < nrows; r++) {
         const uint8_t *grow = plane + (size_t)iclamp(y0 + r, 0, a.Hq - 1) * a.Wq;
         for (int j = lane; j < wpw; j += 32) {
@@ -470,7 +566,9 @@ __device__ __noinline__ void fs_advance(SLOT &S, FsWarp &ws, uint8_t *win, const
     __syncwarp();
     if (inside) {
       const uint32_t parity = (uint32_t)S.tma_uses & 1u;
+      const long long tw0 = clock64();
       while (!mbar_try_wait(&S.mbar, parity)) { }
+      if (lane == 0) atomicAdd(&st->cyc[5], (unsigned long long)(clock64() - tw0));
       __syncwarp();
       if (lane == 0) S.tma_uses++;
     }
@@ -494,19 +592,21 @@ __device__ __noinline__ void fs_advance(SLOT &S, FsWarp &ws, uint8_t *win, const
       *reinterpret_cast<volatile int *>(&S.ready_epoch) = ep;
       __threadfence_block();
       atomicExch(&S.next, (ep & 0x7ff) << 20);
+      atomicAdd(&st->cyc[2], (unsigned long long)(clock64() - t_adv0));
     }
     __syncwarp();
     return;
   }
 }
 
-template <int PITCH, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_sad_fs(const CUtensorMap *__restrict__ tmap, const FsArgs a)
+template <int PITCH, int NWORK, int MINB>
+__global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtensorMap *__restrict__ tmap, const __grid_constant__ FsArgs a)
 {
   using SLOT = FsSlotT<PITCH>;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ SLOT SS[2];
-  __shared__ FsWarp WS[NT / 32];
+  constexpr int NT = (NWORK + 1) * 32;
+  __shared__ FsWarp WS[NWORK + 1];
   __shared__ uint32_t pgt[NPART];
   __shared__ FsCtaStats st;
   constexpr int K = FS_K;
@@ -518,24 +618,51 @@ __global__ void __launch_bounds__(NT, MINB) k_sad_fs(const CUtensorMap *__restri
     const PartGeom gm = part_geom(tid);
     pgt[tid] = (gm.ox >> 2) | ((gm.oy >> 2) << 4) | (((gm.ox + gm.w) >> 2) << 8) | (((gm.oy + gm.h) >> 2) << 12);
   }
-  for (int i = tid; i < (NT / 32) * 2 * 28; i += NT) (&WS[0].sat[0][0])[i] = 0;
-  if (tid == 0) { st.err = 0; st.nhits = 0; st.ngroups = 0; st.nitems = 0; }
+  for (int i = tid; i < (NWORK + 1) * 2 * 28; i += NT) (&WS[0].sat[0][0])[i] = 0;
+  if (tid == 0) { st.err = 0; st.nhits = 0; st.ngroups = 0; st.nitems = 0; for (int i = 0; i < 6; i++) st.cyc[i] = 0; }
   if (tid < 2) {
     SLOT &S = SS[tid];
-    S.ready_epoch = 0; S.next = 0; S.done = 0; S.ended = 0; S.epoch = 0; S.tma_uses = 0; S.ntask = 0;
+    S.ready_epoch = 0; S.finished_epoch = 0; S.next = 0; S.done = 0; S.ended = 0; S.epoch = 0; S.tma_uses = 0; S.ntask = 0;
     S.g = 0; S.ngroups = 0;
-    S.item = (int)blockIdx.x + tid * (int)gridDim.x - 2 * (int)gridDim.x - 0x40000000;   // "before the first item"
+    S.item = -1;
     mbar_init(&S.mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp < 2) fs_advance<PITCH>(SS[warp], WS[warp], smem + warp * G.slot_bytes, pgt, a, tmap, &st);
+  if (warp == NWORK) {
+    // ---- producer warp: sets up both buffers, then re-arms whichever buffer's unit the workers have completed ----
+    int seen0 = 0, seen1 = 0;
+    fs_advance<PITCH>(SS[0], WS[warp], smem, pgt, a, tmap, &st);
+    fs_advance<PITCH>(SS[1], WS[warp], smem + G.slot_bytes, pgt, a, tmap, &st);
+    for (;;) {
+      int nend = 0; bool any = false;
+#pragma unroll 1
+      for (int b = 0; b < 2; b++) {
+        SLOT &S = SS[b];
+        if (*reinterpret_cast<volatile int *>(&S.ended)) { nend++; continue; }
+        const int fin = *reinterpret_cast<volatile int *>(&S.finished_epoch);
+        if (fin == (b ? seen1 : seen0)) continue;
+        __threadfence_block();
+        if (b) seen1 = fin; else seen0 = fin;
+        fs_advance<PITCH>(S, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st);
+        any = true;
+      }
+      if (nend == 2) break;
+      if (!any) __nanosleep(100);
+    }
+  } else {
 
-  int ex0 = 0, ex1 = 0, nh = 0;
+  // Warps drain ONE buffer at a time (pref) and move to the other only when pref has no task left to claim, so
+  // the two units finish staggered and the set-up of a buffer's next unit overlaps the other buffer's tasks.
+  int ex0 = 0, ex1 = 0, nh = 0, pref = 0;
+  long long c_task = 0, c_exact = 0;
+  const long long t_begin = clock64();
+  unsigned long long g_begin; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_begin));
   for (;;) {
     bool any = false; int nend = 0;
 #pragma unroll 1
-    for (int b = 0; b < 2; b++) {
+    for (int k = 0; k < 2 && !any; k++) {
+      const int b = pref ^ k;
       SLOT &S = SS[b];
       const int ep0 = *reinterpret_cast<volatile int *>(&S.ready_epoch);
       if (ep0 == (b ? ex1 : ex0)) { if (*reinterpret_cast<volatile int *>(&S.ended)) nend++; continue; }
@@ -548,6 +675,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sad_fs(const CUtensorMap *__restri
       const int t = c & 0xfffff;
       const int ntask = *reinterpret_cast<volatile int *>(&S.ntask);
       if (t >= ntask) { if (b) ex1 = ep; else ex0 = ep; continue; }
+      pref = b;
       any = true;
       uint8_t *win = smem + b * G.slot_bytes;
       const int g = S.g;
@@ -568,11 +696,18 @@ __global__ void __launch_bounds__(NT, MINB) k_sad_fs(const CUtensorMap *__restri
       if (!va) dxa = 0;
       const int cc = dxa & 3;
       const uint8_t *wb = win + cc * G.copy_bytes + (dy0 + cc) * PITCH + (dxa >> 2) * 4;
-      uint32_t pass = fs_task<K, PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
+      const long long tt0 = clock64();
+      uint32_t pass = 0;
+#pragma unroll 1
+      for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
+        pass |= K == 4 ? fs_task4<PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one)
+                       : fs_task<5, PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
       uint32_t vm = 0;
 #pragma unroll
       for (int j = 0; j < K; j++) if (dy0 + j < S.ncy) vm |= (va ? 1u << j : 0u) | (vb ? 1u << (K + j) : 0u);
       pass &= vm;
+      const long long tt1 = clock64();
+      c_task += tt1 - tt0;
       if (__any_sync(0xffffffffu, pass != 0)) {
         for (int bb = 0; bb < 2 * K; bb++) {
           uint32_t m = __ballot_sync(0xffffffffu, (pass >> bb) & 1u);
@@ -589,19 +724,28 @@ __global__ void __launch_bounds__(NT, MINB) k_sad_fs(const CUtensorMap *__restri
         }
       }
       __syncwarp();
+      c_exact += clock64() - tt1;
       int d = 0;
       if (lane == 0) { __threadfence_block(); d = atomicAdd(&S.done, 1) + 1; }
       d = __shfl_sync(0xffffffffu, d, 0);
-      if (d == ntask) {
+      if (d == ntask) {                              // unit complete: hand the buffer to the producer warp
         if (b) ex1 = ep; else ex0 = ep;
-        __threadfence_block();
-        fs_advance<PITCH>(S, WS[warp], win, pgt, a, tmap, &st);
+        if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int *>(&S.finished_epoch) = ep; }
       }
     }
     if (nend == 2) break;
-    if (!any) __nanosleep(40);
+    if (!any) __nanosleep(200);
   }
   if (lane == 0 && nh) atomicAdd(&st.nhits, nh);
+  if (lane == 0) {
+    atomicAdd(&st.cyc[0], (unsigned long long)c_task); atomicAdd(&st.cyc[1], (unsigned long long)c_exact);
+    atomicAdd(&st.cyc[4], (unsigned long long)(clock64() - t_begin));
+    if (blockIdx.x == 0 && warp == 0 && a.stats) {
+      unsigned long long g_end; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_end));
+      atomicAdd(&a.stats[9], (unsigned long long)(clock64() - t_begin)); atomicAdd(&a.stats[10], g_end - g_begin);
+    }
+  }
+  }
   __syncthreads();
   if (tid == 0) {
     if (st.err) *a.errflag = 1;
@@ -609,6 +753,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sad_fs(const CUtensorMap *__restri
       atomicAdd(&a.stats[0], (unsigned long long)st.nhits);
       atomicAdd(&a.stats[1], (unsigned long long)st.ngroups);
       atomicAdd(&a.stats[2], (unsigned long long)st.nitems);
+      for (int i = 0; i < 6; i++) atomicAdd(&a.stats[3 + i], st.cyc[i]);
     }
   }
 }
@@ -623,20 +768,26 @@ cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, 
   if (smem_bytes_out) *smem_bytes_out = G.total;
   if (G.pitch == 96) {
     if (configured96 < G.total) {
-      e = cudaFuncSetAttribute(k_sad_fs<96, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
+      e = cudaFuncSetAttribute(k_sad_fs<96, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
       if (e != cudaSuccess) return e;
       configured96 = G.total;
     }
-    const int grid = min((a.nitems + 1) / 2, sm_count * 3);
-    k_sad_fs<96, 128, 3><<<grid, 128, G.total, s>>>(tm, a);
+    static int occ = -1;
+    if (occ < 0) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sad_fs<96, 4, 3>, G.threads, G.total);
+      if (getenv("B2ME_FS_PROFILE")) fprintf(stderr, "[b2me] k_sad_fs<96>: %d CTAs/SM (threads %d, dyn smem %d)\n", occ, G.threads, G.total);
+      if (occ < 1) occ = 1;
+    }
+    const int grid = min((a.nitems + 1) / 2, sm_count * occ);
+    k_sad_fs<96, 4, 3><<<grid, G.threads, G.total, s>>>(tm, a);
   } else if (G.pitch == 160) {
     if (configured160 < G.total) {
-      e = cudaFuncSetAttribute(k_sad_fs<160, 384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
+      e = cudaFuncSetAttribute(k_sad_fs<160, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
       if (e != cudaSuccess) return e;
       configured160 = G.total;
     }
     const int grid = min((a.nitems + 1) / 2, sm_count);
-    k_sad_fs<160, 384, 1><<<grid, 384, G.total, s>>>(tm, a);
+    k_sad_fs<160, 12, 1><<<grid, G.threads, G.total, s>>>(tm, a);
   } else {
     return cudaErrorInvalidValue;
   }
