@@ -54,7 +54,18 @@ extern "C" int b2me_create(b2me_ctx **out, int device, int width, int height, in
     const cuuint64_t strides[2] = {(cuuint64_t)c->Wq, (cuuint64_t)c->Wq * c->Hq};
     const cuuint32_t box[3] = {(cuuint32_t)G.pitch, (cuuint32_t)G.rows, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult cr = cuTensorMapEncodeTiled(&c->tmap_spl, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d_spl, dims, strides, box, estr,
+    // resolved through the runtime so that libb2me.so carries no link-time dependency on libcuda.so.1
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    B2_CUDA_CHECK(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled is not available in this driver");
+      return B2ME_ECUDA;
+    }
+    CUresult cr = reinterpret_cast<encode_fn>(fn)(&c->tmap_spl, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d_spl, dims, strides, box, estr,
                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
@@ -135,7 +146,7 @@ extern "C" int b2me_search_stats(b2me_ctx *c, int64_t out[3], int reset)
   B2_CUDA_CHECK(c, cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
   out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = (int64_t)h[2];
   if (getenv("B2ME_FS_PROFILE"))
-    fprintf(stderr, "[b2me] k_sad_fs warp-cycles: task %llu exact %llu advance %llu (tma wait %llu) total %llu; CTA0 warp0: %llu cycles in %llu ns = %.0f MHz\n", h[3], h[4], h[5], h[8], h[7], h[9], h[10], h[10] ? 1e3 * (double)h[9] / (double)h[10] : 0.0);
+    fprintf(stderr, "[b2me] k_sad_fs warp-cycles: task %llu exact %llu idle %llu total %llu | producer %llu (tma wait %llu); CTA0 warp0: %llu cycles in %llu ns = %.0f MHz\n", h[3], h[4], h[6], h[7], h[5], h[8], h[9], h[10], h[10] ? 1e3 * (double)h[9] / (double)h[10] : 0.0);
   if (reset) B2_CUDA_CHECK(c, cudaMemset(c->d_stats, 0, sizeof(h)));
   return B2ME_OK;
 }

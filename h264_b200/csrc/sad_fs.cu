@@ -57,10 +57,10 @@ namespace b2 {
 
 constexpr int FS_K = 4;          // candidate rows per task (lock step): 4 = rolled fs_task4, 5 = fully unrolled fs_task
 constexpr int FS_PRE = 0;        // radius of the exact pre-pass around the centres (initial bounds)
-constexpr int FS_SMAX = 8;       // partitions whose centres lie within an 8-pel box share one window pass
+constexpr int FS_SMAX = 7;       // partitions whose centres lie within a 7-pel box share one window pass
 constexpr int FS_BMAX = 12;      // a trailing column block of at most this width is walked row-major (type B)
 constexpr int FS_MCAP = 2047;    // cap of each half of the mv-cost lower bound (keeps packed sums in range)
-constexpr int FS_MAXW = 12;      // max warps per CTA
+constexpr int FS_CLAIM = 2;      // tasks claimed per visit of the shared counter (amortises the claim / completion protocol)
 
 __host__ __device__ inline FsGeom fs_geom(int R)
 {
@@ -83,11 +83,10 @@ __host__ __device__ inline FsGeom fs_geom(int R)
 }
 
 template <int PITCH>
-struct __align__(16) FsSlotT {    // per-buffer state: one (item, centre group) unit at a time
+struct __align__(16) FsSlotT {    // one unit = (item, centre group): everything but the window
   static constexpr int NTAB = PITCH == 96 ? 88 : 152;
   uint32_t cur[64];               // current MB, 16 rows x 4 words
   unsigned long long best[NPART]; // (cost << 20) | pos
-  unsigned long long mbar;        // TMA completion barrier of this buffer
   uint32_t Cw[20];                // packed filter constants, see cmap()
   int C16;                        // 16x16: -B-1
   unsigned short mxs[NTAB], mys[NTAB];   // per window column / row: lower bound of lambda*bits >> 5 (also clustering scratch)
@@ -96,17 +95,23 @@ struct __align__(16) FsSlotT {    // per-buffer state: one (item, centre group) 
   short psr[NPART];               // per-partition search range (pel)
   signed char pgrp[NPART];        // centre group of the partition (-1 inactive)
   signed char pex[NPART], pey[NPART];   // centre of the partition relative to its group's box origin (pel)
-  // pipeline
-  int ready_epoch;                // epoch whose window + setup are complete (written last, read first)
+  int item, mb, ref, g, ngroups; unsigned base_lo, base_hi;
+  int gx0, gy0, spanx, spany;     // the group's centre box (pel)
+  int wx0, wy0, inside;           // window origin in the search plane; inside: the TMA path applies
+  int ncx, ncy, ngy, gc, ncbA, ntaskA, npb, ntask;
+  unsigned short ttab[96];        // type-A task t -> dy0 | column block << 8, centre rows first
+};
+
+struct FsCtl {                    // per window buffer: the pipeline between the producer warp and the workers
+  unsigned long long mbar;        // TMA completion barrier
+  int ready_epoch;                // epoch whose window + unit are complete (written last, read first)
   int finished_epoch;             // epoch whose tasks are all done (written by the worker that completed the last one)
   int next;                       // (epoch << 20) | tasks claimed
   int done;                       // tasks completed in the current epoch
-  int ended;                      // no more items for this buffer
+  int ntask;                      // tasks of the current epoch
+  int slot;                       // unit slot attached to this buffer
+  int ended;                      // no more units for this buffer
   int epoch, tma_uses;
-  // current unit
-  int item, mb, ref, g, ngroups; unsigned base_lo, base_hi;
-  int gx0, gy0;                   // origin of the group's centre box (pel)
-  int ncx, ncy, ngy, gc, ncbA, ntaskA, npb, ntask;
 };
 
 struct FsWarp { unsigned short sat[2][28]; };
@@ -393,210 +398,248 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, vo
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
-struct FsCtaStats { int err, nhits, ngroups, nitems; unsigned long long cyc[6]; };   // cyc: task, exact, advance, idle, total, tma-wait (warp cycles)
+// Ordering between the shared-memory accesses of the claim / completion protocol: CTA-scope acquire-release
+// fence (cheaper than the sequentially-consistent __threadfence_block()).
+#define FS_FENCE() asm volatile("fence.acq_rel.cta;" ::: "memory")
 
-// Called by ONE warp when the unit of buffer S is complete (or at kernel start): writes the results of a
-// finished item, fetches the buffer's next unit (next centre group of the same item, else the next item
-// of this buffer's sequence) and sets it up: parameters, centre groups, window (TMA), filter constants,
-// mv-cost tables, exact pre-pass over the centres' box.  Publishes the unit with ready_epoch, then arms
-// the task counter.
+#ifdef FS_PROFILE
+#define FS_CLOCK() clock64()
+#else
+#define FS_CLOCK() 0ll
+#endif
+
+struct FsCtaStats { int err, nhits, ngroups, nitems; unsigned long long cyc[6]; };   // cyc: task, exact, producer, -, total, tma-wait (warp cycles)
+
+// ---- producer-warp routines (called by ONE warp) -------------------------------------------------------------
+
+// Results of a finished item (me_fullsearch.c:95-102: mv += spiral[best], return min_mcost).
+template <class SLOT>
+__device__ __forceinline__ void fs_write_results(const SLOT &S, const FsArgs &a, FsCtaStats *st)
+{
+  const int lane = threadIdx.x & 31;
+  if (S.item < 0 || S.ngroups <= 0) return;
+  const size_t base = ((size_t)S.base_hi << 32) | S.base_lo;
+  for (int p = lane; p < NPART; p += 32) {
+    if (!((a.part_mask >> p) & 1ull)) continue;
+    const unsigned long long key = S.best[p];
+    const int pos = (int)(key & 0xfffffull);
+    int sx, sy; spiral_xy(pos, &sx, &sy);
+    a.mv_int[(base + p) * 2]     = (int16_t)(S.pcx[p] + 4 * sx);
+    a.mv_int[(base + p) * 2 + 1] = (int16_t)(S.pcy[p] + 4 * sy);
+    long long cost = (long long)(key >> 20);
+    if (pos == 0 && cost == (1ll << 42) && a.min_mcost > (1ll << 42)) cost = a.min_mcost;   // bound never beaten
+    a.cost_int[base + p] = cost;
+  }
+  if (lane == 0) { atomicAdd(&st->ngroups, S.ngroups); atomicAdd(&st->nitems, 1); }
+}
+
+// Everything of centre group g that does not need the window: box, geometry, window origin, filter constants
+// (from the partitions' current bounds), mv-cost tables.
 template <int PITCH, class SLOT>
-__device__ __noinline__ void fs_advance(SLOT &S, FsWarp &ws, uint8_t *win, const uint32_t *pgt, const FsArgs &a,
-                                        const CUtensorMap *tm, FsCtaStats *st)
+__device__ __forceinline__ void fs_setup_group(SLOT &S, int g, const FsArgs &a)
+{
+  constexpr int K = FS_K;
+  const int lane = threadIdx.x & 31, R = a.R;
+  int gx0 = 0x7fff, gx1 = -0x7fff, gy0 = 0x7fff, gy1 = -0x7fff, qx0 = 0x7fff, qx1 = -0x7fff, qy0 = 0x7fff, qy1 = -0x7fff;
+  for (int p = lane; p < NPART; p += 32) {
+    if (S.pgrp[p] != g) continue;
+    const int cx = S.pcx[p] >> 2, cy = S.pcy[p] >> 2, px = S.ppx[p], py = S.ppy[p];
+    gx0 = min(gx0, cx); gx1 = max(gx1, cx); gy0 = min(gy0, cy); gy1 = max(gy1, cy);
+    qx0 = min(qx0, px); qx1 = max(qx1, px); qy0 = min(qy0, py); qy1 = max(qy1, py);
+  }
+  gx0 = __reduce_min_sync(0xffffffffu, gx0); gx1 = __reduce_max_sync(0xffffffffu, gx1);
+  gy0 = __reduce_min_sync(0xffffffffu, gy0); gy1 = __reduce_max_sync(0xffffffffu, gy1);
+  qx0 = __reduce_min_sync(0xffffffffu, qx0); qx1 = __reduce_max_sync(0xffffffffu, qx1);
+  qy0 = __reduce_min_sync(0xffffffffu, qy0); qy1 = __reduce_max_sync(0xffffffffu, qy1);
+  const int spanx = gx1 - gx0, spany = gy1 - gy0;
+  const int ncx = 2 * R + 1 + spanx, ncy = 2 * R + 1 + spany;
+  const int ngy = (ncy + K - 1) / K;
+  const int ncb = (ncx + 63) >> 6, wlast = ncx - 64 * (ncb - 1);
+  const int ncbA = wlast <= FS_BMAX ? ncb - 1 : ncb;
+  int npb = 0;
+  if (ncbA < ncb) npb = wlast <= 4 ? wlast : (wlast <= 8 ? 4 : wlast - 4);
+  const int mbx = S.mb % a.mbw, mby = S.mb / a.mbw;
+  const int x0 = mbx * 16 + gx0 - R + a.spad, y0 = mby * 16 + gy0 - R + a.spad;
+  // ---- filter constants: partitions of other groups never pass ----
+  if (lane < 20) S.Cw[lane] = 0;
+  if (lane == 20) S.C16 = 0;
+  __syncwarp();
+  for (int p = lane; p < NPART; p += 32) {
+    if (S.pgrp[p] != g) continue;
+    S.pex[p] = (signed char)((S.pcx[p] >> 2) - gx0); S.pey[p] = (signed char)((S.pcy[p] >> 2) - gy0);
+    set_threshold(S, p, S.best[p]);
+  }
+  // ---- lower bound of the mv cost per window column / row: every partition of the group sees the same
+  //      displacement 4*(g0 + d - R); bits is monotone in |mv - pred|, so the distance to the predictors'
+  //      [min,max] interval bounds every partition's term from below ----
+  for (int i = lane; i < ncx + ncy + K + 4; i += 32) {
+    const bool isy = i >= ncx + 4;
+    const int d = isy ? i - ncx - 4 : i;
+    const int mv = 4 * ((isy ? gy0 : gx0) + d - R);
+    const int lo = isy ? qy0 : qx0, hi = isy ? qy1 : qx1;
+    const int dist = max(0, max(lo - mv, mv - hi));
+    const long long v = ((long long)a.lambda_f * mvbits(dist)) >> 5;
+    (isy ? S.mys : S.mxs)[d] = (unsigned short)(v > FS_MCAP ? FS_MCAP : v);
+  }
+  {                                                // type-A tasks: row groups from the centre outwards, per column block
+    const int gc = min(ngy - 1, (R + (spany >> 1)) / K), lo = gc, hi = ngy - 1 - gc, mn = min(lo, hi);
+    for (int t = lane; t < ncbA * ngy && t < 96; t += 32) {
+      const int cb = t / ngy, k = t - cb * ngy;
+      const int gy = k <= 2 * mn ? ((k & 1) ? gc + ((k + 1) >> 1) : gc - (k >> 1)) : (lo > hi ? gc - (k - hi) : gc + (k - lo));
+      S.ttab[t] = (unsigned short)((gy * K) | (cb << 8));
+    }
+  }
+  if (lane == 0) {
+    S.g = g; S.gx0 = gx0; S.gy0 = gy0; S.spanx = spanx; S.spany = spany;
+    S.wx0 = x0; S.wy0 = y0;
+    S.inside = (x0 >= 0 && y0 >= 0 && x0 + ncx + 15 <= a.Wq && y0 + ncy + 15 <= a.Hq && !(a.flags & 1)) ? 1 : 0;
+    S.ncx = ncx; S.ncy = ncy; S.ngy = ngy; S.gc = min(ngy - 1, (R + (spany >> 1)) / K);
+    S.ncbA = ncbA; S.ntaskA = ncbA * ngy; S.npb = npb; S.ntask = ncbA * ngy + (npb * ngy + 31) / 32;
+  }
+  __syncwarp();
+}
+
+// Loads item `item` (handed out in order by a global counter: load balance) into slot S and prepares its first
+// centre group; fetches the index of the following item into `item` while the loads are in flight.  Returns false
+// when the items are exhausted.  Touches no window: runs while the workers are busy.
+template <int PITCH, class SLOT>
+__device__ __noinline__ bool fs_prepare(SLOT &S, int &item_io, const FsArgs &a, FsCtaStats *st)
+{
+  const int lane = threadIdx.x & 31, R = a.R;
+  for (;;) {
+    const int item = item_io;
+    if (item >= a.nitems) { if (lane == 0) { S.item = -1; S.ngroups = 0; } __syncwarp(); return false; }
+    int nxt = 0;
+    if (lane == 0) nxt = atomicAdd(a.work_counter, 1);
+    // ---- per-partition parameters, current MB: every load is issued before the first use ----
+    const int mb = a.mb_first + item / a.refs_per_mb, ref = a.ref_first + item % a.refs_per_mb;
+    const int mbx = mb % a.mbw, mby = mb / a.mbw;
+    const size_t base = (a.abs_index ? ((size_t)mb * a.nrefs + ref) : (size_t)item) * NPART;
+    const uint32_t *cen32 = reinterpret_cast<const uint32_t *>(a.center) + base, *prd32 = reinterpret_cast<const uint32_t *>(a.pred) + base;
+    const bool has1 = lane + 32 < NPART;
+    const uint32_t c0 = cen32[lane], q0 = prd32[lane], c1 = has1 ? cen32[lane + 32] : 0u, q1 = has1 ? prd32[lane + 32] : 0u;
+    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(a.cur + (size_t)(mby * 16 + (lane >> 2)) * a.cur_pitch + mbx * 16 + (lane & 3) * 4);
+    const uint32_t w1 = *reinterpret_cast<const uint32_t *>(a.cur + (size_t)(mby * 16 + 8 + (lane >> 2)) * a.cur_pitch + mbx * 16 + (lane & 3) * 4);
+    const long long mm = a.min_mcost < 0 ? 0 : (a.min_mcost > (1ll << 42) ? (1ll << 42) : a.min_mcost);
+    int bx0 = 0x7fff, bx1 = -0x7fff, by0 = 0x7fff, by1 = -0x7fff;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int p = lane + 32 * h;
+      if (p >= NPART) continue;
+      const uint32_t cw = h ? c1 : c0, qw = h ? q1 : q0;
+      const int cx = (short)(cw & 0xffffu), cy = (short)(cw >> 16);
+      const bool act = (a.part_mask >> p) & 1ull;
+      const PartGeom gm = part_geom(p);
+      S.pcx[p] = (short)cx; S.pcy[p] = (short)cy;
+      S.ppx[p] = (short)(qw & 0xffffu); S.ppy[p] = (short)(qw >> 16);
+      S.psr[p] = (short)(a.restrict_mode < 0 ? a.sr_override : block_search_range(R, a.restrict_mode, ref, gm.bt));
+      S.pgrp[p] = act ? 0 : -1;
+      S.best[p] = ((unsigned long long)mm << 20);
+      if (act) {
+        if ((cx | cy) & 3) st->err = 1;            // sub-pel centres are not a full-search input
+        bx0 = min(bx0, cx >> 2); bx1 = max(bx1, cx >> 2); by0 = min(by0, cy >> 2); by1 = max(by1, cy >> 2);
+      }
+    }
+    S.cur[lane] = w0; S.cur[lane + 32] = w1;
+    item_io = __shfl_sync(0xffffffffu, nxt, 0);
+    bx0 = __reduce_min_sync(0xffffffffu, bx0); bx1 = __reduce_max_sync(0xffffffffu, bx1);
+    by0 = __reduce_min_sync(0xffffffffu, by0); by1 = __reduce_max_sync(0xffffffffu, by1);
+    int ng = bx1 >= bx0 ? 1 : 0;
+    __syncwarp();
+    // ---- cluster partitions whose centres fit in one FS_SMAX box (usually all of them) ----
+    if (ng && (bx1 - bx0 > FS_SMAX || by1 - by0 > FS_SMAX)) {      // general case: greedy clustering (serial, rare)
+      if (lane == 0) {
+        short *gx0 = reinterpret_cast<short *>(S.mxs), *gx1 = gx0 + NPART, *gy0 = gx1 + NPART, *gy1 = gy0 + NPART;   // scratch
+        ng = 0;
+        for (int p = 0; p < NPART; p++) {
+          if (S.pgrp[p] < 0) continue;
+          const int cx = S.pcx[p] >> 2, cy = S.pcy[p] >> 2;
+          int gg = -1;
+          for (int q = 0; q < ng; q++) {
+            const int nx0 = min((int)gx0[q], cx), nx1 = max((int)gx1[q], cx), ny0 = min((int)gy0[q], cy), ny1 = max((int)gy1[q], cy);
+            if (nx1 - nx0 <= FS_SMAX && ny1 - ny0 <= FS_SMAX) { gg = q; gx0[q] = nx0; gx1[q] = nx1; gy0[q] = ny0; gy1[q] = ny1; break; }
+          }
+          if (gg < 0) { gg = ng++; gx0[gg] = gx1[gg] = cx; gy0[gg] = gy1[gg] = cy; }
+          S.pgrp[p] = (signed char)gg;
+        }
+      }
+      ng = __shfl_sync(0xffffffffu, ng, 0);
+    }
+    if (lane == 0) {
+      S.item = item; S.mb = mb; S.ref = ref; S.base_lo = (unsigned)base; S.base_hi = (unsigned)((unsigned long long)base >> 32);
+      S.ngroups = ng; S.g = 0;
+    }
+    __syncwarp();
+    if (ng == 0) continue;                         // no active partition: nothing to search, nothing to write
+    fs_setup_group<PITCH>(S, 0, a);
+    return true;
+  }
+}
+
+// Attaches the prepared unit S to window buffer C: window (TMA, or clamped staging at the picture's far
+// outside), exact pre-pass over the centres' box (initial bounds), then publishes the unit: ready_epoch first,
+// task counter second (see the worker loop).
+template <int PITCH, class SLOT>
+__device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWarp &ws, uint8_t *win, const uint32_t *pgt,
+                                         const FsArgs &a, const CUtensorMap *tm, FsCtaStats *st)
 {
   constexpr int K = FS_K;
   const FsGeom G = fs_geom(a.R);
   const int lane = threadIdx.x & 31, R = a.R;
-  const long long t_adv0 = clock64();
-  for (;;) {
-    int g;
-    if (S.item >= 0 && S.g + 1 < S.ngroups) g = S.g + 1;
-    else {
-      if (S.item >= 0 && S.ngroups > 0) {          // ---- results of the finished item ----
-        const size_t base = ((size_t)S.base_hi << 32) | S.base_lo;
-        for (int p = lane; p < NPART; p += 32) {
-          if (!((a.part_mask >> p) & 1ull)) continue;
-          const unsigned long long key = S.best[p];
-          const int pos = (int)(key & 0xfffffull);
-          int sx, sy; spiral_xy(pos, &sx, &sy);
-          a.mv_int[(base + p) * 2]     = (int16_t)(S.pcx[p] + 4 * sx);
-          a.mv_int[(base + p) * 2 + 1] = (int16_t)(S.pcy[p] + 4 * sy);
-          long long cost = (long long)(key >> 20);
-          if (pos == 0 && cost == (1ll << 42) && a.min_mcost > (1ll << 42)) cost = a.min_mcost;   // bound never beaten
-          a.cost_int[base + p] = cost;
-        }
-        if (lane == 0) { atomicAdd(&st->ngroups, S.ngroups); atomicAdd(&st->nitems, 1); }
-      }
-      __syncwarp();
-      int item = 0;                                // items are handed out in order by a global counter (load balance)
-      if (lane == 0) item = atomicAdd(a.work_counter, 1);
-      item = __shfl_sync(0xffffffffu, item, 0);
-      if (item >= a.nitems) {
-        if (lane == 0) { S.item = -1; S.ngroups = 0; __threadfence_block(); *reinterpret_cast<volatile int *>(&S.ended) = 1; }
-        __syncwarp();
-        return;
-      }
-      // ---- per-partition parameters, current MB ----
-      const int mb = a.mb_first + item / a.refs_per_mb, ref = a.ref_first + item % a.refs_per_mb;
-      const int mbx = mb % a.mbw, mby = mb / a.mbw;
-      const size_t base = (a.abs_index ? ((size_t)mb * a.nrefs + ref) : (size_t)item) * NPART;
-      int bx0 = 0x7fff, bx1 = -0x7fff, by0 = 0x7fff, by1 = -0x7fff;
-      for (int p = lane; p < NPART; p += 32) {
-        const bool act = (a.part_mask >> p) & 1ull;
-        const PartGeom gm = part_geom(p);
-        const int cx = a.center[(base + p) * 2], cy = a.center[(base + p) * 2 + 1];
-        S.pcx[p] = (short)cx; S.pcy[p] = (short)cy;
-        S.ppx[p] = a.pred[(base + p) * 2];   S.ppy[p] = a.pred[(base + p) * 2 + 1];
-        S.psr[p] = (short)(a.restrict_mode < 0 ? a.sr_override : block_search_range(R, a.restrict_mode, ref, gm.bt));
-        S.pgrp[p] = act ? 0 : -1;
-        const long long mm = a.min_mcost < 0 ? 0 : (a.min_mcost > (1ll << 42) ? (1ll << 42) : a.min_mcost);
-        S.best[p] = ((unsigned long long)mm << 20);
-        if (act) {
-          if ((cx | cy) & 3) st->err = 1;          // sub-pel centres are not a full-search input
-          bx0 = min(bx0, cx >> 2); bx1 = max(bx1, cx >> 2); by0 = min(by0, cy >> 2); by1 = max(by1, cy >> 2);
-        }
-      }
-      for (int t = lane; t < 64; t += 32)
-        S.cur[t] = *reinterpret_cast<const uint32_t *>(a.cur + (size_t)(mby * 16 + (t >> 2)) * a.cur_pitch + mbx * 16 + (t & 3) * 4);
-      bx0 = __reduce_min_sync(0xffffffffu, bx0); bx1 = __reduce_max_sync(0xffffffffu, bx1);
-      by0 = __reduce_min_sync(0xffffffffu, by0); by1 = __reduce_max_sync(0xffffffffu, by1);
-      int ng = bx1 >= bx0 ? 1 : 0;
-      __syncwarp();
-      // ---- cluster partitions whose centres fit in one FS_SMAX box (usually all of them) ----
-      if (ng && (bx1 - bx0 > FS_SMAX || by1 - by0 > FS_SMAX)) {      // general case: greedy clustering (serial, rare)
-        if (lane == 0) {
-          short *gx0 = reinterpret_cast<short *>(S.mxs), *gx1 = gx0 + NPART, *gy0 = gx1 + NPART, *gy1 = gy0 + NPART;   // scratch
-          ng = 0;
-          for (int p = 0; p < NPART; p++) {
-            if (S.pgrp[p] < 0) continue;
-            const int cx = S.pcx[p] >> 2, cy = S.pcy[p] >> 2;
-            int gg = -1;
-            for (int q = 0; q < ng; q++) {
-              const int nx0 = min((int)gx0[q], cx), nx1 = max((int)gx1[q], cx), ny0 = min((int)gy0[q], cy), ny1 = max((int)gy1[q], cy);
-              if (nx1 - nx0 <= FS_SMAX && ny1 - ny0 <= FS_SMAX) { gg = q; gx0[q] = nx0; gx1[q] = nx1; gy0[q] = ny0; gy1[q] = ny1; break; }
-            }
-            if (gg < 0) { gg = ng++; gx0[gg] = gx1[gg] = cx; gy0[gg] = gy1[gg] = cy; }
-            S.pgrp[p] = (signed char)gg;
-          }
-        }
-        ng = __shfl_sync(0xffffffffu, ng, 0);
-      }
-      if (lane == 0) {
-        S.item = item; S.mb = mb; S.ref = ref; S.base_lo = (unsigned)base; S.base_hi = (unsigned)((unsigned long long)base >> 32);
-        S.ngroups = ng; S.g = 0;
-      }
-      __syncwarp();
-      if (ng == 0) continue;                       // no active partition: nothing to search, nothing to write
-      g = 0;
-    }
-    // ---- set up centre group g of the current item ----
-    int gx0 = 0x7fff, gx1 = -0x7fff, gy0 = 0x7fff, gy1 = -0x7fff, qx0 = 0x7fff, qx1 = -0x7fff, qy0 = 0x7fff, qy1 = -0x7fff;
-    for (int p = lane; p < NPART; p += 32) {
-      if (S.pgrp[p] != g) continue;
-      const int cx = S.pcx[p] >> 2, cy = S.pcy[p] >> 2, px = S.ppx[p], py = S.ppy[p];
-      gx0 = min(gx0, cx); gx1 = max(gx1, cx); gy0 = min(gy0, cy); gy1 = max(gy1, cy);
-      qx0 = min(qx0, px); qx1 = max(qx1, px); qy0 = min(qy0, py); qy1 = max(qy1, py);
-    }
-    gx0 = __reduce_min_sync(0xffffffffu, gx0); gx1 = __reduce_max_sync(0xffffffffu, gx1);
-    gy0 = __reduce_min_sync(0xffffffffu, gy0); gy1 = __reduce_max_sync(0xffffffffu, gy1);
-    qx0 = __reduce_min_sync(0xffffffffu, qx0); qx1 = __reduce_max_sync(0xffffffffu, qx1);
-    qy0 = __reduce_min_sync(0xffffffffu, qy0); qy1 = __reduce_max_sync(0xffffffffu, qy1);
-    const int spanx = gx1 - gx0, spany = gy1 - gy0;
-    const int ncx = 2 * R + 1 + spanx, ncy = 2 * R + 1 + spany;
-    const int ngy = (ncy + K - 1) / K;
-    const int ncb = (ncx + 63) >> 6, wlast = ncx - 64 * (ncb - 1);
-    const int ncbA = wlast <= FS_BMAX ? ncb - 1 : ncb;
-    int npb = 0;
-    if (ncbA < ncb) npb = wlast <= 4 ? wlast : (wlast <= 8 ? 4 : wlast - 4);
-    const int ntask = ncbA * ngy + (npb * ngy + 31) / 32;
-    const int mbx = S.mb % a.mbw, mby = S.mb / a.mbw;
-    const int x0 = mbx * 16 + gx0 - R + a.spad, y0 = mby * 16 + gy0 - R + a.spad;
-    const bool inside = x0 >= 0 && y0 >= 0 && x0 + ncx + 15 <= a.Wq && y0 + ncy + 15 <= a.Hq && !(a.flags & 1);
-    const int ep = S.epoch + 1;
-    if (inside) {                                  // ---- window: four TMA boxes (copy c starts c bytes right, c rows up) ----
-      if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&S.mbar, 4u * PITCH * G.rows);
-#pragma unroll
-        for (int c = 0; c < 4; c++)      // a TMA box must start on a 16-byte boundary: take plane (x0+c)&15 at the aligned column
-          tma_load_3d(win + c * G.copy_bytes, tm, &S.mbar, (x0 + c) & ~15, y0 - c, S.ref * 16 + ((x0 + c) & 15));
-      }
-    } else {                                       // window leaves the search plane: per-pixel coordinate clamp
-      const uint8_t *plane = a.spl + (size_t)S.ref * 16 * a.Wq * a.Hq;     // shift-0 plane
-      const int nrows = min(K * ngy + 15, G.rows - 3), wpw = PITCH >> 2;
-      for (int r = 0; r < nrows; r++) {
-        const uint8_t *grow = plane + (size_t)iclamp(y0 + r, 0, a.Hq - 1) * a.Wq;
-        for (int j = lane; j < wpw; j += 32) {
-          uint32_t b[7];
-#pragma unroll
-          for (int k = 0; k < 7; k++) b[k] = grow[iclamp(x0 + 4 * j + k, 0, a.Wq - 1)];
-#pragma unroll
-          for (int c = 0; c < 4; c++)
-            reinterpret_cast<uint32_t *>(win + c * G.copy_bytes + (r + c) * PITCH)[j] = b[c] | (b[c + 1] << 8) | (b[c + 2] << 16) | (b[c + 3] << 24);
-        }
-      }
-    }
-    // ---- filter constants: partitions of other groups never pass ----
-    if (lane < 20) S.Cw[lane] = 0;
-    if (lane == 20) S.C16 = 0;
-    __syncwarp();
-    for (int p = lane; p < NPART; p += 32) {
-      if (S.pgrp[p] != g) continue;
-      S.pex[p] = (signed char)((S.pcx[p] >> 2) - gx0); S.pey[p] = (signed char)((S.pcy[p] >> 2) - gy0);
-      set_threshold(S, p, S.best[p]);
-    }
-    // ---- lower bound of the mv cost per window column / row: every partition of the group sees the same
-    //      displacement 4*(g0 + d - R); bits is monotone in |mv - pred|, so the distance to the predictors'
-    //      [min,max] interval bounds every partition's term from below ----
-    for (int i = lane; i < ncx + ncy + K + 4; i += 32) {
-      const bool isy = i >= ncx + 4;
-      const int d = isy ? i - ncx - 4 : i;
-      const int mv = 4 * ((isy ? gy0 : gx0) + d - R);
-      const int lo = isy ? qy0 : qx0, hi = isy ? qy1 : qx1;
-      const int dist = max(0, max(lo - mv, mv - hi));
-      const long long v = ((long long)a.lambda_f * mvbits(dist)) >> 5;
-      (isy ? S.mys : S.mxs)[d] = (unsigned short)(v > FS_MCAP ? FS_MCAP : v);
-    }
+  const int ep = C.epoch + 1;
+  const int x0 = S.wx0, y0 = S.wy0;
+  if (S.inside) {                                  // ---- window: four TMA boxes (copy c starts c bytes right, c rows up) ----
     if (lane == 0) {
-      S.g = g; S.gx0 = gx0; S.gy0 = gy0;
-      S.ncx = ncx; S.ncy = ncy; S.ngy = ngy; S.gc = min(ngy - 1, (R + (spany >> 1)) / K);
-      S.ncbA = ncbA; S.ntaskA = ncbA * ngy; S.npb = npb; S.ntask = ntask;
-      S.done = 0; S.epoch = ep;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&C.mbar, 4u * PITCH * G.rows);
+#pragma unroll
+      for (int c = 0; c < 4; c++)      // a TMA box must start on a 16-byte boundary: take plane (x0+c)&15 at the aligned column
+        tma_load_3d(win + c * G.copy_bytes, tm, &C.mbar, (x0 + c) & ~15, y0 - c, S.ref * 16 + ((x0 + c) & 15));
     }
     __syncwarp();
-    if (inside) {
-      const uint32_t parity = (uint32_t)S.tma_uses & 1u;
-      const long long tw0 = clock64();
-      while (!mbar_try_wait(&S.mbar, parity)) { }
-      if (lane == 0) atomicAdd(&st->cyc[5], (unsigned long long)(clock64() - tw0));
-      __syncwarp();
-      if (lane == 0) S.tma_uses++;
-    }
+    const uint32_t parity = (uint32_t)C.tma_uses & 1u;
+    const long long tw0 = clock64();
+    while (!mbar_try_wait(&C.mbar, parity)) { }
     __syncwarp();
-    // ---- initial bounds: exact pre-pass over the centres' box ----
-    {
-      const int xlo = max(0, R - FS_PRE), ylo = max(0, R - FS_PRE);
-      const int pw = min(ncx - 1, R + spanx + FS_PRE) - xlo + 1, ph = min(ncy - 1, R + spany + FS_PRE) - ylo + 1;
-      const int total = pw * ph;
-      for (int i0 = 0; i0 < total; i0 += 2) {
-        const int i1 = i0 + 1;
-        const bool v1 = i1 < total;
-        const int dx0 = xlo + i0 % pw, dy0 = ylo + i0 / pw;
-        const int dx1 = v1 ? xlo + i1 % pw : dx0, dy1 = v1 ? ylo + i1 / pw : dy0;
-        fs_exact2<PITCH>(S, ws, win, G.copy_bytes, pgt, dx0, dy0, dx1, dy1, v1, R, g, a.lambda_f);
+    if (lane == 0) { C.tma_uses++; atomicAdd(&st->cyc[5], (unsigned long long)(clock64() - tw0)); }
+  } else {                                         // window leaves the search plane: per-pixel coordinate clamp
+    const uint8_t *plane = a.spl + (size_t)S.ref * 16 * a.Wq * a.Hq;     // shift-0 plane
+    const int nrows = min(K * S.ngy + 15, G.rows - 3), wpw = PITCH >> 2;
+    for (int r = 0; r < nrows; r++) {
+      const uint8_t *grow = plane + (size_t)iclamp(y0 + r, 0, a.Hq - 1) * a.Wq;
+      for (int j = lane; j < wpw; j += 32) {
+        uint32_t b[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) b[k] = grow[iclamp(x0 + 4 * j + k, 0, a.Wq - 1)];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          reinterpret_cast<uint32_t *>(win + c * G.copy_bytes + (r + c) * PITCH)[j] = b[c] | (b[c + 1] << 8) | (b[c + 2] << 16) | (b[c + 3] << 24);
       }
     }
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      *reinterpret_cast<volatile int *>(&S.ready_epoch) = ep;
-      __threadfence_block();
-      atomicExch(&S.next, (ep & 0x7ff) << 20);
-      atomicAdd(&st->cyc[2], (unsigned long long)(clock64() - t_adv0));
-    }
-    __syncwarp();
-    return;
   }
+  __syncwarp();
+  // ---- initial bounds: exact pre-pass over the centres' box ----
+  {
+    const int xlo = max(0, R - FS_PRE), ylo = max(0, R - FS_PRE);
+    const int pw = min(S.ncx - 1, R + S.spanx + FS_PRE) - xlo + 1, ph = min(S.ncy - 1, R + S.spany + FS_PRE) - ylo + 1;
+    const int total = pw * ph;
+    for (int i0 = 0; i0 < total; i0 += 2) {
+      const int i1 = i0 + 1;
+      const bool v1 = i1 < total;
+      const int dx0 = xlo + i0 % pw, dy0 = ylo + i0 / pw;
+      const int dx1 = v1 ? xlo + i1 % pw : dx0, dy1 = v1 ? ylo + i1 / pw : dy0;
+      fs_exact2<PITCH>(S, ws, win, G.copy_bytes, pgt, dx0, dy0, dx1, dy1, v1, R, S.g, a.lambda_f);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    C.slot = slot_index; C.ntask = S.ntask; C.done = 0; C.epoch = ep;
+    __threadfence_block();
+    *reinterpret_cast<volatile int *>(&C.ready_epoch) = ep;
+    __threadfence_block();
+    atomicExch(&C.next, (ep & 0x7ff) << 20);
+  }
+  __syncwarp();
 }
 
 template <int PITCH, int NWORK, int MINB>
@@ -604,7 +647,8 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
 {
   using SLOT = FsSlotT<PITCH>;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ SLOT SS[2];
+  __shared__ SLOT SS[3];                           // two attached to the window buffers, one being prepared
+  __shared__ FsCtl CB[2];
   constexpr int NT = (NWORK + 1) * 32;
   __shared__ FsWarp WS[NWORK + 1];
   __shared__ uint32_t pgt[NPART];
@@ -621,122 +665,152 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
   for (int i = tid; i < (NWORK + 1) * 2 * 28; i += NT) (&WS[0].sat[0][0])[i] = 0;
   if (tid == 0) { st.err = 0; st.nhits = 0; st.ngroups = 0; st.nitems = 0; for (int i = 0; i < 6; i++) st.cyc[i] = 0; }
   if (tid < 2) {
-    SLOT &S = SS[tid];
-    S.ready_epoch = 0; S.finished_epoch = 0; S.next = 0; S.done = 0; S.ended = 0; S.epoch = 0; S.tma_uses = 0; S.ntask = 0;
-    S.g = 0; S.ngroups = 0;
-    S.item = -1;
-    mbar_init(&S.mbar, 1);
+    FsCtl &C = CB[tid];
+    C.ready_epoch = 0; C.finished_epoch = 0; C.next = 0; C.done = 0; C.ended = 0; C.epoch = 0; C.tma_uses = 0; C.ntask = 0; C.slot = tid;
+    mbar_init(&C.mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < 3) { SS[tid].item = -1; SS[tid].ngroups = 0; SS[tid].g = 0; }
   __syncthreads();
+
   if (warp == NWORK) {
-    // ---- producer warp: sets up both buffers, then re-arms whichever buffer's unit the workers have completed ----
-    int seen0 = 0, seen1 = 0;
-    fs_advance<PITCH>(SS[0], WS[warp], smem, pgt, a, tmap, &st);
-    fs_advance<PITCH>(SS[1], WS[warp], smem + G.slot_bytes, pgt, a, tmap, &st);
+    // ---- producer warp: keeps one unit prepared ahead; when the workers complete a buffer's unit it attaches
+    //      the prepared unit to that buffer, then writes the finished item's results and prepares the next ----
+    const long long t_p0 = clock64();
+    int seen0 = 0, seen1 = 0, stage = 2, item = 0;
+    if (lane == 0) item = atomicAdd(a.work_counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    bool staged = fs_prepare<PITCH>(SS[0], item, a, &st);
+    for (int b = 0; b < 2; b++) {
+      if (staged) {
+        fs_activate<PITCH>(CB[b], SS[b], b, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st);
+        staged = fs_prepare<PITCH>(SS[b == 0 ? 1 : 2], item, a, &st);
+      } else if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int *>(&CB[b].ended) = 1; }
+    }
     for (;;) {
       int nend = 0; bool any = false;
 #pragma unroll 1
       for (int b = 0; b < 2; b++) {
-        SLOT &S = SS[b];
-        if (*reinterpret_cast<volatile int *>(&S.ended)) { nend++; continue; }
-        const int fin = *reinterpret_cast<volatile int *>(&S.finished_epoch);
+        FsCtl &C = CB[b];
+        if (*reinterpret_cast<volatile int *>(&C.ended)) { nend++; continue; }
+        const int fin = *reinterpret_cast<volatile int *>(&C.finished_epoch);
         if (fin == (b ? seen1 : seen0)) continue;
         __threadfence_block();
         if (b) seen1 = fin; else seen0 = fin;
-        fs_advance<PITCH>(S, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st);
         any = true;
+        const int old = C.slot;
+        SLOT &O = SS[old];
+        if (O.g + 1 < O.ngroups) {                   // next centre group of the same item, in place (rare)
+          fs_setup_group<PITCH>(O, O.g + 1, a);
+          fs_activate<PITCH>(C, O, old, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st);
+        } else if (staged) {
+          fs_activate<PITCH>(C, SS[stage], stage, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st);
+          fs_write_results(O, a, &st);
+          __syncwarp();
+          stage = old;
+          staged = fs_prepare<PITCH>(SS[stage], item, a, &st);
+        } else {
+          fs_write_results(O, a, &st);
+          __syncwarp();
+          if (lane == 0) { O.item = -1; __threadfence_block(); *reinterpret_cast<volatile int *>(&C.ended) = 1; }
+        }
       }
       if (nend == 2) break;
-      if (!any) __nanosleep(100);
+      if (!any) __nanosleep(1000);
     }
+    if (lane == 0) atomicAdd(&st.cyc[2], (unsigned long long)(clock64() - t_p0));
   } else {
-
-  // Warps drain ONE buffer at a time (pref) and move to the other only when pref has no task left to claim, so
-  // the two units finish staggered and the set-up of a buffer's next unit overlaps the other buffer's tasks.
+  // ---- worker warps.  They drain ONE buffer at a time (pref) and move to the other only when pref has no task
+  //      left to claim, so the two units finish staggered and the producer's work overlaps the other buffer ----
   int ex0 = 0, ex1 = 0, nh = 0, pref = 0;
   long long c_task = 0, c_exact = 0;
   const long long t_begin = clock64();
   unsigned long long g_begin; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_begin));
+  long long c_idle = 0;
   for (;;) {
     bool any = false; int nend = 0;
+    const long long ti0 = FS_CLOCK();
 #pragma unroll 1
     for (int k = 0; k < 2 && !any; k++) {
       const int b = pref ^ k;
-      SLOT &S = SS[b];
-      const int ep0 = *reinterpret_cast<volatile int *>(&S.ready_epoch);
-      if (ep0 == (b ? ex1 : ex0)) { if (*reinterpret_cast<volatile int *>(&S.ended)) nend++; continue; }
+      FsCtl &C = CB[b];
+      const int ep0 = *reinterpret_cast<volatile int *>(&C.ready_epoch);
+      if (ep0 == (b ? ex1 : ex0)) { if (*reinterpret_cast<volatile int *>(&C.ended)) nend++; continue; }
       int c = 0;
-      if (lane == 0) c = atomicAdd(&S.next, 1);
+      if (lane == 0) c = atomicAdd(&C.next, FS_CLAIM);
       c = __shfl_sync(0xffffffffu, c, 0);
-      const int ep = *reinterpret_cast<volatile int *>(&S.ready_epoch);
+      const int ep = *reinterpret_cast<volatile int *>(&C.ready_epoch);
       if ((c >> 20) != (ep & 0x7ff)) continue;       // counter not (yet) armed for the published epoch
-      __threadfence_block();
-      const int t = c & 0xfffff;
-      const int ntask = *reinterpret_cast<volatile int *>(&S.ntask);
-      if (t >= ntask) { if (b) ex1 = ep; else ex0 = ep; continue; }
+      FS_FENCE();
+      const int t0 = c & 0xfffff;
+      const int ntask = *reinterpret_cast<volatile int *>(&C.ntask);
+      if (t0 >= ntask) { if (b) ex1 = ep; else ex0 = ep; continue; }
       pref = b;
       any = true;
+      SLOT &S = SS[*reinterpret_cast<volatile int *>(&C.slot)];
       uint8_t *win = smem + b * G.slot_bytes;
       const int g = S.g;
-      int dxa, dy0; bool va, vb;
-      if (t < S.ntaskA) {
-        const int cb = t / S.ngy, k = t - cb * S.ngy;
-        const int gc = S.gc, lo = gc, hi = S.ngy - 1 - gc, mn = min(lo, hi);
-        const int gy = k <= 2 * mn ? ((k & 1) ? gc + ((k + 1) >> 1) : gc - (k >> 1)) : (lo > hi ? gc - (k - hi) : gc + (k - lo));
-        dxa = 64 * cb + 8 * (lane >> 2) + (lane & 3); dy0 = gy * K;
-        va = dxa < S.ncx; vb = dxa + 4 < S.ncx;
-      } else {
-        const int job = (t - S.ntaskA) * 32 + lane;
-        const int i = job / S.ngy, gy = job - i * S.ngy;
-        dxa = 64 * S.ncbA + 8 * (i >> 2) + (i & 3); dy0 = gy * K;
-        va = i < S.npb && dxa < S.ncx; vb = va && dxa + 4 < S.ncx;
-        if (!va) dy0 = 0;
-      }
-      if (!va) dxa = 0;
-      const int cc = dxa & 3;
-      const uint8_t *wb = win + cc * G.copy_bytes + (dy0 + cc) * PITCH + (dxa >> 2) * 4;
-      const long long tt0 = clock64();
-      uint32_t pass = 0;
+      const int t1 = min(t0 + FS_CLAIM, ntask);
 #pragma unroll 1
-      for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
-        pass |= K == 4 ? fs_task4<PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one)
-                       : fs_task<5, PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
-      uint32_t vm = 0;
+      for (int t = t0; t < t1; t++) {
+        int dxa, dy0; bool va, vb;
+        if (t < S.ntaskA) {
+          const int e = S.ttab[t];
+          dxa = 64 * (e >> 8) + 8 * (lane >> 2) + (lane & 3); dy0 = e & 255;
+          va = dxa < S.ncx; vb = dxa + 4 < S.ncx;
+        } else {
+          const int job = (t - S.ntaskA) * 32 + lane;
+          const int i = job / S.ngy, gy = job - i * S.ngy;
+          dxa = 64 * S.ncbA + 8 * (i >> 2) + (i & 3); dy0 = gy * K;
+          va = i < S.npb && dxa < S.ncx; vb = va && dxa + 4 < S.ncx;
+          if (!va) dy0 = 0;
+        }
+        if (!va) dxa = 0;
+        const int cc = dxa & 3;
+        const uint8_t *wb = win + cc * G.copy_bytes + (dy0 + cc) * PITCH + (dxa >> 2) * 4;
+        const long long tt0 = FS_CLOCK();
+        uint32_t pass = 0;
+#pragma unroll 1
+        for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
+          pass |= K == 4 ? fs_task4<PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one)
+                         : fs_task<5, PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
+        uint32_t vm = 0;
 #pragma unroll
-      for (int j = 0; j < K; j++) if (dy0 + j < S.ncy) vm |= (va ? 1u << j : 0u) | (vb ? 1u << (K + j) : 0u);
-      pass &= vm;
-      const long long tt1 = clock64();
-      c_task += tt1 - tt0;
-      if (__any_sync(0xffffffffu, pass != 0)) {
-        for (int bb = 0; bb < 2 * K; bb++) {
-          uint32_t m = __ballot_sync(0xffffffffu, (pass >> bb) & 1u);
-          while (m) {
-            const int l0 = __ffs(m) - 1; m &= m - 1;
-            const bool v1 = m != 0;
-            const int l1 = v1 ? __ffs(m) - 1 : l0; m &= m - 1;
-            const int ddx = bb >= K ? 4 : 0, ddy = bb >= K ? bb - K : bb;
-            const int ex0_ = __shfl_sync(0xffffffffu, dxa, l0) + ddx, ey0 = __shfl_sync(0xffffffffu, dy0, l0) + ddy;
-            const int ex1_ = __shfl_sync(0xffffffffu, dxa, l1) + ddx, ey1 = __shfl_sync(0xffffffffu, dy0, l1) + ddy;
-            fs_exact2<PITCH>(S, WS[warp], win, G.copy_bytes, pgt, ex0_, ey0, ex1_, ey1, v1, R, g, a.lambda_f);
-            nh += v1 ? 2 : 1;
+        for (int j = 0; j < K; j++) if (dy0 + j < S.ncy) vm |= (va ? 1u << j : 0u) | (vb ? 1u << (K + j) : 0u);
+        pass &= vm;
+        const long long tt1 = FS_CLOCK();
+        c_task += tt1 - tt0;
+        if (__any_sync(0xffffffffu, pass != 0)) {
+          for (int bb = 0; bb < 2 * K; bb++) {
+            uint32_t m = __ballot_sync(0xffffffffu, (pass >> bb) & 1u);
+            while (m) {
+              const int l0 = __ffs(m) - 1; m &= m - 1;
+              const bool v1 = m != 0;
+              const int l1 = v1 ? __ffs(m) - 1 : l0; m &= m - 1;
+              const int ddx = bb >= K ? 4 : 0, ddy = bb >= K ? bb - K : bb;
+              const int ex0_ = __shfl_sync(0xffffffffu, dxa, l0) + ddx, ey0 = __shfl_sync(0xffffffffu, dy0, l0) + ddy;
+              const int ex1_ = __shfl_sync(0xffffffffu, dxa, l1) + ddx, ey1 = __shfl_sync(0xffffffffu, dy0, l1) + ddy;
+              fs_exact2<PITCH>(S, WS[warp], win, G.copy_bytes, pgt, ex0_, ey0, ex1_, ey1, v1, R, g, a.lambda_f);
+              nh += v1 ? 2 : 1;
+            }
           }
+          c_exact += FS_CLOCK() - tt1;
         }
       }
       __syncwarp();
-      c_exact += clock64() - tt1;
       int d = 0;
-      if (lane == 0) { __threadfence_block(); d = atomicAdd(&S.done, 1) + 1; }
+      if (lane == 0) { FS_FENCE(); d = atomicAdd(&C.done, t1 - t0) + (t1 - t0); }
       d = __shfl_sync(0xffffffffu, d, 0);
       if (d == ntask) {                              // unit complete: hand the buffer to the producer warp
         if (b) ex1 = ep; else ex0 = ep;
-        if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int *>(&S.finished_epoch) = ep; }
+        if (lane == 0) { FS_FENCE(); *reinterpret_cast<volatile int *>(&C.finished_epoch) = ep; }
       }
     }
     if (nend == 2) break;
-    if (!any) __nanosleep(200);
+    if (!any) { __nanosleep(200); c_idle += FS_CLOCK() - ti0; }
   }
   if (lane == 0 && nh) atomicAdd(&st.nhits, nh);
+  if (lane == 0) atomicAdd(&st.cyc[3], (unsigned long long)c_idle);
   if (lane == 0) {
     atomicAdd(&st.cyc[0], (unsigned long long)c_task); atomicAdd(&st.cyc[1], (unsigned long long)c_exact);
     atomicAdd(&st.cyc[4], (unsigned long long)(clock64() - t_begin));

@@ -1,0 +1,11 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, bench line, ncu launch list, ncu --set full of the main kernels.
+# usage (under gpurun): bash tools/gpu_round.sh TAG
+TAG=${1:-rX}
+O=gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; tail -3 $O/${TAG}_pytest.log
+timeout 600 python bench.py --steps 20 --warmup 3 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err && cat $O/${TAG}_bench.json | cut -c1-600
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > $O/${TAG}_ncu_bench.log 2>&1
+ITERS=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_sad_fs -c 1 -f -o $O/${TAG}_sad_fs python tools/prof_fs.py > $O/${TAG}_ncu1.log 2>&1
+ITERS=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_subpel_refine|k_half_planes|k_quarter_planes|k_search_plane' -c 4 -f -o $O/${TAG}_other python tools/prof_fs.py > $O/${TAG}_ncu2.log 2>&1
+tail -2 $O/${TAG}_ncu1.log $O/${TAG}_ncu2.log
