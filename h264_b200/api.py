@@ -262,6 +262,84 @@ class FractalSearcher:
         return self.L.b2fr_launch_count(self.h)
 
 
+class PoolSearcher:
+    """One b2fp context (include/b2me.h): 8x8 range blocks x 8 isometries against a pool of 2:1-averaged
+    16x16 domain blocks, cross terms on the tensor cores (tcgen05.mma kind::i8)."""
+
+    def __init__(self, range_w, range_h, domain_w, domain_h, pool_size, device=0):
+        self.L = lib()
+        self.L.b2fp_last_error.restype = C.c_char_p
+        self.L.b2fp_last_error.argtypes = [_vp]
+        self.L.b2fp_destroy.argtypes = [_vp]
+        self.L.b2fp_destroy.restype = None
+        self.L.b2fp_launch_count.restype = C.c_int64
+        self.L.b2fp_launch_count.argtypes = [_vp]
+        self.rw, self.rh, self.dw, self.dh, self.nd = range_w, range_h, domain_w, domain_h, pool_size
+        self.nr = (range_w // 8) * (range_h // 8)
+        h = _vp()
+        r = self.L.b2fp_create(C.byref(h), C.c_int(device), C.c_int(range_w), C.c_int(range_h), C.c_int(domain_w), C.c_int(domain_h), C.c_int(pool_size))
+        self.h = h
+        if r:
+            msg = self.L.b2fp_last_error(h if h else _vp(0))
+            raise B2Error(f"b2fp_create failed ({r}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b2fp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, r, what):
+        if r:
+            msg = self.L.b2fp_last_error(self.h)
+            raise B2Error(f"{what} failed ({r}): {msg.decode() if msg else ''}")
+
+    def positions(self):
+        xy = np.zeros((self.nd, 2), np.int32)
+        self._chk(self.L.b2fp_pool_positions(self.h, _p(xy)), "b2fp_pool_positions")
+        return xy
+
+    def set_planes(self, range_plane, domain_plane):
+        r = np.ascontiguousarray(range_plane, np.uint8); d = np.ascontiguousarray(domain_plane, np.uint8)
+        assert r.shape == (self.rh, self.rw) and d.shape == (self.dh, self.dw)
+        self._chk(self.L.b2fp_set_planes(self.h, _p(r), C.c_int(self.rw), _p(d), C.c_int(self.dw)), "b2fp_set_planes")
+
+    def set_planes_dev(self, range_ptr, range_stride, domain_ptr, domain_stride, stream):
+        self._chk(self.L.b2fp_set_planes_dev(self.h, _vp(range_ptr), C.c_int(range_stride), _vp(domain_ptr), C.c_int(domain_stride), _vp(stream)), "b2fp_set_planes_dev")
+
+    def search(self):
+        dom = np.zeros(self.nr, np.int32); iso = np.zeros(self.nr, np.uint8)
+        aq = np.zeros(self.nr, np.int16); beta = np.zeros(self.nr, np.int16); err = np.zeros(self.nr, np.int64)
+        self._chk(self.L.b2fp_search(self.h, _p(dom), _p(iso), _p(aq), _p(beta), _p(err)), "b2fp_search")
+        return dom, iso, aq, beta, err
+
+    def search_dev(self, dom, iso, aq, beta, err, stream):
+        self._chk(self.L.b2fp_search_dev(self.h, _vp(dom), _vp(iso), _vp(aq), _vp(beta), _vp(err), _vp(stream)), "b2fp_search_dev")
+
+    def kernel_time_ms(self, reset=True):
+        ms, n = C.c_double(), C.c_int64()
+        self._chk(self.L.b2fp_kernel_time_ms(self.h, C.byref(ms), C.byref(n), C.c_int(int(reset))), "b2fp_kernel_time_ms")
+        return ms.value, n.value
+
+    def probe_ms(self):
+        ms = C.c_double()
+        self._chk(self.L.b2fp_probe(self.h, C.byref(ms)), "b2fp_probe")
+        return ms.value
+
+    def stats(self, reset=True):
+        out = (C.c_int64 * 3)()
+        self._chk(self.L.b2fp_stats(self.h, out, C.c_int(int(reset))), "b2fp_stats")
+        return {"exact_evals": out[0], "chunk_rescans": out[1], "chunks": out[2]}
+
+    def launch_count(self):
+        return self.L.b2fp_launch_count(self.h)
+
+
 class TQParams(C.Structure):
     """b2tq_params (include/b2me.h)"""
     _fields_ = [("qp", C.c_int32), ("mode", C.c_int32), ("cavlc", C.c_int32), ("field_scan", C.c_int32),

@@ -1,0 +1,643 @@
+// fractal_pool.cu -- fractal range x domain-POOL matching on the tensor cores (BASELINE config 5).
+//
+// Every 8x8 range block (x 8 isometries) is matched against a pool of nd domain blocks (2:1-averaged 16x16
+// blocks of the domain plane).  The cross terms  Srd[r,d] = sum_k r_k d_k  over all (range-isometry, domain)
+// pairs are a dense u8 x u8 -> s32 contraction with K = 64: they run as tcgen05.mma kind::i8 tiles
+// (M = 128 range rows, N = 256 domains, K = 32 per instruction) with the accumulators in TMEM.  The per-pair
+// least-squares fit of version1's compute_rms (V1/src/compute.c:156-182: alpha = (n*Srd - Sr*Sd)/det,
+// QUAN_A, limits, collage error) and the argmin are fused in the epilogue.
+//
+// Semantics = oracle/b2_oracle_pool.c (version1 has no pool search, SURVEY Q-F1; the fit is compute_rms's,
+// evaluated in exact integer arithmetic so that the best (domain, isometry) is an exact integer argmax):
+//     num = 64*Srd - Sr*Sd, det = 64*Sd2 - Sd^2, a = trunc(100*num/det), aq = QUAN_A(a), reject aq outside
+//     [-235,400];  G = 200*aq*num - aq^2*det;  640000*rms = 640000*sum(r-beta)^2 - G;  maximise G.
+//
+// Epilogue = conservative filter + exact re-evaluation (same idea as sad_fs.cu).  K = 64 is a thin
+// contraction: one output costs the tensor pipe 64 MACs (~1/100 clk per SM) but ANY per-output work on the
+// FP32/INT pipes costs >= 1 issue slot per 32 outputs, so the epilogue, not the MMA, bounds this kernel; it
+// is therefore cut to ~2.3 instructions per output:
+//   * the accumulators are pre-loaded with 0x4B000000 (tcgen05.st), so an s32 result C reads back as the
+//     bit pattern of the float 2^23 + C: no I2F;
+//   * one FFMA gives g = 2^23 + (C - Sr*Sd/64) = 2^23 + num/64 (+-0.5);
+//   * integer 3-input max / min (VIMNMX3) over the positive float patterns of a 32-column chunk give
+//     X = max |num|/64 of the chunk; G <= 10000*num^2/det (the unquantised optimum), so the chunk can hold a
+//     winner only if  10000*(64 X)^2 / detmin(chunk) >= best G of the row.  Domains are sorted by det so that
+//     detmin(chunk) is tight.  Only then are the 32 columns (still in registers) re-examined and the
+//     survivors evaluated exactly (int64).
+//
+// Layout in HBM: operands in UMMA "core matrix" order (K-major, no swizzle): a 128-row tile is
+// [16 row groups][4 k-chunks][8 rows][16 bytes] = 8 KB contiguous, so a tile is ONE cp.async.bulk and its
+// shared-memory descriptor has LBO = 128 B (next k-chunk), SBO = 512 B (next 8-row group).
+#include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
+#include "b2_common.cuh"
+#include "../../include/b2me.h"
+
+namespace b2 {
+
+constexpr int FP_TM = 128;            // range rows (range x isometry) per CTA tile
+constexpr int FP_TN = 256;            // domains per MMA tile
+constexpr int FP_BSTAGES = 4;         // B-tile ring in shared memory
+constexpr int FP_CHUNK = 32;          // epilogue column chunk
+constexpr uint32_t FP_MAGIC = 0x4B000000u;   // float 2^23
+constexpr int FP_CT_BYTES = 2112;     // per-tile constants: float Sd[256] | int det[256] | float wchunk[8] | pad
+constexpr int FP_THREADS = 256;       // warp 0 producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 epilogue
+
+struct FpArgs {
+  const uint8_t *A;       // [mtiles][8192] range rows, core-matrix order
+  const uint8_t *B;       // [ntiles][16384] domains (sorted by det), core-matrix order
+  const uint8_t *ctile;   // [ntiles][FP_CT_BYTES] per-tile constants of the sorted domains: float Sd[256] | int det[256]
+                          //   (padding entries: -1) | float wchunk[8] = 10000*4096/detmin of each 32-column chunk
+  const int *sd;          // [ntiles*256] Sd (int)
+  const int *det;         // [ntiles*256] det (int); padding entries: -1
+  const int *orig;        // [ntiles*256] original pool index; padding: 0x7fffffff
+  const int *sr;          // [nranges] Sr per range block
+  const long long *ar;    // [nranges] 640000 * sum (r - beta)^2
+  const short *betaq;     // [nranges]
+  int mtiles, ntiles, nranges, nd;
+  int *best_dom; unsigned char *best_iso; short *aq; short *beta; long long *err_num;
+  unsigned long long *stats;   // [0] exact evaluations, [1] chunk rescans, [2] chunks
+  int probe;              // 1: tensor-only probe (no epilogue math), see b2fp_ubench_i8
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fp_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fp_mbar_init(void *bar, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fp_smem(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void fp_mbar_expect_tx(void *bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fp_smem(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void fp_mbar_arrive(void *bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fp_smem(bar)) : "memory"); }
+__device__ __forceinline__ void fp_mbar_wait(void *bar, uint32_t parity)
+{
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(fp_smem(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fp_bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(fp_smem(dst)), "l"(src), "r"(bytes), "r"(fp_smem(bar)) : "memory");
+}
+// K-major, no swizzle: LBO = 128 B between the two 16-byte k-chunks of an instruction, SBO = 512 B between 8-row groups
+__device__ __forceinline__ uint64_t fp_smem_desc(const void *p)
+{
+  const uint64_t a = (uint64_t)((fp_smem(p) & 0x3ffffu) >> 4);
+  return a | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
+}
+// kind::i8, u8 x u8 -> s32, K-major A and B, M = 128, N = 256
+constexpr uint32_t FP_IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(FP_TN >> 3) << 17) | ((uint32_t)(FP_TM >> 4) << 24);
+__device__ __forceinline__ void fp_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(FP_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void fp_commit(void *bar)
+{ asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(fp_smem(bar)) : "memory"); }
+__device__ __forceinline__ void fp_tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fp_tmem_st32_const(uint32_t taddr, uint32_t c)
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+               "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+               "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+               ::"r"(taddr), "r"(c) : "memory");
+}
+
+__host__ __device__ __forceinline__ int fp_quan_a(int x)
+{
+  int b = x % 10, c = x / 10;
+  if (b > 2 && b < 8) b = 5;
+  else if (b > 7) { b = 0; c += 1; }
+  else b = 0;
+  return c * 10 + b;
+}
+
+struct FpSmem {
+  unsigned long long b_full[FP_BSTAGES], b_empty[FP_BSTAGES];
+  unsigned long long a_full[2], a_empty[2];
+  unsigned long long t_full[2], t_empty[2];
+  uint32_t tmem_base;
+};
+
+// exact integer fit of (row with sum sr, column j of the sorted pool) given the cross term c
+__device__ __noinline__ void fp_exact(const FpArgs &a, int col, int c, int sr, long long &bestG, int &bestIdx, int &bestAq)
+{
+  const int det = a.det[col];
+  if (det < 0) return;                              // padding column
+  const int num = 64 * c - sr * a.sd[col];
+  const long long q = det == 0 ? 0 : (100ll * num) / det;
+  const int aq = fp_quan_a((int)q);
+  if (aq < -235 || aq > 400) return;
+  const long long G = 200ll * aq * num - (long long)aq * aq * det;
+  const int idx = a.orig[col];
+  if (G > bestG || (G == bestG && idx < bestIdx)) { bestG = G; bestIdx = idx; bestAq = aq; }
+}
+
+__global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_constant__ FpArgs a)
+{
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // carve: A[2][8192] | B[FP_BSTAGES][16384] | constants[FP_BSTAGES][FP_CT_BYTES] | control
+  uint8_t *sA = smem;
+  uint8_t *sB = smem + 2 * 8192;
+  uint8_t *sCt = sB + FP_BSTAGES * 16384;
+  FpSmem *S = reinterpret_cast<FpSmem *>(sCt + FP_BSTAGES * FP_CT_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < FP_BSTAGES; i++) { fp_mbar_init(&S->b_full[i], 1); fp_mbar_init(&S->b_empty[i], 1); }
+    for (int i = 0; i < 2; i++) {
+      fp_mbar_init(&S->a_full[i], 1); fp_mbar_init(&S->a_empty[i], 1);
+      fp_mbar_init(&S->t_full[i], 1); fp_mbar_init(&S->t_empty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {                                  // TMEM: all 512 columns (two 256-column accumulator stages)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(fp_smem(&S->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S->tmem_base;
+
+  const int nmt = (a.mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // M tiles of this CTA
+  if (warp == 0) {
+    // ===== producer: A tile per M tile, B tiles (+ their Sd floats) through the ring =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int i = 0; i < nmt; i++) {
+        const int mt = (int)blockIdx.x + i * (int)gridDim.x;
+        const int ab = i & 1;
+        fp_mbar_wait(&S->a_empty[ab], ((i >> 1) & 1) ^ 1);
+        fp_mbar_expect_tx(&S->a_full[ab], 8192);
+        fp_bulk_g2s(sA + ab * 8192, a.A + (size_t)mt * 8192, 8192, &S->a_full[ab]);
+        for (int nt = 0; nt < a.ntiles; nt++, it++) {
+          const int st = it % FP_BSTAGES;
+          fp_mbar_wait(&S->b_empty[st], ((it / FP_BSTAGES) & 1) ^ 1);
+          fp_mbar_expect_tx(&S->b_full[st], 16384 + FP_CT_BYTES);
+          fp_bulk_g2s(sB + st * 16384, a.B + (size_t)nt * 16384, 16384, &S->b_full[st]);
+          fp_bulk_g2s(sCt + st * FP_CT_BYTES, a.ctile + (size_t)nt * FP_CT_BYTES, FP_CT_BYTES, &S->b_full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: D[stage] (pre-loaded with the magic constant) += A x B^T, two K = 32 steps =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int i = 0; i < nmt; i++) {
+        const int ab = i & 1;
+        fp_mbar_wait(&S->a_full[ab], (i >> 1) & 1);
+        for (int nt = 0; nt < a.ntiles; nt++, it++) {
+          const int st = it % FP_BSTAGES, ts = it & 1;
+          fp_mbar_wait(&S->t_empty[ts], (it >> 1) & 1);      // phase 0 = the epilogue's initial arming of the stage
+          fp_mbar_wait(&S->b_full[st], (it / FP_BSTAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t ad = fp_smem_desc(sA + ab * 8192), bd = fp_smem_desc(sB + st * 16384);
+          fp_mma_i8(tmem + ts * FP_TN, ad, bd, 1u);
+          fp_mma_i8(tmem + ts * FP_TN, ad + (256 >> 4), bd + (256 >> 4), 1u);
+          fp_commit(&S->b_empty[st]);               // the ring slot is free once these MMAs have read it
+          fp_commit(&S->t_full[ts]);                // ... and the accumulator stage is complete
+        }
+        fp_commit(&S->a_empty[ab]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: warp q = warp & 3 owns TMEM lanes 32q..32q+31 = rows 32q.. of the tile; row = range*8 + iso =====
+    const int q = warp & 3;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < 512; c0 += 32) fp_tmem_st32_const(tl + c0, FP_MAGIC);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (lane == 0) { fp_mbar_arrive(&S->t_empty[0]); fp_mbar_arrive(&S->t_empty[1]); }
+    unsigned long long n_exact = 0, n_rescan = 0, n_chunk = 0;
+    uint32_t it = 0;
+    for (int i = 0; i < nmt; i++) {
+      const int mt = (int)blockIdx.x + i * (int)gridDim.x;
+      const int row = mt * FP_TM + q * 32 + lane;
+      const int rng = row >> 3;
+      const bool rvalid = rng < a.nranges;
+      const int sr = rvalid ? a.sr[rng] : 0;
+      const float nfr = -(float)sr * (1.0f / 64.0f);          // exact: sr < 2^14
+      long long bestG = -1; int bestIdx = 0x7fffffff, bestAq = 0;
+      float Tf = -1.0f;                                        // float of bestG, rounded down
+      for (int nt = 0; nt < a.ntiles; nt++, it++) {
+        const int st = it % FP_BSTAGES, ts = it & 1;
+        fp_mbar_wait(&S->t_full[ts], (it >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float *fdp = reinterpret_cast<const float *>(sCt + st * FP_CT_BYTES);
+        const int *detp = reinterpret_cast<const int *>(sCt + st * FP_CT_BYTES + 1024);
+        const float *wp = reinterpret_cast<const float *>(sCt + st * FP_CT_BYTES + 2048);
+        for (int ch = 0; ch < FP_TN / FP_CHUNK; ch++) {
+          uint32_t v[32];
+          fp_tmem_ld32(tl + ts * FP_TN + ch * FP_CHUNK, v);
+          fp_tmem_st32_const(tl + ts * FP_TN + ch * FP_CHUNK, FP_MAGIC);   // re-arm the accumulator
+          if (a.probe) continue;
+          float g[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++) {
+            const float4 f = reinterpret_cast<const float4 *>(fdp + ch * FP_CHUNK)[j4];
+            g[4 * j4 + 0] = fmaf(nfr, f.x, __uint_as_float(v[4 * j4 + 0]));
+            g[4 * j4 + 1] = fmaf(nfr, f.y, __uint_as_float(v[4 * j4 + 1]));
+            g[4 * j4 + 2] = fmaf(nfr, f.z, __uint_as_float(v[4 * j4 + 2]));
+            g[4 * j4 + 3] = fmaf(nfr, f.w, __uint_as_float(v[4 * j4 + 3]));
+          }
+          // all g are positive floats (2^23 + num/64, |num/64| < 2^22): their bit patterns order like integers
+          int mx = __float_as_int(g[0]), mn = mx;
+#pragma unroll
+          for (int j = 1; j < 31; j += 2) {
+            mx = __vimax3_s32(mx, __float_as_int(g[j]), __float_as_int(g[j + 1]));
+            mn = __vimin3_s32(mn, __float_as_int(g[j]), __float_as_int(g[j + 1]));
+          }
+          mx = max(mx, __float_as_int(g[31])); mn = min(mn, __float_as_int(g[31]));
+          const float X = fmaxf(__int_as_float(mx) - 8388608.0f, 8388608.0f - __int_as_float(mn)) + 0.5f;
+          const float w = wp[ch];
+          const bool pass = rvalid && (X * X) * w * 1.00001f >= Tf;
+          n_chunk++;
+          if (__any_sync(0xffffffffu, pass)) {
+            n_rescan++;
+            if (pass) {
+              const int colbase = nt * FP_TN + ch * FP_CHUNK;
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                const uint32_t vj = v[j]; const float gj = g[j];
+                const int det = detp[ch * FP_CHUNK + j];
+                if (det < 0) continue;
+                const float x = fabsf(gj - 8388608.0f) + 0.5f;
+                const float wj = det > 0 ? 40960000.0f / (float)det : 3.0e38f;
+                if ((x * x) * wj * 1.00001f < Tf) continue;
+                n_exact++;
+                fp_exact(a, colbase + j, (int)(vj - FP_MAGIC), sr, bestG, bestIdx, bestAq);
+                Tf = bestG < 0 ? -1.0f : __ll2float_rd(bestG);
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) fp_mbar_arrive(&S->t_empty[ts]);
+      }
+      // ---- the 8 isometries of a range are 8 consecutive lanes: first maximum in (iso, pool index) order ----
+      if (!a.probe) {
+        long long G = bestG; int idx = bestIdx, aq = bestAq, iso = lane & 7;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+          const long long G2 = __shfl_xor_sync(0xffffffffu, G, off);
+          const int idx2 = __shfl_xor_sync(0xffffffffu, idx, off), aq2 = __shfl_xor_sync(0xffffffffu, aq, off), iso2 = __shfl_xor_sync(0xffffffffu, iso, off);
+          if (G2 > G || (G2 == G && iso2 < iso)) { G = G2; idx = idx2; aq = aq2; iso = iso2; }
+        }
+        if ((lane & 7) == 0 && rvalid) {
+          a.best_dom[rng] = G < 0 ? -1 : idx;
+          a.best_iso[rng] = (unsigned char)(G < 0 ? 0 : iso);
+          a.aq[rng] = (short)(G < 0 ? 0 : aq);
+          a.beta[rng] = a.betaq[rng];
+          a.err_num[rng] = G < 0 ? -1 : a.ar[rng] - G;
+        }
+      }
+    }
+    if (a.stats) {                                  // [0] exact evaluations (all lanes), [1] chunk rescans, [2] chunks (per warp)
+      const unsigned ne = __reduce_add_sync(0xffffffffu, (unsigned)n_exact);
+      if (lane == 0) { atomicAdd(&a.stats[0], (unsigned long long)ne); atomicAdd(&a.stats[1], n_rescan); atomicAdd(&a.stats[2], n_chunk); }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---- preparation kernels (HBM-bound, tiny) ---------------------------------------------------------------
+__device__ __forceinline__ int fp_iso_src(int iso, int i, int j)
+{
+  switch (iso) {
+    case 0: return i * 8 + j;
+    case 1: return i * 8 + (7 - j);
+    case 2: return (7 - i) * 8 + j;
+    case 3: return (7 - i) * 8 + (7 - j);
+    case 4: return j * 8 + i;
+    case 5: return (7 - j) * 8 + i;
+    case 6: return j * 8 + (7 - i);
+    default: return (7 - j) * 8 + (7 - i);
+  }
+}
+// byte offset of element (row, k) inside the core-matrix layout (rows counted from the start of the operand)
+__device__ __forceinline__ size_t fp_blk_off(int row, int k) { return (size_t)(row >> 3) * 512 + (size_t)(k >> 4) * 128 + (row & 7) * 16 + (k & 15); }
+
+// one thread per (range, isometry) row: writes the 64 bytes of its A row; iso 0 also writes Sr, err base, beta
+__global__ void __launch_bounds__(256) k_fp_ranges(const uint8_t *__restrict__ plane, int stride, int rw, int nranges, int mrows,
+                                                   uint8_t *__restrict__ A, int *__restrict__ sr, long long *__restrict__ ar, short *__restrict__ betaq)
+{
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= mrows) return;
+  const int rng = row >> 3, iso = row & 7;
+  uint8_t px[64];
+  if (rng < nranges) {
+    const int bx = rng % (rw / 8), by = rng / (rw / 8);
+    int s = 0; long long s2 = 0;
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) { const int v = plane[(size_t)(by * 8 + i) * stride + bx * 8 + j]; px[i * 8 + j] = (uint8_t)v; s += v; s2 += v * v; }
+    if (iso == 0) {
+      const int beta = fp_quan_a(s / 64);
+      sr[rng] = s; betaq[rng] = (short)beta;
+      ar[rng] = 640000ll * (s2 - 2ll * beta * s + 64ll * beta * beta);
+    }
+  } else {
+    for (int k = 0; k < 64; k++) px[k] = 0;
+  }
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 8; j++) A[fp_blk_off(row, i * 8 + j)] = px[fp_iso_src(iso, i, j)];
+}
+
+// one thread per pool entry: 2x2-averaged 8x8 block -> tmp[p][64], det key
+__global__ void __launch_bounds__(256) k_fp_domains(const uint8_t *__restrict__ plane, int stride, const int *__restrict__ xy, int nd,
+                                                    uint8_t *__restrict__ tmp, unsigned *__restrict__ key, int *__restrict__ val, int *__restrict__ sdv)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nd) return;
+  const int x = xy[2 * p], y = xy[2 * p + 1];
+  int s = 0; long long s2 = 0;
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 8; j++) {
+      const uint8_t *q = plane + (size_t)(y + 2 * i) * stride + x + 2 * j;
+      const int v = (q[0] + q[1] + q[stride] + q[stride + 1] + 2) >> 2;
+      tmp[(size_t)p * 64 + i * 8 + j] = (uint8_t)v; s += v; s2 += v * v;
+    }
+  key[p] = (unsigned)(64 * s2 - (long long)s * s);
+  val[p] = p; sdv[p] = s;
+}
+
+// one thread per sorted column: core-matrix B rows + per-column constants; padding columns are inert
+__global__ void __launch_bounds__(256) k_fp_pack(const uint8_t *__restrict__ tmp, const unsigned *__restrict__ key_sorted, const int *__restrict__ val_sorted,
+                                                 const int *__restrict__ sdv, int nd, int ncols, uint8_t *__restrict__ B, uint8_t *__restrict__ ctile,
+                                                 int *__restrict__ sd, int *__restrict__ det, int *__restrict__ orig)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  float *fd = reinterpret_cast<float *>(ctile + (size_t)(c >> 8) * FP_CT_BYTES) + (c & 255);
+  int *dt = reinterpret_cast<int *>(ctile + (size_t)(c >> 8) * FP_CT_BYTES + 1024) + (c & 255);
+  if (c < nd) {
+    const int p = val_sorted[c];
+    for (int k = 0; k < 64; k++) B[fp_blk_off(c, k)] = tmp[(size_t)p * 64 + k];
+    *fd = (float)sdv[p]; *dt = (int)key_sorted[c]; sd[c] = sdv[p]; det[c] = (int)key_sorted[c]; orig[c] = p;
+  } else {
+    for (int k = 0; k < 64; k++) B[fp_blk_off(c, k)] = 0;
+    *fd = 0.f; *dt = -1; sd[c] = 0; det[c] = -1; orig[c] = 0x7fffffff;
+  }
+}
+__global__ void __launch_bounds__(256) k_fp_wchunk(const int *__restrict__ det, int nchunks, uint8_t *__restrict__ ctile)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  int mn = 0x7fffffff; bool any = false;
+  for (int j = 0; j < FP_CHUNK; j++) { const int d = det[c * FP_CHUNK + j]; if (d >= 0) { any = true; mn = min(mn, d); } }
+  reinterpret_cast<float *>(ctile + (size_t)(c >> 3) * FP_CT_BYTES + 2048)[c & 7] = !any ? 0.f : (mn == 0 ? 3.0e38f : 40960000.0f / (float)mn);
+}
+
+}  // namespace b2
+
+// ---- C ABI ------------------------------------------------------------------------------------------------
+using namespace b2;
+
+struct b2fp_ctx {
+  int device, rw, rh, dw, dh, nd, nranges, mrows, mtiles, ncols, ntiles, sm_count;
+  uint8_t *d_rplane, *d_dplane, *d_A, *d_B, *d_tmp;
+  int *d_xy, *d_val, *d_val_s, *d_sdv, *d_sd, *d_det, *d_orig, *d_sr;
+  unsigned *d_key, *d_key_s;
+  uint8_t *d_ctile;
+  long long *d_ar, *d_err; short *d_betaq, *d_aq, *d_beta; int *d_dom; unsigned char *d_iso;
+  unsigned long long *d_stats;
+  void *d_sort_tmp; size_t sort_bytes;
+  int32_t *h_xy;
+  cudaStream_t stream; cudaEvent_t ev0, ev1;
+  double t_ms; long long t_n; long long launches;
+  char err[512];
+};
+static char g_fperr[512] = "no context";
+#define FP_CHECK(ctx, expr)                                                                                  \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return B2ME_ECUDA;                                                                                     \
+    }                                                                                                        \
+  } while (0)
+
+extern "C" const char *b2fp_last_error(b2fp_ctx *c) { return c ? c->err : g_fperr; }
+
+// grid of nd top-left corners (same integer formula as oracle/b2_oracle_pool.c orc_pool_positions)
+static void fp_positions(int dw, int dh, int nd, int32_t *xy)
+{
+  int nx = 1;
+  while ((int64_t)nx * nx * (dh - 15) < (int64_t)nd * (dw - 15)) nx++;
+  const int ny = (nd + nx - 1) / nx;
+  for (int p = 0; p < nd; p++) {
+    const int ix = p % nx, iy = p / nx;
+    xy[2 * p]     = nx > 1 ? (int)((int64_t)ix * (dw - 16) / (nx - 1)) : 0;
+    xy[2 * p + 1] = ny > 1 ? (int)((int64_t)iy * (dh - 16) / (ny - 1)) : 0;
+  }
+}
+
+extern "C" int b2fp_create(b2fp_ctx **out, int device, int range_w, int range_h, int domain_w, int domain_h, int pool_size)
+{
+  if (!out || range_w < 8 || range_h < 8 || (range_w & 7) || (range_h & 7) || domain_w < 16 || domain_h < 16 || pool_size < 1 || pool_size > (1 << 20)) {
+    snprintf(g_fperr, sizeof(g_fperr), "b2fp_create: invalid argument");
+    return B2ME_EINVAL;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) {
+    snprintf(g_fperr, sizeof(g_fperr), "b2fp_create: no CUDA device %d (%s)", device, cudaGetErrorString(e));
+    return B2ME_ECUDA;
+  }
+  b2fp_ctx *c = (b2fp_ctx *)calloc(1, sizeof(b2fp_ctx));
+  if (!c) return B2ME_ENOMEM;
+  *out = c;
+  c->device = device; c->rw = range_w; c->rh = range_h; c->dw = domain_w; c->dh = domain_h; c->nd = pool_size;
+  c->nranges = (range_w / 8) * (range_h / 8);
+  c->mtiles = (c->nranges * 8 + FP_TM - 1) / FP_TM; c->mrows = c->mtiles * FP_TM;
+  c->ntiles = (pool_size + FP_TN - 1) / FP_TN; c->ncols = c->ntiles * FP_TN;
+  FP_CHECK(c, cudaSetDevice(device));
+  FP_CHECK(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  FP_CHECK(c, cudaMalloc(&c->d_rplane, (size_t)range_w * range_h));
+  FP_CHECK(c, cudaMalloc(&c->d_dplane, (size_t)domain_w * domain_h));
+  FP_CHECK(c, cudaMalloc(&c->d_A, (size_t)c->mtiles * 8192));
+  FP_CHECK(c, cudaMalloc(&c->d_B, (size_t)c->ntiles * 16384));
+  FP_CHECK(c, cudaMalloc(&c->d_tmp, (size_t)pool_size * 64));
+  FP_CHECK(c, cudaMalloc(&c->d_xy, (size_t)pool_size * 2 * sizeof(int)));
+  FP_CHECK(c, cudaMalloc(&c->d_val, (size_t)pool_size * sizeof(int)));
+  FP_CHECK(c, cudaMalloc(&c->d_val_s, (size_t)pool_size * sizeof(int)));
+  FP_CHECK(c, cudaMalloc(&c->d_key, (size_t)pool_size * sizeof(unsigned)));
+  FP_CHECK(c, cudaMalloc(&c->d_key_s, (size_t)pool_size * sizeof(unsigned)));
+  FP_CHECK(c, cudaMalloc(&c->d_sdv, (size_t)pool_size * sizeof(int)));
+  FP_CHECK(c, cudaMalloc(&c->d_ctile, (size_t)c->ntiles * FP_CT_BYTES));
+  FP_CHECK(c, cudaMemset(c->d_ctile, 0, (size_t)c->ntiles * FP_CT_BYTES));
+  FP_CHECK(c, cudaMalloc(&c->d_sd, (size_t)c->ncols * sizeof(int)));
+  FP_CHECK(c, cudaMalloc(&c->d_det, (size_t)c->ncols * sizeof(int)));
+  FP_CHECK(c, cudaMalloc(&c->d_orig, (size_t)c->ncols * sizeof(int)));
+  FP_CHECK(c, cudaMalloc(&c->d_sr, (size_t)c->nranges * sizeof(int)));
+  FP_CHECK(c, cudaMalloc(&c->d_ar, (size_t)c->nranges * sizeof(long long)));
+  FP_CHECK(c, cudaMalloc(&c->d_betaq, (size_t)c->nranges * sizeof(short)));
+  FP_CHECK(c, cudaMalloc(&c->d_dom, (size_t)c->nranges * sizeof(int)));
+  FP_CHECK(c, cudaMalloc(&c->d_iso, (size_t)c->nranges));
+  FP_CHECK(c, cudaMalloc(&c->d_aq, (size_t)c->nranges * sizeof(short)));
+  FP_CHECK(c, cudaMalloc(&c->d_beta, (size_t)c->nranges * sizeof(short)));
+  FP_CHECK(c, cudaMalloc(&c->d_err, (size_t)c->nranges * sizeof(long long)));
+  FP_CHECK(c, cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long)));
+  FP_CHECK(c, cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
+  c->sort_bytes = 0;
+  FP_CHECK(c, cub::DeviceRadixSort::SortPairs(nullptr, c->sort_bytes, c->d_key, c->d_key_s, c->d_val, c->d_val_s, pool_size));
+  FP_CHECK(c, cudaMalloc(&c->d_sort_tmp, c->sort_bytes));
+  c->h_xy = (int32_t *)malloc((size_t)pool_size * 2 * sizeof(int32_t));
+  if (!c->h_xy) return B2ME_ENOMEM;
+  fp_positions(domain_w, domain_h, pool_size, c->h_xy);
+  FP_CHECK(c, cudaMemcpy(c->d_xy, c->h_xy, (size_t)pool_size * 2 * sizeof(int), cudaMemcpyHostToDevice));
+  FP_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  FP_CHECK(c, cudaEventCreate(&c->ev0));
+  FP_CHECK(c, cudaEventCreate(&c->ev1));
+  return B2ME_OK;
+}
+
+extern "C" void b2fp_destroy(b2fp_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_rplane); cudaFree(c->d_dplane); cudaFree(c->d_A); cudaFree(c->d_B); cudaFree(c->d_tmp); cudaFree(c->d_xy);
+  cudaFree(c->d_val); cudaFree(c->d_val_s); cudaFree(c->d_key); cudaFree(c->d_key_s); cudaFree(c->d_sdv); cudaFree(c->d_ctile);
+  cudaFree(c->d_sd); cudaFree(c->d_det); cudaFree(c->d_orig); cudaFree(c->d_sr); cudaFree(c->d_ar);
+  cudaFree(c->d_betaq); cudaFree(c->d_dom); cudaFree(c->d_iso); cudaFree(c->d_aq); cudaFree(c->d_beta); cudaFree(c->d_err);
+  cudaFree(c->d_stats); cudaFree(c->d_sort_tmp);
+  free(c->h_xy);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  free(c);
+}
+
+extern "C" int b2fp_pool_positions(b2fp_ctx *c, int32_t *xy)
+{
+  if (!c || !xy) return B2ME_EINVAL;
+  memcpy(xy, c->h_xy, (size_t)c->nd * 2 * sizeof(int32_t));
+  return B2ME_OK;
+}
+
+static int fp_prepare(b2fp_ctx *c, const uint8_t *rplane_dev, int rstride, const uint8_t *dplane_dev, int dstride, cudaStream_t s)
+{
+  k_fp_ranges<<<(c->mrows + 255) / 256, 256, 0, s>>>(rplane_dev, rstride, c->rw, c->nranges, c->mrows, c->d_A, c->d_sr, c->d_ar, c->d_betaq);
+  k_fp_domains<<<(c->nd + 255) / 256, 256, 0, s>>>(dplane_dev, dstride, c->d_xy, c->nd, c->d_tmp, c->d_key, c->d_val, c->d_sdv);
+  FP_CHECK(c, cudaGetLastError());
+  FP_CHECK(c, cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, c->sort_bytes, c->d_key, c->d_key_s, c->d_val, c->d_val_s, c->nd, 0, 32, s));
+  k_fp_pack<<<(c->ncols + 255) / 256, 256, 0, s>>>(c->d_tmp, c->d_key_s, c->d_val_s, c->d_sdv, c->nd, c->ncols, c->d_B, c->d_ctile, c->d_sd, c->d_det, c->d_orig);
+  k_fp_wchunk<<<(c->ncols / FP_CHUNK + 255) / 256, 256, 0, s>>>(c->d_det, c->ncols / FP_CHUNK, c->d_ctile);
+  FP_CHECK(c, cudaGetLastError());
+  c->launches += 4;
+  return B2ME_OK;
+}
+
+extern "C" int b2fp_set_planes_dev(b2fp_ctx *c, const uint8_t *range_dev, int rstride, const uint8_t *domain_dev, int dstride, void *stream)
+{
+  if (!c || !range_dev || !domain_dev || rstride < c->rw || dstride < c->dw) return B2ME_EINVAL;
+  FP_CHECK(c, cudaSetDevice(c->device));
+  return fp_prepare(c, range_dev, rstride, domain_dev, dstride, (cudaStream_t)stream);
+}
+extern "C" int b2fp_set_planes(b2fp_ctx *c, const uint8_t *range_plane, int rstride, const uint8_t *domain_plane, int dstride)
+{
+  if (!c || !range_plane || !domain_plane || rstride < c->rw || dstride < c->dw) return B2ME_EINVAL;
+  FP_CHECK(c, cudaSetDevice(c->device));
+  FP_CHECK(c, cudaMemcpy2DAsync(c->d_rplane, c->rw, range_plane, rstride, c->rw, c->rh, cudaMemcpyHostToDevice, c->stream));
+  FP_CHECK(c, cudaMemcpy2DAsync(c->d_dplane, c->dw, domain_plane, dstride, c->dw, c->dh, cudaMemcpyHostToDevice, c->stream));
+  int r = fp_prepare(c, c->d_rplane, c->rw, c->d_dplane, c->dw, c->stream);
+  if (r) return r;
+  FP_CHECK(c, cudaStreamSynchronize(c->stream));
+  return B2ME_OK;
+}
+
+static int fp_launch(b2fp_ctx *c, int probe, int32_t *dom, uint8_t *iso, int16_t *aq, int16_t *beta, int64_t *err, cudaStream_t s, int timed)
+{
+  FpArgs a;
+  a.A = c->d_A; a.B = c->d_B; a.ctile = c->d_ctile; a.sd = c->d_sd; a.det = c->d_det; a.orig = c->d_orig;
+  a.sr = c->d_sr; a.ar = c->d_ar; a.betaq = c->d_betaq;
+  a.mtiles = c->mtiles; a.ntiles = c->ntiles; a.nranges = c->nranges; a.nd = c->nd;
+  a.best_dom = dom; a.best_iso = iso; a.aq = aq; a.beta = beta; a.err_num = (long long *)err;
+  a.stats = c->d_stats; a.probe = probe;
+  const int smem = 2 * 8192 + FP_BSTAGES * 16384 + FP_BSTAGES * FP_CT_BYTES + (int)sizeof(FpSmem) + 1024;
+  static int configured = 0;
+  if (!configured) { FP_CHECK(c, cudaFuncSetAttribute(k_frac_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); configured = 1; }
+  const int grid = c->mtiles < c->sm_count ? c->mtiles : c->sm_count;
+  if (timed) cudaEventRecord(c->ev0, s);
+  // >= 116 KB of dynamic shared memory keeps ONE CTA per SM: each CTA allocates all 512 TMEM columns
+  k_frac_pool<<<grid, FP_THREADS, smem < 120 * 1024 ? 120 * 1024 : smem, s>>>(a);
+  FP_CHECK(c, cudaGetLastError());
+  if (timed) {
+    cudaEventRecord(c->ev1, s); FP_CHECK(c, cudaEventSynchronize(c->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->t_ms += ms; c->t_n++;
+  }
+  c->launches++;
+  return B2ME_OK;
+}
+
+extern "C" int b2fp_search_dev(b2fp_ctx *c, int32_t *best_dom, uint8_t *best_iso, int16_t *aq, int16_t *beta, int64_t *err_num, void *stream)
+{
+  if (!c || !best_dom || !best_iso || !aq || !beta || !err_num) return B2ME_EINVAL;
+  FP_CHECK(c, cudaSetDevice(c->device));
+  return fp_launch(c, 0, best_dom, best_iso, aq, beta, err_num, (cudaStream_t)stream, 0);
+}
+extern "C" int b2fp_search(b2fp_ctx *c, int32_t *best_dom, uint8_t *best_iso, int16_t *aq, int16_t *beta, int64_t *err_num)
+{
+  if (!c || !best_dom || !best_iso || !aq || !beta || !err_num) return B2ME_EINVAL;
+  FP_CHECK(c, cudaSetDevice(c->device));
+  int r = fp_launch(c, 0, c->d_dom, c->d_iso, c->d_aq, c->d_beta, (int64_t *)c->d_err, c->stream, 1);
+  if (r) return r;
+  const size_t n = c->nranges;
+  FP_CHECK(c, cudaMemcpyAsync(best_dom, c->d_dom, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  FP_CHECK(c, cudaMemcpyAsync(best_iso, c->d_iso, n, cudaMemcpyDeviceToHost, c->stream));
+  FP_CHECK(c, cudaMemcpyAsync(aq, c->d_aq, n * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+  FP_CHECK(c, cudaMemcpyAsync(beta, c->d_beta, n * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+  FP_CHECK(c, cudaMemcpyAsync(err_num, c->d_err, n * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  FP_CHECK(c, cudaStreamSynchronize(c->stream));
+  return B2ME_OK;
+}
+
+// Device time of k_frac_pool accumulated by b2fp_search / b2fp_probe since the last reset (CUDA events).
+extern "C" int b2fp_kernel_time_ms(b2fp_ctx *c, double *ms, int64_t *launches, int reset)
+{
+  if (!c) return B2ME_EINVAL;
+  if (ms) *ms = c->t_ms;
+  if (launches) *launches = c->t_n;
+  if (reset) { c->t_ms = 0; c->t_n = 0; }
+  return B2ME_OK;
+}
+// Tensor-only pass of the same kernel (TMA ring, MMAs, TMEM drain; no per-pair epilogue math): the measured
+// kind::i8 rate this problem shape can reach, used as the tensor roofline denominator next to the nominal peak.
+extern "C" int b2fp_probe(b2fp_ctx *c, double *ms)
+{
+  if (!c || !ms) return B2ME_EINVAL;
+  FP_CHECK(c, cudaSetDevice(c->device));
+  const double t0 = c->t_ms; const long long n0 = c->t_n;
+  int r = fp_launch(c, 1, c->d_dom, c->d_iso, c->d_aq, c->d_beta, (int64_t *)c->d_err, c->stream, 1);
+  if (r) return r;
+  *ms = c->t_ms - t0; c->t_ms = t0; c->t_n = n0;
+  return B2ME_OK;
+}
+extern "C" int b2fp_stats(b2fp_ctx *c, int64_t out[3], int reset)
+{
+  if (!c || !out) return B2ME_EINVAL;
+  FP_CHECK(c, cudaSetDevice(c->device));
+  FP_CHECK(c, cudaDeviceSynchronize());
+  unsigned long long h[4];
+  FP_CHECK(c, cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+  out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = (int64_t)h[2];
+  if (reset) FP_CHECK(c, cudaMemset(c->d_stats, 0, sizeof(h)));
+  return B2ME_OK;
+}
+extern "C" int64_t b2fp_launch_count(b2fp_ctx *c) { return c ? c->launches : 0; }

@@ -169,6 +169,38 @@ int b2fr_get_domain_table(b2fr_ctx *ctx, int plane_set, int con, int bw, int bh,
 int b2fr_get_range_table(b2fr_ctx *ctx, int con, int squares, int32_t *out);
 int64_t b2fr_launch_count(b2fr_ctx *ctx);
 
+/* ==== fractal range x domain-POOL matching (BASELINE config 5; tensor cores) ==============================
+ * Every 8x8 range block of the range plane (raster order, nr = (rw/8)*(rh/8)), in its 8 isometries, against a
+ * pool of `pool_size` domain blocks (2x2-averaged 16x16 blocks of the domain plane on a uniform grid,
+ * b2fp_pool_positions).  The cross terms are tcgen05.mma kind::i8 tiles; the per-pair fit is compute_rms's
+ * (V1/src/compute.c:156-182, QUAN_A V1/inc/defines_enc.h:591-601) in exact integer arithmetic.  version1 itself
+ * has no pool search (its full_search, V1/src/block_enc.c:1933, is b2fr_* above): the semantics are DEFINED by
+ * oracle/b2_oracle_pool.c, whose header states them.
+ *   best_dom [nr] int32  pool index of the best domain (-1: every pair rejected by the alpha limits)
+ *   best_iso [nr] uint8  isometry 0..7 of the range block (0 id, 1 mirror x, 2 mirror y, 3 rot 180, 4 transpose,
+ *                        5 rot 90 cw, 6 rot 90 ccw, 7 anti-transpose); ties: lowest isometry, then lowest index
+ *   aq       [nr] int16  100 * scale after QUAN_A;   beta [nr] int16  offset after QUAN_A
+ *   err_num  [nr] int64  640000 * collage error (rms of compute_rms) as an exact integer */
+typedef struct b2fp_ctx b2fp_ctx;
+int  b2fp_create(b2fp_ctx **out, int device, int range_w, int range_h, int domain_w, int domain_h, int pool_size);
+void b2fp_destroy(b2fp_ctx *ctx);
+const char *b2fp_last_error(b2fp_ctx *ctx);
+int b2fp_pool_positions(b2fp_ctx *ctx, int32_t *xy /* [pool_size][2] top-left corners */);
+/* uploads both planes and builds the operands: range rows x 8 isometries and the det-sorted pool, both in
+ * UMMA core-matrix order */
+int b2fp_set_planes(b2fp_ctx *ctx, const uint8_t *range_plane, int range_stride, const uint8_t *domain_plane, int domain_stride);
+int b2fp_set_planes_dev(b2fp_ctx *ctx, const uint8_t *range_dev, int range_stride, const uint8_t *domain_dev, int domain_stride, void *stream);
+int b2fp_search(b2fp_ctx *ctx, int32_t *best_dom, uint8_t *best_iso, int16_t *aq, int16_t *beta, int64_t *err_num);
+int b2fp_search_dev(b2fp_ctx *ctx, int32_t *best_dom_dev, uint8_t *best_iso_dev, int16_t *aq_dev, int16_t *beta_dev,
+                    int64_t *err_num_dev, void *stream);
+/* instrumentation: device time of k_frac_pool launched by b2fp_search (CUDA events); a tensor-only pass of the
+ * same kernel (no per-pair epilogue arithmetic) = the kind::i8 rate this shape can reach; filter counters
+ * out[0] exact evaluations, out[1] 32-column chunks re-examined, out[2] chunks */
+int b2fp_kernel_time_ms(b2fp_ctx *ctx, double *ms, int64_t *launches, int reset);
+int b2fp_probe(b2fp_ctx *ctx, double *ms);
+int b2fp_stats(b2fp_ctx *ctx, int64_t out[3], int reset);
+int64_t b2fp_launch_count(b2fp_ctx *ctx);
+
 /* ==== residual transform + quantisation + reconstruction ================================= */
 /* Parameter block = the reference's per-(plane, intra, qp) LevelQuantParams table
  * (JM/lencod/inc/global.h LevelQuantParams; q_matrix.c:566-590, q_offsets.c:163-188) plus the

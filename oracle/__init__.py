@@ -384,3 +384,45 @@ class JMQuantRef:
         f = self.L.jmq_tq4x4 if n == 4 else self.L.jmq_tq8x8
         f(self.h, C.c_int(qp), C.c_int(intra), C.c_int(nblk), _ptr(orig), _ptr(pred), _ptr(level), _ptr(run), _ptr(recon), _ptr(cost), _ptr(nz))
         return level[:, :m].astype(np.int16), run[:, :m].astype(np.uint8), recon, cost, nz.astype(np.uint8)
+
+
+# ---- fractal pool matching (oracle/b2_oracle_pool.c: DEFINES the pool-mode semantics, see its header) ----
+def pool_positions(dw, dh, nd):
+    xy = np.zeros((nd, 2), np.int32)
+    orc_lib().orc_pool_positions(C.c_int(dw), C.c_int(dh), C.c_int(nd), _ptr(xy))
+    return xy
+
+
+def pool_domain_block(plane, x, y):
+    plane = np.ascontiguousarray(plane, np.uint8)
+    blk = np.zeros(64, np.uint8)
+    orc_lib().orc_pool_domain_block(_ptr(plane), C.c_int(plane.shape[1]), C.c_int(int(x)), C.c_int(int(y)), _ptr(blk))
+    return blk
+
+
+def pool_iso(block64, iso):
+    src = np.ascontiguousarray(block64, np.uint8).reshape(64)
+    dst = np.zeros(64, np.uint8)
+    orc_lib().orc_pool_iso(_ptr(src), C.c_int(iso), _ptr(dst))
+    return dst
+
+
+def pool_rms_double(r64, d64):
+    """compute_rms's floating-point expression (V1/src/compute.c:156-182) for one pair: (rms, alpha, beta)."""
+    L = orc_lib()
+    L.orc_pool_rms_double.restype = C.c_double
+    al, be = C.c_double(), C.c_double()
+    r = np.ascontiguousarray(r64, np.uint8); d = np.ascontiguousarray(d64, np.uint8)
+    rms = L.orc_pool_rms_double(_ptr(r), _ptr(d), C.byref(al), C.byref(be))
+    return rms, al.value, be.value
+
+
+def pool_search(range_plane, domain_plane, nd):
+    r = np.ascontiguousarray(range_plane, np.uint8); d = np.ascontiguousarray(domain_plane, np.uint8)
+    rh, rw = r.shape; dh, dw = d.shape
+    nr = (rw // 8) * (rh // 8)
+    dom = np.zeros(nr, np.int32); iso = np.zeros(nr, np.uint8)
+    aq = np.zeros(nr, np.int16); beta = np.zeros(nr, np.int16); err = np.zeros(nr, np.int64)
+    orc_lib().orc_pool_search(_ptr(r), C.c_int(rw), C.c_int(rh), C.c_int(rw), _ptr(d), C.c_int(dw), C.c_int(dh), C.c_int(dw),
+                              C.c_int(nd), _ptr(dom), _ptr(iso), _ptr(aq), _ptr(beta), _ptr(err))
+    return dom, iso, aq, beta, err
