@@ -38,10 +38,13 @@ namespace b2 {
 constexpr int FP_TM = 128;            // range rows (range x isometry) per CTA tile
 constexpr int FP_TN = 256;            // domains per MMA tile
 constexpr int FP_BSTAGES = 4;         // B-tile ring in shared memory
+constexpr int FP_CSTAGES = 4;         // per-tile constants ring: a slot is reused only after the EPILOGUE of its tile
 constexpr int FP_CHUNK = 32;          // epilogue column chunk
 constexpr uint32_t FP_MAGIC = 0x4B000000u;   // float 2^23
-constexpr int FP_CT_BYTES = 2112;     // per-tile constants: float Sd[256] | int det[256] | float wchunk[8] | pad
-constexpr int FP_THREADS = 256;       // warp 0 producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 epilogue
+constexpr int FP_CT_BYTES = 3104;     // per-tile constants: float Sd[256] | int det[256] | float wcol[256] | float wchunk[8]
+constexpr int FP_EPI_GROUPS = 2;      // epilogue warp groups (4 warps each, one per TMEM lane quarter); group g takes chunks ch % 2 == g
+constexpr int FP_EPI_WARPS = 4 * FP_EPI_GROUPS;
+constexpr int FP_THREADS = 128 + 32 * FP_EPI_WARPS;   // warp 0 producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4.. epilogue
 
 struct FpArgs {
   const uint8_t *A;       // [mtiles][8192] range rows, core-matrix order
@@ -108,6 +111,17 @@ __device__ __forceinline__ void fp_tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
                : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void fp_tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32])
+{
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void fp_tmem_st32_const(uint32_t taddr, uint32_t c)
 {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -129,22 +143,11 @@ struct FpSmem {
   unsigned long long b_full[FP_BSTAGES], b_empty[FP_BSTAGES];
   unsigned long long a_full[2], a_empty[2];
   unsigned long long t_full[2], t_empty[2];
+  unsigned long long c_empty[FP_CSTAGES];
   uint32_t tmem_base;
+  long long mG[FP_TM]; int mIdx[FP_TM]; short mAq[FP_TM];   // per-row partial results of epilogue group 1, merged by group 0
+  float shareT[FP_EPI_GROUPS][FP_TM];                        // per-row thresholds exchanged between the groups once per tile
 };
-
-// exact integer fit of (row with sum sr, column j of the sorted pool) given the cross term c
-__device__ __noinline__ void fp_exact(const FpArgs &a, int col, int c, int sr, long long &bestG, int &bestIdx, int &bestAq)
-{
-  const int det = a.det[col];
-  if (det < 0) return;                              // padding column
-  const int num = 64 * c - sr * a.sd[col];
-  const long long q = det == 0 ? 0 : (100ll * num) / det;
-  const int aq = fp_quan_a((int)q);
-  if (aq < -235 || aq > 400) return;
-  const long long G = 200ll * aq * num - (long long)aq * aq * det;
-  const int idx = a.orig[col];
-  if (G > bestG || (G == bestG && idx < bestIdx)) { bestG = G; bestIdx = idx; bestAq = aq; }
-}
 
 __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_constant__ FpArgs a)
 {
@@ -153,15 +156,17 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
   uint8_t *sA = smem;
   uint8_t *sB = smem + 2 * 8192;
   uint8_t *sCt = sB + FP_BSTAGES * 16384;
-  FpSmem *S = reinterpret_cast<FpSmem *>(sCt + FP_BSTAGES * FP_CT_BYTES);
+  uint32_t *sScr = reinterpret_cast<uint32_t *>(sCt + FP_CSTAGES * FP_CT_BYTES);     // [FP_EPI_WARPS][32 columns][32 lanes] re-examination scratch
+  FpSmem *S = reinterpret_cast<FpSmem *>(reinterpret_cast<uint8_t *>(sScr) + FP_EPI_WARPS * 4096);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < FP_BSTAGES; i++) { fp_mbar_init(&S->b_full[i], 1); fp_mbar_init(&S->b_empty[i], 1); }
     for (int i = 0; i < 2; i++) {
       fp_mbar_init(&S->a_full[i], 1); fp_mbar_init(&S->a_empty[i], 1);
-      fp_mbar_init(&S->t_full[i], 1); fp_mbar_init(&S->t_empty[i], 4);
+      fp_mbar_init(&S->t_full[i], 1); fp_mbar_init(&S->t_empty[i], FP_EPI_WARPS);
     }
+    for (int i = 0; i < FP_CSTAGES; i++) fp_mbar_init(&S->c_empty[i], FP_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {                                  // TMEM: all 512 columns (two 256-column accumulator stages)
@@ -185,11 +190,12 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
         fp_mbar_expect_tx(&S->a_full[ab], 8192);
         fp_bulk_g2s(sA + ab * 8192, a.A + (size_t)mt * 8192, 8192, &S->a_full[ab]);
         for (int nt = 0; nt < a.ntiles; nt++, it++) {
-          const int st = it % FP_BSTAGES;
+          const int st = it % FP_BSTAGES, cs = it % FP_CSTAGES;
           fp_mbar_wait(&S->b_empty[st], ((it / FP_BSTAGES) & 1) ^ 1);
+          fp_mbar_wait(&S->c_empty[cs], ((it / FP_CSTAGES) & 1) ^ 1);
           fp_mbar_expect_tx(&S->b_full[st], 16384 + FP_CT_BYTES);
           fp_bulk_g2s(sB + st * 16384, a.B + (size_t)nt * 16384, 16384, &S->b_full[st]);
-          fp_bulk_g2s(sCt + st * FP_CT_BYTES, a.ctile + (size_t)nt * FP_CT_BYTES, FP_CT_BYTES, &S->b_full[st]);
+          fp_bulk_g2s(sCt + cs * FP_CT_BYTES, a.ctile + (size_t)nt * FP_CT_BYTES, FP_CT_BYTES, &S->b_full[st]);
         }
       }
     }
@@ -215,34 +221,44 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: warp q = warp & 3 owns TMEM lanes 32q..32q+31 = rows 32q.. of the tile; row = range*8 + iso =====
-    const int q = warp & 3;
+    // ===== epilogue: warp q = warp & 3 owns TMEM lanes 32q..32q+31 = rows 32q.. of the tile (row = range*8 + iso);
+    //       group grp = (warp-4)>>2 takes the 32-column chunks with ch % FP_EPI_GROUPS == grp =====
+    const int q = warp & 3, grp = (warp - 4) >> 2;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < 512; c0 += 32) fp_tmem_st32_const(tl + c0, FP_MAGIC);
+    for (int c0 = grp * 32; c0 < 512; c0 += 32 * FP_EPI_GROUPS) fp_tmem_st32_const(tl + c0, FP_MAGIC);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
     if (lane == 0) { fp_mbar_arrive(&S->t_empty[0]); fp_mbar_arrive(&S->t_empty[1]); }
     unsigned long long n_exact = 0, n_rescan = 0, n_chunk = 0;
     uint32_t it = 0;
+    constexpr int NCH = FP_TN / FP_CHUNK / FP_EPI_GROUPS;     // chunks per tile per group
     for (int i = 0; i < nmt; i++) {
       const int mt = (int)blockIdx.x + i * (int)gridDim.x;
-      const int row = mt * FP_TM + q * 32 + lane;
+      const int rit = q * 32 + lane;                          // row in tile
+      const int row = mt * FP_TM + rit;
       const int rng = row >> 3;
       const bool rvalid = rng < a.nranges;
       const int sr = rvalid ? a.sr[rng] : 0;
       const float nfr = -(float)sr * (1.0f / 64.0f);          // exact: sr < 2^14
       long long bestG = -1; int bestIdx = 0x7fffffff, bestAq = 0;
-      float Tf = -1.0f;                                        // float of bestG, rounded down
+      float Tf = -1.0f;                                        // lower bound of the row's best G (either group's)
+      if (FP_EPI_GROUPS > 1) S->shareT[grp][rit] = -1.0f;
       for (int nt = 0; nt < a.ntiles; nt++, it++) {
-        const int st = it % FP_BSTAGES, ts = it & 1;
+        const int cs = it % FP_CSTAGES, ts = it & 1;
         fp_mbar_wait(&S->t_full[ts], (it >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float *fdp = reinterpret_cast<const float *>(sCt + st * FP_CT_BYTES);
-        const int *detp = reinterpret_cast<const int *>(sCt + st * FP_CT_BYTES + 1024);
-        const float *wp = reinterpret_cast<const float *>(sCt + st * FP_CT_BYTES + 2048);
-        for (int ch = 0; ch < FP_TN / FP_CHUNK; ch++) {
-          uint32_t v[32];
-          fp_tmem_ld32(tl + ts * FP_TN + ch * FP_CHUNK, v);
+        const float *fdp = reinterpret_cast<const float *>(sCt + cs * FP_CT_BYTES);
+        const float *wcp = reinterpret_cast<const float *>(sCt + cs * FP_CT_BYTES + 2048);
+        const float *wp = reinterpret_cast<const float *>(sCt + cs * FP_CT_BYTES + 3072);
+        uint32_t vbuf[2][32];
+        fp_tmem_ld32_nowait(tl + ts * FP_TN + grp * FP_CHUNK, vbuf[0]);
+#pragma unroll
+        for (int k = 0; k < NCH; k++) {
+          const int ch = k * FP_EPI_GROUPS + grp;
+          uint32_t (&v)[32] = vbuf[k & 1];
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (k + 1 < NCH) fp_tmem_ld32_nowait(tl + ts * FP_TN + (ch + FP_EPI_GROUPS) * FP_CHUNK, vbuf[(k + 1) & 1]);   // next chunk in flight
           fp_tmem_st32_const(tl + ts * FP_TN + ch * FP_CHUNK, FP_MAGIC);   // re-arm the accumulator
           if (a.probe) continue;
           float g[32];
@@ -254,58 +270,92 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
             g[4 * j4 + 2] = fmaf(nfr, f.z, __uint_as_float(v[4 * j4 + 2]));
             g[4 * j4 + 3] = fmaf(nfr, f.w, __uint_as_float(v[4 * j4 + 3]));
           }
-          // all g are positive floats (2^23 + num/64, |num/64| < 2^22): their bit patterns order like integers
-          int mx = __float_as_int(g[0]), mn = mx;
+          // all g are positive floats (2^23 + num/64, |num/64| < 2^22): their bit patterns order like integers;
+          // four independent max / min chains (one warp per scheduler: latency, not issue, is what counts)
+          int mx[4], mn[4];
 #pragma unroll
-          for (int j = 1; j < 31; j += 2) {
-            mx = __vimax3_s32(mx, __float_as_int(g[j]), __float_as_int(g[j + 1]));
-            mn = __vimin3_s32(mn, __float_as_int(g[j]), __float_as_int(g[j + 1]));
+          for (int c = 0; c < 4; c++) {
+            mx[c] = __vimax3_s32(__float_as_int(g[8 * c]), __float_as_int(g[8 * c + 1]), __float_as_int(g[8 * c + 2]));
+            mn[c] = __vimin3_s32(__float_as_int(g[8 * c]), __float_as_int(g[8 * c + 1]), __float_as_int(g[8 * c + 2]));
+            mx[c] = __vimax3_s32(mx[c], __float_as_int(g[8 * c + 3]), __float_as_int(g[8 * c + 4]));
+            mn[c] = __vimin3_s32(mn[c], __float_as_int(g[8 * c + 3]), __float_as_int(g[8 * c + 4]));
+            mx[c] = __vimax3_s32(mx[c], __float_as_int(g[8 * c + 5]), __float_as_int(g[8 * c + 6]));
+            mn[c] = __vimin3_s32(mn[c], __float_as_int(g[8 * c + 5]), __float_as_int(g[8 * c + 6]));
+            mx[c] = max(mx[c], __float_as_int(g[8 * c + 7]));
+            mn[c] = min(mn[c], __float_as_int(g[8 * c + 7]));
           }
-          mx = max(mx, __float_as_int(g[31])); mn = min(mn, __float_as_int(g[31]));
-          const float X = fmaxf(__int_as_float(mx) - 8388608.0f, 8388608.0f - __int_as_float(mn)) + 0.5f;
-          const float w = wp[ch];
-          const bool pass = rvalid && (X * X) * w * 1.00001f >= Tf;
+          const int mxa = max(__vimax3_s32(mx[0], mx[1], mx[2]), mx[3]), mna = min(__vimin3_s32(mn[0], mn[1], mn[2]), mn[3]);
+          const float X = fmaxf(__int_as_float(mxa) - 8388608.0f, 8388608.0f - __int_as_float(mna)) + 0.5f;
+          const bool pass = rvalid && (X * X) * wp[ch] * 1.00001f >= Tf;
           n_chunk++;
           if (__any_sync(0xffffffffu, pass)) {
+            // ---- re-examine the 32 columns: the accumulators go through shared memory so that the loop stays
+            //      rolled (one copy of the exact fit) without dynamic register indexing ----
             n_rescan++;
-            if (pass) {
-              const int colbase = nt * FP_TN + ch * FP_CHUNK;
+            uint32_t *scr = sScr + (warp - 4) * 1024 + lane;
 #pragma unroll
+            for (int j = 0; j < 32; j++) scr[j * 32] = v[j];
+            __syncwarp();
+            if (pass) {
+              const int *detp = reinterpret_cast<const int *>(sCt + cs * FP_CT_BYTES + 1024);
+#pragma unroll 1
               for (int j = 0; j < 32; j++) {
-                const uint32_t vj = v[j]; const float gj = g[j];
+                const uint32_t vj = scr[j * 32];
+                const float sdf = fdp[ch * FP_CHUNK + j];
+                const float x = fabsf(fmaf(nfr, sdf, __uint_as_float(vj)) - 8388608.0f) + 0.5f;
+                if ((x * x) * wcp[ch * FP_CHUNK + j] * 1.00001f < Tf) continue;
                 const int det = detp[ch * FP_CHUNK + j];
-                if (det < 0) continue;
-                const float x = fabsf(gj - 8388608.0f) + 0.5f;
-                const float wj = det > 0 ? 40960000.0f / (float)det : 3.0e38f;
-                if ((x * x) * wj * 1.00001f < Tf) continue;
+                if (det < 0) continue;                            // padding column
                 n_exact++;
-                fp_exact(a, colbase + j, (int)(vj - FP_MAGIC), sr, bestG, bestIdx, bestAq);
-                Tf = bestG < 0 ? -1.0f : __ll2float_rd(bestG);
+                // exact integer fit (oracle/b2_oracle_pool.c orc_pool_pair); the double quotient truncates like the
+                // exact rational: a non-integer p/q with q < 2^29 is further than 2^-53 (relative) from an integer
+                const int num = 64 * (int)(vj - FP_MAGIC) - sr * (int)sdf;
+                const int qa = det == 0 ? 0 : (int)((100.0 * (double)num) / (double)det);
+                const int aq = fp_quan_a(qa);
+                if (aq < -235 || aq > 400) continue;
+                const long long G = 200ll * aq * num - (long long)aq * aq * det;
+                if (G < bestG) continue;
+                const int idx = a.orig[nt * FP_TN + ch * FP_CHUNK + j];
+                if (G > bestG || idx < bestIdx) { bestG = G; bestIdx = idx; bestAq = aq; Tf = __ll2float_rd(G); }
               }
             }
+            __syncwarp();
           }
+        }
+        // ---- exchange the row thresholds with the other epilogue group (stale by at most one tile: conservative) ----
+        if (FP_EPI_GROUPS > 1 && !a.probe) {
+          S->shareT[grp][rit] = Tf;
+          Tf = fmaxf(Tf, *reinterpret_cast<volatile float *>(&S->shareT[grp ^ 1][rit]));
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) fp_mbar_arrive(&S->t_empty[ts]);
+        if (lane == 0) { fp_mbar_arrive(&S->t_empty[ts]); fp_mbar_arrive(&S->c_empty[cs]); }
       }
-      // ---- the 8 isometries of a range are 8 consecutive lanes: first maximum in (iso, pool index) order ----
       if (!a.probe) {
-        long long G = bestG; int idx = bestIdx, aq = bestAq, iso = lane & 7;
+        // ---- merge the groups' partial results per row (first maximum in pool-index order) ----
+        if (grp > 0) { S->mG[rit] = bestG; S->mIdx[rit] = bestIdx; S->mAq[rit] = (short)bestAq; }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * FP_EPI_WARPS) : "memory");
+        if (grp == 0) {
+          const long long G1 = S->mG[rit]; const int i1 = S->mIdx[rit], a1 = S->mAq[rit];
+          if (G1 > bestG || (G1 == bestG && i1 < bestIdx)) { bestG = G1; bestIdx = i1; bestAq = a1; }
+          // ---- the 8 isometries of a range are 8 consecutive lanes: first maximum in (iso, pool index) order ----
+          long long G = bestG; int idx = bestIdx, aq = bestAq, iso = lane & 7;
 #pragma unroll
-        for (int off = 1; off < 8; off <<= 1) {
-          const long long G2 = __shfl_xor_sync(0xffffffffu, G, off);
-          const int idx2 = __shfl_xor_sync(0xffffffffu, idx, off), aq2 = __shfl_xor_sync(0xffffffffu, aq, off), iso2 = __shfl_xor_sync(0xffffffffu, iso, off);
-          if (G2 > G || (G2 == G && iso2 < iso)) { G = G2; idx = idx2; aq = aq2; iso = iso2; }
+          for (int off = 1; off < 8; off <<= 1) {
+            const long long G2 = __shfl_xor_sync(0xffffffffu, G, off);
+            const int idx2 = __shfl_xor_sync(0xffffffffu, idx, off), aq2 = __shfl_xor_sync(0xffffffffu, aq, off), iso2 = __shfl_xor_sync(0xffffffffu, iso, off);
+            if (G2 > G || (G2 == G && iso2 < iso)) { G = G2; idx = idx2; aq = aq2; iso = iso2; }
+          }
+          if ((lane & 7) == 0 && rvalid) {
+            a.best_dom[rng] = G < 0 ? -1 : idx;
+            a.best_iso[rng] = (unsigned char)(G < 0 ? 0 : iso);
+            a.aq[rng] = (short)(G < 0 ? 0 : aq);
+            a.beta[rng] = a.betaq[rng];
+            a.err_num[rng] = G < 0 ? -1 : a.ar[rng] - G;
+          }
         }
-        if ((lane & 7) == 0 && rvalid) {
-          a.best_dom[rng] = G < 0 ? -1 : idx;
-          a.best_iso[rng] = (unsigned char)(G < 0 ? 0 : iso);
-          a.aq[rng] = (short)(G < 0 ? 0 : aq);
-          a.beta[rng] = a.betaq[rng];
-          a.err_num[rng] = G < 0 ? -1 : a.ar[rng] - G;
-        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * FP_EPI_WARPS) : "memory");
       }
     }
     if (a.stats) {                                  // [0] exact evaluations (all lanes), [1] chunk rescans, [2] chunks (per warp)
@@ -386,13 +436,14 @@ __global__ void __launch_bounds__(256) k_fp_pack(const uint8_t *__restrict__ tmp
   if (c >= ncols) return;
   float *fd = reinterpret_cast<float *>(ctile + (size_t)(c >> 8) * FP_CT_BYTES) + (c & 255);
   int *dt = reinterpret_cast<int *>(ctile + (size_t)(c >> 8) * FP_CT_BYTES + 1024) + (c & 255);
+  float *wc = reinterpret_cast<float *>(ctile + (size_t)(c >> 8) * FP_CT_BYTES + 2048) + (c & 255);
   if (c < nd) {
     const int p = val_sorted[c];
     for (int k = 0; k < 64; k++) B[fp_blk_off(c, k)] = tmp[(size_t)p * 64 + k];
-    *fd = (float)sdv[p]; *dt = (int)key_sorted[c]; sd[c] = sdv[p]; det[c] = (int)key_sorted[c]; orig[c] = p;
+    *fd = (float)sdv[p]; *dt = (int)key_sorted[c]; *wc = key_sorted[c] ? 40960000.0f / (float)key_sorted[c] : 3.0e38f; sd[c] = sdv[p]; det[c] = (int)key_sorted[c]; orig[c] = p;
   } else {
     for (int k = 0; k < 64; k++) B[fp_blk_off(c, k)] = 0;
-    *fd = 0.f; *dt = -1; sd[c] = 0; det[c] = -1; orig[c] = 0x7fffffff;
+    *fd = 0.f; *dt = -1; *wc = -1.0f; sd[c] = 0; det[c] = -1; orig[c] = 0x7fffffff;
   }
 }
 __global__ void __launch_bounds__(256) k_fp_wchunk(const int *__restrict__ det, int nchunks, uint8_t *__restrict__ ctile)
@@ -401,7 +452,7 @@ __global__ void __launch_bounds__(256) k_fp_wchunk(const int *__restrict__ det, 
   if (c >= nchunks) return;
   int mn = 0x7fffffff; bool any = false;
   for (int j = 0; j < FP_CHUNK; j++) { const int d = det[c * FP_CHUNK + j]; if (d >= 0) { any = true; mn = min(mn, d); } }
-  reinterpret_cast<float *>(ctile + (size_t)(c >> 3) * FP_CT_BYTES + 2048)[c & 7] = !any ? 0.f : (mn == 0 ? 3.0e38f : 40960000.0f / (float)mn);
+  reinterpret_cast<float *>(ctile + (size_t)(c >> 3) * FP_CT_BYTES + 3072)[c & 7] = !any ? 0.f : (mn == 0 ? 3.0e38f : 40960000.0f / (float)mn);
 }
 
 }  // namespace b2
@@ -570,7 +621,7 @@ static int fp_launch(b2fp_ctx *c, int probe, int32_t *dom, uint8_t *iso, int16_t
   a.mtiles = c->mtiles; a.ntiles = c->ntiles; a.nranges = c->nranges; a.nd = c->nd;
   a.best_dom = dom; a.best_iso = iso; a.aq = aq; a.beta = beta; a.err_num = (long long *)err;
   a.stats = c->d_stats; a.probe = probe;
-  const int smem = 2 * 8192 + FP_BSTAGES * 16384 + FP_BSTAGES * FP_CT_BYTES + (int)sizeof(FpSmem) + 1024;
+  const int smem = 2 * 8192 + FP_BSTAGES * 16384 + FP_CSTAGES * FP_CT_BYTES + FP_EPI_WARPS * 4096 + (int)sizeof(FpSmem) + 1024;
   static int configured = 0;
   if (!configured) { FP_CHECK(c, cudaFuncSetAttribute(k_frac_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); configured = 1; }
   const int grid = c->mtiles < c->sm_count ? c->mtiles : c->sm_count;
