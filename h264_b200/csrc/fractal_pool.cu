@@ -79,6 +79,17 @@ __device__ __forceinline__ void fp_mbar_wait(void *bar, uint32_t parity)
                  : "=r"(ok) : "r"(fp_smem(bar)), "r"(parity) : "memory");
   } while (!ok);
 }
+// same, with back-off: the single-lane producer / MMA-issuer warps share their schedulers with epilogue warps
+__device__ __forceinline__ void fp_mbar_wait_sleep(void *bar, uint32_t parity)
+{
+  uint32_t ok;
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(fp_smem(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void fp_bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar)
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -186,13 +197,13 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
       for (int i = 0; i < nmt; i++) {
         const int mt = (int)blockIdx.x + i * (int)gridDim.x;
         const int ab = i & 1;
-        fp_mbar_wait(&S->a_empty[ab], ((i >> 1) & 1) ^ 1);
+        fp_mbar_wait_sleep(&S->a_empty[ab], ((i >> 1) & 1) ^ 1);
         fp_mbar_expect_tx(&S->a_full[ab], 8192);
         fp_bulk_g2s(sA + ab * 8192, a.A + (size_t)mt * 8192, 8192, &S->a_full[ab]);
         for (int nt = 0; nt < a.ntiles; nt++, it++) {
           const int st = it % FP_BSTAGES, cs = it % FP_CSTAGES;
-          fp_mbar_wait(&S->b_empty[st], ((it / FP_BSTAGES) & 1) ^ 1);
-          fp_mbar_wait(&S->c_empty[cs], ((it / FP_CSTAGES) & 1) ^ 1);
+          fp_mbar_wait_sleep(&S->b_empty[st], ((it / FP_BSTAGES) & 1) ^ 1);
+          fp_mbar_wait_sleep(&S->c_empty[cs], ((it / FP_CSTAGES) & 1) ^ 1);
           fp_mbar_expect_tx(&S->b_full[st], 16384 + FP_CT_BYTES);
           fp_bulk_g2s(sB + st * 16384, a.B + (size_t)nt * 16384, 16384, &S->b_full[st]);
           fp_bulk_g2s(sCt + cs * FP_CT_BYTES, a.ctile + (size_t)nt * FP_CT_BYTES, FP_CT_BYTES, &S->b_full[st]);
@@ -205,11 +216,11 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
       uint32_t it = 0;
       for (int i = 0; i < nmt; i++) {
         const int ab = i & 1;
-        fp_mbar_wait(&S->a_full[ab], (i >> 1) & 1);
+        fp_mbar_wait_sleep(&S->a_full[ab], (i >> 1) & 1);
         for (int nt = 0; nt < a.ntiles; nt++, it++) {
           const int st = it % FP_BSTAGES, ts = it & 1;
-          fp_mbar_wait(&S->t_empty[ts], (it >> 1) & 1);      // phase 0 = the epilogue's initial arming of the stage
-          fp_mbar_wait(&S->b_full[st], (it / FP_BSTAGES) & 1);
+          fp_mbar_wait_sleep(&S->t_empty[ts], (it >> 1) & 1);      // phase 0 = the epilogue's initial arming of the stage
+          fp_mbar_wait_sleep(&S->b_full[st], (it / FP_BSTAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t ad = fp_smem_desc(sA + ab * 8192), bd = fp_smem_desc(sB + st * 16384);
           fp_mma_i8(tmem + ts * FP_TN, ad, bd, 1u);
@@ -289,23 +300,36 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
           const bool pass = rvalid && (X * X) * wp[ch] * 1.00001f >= Tf;
           n_chunk++;
           if (__any_sync(0xffffffffu, pass)) {
-            // ---- re-examine the 32 columns: the accumulators go through shared memory so that the loop stays
-            //      rolled (one copy of the exact fit) without dynamic register indexing ----
+            // ---- re-examine the 32 columns.  Phase 1 (registers, branch-free): mask of the columns whose own
+            //      bound 10000*num^2/det reaches the row's threshold ----
             n_rescan++;
-            uint32_t *scr = sScr + (warp - 4) * 1024 + lane;
-#pragma unroll
-            for (int j = 0; j < 32; j++) scr[j * 32] = v[j];
-            __syncwarp();
+            uint32_t m = 0;
             if (pass) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; j4++) {
+                const float4 wc = reinterpret_cast<const float4 *>(wcp + ch * FP_CHUNK)[j4];
+                const float x0 = fabsf(g[4 * j4 + 0] - 8388608.0f) + 0.5f, x1 = fabsf(g[4 * j4 + 1] - 8388608.0f) + 0.5f;
+                const float x2 = fabsf(g[4 * j4 + 2] - 8388608.0f) + 0.5f, x3 = fabsf(g[4 * j4 + 3] - 8388608.0f) + 0.5f;
+                m |= ((x0 * x0) * wc.x * 1.00001f >= Tf ? 1u : 0u) << (4 * j4 + 0);
+                m |= ((x1 * x1) * wc.y * 1.00001f >= Tf ? 1u : 0u) << (4 * j4 + 1);
+                m |= ((x2 * x2) * wc.z * 1.00001f >= Tf ? 1u : 0u) << (4 * j4 + 2);
+                m |= ((x3 * x3) * wc.w * 1.00001f >= Tf ? 1u : 0u) << (4 * j4 + 3);
+              }
+            }
+            if (__any_sync(0xffffffffu, m != 0)) {
+              // ---- phase 2: exact integer fit of the flagged columns; the accumulators go through shared memory so
+              //      that the loop is rolled (one copy of the fit) without dynamic register indexing ----
+              uint32_t *scr = sScr + (warp - 4) * 1024 + lane;
+#pragma unroll
+              for (int j = 0; j < 32; j++) scr[j * 32] = v[j];
+              __syncwarp();
               const int *detp = reinterpret_cast<const int *>(sCt + cs * FP_CT_BYTES + 1024);
-#pragma unroll 1
-              for (int j = 0; j < 32; j++) {
-                const uint32_t vj = scr[j * 32];
-                const float sdf = fdp[ch * FP_CHUNK + j];
-                const float x = fabsf(fmaf(nfr, sdf, __uint_as_float(vj)) - 8388608.0f) + 0.5f;
-                if ((x * x) * wcp[ch * FP_CHUNK + j] * 1.00001f < Tf) continue;
+              while (m) {
+                const int j = __ffs(m) - 1; m &= m - 1;
                 const int det = detp[ch * FP_CHUNK + j];
                 if (det < 0) continue;                            // padding column
+                const uint32_t vj = scr[j * 32];
+                const float sdf = fdp[ch * FP_CHUNK + j];
                 n_exact++;
                 // exact integer fit (oracle/b2_oracle_pool.c orc_pool_pair); the double quotient truncates like the
                 // exact rational: a non-integer p/q with q < 2^29 is further than 2^-53 (relative) from an integer
@@ -318,8 +342,8 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
                 const int idx = a.orig[nt * FP_TN + ch * FP_CHUNK + j];
                 if (G > bestG || idx < bestIdx) { bestG = G; bestIdx = idx; bestAq = aq; Tf = __ll2float_rd(G); }
               }
+              __syncwarp();
             }
-            __syncwarp();
           }
         }
         // ---- exchange the row thresholds with the other epilogue group (stale by at most one tile: conservative) ----
