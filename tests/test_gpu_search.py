@@ -134,3 +134,44 @@ def test_error_codes():
     s.set_cur(np.zeros((48, 64), np.uint8)); s.set_ref(0, np.zeros((48, 64), np.uint8))
     with pytest.raises(api.B2Error):
         s.search_frame(pred, cen, api.make_params(100))
+
+
+def test_search_range_64_kernel():
+    """+-64 takes the other k_sad_fs instantiation (window pitch 160, 12 worker warps)."""
+    W, H, R = 64, 48, 64
+    s, cur, refs = _setup(W, H, R, 1, seed=33)
+    of = oracle.OrcFrame(cur, refs, R)
+    pred, cen = synth.predictors(W, H, 1, seed=8, spread=4, rmax=9)
+    got = s.search_frame(pred, cen, api.make_params((120, 100, 100)))
+    exp = of.search_frame(pred, cen, (120, 100, 100))
+    for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+        assert (a == b).all(), (n, int((a != b).sum()))
+
+
+def test_banded_search_equals_full_frame():
+    """MB-row bands with halo rows only (h264_b200/bands.py): every band's results equal the full-frame search."""
+    import torch
+    from h264_b200 import bands
+    W, H, R, world = 96, 144, 16, 3
+    fr = synth.luma_sequence(W, H, 2, seed=12)
+    cur, ref = fr[1], fr[0]
+    pred, cen = synth.predictors(W, H, 1, seed=5, spread=3, rmax=8)        # |centre| <= 8 pel + rounding
+    s = api.Searcher(W, H, 1, R)
+    s.set_cur(cur); s.set_ref(0, ref)
+    full = s.search_frame(pred, cen, api.make_params((150, 120, 120)))
+    dev = torch.device("cuda", 0)
+    d_pred, d_cen = torch.from_numpy(pred).to(dev), torch.from_numpy(cen).to(dev)
+    nmb = (W // 16) * (H // 16)
+    for rank in range(world):
+        b = bands.BandSearcher(W, H, 1, R, rank, world, max_center_pel=12)
+        lo, hi = bands.needed_rows(rank, world, H // 16, R, 12)
+        part = np.zeros_like(ref); part[lo:hi] = ref[lo:hi]                # what the halo exchange delivers
+        b.set_cur_dev(torch.from_numpy(cur).to(dev))
+        b.s.set_ref_dev(0, torch.from_numpy(part).to(dev))
+        mvi = torch.zeros((nmb, 1, 41, 2), dtype=torch.int16, device=dev); mvs = torch.zeros_like(mvi)
+        ci = torch.zeros((nmb, 1, 41), dtype=torch.int64, device=dev); cs = torch.zeros_like(ci)
+        b.search(d_pred, d_cen, api.make_params((150, 120, 120)), mvi, ci, mvs, cs)
+        torch.cuda.synchronize()
+        sl = slice(b.mb_first, b.mb_first + b.mb_count)
+        for got, exp in zip((mvi, ci, mvs, cs), full):
+            assert (got.cpu().numpy()[sl] == exp[sl]).all(), rank
