@@ -99,12 +99,17 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
           ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX + (tx - gm.ox); oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY + (ty - gm.oy);
         }
         const uint8_t *rp = planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox;
+        const int al = (int)(reinterpret_cast<size_t>(rp) & 3);      // two aligned words per row instead of four byte loads
         int d[16];
 #pragma unroll
-        for (int r = 0; r < 4; r++)
+        for (int r = 0; r < 4; r++) {
+          const uint32_t *w = reinterpret_cast<const uint32_t *>(rp + (size_t)r * a.Wp - al);
+          const uint32_t lo = w[0], hi = al ? w[1] : 0u;
+          const uint32_t px = al ? __funnelshift_r(lo, hi, 8 * al) : lo;
+          const uint32_t cw = *reinterpret_cast<const uint32_t *>(&cur[(ty + r) * 16 + tx]);
 #pragma unroll
-          for (int q = 0; q < 4; q++)
-            d[r * 4 + q] = (int)cur[(ty + r) * 16 + tx + q] - (int)rp[(size_t)r * a.Wp + q];
+          for (int q = 0; q < 4; q++) d[r * 4 + q] = (int)((cw >> (8 * q)) & 255u) - (int)((px >> (8 * q)) & 255u);
+        }
         int val;
         if (metric == 2) val = hadamard4x4_abs(d);
         else { val = 0;
