@@ -4,12 +4,13 @@
 // (JM/lencod/src/me_fullsearch.c:186-289) with computeSATD (me_distortion.c:745-825,
 // HadamardSAD4x4 :175-258) or computeSAD (:349-426) as computePredHPel/QPel.
 //
-// One CTA per (MB, ref).  A unit of work is one 4x4 tile of one candidate of one partition:
-// 9 half-pel (then 8 quarter-pel) candidates x 7 block types x 16 tiles; each thread loads the
-// 4x4 reference tile from the quarter-pel plane [y&3][x&3] with the reference's own
-// tile-origin clamp (UMVLine4X, refbuf.h:22-26), forms the difference against the current MB
-// in shared memory, runs the 4x4 Hadamard in registers and adds (satd+1)>>1 into the
-// candidate's accumulator.  41 threads then take the lexicographic (cost, position) minimum in
+// One CTA per (MB, ref).  A thread owns one 4x4 tile of the macroblock and one candidate index
+// (16 tiles x 9 half-pel, then 8 quarter-pel candidates) and walks the 7 block types whose partition
+// contains the tile; partitions with equal motion vectors ask for the same reference tile, which is
+// then computed once.  The thread loads the 4x4 reference tile from the quarter-pel plane
+// [y&3][x&3] with the reference's own tile-origin clamp (UMVLine4X, refbuf.h:22-26), forms the
+// difference against the current MB in shared memory, runs the 4x4 Hadamard in registers and
+// adds (satd+1)>>1 into each partition's candidate accumulator.  41 threads then take the lexicographic (cost, position) minimum in
 // spiral order with the reference's carried / reset min_mcost rules (mv_search.c:971-974,
 // me_fullsearch.c:252-253).
 #include "b2_common.cuh"
@@ -17,7 +18,7 @@
 
 namespace b2 {
 
-constexpr int SP_NT = 128;
+constexpr int SP_NT = 160;     // 144 = 16 tiles x 9 candidates working threads
 constexpr long long DMAX = ((long long)0x7fffffff) << 5;
 
 // spiral positions 0..8 (x,y) in units of the step (mv_search.c:406-442 with l = 1)
@@ -41,13 +42,54 @@ __device__ __forceinline__ int hadamard4x4_abs(const int d[16])
   return (s + 1) >> 1;
 }
 
+// partition of block type index bti (0..6) containing the 4x4 tile at (tx, ty)
+__device__ __forceinline__ int part_of_tile(int bti, int tx, int ty)
+{
+  switch (bti) {
+    case 0: return 0;
+    case 1: return 1 + (ty >> 3);
+    case 2: return 3 + (tx >> 3);
+    case 3: return 5 + (ty >> 3) * 2 + (tx >> 3);
+    case 4: return 9 + (ty >> 2) * 2 + (tx >> 3);
+    case 5: return 17 + (ty >> 3) * 4 + (tx >> 2);
+    default: return 25 + (ty >> 2) * 4 + (tx >> 2);
+  }
+}
+
+// distortion of the 4x4 tile of the current MB at (tx, ty) against the reference tile `rp` (row pitch Wp)
+__device__ __forceinline__ int tile_distortion(const uint8_t *cur, int tx, int ty, const uint8_t *rp, int Wp, int metric)
+{
+  const int al = (int)(reinterpret_cast<size_t>(rp) & 3);      // two aligned words per row instead of four byte loads
+  int d[16];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(rp + (size_t)r * Wp - al);
+    const uint32_t lo = w[0], hi = al ? w[1] : 0u;
+    const uint32_t px = al ? __funnelshift_r(lo, hi, 8 * al) : lo;
+    const uint32_t cw = *reinterpret_cast<const uint32_t *>(&cur[(ty + r) * 16 + tx]);
+#pragma unroll
+    for (int q = 0; q < 4; q++) d[r * 4 + q] = (int)((cw >> (8 * q)) & 255u) - (int)((px >> (8 * q)) & 255u);
+  }
+  if (metric == 2) return hadamard4x4_abs(d);
+  int v = 0;
+#pragma unroll
+  for (int q = 0; q < 16; q++) v += abs(d[q]);
+  return v;
+}
+
 __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
 {
+  // Thread (k, c) = 4x4 tile k of the macroblock, candidate index c.  The seven partitions (one per block type)
+  // that contain tile k usually carry the same motion vector and then ask for the SAME reference tile: the thread
+  // walks the block types, computes a tile's distortion only when its (plane, x, y) differs from the ones it has
+  // already computed, and adds the value to each partition's candidate accumulator.
   __shared__ __align__(16) uint8_t cur[256];
   __shared__ int dist[NPART][9];
   __shared__ short mv[NPART][2], prd[NPART][2];
   __shared__ long long mincost[NPART];
   const int tid = threadIdx.x;
+  const int k = tid / 9, c = tid - k * 9;              // tid < 144
+  const int tx = (k & 3) * 4, ty = (k >> 2) * 4;
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int mb = a.mb_first + item / a.refs_per_mb, ref = a.ref_first + item % a.refs_per_mb;
     const int mbx = mb % a.mbw, mby = mb / a.mbw;
@@ -70,61 +112,49 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
       __syncthreads();
       for (int i = tid; i < NPART * 9; i += SP_NT) (&dist[0][0])[i] = 0;
       __syncthreads();
-      // units: candidate c (0..8) x blocktype index (0..6) x tile k (0..15)
-      for (int u = tid; u < 9 * 112; u += SP_NT) {
-        const int c = u / 112, v = u - c * 112, bti = v >> 4, k = v & 15;
-        if (c < first) continue;
-        const int tx = (k & 3) * 4, ty = (k >> 2) * 4;
-        int p;   // partition of type bti+1 containing tile k
-        switch (bti) {
-          case 0: p = 0; break;
-          case 1: p = 1 + (ty >> 3); break;
-          case 2: p = 3 + (tx >> 3); break;
-          case 3: p = 5 + (ty >> 3) * 2 + (tx >> 3); break;
-          case 4: p = 9 + (ty >> 2) * 2 + (tx >> 3); break;
-          case 5: p = 17 + (ty >> 3) * 4 + (tx >> 2); break;
-          default: p = 25 + (ty >> 2) * 4 + (tx >> 2); break;
-        }
-        if (!((a.part_mask >> p) & 1ull)) continue;
-        const int mvx = mv[p][0] + step * c_sp9[c][0], mvy = mv[p][1] + step * c_sp9[c][1];
-        int ox, oy, pl;
-        if (metric == 2) {          // SATD: per-tile origin clamp (me_distortion.c:771)
-          const int qx = 4 * (mbx * 16 + tx) + mvx, qy = 4 * (mby * 16 + ty) + mvy;
-          pl = (qy & 3) * 4 + (qx & 3);
-          ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX; oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY;
-        } else {                    // SAD: block origin clamp (me_distortion.c:367)
-          const PartGeom gm = part_geom(p);
-          const int qx = 4 * (mbx * 16 + gm.ox) + mvx, qy = 4 * (mby * 16 + gm.oy) + mvy;
-          pl = (qy & 3) * 4 + (qx & 3);
-          ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX + (tx - gm.ox); oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY + (ty - gm.oy);
-        }
-        const uint8_t *rp = planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox;
-        const int al = (int)(reinterpret_cast<size_t>(rp) & 3);      // two aligned words per row instead of four byte loads
-        int d[16];
+      if (tid < 144 && c >= first) {
+        uint32_t keys[7]; int vals[7];
+        const int sx = step * c_sp9[c][0], sy = step * c_sp9[c][1];
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const uint32_t *w = reinterpret_cast<const uint32_t *>(rp + (size_t)r * a.Wp - al);
-          const uint32_t lo = w[0], hi = al ? w[1] : 0u;
-          const uint32_t px = al ? __funnelshift_r(lo, hi, 8 * al) : lo;
-          const uint32_t cw = *reinterpret_cast<const uint32_t *>(&cur[(ty + r) * 16 + tx]);
+        for (int bti = 0; bti < 7; bti++) {
+          keys[bti] = 0xffffffffu; vals[bti] = 0;
+          const int p = part_of_tile(bti, tx, ty);
+          if (!((a.part_mask >> p) & 1ull)) continue;
+          const uint32_t mvw = *reinterpret_cast<const uint32_t *>(&mv[p][0]);
+          int v = -1;
+          uint32_t kk;
+          if (metric == 2) {          // SATD: per-tile origin clamp (me_distortion.c:771): the tile depends on the vector only
+            kk = mvw;
 #pragma unroll
-          for (int q = 0; q < 4; q++) d[r * 4 + q] = (int)((cw >> (8 * q)) & 255u) - (int)((px >> (8 * q)) & 255u);
+            for (int b2 = 0; b2 < bti; b2++) if (keys[b2] == kk) v = vals[b2];
+            if (v < 0) {
+              const int qx = 4 * (mbx * 16 + tx) + mv[p][0] + sx, qy = 4 * (mby * 16 + ty) + mv[p][1] + sy;
+              const int pl = (qy & 3) * 4 + (qx & 3);
+              const int ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX, oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY;
+              v = tile_distortion(cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, 2);
+            }
+          } else {                    // SAD: block origin clamp (me_distortion.c:367): key = the tile actually read
+            const PartGeom gm = part_geom(p);
+            const int qx = 4 * (mbx * 16 + gm.ox) + mv[p][0] + sx, qy = 4 * (mby * 16 + gm.oy) + mv[p][1] + sy;
+            const int pl = (qy & 3) * 4 + (qx & 3);
+            const int ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX + (tx - gm.ox), oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY + (ty - gm.oy);
+            kk = (uint32_t)pl | ((uint32_t)ox << 4) | ((uint32_t)oy << 18);     // ox, oy < 2^14
+#pragma unroll
+            for (int b2 = 0; b2 < bti; b2++) if (keys[b2] == kk) v = vals[b2];
+            if (v < 0) v = tile_distortion(cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, 0);
+          }
+          keys[bti] = kk; vals[bti] = v;
+          atomicAdd(&dist[p][c], v);
         }
-        int val;
-        if (metric == 2) val = hadamard4x4_abs(d);
-        else { val = 0;
-#pragma unroll
-          for (int q = 0; q < 16; q++) val += abs(d[q]); }
-        atomicAdd(&dist[p][c], val);
       }
       __syncthreads();
       if (tid < NPART && ((a.part_mask >> tid) & 1ull)) {
         const int p = tid;
         long long best = mincost[p]; int best_pos = 0;
-        for (int c = first; c < 9; c++) {
-          const int mvx = mv[p][0] + step * c_sp9[c][0], mvy = mv[p][1] + step * c_sp9[c][1];
-          const long long cost = (long long)lam * (mvbits(mvx - prd[p][0]) + mvbits(mvy - prd[p][1])) + ((long long)dist[p][c] << 5);
-          if (cost < best) { best = cost; best_pos = c; }
+        for (int cc = first; cc < 9; cc++) {
+          const int mvx = mv[p][0] + step * c_sp9[cc][0], mvy = mv[p][1] + step * c_sp9[cc][1];
+          const long long cost = (long long)lam * (mvbits(mvx - prd[p][0]) + mvbits(mvy - prd[p][1])) + ((long long)dist[p][cc] << 5);
+          if (cost < best) { best = cost; best_pos = cc; }
         }
         mv[p][0] = (short)(mv[p][0] + step * c_sp9[best_pos][0]);
         mv[p][1] = (short)(mv[p][1] + step * c_sp9[best_pos][1]);
