@@ -24,6 +24,8 @@ KEYS = [
     "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_op_imma.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_op_imma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed_pipe_tensor.sum",
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
