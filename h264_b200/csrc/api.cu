@@ -91,6 +91,9 @@ extern "C" int b2me_create(b2me_ctx **out, int device, int width, int height, in
   B2_CUDA_CHECK(c, cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)));
   B2_CUDA_CHECK(c, cudaMemset(c->d_stats, 0, 16 * sizeof(unsigned long long)));
   B2_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  B2_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->stream_h2d, cudaStreamNonBlocking));
+  B2_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) B2_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_band[i], cudaEventDisableTiming));
   B2_CUDA_CHECK(c, cudaEventCreate(&c->ev0));
   B2_CUDA_CHECK(c, cudaEventCreate(&c->ev1));
   return B2ME_OK;
@@ -105,6 +108,9 @@ extern "C" void b2me_destroy(b2me_ctx *c)
   cudaFree(c->d_cost_int); cudaFree(c->d_cost_sub); cudaFree(c->d_io16); cudaFree(c->d_io64);
   cudaFreeHost(c->h_io16); cudaFreeHost(c->h_io64); cudaFree(c->d_errflag); cudaFree(c->d_work); cudaFree(c->d_stats);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
+  if (c->stream_d2h) cudaStreamDestroy(c->stream_d2h);
+  for (int i = 0; i < 8; i++) if (c->ev_band[i]) cudaEventDestroy(c->ev_band[i]);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
@@ -308,19 +314,36 @@ extern "C" int b2me_search_frame(b2me_ctx *c, const int16_t *pred, const int16_t
   if (r) return r;
   if (p->do_subpel && (!mv_sub || !cost_sub)) return B2ME_EINVAL;
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
-  const size_t n = (size_t)c->nmb * c->nrefs * NPART;
+  // The picture is processed in bands of MB rows so that the host<->device copies overlap the search: predictors
+  // of band i+1 go up (H2D stream) and results of band i-1 come down (D2H stream) while band i is searched.
+  const int nband = c->mbh >= 16 ? 4 : 1;
   cudaStream_t s = c->stream;
-  B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_pred, pred, n * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, s));
-  B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_center, center, n * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, s));
-  r = run_search(c, 0, c->nmb, 0, c->nrefs, 1, (1ull << NPART) - 1, -1, c->d_pred, c->d_center, p,
-                 c->d_mv_int, c->d_cost_int, c->d_mv_sub, c->d_cost_sub, s);
-  if (r) return r;
-  B2_CUDA_CHECK(c, cudaMemcpyAsync(mv_int, c->d_mv_int, n * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
-  B2_CUDA_CHECK(c, cudaMemcpyAsync(cost_int, c->d_cost_int, n * sizeof(long long), cudaMemcpyDeviceToHost, s));
-  if (p->do_subpel) {
-    B2_CUDA_CHECK(c, cudaMemcpyAsync(mv_sub, c->d_mv_sub, n * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
-    B2_CUDA_CHECK(c, cudaMemcpyAsync(cost_sub, c->d_cost_sub, n * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  for (int b = 0; b < nband; b++) {
+    const int row0 = (int)((long long)c->mbh * b / nband), row1 = (int)((long long)c->mbh * (b + 1) / nband);
+    const int mb0 = row0 * c->mbw, cnt = (row1 - row0) * c->mbw;
+    const size_t o2 = (size_t)mb0 * c->nrefs * NPART * 2, n2 = (size_t)cnt * c->nrefs * NPART * 2;
+    B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_pred + o2, pred + o2, n2 * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream_h2d));
+    B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_center + o2, center + o2, n2 * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream_h2d));
+    B2_CUDA_CHECK(c, cudaEventRecord(c->ev_band[b], c->stream_h2d));
   }
+  for (int b = 0; b < nband; b++) {
+    const int row0 = (int)((long long)c->mbh * b / nband), row1 = (int)((long long)c->mbh * (b + 1) / nband);
+    const int mb0 = row0 * c->mbw, cnt = (row1 - row0) * c->mbw;
+    const size_t o1 = (size_t)mb0 * c->nrefs * NPART, n1 = (size_t)cnt * c->nrefs * NPART;
+    B2_CUDA_CHECK(c, cudaStreamWaitEvent(s, c->ev_band[b], 0));
+    r = run_search(c, mb0, cnt, 0, c->nrefs, 1, (1ull << NPART) - 1, -1, c->d_pred, c->d_center, p,
+                   c->d_mv_int, c->d_cost_int, c->d_mv_sub, c->d_cost_sub, s);
+    if (r) return r;
+    B2_CUDA_CHECK(c, cudaEventRecord(c->ev_band[4 + b], s));
+    B2_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream_d2h, c->ev_band[4 + b], 0));
+    B2_CUDA_CHECK(c, cudaMemcpyAsync(mv_int + o1 * 2, c->d_mv_int + o1 * 2, n1 * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream_d2h));
+    B2_CUDA_CHECK(c, cudaMemcpyAsync(cost_int + o1, c->d_cost_int + o1, n1 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream_d2h));
+    if (p->do_subpel) {
+      B2_CUDA_CHECK(c, cudaMemcpyAsync(mv_sub + o1 * 2, c->d_mv_sub + o1 * 2, n1 * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream_d2h));
+      B2_CUDA_CHECK(c, cudaMemcpyAsync(cost_sub + o1, c->d_cost_sub + o1, n1 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream_d2h));
+    }
+  }
+  B2_CUDA_CHECK(c, cudaStreamSynchronize(c->stream_d2h));
   return check_errflag(c, s);
 }
 

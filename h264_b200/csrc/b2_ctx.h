@@ -28,6 +28,8 @@ struct b2me_ctx {
   int *d_work;                  // k_sad_fs item counter
   unsigned long long *d_stats;
   cudaStream_t stream;          // internal stream for host-pointer calls
+  cudaStream_t stream_h2d, stream_d2h;   // copy streams of the banded host-pointer search
+  cudaEvent_t ev_band[8];       // [0..3] predictors of band b are up, [4..7] band b is searched
   cudaEvent_t ev0, ev1;
   int timing;
   double t_ms[4];
