@@ -60,7 +60,7 @@ constexpr int FS_PRE = 0;        // radius of the exact pre-pass around the cent
 constexpr int FS_SMAX = 7;       // partitions whose centres lie within a 7-pel box share one window pass
 constexpr int FS_BMAX = 12;      // a trailing column block of at most this width is walked row-major (type B)
 constexpr int FS_MCAP = 2047;    // cap of each half of the mv-cost lower bound (keeps packed sums in range)
-constexpr int FS_CLAIM = 2;      // tasks claimed per visit of the shared counter (amortises the claim / completion protocol)
+constexpr int FS_CLAIM = 3;      // tasks claimed per visit of the shared counter (amortises the claim / completion protocol)
 
 __host__ __device__ inline FsGeom fs_geom(int R)
 {
