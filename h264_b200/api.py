@@ -21,16 +21,16 @@ class B2Error(RuntimeError):
 
 class SearchParams(C.Structure):
     _fields_ = [("lambda_factor", C.c_int32 * 3), ("restrict_mode", C.c_int32), ("metric_h", C.c_int32),
-                ("metric_q", C.c_int32), ("do_subpel", C.c_int32), ("reserved", C.c_int32),
+                ("metric_q", C.c_int32), ("do_subpel", C.c_int32), ("subpel_full", C.c_int32),
                 ("min_mcost", C.c_int64)]
 
 
-def make_params(lambda_factor, restrict_mode=2, metric_h=2, metric_q=2, do_subpel=True, min_mcost=DISTBLK_MAX):
+def make_params(lambda_factor, restrict_mode=2, metric_h=2, metric_q=2, do_subpel=True, min_mcost=DISTBLK_MAX, subpel_full=False):
     p = SearchParams()
     lam = [int(x) for x in np.broadcast_to(np.asarray(lambda_factor), (3,))]
     p.lambda_factor[0], p.lambda_factor[1], p.lambda_factor[2] = lam
     p.restrict_mode, p.metric_h, p.metric_q = restrict_mode, metric_h, metric_q
-    p.do_subpel, p.reserved, p.min_mcost = int(bool(do_subpel)), 0, int(min_mcost)
+    p.do_subpel, p.subpel_full, p.min_mcost = int(bool(do_subpel)), int(bool(subpel_full)), int(min_mcost)
     return p
 
 
@@ -338,6 +338,17 @@ class PoolSearcher:
 
     def launch_count(self):
         return self.L.b2fp_launch_count(self.h)
+
+
+def distortion_blocks(kind, n, diff, device=0):
+    """b2me_distortion_blocks: diff [nblk][n*n] int16 -> int64 [nblk] (distortion << 5); kind 0 SAD, 1 SSE, 2 SATD."""
+    d = np.ascontiguousarray(diff, np.int16)
+    assert d.ndim == 2 and d.shape[1] == n * n
+    out = np.zeros(d.shape[0], np.int64)
+    r = lib().b2me_distortion_blocks(C.c_int(device), C.c_int(kind), C.c_int(n), C.c_int(d.shape[0]), _p(d), _p(out))
+    if r:
+        raise B2Error(f"b2me_distortion_blocks failed ({r})")
+    return out
 
 
 class TQParams(C.Structure):

@@ -233,6 +233,7 @@ static int run_subpel(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
   // BlockMotionSearch resets the bound to DISTBLK_MAX when start_me_refinement_hp == 0 (mv_search.c:971-974);
   // the single-call drop-in receives the caller's bound instead
   q.use_bound = use_bound >= 0 ? use_bound : q.start_hp;
+  q.full81 = p->subpel_full ? 1 : 0;
   q.pred = pred; q.mv_int = mv_int; q.cost_int = cost_int; q.mv_sub = mv_sub; q.cost_sub = cost_sub;
   q.mb_first = mb_first; q.ref_first = ref_first; q.refs_per_mb = refs_per_mb; q.nitems = mb_count * refs_per_mb;
   q.abs_index = abs_index; q.part_mask = mask;
@@ -422,6 +423,31 @@ extern "C" int b2me_block_subpel(b2me_ctx *c, int pos_x, int pos_y, int blocktyp
   B2_CUDA_CHECK(c, cudaStreamSynchronize(s));
   mv_out[0] = h16[(3 * NPART + part) * 2]; mv_out[1] = h16[(3 * NPART + part) * 2 + 1];
   *cost_out = h64[NPART + part];
+  return B2ME_OK;
+}
+
+// distortion4x4/8x8{SAD,SSE,SATD} of the mode decision (me_distortion.c:38-134) for nblk difference blocks
+extern "C" int b2me_distortion_blocks_dev(int kind, int n, int nblk, const int16_t *diff_dev, int64_t *out_dev, void *stream)
+{
+  if (kind < 0 || kind > 2 || (n != 4 && n != 8) || nblk < 0 || !diff_dev || !out_dev) return B2ME_EINVAL;
+  if (nblk == 0) return B2ME_OK;
+  cudaError_t e = launch_distortion(kind, n, nblk, diff_dev, (long long *)out_dev, (cudaStream_t)stream);
+  if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "b2me_distortion_blocks: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
+  return B2ME_OK;
+}
+extern "C" int b2me_distortion_blocks(int device, int kind, int n, int nblk, const int16_t *diff, int64_t *out)
+{
+  if (kind < 0 || kind > 2 || (n != 4 && n != 8) || nblk < 0 || !diff || !out) return B2ME_EINVAL;
+  if (nblk == 0) return B2ME_OK;
+  if (cudaSetDevice(device) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "b2me_distortion_blocks: no CUDA device %d", device); return B2ME_ECUDA; }
+  int16_t *d = nullptr; long long *o = nullptr;
+  cudaError_t e = cudaMalloc(&d, (size_t)nblk * n * n * sizeof(int16_t));
+  if (e == cudaSuccess) e = cudaMalloc(&o, (size_t)nblk * sizeof(long long));
+  if (e == cudaSuccess) e = cudaMemcpy(d, diff, (size_t)nblk * n * n * sizeof(int16_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_distortion(kind, n, nblk, d, o, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out, o, (size_t)nblk * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d); cudaFree(o);
+  if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "b2me_distortion_blocks: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
   return B2ME_OK;
 }
 

@@ -80,6 +80,7 @@ struct SubArgs {
   int lambda_h, lambda_q, metric_h, metric_q;
   int start_hp, start_qp;
   int use_bound;         // 1: cost_int is the initial bound of the half-pel stage, 0: DISTBLK_MAX
+  int full81;            // 1: full_sub_pel_motion_estimation (81 quarter-pel positions) instead of the half + quarter stages
   const int16_t *pred;
   const int16_t *mv_int; const long long *cost_int;
   int16_t *mv_sub; long long *cost_sub;
@@ -93,5 +94,6 @@ FsGeom fs_geom_host(int R);
 cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, cudaStream_t s);
 cudaError_t launch_subpel_refine(const SubArgs &a, cudaStream_t s);
 cudaError_t ubench(int kind, int iters, double *gops);
+cudaError_t launch_distortion(int kind, int n, int nblk, const int16_t *diff, long long *out, cudaStream_t s);
 
 }  // namespace b2

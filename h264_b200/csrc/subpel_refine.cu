@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
   // walks the block types, computes a tile's distortion only when its (plane, x, y) differs from the ones it has
   // already computed, and adds the value to each partition's candidate accumulator.
   __shared__ __align__(16) uint8_t cur[256];
-  __shared__ int dist[NPART][9];
+  __shared__ int dist[NPART][81];             // [p][candidate]; 9 used by the half/quarter stages, 81 by the full mode
   __shared__ short mv[NPART][2], prd[NPART][2];
   __shared__ long long mincost[NPART];
   const int tid = threadIdx.x;
-  const int k = tid / 9, c = tid - k * 9;              // tid < 144
+  const int k = tid / 9, c0 = tid - k * 9;             // tid < 144
   const int tx = (k & 3) * 4, ty = (k >> 2) * 4;
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
     const int mb = a.mb_first + item / a.refs_per_mb, ref = a.ref_first + item % a.refs_per_mb;
@@ -104,17 +104,23 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
       // BlockMotionSearch resets the bound when the metric changes between levels (mv_search.c:971-974)
       mincost[tid] = a.use_bound ? a.cost_int[base + tid] : DMAX;
     }
-    for (int stage = 0; stage < 2; stage++) {
-      const int step = stage ? 1 : 2;
-      const int metric = stage ? a.metric_q : a.metric_h;
-      const int first = stage ? a.start_qp : a.start_hp;
-      const int lam = stage ? a.lambda_q : a.lambda_h;
+    const int nstage = a.full81 ? 1 : 2;
+    for (int stage = 0; stage < nstage; stage++) {
+      // full81: full_sub_pel_motion_estimation (me_fullsearch.c:409-469): ONE stage, the 81 quarter-pel positions of
+      // spiral_search (radius 4), computePredQPel, lambda[Q_PEL]
+      const int step = (stage || a.full81) ? 1 : 2;
+      const int metric = (stage || a.full81) ? a.metric_q : a.metric_h;
+      const int first = a.full81 ? 0 : (stage ? a.start_qp : a.start_hp);
+      const int lam = (stage || a.full81) ? a.lambda_q : a.lambda_h;
+      const int ncand = a.full81 ? 81 : 9;
       __syncthreads();
-      for (int i = tid; i < NPART * 9; i += SP_NT) (&dist[0][0])[i] = 0;
+      for (int i = tid; i < NPART * 81; i += SP_NT) (&dist[0][0])[i] = 0;
       __syncthreads();
+      for (int c = c0; c < ncand; c += 9) {
       if (tid < 144 && c >= first) {
         uint32_t keys[7]; int vals[7];
-        const int sx = step * c_sp9[c][0], sy = step * c_sp9[c][1];
+        int spx, spy; spiral_xy(c, &spx, &spy);
+        const int sx = step * spx, sy = step * spy;
 #pragma unroll
         for (int bti = 0; bti < 7; bti++) {
           keys[bti] = 0xffffffffu; vals[bti] = 0;
@@ -147,18 +153,20 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
           atomicAdd(&dist[p][c], v);
         }
       }
+      }
       __syncthreads();
       if (tid < NPART && ((a.part_mask >> tid) & 1ull)) {
         const int p = tid;
         long long best = mincost[p]; int best_pos = 0;
-        for (int cc = first; cc < 9; cc++) {
-          const int mvx = mv[p][0] + step * c_sp9[cc][0], mvy = mv[p][1] + step * c_sp9[cc][1];
+        for (int cc = first; cc < ncand; cc++) {
+          int spx, spy; spiral_xy(cc, &spx, &spy);
+          const int mvx = mv[p][0] + step * spx, mvy = mv[p][1] + step * spy;
           const long long cost = (long long)lam * (mvbits(mvx - prd[p][0]) + mvbits(mvy - prd[p][1])) + ((long long)dist[p][cc] << 5);
           if (cost < best) { best = cost; best_pos = cc; }
         }
-        mv[p][0] = (short)(mv[p][0] + step * c_sp9[best_pos][0]);
-        mv[p][1] = (short)(mv[p][1] + step * c_sp9[best_pos][1]);
-        if (stage == 0 && !a.start_qp) best = DMAX;     // me_fullsearch.c:252-253
+        { int spx, spy; spiral_xy(best_pos, &spx, &spy);
+          mv[p][0] = (short)(mv[p][0] + step * spx); mv[p][1] = (short)(mv[p][1] + step * spy); }
+        if (stage == 0 && !a.full81 && !a.start_qp) best = DMAX;     // me_fullsearch.c:252-253
         mincost[p] = best;
       }
     }
@@ -173,6 +181,67 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
 cudaError_t launch_subpel_refine(const SubArgs &a, cudaStream_t s)
 {
   k_subpel_refine<<<a.nitems, SP_NT, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace b2
+
+// ---- distortion4x4/8x8{SAD,SSE,SATD} on precomputed difference blocks (me_distortion.c:38-134) ----------------
+// One thread per block; HBM-bound (32 or 128 bytes in, 8 out).
+namespace b2 {
+
+__device__ __forceinline__ int hadamard8x8_abs(const short *d)
+{
+  // HadamardSAD8x8 (me_distortion.c:266-341): separable 8-point Hadamard, (sum |coef| + 2) >> 2
+  int m[64], s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = d[8 * i + j];
+#pragma unroll
+    for (int len = 1; len < 8; len <<= 1)
+#pragma unroll
+      for (int j = 0; j < 8; j++) if (!(j & len)) { const int x = v[j], y = v[j + len]; v[j] = x + y; v[j + len] = x - y; }
+#pragma unroll
+    for (int j = 0; j < 8; j++) m[8 * i + j] = v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    int v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = m[8 * i + j];
+#pragma unroll
+    for (int len = 1; len < 8; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < 8; i++) if (!(i & len)) { const int x = v[i], y = v[i + len]; v[i] = x + y; v[i + len] = x - y; }
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += abs(v[i]);
+  }
+  return (s + 2) >> 2;
+}
+
+__global__ void __launch_bounds__(128) k_distortion(int kind, int n, int nblk, const int16_t *__restrict__ diff, long long *__restrict__ out)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblk) return;
+  const int m = n * n;
+  short d[64];
+  const uint4 *src = reinterpret_cast<const uint4 *>(diff + (size_t)b * m);
+  for (int i = 0; i < m / 8; i++) reinterpret_cast<uint4 *>(d)[i] = src[i];
+  long long v = 0;
+  if (kind == 2) {
+    if (n == 4) { int t[16]; for (int i = 0; i < 16; i++) t[i] = d[i]; v = hadamard4x4_abs(t); }
+    else v = hadamard8x8_abs(d);
+  } else {
+    for (int i = 0; i < m; i++) v += kind == 0 ? (long long)abs((int)d[i]) : (long long)d[i] * d[i];
+  }
+  out[b] = v << 5;
+}
+
+cudaError_t launch_distortion(int kind, int n, int nblk, const int16_t *diff, long long *out, cudaStream_t s)
+{
+  k_distortion<<<(nblk + 127) / 128, 128, 0, s>>>(kind, n, nblk, diff, out);
   return cudaGetLastError();
 }
 

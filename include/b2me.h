@@ -58,7 +58,8 @@ typedef struct b2me_search_params {
   int32_t metric_h;          /* MEDistortionHPel: 0 SAD, 2 SATD */
   int32_t metric_q;          /* MEDistortionQPel: 0 SAD, 2 SATD */
   int32_t do_subpel;         /* !DisableSubpelME */
-  int32_t reserved;
+  int32_t subpel_full;       /* 0: sub_pel_motion_estimation (9 half + 8 quarter); 1: full_sub_pel_motion_estimation,
+                                the 81 quarter-pel positions (SubPelME when EPZSSubPelME == 2, me_fullsearch.c:409-469) */
   int64_t min_mcost;         /* initial bound handed to the integer search (B2ME_DISTBLK_MAX) */
 } b2me_search_params;
 
@@ -118,6 +119,13 @@ int b2me_block_search(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int re
 int b2me_block_subpel(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int ref_idx,
                       const int16_t pred_mv[2], const int16_t mv_in[2], const b2me_search_params *params,
                       int64_t min_mcost, int16_t mv_out[2], int64_t *cost_out);
+
+/* ---- mode-decision distortions on precomputed difference blocks ------------------------ */
+/* distortion4x4/8x8{SAD,SSE,SATD} (JM/lencod/src/me_distortion.c:38-134; p_Vid->distortion4x4/8x8 as bound by
+ * select_distortion :136-158): diff [nblk][n*n] int16 raster, n = 4 or 8, kind 0 SAD, 1 SSE, 2 SATD
+ * (HadamardSAD4x4 / HadamardSAD8x8); out [nblk] = dist_scale(distortion) = distortion << 5. */
+int b2me_distortion_blocks(int device, int kind, int n, int nblk, const int16_t *diff, int64_t *out);
+int b2me_distortion_blocks_dev(int kind, int n, int nblk, const int16_t *diff_dev, int64_t *out_dev, void *stream);
 
 /* ---- instrumentation ---------------------------------------------------------------- */
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */

@@ -90,6 +90,14 @@ def hadamard4x4(diff):
     return orc_lib().orc_hadamard4x4(_ptr(d))
 
 
+def distortion_blocks(kind, n, diff):
+    """distortion4x4/8x8{SAD,SSE,SATD} restated (me_distortion.c:38-134): diff [nblk][n*n] int16 -> int64 [nblk]."""
+    L = orc_lib()
+    L.orc_distortion.restype = C.c_int64
+    d = np.ascontiguousarray(diff, np.int16)
+    return np.array([L.orc_distortion(C.c_int(kind), C.c_int(n), _ptr(d[i])) for i in range(d.shape[0])], np.int64)
+
+
 def hadamard8x8(diff):
     d = np.ascontiguousarray(diff, np.int16)
     return orc_lib().orc_hadamard8x8(_ptr(d))
@@ -199,6 +207,12 @@ class JMRef:
 
     def satd(self, pos_x, pos_y, blocktype, ref, cand_x, cand_y, test8x8=0):
         return self.L.jmh_satd(self.h, pos_x, pos_y, blocktype, ref, cand_x, cand_y, test8x8)
+
+    def distortion(self, kind, n, diff):
+        """the reference's distortion4x4/8x8{SAD,SSE,SATD} on one difference block"""
+        self.L.jmh_distortion.restype = C.c_longlong
+        d = np.ascontiguousarray(diff, np.int16)
+        return int(self.L.jmh_distortion(C.c_int(kind), C.c_int(n), _ptr(d)))
 
     def hadamard4x4(self, diff):
         d = np.ascontiguousarray(diff, np.int16)

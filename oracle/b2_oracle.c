@@ -214,6 +214,16 @@ int orc_satd(const uint8_t *planes, int W, int H, const uint8_t *cur, int cur_st
   return s;
 }
 
+/* distortion4x4/8x8{SAD,SSE,SATD} (me_distortion.c:38-134) on a precomputed difference block: dist_scale(d) = d << 5.
+ * kind 0 SAD, 1 SSE, 2 SATD; n = 4 or 8; diff raster n*n shorts. */
+int64_t orc_distortion(int kind, int n, const int16_t *diff)
+{
+  int64_t d = 0; int k;
+  if (kind == 2) d = n == 4 ? orc_hadamard4x4(diff) : orc_hadamard8x8(diff);
+  else for (k = 0; k < n * n; k++) d += kind == 0 ? iabs_(diff[k]) : (int64_t)diff[k] * diff[k];
+  return d << 5;
+}
+
 /* ------------------------------------------------------------------------------------
  * Searches.
  * ---------------------------------------------------------------------------------- */
@@ -305,6 +315,28 @@ int64_t orc_sub_pel(const OrcFrame *f, int ref, int pos_x, int pos_y, int bsx, i
 }
 
 /* partition p (0..40) -> blocktype (1..7, JM block_size[] macroblock.h:58) and offset in MB */
+/* full_sub_pel_motion_estimation (me_fullsearch.c:409-469), RDO build (check_position0 is a !rdopt rule):
+ * the 81 quarter-pel positions of spiral_search (radius 4) around mv, computePredQPel, strict '<' in scan order. */
+int64_t orc_full_sub_pel(const OrcFrame *f, int ref, int pos_x, int pos_y, int bsx, int bsy,
+                         const int16_t *pred_mv, int16_t *mv, int64_t min_mcost, int lambda_q, int metric_q, int test8x8)
+{
+  const uint8_t *pl = orc_frame_planes((void *)f, ref);
+  const uint8_t *cur = f->cur + (size_t)pos_y * f->W + pos_x;
+  int pos, best_pos;
+  for (best_pos = 0, pos = 0; pos < 81; pos++) {
+    int cx = mv[0] + f->spiral[2*pos], cy = mv[1] + f->spiral[2*pos+1];
+    int64_t mcost = orc_mv_cost(lambda_q, cx, cy, pred_mv[0], pred_mv[1]);
+    int d;
+    if (mcost >= min_mcost) continue;
+    d = (metric_q == 2) ? orc_satd(pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2), test8x8)
+                        : orc_sad (pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2));
+    mcost += ((int64_t)d) << 5;
+    if (mcost < min_mcost) { min_mcost = mcost; best_pos = pos; }
+  }
+  if (best_pos) { mv[0] = (int16_t)(mv[0] + f->spiral[2*best_pos]); mv[1] = (int16_t)(mv[1] + f->spiral[2*best_pos+1]); }
+  return min_mcost;
+}
+
 static const uint8_t ORC_BS[8][2] = {{0,0},{16,16},{16,8},{8,16},{8,8},{8,4},{4,8},{4,4}};
 static const int ORC_FIRST[8] = {0, 0, 1, 3, 5, 9, 17, 25};
 void orc_partition_geometry(int p, int *bt, int *ox, int *oy, int *w, int *h)
@@ -347,8 +379,12 @@ void orc_search_frame(void *h, int mb_first, int mb_count, const int16_t *pred, 
         mv_int[2*i] = mv[0]; mv_int[2*i+1] = mv[1]; cost_int[i] = c;
         if (do_subpel) {
           if (!start_hp) c = DISTBLK_MAX_ORC;
-          c = orc_sub_pel(f, r, (m % mbw) * 16 + ox, (m / mbw) * 16 + oy, w, hh, pred + 2*i, mv, c,
-                          lambda_factor, start_hp, start_qp, metric_h, metric_q, 0);
+          if (do_subpel == 2)          /* SubPelME = full_sub_pel_motion_estimation (EPZSSubPelME == 2, me_epzs_common.c:157) */
+            c = orc_full_sub_pel(f, r, (m % mbw) * 16 + ox, (m / mbw) * 16 + oy, w, hh, pred + 2*i, mv, c,
+                                 lambda_factor[2], metric_q, 0);
+          else
+            c = orc_sub_pel(f, r, (m % mbw) * 16 + ox, (m / mbw) * 16 + oy, w, hh, pred + 2*i, mv, c,
+                            lambda_factor, start_hp, start_qp, metric_h, metric_q, 0);
           mv_sub[2*i] = mv[0]; mv_sub[2*i+1] = mv[1]; cost_sub[i] = c;
         }
       }

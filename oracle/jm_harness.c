@@ -187,7 +187,8 @@ void jmh_block_search(void *hh, int pos_x, int pos_y, int blocktype, int ref,
   mv_int_out[0] = b.mv[0].mv_x; mv_int_out[1] = b.mv[0].mv_y; *cost_int_out = (long long)c;
   if (do_subpel) {
     if (!h->p_Vid->start_me_refinement_hp) c = DISTBLK_MAX;     /* mv_search.c:971-974 */
-    c = sub_pel_motion_estimation(&h->mb, &pred, &b, c, lam);
+    c = do_subpel == 2 ? full_sub_pel_motion_estimation(&h->mb, &pred, &b, c, lam)      /* EPZSSubPelME == 2 */
+                       : sub_pel_motion_estimation(&h->mb, &pred, &b, c, lam);
     mv_sub_out[0] = b.mv[0].mv_x; mv_sub_out[1] = b.mv[0].mv_y; *cost_sub_out = (long long)c;
   }
   free(b.orig_pic);
@@ -246,6 +247,12 @@ long long jmh_satd(void *hh, int pos_x, int pos_y, int blocktype, int ref, int c
   c.mv_x = (short)cand_x; c.mv_y = (short)cand_y;
   d = computeSATD(h->refs[ref], &b, DISTBLK_MAX, &c);
   free(b.orig_pic); return (long long)d;
+}
+/* mode-decision distortions on a precomputed difference block (me_distortion.c:38-166): kind 0 SAD, 1 SSE, 2 SATD */
+long long jmh_distortion(int kind, int n, short *diff)
+{
+  if (n == 4) return (long long)(kind == 0 ? distortion4x4SAD(diff, DISTBLK_MAX) : kind == 1 ? distortion4x4SSE(diff, DISTBLK_MAX) : distortion4x4SATD(diff, DISTBLK_MAX));
+  return (long long)(kind == 0 ? distortion8x8SAD(diff, DISTBLK_MAX) : kind == 1 ? distortion8x8SSE(diff, DISTBLK_MAX) : distortion8x8SATD(diff, DISTBLK_MAX));
 }
 int jmh_hadamard4x4(short *diff) { return HadamardSAD4x4(diff); }
 int jmh_hadamard8x8(short *diff) { return HadamardSAD8x8(diff); }

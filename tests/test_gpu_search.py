@@ -175,3 +175,25 @@ def test_banded_search_equals_full_frame():
         sl = slice(b.mb_first, b.mb_first + b.mb_count)
         for got, exp in zip((mvi, ci, mvs, cs), full):
             assert (got.cpu().numpy()[sl] == exp[sl]).all(), rank
+
+
+def test_full_sub_pel_mode_matches_oracle():
+    """b2me_search_params.subpel_full: full_sub_pel_motion_estimation (81 quarter-pel positions), SATD and SAD."""
+    W, H, R = 64, 48, 8
+    s, cur, refs = _setup(W, H, R, 2, seed=41)
+    of = oracle.OrcFrame(cur, refs, R)
+    pred, cen = synth.predictors(W, H, 2, seed=9, spread=5, rmax=5)
+    for mq in (2, 0):
+        got = s.search_frame(pred, cen, api.make_params((130, 100, 80), metric_h=mq, metric_q=mq, subpel_full=True))
+        exp = of.search_frame(pred, cen, (130, 100, 80), metric_h=mq, metric_q=mq, do_subpel=2)
+        for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+            assert (a == b).all(), (mq, n, int((a != b).sum()))
+
+
+def test_distortion_blocks_match_oracle():
+    rng = np.random.default_rng(8)
+    for n in (4, 8):
+        diff = rng.integers(-255, 256, (1000, n * n)).astype(np.int16)
+        diff[0] = 0; diff[1] = 255; diff[2] = -255
+        for kind in (0, 1, 2):
+            assert (api.distortion_blocks(kind, n, diff) == oracle.distortion_blocks(kind, n, diff)).all(), (n, kind)

@@ -85,3 +85,32 @@ def test_oracle_vs_reference_objects_live():
     b = of.search_frame(pred, cen, (120, 100, 100))
     for x, y in zip(a, b):
         assert (x == y).all()
+
+
+@pytest.mark.skipif(not oracle.have_jmref(), reason="needs oracle/_ref/libjmref.so (built from /root/reference)")
+def test_full_sub_pel_restatement_matches_reference():
+    """orc_full_sub_pel == the unmodified full_sub_pel_motion_estimation (me_fullsearch.c:409-469), all 41 partitions."""
+    W, H, R, NR = 64, 48, 8, 1
+    fr = synth.luma_sequence(W, H, 2, seed=17)
+    cur, refs = fr[1], fr[[0]]
+    pred, cen = synth.predictors(W, H, NR, seed=6, spread=5, rmax=5)
+    ref = oracle.JMRef(W, H, R, NR)
+    ref.set_ref(0, refs[0]); ref.set_cur(cur)
+    lam = np.array([120, 90, 70], np.int32)
+    exp = ref.search_frame(pred, cen, lam, do_subpel=2)
+    got = oracle.OrcFrame(cur, refs, R).search_frame(pred, cen, lam, do_subpel=2)
+    for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+        assert (a == b).all(), (n, int((a != b).sum()))
+
+
+@pytest.mark.skipif(not oracle.have_jmref(), reason="needs oracle/_ref/libjmref.so (built from /root/reference)")
+def test_distortion_blocks_restatement_matches_reference():
+    rng = np.random.default_rng(3)
+    ref = oracle.JMRef(64, 48, 8, 1)
+    for n in (4, 8):
+        diff = rng.integers(-255, 256, (40, n * n)).astype(np.int16)
+        diff[0] = 0; diff[1] = 255; diff[2] = -255
+        for kind in (0, 1, 2):
+            got = oracle.distortion_blocks(kind, n, diff)
+            exp = np.array([ref.distortion(kind, n, diff[i]) for i in range(diff.shape[0])], np.int64)
+            assert (got == exp).all(), (n, kind)
