@@ -211,9 +211,9 @@ static int check_params(b2me_ctx *c, const b2me_search_params *p)
 {
   if (!p) return B2ME_EINVAL;
   if (p->restrict_mode < 0 || p->restrict_mode > 2) return B2ME_EINVAL;
-  if (p->do_subpel && ((p->metric_h != 0 && p->metric_h != 2) || (p->metric_q != 0 && p->metric_q != 2))) {
-    snprintf(c->err, sizeof(c->err), "sub-pel metric SSE is not implemented on this path");
-    return B2ME_EUNSUPPORTED;
+  if (p->do_subpel && (p->metric_h < 0 || p->metric_h > 2 || p->metric_q < 0 || p->metric_q > 2)) {
+    snprintf(c->err, sizeof(c->err), "sub-pel metric must be 0 (SAD), 1 (SSE) or 2 (SATD)");
+    return B2ME_EINVAL;
   }
   return B2ME_OK;
 }

@@ -73,7 +73,7 @@ __device__ __forceinline__ int tile_distortion(const uint8_t *cur, int tx, int t
   if (metric == 2) return hadamard4x4_abs(d);
   int v = 0;
 #pragma unroll
-  for (int q = 0; q < 16; q++) v += abs(d[q]);
+  for (int q = 0; q < 16; q++) v += metric == 1 ? d[q] * d[q] : abs(d[q]);      // SSE (computeSSE, me_distortion.c:1190) / SAD
   return v;
 }
 
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
               const int ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX, oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY;
               v = tile_distortion(cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, 2);
             }
-          } else {                    // SAD: block origin clamp (me_distortion.c:367): key = the tile actually read
+          } else {                    // SAD / SSE: block origin clamp (me_distortion.c:367, :1205): key = the tile actually read
             const PartGeom gm = part_geom(p);
             const int qx = 4 * (mbx * 16 + gm.ox) + mv[p][0] + sx, qy = 4 * (mby * 16 + gm.oy) + mv[p][1] + sy;
             const int pl = (qy & 3) * 4 + (qx & 3);
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
             kk = (uint32_t)pl | ((uint32_t)ox << 4) | ((uint32_t)oy << 18);     // ox, oy < 2^14
 #pragma unroll
             for (int b2 = 0; b2 < bti; b2++) if (keys[b2] == kk) v = vals[b2];
-            if (v < 0) v = tile_distortion(cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, 0);
+            if (v < 0) v = tile_distortion(cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, metric);
           }
           keys[bti] = kk; vals[bti] = v;
           atomicAdd(&dist[p][c], v);

@@ -55,8 +55,8 @@ typedef struct b2me_ctx b2me_ctx;
 typedef struct b2me_search_params {
   int32_t lambda_factor[3];  /* F_PEL, H_PEL, Q_PEL lambda_mf (LAMBDA_FACTOR, JM defines.h:130) */
   int32_t restrict_mode;     /* p_Inp->full_search (RestrictSearchRange): 0,1,2 (mv_search.c:70-92) */
-  int32_t metric_h;          /* MEDistortionHPel: 0 SAD, 2 SATD */
-  int32_t metric_q;          /* MEDistortionQPel: 0 SAD, 2 SATD */
+  int32_t metric_h;          /* MEDistortionHPel: 0 SAD, 1 SSE, 2 SATD (computeSAD / computeSSE / computeSATD) */
+  int32_t metric_q;          /* MEDistortionQPel: 0 SAD, 1 SSE, 2 SATD */
   int32_t do_subpel;         /* !DisableSubpelME */
   int32_t subpel_full;       /* 0: sub_pel_motion_estimation (9 half + 8 quarter); 1: full_sub_pel_motion_estimation,
                                 the 81 quarter-pel positions (SubPelME when EPZSSubPelME == 2, me_fullsearch.c:409-469) */

@@ -159,6 +159,21 @@ int orc_sad(const uint8_t *planes, int W, int H, const uint8_t *cur, int cur_str
   return s;
 }
 
+/* computeSSE (JM/lencod/src/me_distortion.c:1190-1255), luma only: as computeSAD with squared differences. */
+int orc_sse(const uint8_t *planes, int W, int H, const uint8_t *cur, int cur_stride,
+            int bsx, int bsy, int cand_x, int cand_y)
+{
+  const int Wp = W + 2 * PAD_X;
+  const uint8_t *ref = orc_umv_line4x(planes, W, H, cand_y, cand_x);
+  int x, y, s = 0;
+  for (y = 0; y < bsy; y++)
+    for (x = 0; x < bsx; x++) {
+      const int d = (int)cur[y * cur_stride + x] - (int)ref[(size_t)y * Wp + x];
+      s += d * d;
+    }
+  return s;
+}
+
 /* HadamardSAD4x4 (me_distortion.c:175-258): 2-D 4-point Hadamard, sum |coef|, (s+1)>>1.
  * The butterfly network is sign/permutation-equivalent to H4 * D * H4; the absolute sum is
  * invariant to row/column sign flips and permutations of the transform, so a plain
@@ -293,6 +308,7 @@ int64_t orc_sub_pel(const OrcFrame *f, int ref, int pos_x, int pos_y, int bsx, i
     int d;
     if (mcost >= min_mcost) continue;
     d = (metric_h == 2) ? orc_satd(pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2), test8x8)
+      : (metric_h == 1) ? orc_sse (pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2))
                         : orc_sad (pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2));
     mcost += ((int64_t)d) << 5;
     if (mcost < min_mcost) { min_mcost = mcost; best_pos = pos; }
@@ -306,6 +322,7 @@ int64_t orc_sub_pel(const OrcFrame *f, int ref, int pos_x, int pos_y, int bsx, i
     int d;
     if (mcost >= min_mcost) continue;
     d = (metric_q == 2) ? orc_satd(pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2), test8x8)
+      : (metric_q == 1) ? orc_sse (pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2))
                         : orc_sad (pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2));
     mcost += ((int64_t)d) << 5;
     if (mcost < min_mcost) { min_mcost = mcost; best_pos = pos; }
@@ -329,6 +346,7 @@ int64_t orc_full_sub_pel(const OrcFrame *f, int ref, int pos_x, int pos_y, int b
     int d;
     if (mcost >= min_mcost) continue;
     d = (metric_q == 2) ? orc_satd(pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2), test8x8)
+      : (metric_q == 1) ? orc_sse (pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2))
                         : orc_sad (pl, f->W, f->H, cur, f->W, bsx, bsy, cx + (pos_x << 2), cy + (pos_y << 2));
     mcost += ((int64_t)d) << 5;
     if (mcost < min_mcost) { min_mcost = mcost; best_pos = pos; }

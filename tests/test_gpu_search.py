@@ -128,7 +128,7 @@ def test_error_codes():
     with pytest.raises(api.B2Error):
         s.block_search(0, 0, 9, 0, (0, 0), (0, 0), api.make_params(100), 7)   # bad blocktype
     with pytest.raises(api.B2Error):
-        s.search_frame(*synth.predictors(64, 48, 1), api.make_params(100, metric_h=1))  # SSE unsupported
+        s.search_frame(*synth.predictors(64, 48, 1), api.make_params(100, metric_h=3))  # no such metric
     pred, cen = synth.predictors(64, 48, 1)
     cen = cen.copy(); cen[0, 0, 0, 0] = 2               # quarter-pel centre
     s.set_cur(np.zeros((48, 64), np.uint8)); s.set_ref(0, np.zeros((48, 64), np.uint8))
@@ -197,3 +197,16 @@ def test_distortion_blocks_match_oracle():
         diff[0] = 0; diff[1] = 255; diff[2] = -255
         for kind in (0, 1, 2):
             assert (api.distortion_blocks(kind, n, diff) == oracle.distortion_blocks(kind, n, diff)).all(), (n, kind)
+
+
+def test_sse_subpel_metric_matches_oracle():
+    """MEDistortionHPel/QPel = SSE (computeSSE, me_distortion.c:1190-1255) and the mixed SAD/SSE/SATD settings."""
+    W, H, R = 64, 48, 7
+    s, cur, refs = _setup(W, H, R, 1, seed=52)
+    of = oracle.OrcFrame(cur, refs, R)
+    pred, cen = synth.predictors(W, H, 1, seed=4, spread=3, rmax=4)
+    for mh, mq in ((1, 1), (1, 2), (0, 1), (2, 1)):
+        got = s.search_frame(pred, cen, api.make_params((100, 60, 60), metric_h=mh, metric_q=mq))
+        exp = of.search_frame(pred, cen, (100, 60, 60), metric_h=mh, metric_q=mq)
+        for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+            assert (a == b).all(), (mh, mq, n, int((a != b).sum()))

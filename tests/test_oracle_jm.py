@@ -114,3 +114,19 @@ def test_distortion_blocks_restatement_matches_reference():
             got = oracle.distortion_blocks(kind, n, diff)
             exp = np.array([ref.distortion(kind, n, diff[i]) for i in range(diff.shape[0])], np.int64)
             assert (got == exp).all(), (n, kind)
+
+
+@pytest.mark.skipif(not oracle.have_jmref(), reason="needs oracle/_ref/libjmref.so (built from /root/reference)")
+def test_sse_subpel_restatement_matches_reference():
+    """orc_sse inside the sub-pel refinement == the unmodified JM with MEDistortionHPel = QPel = SSE."""
+    W, H, R, NR = 64, 48, 8, 1
+    fr = synth.luma_sequence(W, H, 2, seed=19)
+    cur, refs = fr[1], fr[[0]]
+    pred, cen = synth.predictors(W, H, NR, seed=7, spread=4, rmax=5)
+    ref = oracle.JMRef(W, H, R, NR, metric=(0, 1, 1))
+    ref.set_ref(0, refs[0]); ref.set_cur(cur)
+    lam = np.array([120, 60, 60], np.int32)
+    exp = ref.search_frame(pred, cen, lam)
+    got = oracle.OrcFrame(cur, refs, R).search_frame(pred, cen, lam, metric_h=1, metric_q=1)
+    for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+        assert (a == b).all(), (n, int((a != b).sum()))
