@@ -113,6 +113,11 @@ class Searcher:
         assert luma.shape == (self.H, self.W)
         self._chk(self.L.b2me_set_ref(self.h, C.c_int(r), _p(luma), C.c_int(self.W)), "b2me_set_ref")
 
+    def set_ref_weights(self, r, weight, offset, log_denom, apply=True):
+        """explicit weighted prediction of reference slot r; takes effect at the next set_ref of that slot"""
+        self._chk(self.L.b2me_set_ref_weights(self.h, C.c_int(r), C.c_int(int(apply)), C.c_int(weight), C.c_int(offset), C.c_int(log_denom)),
+                  "b2me_set_ref_weights")
+
     def set_cur_dev(self, t, stream=0):
         self._chk(self.L.b2me_set_cur_dev(self.h, _dp(t), C.c_int(t.stride(0)), _vp(stream)), "b2me_set_cur_dev")
 

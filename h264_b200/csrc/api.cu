@@ -179,7 +179,21 @@ static int build_planes(b2me_ctx *c, int ref_idx, const uint8_t *luma_dev, int s
   B2_CUDA_CHECK(c, launch_subpel_planes(luma_dev, stride, c->W, c->H, c->d_planes + (size_t)ref_idx * 16 * c->plane_size, s));
   B2_CUDA_CHECK(c, launch_search_plane(luma_dev, stride, c->W, c->H, c->d_spl + (size_t)ref_idx * 16 * c->Wq * c->Hq, c->Wq, c->Hq, c->spad, s));
   c->launches += 3;
+  if (c->wp_apply[ref_idx]) {          // weighted reference: map the planes the distortions read (see k_apply_wp)
+    B2_CUDA_CHECK(c, launch_apply_wp(c->d_planes + (size_t)ref_idx * 16 * c->plane_size, c->plane_size * 16,
+                                     c->wp_weight[ref_idx], c->wp_offset[ref_idx], c->wp_denom[ref_idx], s));
+    B2_CUDA_CHECK(c, launch_apply_wp(c->d_spl + (size_t)ref_idx * 16 * c->Wq * c->Hq, (size_t)c->Wq * c->Hq * 16,
+                                     c->wp_weight[ref_idx], c->wp_offset[ref_idx], c->wp_denom[ref_idx], s));
+    c->launches += 2;
+  }
   t.stop();
+  return B2ME_OK;
+}
+extern "C" int b2me_set_ref_weights(b2me_ctx *c, int ref_idx, int apply, int weight, int offset, int log_weight_denom)
+{
+  if (!c || ref_idx < 0 || ref_idx >= c->nrefs || log_weight_denom < 0 || log_weight_denom > 7 ||
+      weight < -128 || weight > 127 || offset < -128 || offset > 127) return B2ME_EINVAL;
+  c->wp_apply[ref_idx] = apply ? 1 : 0; c->wp_weight[ref_idx] = weight; c->wp_offset[ref_idx] = offset; c->wp_denom[ref_idx] = log_weight_denom;
   return B2ME_OK;
 }
 extern "C" int b2me_set_ref_dev(b2me_ctx *c, int ref_idx, const uint8_t *luma_dev, int stride, void *stream)

@@ -26,6 +26,7 @@ struct b2me_ctx {
   long long *d_io64;
   int *d_errflag;
   int *d_work;                  // k_sad_fs item counter
+  int wp_apply[16], wp_weight[16], wp_offset[16], wp_denom[16];   // explicit weighted prediction per reference slot
   unsigned long long *d_stats;
   cudaStream_t stream;          // internal stream for host-pointer calls
   cudaStream_t stream_h2d, stream_d2h;   // copy streams of the banded host-pointer search
@@ -91,6 +92,7 @@ struct SubArgs {
 cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, cudaStream_t s);
 cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, cudaStream_t s, int *smem_bytes_out);
 FsGeom fs_geom_host(int R);
+cudaError_t launch_apply_wp(uint8_t *buf, size_t bytes, int weight, int offset, int log_denom, cudaStream_t s);
 cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, cudaStream_t s);
 cudaError_t launch_subpel_refine(const SubArgs &a, cudaStream_t s);
 cudaError_t ubench(int kind, int iters, double *gops);

@@ -117,6 +117,31 @@ __global__ void __launch_bounds__(256) k_search_plane(const uint8_t *__restrict_
     reinterpret_cast<uint32_t *>(out + (size_t)s * Wq * Hq)[i] = b[s] | (b[s + 1] << 8) | (b[s + 2] << 16) | (b[s + 3] << 24);
 }
 
+// Explicit weighted prediction of the single-list search (computeSADWP / SATDWP / SSEWP, me_distortion.c:434-517,
+// 833-935, 1262-1345): the distortion replaces every reference sample v it reads by
+// clip1(((weight*v + round) >> log_denom) + offset).  The mapping is pointwise on the fetched sample, so it is
+// applied once to the reference's planes (16 quarter-pel planes and 16 search planes) instead of per candidate.
+__global__ void __launch_bounds__(256) k_apply_wp(uint32_t *__restrict__ buf, size_t nwords, int weight, int offset, int log_denom, int rnd)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t w = buf[i];
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int v = (int)((w >> (8 * k)) & 255u);
+      o |= (uint32_t)iclamp(((weight * v + rnd) >> log_denom) + offset, 0, 255) << (8 * k);
+    }
+    buf[i] = o;
+  }
+}
+cudaError_t launch_apply_wp(uint8_t *buf, size_t bytes, int weight, int offset, int log_denom, cudaStream_t s)
+{
+  const size_t nw = bytes / 4;
+  const int grid = (int)((nw + 255) / 256 < 148 * 16 ? (nw + 255) / 256 : 148 * 16);
+  k_apply_wp<<<grid, 256, 0, s>>>(reinterpret_cast<uint32_t *>(buf), nw, weight, offset, log_denom, log_denom ? 1 << (log_denom - 1) : 0);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, cudaStream_t s)
 {
   const int n = (Wq >> 2) * Hq;

@@ -79,6 +79,11 @@ int b2me_set_cur_dev(b2me_ctx *ctx, const uint8_t *luma_dev, int stride, void *s
  * quarter-pel planes on the device (getSubImagesLuma). */
 int b2me_set_ref(b2me_ctx *ctx, int ref_idx, const uint8_t *luma, int stride);
 int b2me_set_ref_dev(b2me_ctx *ctx, int ref_idx, const uint8_t *luma_dev, int stride, void *stream);
+/* Explicit weighted prediction for the single-list search (UseWeightedReferenceME: computeSADWP / SATDWP / SSEWP,
+ * JM/lencod/src/me_distortion.c:434-517, 833-935, 1262-1345; weights from PrepareMEParams, mv_search.c:183-188):
+ * luma weight / offset of reference ref_idx and the slice's luma_log_weight_denom.  Takes effect at the NEXT
+ * b2me_set_ref[_dev] of that slot (the planes the distortions read are stored weighted); apply = 0 turns it off. */
+int b2me_set_ref_weights(b2me_ctx *ctx, int ref_idx, int apply, int weight, int offset, int log_weight_denom);
 /* Read back sub-pel plane [yy][xx] (padded (H+40) x (W+64), tightly packed) -- parity tests. */
 int b2me_get_subplane(b2me_ctx *ctx, int ref_idx, int yy, int xx, uint8_t *out);
 

@@ -122,6 +122,10 @@ class OrcFrame:
         except Exception:
             pass
 
+    def set_weights(self, ref, weight, offset, log_denom):
+        """explicit WP of reference `ref` (computeSADWP/SATDWP/SSEWP); call once, after construction"""
+        self.L.orc_frame_set_weights(self.h, C.c_int(ref), C.c_int(weight), C.c_int(offset), C.c_int(log_denom))
+
     def planes(self, r):
         Hp, Wp = self.H + 2 * PAD_Y, self.W + 2 * PAD_X
         p = self.L.orc_frame_planes(self.h, C.c_int(r))
@@ -180,6 +184,11 @@ class JMRef:
         luma = np.ascontiguousarray(luma, np.uint8)
         assert luma.shape == (self.H, self.W)
         self.L.jmh_set_ref(self.h, C.c_int(r), _ptr(luma))
+
+    def set_weights(self, log_denom, weights, offsets, apply=True):
+        """UseWeightedReferenceME with explicit weights: per-reference luma weight / offset"""
+        w = np.ascontiguousarray(weights, np.int16); o = np.ascontiguousarray(offsets, np.int16)
+        self.L.jmh_set_weights(self.h, C.c_int(int(apply)), C.c_int(log_denom), _ptr(w), _ptr(o))
 
     def set_cur(self, luma):
         luma = np.ascontiguousarray(luma, np.uint8)

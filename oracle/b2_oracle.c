@@ -263,6 +263,22 @@ void *orc_frame_create(int W, int H, int nrefs, int R, const uint8_t *cur, const
   orc_spiral(R, f->spiral);
   return f;
 }
+/* Explicit weighted prediction of the single-list search (computeSADWP / SATDWP / SSEWP, me_distortion.c:434-517,
+ * :833-935, :1262-1345): every reference sample v read by the distortion is replaced by
+ *     clip1(((weight * v + round) >> log_denom) + offset),  round = log_denom ? 1 << (log_denom-1) : 0.
+ * The mapping is pointwise on the fetched (integer or interpolated) sample, so applying it to the 16 quarter-pel
+ * planes of the reference is the same computation. */
+void orc_frame_set_weights(void *h, int ref, int weight, int offset, int log_denom)
+{
+  OrcFrame *f = (OrcFrame *)h;
+  const size_t n = (size_t)16 * (f->W + 2 * PAD_X) * (f->H + 2 * PAD_Y);
+  uint8_t *p = (uint8_t *)f->planes + (size_t)ref * n;
+  const int rnd = log_denom ? 1 << (log_denom - 1) : 0;
+  uint8_t lut[256]; size_t i; int v;
+  for (v = 0; v < 256; v++) lut[v] = (uint8_t)clip1_255(((weight * v + rnd) >> log_denom) + offset);
+  for (i = 0; i < n; i++) p[i] = lut[p[i]];
+}
+
 void orc_frame_destroy(void *h)
 { OrcFrame *f = (OrcFrame *)h; free((void *)f->cur); free((void *)f->planes); free(f->spiral); free(f); }
 const uint8_t *orc_frame_planes(void *h, int r)

@@ -38,6 +38,8 @@ typedef struct {
   StorablePicture **refs;     /* nrefs pictures with 16 sub-planes each */
   StorablePicture **listX0;   /* list 0 */
   imgpel **cur;               /* current (original) luma */
+  int wp_apply;               /* UseWeightedReferenceME && weighted_prediction: computeUniPred[x + 3] (the *WP variants) */
+  short wp_weight[16], wp_offset[16];
 } JMH;
 
 /* metric codes follow JM: 0 SAD, 1 SSE, 2 SATD (lcommon/inc/types.h) */
@@ -136,6 +138,18 @@ void jmh_get_subplane(void *hh, int r, int yy, int xx, unsigned char *out)
       out[y * Wp + x] = (unsigned char)p[y - IMG_PAD_SIZE_Y][x - IMG_PAD_SIZE_X];
 }
 
+/* explicit weighted prediction for the single-list search (PrepareMEParams, mv_search.c:183-188; init_mv_block
+ * :731-748): per-reference luma weight / offset, slice-level log2 denominator; wp_luma_round as in
+ * JM/lencod/src/weighted_prediction.c (denom ? 1 << (denom - 1) : 0). */
+void jmh_set_weights(void *hh, int apply, int log_denom, const short *weight, const short *offset)
+{
+  JMH *h = (JMH *)hh; int r;
+  h->wp_apply = apply;
+  h->slice->luma_log_weight_denom = (short)log_denom;
+  h->slice->wp_luma_round = log_denom ? 1 << (log_denom - 1) : 0;
+  for (r = 0; r < h->nrefs && r < 16; r++) { h->wp_weight[r] = weight[r]; h->wp_offset[r] = offset[r]; }
+}
+
 static const short jmh_bs[8][2] = {{0,0},{16,16},{16,8},{8,16},{8,8},{8,4},{4,8},{4,4}};
 
 static void jmh_setup_block(JMH *h, MEBlock *b, imgpel *orig, int pos_x, int pos_y, int blocktype, int ref)
@@ -155,6 +169,13 @@ static void jmh_setup_block(JMH *h, MEBlock *b, imgpel *orig, int pos_x, int pos
   b->computePredFPel = h->p_Vid->computeUniPred[F_PEL];
   b->computePredHPel = h->p_Vid->computeUniPred[H_PEL];
   b->computePredQPel = h->p_Vid->computeUniPred[Q_PEL];
+  if (h->wp_apply) {
+    b->apply_weights = 1;
+    b->computePredFPel = h->p_Vid->computeUniPred[F_PEL + 3];
+    b->computePredHPel = h->p_Vid->computeUniPred[H_PEL + 3];
+    b->computePredQPel = h->p_Vid->computeUniPred[Q_PEL + 3];
+    b->weight_luma = h->wp_weight[ref]; b->offset_luma = h->wp_offset[ref];
+  }
   get_search_range(b, h->p_Inp, (short)ref, blocktype);
   b->orig_pic = (imgpel **)malloc(sizeof(imgpel *));
   b->orig_pic[0] = orig;

@@ -210,3 +210,25 @@ def test_sse_subpel_metric_matches_oracle():
         exp = of.search_frame(pred, cen, (100, 60, 60), metric_h=mh, metric_q=mq)
         for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
             assert (a == b).all(), (mh, mq, n, int((a != b).sum()))
+
+
+def test_weighted_prediction_matches_oracle():
+    """b2me_set_ref_weights: explicit WP of the single-list search (computeSADWP / SATDWP), two references."""
+    W, H, R, NR = 64, 48, 8, 2
+    fr = synth.luma_sequence(W, H, 3, seed=23, gain=0.93, offset=4.0)
+    cur, refs = fr[2], fr[[1, 0]]
+    pred, cen = synth.predictors(W, H, NR, seed=7, spread=4, rmax=5)
+    denom, wts, offs = 5, [30, 27], [3, -6]
+    s = api.Searcher(W, H, NR, R)
+    s.set_cur(cur)
+    of = oracle.OrcFrame(cur, refs, R)
+    for r in range(NR):
+        s.set_ref_weights(r, wts[r], offs[r], denom)
+        s.set_ref(r, refs[r])
+        of.set_weights(r, wts[r], offs[r], denom)
+    got = s.search_frame(pred, cen, api.make_params((120, 90, 90)))
+    exp = of.search_frame(pred, cen, (120, 90, 90))
+    for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+        assert (a == b).all(), (n, int((a != b).sum()))
+    s.set_ref_weights(0, 32, 0, 5, apply=False); s.set_ref(0, refs[0])      # off again: plain planes
+    assert (s.subplane(0, 0, 0) == oracle.subpel_planes(refs[0])[0, 0]).all()

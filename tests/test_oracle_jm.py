@@ -130,3 +130,29 @@ def test_sse_subpel_restatement_matches_reference():
     got = oracle.OrcFrame(cur, refs, R).search_frame(pred, cen, lam, metric_h=1, metric_q=1)
     for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
         assert (a == b).all(), (n, int((a != b).sum()))
+
+
+@pytest.mark.skipif(not oracle.have_jmref(), reason="needs oracle/_ref/libjmref.so (built from /root/reference)")
+@pytest.mark.parametrize("metric", [(0, 2, 2), (0, 0, 0), (0, 1, 1)])
+def test_weighted_prediction_restatement_matches_reference(metric):
+    """Weighted planes + plain distortions == the unmodified computeSADWP / SATDWP / SSEWP (UseWeightedReferenceME)."""
+    W, H, R, NR = 64, 48, 8, 2
+    fr = synth.luma_sequence(W, H, 3, seed=23, gain=0.93, offset=4.0)      # fading clip: weights matter
+    cur, refs = fr[2], fr[[1, 0]]
+    pred, cen = synth.predictors(W, H, NR, seed=7, spread=4, rmax=5)
+    denom, wts, offs = 5, [30, 27], [3, -6]
+    ref = oracle.JMRef(W, H, R, NR, metric=metric)
+    for r in range(NR):
+        ref.set_ref(r, refs[r])
+    ref.set_cur(cur)
+    ref.set_weights(denom, wts, offs)
+    lam = np.array([120, 90, 90], np.int32)
+    exp = ref.search_frame(pred, cen, lam)
+    of = oracle.OrcFrame(cur, refs, R)
+    for r in range(NR):
+        of.set_weights(r, wts[r], offs[r], denom)
+    got = of.search_frame(pred, cen, lam, metric_h=metric[1], metric_q=metric[2])
+    for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+        assert (a == b).all(), (n, int((a != b).sum()))
+    plain = oracle.OrcFrame(cur, refs, R).search_frame(pred, cen, lam, metric_h=metric[1], metric_q=metric[2])
+    assert (plain[1] != got[1]).any()                                     # the weights really change the costs
