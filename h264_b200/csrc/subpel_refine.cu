@@ -4,10 +4,10 @@
 // (JM/lencod/src/me_fullsearch.c:186-289) with computeSATD (me_distortion.c:745-825,
 // HadamardSAD4x4 :175-258) or computeSAD (:349-426) as computePredHPel/QPel.
 //
-// One CTA per (MB, ref).  A thread owns one 4x4 tile of the macroblock and one candidate index
+// One warp per (MB, ref).  A lane-job is one 4x4 tile of the macroblock and one candidate index
 // (16 tiles x 9 half-pel, then 8 quarter-pel candidates) and walks the 7 block types whose partition
 // contains the tile; partitions with equal motion vectors ask for the same reference tile, which is
-// then computed once.  The thread loads the 4x4 reference tile from the quarter-pel plane
+// then computed once.  The lane loads the 4x4 reference tile from the quarter-pel plane
 // [y&3][x&3] with the reference's own tile-origin clamp (UMVLine4X, refbuf.h:22-26), forms the
 // difference against the current MB in shared memory, runs the 4x4 Hadamard in registers and
 // adds (satd+1)>>1 into each partition's candidate accumulator.  41 threads then take the lexicographic (cost, position) minimum in
@@ -18,11 +18,17 @@
 
 namespace b2 {
 
-constexpr int SP_NT = 160;     // 144 = 16 tiles x 9 candidates working threads
 constexpr long long DMAX = ((long long)0x7fffffff) << 5;
 
 // spiral positions 0..8 (x,y) in units of the step (mv_search.c:406-442 with l = 1)
 __constant__ signed char c_sp9[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};
+
+// spiral position c (0..80) -> (x, y); the first nine come from packed 2-bit tables (the hot case)
+__device__ __forceinline__ void sp_xy(int c, int *x, int *y)
+{
+  if (c < 9) { *x = (int)((0x22215u >> (2 * c)) & 3u) - 1; *y = (int)((0x29421u >> (2 * c)) & 3u) - 1; }
+  else spiral_xy(c, x, y);
+}
 
 __device__ __forceinline__ int hadamard4x4_abs(const int d[16])
 {
@@ -77,32 +83,40 @@ __device__ __forceinline__ int tile_distortion(const uint8_t *cur, int tx, int t
   return v;
 }
 
-__global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
+// One WARP per (MB, ref) item: nothing in the refinement of an item needs more than warp-level synchronisation,
+// and CTA barriers between its short phases were the dominant stall.  NC = candidates per stage (9; 81 for
+// full_sub_pel_motion_estimation); SP_WPC warps (items) per CTA.
+template <int NC>
+struct SpWarp {
+  alignas(16) uint8_t cur[256];
+  int dist[NPART][NC];
+  short mv[NPART][2], prd[NPART][2];
+  long long mincost[NPART];
+};
+
+template <int NC, int WPC>
+__global__ void __launch_bounds__(32 * WPC) k_subpel_refine(const SubArgs a)
 {
-  // Thread (k, c) = 4x4 tile k of the macroblock, candidate index c.  The seven partitions (one per block type)
-  // that contain tile k usually carry the same motion vector and then ask for the SAME reference tile: the thread
+  // Lane-job (k, c) = 4x4 tile k of the macroblock, candidate index c.  The seven partitions (one per block type)
+  // that contain tile k usually carry the same motion vector and then ask for the SAME reference tile: the lane
   // walks the block types, computes a tile's distortion only when its (plane, x, y) differs from the ones it has
   // already computed, and adds the value to each partition's candidate accumulator.
-  __shared__ __align__(16) uint8_t cur[256];
-  __shared__ int dist[NPART][81];             // [p][candidate]; 9 used by the half/quarter stages, 81 by the full mode
-  __shared__ short mv[NPART][2], prd[NPART][2];
-  __shared__ long long mincost[NPART];
-  const int tid = threadIdx.x;
-  const int k = tid / 9, c0 = tid - k * 9;             // tid < 144
-  const int tx = (k & 3) * 4, ty = (k >> 2) * 4;
-  for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+  __shared__ SpWarp<NC> W[WPC];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  SpWarp<NC> &S = W[w];
+  for (int item = blockIdx.x * WPC + w; item < a.nitems; item += gridDim.x * WPC) {
     const int mb = a.mb_first + item / a.refs_per_mb, ref = a.ref_first + item % a.refs_per_mb;
     const int mbx = mb % a.mbw, mby = mb / a.mbw;
     const size_t base = (a.abs_index ? ((size_t)mb * a.nrefs + ref) : (size_t)item) * NPART;
     const uint8_t *planes = a.planes + (size_t)ref * 16 * a.plane_size;
-    __syncthreads();
-    if (tid < 64) reinterpret_cast<uint32_t *>(cur)[tid] =
-        *reinterpret_cast<const uint32_t *>(a.cur + (size_t)(mby * 16 + (tid >> 2)) * a.cur_pitch + mbx * 16 + (tid & 3) * 4);
-    if (tid < NPART) {
-      mv[tid][0] = a.mv_int[(base + tid) * 2]; mv[tid][1] = a.mv_int[(base + tid) * 2 + 1];
-      prd[tid][0] = a.pred[(base + tid) * 2];  prd[tid][1] = a.pred[(base + tid) * 2 + 1];
+    __syncwarp();
+    for (int t = lane; t < 64; t += 32) reinterpret_cast<uint32_t *>(S.cur)[t] =
+        *reinterpret_cast<const uint32_t *>(a.cur + (size_t)(mby * 16 + (t >> 2)) * a.cur_pitch + mbx * 16 + (t & 3) * 4);
+    for (int p = lane; p < NPART; p += 32) {
+      S.mv[p][0] = a.mv_int[(base + p) * 2]; S.mv[p][1] = a.mv_int[(base + p) * 2 + 1];
+      S.prd[p][0] = a.pred[(base + p) * 2];  S.prd[p][1] = a.pred[(base + p) * 2 + 1];
       // BlockMotionSearch resets the bound when the metric changes between levels (mv_search.c:971-974)
-      mincost[tid] = a.use_bound ? a.cost_int[base + tid] : DMAX;
+      S.mincost[p] = a.use_bound ? a.cost_int[base + p] : DMAX;
     }
     const int nstage = a.full81 ? 1 : 2;
     for (int stage = 0; stage < nstage; stage++) {
@@ -113,20 +127,21 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
       const int first = a.full81 ? 0 : (stage ? a.start_qp : a.start_hp);
       const int lam = (stage || a.full81) ? a.lambda_q : a.lambda_h;
       const int ncand = a.full81 ? 81 : 9;
-      __syncthreads();
-      for (int i = tid; i < NPART * 81; i += SP_NT) (&dist[0][0])[i] = 0;
-      __syncthreads();
-      for (int c = c0; c < ncand; c += 9) {
-      if (tid < 144 && c >= first) {
+      for (int i = lane; i < NPART * NC; i += 32) (&S.dist[0][0])[i] = 0;
+      __syncwarp();
+      for (int job = lane; job < 16 * ncand; job += 32) {
+        const int k = job / ncand, c = job - k * ncand;
+        if (c < first) continue;
+        const int tx = (k & 3) * 4, ty = (k >> 2) * 4;
         uint32_t keys[7]; int vals[7];
-        int spx, spy; spiral_xy(c, &spx, &spy);
+        int spx, spy; sp_xy(c, &spx, &spy);
         const int sx = step * spx, sy = step * spy;
 #pragma unroll
         for (int bti = 0; bti < 7; bti++) {
           keys[bti] = 0xffffffffu; vals[bti] = 0;
           const int p = part_of_tile(bti, tx, ty);
           if (!((a.part_mask >> p) & 1ull)) continue;
-          const uint32_t mvw = *reinterpret_cast<const uint32_t *>(&mv[p][0]);
+          const uint32_t mvw = *reinterpret_cast<const uint32_t *>(&S.mv[p][0]);
           int v = -1;
           uint32_t kk;
           if (metric == 2) {          // SATD: per-tile origin clamp (me_distortion.c:771): the tile depends on the vector only
@@ -134,57 +149,59 @@ __global__ void __launch_bounds__(SP_NT) k_subpel_refine(const SubArgs a)
 #pragma unroll
             for (int b2 = 0; b2 < bti; b2++) if (keys[b2] == kk) v = vals[b2];
             if (v < 0) {
-              const int qx = 4 * (mbx * 16 + tx) + mv[p][0] + sx, qy = 4 * (mby * 16 + ty) + mv[p][1] + sy;
+              const int qx = 4 * (mbx * 16 + tx) + S.mv[p][0] + sx, qy = 4 * (mby * 16 + ty) + S.mv[p][1] + sy;
               const int pl = (qy & 3) * 4 + (qx & 3);
               const int ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX, oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY;
-              v = tile_distortion(cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, 2);
+              v = tile_distortion(S.cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, 2);
             }
           } else {                    // SAD / SSE: block origin clamp (me_distortion.c:367, :1205): key = the tile actually read
             const PartGeom gm = part_geom(p);
-            const int qx = 4 * (mbx * 16 + gm.ox) + mv[p][0] + sx, qy = 4 * (mby * 16 + gm.oy) + mv[p][1] + sy;
+            const int qx = 4 * (mbx * 16 + gm.ox) + S.mv[p][0] + sx, qy = 4 * (mby * 16 + gm.oy) + S.mv[p][1] + sy;
             const int pl = (qy & 3) * 4 + (qx & 3);
             const int ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX + (tx - gm.ox), oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY + (ty - gm.oy);
             kk = (uint32_t)pl | ((uint32_t)ox << 4) | ((uint32_t)oy << 18);     // ox, oy < 2^14
 #pragma unroll
             for (int b2 = 0; b2 < bti; b2++) if (keys[b2] == kk) v = vals[b2];
-            if (v < 0) v = tile_distortion(cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, metric);
+            if (v < 0) v = tile_distortion(S.cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, metric);
           }
           keys[bti] = kk; vals[bti] = v;
-          atomicAdd(&dist[p][c], v);
+          atomicAdd(&S.dist[p][c], v);
         }
       }
-      }
-      __syncthreads();
-      if (tid < NPART && ((a.part_mask >> tid) & 1ull)) {
-        const int p = tid;
-        long long best = mincost[p]; int best_pos = 0;
+      __syncwarp();
+      for (int p = lane; p < NPART; p += 32) {
+        if (!((a.part_mask >> p) & 1ull)) continue;
+        long long best = S.mincost[p]; int best_pos = 0;
         for (int cc = first; cc < ncand; cc++) {
-          int spx, spy; spiral_xy(cc, &spx, &spy);
-          const int mvx = mv[p][0] + step * spx, mvy = mv[p][1] + step * spy;
-          const long long cost = (long long)lam * (mvbits(mvx - prd[p][0]) + mvbits(mvy - prd[p][1])) + ((long long)dist[p][cc] << 5);
+          int spx, spy; sp_xy(cc, &spx, &spy);
+          const int mvx = S.mv[p][0] + step * spx, mvy = S.mv[p][1] + step * spy;
+          const long long cost = (long long)lam * (mvbits(mvx - S.prd[p][0]) + mvbits(mvy - S.prd[p][1])) + ((long long)S.dist[p][cc] << 5);
           if (cost < best) { best = cost; best_pos = cc; }
         }
-        { int spx, spy; spiral_xy(best_pos, &spx, &spy);
-          mv[p][0] = (short)(mv[p][0] + step * spx); mv[p][1] = (short)(mv[p][1] + step * spy); }
+        { int spx, spy; sp_xy(best_pos, &spx, &spy);
+          S.mv[p][0] = (short)(S.mv[p][0] + step * spx); S.mv[p][1] = (short)(S.mv[p][1] + step * spy); }
         if (stage == 0 && !a.full81 && !a.start_qp) best = DMAX;     // me_fullsearch.c:252-253
-        mincost[p] = best;
+        S.mincost[p] = best;
       }
+      __syncwarp();
     }
-    __syncthreads();
-    if (tid < NPART && ((a.part_mask >> tid) & 1ull)) {
-      a.mv_sub[(base + tid) * 2] = mv[tid][0]; a.mv_sub[(base + tid) * 2 + 1] = mv[tid][1];
-      a.cost_sub[base + tid] = mincost[tid];
+    for (int p = lane; p < NPART; p += 32) {
+      if (!((a.part_mask >> p) & 1ull)) continue;
+      a.mv_sub[(base + p) * 2] = S.mv[p][0]; a.mv_sub[(base + p) * 2 + 1] = S.mv[p][1];
+      a.cost_sub[base + p] = S.mincost[p];
     }
   }
 }
 
 cudaError_t launch_subpel_refine(const SubArgs &a, cudaStream_t s)
 {
-  k_subpel_refine<<<a.nitems, SP_NT, 0, s>>>(a);
+  if (a.full81) k_subpel_refine<81, 2><<<(a.nitems + 1) / 2, 64, 0, s>>>(a);
+  else k_subpel_refine<9, 4><<<(a.nitems + 3) / 4, 128, 0, s>>>(a);
   return cudaGetLastError();
 }
 
 }  // namespace b2
+
 
 // ---- distortion4x4/8x8{SAD,SSE,SATD} on precomputed difference blocks (me_distortion.c:38-134) ----------------
 // One thread per block; HBM-bound (32 or 128 bytes in, 8 out).
