@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (k + 1 < NCH) fp_tmem_ld32_nowait(tl + ts * FP_TN + (ch + FP_EPI_GROUPS) * FP_CHUNK, vbuf[(k + 1) & 1]);   // next chunk in flight
           fp_tmem_st32_const(tl + ts * FP_TN + ch * FP_CHUNK, FP_MAGIC);   // re-arm the accumulator
-          if (a.probe) continue;
+          if (a.probe == 1) continue;
           float g[32];
 #pragma unroll
           for (int j4 = 0; j4 < 8; j4++) {
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
           }
           const int mxa = max(__vimax3_s32(mx[0], mx[1], mx[2]), mx[3]), mna = min(__vimin3_s32(mn[0], mn[1], mn[2]), mn[3]);
           const float X = fmaxf(__int_as_float(mxa) - 8388608.0f, 8388608.0f - __int_as_float(mna)) + 0.5f;
-          const bool pass = rvalid && (X * X) * wp[ch] * 1.00001f >= Tf;
+          const bool pass = rvalid && a.probe != 2 && (X * X) * wp[ch] * 1.00001f >= Tf;     // probe 2: filter arithmetic only
           n_chunk++;
           if (__any_sync(0xffffffffu, pass)) {
             // ---- re-examine the 32 columns.  Phase 1 (registers, branch-free): mask of the columns whose own
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
           }
         }
         // ---- exchange the row thresholds with the other epilogue group (stale by at most one tile: conservative) ----
-        if (FP_EPI_GROUPS > 1 && !a.probe) {
+        if (FP_EPI_GROUPS > 1 && a.probe != 1) {
           S->shareT[grp][rit] = Tf;
           Tf = fmaxf(Tf, *reinterpret_cast<volatile float *>(&S->shareT[grp ^ 1][rit]));
         }
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
         __syncwarp();
         if (lane == 0) { fp_mbar_arrive(&S->t_empty[ts]); fp_mbar_arrive(&S->c_empty[cs]); }
       }
-      if (!a.probe) {
+      if (a.probe != 1) {
         // ---- merge the groups' partial results per row (first maximum in pool-index order) ----
         if (grp > 0) { S->mG[rit] = bestG; S->mIdx[rit] = bestIdx; S->mAq[rit] = (short)bestAq; }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * FP_EPI_WARPS) : "memory");
@@ -699,7 +699,8 @@ extern "C" int b2fp_probe(b2fp_ctx *c, double *ms)
   if (!c || !ms) return B2ME_EINVAL;
   FP_CHECK(c, cudaSetDevice(c->device));
   const double t0 = c->t_ms; const long long n0 = c->t_n;
-  int r = fp_launch(c, 1, c->d_dom, c->d_iso, c->d_aq, c->d_beta, (int64_t *)c->d_err, c->stream, 1);
+  const char *e = getenv("B2FP_PROBE");            // 2: MMAs + the filter arithmetic of the epilogue, no re-examination (development)
+  int r = fp_launch(c, e && e[0] == '2' ? 2 : 1, c->d_dom, c->d_iso, c->d_aq, c->d_beta, (int64_t *)c->d_err, c->stream, 1);
   if (r) return r;
   *ms = c->t_ms - t0; c->t_ms = t0; c->t_n = n0;
   return B2ME_OK;
