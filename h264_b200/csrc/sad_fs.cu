@@ -633,6 +633,10 @@ __device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWa
   }
   __syncwarp();
   if (lane == 0) {
+    // seqlock: the negative epoch marks "being re-armed" BEFORE any field changes, so that a worker that still holds
+    // a stale claim on the previous epoch's (exhausted) counter cannot pair it with the new unit's ntask / slot
+    *reinterpret_cast<volatile int *>(&C.ready_epoch) = -ep;
+    __threadfence_block();
     C.slot = slot_index; C.ntask = S.ntask; C.done = 0; C.epoch = ep;
     __threadfence_block();
     *reinterpret_cast<volatile int *>(&C.ready_epoch) = ep;
@@ -740,14 +744,17 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
       if (lane == 0) c = atomicAdd(&C.next, FS_CLAIM);
       c = __shfl_sync(0xffffffffu, c, 0);
       const int ep = *reinterpret_cast<volatile int *>(&C.ready_epoch);
-      if ((c >> 20) != (ep & 0x7ff)) continue;       // counter not (yet) armed for the published epoch
+      if (ep <= 0 || (c >> 20) != (ep & 0x7ff)) continue;       // counter not (yet) armed for the published epoch
       FS_FENCE();
       const int t0 = c & 0xfffff;
       const int ntask = *reinterpret_cast<volatile int *>(&C.ntask);
+      const int slot = *reinterpret_cast<volatile int *>(&C.slot);
+      FS_FENCE();
+      if (*reinterpret_cast<volatile int *>(&C.ready_epoch) != ep) continue;   // re-armed meanwhile: ntask / slot may be the next unit's
       if (t0 >= ntask) { if (b) ex1 = ep; else ex0 = ep; continue; }
       pref = b;
       any = true;
-      SLOT &S = SS[*reinterpret_cast<volatile int *>(&C.slot)];
+      SLOT &S = SS[slot];
       uint8_t *win = smem + b * G.slot_bytes;
       const int g = S.g;
       const int t1 = min(t0 + FS_CLAIM, ntask);
