@@ -153,6 +153,11 @@ class Searcher:
                                              C.byref(params), _dp(mv_int), _dp(cost_int), _dp(mv_sub), _dp(cost_sub),
                                              _vp(stream)), "b2me_search_mbs_dev")
 
+    def mc_luma_dev(self, mb_mode, b8mode, ref8, mv, orig_blk, pred_blk, stream=0):
+        """torch CUDA tensors: luma_prediction (list 0) of the picture into the b2tq block layout"""
+        self._chk(self.L.b2me_mc_luma_dev(self.h, _dp(mb_mode), _dp(b8mode), _dp(ref8), _dp(mv), _dp(orig_blk), _dp(pred_blk), _vp(stream)),
+                  "b2me_mc_luma_dev")
+
     def block_search(self, pos_x, pos_y, blocktype, ref, pred_mv, center_mv, params, search_range):
         pm = (C.c_int16 * 2)(int(pred_mv[0]), int(pred_mv[1]))
         cm = (C.c_int16 * 2)(int(center_mv[0]), int(center_mv[1]))
@@ -343,6 +348,16 @@ class PoolSearcher:
 
     def launch_count(self):
         return self.L.b2fp_launch_count(self.h)
+
+
+def tq_dev(params, orig, pred, n, level, run, recon, cost, nonzero, stream=0):
+    """b2tq_4x4_dev / b2tq_8x8_dev on torch CUDA tensors (orig, pred [nblk][n*n] u8; outputs preallocated)."""
+    L = lib()
+    L.b2tq_last_error.restype = C.c_char_p
+    f = L.b2tq_4x4_dev if n == 4 else L.b2tq_8x8_dev
+    r = f(C.byref(params), C.c_int(orig.shape[0]), _dp(orig), _dp(pred), _dp(level), _dp(run), _dp(recon), _dp(cost), _dp(nonzero), _vp(stream))
+    if r:
+        raise B2Error(f"b2tq_{n}x{n}_dev failed ({r}): {L.b2tq_last_error().decode()}")
 
 
 def distortion_blocks(kind, n, diff, device=0):

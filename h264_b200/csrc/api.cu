@@ -440,6 +440,21 @@ extern "C" int b2me_block_subpel(b2me_ctx *c, int pos_x, int pos_y, int blocktyp
   return B2ME_OK;
 }
 
+// luma_prediction (list 0) of the whole picture from a search result array; device pointers
+extern "C" int b2me_mc_luma_dev(b2me_ctx *c, const uint8_t *mb_mode, const uint8_t *b8mode, const int8_t *ref8, const int16_t *mv,
+                                uint8_t *orig_blk, uint8_t *pred_blk, void *stream)
+{
+  if (!c || !mb_mode || !b8mode || !ref8 || !mv || !orig_blk || !pred_blk) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  McArgs m;
+  m.cur = c->d_cur; m.cur_pitch = c->W; m.planes = c->d_planes; m.plane_size = c->plane_size;
+  m.W = c->W; m.H = c->H; m.Wp = c->Wp; m.mbw = c->mbw; m.nmb = c->nmb; m.nrefs = c->nrefs;
+  m.mb_mode = mb_mode; m.b8mode = b8mode; m.ref8 = ref8; m.mv = mv; m.orig_blk = orig_blk; m.pred_blk = pred_blk;
+  B2_CUDA_CHECK(c, launch_mc_luma(m, (cudaStream_t)stream));
+  c->launches++;
+  return B2ME_OK;
+}
+
 // distortion4x4/8x8{SAD,SSE,SATD} of the mode decision (me_distortion.c:38-134) for nblk difference blocks
 extern "C" int b2me_distortion_blocks_dev(int kind, int n, int nblk, const int16_t *diff_dev, int64_t *out_dev, void *stream)
 {

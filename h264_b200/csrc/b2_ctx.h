@@ -89,6 +89,14 @@ struct SubArgs {
   unsigned long long part_mask;
 };
 
+struct McArgs {
+  const uint8_t *cur; int cur_pitch;
+  const uint8_t *planes; size_t plane_size;
+  int W, H, Wp, mbw, nmb, nrefs;
+  const uint8_t *mb_mode, *b8mode; const int8_t *ref8; const int16_t *mv;
+  uint8_t *orig_blk, *pred_blk;
+};
+cudaError_t launch_mc_luma(const McArgs &a, cudaStream_t s);
 cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, cudaStream_t s);
 cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, cudaStream_t s, int *smem_bytes_out);
 FsGeom fs_geom_host(int R);

@@ -263,3 +263,55 @@ cudaError_t launch_distortion(int kind, int n, int nblk, const int16_t *diff, lo
 }
 
 }  // namespace b2
+
+
+// ---- motion-compensated luma prediction of list 0 (luma_prediction / OneComponentLumaPrediction,
+//      JM/lencod/src/mc_prediction.c:117-236), SURVEY 8(f)-1: keeps the vectors on the device between the search and
+//      the transform.  One thread per 4x4 block: the block's partition (from the MB mode / 8x8 sub-modes), its
+//      vector, UMVLine4X's whole-partition origin clamp, then 4 rows of 4 samples of quarter-pel plane [y&3][x&3];
+//      writes prediction and original in the block-packed layout b2tq_4x4 takes.  HBM/L2-bound.
+namespace b2 {
+
+__global__ void __launch_bounds__(256) k_mc_luma(const McArgs a)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.nmb * 16) return;
+  const int m = t >> 4, k = t & 15, bx = k & 3, by = k >> 2, qd = (by >> 1) * 2 + (bx >> 1);
+  const int mode = a.mb_mode[m], r = a.ref8[m * 4 + qd];
+  int p, ox, oy;
+  if (mode == 1) { p = 0; ox = 0; oy = 0; }
+  else if (mode == 2) { p = 1 + (by >> 1); ox = 0; oy = 8 * (by >> 1); }
+  else if (mode == 3) { p = 3 + (bx >> 1); ox = 8 * (bx >> 1); oy = 0; }
+  else {
+    const int sub = a.b8mode[m * 4 + qd];
+    if (sub == 4) { p = 5 + qd; ox = 8 * (bx >> 1); oy = 8 * (by >> 1); }
+    else if (sub == 5) { p = 9 + by * 2 + (bx >> 1); ox = 8 * (bx >> 1); oy = 4 * by; }
+    else if (sub == 6) { p = 17 + (by >> 1) * 4 + bx; ox = 4 * bx; oy = 8 * (by >> 1); }
+    else { p = 25 + by * 4 + bx; ox = 4 * bx; oy = 4 * by; }
+  }
+  const int mbx = m % a.mbw, mby = m / a.mbw;
+  const int16_t *v = a.mv + (((size_t)m * a.nrefs + r) * NPART + p) * 2;
+  const int qx = 4 * (mbx * 16 + ox) + v[0], qy = 4 * (mby * 16 + oy) + v[1];
+  const int pl = (qy & 3) * 4 + (qx & 3);
+  const int x = iclamp(qx >> 2, -PADX, a.W + 15) + PADX + (4 * bx - ox), y = iclamp(qy >> 2, -PADY, a.H + 3) + PADY + (4 * by - oy);
+  const uint8_t *rp = a.planes + ((size_t)r * 16 + pl) * a.plane_size + (size_t)y * a.Wp + x;
+  const int al = (int)(reinterpret_cast<size_t>(rp) & 3);
+  uint32_t pw[4], cw[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(rp + (size_t)i * a.Wp - al);
+    const uint32_t lo = w[0], hi = al ? w[1] : 0u;
+    pw[i] = al ? __funnelshift_r(lo, hi, 8 * al) : lo;
+    cw[i] = *reinterpret_cast<const uint32_t *>(a.cur + (size_t)(mby * 16 + 4 * by + i) * a.cur_pitch + mbx * 16 + 4 * bx);
+  }
+  reinterpret_cast<uint4 *>(a.pred_blk)[t] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+  reinterpret_cast<uint4 *>(a.orig_blk)[t] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+}
+
+cudaError_t launch_mc_luma(const McArgs &a, cudaStream_t s)
+{
+  k_mc_luma<<<(a.nmb * 16 + 255) / 256, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace b2

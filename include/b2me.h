@@ -125,6 +125,17 @@ int b2me_block_subpel(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int re
                       const int16_t pred_mv[2], const int16_t mv_in[2], const b2me_search_params *params,
                       int64_t min_mcost, int16_t mv_out[2], int64_t *cost_out);
 
+/* ---- motion-compensated prediction (keeps the vectors on the device between search and transform) ---- */
+/* luma_prediction with p_dir == 0 (list 0), no weighting (JM/lencod/src/mc_prediction.c:144-236;
+ * OneComponentLumaPrediction :117-136) for every macroblock of the picture, from a search result array.
+ *   mb_mode [nmb] uint8: 1 16x16, 2 16x8, 3 8x16, 8 P8x8;   b8mode [nmb][4] uint8: 4 8x8, 5 8x4, 6 4x8, 7 4x4
+ *   ref8 [nmb][4] int8: reference slot of each 8x8 quadrant;  mv [nmb][nrefs][41][2]: mv_sub (or mv_int) of the search
+ *   orig_blk, pred_blk [nmb*16][16] uint8: the sixteen 4x4 blocks of every MB in raster order, each raster --
+ *   exactly the `orig` / `pred` arguments of b2tq_4x4_dev, so search -> prediction -> transform/quant chain on the
+ *   device.  All pointers are device pointers. */
+int b2me_mc_luma_dev(b2me_ctx *ctx, const uint8_t *mb_mode, const uint8_t *b8mode, const int8_t *ref8, const int16_t *mv,
+                     uint8_t *orig_blk, uint8_t *pred_blk, void *stream);
+
 /* ---- mode-decision distortions on precomputed difference blocks ------------------------ */
 /* distortion4x4/8x8{SAD,SSE,SATD} (JM/lencod/src/me_distortion.c:38-134; p_Vid->distortion4x4/8x8 as bound by
  * select_distortion :136-158): diff [nblk][n*n] int16 raster, n = 4 or 8, kind 0 SAD, 1 SSE, 2 SATD

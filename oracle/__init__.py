@@ -126,6 +126,16 @@ class OrcFrame:
         """explicit WP of reference `ref` (computeSADWP/SATDWP/SSEWP); call once, after construction"""
         self.L.orc_frame_set_weights(self.h, C.c_int(ref), C.c_int(weight), C.c_int(offset), C.c_int(log_denom))
 
+    def mc_luma(self, mb_mode, b8mode, ref8, mv):
+        """luma_prediction (list 0) of the whole picture from a search result array: (orig_blk, pred_blk) [nmb*16][16]"""
+        nmb = (self.W // 16) * (self.H // 16)
+        mb_mode = np.ascontiguousarray(mb_mode, np.uint8); b8mode = np.ascontiguousarray(b8mode, np.uint8)
+        ref8 = np.ascontiguousarray(ref8, np.int8); mv = np.ascontiguousarray(mv, np.int16)
+        assert mb_mode.shape == (nmb,) and b8mode.shape == (nmb, 4) and ref8.shape == (nmb, 4) and mv.shape == (nmb, self.nrefs, 41, 2)
+        orig = np.zeros((nmb * 16, 16), np.uint8); pred = np.zeros((nmb * 16, 16), np.uint8)
+        self.L.orc_mc_luma(self.h, _ptr(mb_mode), _ptr(b8mode), _ptr(ref8), _ptr(mv), _ptr(orig), _ptr(pred))
+        return orig, pred
+
     def planes(self, r):
         Hp, Wp = self.H + 2 * PAD_Y, self.W + 2 * PAD_X
         p = self.L.orc_frame_planes(self.h, C.c_int(r))

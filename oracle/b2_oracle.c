@@ -441,3 +441,49 @@ int64_t orc_call_sub_pel(void *h, int ref, int pos_x, int pos_y, int blocktype, 
   return orc_sub_pel((OrcFrame *)h, ref, pos_x, pos_y, ORC_BS[blocktype][0], ORC_BS[blocktype][1], pred_mv,
                      mv_inout, min_mcost, lam, start_hp, start_qp, metric_h, metric_q, 0);
 }
+
+
+/* ------------------------------------------------------------------------------------
+ * Motion-compensated luma prediction of list 0: luma_prediction with p_dir == 0, no weighting
+ * (JM/lencod/src/mc_prediction.c:144-236) = OneComponentLumaPrediction (:117-136): block_size_y rows of block_size_x
+ * samples copied from UMVLine4X(ref, 4*(pix_y+block_y) + mv_y, 4*(pix_x+block_x) + mv_x) -- the same plane address
+ * (and whole-block origin clamp) the distortions read, which the SAD/SATD tests pin against the reference.
+ *   mb_mode [nmb]: 1 16x16, 2 16x8, 3 8x16, 8 P8x8;  b8mode [nmb][4]: 4 8x8, 5 8x4, 6 4x8, 7 4x4 (per 8x8 quadrant)
+ *   ref8 [nmb][4]: reference of each quadrant;  mv [nmb][nrefs][41][2] quarter-pel (a search result array)
+ *   orig_blk / pred_blk [nmb*16][16]: the sixteen 4x4 blocks of every MB in raster order, each raster (b2tq layout)
+ * ---------------------------------------------------------------------------------- */
+static void orc_block_partition(int mode, const uint8_t *b8, int bx, int by, int *p, int *ox, int *oy)
+{
+  const int qd = (by >> 1) * 2 + (bx >> 1);
+  if (mode == 1) { *p = 0; *ox = 0; *oy = 0; }
+  else if (mode == 2) { *p = 1 + (by >> 1); *ox = 0; *oy = 8 * (by >> 1); }
+  else if (mode == 3) { *p = 3 + (bx >> 1); *ox = 8 * (bx >> 1); *oy = 0; }
+  else switch (b8[qd]) {
+    case 4:  *p = 5 + qd; *ox = 8 * (bx >> 1); *oy = 8 * (by >> 1); break;
+    case 5:  *p = 9 + by * 2 + (bx >> 1); *ox = 8 * (bx >> 1); *oy = 4 * by; break;
+    case 6:  *p = 17 + (by >> 1) * 4 + bx; *ox = 4 * bx; *oy = 8 * (by >> 1); break;
+    default: *p = 25 + by * 4 + bx; *ox = 4 * bx; *oy = 4 * by; break;
+  }
+}
+void orc_mc_luma(void *h, const uint8_t *mb_mode, const uint8_t *b8mode, const int8_t *ref8, const int16_t *mv,
+                 uint8_t *orig_blk, uint8_t *pred_blk)
+{
+  OrcFrame *f = (OrcFrame *)h;
+  const int mbw = f->W / 16, nmb = mbw * (f->H / 16), Wp = f->W + 2 * PAD_X;
+  int m, k, i, j;
+  for (m = 0; m < nmb; m++)
+    for (k = 0; k < 16; k++) {
+      const int bx = k & 3, by = k >> 2, qd = (by >> 1) * 2 + (bx >> 1), r = ref8[m * 4 + qd];
+      int p, ox, oy;
+      const int16_t *v;
+      const uint8_t *ref, *pl = orc_frame_planes(h, r);
+      orc_block_partition(mb_mode[m], b8mode + m * 4, bx, by, &p, &ox, &oy);
+      v = mv + (((size_t)m * f->nrefs + r) * 41 + p) * 2;
+      ref = orc_umv_line4x(pl, f->W, f->H, 4 * ((m / mbw) * 16 + oy) + v[1], 4 * ((m % mbw) * 16 + ox) + v[0]);
+      for (i = 0; i < 4; i++)
+        for (j = 0; j < 4; j++) {
+          pred_blk[((size_t)m * 16 + k) * 16 + i * 4 + j] = ref[(size_t)(4 * by - oy + i) * Wp + (4 * bx - ox + j)];
+          orig_blk[((size_t)m * 16 + k) * 16 + i * 4 + j] = f->cur[(size_t)((m / mbw) * 16 + 4 * by + i) * f->W + (m % mbw) * 16 + 4 * bx + j];
+        }
+    }
+}

@@ -1,0 +1,56 @@
+"""Search -> motion-compensated prediction -> transform/quant on the device: the vectors never leave
+the GPU between the stages; every stage's output is compared with the oracle's chain."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from h264_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_search_mc_tq_chain_matches_oracle():
+    W, H, R, NR = 96, 64, 12, 2
+    fr = synth.luma_sequence(W, H, NR + 1, seed=31)
+    cur, refs = fr[NR], fr[[1, 0]]
+    nmb = (W // 16) * (H // 16)
+    pred, cen = synth.predictors(W, H, NR, seed=3, spread=4, rmax=30)          # some vectors reach far outside the picture
+    rng = np.random.default_rng(4)
+    mb_mode = rng.choice([1, 2, 3, 8], nmb).astype(np.uint8)
+    b8mode = rng.integers(4, 8, (nmb, 4)).astype(np.uint8)
+    ref8 = rng.integers(0, NR, (nmb, 4)).astype(np.int8)
+    ref8[mb_mode == 1] = ref8[mb_mode == 1][:, :1]                               # one reference per partition
+    ref8[mb_mode == 2, 1] = ref8[mb_mode == 2, 0]; ref8[mb_mode == 2, 3] = ref8[mb_mode == 2, 2]
+    ref8[mb_mode == 3, 2] = ref8[mb_mode == 3, 0]; ref8[mb_mode == 3, 3] = ref8[mb_mode == 3, 1]
+    lam = (140, 100, 100)
+    # ---- GPU chain, device pointers only ----
+    dev = torch.device("cuda", 0)
+    s = api.Searcher(W, H, NR, R)
+    s.set_cur(cur)
+    for r in range(NR):
+        s.set_ref(r, refs[r])
+    t = lambda a: torch.from_numpy(a).to(dev)
+    d_mvi = torch.zeros((nmb, NR, 41, 2), dtype=torch.int16, device=dev); d_mvs = torch.zeros_like(d_mvi)
+    d_ci = torch.zeros((nmb, NR, 41), dtype=torch.int64, device=dev); d_cs = torch.zeros_like(d_ci)
+    s.search_frame_dev(t(pred), t(cen), api.make_params(lam), d_mvi, d_ci, d_mvs, d_cs)
+    d_orig = torch.zeros((nmb * 16, 16), dtype=torch.uint8, device=dev); d_pred = torch.zeros_like(d_orig)
+    s.mc_luma_dev(t(mb_mode), t(b8mode), t(ref8), d_mvs, d_orig, d_pred)
+    p = api.tq_default_params(4, 28, 0)
+    d_level = torch.zeros((nmb * 16, 16), dtype=torch.int16, device=dev); d_run = torch.zeros((nmb * 16, 16), dtype=torch.uint8, device=dev)
+    d_recon = torch.zeros_like(d_orig); d_cost = torch.zeros(nmb * 16, dtype=torch.int32, device=dev); d_nz = torch.zeros(nmb * 16, dtype=torch.uint8, device=dev)
+    api.tq_dev(p, d_orig, d_pred, 4, d_level, d_run, d_recon, d_cost, d_nz)
+    torch.cuda.synchronize()
+    # ---- oracle chain ----
+    of = oracle.OrcFrame(cur, refs, R)
+    exp = of.search_frame(pred, cen, lam)
+    assert (d_mvs.cpu().numpy() == exp[2]).all()
+    o_orig, o_pred = of.mc_luma(mb_mode, b8mode, ref8, exp[2])
+    assert (d_orig.cpu().numpy() == o_orig).all()
+    assert (d_pred.cpu().numpy() == o_pred).all()
+    q = oracle.tq_params(api.tq_params_table(p, 4), 28, cavlc=1)
+    e_level, e_run, e_recon, e_cost, e_nz = oracle.tq(q, o_orig, o_pred, 4)
+    for g, e, n in zip((d_level, d_run, d_recon, d_cost, d_nz), (e_level, e_run, e_recon, e_cost, e_nz), ("level", "run", "recon", "cost", "nz")):
+        assert (g.cpu().numpy() == e).all(), n
+    # the prediction is a good one: the reconstruction is close to the original
+    assert np.abs(d_recon.cpu().numpy().astype(int) - o_orig.astype(int)).mean() < 8.0

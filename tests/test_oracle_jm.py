@@ -156,3 +156,23 @@ def test_weighted_prediction_restatement_matches_reference(metric):
         assert (a == b).all(), (n, int((a != b).sum()))
     plain = oracle.OrcFrame(cur, refs, R).search_frame(pred, cen, lam, metric_h=metric[1], metric_q=metric[2])
     assert (plain[1] != got[1]).any()                                     # the weights really change the costs
+
+
+def test_mc_luma_restatement_is_the_distortions_block():
+    """orc_mc_luma reads through the same UMVLine4X address the pinned computeSAD does: SAD(orig, pred) of a
+    partition's prediction equals the search's own SAD at that vector."""
+    W, H, R, NR = 64, 48, 8, 1
+    fr = synth.luma_sequence(W, H, 2, seed=29)
+    cur, refs = fr[1], fr[[0]]
+    of = oracle.OrcFrame(cur, refs, R)
+    pred, cen = synth.predictors(W, H, NR, seed=3, spread=0, rmax=40)            # far vectors: clamped origins
+    mv_int, cost_int, _, _ = of.search_frame(pred, cen, (0, 0, 0), do_subpel=False)   # lambda 0: cost = SAD << 5
+    nmb = (W // 16) * (H // 16)
+    for mode, plist in ((1, [0]), (2, [1, 2]), (3, [3, 4])):
+        orig, prd = of.mc_luma(np.full(nmb, mode, np.uint8), np.full((nmb, 4), 4, np.uint8), np.zeros((nmb, 4), np.int8), mv_int)
+        sad4 = np.abs(orig.astype(int) - prd.astype(int)).sum(1).reshape(nmb, 16)      # per 4x4 block
+        for m in range(nmb):
+            for p in plist:
+                bt, ox, oy, w, h = oracle.partition_geometry()[p]
+                blocks = [by * 4 + bx for by in range(oy // 4, (oy + h) // 4) for bx in range(ox // 4, (ox + w) // 4)]
+                assert sad4[m, blocks].sum() << 5 == cost_int[m, 0, p], (mode, m, p)
