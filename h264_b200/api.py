@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2me.so")
+LIB_PATH = os.environ.get("B2ME_LIB") or os.path.join(_HERE, "libb2me.so")   # B2ME_LIB: development builds (tools/)
 NPART = 41
 DISTBLK_MAX = (2**31 - 1) << 5
 PAD_X, PAD_Y = 32, 20

@@ -61,6 +61,7 @@ struct FsArgs {
   int *errflag;
   int *work_counter;     // device int, zero at launch: next (MB, ref) item to hand out
   int flags;             // bit 0: stage every window with the clamped (non-TMA) path (debug, B2ME_FS_NOTMA=1)
+  int claim;             // tasks claimed per visit of a buffer's counter (amortises the claim / completion protocol)
   int one;               // 1 (a run-time constant the compiler cannot fold, see sad_fs.cu addmin2)
   unsigned long long *stats;   // optional: [0] exact re-evaluations, [1] window passes, [2] items
 };

@@ -55,12 +55,14 @@
 
 namespace b2 {
 
-constexpr int FS_K = 4;          // candidate rows per task (lock step): 4 = rolled fs_task4, 5 = fully unrolled fs_task
+#ifndef FS_KV
+#define FS_KV 4
+#endif
+constexpr int FS_K = FS_KV;         // candidate rows per task (lock step): 4 = rolled fs_task4, 5 = fully unrolled fs_task
 constexpr int FS_PRE = 0;        // radius of the exact pre-pass around the centres (initial bounds)
 constexpr int FS_SMAX = 7;       // partitions whose centres lie within a 7-pel box share one window pass
 constexpr int FS_BMAX = 12;      // a trailing column block of at most this width is walked row-major (type B)
 constexpr int FS_MCAP = 2047;    // cap of each half of the mv-cost lower bound (keeps packed sums in range)
-constexpr int FS_CLAIM = 3;      // tasks claimed per visit of the shared counter (amortises the claim / completion protocol)
 
 __host__ __device__ inline FsGeom fs_geom(int R)
 {
@@ -337,8 +339,13 @@ __device__ __forceinline__ uint32_t fs_task4(const SLOT &S, const uint8_t *wb, u
       if ((r & 3) == 3) {
         const int odd = r >> 2;                       // block row b = 2*bb + odd
         const uint32_t cx = ld_vol(&Cb[3 * odd]), cy = ld_vol(&Cb[3 * odd + 1]), ch = ld_vol(&Cb[3 * odd + 2]);
-        uint32_t cxv = 0, cyv = 0, ce = 0;
+        uint32_t cxv = 0, cyv = 0, ce = 0, ctb = 0, clr = 0, myj[K]; int c16 = 0;
         if (odd) { cxv = ld_vol(&S.Cw[12 + 3 * bb]); cyv = ld_vol(&S.Cw[13 + 3 * bb]); ce = ld_vol(&S.Cw[14 + 3 * bb]); }
+        if (odd && bb) {                              // loaded once per task, not once per candidate (the loads are volatile)
+          ctb = ld_vol(&S.Cw[18]); clr = ld_vol(&S.Cw[19]); c16 = *reinterpret_cast<const volatile int *>(&S.C16);
+#pragma unroll
+          for (int j = 0; j < K; j++) myj[j] = mys[j];
+        }
 #pragma unroll
         for (int j = 0; j < K; j++) {
 #pragma unroll
@@ -356,24 +363,140 @@ __device__ __forceinline__ uint32_t fs_task4(const SLOT &S, const uint8_t *wb, u
               rr = addmin2(XV, cxv, rr, one);
               rr = addmin2(YV, cyv, rr, one);
               rr = addmin2(E, ce, rr, one);
-              if (bb == 0) E0[q][j] = E;
-              else {
-                const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
-                const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
-                const uint32_t top = __dp2a_lo(E0[q][j], 0x0101u, 0u), bot = __dp2a_lo(E, 0x0101u, 0u);
-                const uint32_t TB = bot * 65536u + top, LR = add2(E0[q][j], E);
-                rr = addmin2(TB, ctb, rr, one);
-                rr = addmin2(LR, clr, rr, one);
-                const uint32_t m = (q ? mxb : mxa) + mys[j];
-                const int s = (int)(top + bot) + c16 + (int)m;
-                const uint32_t t = rr + m * 0x10001u;
-                if ((t & 0x80008000u) != 0u || s < 0) pass |= 1u << (q * K + j);
-              }
+              X0[q][j] = E;                           // the half's 8x8 sums (X0 is dead from here on)
             } else { X0[q][j] = X; Y0[q][j] = Y; }
             run[q][j] = rr;
           }
         }
+        if (odd) {
+          if (bb == 0) {
+#pragma unroll
+            for (int j = 0; j < K; j++) { E0[0][j] = X0[0][j]; E0[1][j] = X0[1][j]; }
+          } else {                                    // whole-MB partitions and the verdict: one uniform branch per task
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+#pragma unroll
+              for (int q = 0; q < 2; q++) {
+                const uint32_t E = X0[q][j];
+                const uint32_t top = __dp2a_lo(E0[q][j], 0x0101u, 0u), bot = __dp2a_lo(E, 0x0101u, 0u);
+                const uint32_t TB = bot * 65536u + top, LR = add2(E0[q][j], E);
+                uint32_t rr = run[q][j];
+                rr = addmin2(TB, ctb, rr, one);
+                rr = addmin2(LR, clr, rr, one);
+                const uint32_t m = (q ? mxb : mxa) + myj[j];
+                const int s = (int)(top + bot) + c16 + (int)m;
+                const uint32_t t = rr + m * 0x10001u;
+                if ((t & 0x80008000u) != 0u || s < 0) pass |= 1u << (q * K + j);
+              }
+            }
+          }
+        }
       }
+    }
+  }
+  return pass;
+}
+
+// fs_task4 with ONE block row (4 rows) per loop iteration: the body (~7 KB of SASS) is close to the L0 instruction cache;
+// the odd block rows' extra partitions and the verdict are uniform branches.  -DFS_ROLL4 selects it (development probe).
+template <int PITCH, class SLOT>
+__device__ __forceinline__ uint32_t fs_task4r(const SLOT &S, const uint8_t *wb, uint32_t mxa, uint32_t mxb, const unsigned short *mys, uint32_t one)
+{
+  constexpr int K = 4;
+  const uint4 *cur = reinterpret_cast<const uint4 *>(S.cur);
+  uint32_t rw[K][6];
+  uint32_t acc[2][K][4];
+  uint32_t run[2][K], X0[2][K], Y0[2][K], E0[2][K];
+  uint32_t pass = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++) { run[0][j] = run[1][j] = 0x7fff7fffu; E0[0][j] = E0[1][j] = 0; X0[0][j] = X0[1][j] = 0; Y0[0][j] = Y0[1][j] = 0; }
+#pragma unroll
+  for (int j = 0; j < K - 1; j++) ld3(rw[j], wb + j * PITCH);
+#pragma unroll 1
+  for (int b = 0; b < 4; b++) {
+    const uint8_t *wr = wb + b * 4 * PITCH;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      ld3(rw[(r + K - 1) & 3], wr + (r + K - 1) * PITCH);
+      const uint4 c = cur[b * 4 + r];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const int sl = (r + j) & 3;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          if (r == 0) {
+            acc[q][j][0] = sad4(c.x, rw[sl][q + 0], 0u);
+            acc[q][j][1] = sad4(c.y, rw[sl][q + 1], 0u);
+            acc[q][j][2] = sad4(c.z, rw[sl][q + 2], 0u);
+            acc[q][j][3] = sad4(c.w, rw[sl][q + 3], 0u);
+          } else {
+            acc[q][j][0] = sad4(c.x, rw[sl][q + 0], acc[q][j][0]);
+            acc[q][j][1] = sad4(c.y, rw[sl][q + 1], acc[q][j][1]);
+            acc[q][j][2] = sad4(c.z, rw[sl][q + 2], acc[q][j][2]);
+            acc[q][j][3] = sad4(c.w, rw[sl][q + 3], acc[q][j][3]);
+          }
+        }
+      }
+    }
+    const uint32_t cx = ld_vol(&S.Cw[3 * b]), cy = ld_vol(&S.Cw[3 * b + 1]), ch = ld_vol(&S.Cw[3 * b + 2]);
+    uint32_t Xc[2][K], Yc[2][K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const uint32_t X = acc[q][j][2] * 65536u + acc[q][j][0];
+        const uint32_t Y = acc[q][j][3] * 65536u + acc[q][j][1];
+        const uint32_t H = add2(X, Y);
+        uint32_t rr = run[q][j];
+        rr = addmin2(X, cx, rr, one);
+        rr = addmin2(Y, cy, rr, one);
+        rr = addmin2(H, ch, rr, one);
+        run[q][j] = rr; Xc[q][j] = X; Yc[q][j] = Y;
+      }
+    }
+    if (b & 1) {
+      const int bb = b >> 1;
+      const uint32_t cxv = ld_vol(&S.Cw[12 + 3 * bb]), cyv = ld_vol(&S.Cw[13 + 3 * bb]), ce = ld_vol(&S.Cw[14 + 3 * bb]);
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const uint32_t XV = add2(Xc[q][j], X0[q][j]), YV = add2(Yc[q][j], Y0[q][j]);
+          const uint32_t E = add2(XV, YV);
+          uint32_t rr = run[q][j];
+          rr = addmin2(XV, cxv, rr, one);
+          rr = addmin2(YV, cyv, rr, one);
+          rr = addmin2(E, ce, rr, one);
+          run[q][j] = rr; X0[q][j] = E;
+        }
+      }
+      if (b == 1) {
+#pragma unroll
+        for (int j = 0; j < K; j++) { E0[0][j] = X0[0][j]; E0[1][j] = X0[1][j]; }
+      } else {
+        const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
+        const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          const uint32_t my = mys[j];
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const uint32_t E = X0[q][j];
+            const uint32_t top = __dp2a_lo(E0[q][j], 0x0101u, 0u), bot = __dp2a_lo(E, 0x0101u, 0u);
+            const uint32_t TB = bot * 65536u + top, LR = add2(E0[q][j], E);
+            uint32_t rr = run[q][j];
+            rr = addmin2(TB, ctb, rr, one);
+            rr = addmin2(LR, clr, rr, one);
+            const uint32_t m = (q ? mxb : mxa) + my;
+            const int s = (int)(top + bot) + c16 + (int)m;
+            const uint32_t t = rr + m * 0x10001u;
+            if ((t & 0x80008000u) != 0u || s < 0) pass |= 1u << (q * K + j);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < K; j++) { X0[0][j] = Xc[0][j]; X0[1][j] = Xc[1][j]; Y0[0][j] = Yc[0][j]; Y0[1][j] = Yc[1][j]; }
     }
   }
   return pass;
@@ -389,6 +512,23 @@ __device__ __forceinline__ bool mbar_try_wait(void *bar, uint32_t parity)
 {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(void *bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+// waits (hardware-suspended, no issue slots) until the phase of parity `parity` completes or about `ns` pass
+__device__ __forceinline__ bool mbar_try_wait_ns(void *bar, uint32_t parity, uint32_t ns)
+{
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(void *bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
@@ -653,6 +793,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ SLOT SS[3];                           // two attached to the window buffers, one being prepared
   __shared__ FsCtl CB[2];
+  __shared__ unsigned long long evt;               // completes a phase whenever a worker finishes a unit: the producer sleeps on it
   constexpr int NT = (NWORK + 1) * 32;
   __shared__ FsWarp WS[NWORK + 1];
   __shared__ uint32_t pgt[NPART];
@@ -672,6 +813,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
     FsCtl &C = CB[tid];
     C.ready_epoch = 0; C.finished_epoch = 0; C.next = 0; C.done = 0; C.ended = 0; C.epoch = 0; C.tma_uses = 0; C.ntask = 0; C.slot = tid;
     mbar_init(&C.mbar, 1);
+    if (tid == 0) mbar_init(&evt, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 3) { SS[tid].item = -1; SS[tid].ngroups = 0; SS[tid].g = 0; }
@@ -693,6 +835,8 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
     }
     for (;;) {
       int nend = 0; bool any = false;
+      // parity of evt's current phase, read BEFORE the scan: a completion after this read ends the wait below at once
+      const uint32_t evp = mbar_test_wait(&evt, 0) ? 1u : 0u;
 #pragma unroll 1
       for (int b = 0; b < 2; b++) {
         FsCtl &C = CB[b];
@@ -720,7 +864,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         }
       }
       if (nend == 2) break;
-      if (!any) __nanosleep(1000);
+      if (!any) mbar_try_wait_ns(&evt, evp, 20000u);   // (two completions inside one scan would be seen at the time-out)
     }
     if (lane == 0) atomicAdd(&st.cyc[2], (unsigned long long)(clock64() - t_p0));
   } else {
@@ -741,7 +885,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
       const int ep0 = *reinterpret_cast<volatile int *>(&C.ready_epoch);
       if (ep0 == (b ? ex1 : ex0)) { if (*reinterpret_cast<volatile int *>(&C.ended)) nend++; continue; }
       int c = 0;
-      if (lane == 0) c = atomicAdd(&C.next, FS_CLAIM);
+      if (lane == 0) c = atomicAdd(&C.next, a.claim);
       c = __shfl_sync(0xffffffffu, c, 0);
       const int ep = *reinterpret_cast<volatile int *>(&C.ready_epoch);
       if (ep <= 0 || (c >> 20) != (ep & 0x7ff)) continue;       // counter not (yet) armed for the published epoch
@@ -757,7 +901,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
       SLOT &S = SS[slot];
       uint8_t *win = smem + b * G.slot_bytes;
       const int g = S.g;
-      const int t1 = min(t0 + FS_CLAIM, ntask);
+      const int t1 = min(t0 + a.claim, ntask);
 #pragma unroll 1
       for (int t = t0; t < t1; t++) {
         int dxa, dy0; bool va, vb;
@@ -779,8 +923,12 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         uint32_t pass = 0;
 #pragma unroll 1
         for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
+#ifdef FS_ROLL4
+          pass |= fs_task4r<PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
+#else
           pass |= K == 4 ? fs_task4<PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one)
                          : fs_task<5, PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
+#endif
         uint32_t vm = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) if (dy0 + j < S.ncy) vm |= (va ? 1u << j : 0u) | (vb ? 1u << (K + j) : 0u);
@@ -810,7 +958,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
       d = __shfl_sync(0xffffffffu, d, 0);
       if (d == ntask) {                              // unit complete: hand the buffer to the producer warp
         if (b) ex1 = ep; else ex0 = ep;
-        if (lane == 0) { FS_FENCE(); *reinterpret_cast<volatile int *>(&C.finished_epoch) = ep; }
+        if (lane == 0) { FS_FENCE(); *reinterpret_cast<volatile int *>(&C.finished_epoch) = ep; FS_FENCE(); mbar_arrive(&evt); }
       }
     }
     if (nend == 2) break;
@@ -844,23 +992,33 @@ FsGeom fs_geom_host(int R) { return fs_geom(R); }
 cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, cudaStream_t s, int *smem_bytes_out)
 {
   const FsGeom G = fs_geom(a.R);
-  static int configured96 = 0, configured160 = 0;
+  static int configured160 = 0;
   cudaError_t e;
   if (smem_bytes_out) *smem_bytes_out = G.total;
   if (G.pitch == 96) {
-    if (configured96 < G.total) {
-      e = cudaFuncSetAttribute(k_sad_fs<96, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
-      if (e != cudaSuccess) return e;
-      configured96 = G.total;
+    // CTA shape: workers x resident CTAs per SM (B2ME_FS_VAR = "4x3" default, "7x2", "6x2": development probes)
+    static int var = -1;
+    if (var < 0) { const char *e = getenv("B2ME_FS_VAR"); var = !e ? 0 : (e[0] == '7' ? 1 : (e[0] == '6' ? 2 : 0)); }
+#define FS_LAUNCH96(NW, MB)                                                                                                   \
+    {                                                                                                                         \
+      static int configured = 0, occ = -1;                                                                                    \
+      if (configured < G.total) {                                                                                             \
+        e = cudaFuncSetAttribute(k_sad_fs<96, NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);                 \
+        if (e != cudaSuccess) return e;                                                                                       \
+        configured = G.total;                                                                                                 \
+      }                                                                                                                       \
+      if (occ < 0) {                                                                                                          \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sad_fs<96, NW, MB>, (NW + 1) * 32, G.total);                    \
+        if (getenv("B2ME_FS_PROFILE")) fprintf(stderr, "[b2me] k_sad_fs<96,%d>: %d CTAs/SM (dyn smem %d)\n", NW, occ, G.total); \
+        if (occ < 1) occ = 1;                                                                                                 \
+      }                                                                                                                       \
+      const int grid = min((a.nitems + 1) / 2, sm_count * occ);                                                               \
+      k_sad_fs<96, NW, MB><<<grid, (NW + 1) * 32, G.total, s>>>(tm, a);                                                       \
     }
-    static int occ = -1;
-    if (occ < 0) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sad_fs<96, 4, 3>, G.threads, G.total);
-      if (getenv("B2ME_FS_PROFILE")) fprintf(stderr, "[b2me] k_sad_fs<96>: %d CTAs/SM (threads %d, dyn smem %d)\n", occ, G.threads, G.total);
-      if (occ < 1) occ = 1;
-    }
-    const int grid = min((a.nitems + 1) / 2, sm_count * occ);
-    k_sad_fs<96, 4, 3><<<grid, G.threads, G.total, s>>>(tm, a);
+    if (var == 1) FS_LAUNCH96(7, 2)
+    else if (var == 2) FS_LAUNCH96(6, 2)
+    else FS_LAUNCH96(4, 3)
+#undef FS_LAUNCH96
   } else if (G.pitch == 160) {
     if (configured160 < G.total) {
       e = cudaFuncSetAttribute(k_sad_fs<160, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
