@@ -310,8 +310,8 @@ def main():
     h_cur = [torch.from_numpy(fr[NREFS + j]).pin_memory() for j in range(2)]
     h_ref = [torch.from_numpy(fr[j]).pin_memory() for j in range(NREFS + 2)]
     h_pred = torch.from_numpy(pred_np).pin_memory(); h_cen = torch.from_numpy(cen_np).pin_memory()
-    h_mvi = torch.zeros((nmb, NREFS, 41, 2), dtype=torch.int16).pin_memory(); h_mvs = torch.zeros_like(h_mvi).pin_memory()
-    h_ci = torch.zeros((nmb, NREFS, 41), dtype=torch.int64).pin_memory(); h_cs = torch.zeros_like(h_ci).pin_memory()
+    h_mvs = torch.zeros((nmb, NREFS, 41, 2), dtype=torch.int16).pin_memory()
+    h_cs = torch.zeros((nmb, NREFS, 41), dtype=torch.int64).pin_memory()
     import ctypes as C
     L = s.L
 
@@ -319,7 +319,7 @@ def main():
         r = L.b2me_set_cur(s.h, C.c_void_p(h_cur[0].data_ptr()), C.c_int(W))
         r |= L.b2me_set_ref(s.h, C.c_int(i % NREFS), C.c_void_p(h_ref[NREFS - 1 - (i % NREFS)].data_ptr()), C.c_int(W))
         r |= L.b2me_search_frame(s.h, C.c_void_p(h_pred.data_ptr()), C.c_void_p(h_cen.data_ptr()), C.byref(params),
-                                 C.c_void_p(h_mvi.data_ptr()), C.c_void_p(h_ci.data_ptr()),
+                                 None, None,                     # the caller consumes the refined vectors / costs only
                                  C.c_void_p(h_mvs.data_ptr()), C.c_void_p(h_cs.data_ptr()))
         if r:
             raise RuntimeError(f"C ABI call failed: {L.b2me_last_error(s.h)}")
@@ -337,7 +337,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * pel_sp(nmb) / float(t.item()) / 1e6
     h2d = 2 * W * H + 2 * n * 2 * 2
-    d2h = 2 * n * 2 * 2 + 2 * n * 8
+    d2h = n * 2 * 2 + n * 8
     checksum = int(h_mvs.to(torch.int64).sum().item())           # the result really is on the host
 
     if rank != 0:

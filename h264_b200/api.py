@@ -130,8 +130,9 @@ class Searcher:
         return out
 
     # ---- search -------------------------------------------------------------------------
-    def search_frame(self, pred, center, params):
-        """Host numpy in/out through the C ABI (copies inside the call)."""
+    def search_frame(self, pred, center, params, want_int=True):
+        """Host numpy in/out through the C ABI (copies inside the call).  want_int=False (sub-pel searches only):
+        the integer stage's results stay on the device, (None, None, mv_sub, cost_sub) comes back."""
         pred = np.ascontiguousarray(pred, np.int16)
         center = np.ascontiguousarray(center, np.int16)
         shape = (self.nmb, self.nrefs, NPART, 2)
@@ -140,6 +141,10 @@ class Searcher:
         mv_sub = np.zeros(shape, np.int16)
         cost_int = np.zeros(shape[:3], np.int64)
         cost_sub = np.zeros(shape[:3], np.int64)
+        if not want_int:
+            self._chk(self.L.b2me_search_frame(self.h, _p(pred), _p(center), C.byref(params), None, None,
+                                               _p(mv_sub), _p(cost_sub)), "b2me_search_frame")
+            return None, None, mv_sub, cost_sub
         self._chk(self.L.b2me_search_frame(self.h, _p(pred), _p(center), C.byref(params), _p(mv_int), _p(cost_int),
                                            _p(mv_sub), _p(cost_sub)), "b2me_search_frame")
         return mv_int, cost_int, mv_sub, cost_sub

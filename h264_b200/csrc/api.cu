@@ -96,6 +96,8 @@ extern "C" int b2me_create(b2me_ctx **out, int device, int width, int height, in
   for (int i = 0; i < 8; i++) B2_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_band[i], cudaEventDisableTiming));
   B2_CUDA_CHECK(c, cudaEventCreate(&c->ev0));
   B2_CUDA_CHECK(c, cudaEventCreate(&c->ev1));
+  B2_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+  B2_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->ev_planes, cudaEventDisableTiming));
   return B2ME_OK;
 }
 
@@ -113,6 +115,8 @@ extern "C" void b2me_destroy(b2me_ctx *c)
   for (int i = 0; i < 8; i++) if (c->ev_band[i]) cudaEventDestroy(c->ev_band[i]);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->ev_planes) cudaEventDestroy(c->ev_planes);
   delete c;
 }
 
@@ -173,6 +177,14 @@ extern "C" int b2me_set_cur(b2me_ctx *c, const uint8_t *luma, int stride)
   B2_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
   return B2ME_OK;
 }
+// Work on a caller's stream that reads the reference planes is ordered after a plane build that a host-pointer
+// b2me_set_ref left running on the context's own stream.
+static int after_uploads(b2me_ctx *c, cudaStream_t s)
+{
+  if (c->planes_pending && s != c->stream) B2_CUDA_CHECK(c, cudaStreamWaitEvent(s, c->ev_planes, 0));
+  return B2ME_OK;
+}
+
 static int build_planes(b2me_ctx *c, int ref_idx, const uint8_t *luma_dev, int stride, cudaStream_t s)
 {
   FamilyTimer t(c, 1, s);
@@ -200,6 +212,7 @@ extern "C" int b2me_set_ref_dev(b2me_ctx *c, int ref_idx, const uint8_t *luma_de
 {
   if (!c || !luma_dev || stride < c->W || ref_idx < 0 || ref_idx >= c->nrefs) return B2ME_EINVAL;
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  { int r0 = after_uploads(c, (cudaStream_t)stream); if (r0) return r0; }
   return build_planes(c, ref_idx, luma_dev, stride, (cudaStream_t)stream);
 }
 extern "C" int b2me_set_ref(b2me_ctx *c, int ref_idx, const uint8_t *luma, int stride)
@@ -207,15 +220,21 @@ extern "C" int b2me_set_ref(b2me_ctx *c, int ref_idx, const uint8_t *luma, int s
   if (!c || !luma || stride < c->W || ref_idx < 0 || ref_idx >= c->nrefs) return B2ME_EINVAL;
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
   B2_CUDA_CHECK(c, cudaMemcpy2DAsync(c->d_stage, c->W, luma, stride, c->W, c->H, cudaMemcpyHostToDevice, c->stream));
+  B2_CUDA_CHECK(c, cudaEventRecord(c->ev_copy, c->stream));
   int r = build_planes(c, ref_idx, c->d_stage, c->W, c->stream);
   if (r) return r;
-  B2_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  B2_CUDA_CHECK(c, cudaEventRecord(c->ev_planes, c->stream));
+  c->planes_pending = 1;
+  // the caller's buffer is free once the copy is done; the plane kernels run on behind it (every later call of this
+  // context runs on c->stream or waits for ev_planes, see after_uploads)
+  B2_CUDA_CHECK(c, cudaEventSynchronize(c->ev_copy));
   return B2ME_OK;
 }
 extern "C" int b2me_get_subplane(b2me_ctx *c, int ref_idx, int yy, int xx, uint8_t *out)
 {
   if (!c || !out || ref_idx < 0 || ref_idx >= c->nrefs || yy < 0 || yy > 3 || xx < 0 || xx > 3) return B2ME_EINVAL;
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  B2_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
   B2_CUDA_CHECK(c, cudaMemcpy(out, c->d_planes + ((size_t)ref_idx * 16 + yy * 4 + xx) * c->plane_size, c->plane_size, cudaMemcpyDeviceToHost));
   return B2ME_OK;
 }
@@ -237,6 +256,7 @@ static int run_subpel(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
                       const int16_t *mv_int, const long long *cost_int, int16_t *mv_sub, long long *cost_sub,
                       int use_bound, cudaStream_t s)
 {
+  { int r0 = after_uploads(c, s); if (r0) return r0; }
   SubArgs q;
   q.cur = c->d_cur; q.cur_pitch = c->W; q.planes = c->d_planes; q.plane_size = c->plane_size;
   q.W = c->W; q.H = c->H; q.Wp = c->Wp; q.Hp = c->Hp; q.mbw = c->mbw; q.nrefs = c->nrefs;
@@ -263,6 +283,7 @@ static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
                       const int16_t *pred, const int16_t *center, const b2me_search_params *p,
                       int16_t *mv_int, long long *cost_int, int16_t *mv_sub, long long *cost_sub, cudaStream_t s)
 {
+  { int r0 = after_uploads(c, s); if (r0) return r0; }
   FsArgs f;
   f.cur = c->d_cur; f.cur_pitch = c->W; f.spl = c->d_spl; f.Wq = c->Wq; f.Hq = c->Hq; f.spad = c->spad;
   f.W = c->W; f.H = c->H; f.mbw = c->mbw; f.nrefs = c->nrefs;
@@ -325,10 +346,11 @@ static int check_errflag(b2me_ctx *c, cudaStream_t s)
 extern "C" int b2me_search_frame(b2me_ctx *c, const int16_t *pred, const int16_t *center, const b2me_search_params *p,
                                  int16_t *mv_int, int64_t *cost_int, int16_t *mv_sub, int64_t *cost_sub)
 {
-  if (!c || !pred || !center || !mv_int || !cost_int) return B2ME_EINVAL;
+  if (!c || !pred || !center) return B2ME_EINVAL;
   int r = check_params(c, p);
   if (r) return r;
   if (p->do_subpel && (!mv_sub || !cost_sub)) return B2ME_EINVAL;
+  if ((!mv_int) != (!cost_int) || (!mv_int && !p->do_subpel)) return B2ME_EINVAL;
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
   // The picture is processed in bands of MB rows so that the host<->device copies overlap the search: predictors
   // of band i+1 go up (H2D stream) and results of band i-1 come down (D2H stream) while band i is searched.
@@ -352,8 +374,10 @@ extern "C" int b2me_search_frame(b2me_ctx *c, const int16_t *pred, const int16_t
     if (r) return r;
     B2_CUDA_CHECK(c, cudaEventRecord(c->ev_band[4 + b], s));
     B2_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream_d2h, c->ev_band[4 + b], 0));
-    B2_CUDA_CHECK(c, cudaMemcpyAsync(mv_int + o1 * 2, c->d_mv_int + o1 * 2, n1 * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream_d2h));
-    B2_CUDA_CHECK(c, cudaMemcpyAsync(cost_int + o1, c->d_cost_int + o1, n1 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream_d2h));
+    if (mv_int) {
+      B2_CUDA_CHECK(c, cudaMemcpyAsync(mv_int + o1 * 2, c->d_mv_int + o1 * 2, n1 * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream_d2h));
+      B2_CUDA_CHECK(c, cudaMemcpyAsync(cost_int + o1, c->d_cost_int + o1, n1 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream_d2h));
+    }
     if (p->do_subpel) {
       B2_CUDA_CHECK(c, cudaMemcpyAsync(mv_sub + o1 * 2, c->d_mv_sub + o1 * 2, n1 * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream_d2h));
       B2_CUDA_CHECK(c, cudaMemcpyAsync(cost_sub + o1, c->d_cost_sub + o1, n1 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream_d2h));
@@ -447,6 +471,7 @@ extern "C" int b2me_mc_luma_dev(b2me_ctx *c, const uint8_t *mb_mode, const uint8
 {
   if (!c || !mb_mode || !b8mode || !ref8 || !mv || !orig_blk || !pred_blk) return B2ME_EINVAL;
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  { int r0 = after_uploads(c, (cudaStream_t)stream); if (r0) return r0; }
   McArgs m;
   m.cur = c->d_cur; m.cur_pitch = c->W; m.planes = c->d_planes; m.plane_size = c->plane_size;
   m.W = c->W; m.H = c->H; m.Wp = c->Wp; m.mbw = c->mbw; m.nmb = c->nmb; m.nrefs = c->nrefs;

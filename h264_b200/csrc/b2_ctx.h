@@ -32,6 +32,8 @@ struct b2me_ctx {
   cudaStream_t stream_h2d, stream_d2h;   // copy streams of the banded host-pointer search
   cudaEvent_t ev_band[8];       // [0..3] predictors of band b are up, [4..7] band b is searched
   cudaEvent_t ev0, ev1;
+  cudaEvent_t ev_planes; int planes_pending;   // a host-pointer b2me_set_ref left its plane build running on `stream`
+  cudaEvent_t ev_copy;          // host-pointer uploads return when the copy (not the plane build behind it) is done
   int timing;
   double t_ms[4];
   int64_t t_n[4];

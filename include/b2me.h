@@ -94,7 +94,9 @@ int b2me_get_subplane(b2me_ctx *ctx, int ref_idx, int yy, int xx, uint8_t *out);
  *                  (centre = relative MV, multiple of 4; JM derives it at mv_search.c:931-932)
  *   mv_int, mv_sub : same shape, best integer / final quarter-pel MV
  *   cost_int, cost_sub : [nmb][nrefs][41] int64 motion costs (SAD or SATD <<5 + lambda*bits)
- * mv_sub/cost_sub may be NULL when do_subpel == 0. */
+ * mv_sub/cost_sub may be NULL when do_subpel == 0.  With do_subpel != 0, mv_int and cost_int may BOTH be NULL (host-pointer
+ * call only): BlockMotionSearch hands only the refined vector and cost on (mv_search.c:960-976), and the integer
+ * stage's 16 MB per 1080p x 4 refs picture then stay on the device. */
 int b2me_search_frame(b2me_ctx *ctx, const int16_t *pred, const int16_t *center,
                       const b2me_search_params *params,
                       int16_t *mv_int, int64_t *cost_int, int16_t *mv_sub, int64_t *cost_sub);

@@ -232,3 +232,41 @@ def test_weighted_prediction_matches_oracle():
         assert (a == b).all(), (n, int((a != b).sum()))
     s.set_ref_weights(0, 32, 0, 5, apply=False); s.set_ref(0, refs[0])      # off again: plain planes
     assert (s.subplane(0, 0, 0) == oracle.subpel_planes(refs[0])[0, 0]).all()
+
+
+def test_refined_results_only_and_upload_ordering():
+    """b2me_search_frame with mv_int = cost_int = NULL (the refined results alone come down), directly behind host-pointer
+    b2me_set_ref calls whose plane build is still running on the context's stream; the device-pointer call on ANOTHER
+    stream must wait for that build too."""
+    import torch
+    W, H, R, NR = 128, 96, 16, 2
+    fr = synth.luma_sequence(W, H, NR + 2, seed=5)
+    pred, cen = synth.predictors(W, H, NR, seed=6, spread=2, rmax=6)
+    lam = (187, 150, 150)
+    p = api.make_params(lam)
+    s = api.Searcher(W, H, NR, R)
+    for rep in range(3):                            # new pictures every round: stale planes would show
+        cur, refs = fr[NR + (rep & 1)], fr[[1 + (rep & 1), rep & 1]]
+        exp = oracle.OrcFrame(cur, refs, R).search_frame(pred, cen, lam)
+        s.set_cur(cur)
+        for r in range(NR):
+            s.set_ref(r, refs[r])
+        got = s.search_frame(pred, cen, p, want_int=False)
+        assert got[0] is None and got[1] is None
+        assert (got[2] == exp[2]).all() and (got[3] == exp[3]).all()
+        for r in range(NR):
+            s.set_ref(r, refs[r])
+        st = torch.cuda.Stream()
+        dev = torch.device("cuda", 0)
+        dp, dc = torch.from_numpy(pred).to(dev), torch.from_numpy(cen).to(dev)
+        mvi = torch.zeros((s.nmb, NR, 41, 2), dtype=torch.int16, device=dev); mvs = torch.zeros_like(mvi)
+        ci = torch.zeros((s.nmb, NR, 41), dtype=torch.int64, device=dev); cs = torch.zeros_like(ci)
+        torch.cuda.synchronize()
+        for r in range(NR):
+            s.set_ref(r, refs[r])
+        s.search_frame_dev(dp, dc, p, mvi, ci, mvs, cs, stream=st.cuda_stream)
+        st.synchronize()
+        assert (mvs.cpu().numpy() == exp[2]).all() and (cs.cpu().numpy() == exp[3]).all()
+    import ctypes as C
+    assert s.L.b2me_search_frame(s.h, pred.ctypes.data_as(C.c_void_p), cen.ctypes.data_as(C.c_void_p),
+                                 C.byref(api.make_params(lam, do_subpel=False)), None, None, None, None) == -1
