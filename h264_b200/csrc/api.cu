@@ -354,7 +354,8 @@ extern "C" int b2me_search_frame(b2me_ctx *c, const int16_t *pred, const int16_t
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
   // The picture is processed in bands of MB rows so that the host<->device copies overlap the search: predictors
   // of band i+1 go up (H2D stream) and results of band i-1 come down (D2H stream) while band i is searched.
-  const int nband = c->mbh >= 16 ? 4 : 1;
+  int nband = c->mbh >= 16 ? 2 : 1;               // measured (tools/e2e_probe.py, 1080p x 4 refs): 1 band 2.07 ms, 2: 2.02, 3: 2.08, 4: 2.20
+  { const char *e = getenv("B2ME_BANDS"); if (e && atoi(e) >= 1 && atoi(e) <= 4 && c->mbh >= 16) nband = atoi(e); }   // development probe
   cudaStream_t s = c->stream;
   for (int b = 0; b < nband; b++) {
     const int row0 = (int)((long long)c->mbh * b / nband), row1 = (int)((long long)c->mbh * (b + 1) / nband);
