@@ -163,6 +163,15 @@ class Searcher:
         self._chk(self.L.b2me_mc_luma_dev(self.h, _dp(mb_mode), _dp(b8mode), _dp(ref8), _dp(mv), _dp(orig_blk), _dp(pred_blk), _vp(stream)),
                   "b2me_mc_luma_dev")
 
+    def bipred_search(self, jobs, params, apply_weights=False, log_denom=0, test8x8=False):
+        """full_search_bipred (+ sub_pel_bipred) for an array of synth.BIPRED_JOB records; returns BIPRED_RESULT records"""
+        from . import synth
+        jobs = np.ascontiguousarray(jobs, synth.BIPRED_JOB)
+        out = np.zeros(len(jobs), synth.BIPRED_RESULT)
+        self._chk(self.L.b2me_bipred_search(self.h, C.c_int(len(jobs)), _p(jobs), C.byref(params), C.c_int(int(apply_weights)),
+                                            C.c_int(log_denom), C.c_int(int(test8x8)), _p(out)), "b2me_bipred_search")
+        return out
+
     def block_search(self, pos_x, pos_y, blocktype, ref, pred_mv, center_mv, params, search_range):
         pm = (C.c_int16 * 2)(int(pred_mv[0]), int(pred_mv[1]))
         cm = (C.c_int16 * 2)(int(center_mv[0]), int(center_mv[1]))

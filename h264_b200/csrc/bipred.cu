@@ -1,0 +1,270 @@
+// bipred.cu -- bi-predictive block search (B slices): one CTA per call of
+//   full_search_bipred_motion_estimation   JM/lencod/src/me_fullsearch.c:112-176
+//   sub_pel_bipred_motion_estimation       JM/lencod/src/me_fullsearch.c:300-399
+// with the distortions behind them,
+//   computeBiPredSAD1/2   JM/lencod/src/me_distortion.c:525-620 / 628-737
+//   computeBiPredSATD1/2  :943-1040 / 1048-1182      computeBiPredSSE1/2  :1353-1442 / 1450-1549
+// sequenced as BiPredBlockMotionSearch does (mv_search.c:1100-1126).
+//
+// The block of the searched list moves over the spiral, the block of the other list stays where the caller's vector
+// puts it; the distortion is taken against their (weighted) average.  Every candidate is independent: candidates
+// are spread over the CTA's threads and the reference's strict-'<' scan order is the lexicographic minimum of
+// (cost, spiral position), kept with a 64-bit shared atomicMin that starts from the caller's bound.  The early
+// exits of the reference only ever skip candidates that cannot win (they return a value >= the bound).
+// Both blocks come straight from the 16 quarter-pel planes (UMVLine4X clamp, refbuf.h:25); this path serves B
+// slices, which none of the BASELINE configs code, so it is written for exactness first.
+#include "b2_common.cuh"
+#include "b2_ctx.h"
+
+namespace b2 {
+
+struct BiArgs {
+  const uint8_t *cur; int cur_pitch;
+  const uint8_t *planes; size_t plane_size;
+  int W, H, Wp, nrefs, R;
+  int lambda[3], metric_h, metric_q, do_subpel, test8x8, wp, denom;
+  const b2me_bipred_job *jobs; b2me_bipred_result *out; int njobs;
+  int *errflag;
+};
+
+__device__ __forceinline__ const uint8_t *bi_umv(const BiArgs &a, int ref, int qx, int qy)
+{
+  const uint8_t *pl = a.planes + ((size_t)ref * 16 + (qy & 3) * 4 + (qx & 3)) * a.plane_size;
+  const int yy = iclamp(qy >> 2, -PADY, a.H + 3), xx = iclamp(qx >> 2, -PADX, a.W + 15);
+  return pl + (size_t)(yy + PADY) * a.Wp + (xx + PADX);
+}
+
+struct BiWp { int wp, w1, w2, off, shift, lround; };
+__device__ __forceinline__ int bi_pel(int r1, int r2, const BiWp &w)
+{
+  if (!w.wp) return (r1 + r2 + 1) >> 1;
+  return iclamp(((w.w1 * r1 + w.w2 * r2 + w.lround) >> w.shift) + w.off, 0, 255);
+}
+
+__device__ __forceinline__ int bi_had4(int *d)          // sum |H4 D H4|, (s + 1) >> 1   (HadamardSAD4x4, me_distortion.c:175-258)
+{
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int p = d[4 * i], q = d[4 * i + 1], r = d[4 * i + 2], s = d[4 * i + 3];
+    d[4 * i] = p + q + r + s; d[4 * i + 1] = p - q + r - s; d[4 * i + 2] = p + q - r - s; d[4 * i + 3] = p - q - r + s;
+  }
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int p = d[i], q = d[4 + i], r = d[8 + i], s = d[12 + i];
+    t += abs(p + q + r + s) + abs(p - q + r - s) + abs(p + q - r - s) + abs(p - q - r + s);
+  }
+  return (t + 1) >> 1;
+}
+__device__ __noinline__ int bi_had8(short *d)           // sum |H8 D H8|, (s + 2) >> 2   (HadamardSAD8x8, :266-341)
+{
+  for (int j = 0; j < 8; j++)
+    for (int k = 1; k < 8; k <<= 1)
+      for (int i = 0; i < 8; i++)
+        if (!(i & k)) { const short p = d[8 * j + i], q = d[8 * j + (i | k)]; d[8 * j + i] = p + q; d[8 * j + (i | k)] = p - q; }
+  int t = 0;
+  for (int i = 0; i < 8; i++) {
+    int c[8];
+    for (int j = 0; j < 8; j++) c[j] = d[8 * j + i];
+    for (int k = 1; k < 8; k <<= 1)
+      for (int j = 0; j < 8; j++)
+        if (!(j & k)) { const int p = c[j], q = c[j | k]; c[j] = p + q; c[j | k] = p - q; }
+    for (int j = 0; j < 8; j++) t += abs(c[j]);
+  }
+  return (t + 2) >> 2;
+}
+
+// distortion of the block against the average of (ref1 at c1) and (ref2 at c2); metric 0 SAD, 1 SSE, 2 SATD
+__device__ int bi_dist(const BiArgs &a, const uint8_t *cur /* smem, pitch 16 */, int bsx, int bsy, int ref1, int ref2,
+                       int c1x, int c1y, int c2x, int c2y, int metric, const BiWp &w)
+{
+  int s = 0;
+  if (metric != 2) {                                  // one origin clamp per reference (me_distortion.c:546-547)
+    const uint8_t *r1 = bi_umv(a, ref1, c1x, c1y), *r2 = bi_umv(a, ref2, c2x, c2y);
+    for (int y = 0; y < bsy; y++)
+      for (int x = 0; x < bsx; x++) {
+        const int d = (int)cur[y * 16 + x] - bi_pel(r1[(size_t)y * a.Wp + x], r2[(size_t)y * a.Wp + x], w);
+        s += metric == 0 ? abs(d) : d * d;
+      }
+    return s;
+  }
+  if (!a.test8x8) {                                   // every 4x4 tile origin is clamped on its own (:971-972)
+    for (int by = 0; by < bsy; by += 4)
+      for (int bx = 0; bx < bsx; bx += 4) {
+        const uint8_t *r1 = bi_umv(a, ref1, c1x + (bx << 2), c1y + (by << 2)), *r2 = bi_umv(a, ref2, c2x + (bx << 2), c2y + (by << 2));
+        int d[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            d[j * 4 + i] = (int)cur[(by + j) * 16 + bx + i] - bi_pel(r1[(size_t)j * a.Wp + i], r2[(size_t)j * a.Wp + i], w);
+        s += bi_had4(d);
+      }
+    return s;
+  }
+  for (int by = 0; by < bsy; by += 8)
+    for (int bx = 0; bx < bsx; bx += 8) {
+      const uint8_t *r1 = bi_umv(a, ref1, c1x + (bx << 2), c1y + (by << 2)), *r2 = bi_umv(a, ref2, c2x + (bx << 2), c2y + (by << 2));
+      short d[64];
+      for (int j = 0; j < 8; j++)
+        for (int i = 0; i < 8; i++)
+          d[j * 8 + i] = (short)((int)cur[(by + j) * 16 + bx + i] - bi_pel(r1[(size_t)j * a.Wp + i], r2[(size_t)j * a.Wp + i], w));
+      s += bi_had8(d);
+    }
+  return s;
+}
+
+constexpr long long BI_DISTBLK_MAX = ((long long)0x7fffffff) << 5;
+
+__global__ void __launch_bounds__(128) k_bipred(const BiArgs a)
+{
+  __shared__ uint8_t cur[256];
+  __shared__ unsigned long long key;
+  __shared__ int mv1[2];
+  __shared__ long long bound;
+  const int tid = threadIdx.x;
+  const b2me_bipred_job J = a.jobs[blockIdx.x];
+  b2me_bipred_result *O = &a.out[blockIdx.x];
+  const int bt = J.blocktype;
+  const bool bad = bt < 1 || bt > 7 || J.ref1 < 0 || J.ref1 >= a.nrefs || J.ref2 < 0 || J.ref2 >= a.nrefs || J.search_range < 0 ||
+                   J.search_range > a.R || J.pos_x < 0 || J.pos_y < 0 || J.pos_x >= a.W || J.pos_y >= a.H || ((J.mv1[0] | J.mv1[1]) & 3);
+  if (bad) {                                          // uniform over the CTA
+    if (tid == 0) { *a.errflag = 1; O->cost_int = O->cost_sub = -1; O->mv_int[0] = O->mv_int[1] = O->mv_sub[0] = O->mv_sub[1] = 0; }
+    return;
+  }
+  const PartGeom gm = part_geom(part_first(bt));
+  const int bsx = gm.w, bsy = gm.h;
+  for (int i = tid; i < 256; i += 128) {
+    const int x = i & 15, y = i >> 4;
+    cur[i] = (x < bsx && y < bsy && J.pos_x + x < a.W && J.pos_y + y < a.H) ? a.cur[(size_t)(J.pos_y + y) * a.cur_pitch + J.pos_x + x] : 0;
+  }
+  BiWp w; w.wp = a.wp; w.w1 = J.weight1; w.w2 = J.weight2; w.off = J.offset_bi; w.shift = a.denom + 1;
+  w.lround = 2 * (a.denom ? 1 << (a.denom - 1) : 0);
+  const int ox = J.pos_x << 2, oy = J.pos_y << 2;
+  const int c2x = ox + J.mv2[0], c2y = oy + J.mv2[1];
+  long long min_mcost = J.min_mcost < 0 ? 0 : (J.min_mcost > BI_DISTBLK_MAX ? BI_DISTBLK_MAX : J.min_mcost);
+  if (tid == 0) { key = (unsigned long long)min_mcost << 20; mv1[0] = J.mv1[0]; mv1[1] = J.mv1[1]; }
+  __syncthreads();
+  // ---- integer pel: (2 sr + 1)^2 spiral positions around mv1, SAD ----
+  {
+    const int sr = J.search_range, max_pos = (2 * sr + 1) * (2 * sr + 1);
+    const long long c2 = (long long)a.lambda[0] * (mvbits(J.mv2[0] - J.pred2[0]) + mvbits(J.mv2[1] - J.pred2[1]));
+    for (int pos = tid; pos < max_pos; pos += 128) {
+      int sx, sy; spiral_xy(pos, &sx, &sy);
+      const int cx = J.mv1[0] + 4 * sx, cy = J.mv1[1] + 4 * sy;
+      long long mcost = (long long)a.lambda[0] * (mvbits(cx - J.pred1[0]) + mvbits(cy - J.pred1[1])) + c2;
+      if ((unsigned long long)mcost >= (*reinterpret_cast<volatile unsigned long long *>(&key) >> 20)) continue;
+      mcost += (long long)bi_dist(a, cur, bsx, bsy, J.ref1, J.ref2, ox + cx, oy + cy, c2x, c2y, 0, w) << 5;
+      atomicMin(&key, ((unsigned long long)mcost << 20) | (unsigned)pos);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int pos = (int)(key & 0xfffffull);
+    int sx, sy; spiral_xy(pos, &sx, &sy);
+    mv1[0] += 4 * sx; mv1[1] += 4 * sy;
+    long long c = (long long)(key >> 20);
+    if (pos == 0 && c == BI_DISTBLK_MAX && J.min_mcost > BI_DISTBLK_MAX) c = J.min_mcost;
+    O->mv_int[0] = (int16_t)mv1[0]; O->mv_int[1] = (int16_t)mv1[1]; O->cost_int = c;
+    O->mv_sub[0] = (int16_t)mv1[0]; O->mv_sub[1] = (int16_t)mv1[1]; O->cost_sub = c;
+    bound = c;
+  }
+  if (!a.do_subpel) return;
+  // ---- half pel, then quarter pel: positions start..8 of the spiral, step 2 / 1 quarter-pel ----
+  const int start_hp_cfg = (0 != a.metric_h) ? 0 : 1, start_qp = (a.metric_h != a.metric_q) ? 0 : 1;
+#pragma unroll 1
+  for (int stage = 0; stage < 2; stage++) {
+    __syncthreads();
+    long long b = bound;
+    if (stage == 0 && !start_hp_cfg) b = BI_DISTBLK_MAX;              // mv_search.c:1119-1120
+    const int start = stage ? start_qp : (b == BI_DISTBLK_MAX ? 0 : start_hp_cfg);
+    if (stage == 1 && !start_qp) b = BI_DISTBLK_MAX;                  // me_fullsearch.c:364-365
+    const int m0 = mv1[0], m1 = mv1[1];
+    __syncthreads();
+    if (tid == 0) key = (unsigned long long)b << 20;
+    __syncthreads();
+    const int lam = a.lambda[1 + stage], metric = stage ? a.metric_q : a.metric_h, step = stage ? 1 : 2;
+    if (tid >= start && tid < 9) {
+      int sx, sy; spiral_xy(tid, &sx, &sy);
+      const int cx = m0 + step * sx, cy = m1 + step * sy;
+      long long mcost = (long long)lam * (mvbits(cx - J.pred1[0]) + mvbits(cy - J.pred1[1]) + mvbits(J.mv2[0] - J.pred2[0]) + mvbits(J.mv2[1] - J.pred2[1]));
+      if (mcost < b) {
+        mcost += (long long)bi_dist(a, cur, bsx, bsy, J.ref1, J.ref2, ox + cx, oy + cy, c2x, c2y, metric, w) << 5;
+        atomicMin(&key, ((unsigned long long)mcost << 20) | (unsigned)tid);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int pos = (int)(key & 0xfffffull);
+      int sx, sy; spiral_xy(pos, &sx, &sy);
+      mv1[0] += step * sx; mv1[1] += step * sy;
+      bound = (long long)(key >> 20);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) { O->mv_sub[0] = (int16_t)mv1[0]; O->mv_sub[1] = (int16_t)mv1[1]; O->cost_sub = bound; }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+static int bipred_check(b2me_ctx *c, int njobs, const void *jobs, const b2me_search_params *p, int apply_weights, int denom, int test8x8, const void *out)
+{
+  if (!c || njobs < 0 || (njobs && (!jobs || !out)) || !p) return B2ME_EINVAL;
+  if (p->do_subpel && (p->metric_h < 0 || p->metric_h > 2 || p->metric_q < 0 || p->metric_q > 2)) return B2ME_EINVAL;
+  if (denom < 0 || denom > 7) return B2ME_EINVAL;
+  if (apply_weights && test8x8 && p->do_subpel && (p->metric_h == 2 || p->metric_q == 2)) {
+    snprintf(c->err, sizeof(c->err), "weighted bi-predictive SATD with the 8x8 Hadamard is not implemented (the reference's "
+                                     "computeBiPredSATD2 8x8 branch reads past its source row, me_distortion.c:1167)");
+    return B2ME_EUNSUPPORTED;
+  }
+  return B2ME_OK;
+}
+
+extern "C" int b2me_bipred_search_dev(b2me_ctx *c, int njobs, const b2me_bipred_job *jobs_dev, const b2me_search_params *p,
+                                      int apply_weights, int luma_log_weight_denom, int test8x8, b2me_bipred_result *out_dev, void *stream)
+{
+  int r = bipred_check(c, njobs, jobs_dev, p, apply_weights, luma_log_weight_denom, test8x8, out_dev);
+  if (r || !njobs) return r;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->planes_pending && s != c->stream) B2_CUDA_CHECK(c, cudaStreamWaitEvent(s, c->ev_planes, 0));
+  BiArgs a;
+  a.cur = c->d_cur; a.cur_pitch = c->W; a.planes = c->d_planes; a.plane_size = c->plane_size;
+  a.W = c->W; a.H = c->H; a.Wp = c->Wp; a.nrefs = c->nrefs; a.R = c->R;
+  a.lambda[0] = p->lambda_factor[0]; a.lambda[1] = p->lambda_factor[1]; a.lambda[2] = p->lambda_factor[2];
+  a.metric_h = p->metric_h; a.metric_q = p->metric_q; a.do_subpel = p->do_subpel; a.test8x8 = test8x8;
+  a.wp = apply_weights; a.denom = luma_log_weight_denom; a.jobs = jobs_dev; a.out = out_dev; a.njobs = njobs; a.errflag = c->d_errflag;
+  k_bipred<<<njobs, 128, 0, s>>>(a);
+  B2_CUDA_CHECK(c, cudaGetLastError());
+  c->launches++;
+  return B2ME_OK;
+}
+
+extern "C" int b2me_bipred_search(b2me_ctx *c, int njobs, const b2me_bipred_job *jobs, const b2me_search_params *p,
+                                  int apply_weights, int luma_log_weight_denom, int test8x8, b2me_bipred_result *out)
+{
+  int r = bipred_check(c, njobs, jobs, p, apply_weights, luma_log_weight_denom, test8x8, out);
+  if (r || !njobs) return r;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  b2me_bipred_job *dj = nullptr; b2me_bipred_result *dr = nullptr;
+  B2_CUDA_CHECK(c, cudaMallocAsync(&dj, sizeof(b2me_bipred_job) * njobs, c->stream));
+  B2_CUDA_CHECK(c, cudaMallocAsync(&dr, sizeof(b2me_bipred_result) * njobs, c->stream));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(dj, jobs, sizeof(b2me_bipred_job) * njobs, cudaMemcpyHostToDevice, c->stream));
+  r = b2me_bipred_search_dev(c, njobs, dj, p, apply_weights, luma_log_weight_denom, test8x8, dr, c->stream);
+  if (!r) {
+    cudaError_t e = cudaMemcpyAsync(out, dr, sizeof(b2me_bipred_result) * njobs, cudaMemcpyDeviceToHost, c->stream);
+    int flag = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "b2me_bipred_search: %s", cudaGetErrorString(e)); r = B2ME_ECUDA; }
+    else if (flag) {
+      cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream);
+      snprintf(c->err, sizeof(c->err), "b2me_bipred_search: a job is out of range (blocktype, reference slot, position, search range or a sub-pel centre)");
+      r = B2ME_EINVAL;
+    }
+  }
+  cudaFreeAsync(dj, c->stream); cudaFreeAsync(dr, c->stream);
+  return r;
+}

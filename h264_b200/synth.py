@@ -100,3 +100,35 @@ def yuv420_sequence(W, H, nframes, seed=20261018):
         v = (y[t][::2, ::2].astype(np.int32) // 4 + 96).astype(np.uint8)
         out += v.tobytes()
     return bytes(out)
+
+
+# b2me_bipred_job / b2me_bipred_result of include/b2me.h as numpy record types
+BIPRED_JOB = np.dtype([("min_mcost", np.int64), ("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.int16),
+                       ("ref1", np.int16), ("ref2", np.int16), ("search_range", np.int16),
+                       ("pred1", np.int16, 2), ("pred2", np.int16, 2), ("mv1", np.int16, 2), ("mv2", np.int16, 2),
+                       ("weight1", np.int16), ("weight2", np.int16), ("offset_bi", np.int16), ("reserved", np.int16)], align=True)
+BIPRED_RESULT = np.dtype([("cost_int", np.int64), ("cost_sub", np.int64), ("mv_int", np.int16, 2), ("mv_sub", np.int16, 2)], align=True)
+_BS = {1: (16, 16), 2: (16, 8), 3: (8, 16), 4: (8, 8), 5: (8, 4), 6: (4, 8), 7: (4, 4)}
+
+
+def bipred_jobs(W, H, nrefs, R, n, seed=1, weighted=False, blocktypes=(1, 2, 3, 4, 5, 6, 7), rmax=5):
+    """n seeded calls of the bi-predictive block search: blocks on their own grid anywhere in the picture (borders
+    included), the searched vector's centre integer-pel (BiPredBlockMotionSearch rounds it, mv_search.c:1079-1085),
+    the static vector of the other list at any quarter-pel, ranges 0..R, some calls with a finite incoming bound."""
+    rng = np.random.default_rng(seed)
+    j = np.zeros(n, BIPRED_JOB)
+    for i in range(n):
+        bt = int(rng.choice(blocktypes)); w, h = _BS[bt]
+        j[i]["blocktype"] = bt
+        j[i]["pos_x"] = w * rng.integers(0, W // w); j[i]["pos_y"] = h * rng.integers(0, H // h)
+        j[i]["ref1"] = rng.integers(0, nrefs); j[i]["ref2"] = rng.integers(0, nrefs)
+        j[i]["search_range"] = rng.integers(0, R + 1) if i % 3 else R
+        j[i]["pred1"] = rng.integers(-4 * rmax, 4 * rmax + 1, 2); j[i]["pred2"] = rng.integers(-4 * rmax, 4 * rmax + 1, 2)
+        j[i]["mv1"] = 4 * rng.integers(-rmax, rmax + 1, 2)
+        j[i]["mv2"] = rng.integers(-4 * rmax, 4 * rmax + 1, 2)
+        j[i]["min_mcost"] = (0x7fffffff << 5) if i % 4 else int(rng.integers(2000, 60000))
+        if weighted:
+            j[i]["weight1"] = rng.integers(10, 60); j[i]["weight2"] = rng.integers(10, 60); j[i]["offset_bi"] = rng.integers(-8, 9)
+        else:
+            j[i]["weight1"] = j[i]["weight2"] = 32
+    return j

@@ -13,6 +13,9 @@
  *           sub_pel_motion_estimation       JM/lencod/src/me_fullsearch.c:186-289
  *           computeSAD / computeSATD        JM/lencod/src/me_distortion.c:349-426 / 745-825
  *           (the per-call sequencing of BlockMotionSearch, JM/lencod/src/mv_search.c:960-976)
+ *   b2me_bipred_search
+ *        <- full_search_bipred_motion_estimation / sub_pel_bipred_motion_estimation  JM/lencod/src/me_fullsearch.c:112-176 / 300-399
+ *           computeBiPred{SAD,SSE,SATD}{1,2}   JM/lencod/src/me_distortion.c:525-737, 943-1182, 1353-1549
  *   b2me_set_ref (sub-pel plane build)
  *        <- getSubImagesLuma                JM/lencod/src/img_luma.c:611-680
  *   b2me_tq4x4
@@ -126,6 +129,38 @@ int b2me_block_search(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int re
 int b2me_block_subpel(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int ref_idx,
                       const int16_t pred_mv[2], const int16_t mv_in[2], const b2me_search_params *params,
                       int64_t min_mcost, int16_t mv_out[2], int64_t *cost_out);
+
+/* ---- bi-predictive block search (B slices) ------------------------------------------------- */
+/* One job = one call of full_search_bipred_motion_estimation (JM/lencod/src/me_fullsearch.c:112-176) followed, when
+ * params->do_subpel, by sub_pel_bipred_motion_estimation (:300-399), sequenced as BiPredBlockMotionSearch does
+ * (mv_search.c:1100-1126).  The distortions are computeBiPredSAD1 / SSE1 / SATD1 (me_distortion.c:525, 1353, 943) or,
+ * with apply_weights, computeBiPredSAD2 / SSE2 / SATD2 (:628, 1450, 1048); F_PEL metric = SAD, H_PEL / Q_PEL =
+ * params->metric_h / metric_q.  ref1 is the reference slot of the SEARCHED list (listX[list][ref]), ref2 the slot that
+ * holds listX[list ^ 1][0], whose block stays at mv2.  Slots are the ones b2me_set_ref fills (upload them unweighted:
+ * the bi-predictive weights are applied to the pair of samples, not to a plane). */
+typedef struct b2me_bipred_job {
+  int64_t min_mcost;          /* incoming bound (DISTBLK_MAX in the first refinement iteration) */
+  int16_t pos_x, pos_y;       /* luma position of the block */
+  int16_t blocktype;          /* 1..7 */
+  int16_t ref1, ref2;         /* reference slots */
+  int16_t search_range;       /* pel: (BiPredMESearchRange) >> iteration_no, <= the context's search_range */
+  int16_t pred1[2], pred2[2]; /* predictors of the two lists, quarter-pel */
+  int16_t mv1[2];             /* search centre of the searched list (relative MV, multiple of 4) */
+  int16_t mv2[2];             /* the other list's vector (relative MV, any quarter-pel) */
+  int16_t weight1, weight2, offset_bi;   /* MEBlock weight1 / weight2 / offsetBi (PrepareBiPredMEParams, mv_search.c:196-262);
+                                            read only with apply_weights */
+  int16_t reserved;
+} b2me_bipred_job;            /* 48 bytes */
+typedef struct b2me_bipred_result {
+  int64_t cost_int, cost_sub; /* returned motion costs of the two calls (cost_sub = cost_int when !do_subpel) */
+  int16_t mv_int[2], mv_sub[2];   /* mv1 after the integer search / after the sub-pel refinement */
+} b2me_bipred_result;         /* 24 bytes */
+/* test8x8: MEBlock test8x8 (8x8 Hadamard in SATD).  apply_weights && test8x8 with a SATD metric returns
+ * B2ME_EUNSUPPORTED: that branch of the reference reads past its source row (me_distortion.c:1167, SURVEY Q-J5). */
+int b2me_bipred_search(b2me_ctx *ctx, int njobs, const b2me_bipred_job *jobs, const b2me_search_params *params,
+                       int apply_weights, int luma_log_weight_denom, int test8x8, b2me_bipred_result *out);
+int b2me_bipred_search_dev(b2me_ctx *ctx, int njobs, const b2me_bipred_job *jobs_dev, const b2me_search_params *params,
+                           int apply_weights, int luma_log_weight_denom, int test8x8, b2me_bipred_result *out_dev, void *stream);
 
 /* ---- motion-compensated prediction (keeps the vectors on the device between search and transform) ---- */
 /* luma_prediction with p_dir == 0 (list 0), no weighting (JM/lencod/src/mc_prediction.c:144-236;

@@ -103,6 +103,15 @@ def hadamard8x8(diff):
     return orc_lib().orc_hadamard8x8(_ptr(d))
 
 
+# b2me_bipred_job / b2me_bipred_result (include/b2me.h)
+BIPRED_JOB = np.dtype([("min_mcost", np.int64), ("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.int16),
+                       ("ref1", np.int16), ("ref2", np.int16), ("search_range", np.int16),
+                       ("pred1", np.int16, 2), ("pred2", np.int16, 2), ("mv1", np.int16, 2), ("mv2", np.int16, 2),
+                       ("weight1", np.int16), ("weight2", np.int16), ("offset_bi", np.int16), ("reserved", np.int16)], align=True)
+BIPRED_RESULT = np.dtype([("cost_int", np.int64), ("cost_sub", np.int64), ("mv_int", np.int16, 2), ("mv_sub", np.int16, 2)], align=True)
+assert BIPRED_JOB.itemsize == 48 and BIPRED_RESULT.itemsize == 24
+
+
 class OrcFrame:
     """Restated oracle for one (current frame, reference frames) pair."""
 
@@ -135,6 +144,15 @@ class OrcFrame:
         orig = np.zeros((nmb * 16, 16), np.uint8); pred = np.zeros((nmb * 16, 16), np.uint8)
         self.L.orc_mc_luma(self.h, _ptr(mb_mode), _ptr(b8mode), _ptr(ref8), _ptr(mv), _ptr(orig), _ptr(pred))
         return orig, pred
+
+    def bipred_search(self, jobs, lam, metric_h=2, metric_q=2, do_subpel=True, test8x8=False, wp=False, log_denom=0):
+        """full_search_bipred (+ sub_pel_bipred) for an array of BIPRED_JOB; returns BIPRED_RESULT array"""
+        jobs = np.ascontiguousarray(jobs, BIPRED_JOB)
+        out = np.zeros(len(jobs), BIPRED_RESULT)
+        lam = np.ascontiguousarray(np.broadcast_to(np.asarray(lam), (3,)), np.int32)
+        self.L.orc_bipred_search(self.h, C.c_int(len(jobs)), _ptr(jobs), _ptr(lam), C.c_int(metric_h), C.c_int(metric_q),
+                                 C.c_int(int(do_subpel)), C.c_int(int(test8x8)), C.c_int(int(wp)), C.c_int(log_denom), _ptr(out))
+        return out
 
     def planes(self, r):
         Hp, Wp = self.H + 2 * PAD_Y, self.W + 2 * PAD_X
@@ -240,6 +258,15 @@ class JMRef:
     def hadamard8x8(self, diff):
         d = np.ascontiguousarray(diff, np.int16)
         return self.L.jmh_hadamard8x8(_ptr(d))
+
+    def bipred_search(self, jobs, lam, do_subpel=True, test8x8=False, wp=False, log_denom=0):
+        """the reference's full_search_bipred_motion_estimation (+ sub_pel_bipred_motion_estimation) per BIPRED_JOB"""
+        jobs = np.ascontiguousarray(jobs, BIPRED_JOB)
+        out = np.zeros(len(jobs), BIPRED_RESULT)
+        lam = np.ascontiguousarray(np.broadcast_to(np.asarray(lam), (3,)), np.int32)
+        self.L.jmh_bipred_search(self.h, C.c_int(len(jobs)), _ptr(jobs), _ptr(lam), C.c_int(int(do_subpel)), C.c_int(int(test8x8)),
+                                 C.c_int(int(wp)), C.c_int(log_denom), _ptr(out))
+        return out
 
     def search_frame(self, pred, center, lambda_factor, do_subpel=True, mb_first=0, mb_count=None):
         nmb = (self.W // 16) * (self.H // 16)

@@ -487,3 +487,113 @@ void orc_mc_luma(void *h, const uint8_t *mb_mode, const uint8_t *b8mode, const i
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------
+ * Bi-predictive search (B slices): distortion against the average of two reference blocks.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {            /* mirrors b2me_bipred_job (include/b2me.h) */
+  int64_t min_mcost;
+  int16_t pos_x, pos_y, blocktype, ref1, ref2, search_range;
+  int16_t pred1[2], pred2[2], mv1[2], mv2[2];
+  int16_t weight1, weight2, offset_bi, reserved;
+} OrcBiJob;
+typedef struct { int64_t cost_int, cost_sub; int16_t mv_int[2], mv_sub[2]; } OrcBiResult;
+
+/* the prediction sample of computeBiPred*1 (me_distortion.c:556: (r1 + r2 + 1) >> 1) and computeBiPred*2
+ * (:655-657: iClip1(max, ((w1*r1 + w2*r2 + 2*wp_luma_round) >> (denom+1)) + offsetBi)) */
+static inline int orc_bi_pel(int r1, int r2, int wp, int w1, int w2, int off, int denom)
+{
+  if (!wp) return (r1 + r2 + 1) >> 1;
+  { const int lround = 2 * (denom ? 1 << (denom - 1) : 0);
+    return clip1_255(((w1 * r1 + w2 * r2 + lround) >> (denom + 1)) + off); }
+}
+
+/* computeBiPredSAD1/2 (me_distortion.c:525-620, :628-737), computeBiPredSSE1/2 (:1353-1442, :1450-1549),
+ * computeBiPredSATD1/2 (:943-1040, :1048-1182), luma only, no early exit (result-neutral as in computeSAD).
+ * metric 0 SAD, 1 SSE, 2 SATD.  cand1/cand2 = absolute quarter-pel coordinates.  SAD/SSE clamp the block origin
+ * once per reference (:546-547); SATD clamps every 4x4 (8x8) tile origin (:971-972). */
+int orc_bipred_dist(const uint8_t *pl1, const uint8_t *pl2, int W, int H, const uint8_t *cur, int cur_stride,
+                    int bsx, int bsy, int c1x, int c1y, int c2x, int c2y, int metric, int test8x8,
+                    int wp, int w1, int w2, int off, int denom)
+{
+  const int Wp = W + 2 * PAD_X;
+  int x, y, s = 0;
+  if (metric != 2) {
+    const uint8_t *r1 = orc_umv_line4x(pl1, W, H, c1y, c1x), *r2 = orc_umv_line4x(pl2, W, H, c2y, c2x);
+    for (y = 0; y < bsy; y++)
+      for (x = 0; x < bsx; x++) {
+        const int d = (int)cur[y * cur_stride + x] - orc_bi_pel(r1[(size_t)y * Wp + x], r2[(size_t)y * Wp + x], wp, w1, w2, off, denom);
+        s += metric == 0 ? iabs_(d) : d * d;
+      }
+    return s;
+  }
+  { const int T = test8x8 ? 8 : 4; int bx, by, i, j; int16_t diff[64];
+    for (by = 0; by < bsy; by += T)
+      for (bx = 0; bx < bsx; bx += T) {
+        const uint8_t *r1 = orc_umv_line4x(pl1, W, H, c1y + (by << 2), c1x + (bx << 2));
+        const uint8_t *r2 = orc_umv_line4x(pl2, W, H, c2y + (by << 2), c2x + (bx << 2));
+        for (j = 0; j < T; j++)
+          for (i = 0; i < T; i++)
+            diff[j * T + i] = (int16_t)((int)cur[(by + j) * cur_stride + bx + i] -
+                                        orc_bi_pel(r1[(size_t)j * Wp + i], r2[(size_t)j * Wp + i], wp, w1, w2, off, denom));
+        s += test8x8 ? orc_hadamard8x8(diff) : orc_hadamard4x4(diff);
+      }
+  }
+  return s;
+}
+
+/* full_search_bipred_motion_estimation (me_fullsearch.c:112-176) followed, if do_subpel, by
+ * sub_pel_bipred_motion_estimation (:300-399) sequenced as BiPredBlockMotionSearch does (mv_search.c:1117-1126:
+ * the bound is reset to DISTBLK_MAX when the half-pel stage re-examines the centre).  F_PEL metric = SAD.
+ * lambda[3] = F, H, Q;  the weighted 8x8-Hadamard variant is not restated (reference bug Q-J5). */
+void orc_bipred_search(void *h, int njobs, const OrcBiJob *jobs, const int *lambda, int metric_h, int metric_q,
+                       int do_subpel, int test8x8, int wp, int denom, OrcBiResult *out)
+{
+  const OrcFrame *f = (const OrcFrame *)h;
+  int n;
+  for (n = 0; n < njobs; n++) {
+    const OrcBiJob *J = &jobs[n];
+    const int bsx = ORC_BS[J->blocktype][0], bsy = ORC_BS[J->blocktype][1];
+    const uint8_t *pl1 = orc_frame_planes(h, J->ref1), *pl2 = orc_frame_planes(h, J->ref2);
+    const uint8_t *cur = f->cur + (size_t)J->pos_y * f->W + J->pos_x;
+    const int ox = J->pos_x << 2, oy = J->pos_y << 2;
+    const int sr = J->search_range, max_pos = (2 * sr + 1) * (2 * sr + 1);
+    const int start_hp_cfg = (0 != metric_h) ? 0 : 1, start_qp = (metric_h != metric_q) ? 0 : 1;
+    int16_t mv1[2] = {J->mv1[0], J->mv1[1]};
+    int64_t min_mcost = J->min_mcost;
+    int pos, best_pos = 0;
+    const int64_t c2f = orc_mv_cost(lambda[0], J->mv2[0], J->mv2[1], J->pred2[0], J->pred2[1]);
+    for (pos = 0; pos < max_pos; pos++) {
+      const int cx = mv1[0] + 4 * f->spiral[2*pos], cy = mv1[1] + 4 * f->spiral[2*pos+1];
+      int64_t mcost = orc_mv_cost(lambda[0], cx, cy, J->pred1[0], J->pred1[1]) + c2f;
+      if (mcost >= min_mcost) continue;
+      mcost += ((int64_t)orc_bipred_dist(pl1, pl2, f->W, f->H, cur, f->W, bsx, bsy, ox + cx, oy + cy, ox + J->mv2[0], oy + J->mv2[1],
+                                         0, test8x8, wp, J->weight1, J->weight2, J->offset_bi, denom)) << 5;
+      if (mcost < min_mcost) { best_pos = pos; min_mcost = mcost; }
+    }
+    if (best_pos) { mv1[0] = (int16_t)(mv1[0] + 4 * f->spiral[2*best_pos]); mv1[1] = (int16_t)(mv1[1] + 4 * f->spiral[2*best_pos+1]); }
+    out[n].mv_int[0] = mv1[0]; out[n].mv_int[1] = mv1[1]; out[n].cost_int = min_mcost;
+    out[n].mv_sub[0] = mv1[0]; out[n].mv_sub[1] = mv1[1]; out[n].cost_sub = min_mcost;
+    if (!do_subpel) continue;
+    if (!start_hp_cfg) min_mcost = DISTBLK_MAX_ORC;                      /* mv_search.c:1119-1120 */
+    {
+      int stage;
+      for (stage = 0; stage < 2; stage++) {
+        const int lam = lambda[1 + stage], metric = stage ? metric_q : metric_h, step = stage ? 1 : 2;
+        const int64_t c2 = orc_mv_cost(lam, J->mv2[0], J->mv2[1], J->pred2[0], J->pred2[1]);
+        int start = stage ? start_qp : ((min_mcost == DISTBLK_MAX_ORC) ? 0 : start_hp_cfg);
+        if (stage && !start_qp) min_mcost = DISTBLK_MAX_ORC;             /* me_fullsearch.c:364-365 */
+        for (best_pos = 0, pos = start; pos < 9; pos++) {
+          const int cx = mv1[0] + step * f->spiral[2*pos], cy = mv1[1] + step * f->spiral[2*pos+1];
+          int64_t mcost = orc_mv_cost(lam, cx, cy, J->pred1[0], J->pred1[1]) + c2;
+          if (mcost >= min_mcost) continue;
+          mcost += ((int64_t)orc_bipred_dist(pl1, pl2, f->W, f->H, cur, f->W, bsx, bsy, ox + cx, oy + cy, ox + J->mv2[0], oy + J->mv2[1],
+                                             metric, test8x8, wp, J->weight1, J->weight2, J->offset_bi, denom)) << 5;
+          if (mcost < min_mcost) { min_mcost = mcost; best_pos = pos; }
+        }
+        if (best_pos) { mv1[0] = (int16_t)(mv1[0] + step * f->spiral[2*best_pos]); mv1[1] = (int16_t)(mv1[1] + step * f->spiral[2*best_pos+1]); }
+      }
+    }
+    out[n].mv_sub[0] = mv1[0]; out[n].mv_sub[1] = mv1[1]; out[n].cost_sub = min_mcost;
+  }
+}

@@ -277,3 +277,53 @@ long long jmh_distortion(int kind, int n, short *diff)
 }
 int jmh_hadamard4x4(short *diff) { return HadamardSAD4x4(diff); }
 int jmh_hadamard8x8(short *diff) { return HadamardSAD8x8(diff); }
+
+/* Bi-predictive search: the reference's full_search_bipred_motion_estimation (me_fullsearch.c:112) followed by
+ * sub_pel_bipred_motion_estimation (:300), sequenced as BiPredBlockMotionSearch does (mv_search.c:1100-1126).
+ * ref1 = searched picture (listX[list][ref]), ref2 = the static one (listX[list ^ 1][0]); the MEBlock carries the
+ * weights PrepareBiPredMEParams (mv_search.c:196-262) would set.  job/result layouts = b2me_bipred_job / _result. */
+typedef struct {
+  long long min_mcost;
+  short pos_x, pos_y, blocktype, ref1, ref2, search_range;
+  short pred1[2], pred2[2], mv1[2], mv2[2];
+  short weight1, weight2, offset_bi, reserved;
+} JmhBiJob;
+typedef struct { long long cost_int, cost_sub; short mv_int[2], mv_sub[2]; } JmhBiResult;
+
+void jmh_bipred_search(void *hh, int njobs, const JmhBiJob *jobs, const int *lambda_factor, int do_subpel, int test8x8,
+                       int wp, int log_denom, JmhBiResult *out)
+{
+  JMH *h = (JMH *)hh; int n;
+  StorablePicture *l0[2], *l1[2];
+  StorablePicture **save0 = h->slice->listX[0], **save1 = h->slice->listX[1];
+  l0[1] = l1[1] = NULL;
+  h->slice->luma_log_weight_denom = (short)log_denom;
+  h->slice->wp_luma_round = log_denom ? 1 << (log_denom - 1) : 0;
+  if (!h->p_Vid->mb_data) h->p_Vid->mb_data = (Macroblock *)calloc(1, sizeof(Macroblock));   /* sub_pel_bipred reads mb_data[mbAddrX].list_offset */
+  for (n = 0; n < njobs; n++) {
+    const JmhBiJob *J = &jobs[n];
+    MEBlock b; imgpel orig[256]; MotionVector p1, p2, m1, m2; distblk c; int lam[3];
+    jmh_setup_block(h, &b, orig, J->pos_x, J->pos_y, J->blocktype, 0);
+    b.test8x8 = test8x8; b.ref_idx = 0;
+    l0[0] = h->refs[J->ref1]; l1[0] = h->refs[J->ref2];
+    h->slice->listX[0] = l0; h->slice->listX[1] = l1;
+    b.apply_weights = wp;
+    b.computeBiPredFPel = wp ? h->p_Vid->computeBiPred2[F_PEL] : h->p_Vid->computeBiPred1[F_PEL];   /* init_mv_block, mv_search.c:752-768 */
+    b.computeBiPredHPel = wp ? h->p_Vid->computeBiPred2[H_PEL] : h->p_Vid->computeBiPred1[H_PEL];
+    b.computeBiPredQPel = wp ? h->p_Vid->computeBiPred2[Q_PEL] : h->p_Vid->computeBiPred1[Q_PEL];
+    b.weight1 = J->weight1; b.weight2 = J->weight2; b.offsetBi = J->offset_bi;
+    p1.mv_x = J->pred1[0]; p1.mv_y = J->pred1[1]; p2.mv_x = J->pred2[0]; p2.mv_y = J->pred2[1];
+    m1.mv_x = J->mv1[0]; m1.mv_y = J->mv1[1]; m2.mv_x = J->mv2[0]; m2.mv_y = J->mv2[1];
+    lam[0] = lambda_factor[0]; lam[1] = lambda_factor[1]; lam[2] = lambda_factor[2];
+    c = full_search_bipred_motion_estimation(&h->mb, 0, &p1, &p2, &m1, &m2, &b, J->search_range << 2, (distblk)J->min_mcost, lam[F_PEL]);
+    out[n].mv_int[0] = m1.mv_x; out[n].mv_int[1] = m1.mv_y; out[n].cost_int = (long long)c;
+    out[n].mv_sub[0] = m1.mv_x; out[n].mv_sub[1] = m1.mv_y; out[n].cost_sub = (long long)c;
+    if (do_subpel) {
+      if (!h->p_Vid->start_me_refinement_hp) c = DISTBLK_MAX;   /* mv_search.c:1119-1120 */
+      c = sub_pel_bipred_motion_estimation(&h->mb, &b, 0, &p1, &p2, &m1, &m2, c, lam);
+      out[n].mv_sub[0] = m1.mv_x; out[n].mv_sub[1] = m1.mv_y; out[n].cost_sub = (long long)c;
+    }
+    free(b.orig_pic);
+  }
+  h->slice->listX[0] = save0; h->slice->listX[1] = save1;
+}

@@ -1,0 +1,75 @@
+"""GPU parity tests (through the C ABI): bi-predictive block search (b2me_bipred_search) against the golden vectors
+captured from the unmodified JM (full_search_bipred_motion_estimation + sub_pel_bipred_motion_estimation with
+computeBiPred{SAD,SSE,SATD}{1,2}) and against the oracle on other seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from h264_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _flat(r):
+    return np.concatenate([r["cost_int"][:, None], r["cost_sub"][:, None], r["mv_int"], r["mv_sub"]], axis=1)
+
+
+def _searcher(cur, refs, R):
+    H, W = cur.shape
+    s = api.Searcher(W, H, len(refs), R)
+    s.set_cur(cur)
+    for r in range(len(refs)):
+        s.set_ref(r, refs[r])
+    return s
+
+
+def test_bipred_matches_reference_golden(golden_dir):
+    from oracle import gen_golden_bipred as gb
+    g = np.load(os.path.join(golden_dir, "jm_bipred.npz"))
+    cur, refs = gb.frames()
+    s = _searcher(cur, refs, gb.R)
+    for k, (mh, mq, wp, t8) in enumerate(g["cases"]):
+        jobs = gb.jobs_of(k, wp, t8)
+        got = s.bipred_search(jobs, api.make_params(gb.LAM, metric_h=int(mh), metric_q=int(mq)), apply_weights=bool(wp),
+                              log_denom=gb.DENOM, test8x8=bool(t8))
+        bad = np.nonzero((_flat(got) != g[f"c{k}"]).any(1))[0]
+        assert len(bad) == 0, ((mh, mq, wp, t8), jobs[bad[:2]], _flat(got)[bad[:2]], g[f"c{k}"][bad[:2]])
+
+
+@pytest.mark.parametrize("W,H,R,NR,lam", [(64, 48, 16, 2, (40, 30, 30)), (176, 144, 32, 3, (700, 500, 400))])
+def test_bipred_matches_oracle(W, H, R, NR, lam):
+    fr = synth.luma_sequence(W, H, NR + 1, seed=W + R)
+    cur, refs = fr[NR], fr[list(range(NR - 1, -1, -1))]
+    s = _searcher(cur, refs, R)
+    of = oracle.OrcFrame(cur, refs, R)
+    for wp in (False, True):
+        jobs = synth.bipred_jobs(W, H, NR, R, 64, seed=3 + wp, weighted=wp, rmax=9)
+        for mh, mq in ((2, 2), (0, 2)):
+            got = s.bipred_search(jobs, api.make_params(lam, metric_h=mh, metric_q=mq), apply_weights=wp, log_denom=5)
+            exp = of.bipred_search(jobs, lam, metric_h=mh, metric_q=mq, wp=wp, log_denom=5)
+            assert (_flat(got) == _flat(exp)).all(), (wp, mh, mq)
+        got = s.bipred_search(jobs, api.make_params(lam, do_subpel=False), apply_weights=wp, log_denom=5)
+        exp = of.bipred_search(jobs, lam, do_subpel=False, wp=wp, log_denom=5)
+        assert (_flat(got) == _flat(exp)).all()
+
+
+def test_bipred_error_codes():
+    W, H, R = 64, 48, 8
+    fr = synth.luma_sequence(W, H, 2, seed=1)
+    s = _searcher(fr[1], fr[[0]], R)
+    p = api.make_params((100, 100, 100))
+    jobs = synth.bipred_jobs(W, H, 1, R, 4, seed=1)
+    assert len(s.bipred_search(jobs[:0], p)) == 0                      # empty batch
+    with pytest.raises(api.B2Error):                                   # weighted SATD with the 8x8 Hadamard (Q-J5)
+        s.bipred_search(jobs, p, apply_weights=True, log_denom=5, test8x8=True)
+    bad = jobs.copy(); bad[1]["ref2"] = 3
+    with pytest.raises(api.B2Error):
+        s.bipred_search(bad, p)
+    bad = jobs.copy(); bad[2]["mv1"] = (5, 0)                          # sub-pel centre is not an integer-search input
+    with pytest.raises(api.B2Error):
+        s.bipred_search(bad, p)
+    got = s.bipred_search(jobs, p)                                     # the context is still usable
+    exp = oracle.OrcFrame(fr[1], fr[[0]], R).bipred_search(jobs, (100, 100, 100))
+    assert (_flat(got) == _flat(exp)).all()

@@ -176,3 +176,41 @@ def test_mc_luma_restatement_is_the_distortions_block():
                 bt, ox, oy, w, h = oracle.partition_geometry()[p]
                 blocks = [by * 4 + bx for by in range(oy // 4, (oy + h) // 4) for bx in range(ox // 4, (ox + w) // 4)]
                 assert sad4[m, blocks].sum() << 5 == cost_int[m, 0, p], (mode, m, p)
+
+
+def _bipred_cases(golden_dir):
+    from oracle import gen_golden_bipred as gb
+    g = np.load(os.path.join(golden_dir, "jm_bipred.npz"))
+    cur, refs = gb.frames()
+    for k, (mh, mq, wp, t8) in enumerate(g["cases"]):
+        yield gb, cur, refs, gb.jobs_of(k, wp, t8), int(mh), int(mq), bool(wp), bool(t8), g[f"c{k}"]
+
+
+def test_bipred_oracle_reproduces_reference_golden(golden_dir):
+    """full_search_bipred + sub_pel_bipred with computeBiPred{SAD,SSE,SATD}{1,2}: vectors captured from the unmodified JM"""
+    n = 0
+    for gb, cur, refs, jobs, mh, mq, wp, t8, exp in _bipred_cases(golden_dir):
+        of = oracle.OrcFrame(cur, refs, gb.R)
+        r = of.bipred_search(jobs, gb.LAM, metric_h=mh, metric_q=mq, test8x8=t8, wp=wp, log_denom=gb.DENOM)
+        got = np.concatenate([r["cost_int"][:, None], r["cost_sub"][:, None], r["mv_int"], r["mv_sub"]], axis=1)
+        assert (got == exp).all(), (mh, mq, wp, t8)
+        n += len(jobs)
+    assert n >= 14 * 48
+
+
+@pytest.mark.skipif(not oracle.have_jmref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_bipred_oracle_equals_live_reference():
+    W, H, R, NR = 64, 48, 6, 2
+    fr = synth.luma_sequence(W, H, NR + 1, seed=17)
+    cur, refs = fr[NR], fr[[1, 0]]
+    of = oracle.OrcFrame(cur, refs, R)
+    for metric in ((0, 2, 2), (0, 0, 0)):
+        jm = oracle.JMRef(W, H, R, NR, metric=metric)
+        jm.set_cur(cur)
+        for r in range(NR):
+            jm.set_ref(r, refs[r])
+        for wp in (False, True):
+            jobs = synth.bipred_jobs(W, H, NR, R, 40, seed=9 + wp, weighted=wp)
+            a = jm.bipred_search(jobs, (90, 80, 70), wp=wp, log_denom=6)
+            b = of.bipred_search(jobs, (90, 80, 70), metric_h=metric[1], metric_q=metric[2], wp=wp, log_denom=6)
+            assert (a == b).all()
