@@ -172,6 +172,15 @@ class Searcher:
                                             C.c_int(log_denom), C.c_int(int(test8x8)), _p(out)), "b2me_bipred_search")
         return out
 
+    def distortion_candidates(self, cands, metric, test8x8=False):
+        """computeSAD / SSE / SATD (<< 5) of synth.CANDIDATE records; int64 array"""
+        from . import synth
+        cands = np.ascontiguousarray(cands, synth.CANDIDATE)
+        out = np.zeros(len(cands), np.int64)
+        self._chk(self.L.b2me_distortion_candidates(self.h, C.c_int(metric), C.c_int(int(test8x8)), C.c_int(len(cands)), _p(cands), _p(out)),
+                  "b2me_distortion_candidates")
+        return out
+
     def block_search(self, pos_x, pos_y, blocktype, ref, pred_mv, center_mv, params, search_range):
         pm = (C.c_int16 * 2)(int(pred_mv[0]), int(pred_mv[1]))
         cm = (C.c_int16 * 2)(int(center_mv[0]), int(center_mv[1]))

@@ -205,9 +205,114 @@ __global__ void __launch_bounds__(128) k_bipred(const BiArgs a)
   if (tid == 0) { O->mv_sub[0] = (int16_t)mv1[0]; O->mv_sub[1] = (int16_t)mv1[1]; O->cost_sub = bound; }
 }
 
+// ---- distortion of a list of (block, reference, candidate) triples ---------------------------------------------
+// computeSAD / computeSSE / computeSATD (me_distortion.c:349-426, 1190-1255, 745-825) at their own boundary
+// (mv_block->computePredFPel / HPel / QPel): what a search whose control flow stays on the host (EPZS, UMHex) asks
+// for per predictor set.  One warp per candidate; the value is the reference's return without early exit,
+// dist_scale(distortion) = distortion << 5, no motion-vector cost.
+struct CandArgs {
+  const uint8_t *cur; int cur_pitch;
+  const uint8_t *planes; size_t plane_size;
+  int W, H, Wp, nrefs, metric, test8x8, n;
+  const b2me_candidate *cands; long long *out; int *errflag;
+};
+
+__global__ void __launch_bounds__(128) k_cand_dist(const CandArgs a)
+{
+  const int lane = threadIdx.x & 31, i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= a.n) return;
+  const b2me_candidate c = a.cands[i];
+  if (c.blocktype < 1 || c.blocktype > 7 || c.ref < 0 || c.ref >= a.nrefs || c.pos_x < 0 || c.pos_y < 0 || c.pos_x >= a.W || c.pos_y >= a.H) {
+    if (lane == 0) { *a.errflag = 1; a.out[i] = -1; }
+    return;
+  }
+  const PartGeom gm = part_geom(part_first(c.blocktype));
+  const int bsx = gm.w, bsy = gm.h;
+  const uint8_t *cur = a.cur + (size_t)c.pos_y * a.cur_pitch + c.pos_x;
+  const int qx = (c.pos_x << 2) + c.mv[0], qy = (c.pos_y << 2) + c.mv[1];
+  BiArgs u; u.planes = a.planes; u.plane_size = a.plane_size; u.W = a.W; u.H = a.H; u.Wp = a.Wp;
+  int s = 0;
+  if (a.metric != 2) {
+    const uint8_t *r = bi_umv(u, c.ref, qx, qy);
+    for (int k = lane; k < bsx * bsy; k += 32) {
+      const int x = k % bsx, y = k / bsx;
+      const int d = (int)cur[(size_t)y * a.cur_pitch + x] - (int)r[(size_t)y * a.Wp + x];
+      s += a.metric == 0 ? abs(d) : d * d;
+    }
+  } else if (!a.test8x8) {
+    const int tw = bsx >> 2, nt = tw * (bsy >> 2);
+    if (lane < nt) {
+      const int bx = (lane % tw) * 4, by = (lane / tw) * 4;
+      const uint8_t *r = bi_umv(u, c.ref, qx + (bx << 2), qy + (by << 2));
+      int d[16];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[j * 4 + k] = (int)cur[(size_t)(by + j) * a.cur_pitch + bx + k] - (int)r[(size_t)j * a.Wp + k];
+      s = bi_had4(d);
+    }
+  } else {
+    const int tw = bsx >> 3, nt = tw * (bsy >> 3);
+    if (lane < nt) {
+      const int bx = (lane % tw) * 8, by = (lane / tw) * 8;
+      const uint8_t *r = bi_umv(u, c.ref, qx + (bx << 2), qy + (by << 2));
+      short d[64];
+      for (int j = 0; j < 8; j++)
+        for (int k = 0; k < 8; k++) d[j * 8 + k] = (short)((int)cur[(size_t)(by + j) * a.cur_pitch + bx + k] - (int)r[(size_t)j * a.Wp + k]);
+      s = bi_had8(d);
+    }
+  }
+  s = __reduce_add_sync(0xffffffffu, s);
+  if (lane == 0) a.out[i] = (long long)s << 5;
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2me_distortion_candidates_dev(b2me_ctx *c, int metric, int test8x8, int n, const b2me_candidate *cands_dev,
+                                              int64_t *out_dev, void *stream)
+{
+  if (!c || n < 0 || (n && (!cands_dev || !out_dev)) || metric < 0 || metric > 2) return B2ME_EINVAL;
+  if (!n) return B2ME_OK;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->planes_pending && s != c->stream) B2_CUDA_CHECK(c, cudaStreamWaitEvent(s, c->ev_planes, 0));
+  CandArgs a;
+  a.cur = c->d_cur; a.cur_pitch = c->W; a.planes = c->d_planes; a.plane_size = c->plane_size;
+  a.W = c->W; a.H = c->H; a.Wp = c->Wp; a.nrefs = c->nrefs; a.metric = metric; a.test8x8 = test8x8; a.n = n;
+  a.cands = cands_dev; a.out = reinterpret_cast<long long *>(out_dev); a.errflag = c->d_errflag;
+  k_cand_dist<<<(n + 3) / 4, 128, 0, s>>>(a);
+  B2_CUDA_CHECK(c, cudaGetLastError());
+  c->launches++;
+  return B2ME_OK;
+}
+
+extern "C" int b2me_distortion_candidates(b2me_ctx *c, int metric, int test8x8, int n, const b2me_candidate *cands, int64_t *out)
+{
+  if (!c || n < 0 || (n && (!cands || !out)) || metric < 0 || metric > 2) return B2ME_EINVAL;
+  if (!n) return B2ME_OK;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  b2me_candidate *dc = nullptr; int64_t *dout = nullptr;
+  B2_CUDA_CHECK(c, cudaMallocAsync(&dc, sizeof(b2me_candidate) * n, c->stream));
+  B2_CUDA_CHECK(c, cudaMallocAsync(&dout, sizeof(int64_t) * n, c->stream));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(dc, cands, sizeof(b2me_candidate) * n, cudaMemcpyHostToDevice, c->stream));
+  int r = b2me_distortion_candidates_dev(c, metric, test8x8, n, dc, dout, c->stream);
+  if (!r) {
+    cudaError_t e = cudaMemcpyAsync(out, dout, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, c->stream);
+    int flag = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "b2me_distortion_candidates: %s", cudaGetErrorString(e)); r = B2ME_ECUDA; }
+    else if (flag) {
+      cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream);
+      snprintf(c->err, sizeof(c->err), "b2me_distortion_candidates: a candidate is out of range (blocktype, reference slot or position)");
+      r = B2ME_EINVAL;
+    }
+  }
+  cudaFreeAsync(dc, c->stream); cudaFreeAsync(dout, c->stream);
+  return r;
+}
 
 static int bipred_check(b2me_ctx *c, int njobs, const void *jobs, const b2me_search_params *p, int apply_weights, int denom, int test8x8, const void *out)
 {

@@ -108,6 +108,7 @@ BIPRED_JOB = np.dtype([("min_mcost", np.int64), ("pos_x", np.int16), ("pos_y", n
                        ("pred1", np.int16, 2), ("pred2", np.int16, 2), ("mv1", np.int16, 2), ("mv2", np.int16, 2),
                        ("weight1", np.int16), ("weight2", np.int16), ("offset_bi", np.int16), ("reserved", np.int16)], align=True)
 BIPRED_RESULT = np.dtype([("cost_int", np.int64), ("cost_sub", np.int64), ("mv_int", np.int16, 2), ("mv_sub", np.int16, 2)], align=True)
+CANDIDATE = np.dtype([("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.int16), ("ref", np.int16), ("mv", np.int16, 2)])
 _BS = {1: (16, 16), 2: (16, 8), 3: (8, 16), 4: (8, 8), 5: (8, 4), 6: (4, 8), 7: (4, 4)}
 
 
@@ -132,3 +133,16 @@ def bipred_jobs(W, H, nrefs, R, n, seed=1, weighted=False, blocktypes=(1, 2, 3, 
         else:
             j[i]["weight1"] = j[i]["weight2"] = 32
     return j
+
+
+def candidates(W, H, nrefs, n, seed=1, blocktypes=(1, 2, 3, 4, 5, 6, 7), reach=40):
+    """n seeded (block, reference, vector) triples, vectors up to +-reach pel at any quarter-pel (beyond the pad too)"""
+    rng = np.random.default_rng(seed)
+    c = np.zeros(n, CANDIDATE)
+    for i in range(n):
+        bt = int(rng.choice(blocktypes)); w, h = _BS[bt]
+        c[i]["blocktype"] = bt
+        c[i]["pos_x"] = w * rng.integers(0, W // w); c[i]["pos_y"] = h * rng.integers(0, H // h)
+        c[i]["ref"] = rng.integers(0, nrefs)
+        c[i]["mv"] = rng.integers(-4 * reach, 4 * reach + 1, 2)
+    return c

@@ -162,6 +162,23 @@ int b2me_bipred_search(b2me_ctx *ctx, int njobs, const b2me_bipred_job *jobs, co
 int b2me_bipred_search_dev(b2me_ctx *ctx, int njobs, const b2me_bipred_job *jobs_dev, const b2me_search_params *params,
                            int apply_weights, int luma_log_weight_denom, int test8x8, b2me_bipred_result *out_dev, void *stream);
 
+/* ---- distortion at explicit candidates (the computeSAD family at its own boundary) ---------------------------- */
+/* computeSAD / computeSSE / computeSATD (JM/lencod/src/me_distortion.c:349-426, 1190-1255, 745-825; the WP variants
+ * when the slot was uploaded with b2me_set_ref_weights) for n independent (block, reference slot, vector) triples:
+ * what mv_block->computePredFPel / HPel / QPel (JM/lencod/inc/global.h:316-318) return for `cand = block position +
+ * mv` with min_mcost = DISTBLK_MAX, i.e. dist_scale(distortion) = distortion << 5, no motion-vector cost.  For searches
+ * whose control flow stays in the reference's C (EPZS_motion_estimation, me_epzs.c:54; UMHEX): one call per predictor
+ * set or refinement pattern.  metric 0 SAD, 1 SSE, 2 SATD; test8x8: 8x8 Hadamard (blocktypes 1..4). */
+typedef struct b2me_candidate {
+  int16_t pos_x, pos_y;       /* luma position of the block */
+  int16_t blocktype;          /* 1..7 */
+  int16_t ref;                /* reference slot */
+  int16_t mv[2];              /* vector relative to the block position, quarter-pel */
+} b2me_candidate;             /* 12 bytes */
+int b2me_distortion_candidates(b2me_ctx *ctx, int metric, int test8x8, int n, const b2me_candidate *cands, int64_t *out);
+int b2me_distortion_candidates_dev(b2me_ctx *ctx, int metric, int test8x8, int n, const b2me_candidate *cands_dev,
+                                   int64_t *out_dev, void *stream);
+
 /* ---- motion-compensated prediction (keeps the vectors on the device between search and transform) ---- */
 /* luma_prediction with p_dir == 0 (list 0), no weighting (JM/lencod/src/mc_prediction.c:144-236;
  * OneComponentLumaPrediction :117-136) for every macroblock of the picture, from a search result array.

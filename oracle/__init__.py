@@ -154,6 +154,14 @@ class OrcFrame:
                                  C.c_int(int(do_subpel)), C.c_int(int(test8x8)), C.c_int(int(wp)), C.c_int(log_denom), _ptr(out))
         return out
 
+    def distortion_candidates(self, cands, metric, test8x8=False):
+        """computeSAD / SSE / SATD (<< 5) at explicit (block, ref, vector) records (h264_b200.synth.CANDIDATE layout)"""
+        cands = np.ascontiguousarray(cands)
+        assert cands.dtype.itemsize == 12
+        out = np.zeros(len(cands), np.int64)
+        self.L.orc_distortion_candidates(self.h, C.c_int(metric), C.c_int(int(test8x8)), C.c_int(len(cands)), _ptr(cands), _ptr(out))
+        return out
+
     def planes(self, r):
         Hp, Wp = self.H + 2 * PAD_Y, self.W + 2 * PAD_X
         p = self.L.orc_frame_planes(self.h, C.c_int(r))

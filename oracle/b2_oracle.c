@@ -597,3 +597,19 @@ void orc_bipred_search(void *h, int njobs, const OrcBiJob *jobs, const int *lamb
     out[n].mv_sub[0] = mv1[0]; out[n].mv_sub[1] = mv1[1]; out[n].cost_sub = min_mcost;
   }
 }
+
+/* computeSAD / computeSSE / computeSATD at explicit candidates (mirrors b2me_distortion_candidates): out = distortion << 5 */
+typedef struct { int16_t pos_x, pos_y, blocktype, ref, mv[2]; } OrcCand;
+void orc_distortion_candidates(void *h, int metric, int test8x8, int n, const OrcCand *c, int64_t *out)
+{
+  const OrcFrame *f = (const OrcFrame *)h; int i;
+  for (i = 0; i < n; i++) {
+    const int bsx = ORC_BS[c[i].blocktype][0], bsy = ORC_BS[c[i].blocktype][1];
+    const uint8_t *pl = orc_frame_planes(h, c[i].ref), *cur = f->cur + (size_t)c[i].pos_y * f->W + c[i].pos_x;
+    const int qx = (c[i].pos_x << 2) + c[i].mv[0], qy = (c[i].pos_y << 2) + c[i].mv[1];
+    const int d = metric == 2 ? orc_satd(pl, f->W, f->H, cur, f->W, bsx, bsy, qx, qy, test8x8)
+                : metric == 1 ? orc_sse(pl, f->W, f->H, cur, f->W, bsx, bsy, qx, qy)
+                              : orc_sad(pl, f->W, f->H, cur, f->W, bsx, bsy, qx, qy);
+    out[i] = ((int64_t)d) << 5;
+  }
+}

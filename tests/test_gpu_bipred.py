@@ -73,3 +73,26 @@ def test_bipred_error_codes():
     got = s.bipred_search(jobs, p)                                     # the context is still usable
     exp = oracle.OrcFrame(fr[1], fr[[0]], R).bipred_search(jobs, (100, 100, 100))
     assert (_flat(got) == _flat(exp)).all()
+
+
+def test_candidate_distortions_match_oracle():
+    """b2me_distortion_candidates: computeSAD / SSE / SATD (4x4 and 8x8 Hadamard) at arbitrary candidates, weighted slot too"""
+    W, H, NR = 176, 144, 3
+    fr = synth.luma_sequence(W, H, NR + 1, seed=31)
+    cur, refs = fr[NR], fr[[2, 1, 0]]
+    s = api.Searcher(W, H, NR, 16)
+    s.set_cur(cur)
+    s.set_ref_weights(1, 40, -3, 5)
+    for r in range(NR):
+        s.set_ref(r, refs[r])
+    of = oracle.OrcFrame(cur, refs, 16)
+    of.set_weights(1, 40, -3, 5)
+    c = synth.candidates(W, H, NR, 3000, seed=4)
+    for metric in (0, 1, 2):
+        assert (s.distortion_candidates(c, metric) == of.distortion_candidates(c, metric)).all(), metric
+    c8 = synth.candidates(W, H, NR, 1000, seed=5, blocktypes=(1, 2, 3, 4))
+    assert (s.distortion_candidates(c8, 2, test8x8=True) == of.distortion_candidates(c8, 2, test8x8=True)).all()
+    assert len(s.distortion_candidates(c[:0], 0)) == 0
+    bad = c[:8].copy(); bad[3]["blocktype"] = 9
+    with pytest.raises(api.B2Error):
+        s.distortion_candidates(bad, 0)

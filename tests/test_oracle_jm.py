@@ -214,3 +214,27 @@ def test_bipred_oracle_equals_live_reference():
             a = jm.bipred_search(jobs, (90, 80, 70), wp=wp, log_denom=6)
             b = of.bipred_search(jobs, (90, 80, 70), metric_h=metric[1], metric_q=metric[2], wp=wp, log_denom=6)
             assert (a == b).all()
+
+
+@pytest.mark.skipif(not oracle.have_jmref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_candidate_distortions_equal_live_reference():
+    """computeSAD / computeSATD of the unmodified JM at arbitrary quarter-pel candidates (beyond the pad too)"""
+    W, H, NR = 64, 48, 2
+    fr = synth.luma_sequence(W, H, NR + 1, seed=23)
+    cur, refs = fr[NR], fr[[1, 0]]
+    of = oracle.OrcFrame(cur, refs, 4)
+    jm = oracle.JMRef(W, H, 4, NR)
+    jm.set_cur(cur)
+    for r in range(NR):
+        jm.set_ref(r, refs[r])
+    c = synth.candidates(W, H, NR, 150, seed=2)
+    sad, satd = of.distortion_candidates(c, 0), of.distortion_candidates(c, 2)
+    c8 = synth.candidates(W, H, NR, 60, seed=3, blocktypes=(1, 2, 3, 4))
+    satd8 = of.distortion_candidates(c8, 2, test8x8=True)
+    for i, k in enumerate(c):
+        q = (int(k["pos_x"]) * 4 + int(k["mv"][0]), int(k["pos_y"]) * 4 + int(k["mv"][1]))
+        assert jm.sad(int(k["pos_x"]), int(k["pos_y"]), int(k["blocktype"]), int(k["ref"]), *q) == sad[i]
+        assert jm.satd(int(k["pos_x"]), int(k["pos_y"]), int(k["blocktype"]), int(k["ref"]), *q) == satd[i]
+    for i, k in enumerate(c8):
+        q = (int(k["pos_x"]) * 4 + int(k["mv"][0]), int(k["pos_y"]) * 4 + int(k["mv"][1]))
+        assert jm.satd(int(k["pos_x"]), int(k["pos_y"]), int(k["blocktype"]), int(k["ref"]), *q, test8x8=1) == satd8[i]
