@@ -357,11 +357,35 @@ class V1Ref:
                 xy[mb, p], so[mb, p], rms[mb, p] = a, b, r
         return xy, so, rms
 
+    def reset_trans(self):
+        """fresh TRANS_NODE trees (call between components: the harness indexes one tree array by macroblock number)"""
+        self.L.v1h_reset_trans()
+
     def encode_mb(self, mb, con):
         out = np.zeros((21, 5), np.int32)
         outd = np.zeros((21, 2), np.float64)
         n = self.L.v1h_encode_mb(C.c_int(mb), C.c_int(con), _ptr(out), _ptr(outd), C.c_int(21))
         return out[:n], outd[:n]
+
+
+V1_NODE = np.dtype([("block_type", np.int32), ("partition", np.int32), ("reference", np.int32), ("x", np.int32), ("y", np.int32),
+                    ("pad", np.int32), ("scale", np.float64), ("offset", np.float64)])     # = b2fr_node (include/b2me.h)
+assert V1_NODE.itemsize == 40
+
+
+def v1_encode_plane(org, refC, xy, so, rms, tol):
+    """F5: the partition cascade of every macroblock of one component plane from the search results of the four
+    plane sets (xy/so [4][nmb][41][2], rms [4][nmb][41]); returns V1_NODE [nmb][21] (pre-order)."""
+    org = np.ascontiguousarray(org, np.uint8); refC = np.ascontiguousarray(refC, np.uint8)
+    h, w = org.shape
+    mbw, mbh = w // 16, h // 16
+    xy = np.ascontiguousarray(xy, np.int32); so = np.ascontiguousarray(so, np.float64); rms = np.ascontiguousarray(rms, np.float64)
+    assert xy.shape == (4, mbw * mbh, 41, 2) and so.shape == xy.shape and rms.shape == xy.shape[:3]
+    tol = np.ascontiguousarray(tol, np.float64)
+    nodes = np.zeros((mbw * mbh, 21), V1_NODE)
+    orc_lib().orc_v1_encode_plane(_ptr(org), _ptr(refC), C.c_int(w), C.c_int(mbw), C.c_int(mbh), _ptr(xy), _ptr(so), _ptr(rms),
+                                  _ptr(tol), _ptr(nodes))
+    return nodes
 
 
 def v1_box_table(img, bw, bh, squares):

@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 typedef struct {
   int w, h, R;
@@ -143,4 +144,119 @@ void orc_v1_search_plane(const uint8_t *org, const uint8_t *ref, int w, int h, i
       rms[o] = orc_v1_full_search(&pl, (mb % mbw) * 16 + ox, (mb / mbw) * 16 + oy, bw, bh, v, so + 2 * o);
       xy[2 * o] = v[0]; xy[2 * o + 1] = v[1];
     }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * F5: the partition cascade of one macroblock -- encode_one_macroblock (V1/src/block_enc.c:508-1051),
+ * encode_block_rect (:1072-1334), encode_block_8 (:1337-1675), encode_block_4 (:1676-1930) for the shipped
+ * configuration (num_regions == 1, search_mode == 0, currentVideo == 'C').
+ *
+ * Every block is searched on the four plane sets C, H, M, N (strict '<' keeps the earlier set, :652-733);
+ * the cascade itself only compares those rms values with tol^2 * n and, at the macroblock level, the squared
+ * normalised cross-correlation `chun` of the range block with the CO-LOCATED block of plane set C (:811-848).
+ * Restated as a replay of the reference's writes to its TRANS_NODE tree (the nodes are reused between the 16x8,
+ * 8x16 and 8x8 attempts and several fields survive from one attempt to the next -- e.g. `reference` of a 4x4 node
+ * is only rewritten by the H comparison, and encode_block_4 also sets partition = 1 when H wins, :1773), from the
+ * per-partition search results  xy/so/rms [4 sets][nmb][41].  Quirks kept: after the 16x8 / 8x16 attempts the
+ * macroblock ALWAYS goes on to four 8x8 blocks (`if(mode<4)` after `for(mode=1;mode<3;mode++)`, :915), while an 8x8
+ * block does stop at 8x4 / 4x8 (`mode=4`, :1641).
+ * nodes: [nmb][21] in the harness' pre-order (root, child 0, its 4 children, child 1, ...).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { int32_t block_type, partition, reference, x, y, pad; double scale, offset; } OrcV1Node;   /* = b2fr_node */
+
+typedef struct { const int32_t *xy[4]; const double *so[4], *rms[4]; size_t base; } OrcV1Res;
+
+/* the four searches of one block (node = trans of the reference): returns the best rms */
+static double v1_search4(const OrcV1Res *R, int p, OrcV1Node *t, int is4x4)
+{
+  size_t o = R->base + p; int s;
+  double rms = R->rms[0][o];
+  if (R->xy[0][2 * o] || R->xy[0][2 * o + 1]) { t->x = R->xy[0][2 * o]; t->y = R->xy[0][2 * o + 1]; }   /* Q-F11 */
+  t->scale = R->so[0][2 * o]; t->offset = R->so[0][2 * o + 1];
+  for (s = 1; s < 4; s++) {
+    if (R->rms[s][o] < rms) {
+      if (s == 1 && is4x4) t->partition = 1;        /* block_enc.c:1773 */
+      t->reference = s; rms = R->rms[s][o];
+      t->x = R->xy[s][2 * o]; t->y = R->xy[s][2 * o + 1];
+      t->offset = R->so[s][2 * o + 1]; t->scale = R->so[s][2 * o];
+      t->block_type = 0;
+    } else if (s == 1) t->reference = 0;
+  }
+  return rms;
+}
+
+/* chun of encode_one_macroblock (:811-848): doubles, column-major walk, in the reference's operation order */
+double orc_v1_chun(const uint8_t *org, const uint8_t *ref, int w, int bx, int by)
+{
+  double Rv[256], Dv[256], sumR = 0, sumD = 0, r, d, sR = 0, sD = 0, mr = 0;
+  int i, j, ii = 0;
+  for (j = bx; j < bx + 16; j++)
+    for (i = by; i < by + 16; i++) {
+      Rv[ii] = org[(size_t)i * w + j]; Dv[ii] = ref[(size_t)i * w + j];
+      sumR += Rv[ii]; sumD += Dv[ii]; ii++;
+    }
+  r = sumR / 256; d = sumD / 256;
+  for (ii = 0; ii < 256; ii++) { sR += (Rv[ii] - r) * (Rv[ii] - r); sD += (Dv[ii] - d) * (Dv[ii] - d); }
+  for (ii = 0; ii < 256; ii++) mr += ((Rv[ii] - r) / (sqrt(sR))) * ((Dv[ii] - d) / (sqrt(sD)));
+  return mr * mr;
+}
+
+static int v1_rect(const OrcV1Res *R, OrcV1Node *t, int p, double tol8, int n)
+{ return !(v1_search4(R, p, t, 0) > tol8 * tol8 * n); }
+
+void orc_v1_encode_plane(const uint8_t *org, const uint8_t *refC, int w, int mbw, int mbh,
+                         const int32_t *xy /*[4][nmb][41][2]*/, const double *so, const double *rms,
+                         const double *tol /*[3]: tol_16, tol_8, tol_4*/, OrcV1Node *nodes /*[nmb][21]*/)
+{
+  const int nmb = mbw * mbh; int mb, s;
+  OrcV1Res R;
+  for (s = 0; s < 4; s++) { R.xy[s] = xy + (size_t)s * nmb * 82; R.so[s] = so + (size_t)s * nmb * 82; R.rms[s] = rms + (size_t)s * nmb * 41; }
+  memset(nodes, 0, sizeof(OrcV1Node) * 21 * (size_t)nmb);
+  for (mb = 0; mb < nmb; mb++) {
+    OrcV1Node *root = nodes + (size_t)mb * 21;
+    const int bx = (mb % mbw) * 16, by = (mb / mbw) * 16;
+    double r16, chun;
+    int mode, i, j, k;
+    R.base = (size_t)mb * 41;
+    root->partition = 0; root->block_type = 0; root->x = root->y = 0; root->reference = 0;
+    r16 = v1_search4(&R, 0, root, 0);
+    chun = orc_v1_chun(org, refC, w, bx, by);
+    if (!(chun <= 1 && chun >= 0.9 && r16 > tol[0] * tol[0] * 256)) continue;       /* 16x16 accepted */
+    for (mode = 1; mode < 3; mode++) {
+      root->partition = mode;
+      for (i = 0; i < 2; i++) {
+        OrcV1Node *c = root + 1 + 5 * i;
+        c->x = 0; c->y = 0;
+        if (!v1_rect(&R, c, (mode == 1 ? 1 : 3) + i, tol[1], 128)) break;
+      }
+    }
+    root->partition = 3;
+    for (k = 0; k < 4; k++) {                         /* encode_block_8 */
+      OrcV1Node *c = root + 1 + 5 * k;
+      const int by2 = k >> 1, bx2 = k & 1;
+      c->partition = 0; c->reference = 0; c->x = 0; c->y = 0;
+      if (!(v1_search4(&R, 5 + k, c, 0) > tol[1] * tol[1] * 64)) continue;
+      for (mode = 1; mode < 3; mode++) {
+        int ok = 0;
+        c->partition = mode;
+        for (i = 0; i < 2; i++) {
+          OrcV1Node *g = c + 1 + i;
+          const int p = mode == 1 ? 9 + 2 * (2 * by2 + i) + bx2 : 17 + 4 * by2 + 2 * bx2 + i;
+          g->x = 0; g->y = 0;
+          if (!v1_rect(&R, g, p, tol[1], 32)) break;
+          ok++;
+        }
+        if (ok == 2) { mode = 4; }
+      }
+      if (mode < 4) {
+        c->partition = 3;
+        for (i = 0; i < 2; i++)
+          for (j = 0; j < 2; j++) {
+            OrcV1Node *g = c + 1 + i * 2 + j;
+            g->x = g->y = 0;
+            v1_search4(&R, 25 + 4 * (2 * by2 + i) + 2 * bx2 + j, g, 1);
+          }
+      }
+    }
+  }
 }

@@ -185,6 +185,8 @@ static void give_children(TRANS_NODE *t, int depth)
   t->next = new_nodes(4);
   for (i = 0; i < 4; i++) give_children(&t->next[i], depth - 1);
 }
+/* fresh (all-zero) TRANS_NODE trees: the reference keeps one tree array per component, the harness one in all */
+void v1h_reset_trans(void) { g_trans[0] = g_trans[1] = NULL; }
 int v1h_encode_mb(int CurMb, int con, int32_t *out, double *out_d, int maxn)
 {
   /* out rows: block_type, partition, reference, x, y ; out_d rows: scale, offset ; pre-order, 3 levels */
