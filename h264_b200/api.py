@@ -208,6 +208,10 @@ class Searcher:
         return ms.value, n.value
 
 
+FR_NODE = np.dtype([("block_type", np.int32), ("partition", np.int32), ("reference", np.int32), ("x", np.int32), ("y", np.int32),
+                    ("reserved", np.int32), ("scale", np.float64), ("offset", np.float64)])     # b2fr_node
+
+
 class FractalSearcher:
     """One b2fr context (include/b2me.h): version1's fractal range/domain block search for one
     picture size.  Mirrors the reference's call sequence: set_range (compute_range_Sum),
@@ -278,6 +282,14 @@ class FractalSearcher:
         rms = C.c_double()
         self._chk(self.L.b2fr_full_search(self.h, C.c_int(plane_set), bx, by, bsx, bsy, con, v, so, C.byref(rms)), "b2fr_full_search")
         return (v[0], v[1]), (so[0], so[1]), rms.value
+
+    def encode_plane(self, con, tol):
+        """F5: encode_one_macroblock's TRANS_NODE tree of every macroblock of component con; record array [nmb][21]"""
+        mbw, mbh = self.grid(con)
+        nodes = np.zeros((mbw * mbh, 21), FR_NODE)
+        t = (C.c_double * 3)(*[float(x) for x in tol])
+        self._chk(self.L.b2fr_encode_plane(self.h, C.c_int(con), t, _p(nodes)), "b2fr_encode_plane")
+        return nodes
 
     def domain_table(self, plane_set, con, bw, bh, squares):
         w, h = (self.W, self.H) if con == 1 else (self.W // 2, self.H // 2)

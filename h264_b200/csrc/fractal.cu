@@ -278,6 +278,117 @@ __global__ void __launch_bounds__(FR_NT) k_frac_window(const FrArgs a)
   }
 }
 
+// ---- F5: the partition cascade of every macroblock ----------------------------------------------------------
+// encode_one_macroblock / encode_block_rect / encode_block_8 / encode_block_4 (V1/src/block_enc.c:508-1051,
+// 1072-1334, 1337-1675, 1676-1930; num_regions == 1, search_mode == 0, currentVideo == 'C').  Every block is
+// searched on the four plane sets (k_frac_window) and the best kept with a strict '<' (C, H, M, N order); the cascade
+// compares those rms values with tol^2 * n and, for the macroblock, the squared normalised cross-correlation `chun` of
+// the range block with the CO-LOCATED block of set C (:811-848).  One thread per macroblock replays the reference's
+// writes to its TRANS_NODE tree (fields survive between the 16x8 / 8x16 / 8x8 attempts on the same nodes; `reference`
+// of a node is reset only by the H comparison; encode_block_4 also sets partition = 1 when H wins, :1773; after the
+// 16x8 / 8x16 attempts a macroblock ALWAYS goes on to 8x8, :915, while an 8x8 block stops at 8x4 / 4x8, :1641).
+struct FdArgs {
+  const uint8_t *org, *refC; int w, mbw, nmb;
+  const int *xy[4]; const double *so[4], *rms[4];
+  double tol16, tol8;
+  b2fr_node *nodes;
+};
+
+__device__ double fd_chun(const uint8_t *org, const uint8_t *ref, int w, int bx, int by)
+{
+  // doubles in the reference's operation order (column-major walk, no contraction): sums and squared deviations are
+  // exact, the correlation sum is the order-dependent part
+  double sumR = 0, sumD = 0, sR = 0, sD = 0, mr = 0;
+  for (int j = bx; j < bx + 16; j++)
+    for (int i = by; i < by + 16; i++) { sumR = __dadd_rn(sumR, (double)org[(size_t)i * w + j]); sumD = __dadd_rn(sumD, (double)ref[(size_t)i * w + j]); }
+  const double r = __ddiv_rn(sumR, 256.0), d = __ddiv_rn(sumD, 256.0);
+  for (int j = bx; j < bx + 16; j++)
+    for (int i = by; i < by + 16; i++) {
+      const double a = __dsub_rn((double)org[(size_t)i * w + j], r), b = __dsub_rn((double)ref[(size_t)i * w + j], d);
+      sR = __dadd_rn(sR, __dmul_rn(a, a)); sD = __dadd_rn(sD, __dmul_rn(b, b));
+    }
+  const double qR = __dsqrt_rn(sR), qD = __dsqrt_rn(sD);
+  for (int j = bx; j < bx + 16; j++)
+    for (int i = by; i < by + 16; i++) {
+      const double a = __dsub_rn((double)org[(size_t)i * w + j], r), b = __dsub_rn((double)ref[(size_t)i * w + j], d);
+      mr = __dadd_rn(mr, __dmul_rn(__ddiv_rn(a, qR), __ddiv_rn(b, qD)));
+    }
+  return __dmul_rn(mr, mr);
+}
+
+// the four searches of one block: C into the node, then H, M, N with strict '<'
+__device__ double fd_search4(const FdArgs &a, size_t base, int p, b2fr_node &t, bool is4x4)
+{
+  const size_t o = base + p;
+  double rms = a.rms[0][o];
+  if (a.xy[0][2 * o] || a.xy[0][2 * o + 1]) { t.x = a.xy[0][2 * o]; t.y = a.xy[0][2 * o + 1]; }     // Q-F11
+  t.scale = a.so[0][2 * o]; t.offset = a.so[0][2 * o + 1];
+  for (int s = 1; s < 4; s++) {
+    const double r = a.rms[s][o];
+    if (r < rms) {
+      if (s == 1 && is4x4) t.partition = 1;
+      t.reference = s; rms = r;
+      t.x = a.xy[s][2 * o]; t.y = a.xy[s][2 * o + 1]; t.scale = a.so[s][2 * o]; t.offset = a.so[s][2 * o + 1];
+      t.block_type = 0;
+    } else if (s == 1) t.reference = 0;
+  }
+  return rms;
+}
+
+__global__ void __launch_bounds__(64) k_frac_decide(const FdArgs a)
+{
+  const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mb >= a.nmb) return;
+  b2fr_node nd[21];
+  for (int i = 0; i < 21; i++) { nd[i].block_type = nd[i].partition = nd[i].reference = nd[i].x = nd[i].y = nd[i].reserved = 0; nd[i].scale = nd[i].offset = 0.0; }
+  const size_t base = (size_t)mb * NPART;
+  const int bx = (mb % a.mbw) * 16, by = (mb / a.mbw) * 16;
+  const double t16 = __dmul_rn(__dmul_rn(a.tol16, a.tol16), 256.0);
+  const double r16 = fd_search4(a, base, 0, nd[0], false);
+  const double chun = fd_chun(a.org, a.refC, a.w, bx, by);
+  if (chun <= 1.0 && chun >= 0.9 && r16 > t16) {
+    const double tt = __dmul_rn(a.tol8, a.tol8);
+    for (int mode = 1; mode < 3; mode++) {
+      nd[0].partition = mode;
+      for (int i = 0; i < 2; i++) {
+        b2fr_node &c = nd[1 + 5 * i];
+        c.x = 0; c.y = 0;
+        if (fd_search4(a, base, (mode == 1 ? 1 : 3) + i, c, false) > __dmul_rn(tt, 128.0)) break;
+      }
+    }
+    nd[0].partition = 3;
+    for (int k = 0; k < 4; k++) {
+      b2fr_node *c = &nd[1 + 5 * k];
+      const int by2 = k >> 1, bx2 = k & 1;
+      c->partition = 0; c->reference = 0; c->x = 0; c->y = 0;
+      if (!(fd_search4(a, base, 5 + k, *c, false) > __dmul_rn(tt, 64.0))) continue;
+      int mode;
+      for (mode = 1; mode < 3; mode++) {
+        int ok = 0;
+        c->partition = mode;
+        for (int i = 0; i < 2; i++) {
+          b2fr_node &g = c[1 + i];
+          const int p = mode == 1 ? 9 + 2 * (2 * by2 + i) + bx2 : 17 + 4 * by2 + 2 * bx2 + i;
+          g.x = 0; g.y = 0;
+          if (fd_search4(a, base, p, g, false) > __dmul_rn(tt, 32.0)) break;
+          ok++;
+        }
+        if (ok == 2) mode = 4;
+      }
+      if (mode < 4) {
+        c->partition = 3;
+        for (int i = 0; i < 2; i++)
+          for (int j = 0; j < 2; j++) {
+            b2fr_node &g = c[1 + i * 2 + j];
+            g.x = g.y = 0;
+            fd_search4(a, base, 25 + 4 * (2 * by2 + i) + 2 * bx2 + j, g, true);
+          }
+      }
+    }
+  }
+  for (int i = 0; i < 21; i++) a.nodes[(size_t)mb * 21 + i] = nd[i];
+}
+
 }  // namespace b2
 
 // ================================ C ABI ======================================================
@@ -465,6 +576,29 @@ extern "C" int b2fr_full_search(b2fr_ctx *c, int plane_set, int block_x, int blo
   if (hx[2 * o] != 0 || hx[2 * o + 1] != 0) { xy[0] = hx[2 * o]; xy[1] = hx[2 * o + 1]; }
   scale_offset[0] = c->h_so[plane_set][comp][2 * o]; scale_offset[1] = c->h_so[plane_set][comp][2 * o + 1];
   *rms = c->h_rms[plane_set][comp][o];
+  return B2ME_OK;
+}
+
+extern "C" int b2fr_encode_plane(b2fr_ctx *c, int con, const double tol[3], b2fr_node *nodes)
+{
+  if (!c || con < 1 || con > 3 || !tol || !nodes) return B2ME_EINVAL;
+  FR_CHECK(c, cudaSetDevice(c->device));
+  const int comp = con - 1;
+  for (int s = 0; s < 4; s++) { int r = ensure(c, s, comp); if (r) return r; }
+  const int mbw = comp_mbw(c, comp), nmb = mbw * comp_mbh(c, comp);
+  b2fr_node *d = nullptr;
+  FR_CHECK(c, cudaMallocAsync(&d, sizeof(b2fr_node) * 21 * (size_t)nmb, c->stream));
+  FdArgs a;
+  a.org = c->d_org[comp]; a.refC = c->d_ref[0][comp]; a.w = comp_w(c, comp); a.mbw = mbw; a.nmb = nmb;
+  for (int s = 0; s < 4; s++) { a.xy[s] = c->d_xy[s][comp]; a.so[s] = c->d_so[s][comp]; a.rms[s] = c->d_rms[s][comp]; }
+  a.tol16 = tol[0]; a.tol8 = tol[1]; a.nodes = d;
+  k_frac_decide<<<(nmb + 63) / 64, 64, 0, c->stream>>>(a);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nodes, d, sizeof(b2fr_node) * 21 * (size_t)nmb, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFreeAsync(d, c->stream);
+  if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "b2fr_encode_plane: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
   return B2ME_OK;
 }
 

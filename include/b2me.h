@@ -241,6 +241,21 @@ int b2fr_search_plane(b2fr_ctx *ctx, int plane_set, int con, int32_t *xy, double
  * are table look-ups (SURVEY Q-F10). */
 int b2fr_full_search(b2fr_ctx *ctx, int plane_set, int block_x, int block_y, int block_size_x, int block_size_y,
                      int con, int32_t xy[2], double scale_offset[2], double *rms);
+/* F5 -- the partition cascade of EVERY macroblock of component `con`:
+ *   <- encode_one_macroblock V1/src/block_enc.c:508-1051, encode_block_rect :1072, encode_block_8 :1337, encode_block_4 :1676
+ * (num_regions == 1, full search, current view 'C').  Searches the four plane sets if that has not happened yet, then
+ * decides on the device: 16x16 is kept unless chun (squared normalised cross-correlation with the co-located block of
+ * set C) lies in [0.9, 1] and rms > tol_16^2 * 256; then four 8x8 blocks, each kept if rms <= tol_8^2 * 64, else 8x4
+ * pair / 4x8 pair (each block <= tol_8^2 * 32), else four 4x4.  nodes [nmb][21]: the reference's TRANS_NODE tree in
+ * pre-order (macroblock, 8x8 block 0, its four children, 8x8 block 1, ...), field for field what the reference leaves
+ * there (including what earlier attempts on the same node left behind).  tol = {tol_16, tol_8, tol_4} (tol_4 is read
+ * by the reference but decides nothing). */
+typedef struct b2fr_node {
+  int32_t block_type, partition, reference, x, y, reserved;   /* partition 0 whole, 1 upper/lower, 2 left/right, 3 quarters;
+                                                                 reference 0..3 = plane set C, H, M, N */
+  double scale, offset;
+} b2fr_node;                  /* 40 bytes */
+int b2fr_encode_plane(b2fr_ctx *ctx, int con, const double tol[3], b2fr_node *nodes);
 /* parity read-back of the sum tables: domain table of block size bw x bh at every pixel offset
  * ([h][w] int32, 0 where the block does not fit), range 4x4 table on the block grid ([h/4][w/4]) */
 int b2fr_get_domain_table(b2fr_ctx *ctx, int plane_set, int con, int bw, int bh, int squares, int32_t *out);

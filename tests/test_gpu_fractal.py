@@ -106,3 +106,42 @@ def test_search_matches_oracle(W, H, R, seed, gain, offset, noise):
         dom = ref[con - 1] if which == 0 else np.zeros_like(ref[con - 1])
         exy, eso, erms = oracle.v1_search_plane(org, dom, R, have_sums=(which == 0), chroma=(con > 1), full_wh=(W, H))
         assert (xy == exy).all() and (so == eso).all() and (rms == erms).all(), (which, con)
+
+
+@pytest.mark.parametrize("name", ["loaded", "zero"])
+def test_cascade_matches_reference_golden(golden_dir, name):
+    """F5 on the device (b2fr_encode_plane) against the trees of the unmodified encode_one_macroblock"""
+    from oracle import gen_golden_cascade as gc
+    g = np.load(os.path.join(golden_dir, f"v1_cascade_{name}.npz"))
+    cur, sets, W, H, R, tol, loaded = gc.inputs(name)
+    f = api.FractalSearcher(W, H, R)
+    for s in range(4):
+        if s == 0 or loaded:
+            f.set_domain(s, *sets[s], build_sums=True)
+    f.set_range(*cur)
+    for con in (1, 2, 3):
+        nodes, exp = f.encode_plane(con, tol), g[f"nodes_{con}"]
+        for k in ("block_type", "partition", "reference", "x", "y", "scale", "offset"):
+            assert (nodes[k] == exp[k]).all(), (con, k, int((nodes[k] != exp[k]).sum()))
+
+
+def test_cascade_matches_oracle_cif():
+    """BASELINE config 2 geometry (CIF, +-7): static noisy content so that the cascade splits; oracle cascade on the oracle's searches"""
+    W, H, R, tol = 352, 288, 7, (3.5, 4.5, 2.0)
+    ref, cur = synth.yuv_pair(W, H, seed=11, shift=(0, 0), gain=1.0, offset=0.0, noise=4.0)
+    hset = [np.roll(p, (1, -1), (0, 1)) for p in ref]
+    f = api.FractalSearcher(W, H, R)
+    f.set_domain(0, *ref, build_sums=True)
+    f.set_domain(1, *hset, build_sums=True)
+    f.set_range(*cur)
+    for con in (1, 2):
+        nodes = f.encode_plane(con, tol)
+        org = cur[con - 1]
+        doms = [ref[con - 1], hset[con - 1], np.zeros_like(org), np.zeros_like(org)]
+        res = [oracle.v1_search_plane(org, doms[s], R, have_sums=(s < 2), chroma=(con > 1), full_wh=(W, H)) for s in range(4)]
+        exp = oracle.v1_encode_plane(org, ref[con - 1], np.stack([r[0] for r in res]), np.stack([r[1] for r in res]),
+                                     np.stack([r[2] for r in res]), tol)
+        for k in ("block_type", "partition", "reference", "x", "y", "scale", "offset"):
+            assert (nodes[k] == exp[k]).all(), (con, k)
+        if con == 1:
+            assert len(np.unique(nodes[:, 0]["partition"])) == 2 and len(np.unique(nodes[:, [1, 6, 11, 16]]["partition"])) >= 3

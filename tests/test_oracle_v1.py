@@ -68,3 +68,28 @@ def test_restated_matches_reference_live():
             b = oracle.v1_search_plane(cur[con - 1], ref[con - 1], R, True, chroma=(con > 1), full_wh=(W, H))
             for x, y in zip(a, b):
                 assert (x == y).all()
+
+
+def _cascade_results(cur, sets, W, H, R, loaded, con):
+    org = cur[con - 1]
+    res = [oracle.v1_search_plane(org, sets[s][con - 1], R, have_sums=(s == 0 or loaded), chroma=(con > 1), full_wh=(W, H)) for s in range(4)]
+    return org, np.stack([r[0] for r in res]), np.stack([r[1] for r in res]), np.stack([r[2] for r in res])
+
+
+@pytest.mark.parametrize("name", ["loaded", "zero"])
+def test_cascade_matches_reference_golden(golden_dir, name):
+    """F5: the TRANS_NODE trees the unmodified encode_one_macroblock leaves (block_enc.c:508), every field of every node"""
+    from oracle import gen_golden_cascade as gc
+    g = np.load(os.path.join(golden_dir, f"v1_cascade_{name}.npz"))
+    cur, sets, W, H, R, tol, loaded = gc.inputs(name)
+    for con in (1, 2, 3):
+        org, xy, so, rms = _cascade_results(cur, sets, W, H, R, loaded, con)
+        nodes = oracle.v1_encode_plane(org, sets[0][con - 1], xy, so, rms, tol)
+        exp = g[f"nodes_{con}"]
+        for f in ("block_type", "partition", "reference", "x", "y", "scale", "offset"):
+            assert (nodes[f] == exp[f]).all(), (con, f)
+    n1 = g["nodes_1"]
+    if name == "loaded":      # the fixture reaches every outcome of the cascade
+        assert set(np.unique(n1[:, 0]["partition"])) == {0, 3}
+        assert set(np.unique(n1[:, [1, 6, 11, 16]]["partition"])) == {0, 1, 2, 3}
+        assert set(np.unique(n1["reference"])) == {0, 1, 2, 3}
