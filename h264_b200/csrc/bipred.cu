@@ -126,8 +126,9 @@ __global__ void __launch_bounds__(128) k_bipred(const BiArgs a)
   const b2me_bipred_job J = a.jobs[blockIdx.x];
   b2me_bipred_result *O = &a.out[blockIdx.x];
   const int bt = J.blocktype;
-  const bool bad = bt < 1 || bt > 7 || J.ref1 < 0 || J.ref1 >= a.nrefs || J.ref2 < 0 || J.ref2 >= a.nrefs || J.search_range < 0 ||
-                   J.search_range > a.R || J.pos_x < 0 || J.pos_y < 0 || J.pos_x >= a.W || J.pos_y >= a.H || ((J.mv1[0] | J.mv1[1]) & 3);
+  const bool bad = bt < 1 || bt > 7 || J.ref1 < 0 || J.ref1 >= a.nrefs || J.ref2 < 0 || J.ref2 >= a.nrefs || J.search_range < -1 ||
+                   J.search_range > a.R || J.pos_x < 0 || J.pos_y < 0 || J.pos_x >= a.W || J.pos_y >= a.H ||
+                   (J.search_range >= 0 && ((J.mv1[0] | J.mv1[1]) & 3)) || (J.search_range < 0 && !a.do_subpel);
   if (bad) {                                          // uniform over the CTA
     if (tid == 0) { *a.errflag = 1; O->cost_int = O->cost_sub = -1; O->mv_int[0] = O->mv_int[1] = O->mv_sub[0] = O->mv_sub[1] = 0; }
     return;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(128) k_bipred(const BiArgs a)
   if (tid == 0) { key = (unsigned long long)min_mcost << 20; mv1[0] = J.mv1[0]; mv1[1] = J.mv1[1]; }
   __syncthreads();
   // ---- integer pel: (2 sr + 1)^2 spiral positions around mv1, SAD ----
-  {
+  if (J.search_range >= 0) {                          // search_range == -1: sub_pel_bipred_motion_estimation alone
     const int sr = J.search_range, max_pos = (2 * sr + 1) * (2 * sr + 1);
     const long long c2 = (long long)a.lambda[0] * (mvbits(J.mv2[0] - J.pred2[0]) + mvbits(J.mv2[1] - J.pred2[1]));
     for (int pos = tid; pos < max_pos; pos += 128) {
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(128) k_bipred(const BiArgs a)
   for (int stage = 0; stage < 2; stage++) {
     __syncthreads();
     long long b = bound;
-    if (stage == 0 && !start_hp_cfg) b = BI_DISTBLK_MAX;              // mv_search.c:1119-1120
+    if (stage == 0 && !start_hp_cfg && J.search_range >= 0) b = BI_DISTBLK_MAX;   // the caller's reset, mv_search.c:1119-1120
     const int start = stage ? start_qp : (b == BI_DISTBLK_MAX ? 0 : start_hp_cfg);
     if (stage == 1 && !start_qp) b = BI_DISTBLK_MAX;                  // me_fullsearch.c:364-365
     const int m0 = mv1[0], m1 = mv1[1];

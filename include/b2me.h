@@ -143,7 +143,8 @@ typedef struct b2me_bipred_job {
   int16_t pos_x, pos_y;       /* luma position of the block */
   int16_t blocktype;          /* 1..7 */
   int16_t ref1, ref2;         /* reference slots */
-  int16_t search_range;       /* pel: (BiPredMESearchRange) >> iteration_no, <= the context's search_range */
+  int16_t search_range;       /* pel: (BiPredMESearchRange) >> iteration_no, <= the context's search_range;
+                                 -1: sub_pel_bipred_motion_estimation ALONE (mv1 any quarter-pel, min_mcost used as handed over) */
   int16_t pred1[2], pred2[2]; /* predictors of the two lists, quarter-pel */
   int16_t mv1[2];             /* search centre of the searched list (relative MV, multiple of 4) */
   int16_t mv2[2];             /* the other list's vector (relative MV, any quarter-pel) */

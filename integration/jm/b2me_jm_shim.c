@@ -2,13 +2,15 @@
  * libb2me.so (hand-written sm_100a CUDA behind include/b2me.h).
  *
  * Link-level object replacement: JM's me_fullsearch.o is left out of the link and this
- * file defines the two symbols the IPPP / full-search configurations reach,
+ * file defines the four symbols the full-search configurations reach (P and B slices),
  *     distblk full_search_motion_estimation(Macroblock*, MotionVector*, MEBlock*, distblk, int)
  *     distblk sub_pel_motion_estimation    (Macroblock*, MotionVector*, MEBlock*, distblk, int*)
- * with the exact signatures of JM/lencod/inc/me_fullsearch.h:20-25.  The other four symbols of
- * that object (bi-pred twins, full_sub_pel_motion_estimation) come from JM's own source compiled
- * with the two names above renamed (integration/jm/Makefile), so every other configuration still
- * links and runs the reference code for them.
+ *     distblk full_search_bipred_motion_estimation(Macroblock*, int, MotionVector*, MotionVector*, MotionVector*, MotionVector*, MEBlock*, int, distblk, int)
+ *     distblk sub_pel_bipred_motion_estimation    (Macroblock*, MEBlock*, int, MotionVector*, MotionVector*, MotionVector*, MotionVector*, distblk, int*)
+ * with the exact signatures of JM/lencod/inc/me_fullsearch.h:20-25.  The other two symbols of
+ * that object (full_sub_pel_motion_estimation and its bi-pred twin, EPZSSubPelME == 2 only) come from JM's
+ * own source compiled with the four names above renamed (oracle/Makefile.jm), so every other configuration
+ * still links and runs the reference code for them.
  *
  * Ownership / threading follow the reference: the caller owns every buffer, the callee writes only
  * mv_block->mv[list] and returns the cost; one thread; state hangs off a process-wide context that
@@ -17,7 +19,7 @@
  *   - a reference picture is uploaded (and its 16 quarter-pel planes rebuilt on the GPU) the first
  *     time a (StorablePicture*, poc) pair is searched; slots are recycled least-recently-used.
  * Configurations the CUDA path does not cover (bit depth > 8, field/MBAFF pictures, weighted ME,
- * chroma ME, list 1, SSE metrics, non-RDO (0,0) bias) stop the encoder through JM's own error()
+ * chroma ME, non-RDO (0,0) bias) stop the encoder through JM's own error()
  * -- there is no silent CPU fallback.
  *
  * Built only where the JM headers are available (it includes the reference's global.h).
@@ -46,7 +48,8 @@ static long g_clock;
 static StorablePicture *g_cur_pic;
 static int g_cur_poc = -0x7fffffff;
 static unsigned char *g_stage;
-static long g_calls_int, g_calls_sub, g_uploads;
+static long g_calls_int, g_calls_sub, g_calls_bi, g_uploads;
+static int g_in_bipred;
 
 static void b2_fail(const char *what)
 {
@@ -58,8 +61,8 @@ static void b2_fail(const char *what)
 static void b2_report(void)
 {
   if (getenv("B2ME_SHIM_VERBOSE"))
-    fprintf(stderr, "b2me shim: %ld integer searches, %ld sub-pel refinements, %ld picture uploads, %lld kernel launches\n",
-            g_calls_int, g_calls_sub, g_uploads, g_ctx ? (long long)b2me_launch_count(g_ctx) : 0LL);
+    fprintf(stderr, "b2me shim: %ld integer searches, %ld sub-pel refinements, %ld bi-predictive calls, %ld picture uploads, %lld kernel launches\n",
+            g_calls_int, g_calls_sub, g_calls_bi, g_uploads, g_ctx ? (long long)b2me_launch_count(g_ctx) : 0LL);
   if (g_ctx) b2me_destroy(g_ctx);
   g_ctx = NULL;
 }
@@ -71,9 +74,9 @@ static void b2_check_config(Macroblock *currMB, MEBlock *mv_block)
   Slice *currSlice = currMB->p_Slice;
   if (p_Vid->bitdepth_luma != 8) b2_fail("only 8-bit luma is supported");
   if (currSlice->structure != FRAME || currMB->list_offset != 0) b2_fail("field / MBAFF pictures are not supported");
-  if (mv_block->list != 0) b2_fail("only list 0 is supported");
+  if (mv_block->list != 0 && mv_block->list != 1) b2_fail("only list 0 / list 1 frame references are supported");
   if (p_Inp->ChromaMEEnable || mv_block->ChromaMEEnable) b2_fail("ChromaMEEnable is not supported");
-  if (mv_block->apply_weights) b2_fail("weighted-prediction ME is not supported");
+  if (mv_block->apply_weights && !g_in_bipred) b2_fail("weighted-prediction ME of the single-list search is not supported by the shim");
   if (!p_Inp->rdopt) b2_fail("RDOptimization=0 ((0,0)-bias path) is not supported");
   if (p_Inp->MEErrorMetric[F_PEL] != ERROR_SAD) b2_fail("MEDistortionFPel must be SAD");
   if (p_Inp->OnTheFlyFractMCP) b2_fail("OnTheFlyFractMCP must be 0");
@@ -190,4 +193,55 @@ distblk sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, MEBloc
   g_calls_sub++;
   mv->mv_x = out[0]; mv->mv_y = out[1];
   return (distblk)cost;
+}
+
+/* ---- B slices: the bi-predictive twins (JM/lencod/inc/me_fullsearch.h:21,24) on b2me_bipred_search ---------------- */
+static distblk b2_bipred(Macroblock *currMB, int list, MotionVector *pred_mv1, MotionVector *pred_mv2, MotionVector *mv1,
+                         MotionVector *mv2, MEBlock *mv_block, int search_range_pel, distblk min_mcost, int *lambda, int do_subpel)
+{
+  Slice *currSlice = currMB->p_Slice;
+  StorablePicture *ref_picture1 = currSlice->listX[list + currMB->list_offset][mv_block->ref_idx];
+  StorablePicture *ref_picture2 = currSlice->listX[(list ^ 1) + currMB->list_offset][0];
+  b2me_search_params P;
+  b2me_bipred_job J;
+  b2me_bipred_result R;
+
+  b2_ensure_ctx(currMB);
+  g_in_bipred = 1; b2_check_config(currMB, mv_block); g_in_bipred = 0;
+  b2_ensure_cur(currMB->p_Vid);
+  memset(&J, 0, sizeof(J));
+  J.ref1 = (int16_t)b2_ref_slot(ref_picture1);
+  J.ref2 = (int16_t)b2_ref_slot(ref_picture2);
+  if (g_slot[J.ref1].pic != ref_picture1) J.ref1 = (int16_t)b2_ref_slot(ref_picture1);   /* ref2's upload may have recycled ref1's slot */
+  if (J.ref1 == J.ref2 && ref_picture1 != ref_picture2) b2_fail("reference slots exhausted");
+  b2_params(currMB->p_Inp, &P, lambda[F_PEL], lambda[H_PEL], lambda[Q_PEL], min_mcost);
+  P.do_subpel = do_subpel;
+  J.min_mcost = (int64_t)min_mcost;
+  J.pos_x = mv_block->pos_x; J.pos_y = mv_block->pos_y; J.blocktype = mv_block->blocktype;
+  J.search_range = (int16_t)search_range_pel;
+  J.pred1[0] = pred_mv1->mv_x; J.pred1[1] = pred_mv1->mv_y; J.pred2[0] = pred_mv2->mv_x; J.pred2[1] = pred_mv2->mv_y;
+  J.mv1[0] = mv1->mv_x; J.mv1[1] = mv1->mv_y; J.mv2[0] = mv2->mv_x; J.mv2[1] = mv2->mv_y;
+  J.weight1 = mv_block->weight1; J.weight2 = mv_block->weight2; J.offset_bi = mv_block->offsetBi;
+  if (b2me_bipred_search(g_ctx, 1, &J, &P, mv_block->apply_weights ? 1 : 0, currSlice->luma_log_weight_denom, mv_block->test8x8, &R) != B2ME_OK)
+    b2_fail("b2me_bipred_search failed");
+  g_calls_bi++;
+  if (do_subpel) { mv1->mv_x = R.mv_sub[0]; mv1->mv_y = R.mv_sub[1]; return (distblk)R.cost_sub; }
+  mv1->mv_x = R.mv_int[0]; mv1->mv_y = R.mv_int[1];
+  return (distblk)R.cost_int;
+}
+
+distblk full_search_bipred_motion_estimation(Macroblock *currMB, int list, MotionVector *pred_mv1, MotionVector *pred_mv2,
+                                             MotionVector *mv1, MotionVector *mv2, MEBlock *mv_block, int search_range,
+                                             distblk min_mcost, int lambda_factor)
+{
+  int lam[3];
+  lam[F_PEL] = lam[H_PEL] = lam[Q_PEL] = lambda_factor;
+  return b2_bipred(currMB, list, pred_mv1, pred_mv2, mv1, mv2, mv_block, search_range >> 2, min_mcost, lam, 0);
+}
+
+distblk sub_pel_bipred_motion_estimation(Macroblock *currMB, MEBlock *mv_block, int list, MotionVector *pred_mv1, MotionVector *pred_mv2,
+                                         MotionVector *mv1, MotionVector *mv2, distblk min_mcost, int *lambda)
+{
+  if (mv_block->search_pos2 != 9 || mv_block->search_pos4 != 9) b2_fail("SubPelSearch position counts other than 9/9 are not supported");
+  return b2_bipred(currMB, list, pred_mv1, pred_mv2, mv1, mv2, mv_block, -1, min_mcost, lambda, 1);
 }

@@ -563,7 +563,7 @@ void orc_bipred_search(void *h, int njobs, const OrcBiJob *jobs, const int *lamb
     int64_t min_mcost = J->min_mcost;
     int pos, best_pos = 0;
     const int64_t c2f = orc_mv_cost(lambda[0], J->mv2[0], J->mv2[1], J->pred2[0], J->pred2[1]);
-    for (pos = 0; pos < max_pos; pos++) {
+    for (pos = 0; sr >= 0 && pos < max_pos; pos++) {       /* search_range == -1: the sub-pel call alone */
       const int cx = mv1[0] + 4 * f->spiral[2*pos], cy = mv1[1] + 4 * f->spiral[2*pos+1];
       int64_t mcost = orc_mv_cost(lambda[0], cx, cy, J->pred1[0], J->pred1[1]) + c2f;
       if (mcost >= min_mcost) continue;
@@ -575,7 +575,7 @@ void orc_bipred_search(void *h, int njobs, const OrcBiJob *jobs, const int *lamb
     out[n].mv_int[0] = mv1[0]; out[n].mv_int[1] = mv1[1]; out[n].cost_int = min_mcost;
     out[n].mv_sub[0] = mv1[0]; out[n].mv_sub[1] = mv1[1]; out[n].cost_sub = min_mcost;
     if (!do_subpel) continue;
-    if (!start_hp_cfg) min_mcost = DISTBLK_MAX_ORC;                      /* mv_search.c:1119-1120 */
+    if (!start_hp_cfg && sr >= 0) min_mcost = DISTBLK_MAX_ORC;           /* the caller's reset, mv_search.c:1119-1120 */
     {
       int stage;
       for (stage = 0; stage < 2; stage++) {

@@ -315,11 +315,13 @@ void jmh_bipred_search(void *hh, int njobs, const JmhBiJob *jobs, const int *lam
     p1.mv_x = J->pred1[0]; p1.mv_y = J->pred1[1]; p2.mv_x = J->pred2[0]; p2.mv_y = J->pred2[1];
     m1.mv_x = J->mv1[0]; m1.mv_y = J->mv1[1]; m2.mv_x = J->mv2[0]; m2.mv_y = J->mv2[1];
     lam[0] = lambda_factor[0]; lam[1] = lambda_factor[1]; lam[2] = lambda_factor[2];
-    c = full_search_bipred_motion_estimation(&h->mb, 0, &p1, &p2, &m1, &m2, &b, J->search_range << 2, (distblk)J->min_mcost, lam[F_PEL]);
+    c = (distblk)J->min_mcost;
+    if (J->search_range >= 0)
+      c = full_search_bipred_motion_estimation(&h->mb, 0, &p1, &p2, &m1, &m2, &b, J->search_range << 2, (distblk)J->min_mcost, lam[F_PEL]);
     out[n].mv_int[0] = m1.mv_x; out[n].mv_int[1] = m1.mv_y; out[n].cost_int = (long long)c;
     out[n].mv_sub[0] = m1.mv_x; out[n].mv_sub[1] = m1.mv_y; out[n].cost_sub = (long long)c;
     if (do_subpel) {
-      if (!h->p_Vid->start_me_refinement_hp) c = DISTBLK_MAX;   /* mv_search.c:1119-1120 */
+      if (!h->p_Vid->start_me_refinement_hp && J->search_range >= 0) c = DISTBLK_MAX;   /* mv_search.c:1119-1120 */
       c = sub_pel_bipred_motion_estimation(&h->mb, &b, 0, &p1, &p2, &m1, &m2, c, lam);
       out[n].mv_sub[0] = m1.mv_x; out[n].mv_sub[1] = m1.mv_y; out[n].cost_sub = (long long)c;
     }

@@ -37,4 +37,4 @@ def run_lencod(yuv, W, H, frames, outdir, exe="lencod", search_mode=-1, search_r
     r = subprocess.run(cmd, cwd=outdir, env=e, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"lencod failed: {r.stdout[-2000:]} {r.stderr[-2000:]}")
-    return r.stdout
+    return r.stdout + r.stderr

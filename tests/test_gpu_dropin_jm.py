@@ -36,6 +36,29 @@ def test_lencod_with_cuda_motion_search_is_bit_identical(frames, nrefs, sr, qp):
         assert a[1] == b[1], "reconstructions differ"
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not have, reason="oracle/_ref/lencod{,_b2} not built (needs /root/reference at build time)")
+def test_lencod_b_slices_with_cuda_bipred_search_are_bit_identical():
+    """IBPBP with BiPredMotionEstimation: full_search_bipred_motion_estimation / sub_pel_bipred_motion_estimation (and the
+    list-1 single-list searches) served by libb2me.so; 3 refinement iterations, dual-level sub-pel."""
+    W, H, frames = 176, 144, 7
+    extra = ("NumberBFrames=1", "BiPredMotionEstimation=1", "BiPredMERefinements=3", "BiPredMESearchRange=8", "BiPredMESubPel=2",
+             "HierarchicalCoding=0", "BReferencePictures=0", "QPBSlice=30", "DirectModeType=1", "BList0References=0",
+             "BList1References=1", "BiPredSearch16x16=1", "BiPredSearch16x8=1", "BiPredSearch8x16=1", "BiPredSearch8x8=0")
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(W, H, frames, seed=77))
+        a = _encode("lencod", yuv, W, H, frames, os.path.join(d, "stock"), nrefs=2, search_range=8, qp=30, extra=extra)
+        b = _encode("lencod_b2", yuv, W, H, frames, os.path.join(d, "b2"), nrefs=2, search_range=8, qp=30, extra=extra,
+                    env={"B2ME_SHIM_VERBOSE": "1"})
+        assert len(a[0]) > 1000
+        assert a[0] == b[0], "bitstreams differ"
+        assert a[1] == b[1], "reconstructions differ"
+        import re
+        m = re.search(r"(\d+) bi-predictive calls", b[2])
+        assert m and int(m.group(1)) > 1000, b[2][-400:]      # the B slices really went through b2me_bipred_search
+
+
 @pytest.mark.skipif(not have, reason="oracle/_ref/lencod_b2 not built")
 def test_dropin_fails_loudly_without_a_gpu():
     """No CPU fallback behind the boundary: without a CUDA device the shim stops the encoder."""
