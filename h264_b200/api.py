@@ -291,6 +291,15 @@ class FractalSearcher:
         self._chk(self.L.b2fr_encode_plane(self.h, C.c_int(con), t, _p(nodes)), "b2fr_encode_plane")
         return nodes
 
+    def decode_plane(self, con, nodes=None):
+        """F8: decode_one_macroblock of every macroblock (nodes=None: the trees encode_plane left on the device)"""
+        w, h = (self.W, self.H) if con == 1 else (self.W // 2, self.H // 2)
+        rec = np.zeros((h, w), np.uint8)
+        if nodes is not None:
+            nodes = np.ascontiguousarray(nodes, FR_NODE)
+        self._chk(self.L.b2fr_decode_plane(self.h, C.c_int(con), None if nodes is None else _p(nodes), _p(rec)), "b2fr_decode_plane")
+        return rec
+
     def domain_table(self, plane_set, con, bw, bh, squares):
         w, h = (self.W, self.H) if con == 1 else (self.W // 2, self.H // 2)
         out = np.zeros((h, w), np.int32)

@@ -35,6 +35,9 @@ struct b2fr_ctx {
   int *d_xy[4][3]; double *d_so[4][3]; double *d_rms[4][3];
   int *h_xy[4][3]; double *h_so[4][3]; double *h_rms[4][3];
   int valid[4][3];              // host copy of (set, comp) results is current
+  b2fr_node *d_nodes[3];        // TRANS_NODE trees of the last b2fr_encode_plane / b2fr_decode_plane per component [nmb][21]
+  int nodes_valid[3];
+  uint8_t *d_rec;               // reconstructed plane scratch
   int *d_tab;                   // scratch for table read-back
   cudaStream_t stream;
   int64_t launches;
@@ -389,6 +392,45 @@ __global__ void __launch_bounds__(64) k_frac_decide(const FdArgs a)
   for (int i = 0; i < 21; i++) a.nodes[(size_t)mb * 21 + i] = nd[i];
 }
 
+// ---- F8: the fractal prediction of every macroblock ------------------------------------------------------------
+// decode_one_macroblock / decode_block_rect / decode_block_8 / decode_block_4 (V1/src/block_dec.c:20, 285, 760, 978;
+// num_regions == 1): each leaf block of the TRANS_NODE tree is rec = (unsigned char) bound(0.5 + scale * d + offset -
+// scale * mean_d), d = the displaced block of plane set `reference`, mean_d = its sum table entry / n (:228-232).
+// One CTA per macroblock, one thread per pixel; the domain block's sum comes from the 4x4 sliding sums (exact integers,
+// like the reference's tables), the doubles follow the reference's operation order.
+struct FpArgs {
+  const uint8_t *ref[4]; const int *s4[4]; int w, h, mbw;
+  const b2fr_node *nodes; uint8_t *out;
+};
+
+__global__ void __launch_bounds__(256) k_frac_predict(const FpArgs a)
+{
+  const int mb = blockIdx.x, px = threadIdx.x & 15, py = threadIdx.x >> 4;
+  const b2fr_node *root = a.nodes + (size_t)mb * 21;
+  const b2fr_node *t = root;
+  int bx = 0, by = 0, bw = 16, bh = 16, mb_level = 1;
+  if (root->partition == 1) { const int i = py >> 3; t = root + 1 + 5 * i; by = 8 * i; bh = 8; mb_level = 0; }
+  else if (root->partition == 2) { const int i = px >> 3; t = root + 1 + 5 * i; bx = 8 * i; bw = 8; mb_level = 0; }
+  else if (root->partition != 0) {
+    const int k = (py >> 3) * 2 + (px >> 3);
+    const b2fr_node *c = root + 1 + 5 * k;
+    bx = (k & 1) * 8; by = (k >> 1) * 8; bw = bh = 8; mb_level = 0; t = c;
+    if (c->partition == 1) { const int i = (py & 7) >> 2; t = c + 1 + i; by += 4 * i; bh = 4; }
+    else if (c->partition == 2) { const int i = (px & 7) >> 2; t = c + 1 + i; bx += 4 * i; bw = 4; }
+    else if (c->partition != 0) { const int i = ((py & 7) >> 2) * 2 + ((px & 7) >> 2); t = c + 1 + i; bx += (i & 1) * 4; by += (i >> 1) * 4; bw = bh = 4; }
+  }
+  const int r = t->reference, set = (r >= 0 && r <= 3) ? r : (mb_level ? 0 : 3);
+  const int x0 = (mb % a.mbw) * 16, y0 = (mb / a.mbw) * 16;
+  const int ox = x0 + bx + t->x, oy = y0 + by + t->y;
+  int sum = 0;                                        // (coordinates clamped: foreign trees must not read outside the plane)
+  for (int j = 0; j < bh; j += 4)
+    for (int i = 0; i < bw; i += 4) sum += a.s4[set][(size_t)iclamp(oy + j, 0, a.h - 1) * a.w + iclamp(ox + i, 0, a.w - 1)];
+  const double avg = __ddiv_rn((double)sum, (double)(bh * bw));
+  const double d = (double)a.ref[set][(size_t)iclamp(oy + py - by, 0, a.h - 1) * a.w + iclamp(ox + px - bx, 0, a.w - 1)];
+  const double v = __dsub_rn(__dadd_rn(__dadd_rn(0.5, __dmul_rn(t->scale, d)), t->offset), __dmul_rn(t->scale, avg));
+  a.out[(size_t)(y0 + py) * a.w + x0 + px] = (uint8_t)(v < 0.0 ? 0 : (v > 255.0 ? 255 : (int)v));
+}
+
 }  // namespace b2
 
 // ================================ C ABI ======================================================
@@ -454,7 +496,8 @@ extern "C" void b2fr_destroy(b2fr_ctx *c)
       cudaFreeHost(c->h_xy[s][k]); cudaFreeHost(c->h_so[s][k]); cudaFreeHost(c->h_rms[s][k]);
     }
   }
-  cudaFree(c->d_tab);
+  cudaFree(c->d_tab); cudaFree(c->d_rec);
+  for (int k = 0; k < 3; k++) cudaFree(c->d_nodes[k]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -463,6 +506,7 @@ static void invalidate(b2fr_ctx *c, int set)
 {
   for (int s = 0; s < 4; s++)
     if (set < 0 || s == set) for (int k = 0; k < 3; k++) c->valid[s][k] = 0;
+  for (int k = 0; k < 3; k++) c->nodes_valid[k] = 0;       // trees of other pictures
 }
 
 extern "C" int b2fr_set_range(b2fr_ctx *c, const uint8_t *y, const uint8_t *u, const uint8_t *v)
@@ -586,8 +630,8 @@ extern "C" int b2fr_encode_plane(b2fr_ctx *c, int con, const double tol[3], b2fr
   const int comp = con - 1;
   for (int s = 0; s < 4; s++) { int r = ensure(c, s, comp); if (r) return r; }
   const int mbw = comp_mbw(c, comp), nmb = mbw * comp_mbh(c, comp);
-  b2fr_node *d = nullptr;
-  FR_CHECK(c, cudaMallocAsync(&d, sizeof(b2fr_node) * 21 * (size_t)nmb, c->stream));
+  if (!c->d_nodes[comp]) FR_CHECK(c, cudaMalloc(&c->d_nodes[comp], sizeof(b2fr_node) * 21 * (size_t)nmb));
+  b2fr_node *d = c->d_nodes[comp];
   FdArgs a;
   a.org = c->d_org[comp]; a.refC = c->d_ref[0][comp]; a.w = comp_w(c, comp); a.mbw = mbw; a.nmb = nmb;
   for (int s = 0; s < 4; s++) { a.xy[s] = c->d_xy[s][comp]; a.so[s] = c->d_so[s][comp]; a.rms[s] = c->d_rms[s][comp]; }
@@ -597,8 +641,46 @@ extern "C" int b2fr_encode_plane(b2fr_ctx *c, int con, const double tol[3], b2fr
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(nodes, d, sizeof(b2fr_node) * 21 * (size_t)nmb, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFreeAsync(d, c->stream);
   if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "b2fr_encode_plane: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
+  c->nodes_valid[comp] = 1;
+  return B2ME_OK;
+}
+
+extern "C" int b2fr_decode_plane(b2fr_ctx *c, int con, const b2fr_node *nodes, uint8_t *rec)
+{
+  if (!c || con < 1 || con > 3 || !rec) return B2ME_EINVAL;
+  FR_CHECK(c, cudaSetDevice(c->device));
+  const int comp = con - 1, w = comp_w(c, comp), h = comp_h(c, comp);
+  const int mbw = comp_mbw(c, comp), nmb = mbw * comp_mbh(c, comp);
+  if (nmb == 0) { snprintf(c->err, sizeof(c->err), "component %d has no whole macroblock", comp); return B2ME_EINVAL; }
+  if (!c->d_nodes[comp]) FR_CHECK(c, cudaMalloc(&c->d_nodes[comp], sizeof(b2fr_node) * 21 * (size_t)nmb));
+  if (nodes) {
+    // the displaced blocks must lie inside the plane (the search's bound_chk guarantees it for its own trees)
+    for (int mb = 0; mb < nmb; mb++)
+      for (int k = 0; k < 21; k++) {
+        const b2fr_node &t = nodes[(size_t)mb * 21 + k];
+        const int x0 = (mb % mbw) * 16, y0 = (mb / mbw) * 16;
+        if (x0 + t.x < -16 || y0 + t.y < -16 || x0 + t.x > w || y0 + t.y > h || abs(t.x) > 64 || abs(t.y) > 64) {
+          snprintf(c->err, sizeof(c->err), "b2fr_decode_plane: node %d of macroblock %d displaces its block out of the plane", k, mb);
+          return B2ME_EINVAL;
+        }
+      }
+    FR_CHECK(c, cudaMemcpyAsync(c->d_nodes[comp], nodes, sizeof(b2fr_node) * 21 * (size_t)nmb, cudaMemcpyHostToDevice, c->stream));
+    c->nodes_valid[comp] = 1;
+  } else if (!c->nodes_valid[comp]) {
+    snprintf(c->err, sizeof(c->err), "b2fr_decode_plane: no trees on the device for component %d (call b2fr_encode_plane or pass nodes)", con);
+    return B2ME_EINVAL;
+  }
+  if (!c->d_rec) FR_CHECK(c, cudaMalloc(&c->d_rec, (size_t)c->W * c->H));
+  FR_CHECK(c, cudaMemsetAsync(c->d_rec, 0, (size_t)w * h, c->stream));
+  FpArgs a;
+  for (int s = 0; s < 4; s++) { a.ref[s] = c->d_ref[s][comp]; a.s4[s] = c->d_s4[s][comp]; }
+  a.w = w; a.h = h; a.mbw = mbw; a.nodes = c->d_nodes[comp]; a.out = c->d_rec;
+  k_frac_predict<<<nmb, 256, 0, c->stream>>>(a);
+  c->launches++;
+  FR_CHECK(c, cudaGetLastError());
+  FR_CHECK(c, cudaMemcpyAsync(rec, c->d_rec, (size_t)w * h, cudaMemcpyDeviceToHost, c->stream));
+  FR_CHECK(c, cudaStreamSynchronize(c->stream));
   return B2ME_OK;
 }
 

@@ -257,6 +257,13 @@ typedef struct b2fr_node {
   double scale, offset;
 } b2fr_node;                  /* 40 bytes */
 int b2fr_encode_plane(b2fr_ctx *ctx, int con, const double tol[3], b2fr_node *nodes);
+/* F8 -- the fractal prediction of EVERY macroblock of component `con` from its TRANS_NODE tree:
+ *   <- decode_one_macroblock V1/src/block_dec.c:20-283, decode_block_rect :285, decode_block_8 :760, decode_block_4 :978
+ * Each leaf block becomes (unsigned char) bound(0.5 + scale * d + offset - scale * mean_d), d = the block of plane set
+ * `reference` displaced by (x, y), mean_d = its sum / n.  nodes [nmb][21] as b2fr_encode_plane returns them, or NULL: use the
+ * trees the last b2fr_encode_plane of this component left on the device (search -> cascade -> prediction without a round
+ * trip).  rec: the component plane, tightly packed (rows / columns beyond the last whole macroblock are 0). */
+int b2fr_decode_plane(b2fr_ctx *ctx, int con, const b2fr_node *nodes, uint8_t *rec);
 /* parity read-back of the sum tables: domain table of block size bw x bh at every pixel offset
  * ([h][w] int32, 0 where the block does not fit), range 4x4 table on the block grid ([h/4][w/4]) */
 int b2fr_get_domain_table(b2fr_ctx *ctx, int plane_set, int con, int bw, int bh, int squares, int32_t *out);

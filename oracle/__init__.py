@@ -357,6 +357,13 @@ class V1Ref:
                 xy[mb, p], so[mb, p], rms[mb, p] = a, b, r
         return xy, so, rms
 
+    def decode_plane(self, con):
+        """decode_one_macroblock of every macroblock of component con from the trees the last encode_mb calls left"""
+        w, h = (self.W, self.H) if con == 1 else (self.W // 2, self.H // 2)
+        out = np.zeros((h, w), np.uint8)
+        self.L.v1h_decode_plane(C.c_int(con), _ptr(out))
+        return out
+
     def reset_trans(self):
         """fresh TRANS_NODE trees (call between components: the harness indexes one tree array by macroblock number)"""
         self.L.v1h_reset_trans()
@@ -386,6 +393,19 @@ def v1_encode_plane(org, refC, xy, so, rms, tol):
     orc_lib().orc_v1_encode_plane(_ptr(org), _ptr(refC), C.c_int(w), C.c_int(mbw), C.c_int(mbh), _ptr(xy), _ptr(so), _ptr(rms),
                                   _ptr(tol), _ptr(nodes))
     return nodes
+
+
+def v1_decode_plane(sets, nodes):
+    """F8: decode_one_macroblock of every macroblock; sets = the four domain planes (C, H, M, N) of the component"""
+    sets = [np.ascontiguousarray(p, np.uint8) for p in sets]
+    h, w = sets[0].shape
+    mbw, mbh = w // 16, h // 16
+    nodes = np.ascontiguousarray(nodes, V1_NODE)
+    assert nodes.shape == (mbw * mbh, 21)
+    out = np.zeros((h, w), np.uint8)
+    orc_lib().orc_v1_decode_plane(_ptr(sets[0]), _ptr(sets[1]), _ptr(sets[2]), _ptr(sets[3]), C.c_int(w), C.c_int(mbw), C.c_int(mbh),
+                                  _ptr(nodes), _ptr(out))
+    return out
 
 
 def v1_box_table(img, bw, bh, squares):

@@ -260,3 +260,55 @@ void orc_v1_encode_plane(const uint8_t *org, const uint8_t *refC, int w, int mbw
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * F8: the fractal prediction -- decode_one_macroblock (V1/src/block_dec.c:20-283), decode_block_rect (:285-758),
+ * decode_block_8 (:760-976), decode_block_4 (:978-) for num_regions == 1: every leaf block of the TRANS_NODE tree is
+ *     rec = (unsigned char) bound(0.5 + scale * d + offset - scale * mean_d)          (:232, :726, :913)
+ * with d the displaced block of plane set `reference` (0 C, 1 H, 2 M, 3 N) and mean_d its sum table entry / n.
+ * A macroblock / 8x8 block with partition 0 is one leaf, 1 or 2 two rectangles, anything else four quarters.
+ * ------------------------------------------------------------------------------------------------ */
+static void v1_leaf(const uint8_t *const *sets, int w, const OrcV1Node *t, int bx, int by, int bw, int bh, int mb_level, uint8_t *out)
+{
+  /* macroblock level: reference > 3 selects the *_temp set = C (block_dec.c:148-152); below: anything but 0,1,2 is N (:410-414) */
+  const uint8_t *ref = sets[t->reference >= 0 && t->reference <= 3 ? t->reference : (mb_level ? 0 : 3)];
+  const int ox = bx + t->x, oy = by + t->y;
+  double sum = 0, avg; int i, j;
+  for (j = 0; j < bh; j++) for (i = 0; i < bw; i++) sum += ref[(size_t)(oy + j) * w + ox + i];
+  avg = sum / (double)(bh * bw);
+  for (j = 0; j < bh; j++)
+    for (i = 0; i < bw; i++) {
+      const double a = 0.5 + t->scale * ref[(size_t)(oy + j) * w + ox + i] + t->offset - t->scale * avg;
+      out[(size_t)(by + j) * w + bx + i] = (unsigned char)(a < 0.0 ? 0 : (a > 255.0 ? 255 : a));
+    }
+}
+
+void orc_v1_decode_plane(const uint8_t *refC, const uint8_t *refH, const uint8_t *refM, const uint8_t *refN,
+                         int w, int mbw, int mbh, const OrcV1Node *nodes /*[nmb][21]*/, uint8_t *out /* [h][w], zero where no macroblock */)
+{
+  const uint8_t *sets[4]; int mb, k, i;
+  sets[0] = refC; sets[1] = refH; sets[2] = refM; sets[3] = refN;
+  for (mb = 0; mb < mbw * mbh; mb++) {
+    const OrcV1Node *root = nodes + (size_t)mb * 21;
+    const int bx = (mb % mbw) * 16, by = (mb / mbw) * 16;
+    if (root->partition == 0) { v1_leaf(sets, w, root, bx, by, 16, 16, 1, out); continue; }
+    if (root->partition == 1 || root->partition == 2) {
+      for (i = 0; i < 2; i++)
+        if (root->partition == 1) v1_leaf(sets, w, root + 1 + 5 * i, bx, by + 8 * i, 16, 8, 0, out);
+        else v1_leaf(sets, w, root + 1 + 5 * i, bx + 8 * i, by, 8, 16, 0, out);
+      continue;
+    }
+    for (k = 0; k < 4; k++) {
+      const OrcV1Node *c = root + 1 + 5 * k;
+      const int cx = bx + (k & 1) * 8, cy = by + (k >> 1) * 8;
+      if (c->partition == 0) v1_leaf(sets, w, c, cx, cy, 8, 8, 0, out);
+      else if (c->partition == 1 || c->partition == 2)
+        for (i = 0; i < 2; i++) {
+          if (c->partition == 1) v1_leaf(sets, w, c + 1 + i, cx, cy + 4 * i, 8, 4, 0, out);
+          else v1_leaf(sets, w, c + 1 + i, cx + 4 * i, cy, 4, 8, 0, out);
+        }
+      else
+        for (i = 0; i < 4; i++) v1_leaf(sets, w, c + 1 + i, cx + (i & 1) * 4, cy + (i >> 1) * 4, 4, 4, 0, out);
+    }
+  }
+}

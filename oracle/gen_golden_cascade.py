@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY.  Generates tests/golden/v1_cascade.npz from the UNMODIFIED reference: the TRANS_NODE tree
 encode_one_macroblock (V1/src/block_enc.c:508) leaves for every macroblock of seeded synthetic frames (driven through
-oracle/v1_harness.c), luma and chroma, with the four plane sets C/H/M/N loaded (case "loaded") and with H/M/N left
+oracle/v1_harness.c) and the planes decode_one_macroblock (V1/src/block_dec.c:20) reconstructs from them, luma and chroma, with the four plane sets C/H/M/N loaded (case "loaded") and with H/M/N left
 as the shipped program leaves them, all zero (case "zero").  Tolerances are chosen so that every outcome of the
 cascade occurs: 16x16 kept, 8x8 kept, 8x4 / 4x8 accepted, 4x4, winners from every plane set.
 
@@ -56,6 +56,7 @@ def run_case(name):
         v.reset_trans()
         nmb = (W // 16) * (H // 16) if con == 1 else (W // 32) * (H // 32)
         out[f"nodes_{con}"] = np.stack([node_rows(*v.encode_mb(mb, con)) for mb in range(nmb)])
+        out[f"rec_{con}"] = v.decode_plane(con)        # decode_one_macroblock (V1/src/block_dec.c:20) on those trees
     np.savez_compressed(os.path.join(GOLD, f"v1_cascade_{name}.npz"), **out)
     n1 = out["nodes_1"]
     print(name, "root partitions", np.bincount(n1[:, 0]["partition"], minlength=4), "8x8 partitions",

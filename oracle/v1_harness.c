@@ -214,3 +214,27 @@ int v1h_encode_mb(int CurMb, int con, int32_t *out, double *out_d, int maxn)
   }
   return n;
 }
+
+/* ---- F8: the fractal prediction of decode_one_macroblock (V1/src/block_dec.c:20, decode_block_rect :285,
+ * decode_block_8 :760, decode_block_4 :978) from the TRANS_NODE trees the cascade left.  block_dec.c also holds the
+ * intra / inverse-transform code of the decoder; the symbols only that code needs are stubbed here. ---- */
+#include "block_dec.h"
+StorablePicture *dec_picture;
+const byte QP_SCALE_CR[52] = {0};
+const int dequant_coef[6][4][4] = {{{0}}};
+void error(char *text, int code) { (void)text; (void)code; abort(); }
+void getNeighbour(int curr_mb_nr, int xN, int yN, int luma, PixelPos *pix) { (void)curr_mb_nr; (void)xN; (void)yN; (void)luma; (void)pix; abort(); }
+
+/* reconstruct every macroblock of component con from the current trees: out = the component plane */
+void v1h_decode_plane(int con, uint8_t *out)
+{
+  int w = con == 1 ? g_W : g_W / 2, h = con == 1 ? g_H : g_H / 2, mb, i;
+  int nmb = con == 1 ? (g_W / 16) * (g_H / 16) : (g_W / 32) * (g_H / 32);
+  byte **rec;
+  if (!imgY_rec) { imgY_rec = alloc2b(g_H, g_W); imgUV_rec = alloc_uv(g_H / 2, g_W / 2); }
+  rec = con == 1 ? imgY_rec : imgUV_rec[con - 2];
+  for (i = 0; i < h; i++) memset(rec[i], 0, (size_t)w);
+  currentVideo = 'C';
+  for (mb = 0; mb < nmb; mb++) decode_one_macroblock(mb, g_trans, con);
+  for (i = 0; i < h; i++) memcpy(out + (size_t)i * w, rec[i], (size_t)w);
+}

@@ -123,6 +123,9 @@ def test_cascade_matches_reference_golden(golden_dir, name):
         nodes, exp = f.encode_plane(con, tol), g[f"nodes_{con}"]
         for k in ("block_type", "partition", "reference", "x", "y", "scale", "offset"):
             assert (nodes[k] == exp[k]).all(), (con, k, int((nodes[k] != exp[k]).sum()))
+        # F8: the prediction of decode_one_macroblock, from the trees still on the device and from trees handed in
+        assert (f.decode_plane(con) == g[f"rec_{con}"]).all(), con
+        assert (f.decode_plane(con, exp) == g[f"rec_{con}"]).all(), con
 
 
 def test_cascade_matches_oracle_cif():
@@ -143,5 +146,10 @@ def test_cascade_matches_oracle_cif():
                                      np.stack([r[2] for r in res]), tol)
         for k in ("block_type", "partition", "reference", "x", "y", "scale", "offset"):
             assert (nodes[k] == exp[k]).all(), (con, k)
+        rec = f.decode_plane(con)
+        assert (rec == oracle.v1_decode_plane(doms, exp)).all(), con
+        # hand-made trees reach the macroblock-level rectangles the encoder never leaves (partition 1 / 2)
+        alt = exp.copy(); alt[:, 0]["partition"] = np.arange(len(alt)) % 3
+        assert (f.decode_plane(con, alt) == oracle.v1_decode_plane(doms, alt)).all(), con
         if con == 1:
             assert len(np.unique(nodes[:, 0]["partition"])) == 2 and len(np.unique(nodes[:, [1, 6, 11, 16]]["partition"])) >= 3

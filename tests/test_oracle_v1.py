@@ -88,6 +88,9 @@ def test_cascade_matches_reference_golden(golden_dir, name):
         exp = g[f"nodes_{con}"]
         for f in ("block_type", "partition", "reference", "x", "y", "scale", "offset"):
             assert (nodes[f] == exp[f]).all(), (con, f)
+        # F8: decode_one_macroblock (block_dec.c:20) on those trees
+        rec = oracle.v1_decode_plane([sets[s][con - 1] for s in range(4)], exp)
+        assert (rec == g[f"rec_{con}"]).all(), con
     n1 = g["nodes_1"]
     if name == "loaded":      # the fixture reaches every outcome of the cascade
         assert set(np.unique(n1[:, 0]["partition"])) == {0, 3}
