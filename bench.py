@@ -139,6 +139,57 @@ def pool_leg(device, peaks, nd=16384):
     return out
 
 
+def fractal_leg(device, with_cpu):
+    """BASELINE config 2 (secondary line): one version1 P frame, CIF 352x288 4:2:0, Search_Range 7, the four plane sets
+    searched for every range block of every level, the partition cascade and the prediction of all three components --
+    b2fr_set_domain / b2fr_set_range / b2fr_encode_plane / b2fr_decode_plane through the host-pointer C ABI (copies
+    inside the timed region).  with_cpu: the unmodified version1 code (oracle/_ref/libv1ref.so: compute_domain_Sum,
+    compute_range_Sum, encode_one_macroblock, decode_one_macroblock) on ONE host core on the same frame, and a byte
+    comparison of the two reconstructions (the cpu_baseline leg is the one place bench.py may run oracle/)."""
+    from h264_b200 import api, synth
+    Wc, Hc, Rc, tol = 352, 288, 7, (3.5, 4.5, 2.0)
+    ref, cur = synth.yuv_pair(Wc, Hc, seed=3, shift=(0, 0), gain=1.0, offset=0.0, noise=4.0)
+    f = api.FractalSearcher(Wc, Hc, Rc, device=device)
+
+    def frame():
+        f.set_domain(0, *ref, build_sums=True)
+        f.set_range(*cur)
+        return [(f.encode_plane(con, tol), f.decode_plane(con)) for con in (1, 2, 3)]
+    for _ in range(3):
+        out = frame()
+    n = 10
+    t0 = time.perf_counter()
+    for _ in range(n):
+        out = frame()
+    ms = (time.perf_counter() - t0) * 1e3 / n
+    nmb = (Wc // 16) * (Hc // 16) + 2 * (Wc // 32) * (Hc // 32)
+    res = {"workload": f"{Wc}x{Hc} 4:2:0, Search_Range {Rc}, 41 range blocks/MB x 4 plane sets, cascade + prediction, Y+U+V",
+           "kernels": "k_frac_domain_sums, k_frac_range_sums, k_frac_window, k_frac_decide, k_frac_predict",
+           "ms_per_frame_host_api": ms, "mb_per_s": nmb / (ms * 1e-3), "split_macroblocks": int((out[0][0][:, 0]["partition"] != 0).sum()),
+           "rec_checksum": int(sum(int(o[1].astype(np.int64).sum()) for o in out)), "launches_per_frame": None}
+    l0 = f.launch_count(); frame(); res["launches_per_frame"] = int(f.launch_count() - l0)
+    if with_cpu:
+        import oracle
+        if oracle.have_v1ref():
+            v = oracle.V1Ref(Wc, Hc, Rc, tol=tol)
+            t0 = time.perf_counter()
+            v.set_ref(0, *ref, build_sums=True)
+            v.set_cur(*cur)
+            same = True
+            for con in (1, 2, 3):
+                v.reset_trans()
+                for mb in range((Wc // 16) * (Hc // 16) if con == 1 else (Wc // 32) * (Hc // 32)):
+                    v.encode_mb(mb, con)
+                same = same and bool((v.decode_plane(con) == out[con - 1][1]).all())
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            res["cpu_reference"] = {"ms_per_frame": cpu_ms, "cores": 1, "kind": "reference",
+                                    "note": "unmodified version1 compute.c / block_enc.c / block_dec.c, gcc -O2; it searches the "
+                                            "plane sets lazily (only the blocks its cascade reaches), the GPU path all of them",
+                                    "reconstruction_identical": same}
+    f.close()
+    return res
+
+
 def _cpu_worker(job):
     """One process of the CPU reference arm: its own copy of the reference state, its own MB range."""
     first, cnt, trial = job
@@ -363,7 +414,7 @@ def main():
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tr_path):
         roofline["traffic"] = json.load(open(tr_path)).get("k_sad_fs")
-    secondary = {"fractal_pool": pool_leg(local, peaks)}
+    secondary = {"fractal_pool": pool_leg(local, peaks), "fractal_window": fractal_leg(local, not args.no_cpu)}
     cpu = None if args.no_cpu else cpu_reference(15.0)
     line = {"metric": UNIT, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",

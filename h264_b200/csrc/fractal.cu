@@ -35,6 +35,7 @@ struct b2fr_ctx {
   int *d_xy[4][3]; double *d_so[4][3]; double *d_rms[4][3];
   int *h_xy[4][3]; double *h_so[4][3]; double *h_rms[4][3];
   int valid[4][3];              // host copy of (set, comp) results is current
+  int dvalid[4][3];             // device results of (set, comp) are current
   b2fr_node *d_nodes[3];        // TRANS_NODE trees of the last b2fr_encode_plane / b2fr_decode_plane per component [nmb][21]
   int nodes_valid[3];
   uint8_t *d_rec;               // reconstructed plane scratch
@@ -505,7 +506,7 @@ extern "C" void b2fr_destroy(b2fr_ctx *c)
 static void invalidate(b2fr_ctx *c, int set)
 {
   for (int s = 0; s < 4; s++)
-    if (set < 0 || s == set) for (int k = 0; k < 3; k++) c->valid[s][k] = 0;
+    if (set < 0 || s == set) for (int k = 0; k < 3; k++) c->valid[s][k] = c->dvalid[s][k] = 0;
   for (int k = 0; k < 3; k++) c->nodes_valid[k] = 0;       // trees of other pictures
 }
 
@@ -566,10 +567,20 @@ static int run_window(b2fr_ctx *c, int set, int comp)
   return B2ME_OK;
 }
 
+// results of (set, comp) on the device only (what the cascade needs); ensure() adds the host copy the look-up calls read
+static int ensure_dev(b2fr_ctx *c, int set, int comp)
+{
+  if (c->dvalid[set][comp]) return B2ME_OK;
+  int r = run_window(c, set, comp);
+  if (r) return r;
+  c->dvalid[set][comp] = 1;
+  return B2ME_OK;
+}
+
 static int ensure(b2fr_ctx *c, int set, int comp)
 {
   if (c->valid[set][comp]) return B2ME_OK;
-  int r = run_window(c, set, comp);
+  int r = ensure_dev(c, set, comp);
   if (r) return r;
   const size_t nr = (size_t)comp_mbw(c, comp) * comp_mbh(c, comp) * NPART;
   FR_CHECK(c, cudaMemcpyAsync(c->h_xy[set][comp], c->d_xy[set][comp], nr * 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -628,7 +639,7 @@ extern "C" int b2fr_encode_plane(b2fr_ctx *c, int con, const double tol[3], b2fr
   if (!c || con < 1 || con > 3 || !tol || !nodes) return B2ME_EINVAL;
   FR_CHECK(c, cudaSetDevice(c->device));
   const int comp = con - 1;
-  for (int s = 0; s < 4; s++) { int r = ensure(c, s, comp); if (r) return r; }
+  for (int s = 0; s < 4; s++) { int r = ensure_dev(c, s, comp); if (r) return r; }
   const int mbw = comp_mbw(c, comp), nmb = mbw * comp_mbh(c, comp);
   if (!c->d_nodes[comp]) FR_CHECK(c, cudaMalloc(&c->d_nodes[comp], sizeof(b2fr_node) * 21 * (size_t)nmb));
   b2fr_node *d = c->d_nodes[comp];
