@@ -739,7 +739,7 @@ __device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWa
     __syncwarp();
     const uint32_t parity = (uint32_t)C.tma_uses & 1u;
     const long long tw0 = clock64();
-    while (!mbar_try_wait(&C.mbar, parity)) { }
+    while (!mbar_try_wait_ns(&C.mbar, parity, 2000u)) { if (a.flags & 2) __nanosleep(400); }
     __syncwarp();
     if (lane == 0) { C.tma_uses++; atomicAdd(&st->cyc[5], (unsigned long long)(clock64() - tw0)); }
   } else {                                         // window leaves the search plane: per-pixel coordinate clamp
@@ -864,7 +864,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         }
       }
       if (nend == 2) break;
-      if (!any) mbar_try_wait_ns(&evt, evp, 20000u);   // (two completions inside one scan would be seen at the time-out)
+      if (!any && !mbar_try_wait_ns(&evt, evp, 20000u) && (a.flags & 2)) __nanosleep(1000);   // (two completions inside one scan would be seen at the time-out)
     }
     if (lane == 0) atomicAdd(&st.cyc[2], (unsigned long long)(clock64() - t_p0));
   } else {
