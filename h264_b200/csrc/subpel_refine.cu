@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(32 * WPC) k_subpel_refine(const SubArgs a)
       // BlockMotionSearch resets the bound when the metric changes between levels (mv_search.c:971-974)
       S.mincost[p] = a.use_bound ? a.cost_int[base + p] : DMAX;
     }
+    const bool allp = a.part_mask == ((1ull << NPART) - 1);
     const int nstage = a.full81 ? 1 : 2;
     for (int stage = 0; stage < nstage; stage++) {
       // full81: full_sub_pel_motion_estimation (me_fullsearch.c:409-469): ONE stage, the 81 quarter-pel positions of
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(32 * WPC) k_subpel_refine(const SubArgs a)
       for (int i = lane; i < NPART * NC; i += 32) (&S.dist[0][0])[i] = 0;
       __syncwarp();
       for (int job = lane; job < 16 * ncand; job += 32) {
-        const int k = job / ncand, c = job - k * ncand;
+        const int k = NC == 9 ? (job * 57) >> 9 : job / ncand, c = job - k * ncand;      // job / 9 for job < 144
         if (c < first) continue;
         const int tx = (k & 3) * 4, ty = (k >> 2) * 4;
         uint32_t keys[7]; int vals[7];
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(32 * WPC) k_subpel_refine(const SubArgs a)
         for (int bti = 0; bti < 7; bti++) {
           keys[bti] = 0xffffffffu; vals[bti] = 0;
           const int p = part_of_tile(bti, tx, ty);
-          if (!((a.part_mask >> p) & 1ull)) continue;
+          if (!allp && !((a.part_mask >> p) & 1ull)) continue;
           const uint32_t mvw = *reinterpret_cast<const uint32_t *>(&S.mv[p][0]);
           int v = -1;
           uint32_t kk;
@@ -172,11 +173,26 @@ __global__ void __launch_bounds__(32 * WPC) k_subpel_refine(const SubArgs a)
       for (int p = lane; p < NPART; p += 32) {
         if (!((a.part_mask >> p) & 1ull)) continue;
         long long best = S.mincost[p]; int best_pos = 0;
-        for (int cc = first; cc < ncand; cc++) {
-          int spx, spy; sp_xy(cc, &spx, &spy);
-          const int mvx = S.mv[p][0] + step * spx, mvy = S.mv[p][1] + step * spy;
-          const long long cost = (long long)lam * (mvbits(mvx - S.prd[p][0]) + mvbits(mvy - S.prd[p][1])) + ((long long)S.dist[p][cc] << 5);
-          if (cost < best) { best = cost; best_pos = cc; }
+        if (NC == 9) {
+          // the nine positions share three x and three y displacements: six mvbits instead of eighteen
+          const int dx = S.mv[p][0] - S.prd[p][0], dy = S.mv[p][1] - S.prd[p][1];
+          const int bxm = mvbits(dx - step), bx0 = mvbits(dx), bxp = mvbits(dx + step);
+          const int bym = mvbits(dy - step), by0 = mvbits(dy), byp = mvbits(dy + step);
+#pragma unroll
+          for (int cc = 0; cc < 9; cc++) {
+            if (cc < first) continue;
+            const int spx = (int)((0x22215u >> (2 * cc)) & 3u) - 1, spy = (int)((0x29421u >> (2 * cc)) & 3u) - 1;   // compile-time per cc
+            const int bits = (spx < 0 ? bxm : (spx > 0 ? bxp : bx0)) + (spy < 0 ? bym : (spy > 0 ? byp : by0));
+            const long long cost = (long long)lam * bits + ((long long)S.dist[p][cc] << 5);
+            if (cost < best) { best = cost; best_pos = cc; }
+          }
+        } else {
+          for (int cc = first; cc < ncand; cc++) {
+            int spx, spy; sp_xy(cc, &spx, &spy);
+            const int mvx = S.mv[p][0] + step * spx, mvy = S.mv[p][1] + step * spy;
+            const long long cost = (long long)lam * (mvbits(mvx - S.prd[p][0]) + mvbits(mvy - S.prd[p][1])) + ((long long)S.dist[p][cc] << 5);
+            if (cost < best) { best = cost; best_pos = cc; }
+          }
         }
         { int spx, spy; sp_xy(best_pos, &spx, &spy);
           S.mv[p][0] = (short)(S.mv[p][0] + step * spx); S.mv[p][1] = (short)(S.mv[p][1] + step * spy); }
