@@ -124,6 +124,11 @@ class Searcher:
     def set_ref_dev(self, r, t, stream=0):
         self._chk(self.L.b2me_set_ref_dev(self.h, C.c_int(r), _dp(t), C.c_int(t.stride(0)), _vp(stream)), "b2me_set_ref_dev")
 
+    def set_ref_rows_dev(self, r, t, row_first, row_count, stream=0):
+        """planes of luma rows [row_first, row_first + row_count) only (MB-row bands), from a full-geometry CUDA picture"""
+        self._chk(self.L.b2me_set_ref_rows_dev(self.h, C.c_int(r), _dp(t), C.c_int(t.stride(0)), C.c_int(row_first), C.c_int(row_count),
+                                               _vp(stream)), "b2me_set_ref_rows_dev")
+
     def subplane(self, r, yy, xx):
         out = np.zeros((self.H + 2 * PAD_Y, self.W + 2 * PAD_X), np.uint8)
         self._chk(self.L.b2me_get_subplane(self.h, C.c_int(r), C.c_int(yy), C.c_int(xx), _p(out)), "b2me_get_subplane")

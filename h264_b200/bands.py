@@ -97,9 +97,16 @@ class BandSearcher:
         self.s.set_cur_dev(cur_full, stream)
 
     def set_ref_from_band(self, ref_idx, own_band, stream=0, group=None):
-        """Halo exchange of the reconstructed band (NCCL), then the sub-pel / search planes of the reference."""
-        full = exchange_halos(own_band, self.H, self.W, self.R, self.max_center, group=group)
-        self.s.set_ref_dev(ref_idx, full, stream)
+        """Halo exchange of the reconstructed band (NCCL), then the sub-pel / search planes of the rows this band reads
+        (own rows + halo: b2me_set_ref_rows_dev), in a picture buffer that is allocated once."""
+        if getattr(self, "_full", None) is None or self._full.device != own_band.device:
+            self._full = torch.zeros((self.H, self.W), dtype=torch.uint8, device=own_band.device)
+        full = exchange_halos(own_band, self.H, self.W, self.R, self.max_center, group=group, out=self._full)
+        lo, hi = needed_rows(self.rank, self.world, self.mbh, self.R, self.max_center)
+        if full.is_cuda:
+            self.s.set_ref_rows_dev(ref_idx, full, lo, hi - lo, stream)
+        else:
+            self.s.set_ref_dev(ref_idx, full, stream)
         return full
 
     def search(self, pred, center, params, mv_int, cost_int, mv_sub, cost_sub, stream=0):

@@ -185,11 +185,11 @@ static int after_uploads(b2me_ctx *c, cudaStream_t s)
   return B2ME_OK;
 }
 
-static int build_planes(b2me_ctx *c, int ref_idx, const uint8_t *luma_dev, int stride, cudaStream_t s)
+static int build_planes(b2me_ctx *c, int ref_idx, const uint8_t *luma_dev, int stride, cudaStream_t s, int row_lo = 0, int row_hi = 1 << 30)
 {
   FamilyTimer t(c, 1, s);
-  B2_CUDA_CHECK(c, launch_subpel_planes(luma_dev, stride, c->W, c->H, c->d_planes + (size_t)ref_idx * 16 * c->plane_size, s));
-  B2_CUDA_CHECK(c, launch_search_plane(luma_dev, stride, c->W, c->H, c->d_spl + (size_t)ref_idx * 16 * c->Wq * c->Hq, c->Wq, c->Hq, c->spad, s));
+  B2_CUDA_CHECK(c, launch_subpel_planes(luma_dev, stride, c->W, c->H, c->d_planes + (size_t)ref_idx * 16 * c->plane_size, row_lo, row_hi, s));
+  B2_CUDA_CHECK(c, launch_search_plane(luma_dev, stride, c->W, c->H, c->d_spl + (size_t)ref_idx * 16 * c->Wq * c->Hq, c->Wq, c->Hq, c->spad, row_lo, row_hi, s));
   c->launches += 3;
   if (c->wp_apply[ref_idx]) {          // weighted reference: map the planes the distortions read (see k_apply_wp)
     B2_CUDA_CHECK(c, launch_apply_wp(c->d_planes + (size_t)ref_idx * 16 * c->plane_size, c->plane_size * 16,
@@ -214,6 +214,13 @@ extern "C" int b2me_set_ref_dev(b2me_ctx *c, int ref_idx, const uint8_t *luma_de
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
   { int r0 = after_uploads(c, (cudaStream_t)stream); if (r0) return r0; }
   return build_planes(c, ref_idx, luma_dev, stride, (cudaStream_t)stream);
+}
+extern "C" int b2me_set_ref_rows_dev(b2me_ctx *c, int ref_idx, const uint8_t *luma_dev, int stride, int row_first, int row_count, void *stream)
+{
+  if (!c || !luma_dev || stride < c->W || ref_idx < 0 || ref_idx >= c->nrefs || row_first < 0 || row_count < 0 || row_first + row_count > c->H) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  { int r0 = after_uploads(c, (cudaStream_t)stream); if (r0) return r0; }
+  return build_planes(c, ref_idx, luma_dev, stride, (cudaStream_t)stream, row_first, row_first + row_count);
 }
 extern "C" int b2me_set_ref(b2me_ctx *c, int ref_idx, const uint8_t *luma, int stride)
 {

@@ -100,11 +100,11 @@ struct McArgs {
   uint8_t *orig_blk, *pred_blk;
 };
 cudaError_t launch_mc_luma(const McArgs &a, cudaStream_t s);
-cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, cudaStream_t s);
+cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, int row_lo, int row_hi, cudaStream_t s);
 cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, cudaStream_t s, int *smem_bytes_out);
 FsGeom fs_geom_host(int R);
 cudaError_t launch_apply_wp(uint8_t *buf, size_t bytes, int weight, int offset, int log_denom, cudaStream_t s);
-cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, cudaStream_t s);
+cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, int row_lo, int row_hi, cudaStream_t s);
 cudaError_t launch_subpel_refine(const SubArgs &a, cudaStream_t s);
 cudaError_t ubench(int kind, int iters, double *gops);
 cudaError_t launch_distortion(int kind, int n, int nblk, const int16_t *diff, long long *out, cudaStream_t s);

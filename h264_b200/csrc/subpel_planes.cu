@@ -23,12 +23,12 @@ constexpr int TX = 32, TY = 8;   // output tile per CTA (kernel 1)
 
 // Kernel 1: planes [0][0], [0][2], [2][0], [2][2].
 __global__ void __launch_bounds__(TX * TY) k_half_planes(const uint8_t *__restrict__ luma, int pitch, int W, int H,
-                                                          uint8_t *__restrict__ planes, int Wp, int Hp)
+                                                          uint8_t *__restrict__ planes, int Wp, int Hp, int ybase, int yend)
 {
   // tile of clamped luma: rows y-2..y+3, cols x-2..x+3 around each output sample
   __shared__ uint8_t sl[TY + 5][TX + 5 + 3];
   __shared__ int sh[TY + 5][TX];           // unrounded horizontal 6-tap for rows y-2..y+3
-  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int x0 = blockIdx.x * TX, y0 = ybase + blockIdx.y * TY;      // plane rows [ybase, yend): MB-row bands build only what they read
   const int tid = threadIdx.y * TX + threadIdx.x;
   for (int i = tid; i < (TY + 5) * (TX + 5); i += TX * TY) {
     int r = i / (TX + 5), c = i % (TX + 5);
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(TX * TY) k_half_planes(const uint8_t *__restri
   }
   __syncthreads();
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  if (x >= Wp || y >= Hp) return;
+  if (x >= Wp || y >= yend) return;
   const int r = threadIdx.y + 2, c = threadIdx.x;
   const size_t PS = (size_t)Wp * Hp, o = (size_t)y * Wp + x;
   int p00 = sl[r][c + 2];
@@ -62,9 +62,9 @@ __global__ void __launch_bounds__(TX * TY) k_half_planes(const uint8_t *__restri
 
 // Kernel 2: the twelve quarter planes, (a+b+1)>>1 of two of the four planes above
 // (img_luma.c:653-678).  One thread per 4 horizontally adjacent samples.
-__global__ void __launch_bounds__(256) k_quarter_planes(uint8_t *__restrict__ planes, int Wp, int Hp)
+__global__ void __launch_bounds__(256) k_quarter_planes(uint8_t *__restrict__ planes, int Wp, int Hp, int ybase)
 {
-  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = ybase + blockIdx.y;
   if (x >= Wp) return;
   const size_t PS = (size_t)Wp * Hp;
   const size_t r = (size_t)y * Wp, rn = (size_t)min(y + 1, Hp - 1) * Wp;
@@ -102,11 +102,11 @@ __global__ void __launch_bounds__(256) k_quarter_planes(uint8_t *__restrict__ pl
 // bytes: out[s][y][x] = P[y][x+s].  TMA boxes must start on 16-byte boundaries; the shifted planes make
 // every byte column reachable.  HBM-bound: W*H read, 16*Wq*Hq written.
 __global__ void __launch_bounds__(256) k_search_plane(const uint8_t *__restrict__ luma, int pitch, int W, int H,
-                                                       uint8_t *__restrict__ out, int Wq, int Hq, int spad)
+                                                       uint8_t *__restrict__ out, int Wq, int Hq, int spad, int ybase, int yend)
 {
   const int wq4 = Wq >> 2;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= wq4 * Hq) return;
+  const int i = ybase * wq4 + blockIdx.x * blockDim.x + threadIdx.x;      // plane rows [ybase, yend)
+  if (i >= wq4 * yend) return;
   const int y = i / wq4, x = (i - y * wq4) * 4;
   const uint8_t *row = luma + (size_t)iclamp(y - spad, 0, H - 1) * pitch;
   uint32_t b[19];
@@ -142,20 +142,26 @@ cudaError_t launch_apply_wp(uint8_t *buf, size_t bytes, int weight, int offset, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, cudaStream_t s)
+// row_lo / row_hi: luma rows [row_lo, row_hi) whose planes are (re)built; the pad above / below goes with the first /
+// last picture row.  The whole picture: 0, H.
+cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, int row_lo, int row_hi, cudaStream_t s)
 {
-  const int n = (Wq >> 2) * Hq;
-  k_search_plane<<<(n + 255) / 256, 256, 0, s>>>(luma, pitch, W, H, out, Wq, Hq, spad);
+  const int y0 = row_lo <= 0 ? 0 : row_lo + spad, y1 = row_hi >= H ? Hq : row_hi + spad;
+  const int n = (Wq >> 2) * (y1 - y0);
+  if (n <= 0) return cudaSuccess;
+  k_search_plane<<<(n + 255) / 256, 256, 0, s>>>(luma, pitch, W, H, out, Wq, Hq, spad, y0, y1);
   return cudaGetLastError();
 }
 
-cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, cudaStream_t s)
+cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, int row_lo, int row_hi, cudaStream_t s)
 {
   const int Wp = W + 2 * PADX, Hp = H + 2 * PADY;
-  dim3 g1((Wp + TX - 1) / TX, (Hp + TY - 1) / TY), b1(TX, TY);
-  k_half_planes<<<g1, b1, 0, s>>>(luma, pitch, W, H, planes16, Wp, Hp);
-  dim3 g2((Wp / 4 + 255) / 256, Hp);
-  k_quarter_planes<<<g2, 256, 0, s>>>(planes16, Wp, Hp);
+  const int y0 = row_lo <= 0 ? 0 : row_lo + PADY, y1 = row_hi >= H ? Hp : row_hi + PADY;
+  if (y1 <= y0) return cudaSuccess;
+  dim3 g1((Wp + TX - 1) / TX, (y1 - y0 + TY - 1) / TY), b1(TX, TY);
+  k_half_planes<<<g1, b1, 0, s>>>(luma, pitch, W, H, planes16, Wp, Hp, y0, y1);
+  dim3 g2((Wp / 4 + 255) / 256, y1 - y0);
+  k_quarter_planes<<<g2, 256, 0, s>>>(planes16, Wp, Hp, y0);
   return cudaGetLastError();
 }
 

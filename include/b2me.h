@@ -82,6 +82,10 @@ int b2me_set_cur_dev(b2me_ctx *ctx, const uint8_t *luma_dev, int stride, void *s
  * quarter-pel planes on the device (getSubImagesLuma). */
 int b2me_set_ref(b2me_ctx *ctx, int ref_idx, const uint8_t *luma, int stride);
 int b2me_set_ref_dev(b2me_ctx *ctx, int ref_idx, const uint8_t *luma_dev, int stride, void *stream);
+/* MB-row bands (one picture across several GPUs): rebuild the planes of luma rows [row_first, row_first + row_count)
+ * only -- the rows this GPU's band reads (its own rows plus the halo it received) -- from a full-geometry picture
+ * buffer; the pad above / below goes with the first / last picture row, everything else keeps its old content. */
+int b2me_set_ref_rows_dev(b2me_ctx *ctx, int ref_idx, const uint8_t *luma_dev, int stride, int row_first, int row_count, void *stream);
 /* Explicit weighted prediction for the single-list search (UseWeightedReferenceME: computeSADWP / SATDWP / SSEWP,
  * JM/lencod/src/me_distortion.c:434-517, 833-935, 1262-1345; weights from PrepareMEParams, mv_search.c:183-188):
  * luma weight / offset of reference ref_idx and the slice's luma_log_weight_denom.  Takes effect at the NEXT

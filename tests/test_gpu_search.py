@@ -167,7 +167,12 @@ def test_banded_search_equals_full_frame():
         lo, hi = bands.needed_rows(rank, world, H // 16, R, 12)
         part = np.zeros_like(ref); part[lo:hi] = ref[lo:hi]                # what the halo exchange delivers
         b.set_cur_dev(torch.from_numpy(cur).to(dev))
-        b.s.set_ref_dev(0, torch.from_numpy(part).to(dev))
+        if rank == 1:
+            b.s.set_ref_dev(0, torch.from_numpy(part).to(dev))
+        else:
+            # planes of the needed rows only (b2me_set_ref_rows_dev) over planes of ANOTHER picture: stale rows must not be read
+            b.s.set_ref_dev(0, torch.from_numpy(np.ascontiguousarray(cur[::-1])).to(dev))
+            b.s.set_ref_rows_dev(0, torch.from_numpy(part).to(dev), lo, hi - lo)
         mvi = torch.zeros((nmb, 1, 41, 2), dtype=torch.int16, device=dev); mvs = torch.zeros_like(mvi)
         ci = torch.zeros((nmb, 1, 41), dtype=torch.int64, device=dev); cs = torch.zeros_like(ci)
         b.search(d_pred, d_cen, api.make_params((150, 120, 120)), mvi, ci, mvs, cs)
