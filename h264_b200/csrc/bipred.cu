@@ -22,7 +22,7 @@ struct BiArgs {
   const uint8_t *cur; int cur_pitch;
   const uint8_t *planes; size_t plane_size;
   int W, H, Wp, nrefs, R;
-  int lambda[3], metric_h, metric_q, do_subpel, test8x8, wp, denom;
+  int lambda[3], metric_h, metric_q, do_subpel, full81, test8x8, wp, denom;
   const b2me_bipred_job *jobs; b2me_bipred_result *out; int njobs;
   int *errflag;
 };
@@ -173,19 +173,22 @@ __global__ void __launch_bounds__(128) k_bipred(const BiArgs a)
   if (!a.do_subpel) return;
   // ---- half pel, then quarter pel: positions start..8 of the spiral, step 2 / 1 quarter-pel ----
   const int start_hp_cfg = (0 != a.metric_h) ? 0 : 1, start_qp = (a.metric_h != a.metric_q) ? 0 : 1;
+  // full81: full_sub_pel_bipred_motion_estimation (me_fullsearch.c:478-538) -- ONE stage, the 81 quarter-pel positions of
+  // spiral_search, computeBiPredQPel, lambda[Q_PEL], every position from 0 on
+  const int nstage = a.full81 ? 1 : 2;
 #pragma unroll 1
-  for (int stage = 0; stage < 2; stage++) {
+  for (int stage = 0; stage < nstage; stage++) {
     __syncthreads();
     long long b = bound;
     if (stage == 0 && !start_hp_cfg && J.search_range >= 0) b = BI_DISTBLK_MAX;   // the caller's reset, mv_search.c:1119-1120
-    const int start = stage ? start_qp : (b == BI_DISTBLK_MAX ? 0 : start_hp_cfg);
+    const int start = a.full81 ? 0 : (stage ? start_qp : (b == BI_DISTBLK_MAX ? 0 : start_hp_cfg));
     if (stage == 1 && !start_qp) b = BI_DISTBLK_MAX;                  // me_fullsearch.c:364-365
     const int m0 = mv1[0], m1 = mv1[1];
     __syncthreads();
     if (tid == 0) key = (unsigned long long)b << 20;
     __syncthreads();
-    const int lam = a.lambda[1 + stage], metric = stage ? a.metric_q : a.metric_h, step = stage ? 1 : 2;
-    if (tid >= start && tid < 9) {
+    const int lam = a.full81 ? a.lambda[2] : a.lambda[1 + stage], metric = (stage || a.full81) ? a.metric_q : a.metric_h, step = (stage || a.full81) ? 1 : 2;
+    if (tid >= start && tid < (a.full81 ? 81 : 9)) {
       int sx, sy; spiral_xy(tid, &sx, &sy);
       const int cx = m0 + step * sx, cy = m1 + step * sy;
       long long mcost = (long long)lam * (mvbits(cx - J.pred1[0]) + mvbits(cy - J.pred1[1]) + mvbits(J.mv2[0] - J.pred2[0]) + mvbits(J.mv2[1] - J.pred2[1]));
@@ -340,7 +343,7 @@ extern "C" int b2me_bipred_search_dev(b2me_ctx *c, int njobs, const b2me_bipred_
   a.cur = c->d_cur; a.cur_pitch = c->W; a.planes = c->d_planes; a.plane_size = c->plane_size;
   a.W = c->W; a.H = c->H; a.Wp = c->Wp; a.nrefs = c->nrefs; a.R = c->R;
   a.lambda[0] = p->lambda_factor[0]; a.lambda[1] = p->lambda_factor[1]; a.lambda[2] = p->lambda_factor[2];
-  a.metric_h = p->metric_h; a.metric_q = p->metric_q; a.do_subpel = p->do_subpel; a.test8x8 = test8x8;
+  a.metric_h = p->metric_h; a.metric_q = p->metric_q; a.do_subpel = p->do_subpel; a.full81 = p->subpel_full ? 1 : 0; a.test8x8 = test8x8;
   a.wp = apply_weights; a.denom = luma_log_weight_denom; a.jobs = jobs_dev; a.out = out_dev; a.njobs = njobs; a.errflag = c->d_errflag;
   k_bipred<<<njobs, 128, 0, s>>>(a);
   B2_CUDA_CHECK(c, cudaGetLastError());

@@ -2,15 +2,13 @@
  * libb2me.so (hand-written sm_100a CUDA behind include/b2me.h).
  *
  * Link-level object replacement: JM's me_fullsearch.o is left out of the link and this
- * file defines the four symbols the full-search configurations reach (P and B slices),
+ * file defines all six symbols of that object (P and B slices),
  *     distblk full_search_motion_estimation(Macroblock*, MotionVector*, MEBlock*, distblk, int)
  *     distblk sub_pel_motion_estimation    (Macroblock*, MotionVector*, MEBlock*, distblk, int*)
  *     distblk full_search_bipred_motion_estimation(Macroblock*, int, MotionVector*, MotionVector*, MotionVector*, MotionVector*, MEBlock*, int, distblk, int)
  *     distblk sub_pel_bipred_motion_estimation    (Macroblock*, MEBlock*, int, MotionVector*, MotionVector*, MotionVector*, MotionVector*, distblk, int*)
- * with the exact signatures of JM/lencod/inc/me_fullsearch.h:20-25.  The other two symbols of
- * that object (full_sub_pel_motion_estimation and its bi-pred twin, EPZSSubPelME == 2 only) come from JM's
- * own source compiled with the four names above renamed (oracle/Makefile.jm), so every other configuration
- * still links and runs the reference code for them.
+ *     distblk full_sub_pel_motion_estimation / full_sub_pel_bipred_motion_estimation (same argument lists as the sub_pel pair)
+ * with the exact signatures of JM/lencod/inc/me_fullsearch.h:20-25: nothing of me_fullsearch.c is linked.
  *
  * Ownership / threading follow the reference: the caller owns every buffer, the callee writes only
  * mv_block->mv[list] and returns the cost; one thread; state hangs off a process-wide context that
@@ -195,9 +193,36 @@ distblk sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, MEBloc
   return (distblk)cost;
 }
 
+/* EPZSSubPelME == 2 (me_epzs_common.c:157) and SubPelME overrides: the brute-force 81-position refinement */
+distblk full_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, MEBlock *mv_block, distblk min_mcost, int *lambda)
+{
+  Slice *currSlice = currMB->p_Slice;
+  int list = mv_block->list;
+  MotionVector *mv = &mv_block->mv[list];
+  StorablePicture *ref_picture = currSlice->listX[list + currMB->list_offset][mv_block->ref_idx];
+  b2me_search_params P;
+  int16_t pm[2], in[2], out[2];
+  int64_t cost = 0;
+  int slot;
+
+  b2_ensure_ctx(currMB);
+  b2_check_config(currMB, mv_block);
+  b2_ensure_cur(currMB->p_Vid);
+  slot = b2_ref_slot(ref_picture);
+  b2_params(currMB->p_Inp, &P, lambda[F_PEL], lambda[H_PEL], lambda[Q_PEL], min_mcost);
+  P.do_subpel = 1; P.subpel_full = 1;
+  pm[0] = pred->mv_x; pm[1] = pred->mv_y; in[0] = mv->mv_x; in[1] = mv->mv_y;
+  if (b2me_block_subpel(g_ctx, mv_block->pos_x, mv_block->pos_y, mv_block->blocktype, slot, pm, in, &P, (int64_t)min_mcost,
+                        out, &cost) != B2ME_OK)
+    b2_fail("b2me_block_subpel (81 positions) failed");
+  g_calls_sub++;
+  mv->mv_x = out[0]; mv->mv_y = out[1];
+  return (distblk)cost;
+}
+
 /* ---- B slices: the bi-predictive twins (JM/lencod/inc/me_fullsearch.h:21,24) on b2me_bipred_search ---------------- */
 static distblk b2_bipred(Macroblock *currMB, int list, MotionVector *pred_mv1, MotionVector *pred_mv2, MotionVector *mv1,
-                         MotionVector *mv2, MEBlock *mv_block, int search_range_pel, distblk min_mcost, int *lambda, int do_subpel)
+                         MotionVector *mv2, MEBlock *mv_block, int search_range_pel, distblk min_mcost, int *lambda, int do_subpel /* 2: 81 positions */)
 {
   Slice *currSlice = currMB->p_Slice;
   StorablePicture *ref_picture1 = currSlice->listX[list + currMB->list_offset][mv_block->ref_idx];
@@ -215,7 +240,7 @@ static distblk b2_bipred(Macroblock *currMB, int list, MotionVector *pred_mv1, M
   if (g_slot[J.ref1].pic != ref_picture1) J.ref1 = (int16_t)b2_ref_slot(ref_picture1);   /* ref2's upload may have recycled ref1's slot */
   if (J.ref1 == J.ref2 && ref_picture1 != ref_picture2) b2_fail("reference slots exhausted");
   b2_params(currMB->p_Inp, &P, lambda[F_PEL], lambda[H_PEL], lambda[Q_PEL], min_mcost);
-  P.do_subpel = do_subpel;
+  P.do_subpel = do_subpel ? 1 : 0; P.subpel_full = do_subpel == 2;
   J.min_mcost = (int64_t)min_mcost;
   J.pos_x = mv_block->pos_x; J.pos_y = mv_block->pos_y; J.blocktype = mv_block->blocktype;
   J.search_range = (int16_t)search_range_pel;
@@ -244,4 +269,10 @@ distblk sub_pel_bipred_motion_estimation(Macroblock *currMB, MEBlock *mv_block, 
 {
   if (mv_block->search_pos2 != 9 || mv_block->search_pos4 != 9) b2_fail("SubPelSearch position counts other than 9/9 are not supported");
   return b2_bipred(currMB, list, pred_mv1, pred_mv2, mv1, mv2, mv_block, -1, min_mcost, lambda, 1);
+}
+
+distblk full_sub_pel_bipred_motion_estimation(Macroblock *currMB, MEBlock *mv_block, int list, MotionVector *pred_mv1, MotionVector *pred_mv2,
+                                              MotionVector *mv1, MotionVector *mv2, distblk min_mcost, int *lambda)
+{
+  return b2_bipred(currMB, list, pred_mv1, pred_mv2, mv1, mv2, mv_block, -1, min_mcost, lambda, 2);
 }

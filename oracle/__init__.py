@@ -151,7 +151,7 @@ class OrcFrame:
         out = np.zeros(len(jobs), BIPRED_RESULT)
         lam = np.ascontiguousarray(np.broadcast_to(np.asarray(lam), (3,)), np.int32)
         self.L.orc_bipred_search(self.h, C.c_int(len(jobs)), _ptr(jobs), _ptr(lam), C.c_int(metric_h), C.c_int(metric_q),
-                                 C.c_int(int(do_subpel)), C.c_int(int(test8x8)), C.c_int(int(wp)), C.c_int(log_denom), _ptr(out))
+                                 C.c_int(int(do_subpel)), C.c_int(int(test8x8)), C.c_int(int(wp)), C.c_int(log_denom), _ptr(out))   # do_subpel 2: the 81-position stage
         return out
 
     def distortion_candidates(self, cands, metric, test8x8=False):

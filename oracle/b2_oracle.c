@@ -577,13 +577,15 @@ void orc_bipred_search(void *h, int njobs, const OrcBiJob *jobs, const int *lamb
     if (!do_subpel) continue;
     if (!start_hp_cfg && sr >= 0) min_mcost = DISTBLK_MAX_ORC;           /* the caller's reset, mv_search.c:1119-1120 */
     {
+      /* do_subpel == 2: full_sub_pel_bipred_motion_estimation (me_fullsearch.c:478-538), one stage of 81 quarter-pel positions */
+      const int full81 = do_subpel == 2;
       int stage;
-      for (stage = 0; stage < 2; stage++) {
-        const int lam = lambda[1 + stage], metric = stage ? metric_q : metric_h, step = stage ? 1 : 2;
+      for (stage = 0; stage < (full81 ? 1 : 2); stage++) {
+        const int lam = full81 ? lambda[2] : lambda[1 + stage], metric = (stage || full81) ? metric_q : metric_h, step = (stage || full81) ? 1 : 2;
         const int64_t c2 = orc_mv_cost(lam, J->mv2[0], J->mv2[1], J->pred2[0], J->pred2[1]);
-        int start = stage ? start_qp : ((min_mcost == DISTBLK_MAX_ORC) ? 0 : start_hp_cfg);
+        int start = full81 ? 0 : (stage ? start_qp : ((min_mcost == DISTBLK_MAX_ORC) ? 0 : start_hp_cfg));
         if (stage && !start_qp) min_mcost = DISTBLK_MAX_ORC;             /* me_fullsearch.c:364-365 */
-        for (best_pos = 0, pos = start; pos < 9; pos++) {
+        for (best_pos = 0, pos = start; pos < (full81 ? 81 : 9); pos++) {
           const int cx = mv1[0] + step * f->spiral[2*pos], cy = mv1[1] + step * f->spiral[2*pos+1];
           int64_t mcost = orc_mv_cost(lam, cx, cy, J->pred1[0], J->pred1[1]) + c2;
           if (mcost >= min_mcost) continue;

@@ -322,7 +322,8 @@ void jmh_bipred_search(void *hh, int njobs, const JmhBiJob *jobs, const int *lam
     out[n].mv_sub[0] = m1.mv_x; out[n].mv_sub[1] = m1.mv_y; out[n].cost_sub = (long long)c;
     if (do_subpel) {
       if (!h->p_Vid->start_me_refinement_hp && J->search_range >= 0) c = DISTBLK_MAX;   /* mv_search.c:1119-1120 */
-      c = sub_pel_bipred_motion_estimation(&h->mb, &b, 0, &p1, &p2, &m1, &m2, c, lam);
+      c = do_subpel == 2 ? full_sub_pel_bipred_motion_estimation(&h->mb, &b, 0, &p1, &p2, &m1, &m2, c, lam)
+                         : sub_pel_bipred_motion_estimation(&h->mb, &b, 0, &p1, &p2, &m1, &m2, c, lam);
       out[n].mv_sub[0] = m1.mv_x; out[n].mv_sub[1] = m1.mv_y; out[n].cost_sub = (long long)c;
     }
     free(b.orig_pic);

@@ -55,6 +55,26 @@ def test_bipred_matches_oracle(W, H, R, NR, lam):
         assert (_flat(got) == _flat(exp)).all()
 
 
+def test_bipred_81_positions_and_subpel_only_jobs():
+    """params.subpel_full: full_sub_pel_bipred_motion_estimation (me_fullsearch.c:478); search_range -1: the sub-pel call alone"""
+    W, H, R, NR, lam = 96, 64, 8, 2, (187, 150, 120)
+    fr = synth.luma_sequence(W, H, NR + 1, seed=41)
+    cur, refs = fr[NR], fr[[1, 0]]
+    s = _searcher(cur, refs, R)
+    of = oracle.OrcFrame(cur, refs, R)
+    rng = np.random.default_rng(2)
+    for sub_only in (False, True):
+        jobs = synth.bipred_jobs(W, H, NR, R, 64, seed=8 + sub_only)
+        if sub_only:
+            jobs["search_range"] = -1
+            jobs["mv1"] = rng.integers(-24, 25, (64, 2))
+        for mh, mq in ((2, 2), (0, 2), (1, 1)):
+            for full in (False, True):
+                got = s.bipred_search(jobs, api.make_params(lam, metric_h=mh, metric_q=mq, subpel_full=full))
+                exp = of.bipred_search(jobs, lam, metric_h=mh, metric_q=mq, do_subpel=2 if full else 1)
+                assert (_flat(got) == _flat(exp)).all(), (sub_only, mh, mq, full)
+
+
 def test_bipred_error_codes():
     W, H, R = 64, 48, 8
     fr = synth.luma_sequence(W, H, 2, seed=1)

@@ -59,6 +59,32 @@ def test_lencod_b_slices_with_cuda_bipred_search_are_bit_identical():
         assert m and int(m.group(1)) > 1000, b[2][-400:]      # the B slices really went through b2me_bipred_search
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not have, reason="oracle/_ref/lencod{,_b2} not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("mode,extra", [
+    # EPZS keeps its integer search in JM; its sub-pel stages are the 81-position functions of me_fullsearch.o (EPZSSubPelME = 2)
+    (3, ("EPZSSubPelME=2", "EPZSSubPelMEBiPred=2", "EPZSSubPelGrid=0")),
+    # fast full search (me_fullfast.o, JM) for the single lists; bi-predictive search and every sub-pel stage from libb2me.so
+    (0, ()),
+])
+def test_other_search_modes_share_the_cuda_subpel_and_bipred_functions(mode, extra):
+    W, H, frames = 176, 144, 5
+    extra = tuple(extra) + ("NumberBFrames=1", "BiPredMotionEstimation=1", "BiPredMERefinements=1", "BiPredMESearchRange=8", "BiPredMESubPel=2",
+                            "HierarchicalCoding=0", "BReferencePictures=0", "QPBSlice=30", "BList1References=1")
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(W, H, frames, seed=5))
+        a = _encode("lencod", yuv, W, H, frames, os.path.join(d, "stock"), nrefs=2, search_range=8, qp=30, search_mode=mode, extra=extra)
+        b = _encode("lencod_b2", yuv, W, H, frames, os.path.join(d, "b2"), nrefs=2, search_range=8, qp=30, search_mode=mode, extra=extra,
+                    env={"B2ME_SHIM_VERBOSE": "1"})
+        assert len(a[0]) > 1000
+        assert a[0] == b[0], "bitstreams differ"
+        assert a[1] == b[1], "reconstructions differ"
+        import re
+        m = re.search(r"(\d+) sub-pel refinements, (\d+) bi-predictive calls", b[2])
+        assert m and int(m.group(1)) > 1000 and int(m.group(2)) > 100, b[2][-400:]
+
+
 @pytest.mark.skipif(not have, reason="oracle/_ref/lencod_b2 not built")
 def test_dropin_fails_loudly_without_a_gpu():
     """No CPU fallback behind the boundary: without a CUDA device the shim stops the encoder."""
