@@ -46,7 +46,7 @@ static long g_clock;
 static StorablePicture *g_cur_pic;
 static int g_cur_poc = -0x7fffffff;
 static unsigned char *g_stage;
-static long g_calls_int, g_calls_sub, g_calls_bi, g_uploads;
+static long g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_uploads;
 static int g_in_bipred;
 
 static void b2_fail(const char *what)
@@ -59,8 +59,8 @@ static void b2_fail(const char *what)
 static void b2_report(void)
 {
   if (getenv("B2ME_SHIM_VERBOSE"))
-    fprintf(stderr, "b2me shim: %ld integer searches, %ld sub-pel refinements, %ld bi-predictive calls, %ld picture uploads, %lld kernel launches\n",
-            g_calls_int, g_calls_sub, g_calls_bi, g_uploads, g_ctx ? (long long)b2me_launch_count(g_ctx) : 0LL);
+    fprintf(stderr, "b2me shim: %ld integer searches, %ld sub-pel refinements, %ld bi-predictive calls, %ld distortion calls, %ld picture uploads, %lld kernel launches\n",
+            g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_uploads, g_ctx ? (long long)b2me_launch_count(g_ctx) : 0LL);
   if (g_ctx) b2me_destroy(g_ctx);
   g_ctx = NULL;
 }
@@ -80,10 +80,10 @@ static void b2_check_config(Macroblock *currMB, MEBlock *mv_block)
   if (p_Inp->OnTheFlyFractMCP) b2_fail("OnTheFlyFractMCP must be 0");
 }
 
-static void b2_ensure_ctx(Macroblock *currMB)
+static void b2_ensure_ctx2(VideoParameters *p_Vid, InputParameters *p_Inp);
+static void b2_ensure_ctx(Macroblock *currMB) { b2_ensure_ctx2(currMB->p_Vid, currMB->p_Inp); }
+static void b2_ensure_ctx2(VideoParameters *p_Vid, InputParameters *p_Inp)
 {
-  VideoParameters *p_Vid = currMB->p_Vid;
-  InputParameters *p_Inp = currMB->p_Inp;
   int dev = 0, R = p_Inp->search_range[p_Vid->view_id];
   const char *e = getenv("B2ME_DEVICE");
   if (g_ctx) return;
@@ -276,3 +276,32 @@ distblk full_sub_pel_bipred_motion_estimation(Macroblock *currMB, MEBlock *mv_bl
 {
   return b2_bipred(currMB, list, pred_mv1, pred_mv2, mv1, mv2, mv_block, -1, min_mcost, lambda, 2);
 }
+
+#ifdef B2ME_SHIM_DISTORTION
+/* ---- the computeSAD family at its own boundary (JM/lencod/inc/me_distortion.h:60-62): the distortion pointers
+ * mv_block->computePredFPel / HPel / QPel of EVERY search mode (EPZS, UMHex, ...) then evaluate on the GPU, one candidate per
+ * call -- a functional demonstration of the boundary (lencod_b2d in oracle/Makefile.jm), not a fast path: a search that wants
+ * throughput hands whole predictor sets to b2me_distortion_candidates.  The early exits of the reference return a value above
+ * the caller's bound; the full distortion returned here is above it too, so every comparison falls the same way. ---- */
+static distblk b2_distortion(StorablePicture *ref1, MEBlock *mv_block, MotionVector *cand, int metric)
+{
+  b2me_candidate c;
+  int64_t out = 0;
+  b2_ensure_ctx2(mv_block->p_Vid, mv_block->p_Vid->p_Inp);
+  if (mv_block->ChromaMEEnable) b2_fail("ChromaMEEnable is not supported");
+  if (mv_block->p_Vid->bitdepth_luma != 8) b2_fail("only 8-bit luma is supported");
+  b2_ensure_cur(mv_block->p_Vid);
+  c.pos_x = mv_block->pos_x; c.pos_y = mv_block->pos_y; c.blocktype = mv_block->blocktype;
+  c.ref = (int16_t)b2_ref_slot(ref1);
+  c.mv[0] = (int16_t)(cand->mv_x - mv_block->pos_x_padded); c.mv[1] = (int16_t)(cand->mv_y - mv_block->pos_y_padded);
+  if (b2me_distortion_candidates(g_ctx, metric, mv_block->test8x8, 1, &c, &out) != B2ME_OK) b2_fail("b2me_distortion_candidates failed");
+  g_calls_dist++;
+  return (distblk)out;
+}
+distblk computeSAD(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 0); }
+distblk computeSSE(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 1); }
+distblk computeSATD(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 2); }
+#endif

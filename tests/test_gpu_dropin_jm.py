@@ -85,6 +85,27 @@ def test_other_search_modes_share_the_cuda_subpel_and_bipred_functions(mode, ext
         assert m and int(m.group(1)) > 1000 and int(m.group(2)) > 100, b[2][-400:]
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not (have and os.path.exists(os.path.join(REF, "lencod_b2d"))), reason="oracle/_ref/lencod_b2d not built")
+def test_epzs_with_every_distortion_on_the_gpu_is_bit_identical():
+    """lencod_b2d: computeSAD / computeSATD of me_distortion.o served by b2me_distortion_candidates (one call per candidate).
+    EPZS (SearchMode 3, its own sub-pel search) keeps all its control flow in JM and takes every distortion from the GPU."""
+    W, H, frames = 176, 144, 3
+    extra = ("EPZSSubPelME=1", "EPZSSubPelGrid=0")
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(W, H, frames, seed=9))
+        a = _encode("lencod", yuv, W, H, frames, os.path.join(d, "stock"), nrefs=1, search_range=16, qp=28, search_mode=3, extra=extra)
+        b = _encode("lencod_b2d", yuv, W, H, frames, os.path.join(d, "b2"), nrefs=1, search_range=16, qp=28, search_mode=3, extra=extra,
+                    env={"B2ME_SHIM_VERBOSE": "1"})
+        assert len(a[0]) > 1000
+        assert a[0] == b[0], "bitstreams differ"
+        assert a[1] == b[1], "reconstructions differ"
+        import re
+        m = re.search(r"(\d+) distortion calls", b[2])
+        assert m and int(m.group(1)) > 10000, b[2][-400:]
+
+
 @pytest.mark.skipif(not have, reason="oracle/_ref/lencod_b2 not built")
 def test_dropin_fails_loudly_without_a_gpu():
     """No CPU fallback behind the boundary: without a CUDA device the shim stops the encoder."""

@@ -7,8 +7,8 @@ timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; tai
 timeout 600 python bench.py --steps 20 --warmup 3 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err && cat $O/${TAG}_bench.json | cut -c1-600
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > $O/${TAG}_ncu_bench.log 2>&1
 B2ME_BANDS=1 ITERS=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_sad_fs -c 1 -f -o $O/${TAG}_sad_fs python tools/prof_fs.py > $O/${TAG}_ncu1.log 2>&1
-B2ME_BANDS=1 ITERS=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_subpel_refine|k_search_plane' -c 2 -f -o $O/${TAG}_other python tools/prof_fs.py > $O/${TAG}_ncu2.log 2>&1
+B2ME_BANDS=1 ITERS=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_subpel_refine|k_search_plane' -c 5 -f -o $O/${TAG}_other python tools/prof_fs.py > $O/${TAG}_ncu2.log 2>&1
 ND=16384 timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_frac_pool|k_fp_' -c 5 -f -o $O/${TAG}_pool python tools/prof_pool.py > $O/${TAG}_ncu3.log 2>&1
 timeout 300 python tools/pool_bench.py > $O/${TAG}_pool_bench.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_half|k_quarter|k_apply_wp|k_mc_luma|k_tq|k_distortion|k_bipred|k_cand_dist|k_frac_domain|k_frac_range|k_frac_window' -c 48 -f -o $O/${TAG}_rest python tools/prof_rest.py > $O/${TAG}_ncu4.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_half|k_quarter|k_apply_wp|k_mc_luma|k_tq|k_distortion|k_bipred|k_cand_dist|k_frac_domain|k_frac_range|k_frac_window|k_frac_decide|k_frac_predict' -c 48 -f -o $O/${TAG}_rest python tools/prof_rest.py > $O/${TAG}_ncu4.log 2>&1
 tail -n 2 $O/${TAG}_ncu1.log; tail -n 2 $O/${TAG}_ncu2.log

@@ -43,4 +43,6 @@ f = api.FractalSearcher(352, 288, 7)
 f.set_domain(0, ry, ru, rv)
 f.set_range(cy, cu, cv)
 out = f.search_plane(0, 1)
-print("ok", float(np.asarray(out[2]).min()))
+nodes = f.encode_plane(1, (3.5, 4.5, 2.0))            # k_frac_decide
+rec = f.decode_plane(1)                               # k_frac_predict
+print("ok", float(np.asarray(out[2]).min()), int(rec.sum()))
