@@ -57,17 +57,19 @@ static inline int comp_mbh(const b2fr_ctx *c, int comp) { return comp ? (c->H / 
 namespace b2 {
 
 // ---- compute_domain_Sum: S4/Q4 at every pixel offset where a 4x4 block fits, else 0 ----------
+template <int STRIP>
 __global__ void __launch_bounds__(256) k_frac_domain_sums(const uint8_t *__restrict__ img, int w, int h,
                                                            int *__restrict__ s4, int *__restrict__ q4)
 {
-  // separable: each thread owns one column x of a 64-row strip; horizontal 4-sums of a row are
-  // formed from the row's bytes, vertical 4-sums slide down the strip.
+  // separable: each thread owns one column x of a STRIP-row strip; horizontal 4-sums of a row are
+  // formed from the row's bytes, vertical 4-sums slide down the strip.  (STRIP 16 for planes that would not fill the
+  // chip with 64-row strips: a CIF plane is 10 CTAs of 64 rows, latency-bound at 37 us.)
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y0 = blockIdx.y * 64;
+  const int y0 = blockIdx.y * STRIP;
   if (x >= w) return;
   int hs[4] = {0, 0, 0, 0}, hq[4] = {0, 0, 0, 0};
   const bool xin = x + 3 < w;
-  for (int r = 0; r < 64 + 3; r++) {
+  for (int r = 0; r < STRIP + 3; r++) {
     const int y = y0 + r;
     int a = 0, b = 0;
     if (y < h && xin) {
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) k_frac_domain_sums(const uint8_t *__restr
     hs[r & 3] = a; hq[r & 3] = b;
     if (r >= 3) {
       const int yo = y - 3;
-      if (yo < h && yo < y0 + 64) {
+      if (yo < h && yo < y0 + STRIP) {
         const bool ok = xin && y < h;
         s4[(size_t)yo * w + x] = ok ? hs[0] + hs[1] + hs[2] + hs[3] : 0;
         q4[(size_t)yo * w + x] = ok ? hq[0] + hq[1] + hq[2] + hq[3] : 0;
@@ -298,25 +300,38 @@ struct FdArgs {
   b2fr_node *nodes;
 };
 
-__device__ double fd_chun(const uint8_t *org, const uint8_t *ref, int w, int bx, int by)
+// chun by one warp: the sums and squared deviations are exact in double (order-free), so they are reduced in parallel;
+// the 256 correlation terms are formed in parallel (two divisions each) and then added by ONE lane in the reference's
+// column-major order, the only order-dependent part.
+__device__ double fd_chun_warp(const uint8_t *org, const uint8_t *ref, int w, int bx, int by, double *term /* smem [256] */)
 {
-  // doubles in the reference's operation order (column-major walk, no contraction): sums and squared deviations are
-  // exact, the correlation sum is the order-dependent part
-  double sumR = 0, sumD = 0, sR = 0, sD = 0, mr = 0;
-  for (int j = bx; j < bx + 16; j++)
-    for (int i = by; i < by + 16; i++) { sumR = __dadd_rn(sumR, (double)org[(size_t)i * w + j]); sumD = __dadd_rn(sumD, (double)ref[(size_t)i * w + j]); }
+  const int lane = threadIdx.x & 31;
+  double sumR = 0, sumD = 0;
+  for (int ii = lane; ii < 256; ii += 32) {           // ii = column-major index: j = bx + ii / 16, i = by + ii % 16
+    const size_t o = (size_t)(by + (ii & 15)) * w + bx + (ii >> 4);
+    sumR += (double)org[o]; sumD += (double)ref[o];
+  }
+  for (int m = 16; m; m >>= 1) { sumR += __shfl_xor_sync(0xffffffffu, sumR, m); sumD += __shfl_xor_sync(0xffffffffu, sumD, m); }
   const double r = __ddiv_rn(sumR, 256.0), d = __ddiv_rn(sumD, 256.0);
-  for (int j = bx; j < bx + 16; j++)
-    for (int i = by; i < by + 16; i++) {
-      const double a = __dsub_rn((double)org[(size_t)i * w + j], r), b = __dsub_rn((double)ref[(size_t)i * w + j], d);
-      sR = __dadd_rn(sR, __dmul_rn(a, a)); sD = __dadd_rn(sD, __dmul_rn(b, b));
-    }
+  double sR = 0, sD = 0;
+  for (int ii = lane; ii < 256; ii += 32) {
+    const size_t o = (size_t)(by + (ii & 15)) * w + bx + (ii >> 4);
+    const double a = __dsub_rn((double)org[o], r), b = __dsub_rn((double)ref[o], d);
+    sR += __dmul_rn(a, a); sD += __dmul_rn(b, b);     // multiples of 2^-16 below 2^24: every partial sum is exact
+  }
+  for (int m = 16; m; m >>= 1) { sR += __shfl_xor_sync(0xffffffffu, sR, m); sD += __shfl_xor_sync(0xffffffffu, sD, m); }
   const double qR = __dsqrt_rn(sR), qD = __dsqrt_rn(sD);
-  for (int j = bx; j < bx + 16; j++)
-    for (int i = by; i < by + 16; i++) {
-      const double a = __dsub_rn((double)org[(size_t)i * w + j], r), b = __dsub_rn((double)ref[(size_t)i * w + j], d);
-      mr = __dadd_rn(mr, __dmul_rn(__ddiv_rn(a, qR), __ddiv_rn(b, qD)));
-    }
+  for (int ii = lane; ii < 256; ii += 32) {
+    const size_t o = (size_t)(by + (ii & 15)) * w + bx + (ii >> 4);
+    const double a = __dsub_rn((double)org[o], r), b = __dsub_rn((double)ref[o], d);
+    term[ii] = __dmul_rn(__ddiv_rn(a, qR), __ddiv_rn(b, qD));
+  }
+  __syncwarp();
+  double mr = 0;
+  if (lane == 0)
+    for (int ii = 0; ii < 256; ii++) mr = __dadd_rn(mr, term[ii]);
+  mr = __shfl_sync(0xffffffffu, mr, 0);
+  __syncwarp();
   return __dmul_rn(mr, mr);
 }
 
@@ -339,17 +354,20 @@ __device__ double fd_search4(const FdArgs &a, size_t base, int p, b2fr_node &t, 
   return rms;
 }
 
-__global__ void __launch_bounds__(64) k_frac_decide(const FdArgs a)
+__global__ void __launch_bounds__(128) k_frac_decide(const FdArgs a)
 {
-  const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+  // one WARP per macroblock: chun across the lanes, the replay of the tree by lane 0
+  __shared__ double terms[4][256];
+  const int mb = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (mb >= a.nmb) return;
+  const double chun = fd_chun_warp(a.org, a.refC, a.w, (mb % a.mbw) * 16, (mb / a.mbw) * 16, terms[threadIdx.x >> 5]);
+  if (threadIdx.x & 31) return;
   b2fr_node nd[21];
   for (int i = 0; i < 21; i++) { nd[i].block_type = nd[i].partition = nd[i].reference = nd[i].x = nd[i].y = nd[i].reserved = 0; nd[i].scale = nd[i].offset = 0.0; }
   const size_t base = (size_t)mb * NPART;
   const int bx = (mb % a.mbw) * 16, by = (mb / a.mbw) * 16;
   const double t16 = __dmul_rn(__dmul_rn(a.tol16, a.tol16), 256.0);
   const double r16 = fd_search4(a, base, 0, nd[0], false);
-  const double chun = fd_chun(a.org, a.refC, a.w, bx, by);
   if (chun <= 1.0 && chun >= 0.9 && r16 > t16) {
     const double tt = __dmul_rn(a.tol8, a.tol8);
     for (int mode = 1; mode < 3; mode++) {
@@ -539,8 +557,13 @@ extern "C" int b2fr_set_domain(b2fr_ctx *c, int plane_set, const uint8_t *y, con
     const int w = comp_w(c, k), h = comp_h(c, k);
     FR_CHECK(c, cudaMemcpyAsync(c->d_ref[plane_set][k], src[k], (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
     if (build_sums) {
-      dim3 grid((w + 255) / 256, (h + 63) / 64);
-      k_frac_domain_sums<<<grid, 256, 0, c->stream>>>(c->d_ref[plane_set][k], w, h, c->d_s4[plane_set][k], c->d_q4[plane_set][k]);
+      if ((size_t)w * h >= (size_t)1 << 20) {
+        dim3 grid((w + 255) / 256, (h + 63) / 64);
+        k_frac_domain_sums<64><<<grid, 256, 0, c->stream>>>(c->d_ref[plane_set][k], w, h, c->d_s4[plane_set][k], c->d_q4[plane_set][k]);
+      } else {
+        dim3 grid((w + 255) / 256, (h + 15) / 16);
+        k_frac_domain_sums<16><<<grid, 256, 0, c->stream>>>(c->d_ref[plane_set][k], w, h, c->d_s4[plane_set][k], c->d_q4[plane_set][k]);
+      }
       c->launches++;
     }
   }
@@ -647,7 +670,7 @@ extern "C" int b2fr_encode_plane(b2fr_ctx *c, int con, const double tol[3], b2fr
   a.org = c->d_org[comp]; a.refC = c->d_ref[0][comp]; a.w = comp_w(c, comp); a.mbw = mbw; a.nmb = nmb;
   for (int s = 0; s < 4; s++) { a.xy[s] = c->d_xy[s][comp]; a.so[s] = c->d_so[s][comp]; a.rms[s] = c->d_rms[s][comp]; }
   a.tol16 = tol[0]; a.tol8 = tol[1]; a.nodes = d;
-  k_frac_decide<<<(nmb + 63) / 64, 64, 0, c->stream>>>(a);
+  k_frac_decide<<<(nmb + 3) / 4, 128, 0, c->stream>>>(a);
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(nodes, d, sizeof(b2fr_node) * 21 * (size_t)nmb, cudaMemcpyDeviceToHost, c->stream);
