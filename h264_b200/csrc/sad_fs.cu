@@ -397,111 +397,6 @@ __device__ __forceinline__ uint32_t fs_task4(const SLOT &S, const uint8_t *wb, u
   return pass;
 }
 
-// fs_task4 with ONE block row (4 rows) per loop iteration: the body (~7 KB of SASS) is close to the L0 instruction cache;
-// the odd block rows' extra partitions and the verdict are uniform branches.  -DFS_ROLL4 selects it (development probe).
-template <int PITCH, class SLOT>
-__device__ __forceinline__ uint32_t fs_task4r(const SLOT &S, const uint8_t *wb, uint32_t mxa, uint32_t mxb, const unsigned short *mys, uint32_t one)
-{
-  constexpr int K = 4;
-  const uint4 *cur = reinterpret_cast<const uint4 *>(S.cur);
-  uint32_t rw[K][6];
-  uint32_t acc[2][K][4];
-  uint32_t run[2][K], X0[2][K], Y0[2][K], E0[2][K];
-  uint32_t pass = 0;
-#pragma unroll
-  for (int j = 0; j < K; j++) { run[0][j] = run[1][j] = 0x7fff7fffu; E0[0][j] = E0[1][j] = 0; X0[0][j] = X0[1][j] = 0; Y0[0][j] = Y0[1][j] = 0; }
-#pragma unroll
-  for (int j = 0; j < K - 1; j++) ld3(rw[j], wb + j * PITCH);
-#pragma unroll 1
-  for (int b = 0; b < 4; b++) {
-    const uint8_t *wr = wb + b * 4 * PITCH;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      ld3(rw[(r + K - 1) & 3], wr + (r + K - 1) * PITCH);
-      const uint4 c = cur[b * 4 + r];
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        const int sl = (r + j) & 3;
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          if (r == 0) {
-            acc[q][j][0] = sad4(c.x, rw[sl][q + 0], 0u);
-            acc[q][j][1] = sad4(c.y, rw[sl][q + 1], 0u);
-            acc[q][j][2] = sad4(c.z, rw[sl][q + 2], 0u);
-            acc[q][j][3] = sad4(c.w, rw[sl][q + 3], 0u);
-          } else {
-            acc[q][j][0] = sad4(c.x, rw[sl][q + 0], acc[q][j][0]);
-            acc[q][j][1] = sad4(c.y, rw[sl][q + 1], acc[q][j][1]);
-            acc[q][j][2] = sad4(c.z, rw[sl][q + 2], acc[q][j][2]);
-            acc[q][j][3] = sad4(c.w, rw[sl][q + 3], acc[q][j][3]);
-          }
-        }
-      }
-    }
-    const uint32_t cx = ld_vol(&S.Cw[3 * b]), cy = ld_vol(&S.Cw[3 * b + 1]), ch = ld_vol(&S.Cw[3 * b + 2]);
-    uint32_t Xc[2][K], Yc[2][K];
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const uint32_t X = acc[q][j][2] * 65536u + acc[q][j][0];
-        const uint32_t Y = acc[q][j][3] * 65536u + acc[q][j][1];
-        const uint32_t H = add2(X, Y);
-        uint32_t rr = run[q][j];
-        rr = addmin2(X, cx, rr, one);
-        rr = addmin2(Y, cy, rr, one);
-        rr = addmin2(H, ch, rr, one);
-        run[q][j] = rr; Xc[q][j] = X; Yc[q][j] = Y;
-      }
-    }
-    if (b & 1) {
-      const int bb = b >> 1;
-      const uint32_t cxv = ld_vol(&S.Cw[12 + 3 * bb]), cyv = ld_vol(&S.Cw[13 + 3 * bb]), ce = ld_vol(&S.Cw[14 + 3 * bb]);
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const uint32_t XV = add2(Xc[q][j], X0[q][j]), YV = add2(Yc[q][j], Y0[q][j]);
-          const uint32_t E = add2(XV, YV);
-          uint32_t rr = run[q][j];
-          rr = addmin2(XV, cxv, rr, one);
-          rr = addmin2(YV, cyv, rr, one);
-          rr = addmin2(E, ce, rr, one);
-          run[q][j] = rr; X0[q][j] = E;
-        }
-      }
-      if (b == 1) {
-#pragma unroll
-        for (int j = 0; j < K; j++) { E0[0][j] = X0[0][j]; E0[1][j] = X0[1][j]; }
-      } else {
-        const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
-        const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-          const uint32_t my = mys[j];
-#pragma unroll
-          for (int q = 0; q < 2; q++) {
-            const uint32_t E = X0[q][j];
-            const uint32_t top = __dp2a_lo(E0[q][j], 0x0101u, 0u), bot = __dp2a_lo(E, 0x0101u, 0u);
-            const uint32_t TB = bot * 65536u + top, LR = add2(E0[q][j], E);
-            uint32_t rr = run[q][j];
-            rr = addmin2(TB, ctb, rr, one);
-            rr = addmin2(LR, clr, rr, one);
-            const uint32_t m = (q ? mxb : mxa) + my;
-            const int s = (int)(top + bot) + c16 + (int)m;
-            const uint32_t t = rr + m * 0x10001u;
-            if ((t & 0x80008000u) != 0u || s < 0) pass |= 1u << (q * K + j);
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < K; j++) { X0[0][j] = Xc[0][j]; X0[1][j] = Xc[1][j]; Y0[0][j] = Yc[0][j]; Y0[1][j] = Yc[1][j]; }
-    }
-  }
-  return pass;
-}
-
 // ---- mbarrier / TMA (PTX) ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void *bar, int count)
@@ -923,12 +818,8 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         uint32_t pass = 0;
 #pragma unroll 1
         for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
-#ifdef FS_ROLL4
-          pass |= fs_task4r<PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
-#else
           pass |= K == 4 ? fs_task4<PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one)
                          : fs_task<5, PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
-#endif
         uint32_t vm = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) if (dy0 + j < S.ncy) vm |= (va ? 1u << j : 0u) | (vb ? 1u << (K + j) : 0u);
@@ -996,9 +887,9 @@ cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, 
   cudaError_t e;
   if (smem_bytes_out) *smem_bytes_out = G.total;
   if (G.pitch == 96) {
-    // CTA shape: workers x resident CTAs per SM (B2ME_FS_VAR = "4x3" default, "7x2", "6x2": development probes)
+    // CTA shape: workers x resident CTAs per SM (B2ME_FS_VAR = "4x3" default, "3x3", "7x2", "6x2": development probes)
     static int var = -1;
-    if (var < 0) { const char *e = getenv("B2ME_FS_VAR"); var = !e ? 0 : (e[0] == '7' ? 1 : (e[0] == '6' ? 2 : 0)); }
+    if (var < 0) { const char *e = getenv("B2ME_FS_VAR"); var = !e ? 0 : (e[0] == '7' ? 1 : (e[0] == '6' ? 2 : (e[0] == '3' ? 3 : 0))); }
 #define FS_LAUNCH96(NW, MB)                                                                                                   \
     {                                                                                                                         \
       static int configured = 0, occ = -1;                                                                                    \
@@ -1017,6 +908,7 @@ cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, 
     }
     if (var == 1) FS_LAUNCH96(7, 2)
     else if (var == 2) FS_LAUNCH96(6, 2)
+    else if (var == 3) FS_LAUNCH96(3, 3)
     else FS_LAUNCH96(4, 3)
 #undef FS_LAUNCH96
   } else if (G.pitch == 160) {
