@@ -304,17 +304,18 @@ class V1Ref:
     """The unmodified version1 compute.c/block_enc.c behind oracle/v1_harness.c (one per process:
     the reference keeps its state in globals)."""
     _made = False
+    LIB = "libv1ref.so"
 
     def __init__(self, W, H, R, tol=(10.5, 8.0, 6.0)):
-        if V1Ref._made:
+        if type(self)._made:
             raise RuntimeError("V1Ref: the reference state is global; one instance per process")
-        self.L = _load(os.path.join(_HERE, "_ref", "libv1ref.so"))
+        self.L = _load(os.path.join(_HERE, "_ref", self.LIB))
         self.L.v1h_full_search.restype = C.c_double
         self.L.v1h_compute_rms.restype = C.c_double
         self.W, self.H, self.R = W, H, R
         r = self.L.v1h_init(C.c_int(W), C.c_int(H), C.c_int(R), C.c_double(tol[0]), C.c_double(tol[1]), C.c_double(tol[2]))
         assert r == 0
-        V1Ref._made = True
+        type(self)._made = True
 
     def set_cur(self, y, u, v):
         y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
@@ -440,6 +441,21 @@ def v1_search_plane(org, ref, R, have_sums=True, chroma=False, full_wh=None):
     orc_lib().orc_v1_search_plane(_ptr(org), _ptr(ref), C.c_int(w), C.c_int(h), C.c_int(mbw), C.c_int(mbh), C.c_int(R),
                                   C.c_int(int(have_sums)), _ptr(xy), _ptr(so), _ptr(rms))
     return xy, so, rms
+
+
+class V1DropIn(V1Ref):
+    """The same unmodified version1 objects with full_search served by libb2me.so through integration/v1/b2fr_v1_shim.c
+    (oracle/_ref/libv1b2.so): call new_frame() after the pictures are set, then drive the reference's own cascade."""
+    _made = False
+    LIB = "libv1b2.so"
+
+    def new_frame(self, have=(1, 0, 0, 0)):
+        h = (C.c_int * 4)(*[int(x) for x in have])
+        self.L.v1h_b2_new_frame(h)
+
+    def calls(self):
+        self.L.v1h_b2_calls.restype = C.c_long
+        return self.L.v1h_b2_calls()
 
 
 # ---------------------------------------------------------------------------------------------

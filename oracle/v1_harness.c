@@ -238,3 +238,11 @@ void v1h_decode_plane(int con, uint8_t *out)
   for (mb = 0; mb < nmb; mb++) decode_one_macroblock(mb, g_trans, con);
   for (i = 0; i < h; i++) memcpy(out + (size_t)i * w, rec[i], (size_t)w);
 }
+
+#ifdef V1H_B2
+/* libv1b2.so: the same harness over the same unmodified objects, full_search from integration/v1/b2fr_v1_shim.c */
+void b2fr_v1_new_frame(const int have[4]);
+long b2fr_v1_calls(void);
+void v1h_b2_new_frame(const int *have) { b2fr_v1_new_frame(have); }
+long v1h_b2_calls(void) { return b2fr_v1_calls(); }
+#endif
