@@ -269,6 +269,7 @@ extern "C" int b2tq_8x8_dev(const b2tq_params *p, int nblk, const uint8_t *orig,
 }
 
 // host-pointer variants: stage through device buffers owned by the call
+constexpr size_t TQ_SMALL = (size_t)1 << 20;
 static int tq_host(int n8, int device, const b2tq_params *p, int nblk, const uint8_t *orig, const uint8_t *pred, int16_t *level,
                    uint8_t *run, uint8_t *recon, int32_t *coeff_cost, uint8_t *nonzero)
 {
@@ -281,7 +282,29 @@ static int tq_host(int n8, int device, const b2tq_params *p, int nblk, const uin
   uint8_t *d = nullptr;
   // layout: orig | pred | recon | run | level | cost | nonzero   (each 16-byte aligned)
   const size_t o_pred = N * px, o_rec = 2 * N * px, o_run = 3 * N * px, o_lev = 4 * N * px, o_cost = 6 * N * px, o_nz = o_cost + ((N * 4 + 15) & ~(size_t)15);
-  TQ_CHECK(cudaMalloc(&d, o_nz + N + 16));
+  const size_t total = o_nz + N + 16;
+  if (total <= TQ_SMALL) {
+    // small batches (the per-block calls of a drop-in encoder): a per-thread device scratch and pinned staging buffer, one
+    // copy up, one launch, one copy down -- no allocation per call
+    static thread_local struct { int device; uint8_t *d, *h; cudaStream_t s; } T = {-1, nullptr, nullptr, nullptr};
+    if (T.device != device) {
+      if (T.d) { cudaFree(T.d); cudaFreeHost(T.h); cudaStreamDestroy(T.s); T.d = nullptr; }
+      TQ_CHECK(cudaMalloc(&T.d, TQ_SMALL)); TQ_CHECK(cudaMallocHost(&T.h, TQ_SMALL));
+      TQ_CHECK(cudaStreamCreateWithFlags(&T.s, cudaStreamNonBlocking));
+      T.device = device;
+    }
+    memcpy(T.h, orig, N * px); memcpy(T.h + o_pred, pred, N * px);
+    TQ_CHECK(cudaMemcpyAsync(T.d, T.h, 2 * N * px, cudaMemcpyHostToDevice, T.s));
+    r = n8 ? b2tq_8x8_dev(p, nblk, T.d, T.d + o_pred, (int16_t *)(T.d + o_lev), T.d + o_run, T.d + o_rec, (int32_t *)(T.d + o_cost), T.d + o_nz, T.s)
+           : b2tq_4x4_dev(p, nblk, T.d, T.d + o_pred, (int16_t *)(T.d + o_lev), T.d + o_run, T.d + o_rec, (int32_t *)(T.d + o_cost), T.d + o_nz, T.s);
+    if (r) return r;
+    TQ_CHECK(cudaMemcpyAsync(T.h + o_rec, T.d + o_rec, total - o_rec, cudaMemcpyDeviceToHost, T.s));
+    TQ_CHECK(cudaStreamSynchronize(T.s));
+    memcpy(recon, T.h + o_rec, N * px); memcpy(run, T.h + o_run, N * px); memcpy(level, T.h + o_lev, N * px * 2);
+    memcpy(coeff_cost, T.h + o_cost, N * 4); memcpy(nonzero, T.h + o_nz, N);
+    return B2ME_OK;
+  }
+  TQ_CHECK(cudaMalloc(&d, total));
   cudaStream_t s = 0;
   cudaError_t e = cudaMemcpyAsync(d, orig, N * px, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_pred, pred, N * px, cudaMemcpyHostToDevice, s);

@@ -106,6 +106,27 @@ def test_epzs_with_every_distortion_on_the_gpu_is_bit_identical():
         assert m and int(m.group(1)) > 10000, b[2][-400:]
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not (have and os.path.exists(os.path.join(REF, "lencod_b2t"))), reason="oracle/_ref/lencod_b2t not built")
+@pytest.mark.parametrize("qp", [32])
+def test_lencod_with_cuda_transform_quant_is_bit_identical(qp):
+    """lencod_b2t: residual_transform_quant_luma_4x4 (block.c:660: forward4x4, quant_4x4_normal, inverse4x4, sample_reconstruct)
+    of every luma 4x4 block the mode decision tries, plus the motion search, served by libb2me.so."""
+    W, H, frames = 176, 144, 2
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(W, H, frames, seed=13))
+        a = _encode("lencod", yuv, W, H, frames, os.path.join(d, "stock"), nrefs=1, search_range=8, qp=qp)
+        b = _encode("lencod_b2t", yuv, W, H, frames, os.path.join(d, "b2"), nrefs=1, search_range=8, qp=qp,
+                    env={"B2ME_SHIM_VERBOSE": "1"})
+        assert len(a[0]) > 500
+        assert a[0] == b[0], "bitstreams differ"
+        assert a[1] == b[1], "reconstructions differ"
+        import re
+        m = re.search(r"(\d+) transform/quant calls", b[2])
+        assert m and int(m.group(1)) > 10000, b[2][-400:]
+
+
 @pytest.mark.skipif(not have, reason="oracle/_ref/lencod_b2 not built")
 def test_dropin_fails_loudly_without_a_gpu():
     """No CPU fallback behind the boundary: without a CUDA device the shim stops the encoder."""
