@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(128) k_bipred(const BiArgs a)
   b2me_bipred_result *O = &a.out[blockIdx.x];
   const int bt = J.blocktype;
   const bool bad = bt < 1 || bt > 7 || J.ref1 < 0 || J.ref1 >= a.nrefs || J.ref2 < 0 || J.ref2 >= a.nrefs || J.search_range < -1 ||
-                   J.search_range > a.R || J.pos_x < 0 || J.pos_y < 0 || J.pos_x >= a.W || J.pos_y >= a.H ||
+                   J.search_range > a.R || J.pos_x < 0 || J.pos_y < 0 || J.pos_x + part_geom(part_first(bt < 1 || bt > 7 ? 7 : bt)).w > a.W ||
+                   J.pos_y + part_geom(part_first(bt < 1 || bt > 7 ? 7 : bt)).h > a.H ||
                    (J.search_range >= 0 && ((J.mv1[0] | J.mv1[1]) & 3)) || (J.search_range < 0 && !a.do_subpel);
   if (bad) {                                          // uniform over the CTA
     if (tid == 0) { *a.errflag = 1; O->cost_int = O->cost_sub = -1; O->mv_int[0] = O->mv_int[1] = O->mv_sub[0] = O->mv_sub[1] = 0; }
@@ -226,7 +227,8 @@ __global__ void __launch_bounds__(128) k_cand_dist(const CandArgs a)
   const int lane = threadIdx.x & 31, i = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (i >= a.n) return;
   const b2me_candidate c = a.cands[i];
-  if (c.blocktype < 1 || c.blocktype > 7 || c.ref < 0 || c.ref >= a.nrefs || c.pos_x < 0 || c.pos_y < 0 || c.pos_x >= a.W || c.pos_y >= a.H) {
+  if (c.blocktype < 1 || c.blocktype > 7 || c.ref < 0 || c.ref >= a.nrefs || c.pos_x < 0 || c.pos_y < 0 ||
+      c.pos_x + part_geom(part_first(c.blocktype)).w > a.W || c.pos_y + part_geom(part_first(c.blocktype)).h > a.H) {
     if (lane == 0) { *a.errflag = 1; a.out[i] = -1; }
     return;
   }
