@@ -168,6 +168,11 @@ class Searcher:
         self._chk(self.L.b2me_mc_luma_dev(self.h, _dp(mb_mode), _dp(b8mode), _dp(ref8), _dp(mv), _dp(orig_blk), _dp(pred_blk), _vp(stream)),
                   "b2me_mc_luma_dev")
 
+    def select_refs_dev(self, cost, ref_lambda, best_ref, best_cost, stream=0):
+        """list_prediction_cost (list 0) on torch CUDA tensors: cost [nmb][nrefs][41] i64 -> best_ref [nmb][21] i8, best_cost [nmb][21] i64"""
+        self._chk(self.L.b2me_select_refs_dev(self.h, _dp(cost), C.c_int(int(ref_lambda)), _dp(best_ref), _dp(best_cost), _vp(stream)),
+                  "b2me_select_refs_dev")
+
     def bipred_search(self, jobs, params, apply_weights=False, log_denom=0, test8x8=False):
         """full_search_bipred (+ sub_pel_bipred) for an array of synth.BIPRED_JOB records; returns BIPRED_RESULT records"""
         from . import synth

@@ -272,9 +272,51 @@ __global__ void __launch_bounds__(128) k_cand_dist(const CandArgs a)
   if (lane == 0) a.out[i] = (long long)s << 5;
 }
 
+// ---- list_prediction_cost, list 0 (JM/lencod/src/mode_decision.c:275-300; update_mcost :256-267; ref_cost mv_search.h:114) ---
+// For the 21 (mode, block) entries of every macroblock: the reference minimising motion cost + lambda * refbits(ref),
+// first minimum in reference order; the motion cost of an 8x8 quadrant in modes 5..7 is the sum over its sub-partitions
+// (PartitionMotionSearch, mv_search.c:1601-1843).  One thread per (macroblock, entry); HBM-bound (nrefs * 41 * 8 B in per MB).
+__constant__ signed char c_entry_parts[21][4] = {
+  {0, -1, -1, -1}, {1, -1, -1, -1}, {2, -1, -1, -1}, {3, -1, -1, -1}, {4, -1, -1, -1},
+  {5, -1, -1, -1}, {6, -1, -1, -1}, {7, -1, -1, -1}, {8, -1, -1, -1},
+  {9, 11, -1, -1}, {10, 12, -1, -1}, {13, 15, -1, -1}, {14, 16, -1, -1},
+  {17, 18, -1, -1}, {19, 20, -1, -1}, {21, 22, -1, -1}, {23, 24, -1, -1},
+  {25, 26, 29, 30}, {27, 28, 31, 32}, {33, 34, 37, 38}, {35, 36, 39, 40}};
+
+__global__ void __launch_bounds__(256) k_select_refs(int nmb, int nrefs, const long long *__restrict__ cost, int ref_lambda,
+                                                      int8_t *__restrict__ best_ref, long long *__restrict__ best_cost)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nmb * 21) return;
+  const int mb = i / 21, e = i - mb * 21;
+  long long bm = BI_DISTBLK_MAX; int br = 0;
+  for (int r = 0; r < nrefs; r++) {
+    long long mc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int p = c_entry_parts[e][k]; if (p >= 0) mc += cost[((size_t)mb * nrefs + r) * NPART + p]; }
+    if (mc < bm) {
+      mc += nrefs <= 1 ? 0 : (long long)ref_lambda * (65 - 2 * __clz(r + 1) - 2);    // refbits = 2 * floor(log2(ref + 1)) + 1
+      if (mc < bm) { bm = mc; br = r; }
+    }
+  }
+  best_ref[i] = (int8_t)br; best_cost[i] = bm;
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2me_select_refs_dev(b2me_ctx *c, const int64_t *cost_dev, int ref_lambda, int8_t *best_ref_dev, int64_t *best_cost_dev, void *stream)
+{
+  if (!c || !cost_dev || !best_ref_dev || !best_cost_dev) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const int n = c->nmb * 21;
+  k_select_refs<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->nmb, c->nrefs, reinterpret_cast<const long long *>(cost_dev), ref_lambda,
+                                                                  best_ref_dev, reinterpret_cast<long long *>(best_cost_dev));
+  B2_CUDA_CHECK(c, cudaGetLastError());
+  c->launches++;
+  return B2ME_OK;
+}
 
 extern "C" int b2me_distortion_candidates_dev(b2me_ctx *c, int metric, int test8x8, int n, const b2me_candidate *cands_dev,
                                               int64_t *out_dev, void *stream)

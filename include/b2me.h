@@ -184,6 +184,16 @@ int b2me_distortion_candidates(b2me_ctx *ctx, int metric, int test8x8, int n, co
 int b2me_distortion_candidates_dev(b2me_ctx *ctx, int metric, int test8x8, int n, const b2me_candidate *cands_dev,
                                    int64_t *out_dev, void *stream);
 
+/* ---- reference selection per (mode, block) (the first step of the mode decision) ------------------- */
+/* list_prediction_cost for list 0 (JM/lencod/src/mode_decision.c:275-300, update_mcost :256-267, ref_cost mv_search.h:114,
+ * refbits mv_search.c:377-385) from the search's cost array, for every macroblock of the picture:
+ *   cost [nmb][nrefs][41] int64 (cost_sub or cost_int of b2me_search_frame_dev), ref_lambda = lambda_mf[Q_PEL] (RDO build)
+ *   best_ref [nmb][21] int8, best_cost [nmb][21] int64 for the entries
+ *     0: mode 1;  1..2: mode 2 blocks 0,1;  3..4: mode 3 blocks 0,1;  5 + 4*(m-4) + b: mode m = 4..7, 8x8 quadrant b
+ *   (the motion cost of a quadrant in modes 5..7 is the sum over its sub-partitions, as PartitionMotionSearch accumulates it).
+ * Device pointers; keeps the 41 x nrefs candidates on the device and hands 21 (reference, cost) pairs per macroblock on. */
+int b2me_select_refs_dev(b2me_ctx *ctx, const int64_t *cost_dev, int ref_lambda, int8_t *best_ref_dev, int64_t *best_cost_dev, void *stream);
+
 /* ---- motion-compensated prediction (keeps the vectors on the device between search and transform) ---- */
 /* luma_prediction with p_dir == 0 (list 0), no weighting (JM/lencod/src/mc_prediction.c:144-236;
  * OneComponentLumaPrediction :117-136) for every macroblock of the picture, from a search result array.

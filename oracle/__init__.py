@@ -77,6 +77,18 @@ def partition_geometry():
     return out
 
 
+SELECT_ENTRIES = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1)] + [(m, b) for m in (4, 5, 6, 7) for b in range(4)]   # (mode, block) of the 21 entries
+
+
+def select_refs(cost, ref_lambda):
+    """list_prediction_cost (list 0) for every macroblock: cost [nmb][nrefs][41] -> (best_ref int8 [nmb][21], best_cost int64 [nmb][21])"""
+    cost = np.ascontiguousarray(cost, np.int64)
+    nmb, nrefs = cost.shape[:2]
+    br = np.zeros((nmb, 21), np.int8); bc = np.zeros((nmb, 21), np.int64)
+    orc_lib().orc_select_refs(C.c_int(nmb), C.c_int(nrefs), _ptr(cost), C.c_int(int(ref_lambda)), _ptr(br), _ptr(bc))
+    return br, bc
+
+
 def subpel_planes(luma):
     H, W = luma.shape
     out = np.zeros((4, 4, H + 2 * PAD_Y, W + 2 * PAD_X), np.uint8)
@@ -275,6 +287,13 @@ class JMRef:
         self.L.jmh_bipred_search(self.h, C.c_int(len(jobs)), _ptr(jobs), _ptr(lam), C.c_int(int(do_subpel)), C.c_int(int(test8x8)),
                                  C.c_int(int(wp)), C.c_int(log_denom), _ptr(out))
         return out
+
+    def list_prediction_cost(self, mode, block, costs, ref_lambda):
+        """the reference's list_prediction_cost (list 0) for one (mode, block): (best_ref, bmcost)"""
+        c = np.ascontiguousarray(costs, np.int64)
+        br = C.c_int(); bm = C.c_longlong()
+        self.L.jmh_list_prediction_cost(self.h, C.c_int(mode), C.c_int(block), C.c_int(len(c)), _ptr(c), C.c_int(int(ref_lambda)), C.byref(br), C.byref(bm))
+        return br.value, bm.value
 
     def search_frame(self, pred, center, lambda_factor, do_subpel=True, mb_first=0, mb_count=None):
         nmb = (self.W // 16) * (self.H // 16)

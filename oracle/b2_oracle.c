@@ -615,3 +615,36 @@ void orc_distortion_candidates(void *h, int metric, int test8x8, int n, const Or
     out[i] = ((int64_t)d) << 5;
   }
 }
+
+/* ------------------------------------------------------------------------------------
+ * list_prediction_cost, list 0 (JM/lencod/src/mode_decision.c:275-300) with update_mcost (:256-267) and ref_cost
+ * (JM/lencod/inc/mv_search.h:114-131, refbits of mv_search.c:377-385 = the ue(v) length 2*floor(log2(ref+1))+1):
+ * for the 21 (mode, block) entries of a macroblock -- mode 1 (1 block), 2 and 3 (2 blocks), 4..7 (the four 8x8 quadrants;
+ * the motion cost of a quadrant is the SUM over its sub-partitions, PartitionMotionSearch mv_search.c:1601-1843) -- the
+ * reference that minimises motion cost + lambda * refbits, first minimum in reference order.
+ * cost [nmb][nrefs][41] (cost_sub of the search) -> best_ref [nmb][21], best_cost [nmb][21].
+ * ---------------------------------------------------------------------------------- */
+static const signed char ORC_ENTRY_PARTS[21][4] = {
+  {0, -1, -1, -1}, {1, -1, -1, -1}, {2, -1, -1, -1}, {3, -1, -1, -1}, {4, -1, -1, -1},
+  {5, -1, -1, -1}, {6, -1, -1, -1}, {7, -1, -1, -1}, {8, -1, -1, -1},
+  {9, 11, -1, -1}, {10, 12, -1, -1}, {13, 15, -1, -1}, {14, 16, -1, -1},          /* 8x4: two rows of the quadrant */
+  {17, 18, -1, -1}, {19, 20, -1, -1}, {21, 22, -1, -1}, {23, 24, -1, -1},          /* 4x8: two columns */
+  {25, 26, 29, 30}, {27, 28, 31, 32}, {33, 34, 37, 38}, {35, 36, 39, 40}};         /* 4x4 */
+int orc_refbits(int ref) { int b = 1, v = ref + 1; while (v > 1) { v >>= 1; b += 2; } return b; }
+void orc_select_refs(int nmb, int nrefs, const int64_t *cost, int ref_lambda, int8_t *best_ref, int64_t *best_cost)
+{
+  int mb, e, r, k;
+  for (mb = 0; mb < nmb; mb++)
+    for (e = 0; e < 21; e++) {
+      int64_t bm = DISTBLK_MAX_ORC; int br = 0;
+      for (r = 0; r < nrefs; r++) {
+        int64_t mc = 0;
+        for (k = 0; k < 4 && ORC_ENTRY_PARTS[e][k] >= 0; k++) mc += cost[((size_t)mb * nrefs + r) * 41 + ORC_ENTRY_PARTS[e][k]];
+        if (mc < bm) {                                   /* update_mcost */
+          mc += nrefs <= 1 ? 0 : (int64_t)ref_lambda * orc_refbits(r);
+          if (mc < bm) { bm = mc; br = r; }
+        }
+      }
+      best_ref[(size_t)mb * 21 + e] = (int8_t)br; best_cost[(size_t)mb * 21 + e] = bm;
+    }
+}

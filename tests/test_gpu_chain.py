@@ -54,3 +54,28 @@ def test_search_mc_tq_chain_matches_oracle():
         assert (g.cpu().numpy() == e).all(), n
     # the prediction is a good one: the reconstruction is close to the original
     assert np.abs(d_recon.cpu().numpy().astype(int) - o_orig.astype(int)).mean() < 8.0
+
+
+def test_reference_selection_on_the_device_matches_oracle():
+    """b2me_select_refs_dev (list_prediction_cost, list 0) on the cost array the search left on the device"""
+    import torch
+    W, H, R, NR = 96, 64, 8, 4
+    fr = synth.luma_sequence(W, H, NR + 1, seed=7)
+    cur, refs = fr[NR], fr[[3, 2, 1, 0]]
+    s = api.Searcher(W, H, NR, R)
+    s.set_cur(cur)
+    for r in range(NR):
+        s.set_ref(r, refs[r])
+    pred, cen = synth.predictors(W, H, NR, seed=3, spread=2, rmax=4)
+    dev = torch.device("cuda", 0)
+    dp, dc = torch.from_numpy(pred).to(dev), torch.from_numpy(cen).to(dev)
+    mvi = torch.zeros((s.nmb, NR, 41, 2), dtype=torch.int16, device=dev); mvs = torch.zeros_like(mvi)
+    ci = torch.zeros((s.nmb, NR, 41), dtype=torch.int64, device=dev); cs = torch.zeros_like(ci)
+    s.search_frame_dev(dp, dc, api.make_params((187, 187, 187)), mvi, ci, mvs, cs)
+    br = torch.zeros((s.nmb, 21), dtype=torch.int8, device=dev); bc = torch.zeros((s.nmb, 21), dtype=torch.int64, device=dev)
+    for lam in (187, 4000):
+        s.select_refs_dev(cs, lam, br, bc)
+        torch.cuda.synchronize()
+        ebr, ebc = oracle.select_refs(cs.cpu().numpy(), lam)
+        assert (br.cpu().numpy() == ebr).all() and (bc.cpu().numpy() == ebc).all(), lam
+    assert len(np.unique(br.cpu().numpy())) > 1

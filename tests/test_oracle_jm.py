@@ -238,3 +238,21 @@ def test_candidate_distortions_equal_live_reference():
     for i, k in enumerate(c8):
         q = (int(k["pos_x"]) * 4 + int(k["mv"][0]), int(k["pos_y"]) * 4 + int(k["mv"][1]))
         assert jm.satd(int(k["pos_x"]), int(k["pos_y"]), int(k["blocktype"]), int(k["ref"]), *q, test8x8=1) == satd8[i]
+
+
+@pytest.mark.skipif(not oracle.have_jmref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_reference_selection_equals_live_reference():
+    """list_prediction_cost (mode_decision.c:275, list 0) of the unmodified JM for every (mode, block) entry, ties included"""
+    parts = [[0], [1], [2], [3], [4], [5], [6], [7], [8], [9, 11], [10, 12], [13, 15], [14, 16], [17, 18], [19, 20], [21, 22], [23, 24],
+             [25, 26, 29, 30], [27, 28, 31, 32], [33, 34, 37, 38], [35, 36, 39, 40]]
+    rng = np.random.default_rng(3)
+    for nrefs in (1, 3, 5):
+        jm = oracle.JMRef(64, 48, 4, nrefs)
+        cost = rng.integers(0, 4000, (5, nrefs, 41)).astype(np.int64)
+        cost[0] = 777                                           # every reference ties: the first one stays
+        cost[1] = rng.integers(995, 1005, (nrefs, 41))          # within the reference-cost differences
+        br, bc = oracle.select_refs(cost, 187)
+        for mb in range(5):
+            for e, (mode, blk) in enumerate(oracle.SELECT_ENTRIES):
+                c = [int(cost[mb, r, parts[e]].sum()) for r in range(nrefs)]
+                assert jm.list_prediction_cost(mode, blk, c, 187) == (int(br[mb, e]), int(bc[mb, e])), (nrefs, mb, e)
