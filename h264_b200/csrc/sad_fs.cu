@@ -59,7 +59,10 @@ namespace b2 {
 #define FS_KV 4
 #endif
 constexpr int FS_K = FS_KV;         // candidate rows per task (lock step): 4 = rolled fs_task4, 5 = fully unrolled fs_task
-constexpr int FS_PRE = 0;        // radius of the exact pre-pass around the centres (initial bounds)
+#ifndef FS_PREV
+#define FS_PREV 0
+#endif
+constexpr int FS_PRE = FS_PREV;       // radius of the exact pre-pass around the centres (initial bounds)
 constexpr int FS_SMAX = 7;       // partitions whose centres lie within a 7-pel box share one window pass
 constexpr int FS_BMAX = 12;      // a trailing column block of at most this width is walked row-major (type B)
 constexpr int FS_MCAP = 2047;    // cap of each half of the mv-cost lower bound (keeps packed sums in range)
@@ -443,7 +446,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, vo
 #define FS_CLOCK() 0ll
 #endif
 
-struct FsCtaStats { int err, nhits, ngroups, nitems; unsigned long long cyc[6]; };   // cyc: task, exact, producer, -, total, tma-wait (warp cycles)
+struct FsCtaStats { int err, nhits, ngroups, nitems; unsigned long long cyc[6]; };   // cyc: task, exact, producer total, worker idle, worker total, producer busy (warp cycles)
 
 // ---- producer-warp routines (called by ONE warp) -------------------------------------------------------------
 
@@ -633,10 +636,9 @@ __device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWa
     }
     __syncwarp();
     const uint32_t parity = (uint32_t)C.tma_uses & 1u;
-    const long long tw0 = clock64();
     while (!mbar_try_wait_ns(&C.mbar, parity, 2000u)) { if (a.flags & 2) __nanosleep(400); }
     __syncwarp();
-    if (lane == 0) { C.tma_uses++; atomicAdd(&st->cyc[5], (unsigned long long)(clock64() - tw0)); }
+    if (lane == 0) C.tma_uses++;
   } else {                                         // window leaves the search plane: per-pixel coordinate clamp
     const uint8_t *plane = a.spl + (size_t)S.ref * 16 * a.Wq * a.Hq;     // shift-0 plane
     const int nrows = min(K * S.ngy + 15, G.rows - 3), wpw = PITCH >> 2;
@@ -719,6 +721,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
     //      the prepared unit to that buffer, then writes the finished item's results and prepares the next ----
     const long long t_p0 = clock64();
     int seen0 = 0, seen1 = 0, stage = 2, item = 0;
+    long long p_busy = 0;                            // cycles spent attaching / writing / preparing (FS_PROFILE)
     if (lane == 0) item = atomicAdd(a.work_counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     bool staged = fs_prepare<PITCH>(SS[0], item, a, &st);
@@ -732,6 +735,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
       int nend = 0; bool any = false;
       // parity of evt's current phase, read BEFORE the scan: a completion after this read ends the wait below at once
       const uint32_t evp = mbar_test_wait(&evt, 0) ? 1u : 0u;
+      const long long tb0 = FS_CLOCK();
 #pragma unroll 1
       for (int b = 0; b < 2; b++) {
         FsCtl &C = CB[b];
@@ -758,10 +762,11 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
           if (lane == 0) { O.item = -1; __threadfence_block(); *reinterpret_cast<volatile int *>(&C.ended) = 1; }
         }
       }
+      if (any) p_busy += FS_CLOCK() - tb0;
       if (nend == 2) break;
       if (!any && !mbar_try_wait_ns(&evt, evp, 20000u) && (a.flags & 2)) __nanosleep(1000);   // (two completions inside one scan would be seen at the time-out)
     }
-    if (lane == 0) atomicAdd(&st.cyc[2], (unsigned long long)(clock64() - t_p0));
+    if (lane == 0) { atomicAdd(&st.cyc[2], (unsigned long long)(clock64() - t_p0)); atomicAdd(&st.cyc[5], (unsigned long long)p_busy); }
   } else {
   // ---- worker warps.  They drain ONE buffer at a time (pref) and move to the other only when pref has no task
   //      left to claim, so the two units finish staggered and the producer's work overlaps the other buffer ----
