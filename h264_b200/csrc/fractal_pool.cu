@@ -39,10 +39,17 @@ constexpr int FP_TM = 128;            // range rows (range x isometry) per CTA t
 constexpr int FP_TN = 256;            // domains per MMA tile
 constexpr int FP_BSTAGES = 4;         // B-tile ring in shared memory
 constexpr int FP_CSTAGES = 4;         // per-tile constants ring: a slot is reused only after the EPILOGUE of its tile
+#ifndef FP_SPARSE_V
+#define FP_SPARSE_V 2
+#endif
+constexpr int FP_SPARSE = FP_SPARSE_V;          // rows of a warp passing a chunk's filter: up to this many are re-examined warp-across-columns
 constexpr int FP_CHUNK = 32;          // epilogue column chunk
 constexpr uint32_t FP_MAGIC = 0x4B000000u;   // float 2^23
 constexpr int FP_CT_BYTES = 3104;     // per-tile constants: float Sd[256] | int det[256] | float wcol[256] | float wchunk[8]
-constexpr int FP_EPI_GROUPS = 2;      // epilogue warp groups (4 warps each, one per TMEM lane quarter); group g takes chunks ch % 2 == g
+#ifndef FP_GROUPS_V
+#define FP_GROUPS_V 3
+#endif
+constexpr int FP_EPI_GROUPS = FP_GROUPS_V;      // epilogue warp groups (4 warps each, one per TMEM lane quarter); group g takes chunks ch % 2 == g
 constexpr int FP_EPI_WARPS = 4 * FP_EPI_GROUPS;
 constexpr int FP_THREADS = 128 + 32 * FP_EPI_WARPS;   // warp 0 producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4.. epilogue
 
@@ -156,9 +163,21 @@ struct FpSmem {
   unsigned long long t_full[2], t_empty[2];
   unsigned long long c_empty[FP_CSTAGES];
   uint32_t tmem_base;
-  long long mG[FP_TM]; int mIdx[FP_TM]; short mAq[FP_TM];   // per-row partial results of epilogue group 1, merged by group 0
+  long long mG[FP_EPI_GROUPS - 1][FP_TM]; int mIdx[FP_EPI_GROUPS - 1][FP_TM]; short mAq[FP_EPI_GROUPS - 1][FP_TM];   // per-row partial results of epilogue group 1, merged by group 0
   float shareT[FP_EPI_GROUPS][FP_TM];                        // per-row thresholds exchanged between the groups once per tile
 };
+
+// Folds a candidate (G >= bestG) at pool position `pos` into a row's running best: a larger G wins, equal G goes to the
+// smaller ORIGINAL pool index (the reference scans the pool in that order and keeps the first maximum).
+__device__ __forceinline__ void fp_fold(const int *__restrict__ orig, long long G, int pos, int aq,
+                                        long long &bestG, int &bestPos, int &bestIdx, int &bestAq, float &Tf)
+{
+  if (G > bestG) { bestG = G; bestPos = pos; bestIdx = -1; bestAq = aq; Tf = __ll2float_rd(G); return; }
+  if (G < bestG) return;
+  const int idx = orig[pos];
+  if (bestIdx < 0) bestIdx = bestPos < 0 ? 0x7fffffff : orig[bestPos];
+  if (idx < bestIdx) { bestPos = pos; bestIdx = idx; bestAq = aq; }
+}
 
 __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_constant__ FpArgs a)
 {
@@ -243,7 +262,12 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
     if (lane == 0) { fp_mbar_arrive(&S->t_empty[0]); fp_mbar_arrive(&S->t_empty[1]); }
     unsigned long long n_exact = 0, n_rescan = 0, n_chunk = 0;
     uint32_t it = 0;
-    constexpr int NCH = FP_TN / FP_CHUNK / FP_EPI_GROUPS;     // chunks per tile per group
+    constexpr int NCHT = FP_TN / FP_CHUNK;                     // chunks per tile; group g takes ch = g, g + groups, ...
+    constexpr int NCH = (NCHT + FP_EPI_GROUPS - 1) / FP_EPI_GROUPS;
+    #ifndef FP_PF_MAXG
+#define FP_PF_MAXG 2
+#endif
+    constexpr bool PF = FP_EPI_GROUPS <= FP_PF_MAXG;                    // prefetch the next chunk's accumulators (two register buffers) only while the registers allow
     for (int i = 0; i < nmt; i++) {
       const int mt = (int)blockIdx.x + i * (int)gridDim.x;
       const int rit = q * 32 + lane;                          // row in tile
@@ -252,7 +276,9 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
       const bool rvalid = rng < a.nranges;
       const int sr = rvalid ? a.sr[rng] : 0;
       const float nfr = -(float)sr * (1.0f / 64.0f);          // exact: sr < 2^14
-      long long bestG = -1; int bestIdx = 0x7fffffff, bestAq = 0;
+      // running best of the row: position in the (sorted) pool; its ORIGINAL index (the tie-break key) is fetched from
+      // global memory only when a tie needs it (-1 = not fetched yet), which keeps that latency out of the re-examinations
+      long long bestG = -1; int bestPos = -1, bestIdx = -1, bestAq = 0;
       float Tf = -1.0f;                                        // lower bound of the row's best G (either group's)
       if (FP_EPI_GROUPS > 1) S->shareT[grp][rit] = -1.0f;
       for (int nt = 0; nt < a.ntiles; nt++, it++) {
@@ -262,14 +288,16 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
         const float *fdp = reinterpret_cast<const float *>(sCt + cs * FP_CT_BYTES);
         const float *wcp = reinterpret_cast<const float *>(sCt + cs * FP_CT_BYTES + 2048);
         const float *wp = reinterpret_cast<const float *>(sCt + cs * FP_CT_BYTES + 3072);
-        uint32_t vbuf[2][32];
-        fp_tmem_ld32_nowait(tl + ts * FP_TN + grp * FP_CHUNK, vbuf[0]);
+        uint32_t vbuf[PF ? 2 : 1][32];
+        if (PF) fp_tmem_ld32_nowait(tl + ts * FP_TN + grp * FP_CHUNK, vbuf[0]);
 #pragma unroll
         for (int k = 0; k < NCH; k++) {
           const int ch = k * FP_EPI_GROUPS + grp;
-          uint32_t (&v)[32] = vbuf[k & 1];
+          if (NCHT % FP_EPI_GROUPS != 0 && ch >= NCHT) break;
+          uint32_t (&v)[32] = vbuf[PF ? (k & 1) : 0];
+          if (!PF) fp_tmem_ld32_nowait(tl + ts * FP_TN + ch * FP_CHUNK, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (k + 1 < NCH) fp_tmem_ld32_nowait(tl + ts * FP_TN + (ch + FP_EPI_GROUPS) * FP_CHUNK, vbuf[(k + 1) & 1]);   // next chunk in flight
+          if (PF && k + 1 < NCH && ch + FP_EPI_GROUPS < NCHT) fp_tmem_ld32_nowait(tl + ts * FP_TN + (ch + FP_EPI_GROUPS) * FP_CHUNK, vbuf[(k + 1) & 1]);   // next chunk in flight
           fp_tmem_st32_const(tl + ts * FP_TN + ch * FP_CHUNK, FP_MAGIC);   // re-arm the accumulator
           if (a.probe == 1) continue;
           float g[32];
@@ -299,7 +327,60 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
           const float X = fmaxf(__int_as_float(mxa) - 8388608.0f, 8388608.0f - __int_as_float(mna)) + 0.5f;
           const bool pass = rvalid && a.probe != 2 && (X * X) * wp[ch] * 1.00001f >= Tf;     // probe 2: filter arithmetic only
           n_chunk++;
-          if (__any_sync(0xffffffffu, pass)) {
+          uint32_t pm = __ballot_sync(0xffffffffu, pass);
+          if (pm && __popc(pm) <= FP_SPARSE) {
+            // ---- few rows passed: re-examine the chunk one row at a time with the WARP across its 32 columns
+            //      (rows pass rarely and independently: a lane walking its own 32 columns would idle the other 31).
+            //      The row's accumulators cross through shared memory; lane j takes column j: its own bound
+            //      10000*num^2/det against the row's threshold, then the exact integer fit of the flagged columns in
+            //      parallel; the row's owner folds the survivors into its running best ----
+            n_rescan++;
+            uint32_t *scr = sScr + (warp - 4) * 1024;
+            const int *detp = reinterpret_cast<const int *>(sCt + cs * FP_CT_BYTES + 1024);
+            const int col = ch * FP_CHUNK + lane;
+            const float sdf = fdp[col], wcj = wcp[col];
+            const int det = detp[col];
+            while (pm) {
+              const int r = __ffs(pm) - 1; pm &= pm - 1;
+              if (lane == r) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; j4++) reinterpret_cast<uint4 *>(scr)[j4] = make_uint4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+              }
+              __syncwarp();
+              const uint32_t vj = scr[lane];
+              const float Tr = __shfl_sync(0xffffffffu, Tf, r);
+              const int srr = __shfl_sync(0xffffffffu, sr, r);
+              const float gj = fmaf(-(float)srr * (1.0f / 64.0f), sdf, __uint_as_float(vj));
+              const float xj = fabsf(gj - 8388608.0f) + 0.5f;
+              const bool flag = det >= 0 && (xj * xj) * wcj * 1.00001f >= Tr;     // det < 0: padding column
+              uint32_t cm = 0;
+              long long G = -1; int aq = 0;
+              if (__any_sync(0xffffffffu, flag)) {
+                const long long bG = __shfl_sync(0xffffffffu, bestG, r);
+                bool cand = false;
+                if (flag) {
+                  n_exact++;
+                  // exact integer fit (oracle/b2_oracle_pool.c orc_pool_pair); the double quotient truncates like the
+                  // exact rational: a non-integer p/q with q < 2^29 is further than 2^-53 (relative) from an integer
+                  const int num = 64 * (int)(vj - FP_MAGIC) - srr * (int)sdf;
+                  const int qa = det == 0 ? 0 : (int)((100.0 * (double)num) / (double)det);
+                  aq = fp_quan_a(qa);
+                  if (aq >= -235 && aq <= 400) {
+                    G = 200ll * aq * num - (long long)aq * aq * det;
+                    cand = G >= bG;
+                  }
+                }
+                cm = __ballot_sync(0xffffffffu, cand);
+              }
+              while (cm) {                                        // usually one column; first maximum in pool-index order
+                const int l = __ffs(cm) - 1; cm &= cm - 1;
+                const long long G2 = __shfl_sync(0xffffffffu, G, l);
+                const int aq2 = __shfl_sync(0xffffffffu, aq, l);
+                if (lane == r) fp_fold(a.orig, G2, nt * FP_TN + ch * FP_CHUNK + l, aq2, bestG, bestPos, bestIdx, bestAq, Tf);
+              }
+              __syncwarp();
+            }
+          } else if (pm) {
             // ---- re-examine the 32 columns.  Phase 1 (registers, branch-free): mask of the columns whose own
             //      bound 10000*num^2/det reaches the row's threshold ----
             n_rescan++;
@@ -339,8 +420,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
                 if (aq < -235 || aq > 400) continue;
                 const long long G = 200ll * aq * num - (long long)aq * aq * det;
                 if (G < bestG) continue;
-                const int idx = a.orig[nt * FP_TN + ch * FP_CHUNK + j];
-                if (G > bestG || idx < bestIdx) { bestG = G; bestIdx = idx; bestAq = aq; Tf = __ll2float_rd(G); }
+                fp_fold(a.orig, G, nt * FP_TN + ch * FP_CHUNK + j, aq, bestG, bestPos, bestIdx, bestAq, Tf);
               }
               __syncwarp();
             }
@@ -349,7 +429,8 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
         // ---- exchange the row thresholds with the other epilogue group (stale by at most one tile: conservative) ----
         if (FP_EPI_GROUPS > 1 && a.probe != 1) {
           S->shareT[grp][rit] = Tf;
-          Tf = fmaxf(Tf, *reinterpret_cast<volatile float *>(&S->shareT[grp ^ 1][rit]));
+#pragma unroll
+          for (int o = 1; o < FP_EPI_GROUPS; o++) Tf = fmaxf(Tf, *reinterpret_cast<volatile float *>(&S->shareT[(grp + o) % FP_EPI_GROUPS][rit]));
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -357,12 +438,16 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
         if (lane == 0) { fp_mbar_arrive(&S->t_empty[ts]); fp_mbar_arrive(&S->c_empty[cs]); }
       }
       if (a.probe != 1) {
+        if (bestIdx < 0) bestIdx = bestPos < 0 ? 0x7fffffff : a.orig[bestPos];
         // ---- merge the groups' partial results per row (first maximum in pool-index order) ----
-        if (grp > 0) { S->mG[rit] = bestG; S->mIdx[rit] = bestIdx; S->mAq[rit] = (short)bestAq; }
+        if (grp > 0) { S->mG[grp - 1][rit] = bestG; S->mIdx[grp - 1][rit] = bestIdx; S->mAq[grp - 1][rit] = (short)bestAq; }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * FP_EPI_WARPS) : "memory");
         if (grp == 0) {
-          const long long G1 = S->mG[rit]; const int i1 = S->mIdx[rit], a1 = S->mAq[rit];
-          if (G1 > bestG || (G1 == bestG && i1 < bestIdx)) { bestG = G1; bestIdx = i1; bestAq = a1; }
+#pragma unroll
+          for (int o = 0; o < FP_EPI_GROUPS - 1; o++) {
+            const long long G1 = S->mG[o][rit]; const int i1 = S->mIdx[o][rit], a1 = S->mAq[o][rit];
+            if (G1 > bestG || (G1 == bestG && i1 < bestIdx)) { bestG = G1; bestIdx = i1; bestAq = a1; }
+          }
           // ---- the 8 isometries of a range are 8 consecutive lanes: first maximum in (iso, pool index) order ----
           long long G = bestG; int idx = bestIdx, aq = bestAq, iso = lane & 7;
 #pragma unroll
@@ -647,7 +732,7 @@ static int fp_launch(b2fp_ctx *c, int probe, int32_t *dom, uint8_t *iso, int16_t
   a.stats = c->d_stats; a.probe = probe;
   const int smem = 2 * 8192 + FP_BSTAGES * 16384 + FP_CSTAGES * FP_CT_BYTES + FP_EPI_WARPS * 4096 + (int)sizeof(FpSmem) + 1024;
   static int configured = 0;
-  if (!configured) { FP_CHECK(c, cudaFuncSetAttribute(k_frac_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); configured = 1; }
+  if (!configured) { FP_CHECK(c, cudaFuncSetAttribute(k_frac_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, smem < 160 * 1024 ? 160 * 1024 : smem)); configured = 1; }
   const int grid = c->mtiles < c->sm_count ? c->mtiles : c->sm_count;
   if (timed) cudaEventRecord(c->ev0, s);
   // >= 116 KB of dynamic shared memory keeps ONE CTA per SM: each CTA allocates all 512 TMEM columns

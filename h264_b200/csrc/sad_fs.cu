@@ -446,7 +446,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, vo
 #define FS_CLOCK() 0ll
 #endif
 
-struct FsCtaStats { int err, nhits, ngroups, nitems; unsigned long long cyc[6]; };   // cyc: task, exact, producer total, worker idle, worker total, producer busy (warp cycles)
+struct FsCtaStats { int err, nhits, ngroups, nitems; unsigned long long cyc[9]; };   // cyc: task, exact, producer total, worker idle, worker total, producer busy (warp cycles)
 
 // ---- producer-warp routines (called by ONE warp) -------------------------------------------------------------
 
@@ -705,7 +705,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
     pgt[tid] = (gm.ox >> 2) | ((gm.oy >> 2) << 4) | (((gm.ox + gm.w) >> 2) << 8) | (((gm.oy + gm.h) >> 2) << 12);
   }
   for (int i = tid; i < (NWORK + 1) * 2 * 28; i += NT) (&WS[0].sat[0][0])[i] = 0;
-  if (tid == 0) { st.err = 0; st.nhits = 0; st.ngroups = 0; st.nitems = 0; for (int i = 0; i < 6; i++) st.cyc[i] = 0; }
+  if (tid == 0) { st.err = 0; st.nhits = 0; st.ngroups = 0; st.nitems = 0; for (int i = 0; i < 9; i++) st.cyc[i] = 0; }
   if (tid < 2) {
     FsCtl &C = CB[tid];
     C.ready_epoch = 0; C.finished_epoch = 0; C.next = 0; C.done = 0; C.ended = 0; C.epoch = 0; C.tma_uses = 0; C.ntask = 0; C.slot = tid;
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
   long long c_task = 0, c_exact = 0;
   const long long t_begin = clock64();
   unsigned long long g_begin; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_begin));
-  long long c_idle = 0;
+  long long c_idle = 0, c_claim = 0, c_dec = 0, c_post = 0;
   for (;;) {
     bool any = false; int nend = 0;
     const long long ti0 = FS_CLOCK();
@@ -790,20 +790,30 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
       const int ep = *reinterpret_cast<volatile int *>(&C.ready_epoch);
       if (ep <= 0 || (c >> 20) != (ep & 0x7ff)) continue;       // counter not (yet) armed for the published epoch
       FS_FENCE();
-      const int t0 = c & 0xfffff;
       const int ntask = *reinterpret_cast<volatile int *>(&C.ntask);
       const int slot = *reinterpret_cast<volatile int *>(&C.slot);
       FS_FENCE();
       if (*reinterpret_cast<volatile int *>(&C.ready_epoch) != ep) continue;   // re-armed meanwhile: ntask / slot may be the next unit's
-      if (t0 >= ntask) { if (b) ex1 = ep; else ex0 = ep; continue; }
+      if ((c & 0xfffff) >= ntask) { if (b) ex1 = ep; else ex0 = ep; continue; }
       pref = b;
       any = true;
       SLOT &S = SS[slot];
       uint8_t *win = smem + b * G.slot_bytes;
       const int g = S.g;
+      int t0 = c & 0xfffff;
+      c_claim += FS_CLOCK() - ti0;
+      // A warp that holds unfinished tasks of (b, ep) knows the unit cannot complete, so the buffer cannot be re-armed:
+      // its NEXT claim is issued before the tasks (the shared-memory atomic's latency hides under them) and needs no
+      // validation, and its completion count is a fire-and-forget add unless that next claim came back exhausted.
+#pragma unroll 1
+      for (;;) {
       const int t1 = min(t0 + a.claim, ntask);
+      const bool more = t1 < ntask;
+      int cn = 0;
+      if (more && lane == 0) cn = atomicAdd(&C.next, a.claim);
 #pragma unroll 1
       for (int t = t0; t < t1; t++) {
+        const long long td0 = FS_CLOCK();
         int dxa, dy0; bool va, vb;
         if (t < S.ntaskA) {
           const int e = S.ttab[t];
@@ -820,6 +830,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         const int cc = dxa & 3;
         const uint8_t *wb = win + cc * G.copy_bytes + (dy0 + cc) * PITCH + (dxa >> 2) * 4;
         const long long tt0 = FS_CLOCK();
+        c_dec += tt0 - td0;
         uint32_t pass = 0;
 #pragma unroll 1
         for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
@@ -848,20 +859,32 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
           c_exact += FS_CLOCK() - tt1;
         }
       }
+      const long long tp0 = FS_CLOCK();
       __syncwarp();
+      cn = __shfl_sync(0xffffffffu, cn, 0);
+      cn = more ? (cn & 0xfffff) : ntask;
+      if (cn < ntask) {                              // more tasks of this unit in hand
+        if (lane == 0) { FS_FENCE(); atomicAdd(&C.done, t1 - t0); }
+        t0 = cn;
+        c_post += FS_CLOCK() - tp0;
+        continue;
+      }
       int d = 0;
       if (lane == 0) { FS_FENCE(); d = atomicAdd(&C.done, t1 - t0) + (t1 - t0); }
       d = __shfl_sync(0xffffffffu, d, 0);
+      if (b) ex1 = ep; else ex0 = ep;                // nothing left to claim in this epoch
       if (d == ntask) {                              // unit complete: hand the buffer to the producer warp
-        if (b) ex1 = ep; else ex0 = ep;
         if (lane == 0) { FS_FENCE(); *reinterpret_cast<volatile int *>(&C.finished_epoch) = ep; FS_FENCE(); mbar_arrive(&evt); }
+      }
+      c_post += FS_CLOCK() - tp0;
+      break;
       }
     }
     if (nend == 2) break;
     if (!any) { __nanosleep(200); c_idle += FS_CLOCK() - ti0; }
   }
   if (lane == 0 && nh) atomicAdd(&st.nhits, nh);
-  if (lane == 0) atomicAdd(&st.cyc[3], (unsigned long long)c_idle);
+  if (lane == 0) { atomicAdd(&st.cyc[3], (unsigned long long)c_idle); atomicAdd(&st.cyc[6], (unsigned long long)c_claim); atomicAdd(&st.cyc[7], (unsigned long long)c_dec); atomicAdd(&st.cyc[8], (unsigned long long)c_post); }
   if (lane == 0) {
     atomicAdd(&st.cyc[0], (unsigned long long)c_task); atomicAdd(&st.cyc[1], (unsigned long long)c_exact);
     atomicAdd(&st.cyc[4], (unsigned long long)(clock64() - t_begin));
@@ -879,6 +902,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
       atomicAdd(&a.stats[1], (unsigned long long)st.ngroups);
       atomicAdd(&a.stats[2], (unsigned long long)st.nitems);
       for (int i = 0; i < 6; i++) atomicAdd(&a.stats[3 + i], st.cyc[i]);
+      for (int i = 6; i < 9; i++) atomicAdd(&a.stats[5 + i], st.cyc[i]);     // [9], [10]: CTA 0's clock calibration
     }
   }
 }
