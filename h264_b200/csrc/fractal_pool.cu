@@ -140,12 +140,23 @@ __device__ __forceinline__ void fp_tmem_ld32_nowait(uint32_t taddr, uint32_t (&v
                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void fp_tmem_st32_const(uint32_t taddr, uint32_t c)
+// Re-arms 32 accumulator columns with the magic constant: eight x4 stores from FOUR registers that the caller keeps
+// live (opaque to the compiler, see fp_magic4), instead of one x32 store whose 32 source registers would have to be
+// re-materialised for every chunk (they cannot stay allocated next to the chunk's 64 live values).
+struct FpMagic4 { uint32_t a, b, c, d; };
+__device__ __forceinline__ FpMagic4 fp_magic4()
 {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-               "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
-               "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-               ::"r"(taddr), "r"(c) : "memory");
+  FpMagic4 m;
+  asm volatile("mov.u32 %0, 0x4B000000;\n\tmov.u32 %1, 0x4B000000;\n\tmov.u32 %2, 0x4B000000;\n\tmov.u32 %3, 0x4B000000;"
+               : "=r"(m.a), "=r"(m.b), "=r"(m.c), "=r"(m.d));
+  return m;
+}
+__device__ __forceinline__ void fp_tmem_st32_const(uint32_t taddr, const FpMagic4 &m)
+{
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr + 4 * i), "r"(m.a), "r"(m.b), "r"(m.c), "r"(m.d) : "memory");
 }
 
 __host__ __device__ __forceinline__ int fp_quan_a(int x)
@@ -255,11 +266,16 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
     //       group grp = (warp-4)>>2 takes the 32-column chunks with ch % FP_EPI_GROUPS == grp =====
     const int q = warp & 3, grp = (warp - 4) >> 2;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
-    for (int c0 = grp * 32; c0 < 512; c0 += 32 * FP_EPI_GROUPS) fp_tmem_st32_const(tl + c0, FP_MAGIC);
+    const FpMagic4 magic = fp_magic4();
+    for (int c0 = grp * 32; c0 < 512; c0 += 32 * FP_EPI_GROUPS) fp_tmem_st32_const(tl + c0, magic);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
     if (lane == 0) { fp_mbar_arrive(&S->t_empty[0]); fp_mbar_arrive(&S->t_empty[1]); }
+    // thresholds published to the other groups: reset here and between the two barriers that end an M tile, so that no
+    // group can read a value of the previous tile's rows
+    S->shareT[grp][q * 32 + lane] = -1.0f;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * FP_EPI_WARPS) : "memory");
     unsigned long long n_exact = 0, n_rescan = 0, n_chunk = 0;
     uint32_t it = 0;
     constexpr int NCHT = FP_TN / FP_CHUNK;                     // chunks per tile; group g takes ch = g, g + groups, ...
@@ -280,7 +296,6 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
       // global memory only when a tie needs it (-1 = not fetched yet), which keeps that latency out of the re-examinations
       long long bestG = -1; int bestPos = -1, bestIdx = -1, bestAq = 0;
       float Tf = -1.0f;                                        // lower bound of the row's best G (either group's)
-      if (FP_EPI_GROUPS > 1) S->shareT[grp][rit] = -1.0f;
       for (int nt = 0; nt < a.ntiles; nt++, it++) {
         const int cs = it % FP_CSTAGES, ts = it & 1;
         fp_mbar_wait(&S->t_full[ts], (it >> 1) & 1);
@@ -298,7 +313,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
           if (!PF) fp_tmem_ld32_nowait(tl + ts * FP_TN + ch * FP_CHUNK, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (PF && k + 1 < NCH && ch + FP_EPI_GROUPS < NCHT) fp_tmem_ld32_nowait(tl + ts * FP_TN + (ch + FP_EPI_GROUPS) * FP_CHUNK, vbuf[(k + 1) & 1]);   // next chunk in flight
-          fp_tmem_st32_const(tl + ts * FP_TN + ch * FP_CHUNK, FP_MAGIC);   // re-arm the accumulator
+          fp_tmem_st32_const(tl + ts * FP_TN + ch * FP_CHUNK, magic);   // re-arm the accumulator
           if (a.probe == 1) continue;
           float g[32];
 #pragma unroll
@@ -325,9 +340,14 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
           }
           const int mxa = max(__vimax3_s32(mx[0], mx[1], mx[2]), mx[3]), mna = min(__vimin3_s32(mn[0], mn[1], mn[2]), mn[3]);
           const float X = fmaxf(__int_as_float(mxa) - 8388608.0f, 8388608.0f - __int_as_float(mna)) + 0.5f;
+          if (FP_EPI_GROUPS > 1) {
+#pragma unroll
+            for (int o = 1; o < FP_EPI_GROUPS; o++) Tf = fmaxf(Tf, *reinterpret_cast<volatile float *>(&S->shareT[(grp + o) % FP_EPI_GROUPS][rit]));
+          }
           const bool pass = rvalid && a.probe != 2 && (X * X) * wp[ch] * 1.00001f >= Tf;     // probe 2: filter arithmetic only
           n_chunk++;
           uint32_t pm = __ballot_sync(0xffffffffu, pass);
+          const uint32_t pm0 = pm;
           if (pm && __popc(pm) <= FP_SPARSE) {
             // ---- few rows passed: re-examine the chunk one row at a time with the WARP across its 32 columns
             //      (rows pass rarely and independently: a lane walking its own 32 columns would idle the other 31).
@@ -425,12 +445,14 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
               __syncwarp();
             }
           }
-        }
-        // ---- exchange the row thresholds with the other epilogue group (stale by at most one tile: conservative) ----
-        if (FP_EPI_GROUPS > 1 && a.probe != 1) {
-          S->shareT[grp][rit] = Tf;
-#pragma unroll
-          for (int o = 1; o < FP_EPI_GROUPS; o++) Tf = fmaxf(Tf, *reinterpret_cast<volatile float *>(&S->shareT[(grp + o) % FP_EPI_GROUPS][rit]));
+          if (pm0) {
+            // Only the best of a range's 8 isometries is written, so its rows (8 consecutive lanes) share ONE threshold:
+            // a candidate below another isometry's best can never be the range's result (ties stay in: the tests are >=)
+            Tf = fmaxf(Tf, __shfl_xor_sync(0xffffffffu, Tf, 1));
+            Tf = fmaxf(Tf, __shfl_xor_sync(0xffffffffu, Tf, 2));
+            Tf = fmaxf(Tf, __shfl_xor_sync(0xffffffffu, Tf, 4));
+            if (FP_EPI_GROUPS > 1) S->shareT[grp][rit] = Tf;
+          }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -464,6 +486,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
             a.err_num[rng] = G < 0 ? -1 : a.ar[rng] - G;
           }
         }
+        S->shareT[grp][rit] = -1.0f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * FP_EPI_WARPS) : "memory");
       }
     }
