@@ -90,6 +90,7 @@ template <int NC>
 struct SpWarp {
   alignas(16) uint8_t cur[256];
   int dist[NPART][NC];
+  int tile[NC == 9 ? 10 : 1][16];     // uniform-vector path: SATD of tile k at candidate c (row 9: zeros for the odd lane half)
   short mv[NPART][2], prd[NPART][2];
   long long mincost[NPART];
 };
@@ -128,9 +129,61 @@ __global__ void __launch_bounds__(32 * WPC) k_subpel_refine(const SubArgs a)
       const int first = a.full81 ? 0 : (stage ? a.start_qp : a.start_hp);
       const int lam = (stage || a.full81) ? a.lambda_q : a.lambda_h;
       const int ncand = a.full81 ? 81 : 9;
+      // ---- uniform-vector path (SATD, nine candidates): when every active partition carries the SAME vector - static
+      //      and panning content, the common case - the tile a partition asks for depends on (tile, candidate) only:
+      //      144 tile SATDs, then the 41 partition sums of two candidates at a time through the 4x4 / 8x4 / 4x8 / 8x8 /
+      //      16x8 / 8x16 / 16x16 tree in shuffles (no shared atomics, no per-block-type bookkeeping) ----
+      bool fast = false;
+      __syncwarp();
+      if (NC == 9 && metric == 2 && a.part_mask != 0) {
+        const int pf = __ffsll((long long)a.part_mask) - 1;
+        const uint32_t m0 = *reinterpret_cast<const uint32_t *>(&S.mv[pf][0]);
+        bool same = true;
+        for (int p = lane; p < NPART; p += 32)
+          if ((a.part_mask >> p) & 1ull) same = same && *reinterpret_cast<const uint32_t *>(&S.mv[p][0]) == m0;
+        fast = __all_sync(0xffffffffu, same);
+        if (fast) {
+          const int mvx = (short)(m0 & 0xffffu), mvy = (short)(m0 >> 16);
+          if (lane < 16) S.tile[NC == 9 ? 9 : 0][lane] = 0;
+          for (int job = lane; job < 144; job += 32) {
+            const int k = (job * 57) >> 9, c = job - k * 9;
+            if (c < first) continue;
+            const int tx = (k & 3) * 4, ty = (k >> 2) * 4;
+            int spx, spy; sp_xy(c, &spx, &spy);
+            const int qx = 4 * (mbx * 16 + tx) + mvx + step * spx, qy = 4 * (mby * 16 + ty) + mvy + step * spy;
+            const int pl = (qy & 3) * 4 + (qx & 3);
+            const int ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX, oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY;
+            S.tile[NC == 9 ? c : 0][k] = tile_distortion(S.cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, 2);
+          }
+          __syncwarp();
+          const int k = lane & 15, tx = k & 3, ty = k >> 2;
+#pragma unroll
+          for (int pass = 0; pass < 5; pass++) {
+            const int c = 2 * pass + (lane >> 4);                  // c == 9: the zero row
+            const int v = S.tile[NC == 9 ? c : 0][k];
+            const int h84 = v + __shfl_xor_sync(0xffffffffu, v, 1);
+            const int v48 = v + __shfl_xor_sync(0xffffffffu, v, 4);
+            const int e88 = h84 + __shfl_xor_sync(0xffffffffu, h84, 4);
+            const int s168 = e88 + __shfl_xor_sync(0xffffffffu, e88, 2);
+            const int s816 = e88 + __shfl_xor_sync(0xffffffffu, e88, 8);
+            const int s1616 = s168 + __shfl_xor_sync(0xffffffffu, s168, 8);
+            if (c < 9) {
+              S.dist[25 + k][c] = v;
+              if (!(tx & 1)) S.dist[9 + ty * 2 + (tx >> 1)][c] = h84;
+              if (!(ty & 1)) S.dist[17 + (ty >> 1) * 4 + tx][c] = v48;
+              if (!(tx & 1) && !(ty & 1)) S.dist[5 + (ty >> 1) * 2 + (tx >> 1)][c] = e88;
+              if (tx == 0 && !(ty & 1)) S.dist[1 + (ty >> 1)][c] = s168;
+              if (ty == 0 && !(tx & 1)) S.dist[3 + (tx >> 1)][c] = s816;
+              if (k == 0) S.dist[0][c] = s1616;
+            }
+          }
+        }
+      }
+      if (!fast) {
       for (int i = lane; i < NPART * NC; i += 32) (&S.dist[0][0])[i] = 0;
       __syncwarp();
-      for (int job = lane; job < 16 * ncand; job += 32) {
+      }
+      for (int job = lane; job < (fast ? 0 : 16 * ncand); job += 32) {
         const int k = NC == 9 ? (job * 57) >> 9 : job / ncand, c = job - k * ncand;      // job / 9 for job < 144
         if (c < first) continue;
         const int tx = (k & 3) * 4, ty = (k >> 2) * 4;
