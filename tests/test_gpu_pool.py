@@ -54,6 +54,28 @@ def test_pool_planted_and_different_plane_sizes():
     assert list(dom) == want and (aq == 50).all()
 
 
+def test_pool_isometry_and_index_ties():
+    """Range blocks that are symmetric under flips / transposition make several isometry rows identical (equal G for
+    every domain: the lowest isometry must win although the rows share one threshold), and a domain plane made of
+    repeated tiles makes distinct pool entries identical (equal G: the lowest pool index must win, across MMA tiles
+    and epilogue groups)."""
+    rng = np.random.default_rng(9)
+    tile = rng.integers(0, 256, (16, 16), dtype=np.uint8)
+    dp = np.tile(tile, (8, 10))                                   # 128 x 160: many identical domain blocks
+    rp = np.zeros((32, 64), np.uint8)
+    for k in range(32):
+        b = rng.integers(0, 256, (8, 8)).astype(np.int64)
+        kind = k % 4
+        if kind == 0: b = b + b[:, ::-1]                          # left-right symmetric
+        elif kind == 1: b = b + b.T                               # symmetric under transposition
+        elif kind == 2: b = b + b[::-1, :] + b[:, ::-1] + b[::-1, ::-1]   # both flips (and the half turn)
+        else: b = b + b.T + b[::-1, ::-1] + b[::-1, ::-1].T       # both diagonals
+        b = (b * 255 // max(1, b.max())).astype(np.uint8)
+        rp[(k // 8) * 8:(k // 8) * 8 + 8, (k % 8) * 8:(k % 8) * 8 + 8] = b
+    _check(rp, dp, 1200)
+    _check(rp, dp, 300)
+
+
 def test_pool_error_codes():
     with pytest.raises(api.B2Error):
         api.PoolSearcher(60, 48, 64, 64, 10)          # range plane not a multiple of 8

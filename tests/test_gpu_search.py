@@ -66,6 +66,34 @@ def test_search_matches_oracle(W, H, R, NR, spread, rmax, lam):
         assert (a == b).all(), (n, int((a != b).sum()))
 
 
+@pytest.mark.parametrize("shift,rmax", [((3, -2), 2), ((-9, 6), 12), ((0, 0), 0)])
+def test_pan_clip_uniform_vectors(shift, rmax):
+    """A noiseless pan: every partition of a macroblock lands on the same vector, which is the case k_subpel_refine
+    serves by its uniform-vector path (tile SATDs summed through the block-size tree); frame borders, vectors that
+    point outside the picture (per-tile clamp) and a second reference with different content included."""
+    W, H, R, NR = 80, 64, 16, 2
+    rng = np.random.default_rng(17)
+    big = rng.integers(0, 256, (H + 64, W + 64)).astype(np.float64)
+    big = (big + np.roll(big, 1, 0) + np.roll(big, 1, 1) + np.roll(big, (1, 1), (0, 1))) / 4
+    ref0 = big[32:32 + H, 32:32 + W].astype(np.uint8)
+    cur = big[32 + shift[1]:32 + shift[1] + H, 32 + shift[0]:32 + shift[0] + W].astype(np.uint8)
+    ref1 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    refs = np.stack([ref0, ref1])
+    s = api.Searcher(W, H, NR, R)
+    s.set_cur(cur)
+    for r in range(NR):
+        s.set_ref(r, refs[r])
+    of = oracle.OrcFrame(cur, refs, R)
+    pred, cen = synth.predictors(W, H, NR, seed=2, spread=0, rmax=rmax)
+    got = s.search_frame(pred, cen, api.make_params((60, 45, 45)))
+    exp = of.search_frame(pred, cen, (60, 45, 45))
+    for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+        assert (a == b).all(), (n, int((a != b).sum()))
+    mi = got[0][:, 0]
+    if rmax <= 2:                                                   # (far random predictors leave the true vector outside many windows)
+        assert ((mi == mi[:, :1]).all(-1).all(-1)).mean() > 0.5    # the uniform path really ran
+
+
 def test_flat_and_noise_content():
     """Flat frames (all-zero SAD, ties decided by spiral order) and pure noise."""
     W, H, R = 48, 32, 7
