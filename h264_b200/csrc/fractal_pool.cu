@@ -431,6 +431,10 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
                 if (det < 0) continue;                            // padding column
                 const uint32_t vj = scr[j * 32];
                 const float sdf = fdp[ch * FP_CHUNK + j];
+                {                                                  // the row's threshold may have risen since the mask was formed
+                  const float xj = fabsf(fmaf(nfr, sdf, __uint_as_float(vj)) - 8388608.0f) + 0.5f;
+                  if ((xj * xj) * wcp[ch * FP_CHUNK + j] * 1.00001f < Tf) continue;
+                }
                 n_exact++;
                 // exact integer fit (oracle/b2_oracle_pool.c orc_pool_pair); the double quotient truncates like the
                 // exact rational: a non-integer p/q with q < 2^29 is further than 2^-53 (relative) from an integer
