@@ -30,6 +30,14 @@ __device__ __forceinline__ void sp_xy(int c, int *x, int *y)
   else spiral_xy(c, x, y);
 }
 
+// dot product of four unsigned bytes (a) with four signed bytes (b), accumulated into c
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
+{
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 __device__ __forceinline__ int hadamard4x4_abs(const int d[16])
 {
   int m[16], s = 0;
@@ -66,6 +74,31 @@ __device__ __forceinline__ int part_of_tile(int bti, int tx, int ty)
 __device__ __forceinline__ int tile_distortion(const uint8_t *cur, int tx, int ty, const uint8_t *rp, int Wp, int metric)
 {
   const int al = (int)(reinterpret_cast<size_t>(rp) & 3);      // two aligned words per row instead of four byte loads
+  if (metric == 2) {
+    // HadamardSAD4x4 without unpacking a byte: a row's four horizontal coefficients are dot products of its packed
+    // bytes with +-1 patterns (dp4a, u8 x s8, on the FMA pipe: current row with +h, reference row with -h chained into
+    // the same accumulator); the vertical 4-point transform then works on scalars, and its last butterfly never
+    // materialises: |u + v| + |u - v| = 2 max(|u|, |v|), so (sum + 1) >> 1 is the sum of max(|u|, |v|) over the pairs.
+    int R[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(rp + (size_t)r * Wp - al);
+      const uint32_t lo = w[0], hi = al ? w[1] : 0u;
+      const uint32_t px = al ? __funnelshift_r(lo, hi, 8 * al) : lo;
+      const uint32_t cw = *reinterpret_cast<const uint32_t *>(&cur[(ty + r) * 16 + tx]);
+      R[r][0] = dp4a_us(cw, 0x01010101u, dp4a_us(px, 0xFFFFFFFFu, 0));
+      R[r][1] = dp4a_us(cw, 0xFF01FF01u, dp4a_us(px, 0x01FF01FFu, 0));
+      R[r][2] = dp4a_us(cw, 0xFFFF0101u, dp4a_us(px, 0x0101FFFFu, 0));
+      R[r][3] = dp4a_us(cw, 0x01FFFF01u, dp4a_us(px, 0xFF0101FFu, 0));
+    }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int p = R[0][k] + R[1][k], q = R[0][k] - R[1][k], r = R[2][k] + R[3][k], t = R[2][k] - R[3][k];
+      s += max(abs(p), abs(r)) + max(abs(q), abs(t));
+    }
+    return s;
+  }
   int d[16];
 #pragma unroll
   for (int r = 0; r < 4; r++) {
