@@ -366,7 +366,7 @@ def main():
     import ctypes as C
     import threading
     L = s.L
-    E2E_STREAMS = 2
+    E2E_STREAMS = int(os.environ.get("B2ME_E2E_STREAMS", "3"))
 
     class Stream:
         def __init__(self, ctx):
@@ -472,7 +472,7 @@ def main():
             "mb_per_s": world * nmb / (ms_step * 1e-3),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": dtS * 1e3, "streams_per_gpu": E2E_STREAMS,
-                    "note": "independent closed-GOP segment streams per GPU, one context + host thread each; a step = one frame of one stream",
+                    "note": "independent closed-GOP segment streams per GPU, one context + host thread each; a step = one frame of one stream (wall time / frames of all streams); kernels of different streams overlap (one stream's sub-pel stage runs under another's search tail, copies under kernels), so the time per frame can fall below the single-stream resident step that `value` measures",
                     "single_stream": {"value": world * pel_sp(nmb) / dt1 / 1e6, "ms_per_step": dt1 * 1e3},
                     "result_checksum": checksum},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary}
