@@ -70,34 +70,43 @@ __device__ __forceinline__ int part_of_tile(int bti, int tx, int ty)
   }
 }
 
+// HadamardSAD4x4 (me_distortion.c:175-258) of the current tile rows cw[0..3] against the reference tile at rp, without
+// unpacking a byte: a row's four horizontal coefficients are dot products of its packed bytes with +-1 patterns (dp4a,
+// u8 x s8, on the FMA pipe: current row with +h, reference row with -h chained into the same accumulator); the vertical
+// 4-point transform then works on scalars, and its last butterfly never materialises: |u + v| + |u - v| = 2 max(|u|, |v|),
+// so (sum + 1) >> 1 is the sum of max(|u|, |v|) over the pairs.
+__device__ __forceinline__ int tile_satd(const uint32_t (&cw)[4], const uint8_t *rp, int Wp)
+{
+  const int al = (int)(reinterpret_cast<size_t>(rp) & 3);      // two aligned words per row instead of four byte loads
+  int R[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(rp + (size_t)r * Wp - al);
+    const uint32_t lo = w[0], hi = al ? w[1] : 0u;
+    const uint32_t px = al ? __funnelshift_r(lo, hi, 8 * al) : lo;
+    R[r][0] = dp4a_us(cw[r], 0x01010101u, dp4a_us(px, 0xFFFFFFFFu, 0));
+    R[r][1] = dp4a_us(cw[r], 0xFF01FF01u, dp4a_us(px, 0x01FF01FFu, 0));
+    R[r][2] = dp4a_us(cw[r], 0xFFFF0101u, dp4a_us(px, 0x0101FFFFu, 0));
+    R[r][3] = dp4a_us(cw[r], 0x01FFFF01u, dp4a_us(px, 0xFF0101FFu, 0));
+  }
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int p = R[0][k] + R[1][k], q = R[0][k] - R[1][k], r = R[2][k] + R[3][k], t = R[2][k] - R[3][k];
+    s += max(abs(p), abs(r)) + max(abs(q), abs(t));
+  }
+  return s;
+}
+
 // distortion of the 4x4 tile of the current MB at (tx, ty) against the reference tile `rp` (row pitch Wp)
 __device__ __forceinline__ int tile_distortion(const uint8_t *cur, int tx, int ty, const uint8_t *rp, int Wp, int metric)
 {
   const int al = (int)(reinterpret_cast<size_t>(rp) & 3);      // two aligned words per row instead of four byte loads
   if (metric == 2) {
-    // HadamardSAD4x4 without unpacking a byte: a row's four horizontal coefficients are dot products of its packed
-    // bytes with +-1 patterns (dp4a, u8 x s8, on the FMA pipe: current row with +h, reference row with -h chained into
-    // the same accumulator); the vertical 4-point transform then works on scalars, and its last butterfly never
-    // materialises: |u + v| + |u - v| = 2 max(|u|, |v|), so (sum + 1) >> 1 is the sum of max(|u|, |v|) over the pairs.
-    int R[4][4];
+    uint32_t cw[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const uint32_t *w = reinterpret_cast<const uint32_t *>(rp + (size_t)r * Wp - al);
-      const uint32_t lo = w[0], hi = al ? w[1] : 0u;
-      const uint32_t px = al ? __funnelshift_r(lo, hi, 8 * al) : lo;
-      const uint32_t cw = *reinterpret_cast<const uint32_t *>(&cur[(ty + r) * 16 + tx]);
-      R[r][0] = dp4a_us(cw, 0x01010101u, dp4a_us(px, 0xFFFFFFFFu, 0));
-      R[r][1] = dp4a_us(cw, 0xFF01FF01u, dp4a_us(px, 0x01FF01FFu, 0));
-      R[r][2] = dp4a_us(cw, 0xFFFF0101u, dp4a_us(px, 0x0101FFFFu, 0));
-      R[r][3] = dp4a_us(cw, 0x01FFFF01u, dp4a_us(px, 0xFF0101FFu, 0));
-    }
-    int s = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int p = R[0][k] + R[1][k], q = R[0][k] - R[1][k], r = R[2][k] + R[3][k], t = R[2][k] - R[3][k];
-      s += max(abs(p), abs(r)) + max(abs(q), abs(t));
-    }
-    return s;
+    for (int r = 0; r < 4; r++) cw[r] = *reinterpret_cast<const uint32_t *>(&cur[(ty + r) * 16 + tx]);
+    return tile_satd(cw, rp, Wp);
   }
   int d[16];
 #pragma unroll
@@ -123,7 +132,6 @@ template <int NC>
 struct SpWarp {
   alignas(16) uint8_t cur[256];
   int dist[NPART][NC];
-  int tile[NC == 9 ? 10 : 1][16];     // uniform-vector path: SATD of tile k at candidate c (row 9: zeros for the odd lane half)
   short mv[NPART][2], prd[NPART][2];
   long long mincost[NPART];
 };
@@ -176,24 +184,25 @@ __global__ void __launch_bounds__(32 * WPC) k_subpel_refine(const SubArgs a)
           if ((a.part_mask >> p) & 1ull) same = same && *reinterpret_cast<const uint32_t *>(&S.mv[p][0]) == m0;
         fast = __all_sync(0xffffffffu, same);
         if (fast) {
+          // lane = (tile k, candidate parity): the lane that computes the SATD of tile k at candidate c is the lane that
+          // needs it in the tree, so the value never leaves its register; the tile's current rows are loaded once
           const int mvx = (short)(m0 & 0xffffu), mvy = (short)(m0 >> 16);
-          if (lane < 16) S.tile[NC == 9 ? 9 : 0][lane] = 0;
-          for (int job = lane; job < 144; job += 32) {
-            const int k = (job * 57) >> 9, c = job - k * 9;
-            if (c < first) continue;
-            const int tx = (k & 3) * 4, ty = (k >> 2) * 4;
-            int spx, spy; sp_xy(c, &spx, &spy);
-            const int qx = 4 * (mbx * 16 + tx) + mvx + step * spx, qy = 4 * (mby * 16 + ty) + mvy + step * spy;
-            const int pl = (qy & 3) * 4 + (qx & 3);
-            const int ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX, oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY;
-            S.tile[NC == 9 ? c : 0][k] = tile_distortion(S.cur, tx, ty, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp, 2);
-          }
-          __syncwarp();
           const int k = lane & 15, tx = k & 3, ty = k >> 2;
+          uint32_t cw[4];
 #pragma unroll
+          for (int r = 0; r < 4; r++) cw[r] = *reinterpret_cast<const uint32_t *>(&S.cur[(4 * ty + r) * 16 + 4 * tx]);
+          const int bx = 4 * (mbx * 16 + 4 * tx) + mvx, by = 4 * (mby * 16 + 4 * ty) + mvy;
+#pragma unroll 1
           for (int pass = 0; pass < 5; pass++) {
-            const int c = 2 * pass + (lane >> 4);                  // c == 9: the zero row
-            const int v = S.tile[NC == 9 ? c : 0][k];
+            const int c = 2 * pass + (lane >> 4);                  // c == 9: no candidate (zero)
+            int v = 0;
+            if (c < 9 && c >= first) {
+              const int spx = (int)((0x22215u >> (2 * c)) & 3u) - 1, spy = (int)((0x29421u >> (2 * c)) & 3u) - 1;
+              const int qx = bx + step * spx, qy = by + step * spy;
+              const int pl = (qy & 3) * 4 + (qx & 3);
+              const int ox = iclamp(qx >> 2, -PADX, a.W + 15) + PADX, oy = iclamp(qy >> 2, -PADY, a.H + 3) + PADY;
+              v = tile_satd(cw, planes + (size_t)pl * a.plane_size + (size_t)oy * a.Wp + ox, a.Wp);
+            }
             const int h84 = v + __shfl_xor_sync(0xffffffffu, v, 1);
             const int v48 = v + __shfl_xor_sync(0xffffffffu, v, 4);
             const int e88 = h84 + __shfl_xor_sync(0xffffffffu, h84, 4);
