@@ -15,7 +15,7 @@
 // Epilogue = conservative filter + exact re-evaluation (same idea as sad_fs.cu).  K = 64 is a thin
 // contraction: one output costs the tensor pipe 64 MACs (~1/100 clk per SM) but ANY per-output work on the
 // FP32/INT pipes costs >= 1 issue slot per 32 outputs, so the epilogue, not the MMA, bounds this kernel; it
-// is therefore cut to ~2.3 instructions per output:
+// is therefore cut to ~3.5 instructions per output (118 SASS instructions per warp and 32-column chunk):
 //   * the accumulators are pre-loaded with 0x4B000000 (tcgen05.st), so an s32 result C reads back as the
 //     bit pattern of the float 2^23 + C: no I2F;
 //   * one FFMA gives g = 2^23 + (C - Sr*Sd/64) = 2^23 + num/64 (+-0.5);
@@ -23,7 +23,11 @@
 //     X = max |num|/64 of the chunk; G <= 10000*num^2/det (the unquantised optimum), so the chunk can hold a
 //     winner only if  10000*(64 X)^2 / detmin(chunk) >= best G of the row.  Domains are sorted by det so that
 //     detmin(chunk) is tight.  Only then are the 32 columns (still in registers) re-examined and the
-//     survivors evaluated exactly (int64).
+//     survivors evaluated exactly (int64): warp-across-columns when few rows of the warp passed, every lane over
+//     its own columns when many did (the start of a sweep);
+//   * only the best of a range's 8 isometries is written, so its 8 rows (consecutive lanes) share ONE threshold,
+//     which the three epilogue groups also exchange through shared memory before every chunk's test;
+//   * the ORIGINAL pool index (tie-break key) is fetched from global memory only when two fits tie.
 //
 // Layout in HBM: operands in UMMA "core matrix" order (K-major, no swizzle): a 128-row tile is
 // [16 row groups][4 k-chunks][8 rows][16 bytes] = 8 KB contiguous, so a tile is ONE cp.async.bulk and its
@@ -49,8 +53,11 @@ constexpr int FP_CT_BYTES = 3104;     // per-tile constants: float Sd[256] | int
 #ifndef FP_GROUPS_V
 #define FP_GROUPS_V 3
 #endif
-constexpr int FP_EPI_GROUPS = FP_GROUPS_V;      // epilogue warp groups (4 warps each, one per TMEM lane quarter); group g takes chunks ch % 2 == g
+constexpr int FP_EPI_GROUPS = FP_GROUPS_V;      // epilogue warp groups (4 warps each, one per TMEM lane quarter); group g takes chunks ch % groups == g
 constexpr int FP_EPI_WARPS = 4 * FP_EPI_GROUPS;
+#ifndef FP_PF_MAXG
+#define FP_PF_MAXG 2                  // largest group count that still double-buffers a chunk in registers (measured: 3 groups without beat 3 with)
+#endif
 constexpr int FP_THREADS = 128 + 32 * FP_EPI_WARPS;   // warp 0 producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4.. epilogue
 
 struct FpArgs {
@@ -280,10 +287,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
     uint32_t it = 0;
     constexpr int NCHT = FP_TN / FP_CHUNK;                     // chunks per tile; group g takes ch = g, g + groups, ...
     constexpr int NCH = (NCHT + FP_EPI_GROUPS - 1) / FP_EPI_GROUPS;
-    #ifndef FP_PF_MAXG
-#define FP_PF_MAXG 2
-#endif
-    constexpr bool PF = FP_EPI_GROUPS <= FP_PF_MAXG;                    // prefetch the next chunk's accumulators (two register buffers) only while the registers allow
+    constexpr bool PF = FP_EPI_GROUPS <= FP_PF_MAXG;           // prefetch the next chunk's accumulators into a second register buffer
     for (int i = 0; i < nmt; i++) {
       const int mt = (int)blockIdx.x + i * (int)gridDim.x;
       const int rit = q * 32 + lane;                          // row in tile
