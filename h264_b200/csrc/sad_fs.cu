@@ -25,10 +25,11 @@
 // per-partition state and filter constants.  A warp-task = 64 window columns x K rows of candidates:
 // lane l owns the column pair (dx, dx+4), dx = 8*(l>>2) + (l&3), and walks K consecutive rows
 // dy0..dy0+K-1 in lock step with a sliding window of K reference rows in registers, so a reference row
-// costs three LDS.64 per 2K candidates and a current row one broadcast LDS.128.  Warps pull tasks of
-// whichever buffer is ready from a shared counter and never meet at a CTA barrier; the warp that
-// completes the last task of a unit writes its results and sets up the buffer's next unit (parameters,
-// TMA of the window, tables, exact pre-pass) while the other warps work on the other buffer.
+// costs three LDS.64 per 2K candidates and a current row one broadcast LDS.128.  Worker warps pull tasks of
+// whichever buffer is ready from a shared counter (the claim of their NEXT tasks is issued before they run the
+// current ones) and never meet at a CTA barrier; a dedicated producer warp writes the results of a finished unit
+// and sets up the buffer's next unit (parameters, TMA of the window, tables, exact pre-pass) while the workers
+// drain the other buffer.
 //
 // Filter.  After every 4 rows the 4x4 SADs of a block row are packed two per register (IMAD on the
 // FMA pipe), tree-summed (VIADD.16x2), and folded into one running minimum per candidate:

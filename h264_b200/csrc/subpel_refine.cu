@@ -9,8 +9,10 @@
 // contains the tile; partitions with equal motion vectors ask for the same reference tile, which is
 // then computed once.  The lane loads the 4x4 reference tile from the quarter-pel plane
 // [y&3][x&3] with the reference's own tile-origin clamp (UMVLine4X, refbuf.h:22-26), forms the
-// difference against the current MB in shared memory, runs the 4x4 Hadamard in registers and
-// adds (satd+1)>>1 into each partition's candidate accumulator.  41 threads then take the lexicographic (cost, position) minimum in
+// difference against the current MB in shared memory, runs the 4x4 Hadamard in registers (tile_satd: dp4a rows) and
+// adds (satd+1)>>1 into each partition's candidate accumulator.  When every active partition of the item carries the
+// same vector (the common case) the tile depends on (tile, candidate) only: lane = (tile, candidate parity) and the
+// 41 partition sums are formed through the block-size tree in shuffles (no atomics, no block-type walk).  41 threads then take the lexicographic (cost, position) minimum in
 // spiral order with the reference's carried / reset min_mcost rules (mv_search.c:971-974,
 // me_fullsearch.c:252-253).
 #include "b2_common.cuh"
