@@ -366,7 +366,9 @@ def main():
     import ctypes as C
     import threading
     L = s.L
-    E2E_STREAMS = int(os.environ.get("B2ME_E2E_STREAMS", "3"))
+    # three streams per GPU (two leave the result sensitive to how the streams' phases lock) unless the ranks of
+    # this box would then outnumber its host cores (one synchronising host thread per stream)
+    E2E_STREAMS = int(os.environ.get("B2ME_E2E_STREAMS", "3" if (os.cpu_count() or 1) >= 3 * world + 2 else "2"))
 
     class Stream:
         def __init__(self, ctx):
