@@ -73,3 +73,58 @@ def test_planted_match_is_found():
     assert list(dom) == want
     assert all(i == (4 if k & 1 else 0) for k, i in enumerate(iso))
     assert (aq == 50).all() and (beta == 120).all()
+
+
+def _trunc_div(n, d):
+    q = abs(n) // d
+    return q if n >= 0 else -q
+
+
+def _quan_a(x):
+    c = _trunc_div(x, 10)
+    b = x - 10 * c
+    if 2 < b < 8:
+        b = 5
+    elif b > 7:
+        b, c = 0, c + 1
+    else:
+        b = 0
+    return c * 10 + b
+
+
+def test_tie_break_is_first_maximum_in_isometry_then_pool_order():
+    """Independent restatement (python integers) of the search's selection rule on inputs full of exact ties: range
+    blocks symmetric under flips / transposition (several isometries give the same G for every domain) against a domain
+    plane of repeated tiles (several pool entries give the same G): the oracle returns the first maximum in
+    (isometry, pool index) order.  The GPU path shares one threshold among a range's 8 isometry rows and fetches the
+    original pool index only on ties, so this rule is what tests/test_gpu_pool.py::test_pool_isometry_and_index_ties
+    holds it to."""
+    rng = np.random.default_rng(9)
+    tile = rng.integers(0, 256, (16, 16), dtype=np.uint8)
+    dp = np.tile(tile, (4, 5))                                      # 64 x 80
+    rp = np.zeros((16, 32), np.uint8)
+    for k in range(8):
+        b = rng.integers(0, 256, (8, 8)).astype(np.int64)
+        b = (b + b[:, ::-1], b + b.T, b + b[::-1, :] + b[:, ::-1] + b[::-1, ::-1], b + b.T + b[::-1, ::-1] + b[::-1, ::-1].T)[k % 4]
+        rp[(k // 4) * 8:(k // 4) * 8 + 8, (k % 4) * 8:(k % 4) * 8 + 8] = (b * 255 // max(1, b.max())).astype(np.uint8)
+    nd = 150
+    dom, iso, aq, beta, err = oracle.pool_search(rp, dp, nd)
+    xy = oracle.pool_positions(dp.shape[1], dp.shape[0], nd)
+    doms = [oracle.pool_domain_block(dp, *p).astype(np.int64) for p in xy]
+    assert len({d.tobytes() for d in doms}) < nd                    # the pool really holds duplicates
+    for ri in range(8):
+        blk = rp[(ri // 4) * 8:(ri // 4) * 8 + 8, (ri % 4) * 8:(ri % 4) * 8 + 8].reshape(64)
+        best = (-1, 0, -1, 0)                                       # (G, iso, dom, aq)
+        for i in range(8):
+            r = oracle.pool_iso(blk, i).astype(np.int64)
+            sr = int(r.sum())
+            for j, d in enumerate(doms):
+                sd, sd2 = int(d.sum()), int((d * d).sum())
+                num, det = 64 * int((r * d).sum()) - sr * sd, 64 * sd2 - sd * sd
+                q = _quan_a(0 if det == 0 else _trunc_div(100 * num, det))
+                if q < -235 or q > 400:
+                    continue
+                G = 200 * q * num - q * q * det
+                if G > best[0]:                                     # strict: the first maximum in (iso, index) order stays
+                    best = (G, i, j, q)
+        assert (dom[ri], iso[ri], aq[ri]) == (best[2], best[1], best[3]), (ri, dom[ri], iso[ri], aq[ri], best)
