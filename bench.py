@@ -56,6 +56,58 @@ def pel_sp(nmb):
     return nmb * NREFS * (2 * R + 1) ** 2 * 256
 
 
+def robustness_cases(seed=1):
+    """The headline frame under less friendly inputs: what full_search_motion_estimation really
+    receives.  Each case = (name, frames, pred, centre).  pan: the headline's own predictors (true pan motion, shared
+    by the 41 partitions); perpart: one predictor per PARTITION (true motion + up to +-3 quarter-pel, the spread JM's
+    median prediction shows on jm_wrap_foreman.npz) so that centres differ inside an MB; off8: predictor wrong by up
+    to +-8 pel per (MB, ref); noise: uniform random pictures (no candidate is good, every bound converges slowly)."""
+    from h264_b200 import synth
+    fr, pred, cen = workload(seed)
+    nmb = (W // 16) * (H // 16)
+    rng = np.random.default_rng(77)
+    cases = [("pan", fr, pred, cen)]
+    pp = (pred.astype(np.int64) + rng.integers(-3, 4, pred.shape)).astype(np.int16)
+    cases.append(("perpart", fr, pp, (((pp.astype(np.int32) + 2) >> 2) * 4).astype(np.int16)))
+    po = (pred.astype(np.int64) + 4 * rng.integers(-8, 9, (nmb, NREFS, 1, 2))).astype(np.int16)
+    cases.append(("off8", fr, po, (((po.astype(np.int32) + 2) >> 2) * 4).astype(np.int16)))
+    cases.append(("noise", rng.integers(0, 256, fr.shape).astype(np.uint8), pred, cen))
+    return cases
+
+
+def robustness_block(device, sad_peak_tpel, iters=3):
+    """k_sad_fs alone (integer stage, resident inputs, CUDA events) on every robustness case."""
+    import torch
+    from h264_b200 import api
+    dev = torch.device("cuda", device)
+    nmb = (W // 16) * (H // 16)
+    s = api.Searcher(W, H, NREFS, R, device=device)
+    p = api.make_params(LAMBDA, do_subpel=False)
+    mvi = torch.zeros((nmb, NREFS, 41, 2), dtype=torch.int16, device=dev); mvs = torch.zeros_like(mvi)
+    ci = torch.zeros((nmb, NREFS, 41), dtype=torch.int64, device=dev); cs = torch.zeros_like(ci)
+    out = {}
+    for name, fr, pred, cen in robustness_cases():
+        d_fr = torch.from_numpy(fr).to(dev)
+        s.set_cur_dev(d_fr[NREFS])
+        for r in range(NREFS):
+            s.set_ref_dev(r, d_fr[NREFS - 1 - r])
+        dp, dc = torch.from_numpy(pred).to(dev), torch.from_numpy(cen).to(dev)
+        s.search_frame_dev(dp, dc, p, mvi, ci, mvs, cs)
+        torch.cuda.synchronize()
+        s.search_stats(); s.kernel_timing(True)
+        for _ in range(iters):
+            s.search_frame_dev(dp, dc, p, mvi, ci, mvs, cs)
+        torch.cuda.synchronize()
+        ms, n = s.kernel_time_ms(0)
+        st = s.search_stats(); s.kernel_timing(False)
+        t = pel_sp(nmb) / (ms / n * 1e-3) / 1e12
+        out[name] = {"kernel_ms": ms / n, "frac": t / sad_peak_tpel, "survivors_per_item": st["exact_evals"] / max(st["items"], 1),
+                     "centre_groups_per_item": st["window_passes"] / max(st["items"], 1),
+                     "mv_checksum": int(mvi.to(torch.int64).sum().item()), "cost_checksum": int(ci.sum().item())}
+    s.close()
+    return out
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region.  NVML (nvidia_ml_py) is polled
     from a thread every ~2 ms (nvidia-smi -lms cannot resolve a region of tens of milliseconds)."""
