@@ -59,7 +59,7 @@ namespace b2 {
 #ifndef FS_KV
 #define FS_KV 4
 #endif
-constexpr int FS_K = FS_KV;         // candidate rows per task (lock step): 4 = rolled fs_task4, 5 = fully unrolled fs_task
+constexpr int FS_K = FS_KV;         // candidate rows per task (lock step); fs_task4 is written for 4
 #ifndef FS_PREV
 #define FS_PREV 0
 #endif
@@ -105,7 +105,8 @@ struct __align__(16) FsSlotT {    // one unit = (item, centre group): everything
   int gx0, gy0, spanx, spany;     // the group's centre box (pel)
   int wx0, wy0, inside;           // window origin in the search plane; inside: the TMA path applies
   int ncx, ncy, ngy, gc, ncbA, ntaskA, npb, ntask;
-  unsigned short ttab[96];        // type-A task t -> dy0 | column block << 8, centre rows first
+  static constexpr int NTT = PITCH == 96 ? 40 : 96;
+  unsigned short ttab[NTT];       // type-A task t -> dy0 | column block << 8, centre rows first
 };
 
 struct FsCtl {                    // per window buffer: the pipeline between the producer warp and the workers
@@ -120,7 +121,12 @@ struct FsCtl {                    // per window buffer: the pipeline between the
   int epoch, tma_uses;
 };
 
-struct FsWarp { unsigned short sat[2][28]; };
+constexpr int FS_RCAP = 24;      // survivor records per warp and task
+struct FsWarp {
+  unsigned short sat[2][28];     // fs_exact2's summed-area tables (row 0 / column 0 stay zero)
+  uint32_t rec[FS_RCAP];
+  int nrec;
+};
 
 // partition p -> index into the u16 view of Cw (word*2 + half); p == 0 -> -1 (scalar C16)
 __device__ __forceinline__ int cmap(int p)
@@ -220,114 +226,176 @@ __device__ __forceinline__ void ld3(uint32_t (&r)[6], const uint8_t *p)
   r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y;
 }
 
-// One lane-job: candidates (dx, dy0..dy0+K-1) and (dx+4, same rows); wb = lane address of window row dy0.
-// Returns the pass mask: bit j = column a row j, bit K+j = column b row j.
-template <int K, int PITCH, class SLOT>
-__device__ __forceinline__ uint32_t fs_task(const SLOT &S, const uint8_t *wb, uint32_t mxa, uint32_t mxb, const unsigned short *mys, uint32_t one)
+// ---- survivor records ---------------------------------------------------------------------------------------
+// A (candidate, partition) pair that passes the precise filter is recorded where its SAD is still in a register:
+//   word = sad (16) | partition << 16 | (q * 4 + j) << 22 | lane << 25        (q: column of the lane's pair, j: row of the task)
+// and evaluated exactly (mv cost, spiral position, 64-bit atomicMin) by the warp at the end of the task, one lane per
+// record.  A task that overflows the list falls back to the per-candidate re-evaluation (fs_exact2)
+// through its pass bits.
+__device__ __noinline__ void fs_rec(FsWarp &ws, uint32_t word)
 {
-  const uint4 *cur = reinterpret_cast<const uint4 *>(S.cur);
-  uint32_t rw[K][6];
-  uint32_t acc[2][K][4];
-  uint32_t run[2][K], X0[2][K], Y0[2][K], E0[2][K];
+  const int i = atomicAdd(&ws.nrec, 1);
+  if (i < FS_RCAP) ws.rec[i] = word;
+}
+
+__device__ __forceinline__ void fs_cold_test(FsWarp &ws, uint32_t V, uint32_t c, uint32_t mcp, int plo, int phi, uint32_t cb, uint32_t &hit)
+{
+  const uint32_t tt = V + c + mcp;                 // per half: sad - B - 1 + m (the high half up to two lower, see set_threshold)
+  if (tt & 0x80008000u) {
+    hit = 1u;
+    if (tt & 0x8000u) fs_rec(ws, (V & 0xffffu) | ((uint32_t)plo << 16) | cb);
+    if (tt & 0x80000000u) fs_rec(ws, (V >> 16) | ((uint32_t)phi << 16) | cb);
+  }
+}
+
+// Records of ONE candidate that passed the quick test of the cold path, at the end of the odd block row b: the partitions
+// inside block rows b - 1 and b (4x4, 8x4), those spanning both (4x8, 8x8) and, at b == 3, the whole-MB ones.  X0, Y0 / X, Y:
+// packed 4x4 SADs ((bx0, bx2), (bx1, bx3)) of rows b - 1 / b; E0: the two 8x8 sums of the upper half; m: the candidate's
+// mv-cost lower bound.
+template <class SLOT>
+__device__ __noinline__ void fs_cold_detail(const SLOT &S, FsWarp &ws, uint32_t X, uint32_t Y, uint32_t X0, uint32_t Y0, uint32_t E0,
+                                            int b, uint32_t m, uint32_t cb)
+{
+  uint32_t hit = 0;
+  const uint32_t mcp = m * 0x10001u;
+  const int a = b - 1, bb = b >> 1;
+  fs_cold_test(ws, X0, ld_vol(&S.Cw[3 * a]), mcp, 25 + 4 * a, 27 + 4 * a, cb, hit);
+  fs_cold_test(ws, Y0, ld_vol(&S.Cw[3 * a + 1]), mcp, 26 + 4 * a, 28 + 4 * a, cb, hit);
+  fs_cold_test(ws, X0 + Y0, ld_vol(&S.Cw[3 * a + 2]), mcp, 9 + 2 * a, 10 + 2 * a, cb, hit);
+  fs_cold_test(ws, X, ld_vol(&S.Cw[3 * b]), mcp, 25 + 4 * b, 27 + 4 * b, cb, hit);
+  fs_cold_test(ws, Y, ld_vol(&S.Cw[3 * b + 1]), mcp, 26 + 4 * b, 28 + 4 * b, cb, hit);
+  fs_cold_test(ws, X + Y, ld_vol(&S.Cw[3 * b + 2]), mcp, 9 + 2 * b, 10 + 2 * b, cb, hit);
+  const uint32_t XV = X + X0, YV = Y + Y0, E = XV + YV;
+  fs_cold_test(ws, XV, ld_vol(&S.Cw[12 + 3 * bb]), mcp, 17 + 4 * bb, 19 + 4 * bb, cb, hit);
+  fs_cold_test(ws, YV, ld_vol(&S.Cw[13 + 3 * bb]), mcp, 18 + 4 * bb, 20 + 4 * bb, cb, hit);
+  fs_cold_test(ws, E, ld_vol(&S.Cw[14 + 3 * bb]), mcp, 5 + 2 * bb, 6 + 2 * bb, cb, hit);
+  if (b == 3) {
+    const uint32_t top = (E0 & 0xffffu) + (E0 >> 16), bot = (E & 0xffffu) + (E >> 16);
+    fs_cold_test(ws, (bot << 16) | top, ld_vol(&S.Cw[18]), mcp, 1, 2, cb, hit);
+    fs_cold_test(ws, E0 + E, ld_vol(&S.Cw[19]), mcp, 3, 4, cb, hit);
+    if ((int)(top + bot) + *reinterpret_cast<const volatile int *>(&S.C16) + (int)m < 0) fs_rec(ws, (top + bot) | cb);
+  }
+}
+
+// The cold path of one lane at the end of the odd block row b: a quick packed test per candidate (the hot path's filter without
+// the minimum over the candidates), the records of those that pass.  buf[5][8]: X, Y, X0, Y0, E0 per candidate q*4+j.
+// Returns the pass bits of the candidates.
+template <class SLOT>
+__device__ __noinline__ uint32_t fs_cold_lane(const SLOT &S, FsWarp &ws, const uint32_t *buf, int b, int dxa, int dy0, uint32_t vm, uint32_t lanebits, int R)
+{
+  const int a = b - 1, bb = b >> 1;
+  const uint32_t cx0 = ld_vol(&S.Cw[3 * a]), cy0 = ld_vol(&S.Cw[3 * a + 1]), ch0 = ld_vol(&S.Cw[3 * a + 2]);
+  const uint32_t cx = ld_vol(&S.Cw[3 * b]), cy = ld_vol(&S.Cw[3 * b + 1]), ch = ld_vol(&S.Cw[3 * b + 2]);
+  const uint32_t cxv = ld_vol(&S.Cw[12 + 3 * bb]), cyv = ld_vol(&S.Cw[13 + 3 * bb]), ce = ld_vol(&S.Cw[14 + 3 * bb]);
+  const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
+  const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
   uint32_t pass = 0;
-#pragma unroll
-  for (int j = 0; j < K - 1; j++) ld3(rw[j], wb + j * PITCH);
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    ld3(rw[(i + K - 1) % K], wb + (i + K - 1) * PITCH);
-    const uint4 c = cur[i];
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-      const int sl = (i + j) % K;
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        if ((i & 3) == 0) {
-          acc[q][j][0] = sad4(c.x, rw[sl][q + 0], 0u);
-          acc[q][j][1] = sad4(c.y, rw[sl][q + 1], 0u);
-          acc[q][j][2] = sad4(c.z, rw[sl][q + 2], 0u);
-          acc[q][j][3] = sad4(c.w, rw[sl][q + 3], 0u);
-        } else {
-          acc[q][j][0] = sad4(c.x, rw[sl][q + 0], acc[q][j][0]);
-          acc[q][j][1] = sad4(c.y, rw[sl][q + 1], acc[q][j][1]);
-          acc[q][j][2] = sad4(c.z, rw[sl][q + 2], acc[q][j][2]);
-          acc[q][j][3] = sad4(c.w, rw[sl][q + 3], acc[q][j][3]);
-        }
-      }
+#pragma unroll 1
+  for (int c = 0; c < 8; c++) {
+    if (!((vm >> c) & 1u)) continue;
+    {                                                // the centres' box was evaluated exactly by the producer's pre-pass
+      const int x = dxa + 4 * (c >> 2) - R, y = dy0 + (c & 3) - R;
+      if (x >= -FS_PRE && x <= S.spanx + FS_PRE && y >= -FS_PRE && y <= S.spany + FS_PRE) continue;
     }
-    if ((i & 3) == 3) {
-      const int b = i >> 2;
-      const uint32_t cx = ld_vol(&S.Cw[3 * b]), cy = ld_vol(&S.Cw[3 * b + 1]), ch = ld_vol(&S.Cw[3 * b + 2]);
-      uint32_t cxv = 0, cyv = 0, ce = 0, ctb = 0, clr = 0; int c16 = 0;
-      if (b & 1) { cxv = ld_vol(&S.Cw[12 + 3 * (b >> 1)]); cyv = ld_vol(&S.Cw[13 + 3 * (b >> 1)]); ce = ld_vol(&S.Cw[14 + 3 * (b >> 1)]); }
-      if (b == 3) { ctb = ld_vol(&S.Cw[18]); clr = ld_vol(&S.Cw[19]); c16 = *reinterpret_cast<const volatile int *>(&S.C16); }
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const uint32_t X = acc[q][j][2] * 65536u + acc[q][j][0];
-          const uint32_t Y = acc[q][j][3] * 65536u + acc[q][j][1];
-          const uint32_t H = add2(X, Y);
-          uint32_t r = (b == 0) ? 0x7fff7fffu : run[q][j];
-          r = addmin2(X, cx, r, one);
-          r = addmin2(Y, cy, r, one);
-          r = addmin2(H, ch, r, one);
-          if (b & 1) {
-            const uint32_t XV = add2(X, X0[q][j]), YV = add2(Y, Y0[q][j]);
-            const uint32_t E = add2(XV, YV);
-            r = addmin2(XV, cxv, r, one);
-            r = addmin2(YV, cyv, r, one);
-            r = addmin2(E, ce, r, one);
-            if (b == 1) E0[q][j] = E;
-            else {
-              const uint32_t top = __dp2a_lo(E0[q][j], 0x0101u, 0u), bot = __dp2a_lo(E, 0x0101u, 0u);
-              const uint32_t TB = bot * 65536u + top, LR = add2(E0[q][j], E);
-              r = addmin2(TB, ctb, r, one);
-              r = addmin2(LR, clr, r, one);
-              const uint32_t m = (q ? mxb : mxa) + mys[j];
-              const int s = (int)(top + bot) + c16 + (int)m;
-              const uint32_t t = r + m * 0x10001u;
-              if ((t & 0x80008000u) != 0u || s < 0) pass |= 1u << (q * K + j);
-            }
-          } else { X0[q][j] = X; Y0[q][j] = Y; }
-          run[q][j] = r;
-        }
-      }
+    const uint32_t m = (uint32_t)S.mxs[dxa + 4 * (c >> 2)] + (uint32_t)S.mys[dy0 + (c & 3)];
+    const uint32_t X = buf[c], Y = buf[8 + c], X0 = buf[16 + c], Y0 = buf[24 + c], E0 = buf[32 + c];
+    const uint32_t XV = X + X0, YV = Y + Y0, E = XV + YV;
+    uint32_t t = __vimin3_s16x2(X0 + cx0, Y0 + cy0, X0 + Y0 + ch0);
+    t = __vimin3_s16x2(t, X + cx, Y + cy);
+    t = __vimin3_s16x2(t, X + Y + ch, XV + cxv);
+    t = __vimin3_s16x2(t, YV + cyv, E + ce);
+    int s16 = 0;
+    if (b == 3) {
+      const uint32_t top = (E0 & 0xffffu) + (E0 >> 16), bot = (E & 0xffffu) + (E >> 16);
+      t = __vimin3_s16x2(t, ((bot << 16) | top) + ctb, E0 + E + clr);
+      s16 = (int)(top + bot) + c16 + (int)m;
+    }
+    if ((((t + m * 0x10001u) & 0x80008000u) != 0u) || s16 < 0) {
+      fs_cold_detail(S, ws, X, Y, X0, Y0, E0, b, m, lanebits | ((uint32_t)c << 22));
+      pass |= 1u << c;
     }
   }
   return pass;
 }
 
-// K = 4 variant of fs_task with the two 8-row halves of the macroblock as a rolled loop: the register window
-// slot of reference row i+j is (i+j)&3, independent of the half, so the loop body (8 rows) is the same code
-// for both halves and the task body shrinks from ~21 KB to ~8 KB of SASS (instruction-cache pressure: 12
-// desynchronised warps per SM stream through this body).
+__device__ __forceinline__ uint32_t min2s(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// per-halfword minimum of the lane's eight candidates (3 VIMNMX3 + 1 VIMNMX)
+__device__ __forceinline__ uint32_t gmin8(const uint32_t (&v)[2][4])
+{
+  const uint32_t a = __vimin3_s16x2(v[0][0], v[0][1], v[0][2]);
+  const uint32_t b = __vimin3_s16x2(v[0][3], v[1][0], v[1][1]);
+  const uint32_t c = __vimin3_s16x2(v[1][2], v[1][3], a);
+  return min2s(b, c);
+}
+
+// The lane's packed sums go to the cold path through local memory: one rolled copy of the per-candidate test, and a small
+// call site (the spill is a handful of STL.128).
+template <class SLOT>
+__device__ __forceinline__ uint32_t fs_cold_spill(const SLOT &S, FsWarp &ws, const uint32_t (&X)[2][4], const uint32_t (&Y)[2][4], const uint32_t (&X0)[2][4],
+                                                  const uint32_t (&Y0)[2][4], const uint32_t (&E0)[2][4], int b, int dxa, int dy0, uint32_t vm, uint32_t lanebits, int R)
+{
+  uint32_t buf[5][8];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      buf[0][q * 4 + j] = X[q][j]; buf[1][q * 4 + j] = Y[q][j];
+      buf[2][q * 4 + j] = X0[q][j]; buf[3][q * 4 + j] = Y0[q][j]; buf[4][q * 4 + j] = E0[q][j];
+    }
+  }
+  return fs_cold_lane(S, ws, &buf[0][0], b, dxa, dy0, vm, lanebits, R);
+}
+
+// One lane-job: candidates (dxa, dy0..dy0+3) and (dxa+4, same rows); wb = lane address of window row dy0.  The two 8-row
+// halves of the macroblock run as a rolled loop (the register window slot of reference row i+j is (i+j)&3 in both halves, so
+// the body is the same code: ~8 KB of SASS instead of ~21 KB; 12 desynchronised warps per SM stream through it).
+//
+// Filter (round 2).  The 41 partition sums of a candidate are still formed per candidate (packed tree sums), but they are no
+// longer tested per candidate: each packed sum is first reduced to its MINIMUM over the lane's eight candidates (7 two-input
+// minima per 8 candidates instead of 8 add + 8 min), and only that minimum meets the threshold  min_c sad_p(c) - B_p - 1 +
+// min_c m(c) < 0  -- a necessary condition for any of the eight to beat partition p's best.  Four warp votes per task (one per
+// block row) decide whether a lane passed; only then do the passing lanes test their candidates one by one (fs_cold_cand)
+// and record the (candidate, partition, SAD) triples that pass.  Returns the pass bits of the lane's candidates (bit q*4+j),
+// used only when the record list overflows.
 template <int PITCH, class SLOT>
-__device__ __forceinline__ uint32_t fs_task4(const SLOT &S, const uint8_t *wb, uint32_t mxa, uint32_t mxb, const unsigned short *mys, uint32_t one)
+__device__ __forceinline__ uint32_t fs_task4(const SLOT &S, FsWarp &ws, const uint8_t *wb, int dxa, int dy0, uint32_t vm, uint32_t mmin, uint32_t one, int R, int &ncold)
 {
   constexpr int K = 4;
   const uint4 *cur = reinterpret_cast<const uint4 *>(S.cur);
+  const uint32_t lanebits = (uint32_t)(threadIdx.x & 31) << 25;
+  const uint32_t mm2 = mmin * 0x10001u;
   uint32_t rw[K][6];
   uint32_t acc[2][K][4];
-  uint32_t run[2][K], X0[2][K], Y0[2][K], E0[2][K];
-  uint32_t pass = 0;
+  uint32_t X[2][K], Y[2][K], T[2][K], X0[2][K], Y0[2][K], E0[2][K];
+  uint32_t pass = 0, rr_even = 0x7fff7fffu, rr = 0x7fff7fffu;
 #pragma unroll
-  for (int j = 0; j < K; j++) { run[0][j] = run[1][j] = 0x7fff7fffu; E0[0][j] = E0[1][j] = 0; }
+  for (int j = 0; j < K; j++) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) { E0[q][j] = 0; X0[q][j] = 0; Y0[q][j] = 0; X[q][j] = 0; Y[q][j] = 0; T[q][j] = 0; }
+  }
 #pragma unroll
   for (int j = 0; j < K - 1; j++) ld3(rw[j], wb + j * PITCH);
+  // One block row (4 pixel rows) per iteration: the body (~5 KB of SASS) stays in the scheduler's L0 instruction cache (~6 KB)
+  // for the four iterations of a task; the 12 workers and 3 producer warps of an SM share a 32 KB L1.5 that the kernel's whole
+  // working set does not fit (measured: stall_no_instruction was 25 % of all samples with the 8-row body).
 #pragma unroll 1
-  for (int bb = 0; bb < 2; bb++) {
-    const uint8_t *wr = wb + bb * 8 * PITCH;
-    const uint32_t *Cb = S.Cw + 6 * bb;
+  for (int b = 0; b < 4; b++) {
+    const uint8_t *wr = wb + b * 4 * PITCH;
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < 4; r++) {
       ld3(rw[(r + K - 1) & 3], wr + (r + K - 1) * PITCH);
-      const uint4 c = cur[bb * 8 + r];
+      const uint4 c = cur[b * 4 + r];
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const int sl = (r + j) & 3;
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-          if ((r & 3) == 0) {
+          if (r == 0) {
             acc[q][j][0] = sad4(c.x, rw[sl][q + 0], 0u);
             acc[q][j][1] = sad4(c.y, rw[sl][q + 1], 0u);
             acc[q][j][2] = sad4(c.z, rw[sl][q + 2], 0u);
@@ -340,65 +408,142 @@ __device__ __forceinline__ uint32_t fs_task4(const SLOT &S, const uint8_t *wb, u
           }
         }
       }
-      if ((r & 3) == 3) {
-        const int odd = r >> 2;                       // block row b = 2*bb + odd
-        const uint32_t cx = ld_vol(&Cb[3 * odd]), cy = ld_vol(&Cb[3 * odd + 1]), ch = ld_vol(&Cb[3 * odd + 2]);
-        uint32_t cxv = 0, cyv = 0, ce = 0, ctb = 0, clr = 0, myj[K]; int c16 = 0;
-        if (odd) { cxv = ld_vol(&S.Cw[12 + 3 * bb]); cyv = ld_vol(&S.Cw[13 + 3 * bb]); ce = ld_vol(&S.Cw[14 + 3 * bb]); }
-        if (odd && bb) {                              // loaded once per task, not once per candidate (the loads are volatile)
-          ctb = ld_vol(&S.Cw[18]); clr = ld_vol(&S.Cw[19]); c16 = *reinterpret_cast<const volatile int *>(&S.C16);
+    }
+    const bool odd = b & 1;
+    if (b == 2) {                                     // T still holds the upper half's 8x8 sums: keep them for the whole-MB partitions
 #pragma unroll
-          for (int j = 0; j < K; j++) myj[j] = mys[j];
-        }
+      for (int j = 0; j < K; j++) { E0[0][j] = T[0][j]; E0[1][j] = T[1][j]; }
+    }
+    if (odd) {                                        // X, Y still hold the previous (even) block row's packed sums
 #pragma unroll
-        for (int j = 0; j < K; j++) {
+      for (int j = 0; j < K; j++) { X0[0][j] = X[0][j]; X0[1][j] = X[1][j]; Y0[0][j] = Y[0][j]; Y0[1][j] = Y[1][j]; }
+    }
+    const uint32_t cx = ld_vol(&S.Cw[3 * b]), cy = ld_vol(&S.Cw[3 * b + 1]), ch = ld_vol(&S.Cw[3 * b + 2]);
 #pragma unroll
-          for (int q = 0; q < 2; q++) {
-            const uint32_t X = acc[q][j][2] * 65536u + acc[q][j][0];
-            const uint32_t Y = acc[q][j][3] * 65536u + acc[q][j][1];
-            const uint32_t H = add2(X, Y);
-            uint32_t rr = run[q][j];
-            rr = addmin2(X, cx, rr, one);
-            rr = addmin2(Y, cy, rr, one);
-            rr = addmin2(H, ch, rr, one);
-            if (odd) {
-              const uint32_t XV = add2(X, X0[q][j]), YV = add2(Y, Y0[q][j]);
-              const uint32_t E = add2(XV, YV);
-              rr = addmin2(XV, cxv, rr, one);
-              rr = addmin2(YV, cyv, rr, one);
-              rr = addmin2(E, ce, rr, one);
-              X0[q][j] = E;                           // the half's 8x8 sums (X0 is dead from here on)
-            } else { X0[q][j] = X; Y0[q][j] = Y; }
-            run[q][j] = rr;
-          }
-        }
-        if (odd) {
-          if (bb == 0) {
+    for (int j = 0; j < K; j++) {
 #pragma unroll
-            for (int j = 0; j < K; j++) { E0[0][j] = X0[0][j]; E0[1][j] = X0[1][j]; }
-          } else {                                    // whole-MB partitions and the verdict: one uniform branch per task
+      for (int q = 0; q < 2; q++) {
+        X[q][j] = acc[q][j][2] * 65536u + acc[q][j][0];
+        Y[q][j] = acc[q][j][3] * 65536u + acc[q][j][1];
+        T[q][j] = add2(X[q][j], Y[q][j]);
+      }
+    }
+    rr = __vimin3_s16x2(gmin8(X) * one + cx, gmin8(Y) * one + cy, gmin8(T) * one + ch);
+    if (!odd) { rr_even = rr; continue; }             // tested with the next block row: one vote per 8 rows
+    {
+      const int bb = b >> 1;
+      const uint32_t cxv = ld_vol(&S.Cw[12 + 3 * bb]), cyv = ld_vol(&S.Cw[13 + 3 * bb]), ce = ld_vol(&S.Cw[14 + 3 * bb]);
+      uint32_t XV[2][K], YV[2][K];
 #pragma unroll
-            for (int j = 0; j < K; j++) {
+      for (int j = 0; j < K; j++) {
 #pragma unroll
-              for (int q = 0; q < 2; q++) {
-                const uint32_t E = X0[q][j];
-                const uint32_t top = __dp2a_lo(E0[q][j], 0x0101u, 0u), bot = __dp2a_lo(E, 0x0101u, 0u);
-                const uint32_t TB = bot * 65536u + top, LR = add2(E0[q][j], E);
-                uint32_t rr = run[q][j];
-                rr = addmin2(TB, ctb, rr, one);
-                rr = addmin2(LR, clr, rr, one);
-                const uint32_t m = (q ? mxb : mxa) + myj[j];
-                const int s = (int)(top + bot) + c16 + (int)m;
-                const uint32_t t = rr + m * 0x10001u;
-                if ((t & 0x80008000u) != 0u || s < 0) pass |= 1u << (q * K + j);
-              }
-            }
-          }
+        for (int q = 0; q < 2; q++) {
+          XV[q][j] = add2(X[q][j], X0[q][j]);
+          YV[q][j] = add2(Y[q][j], Y0[q][j]);
+          T[q][j] = add2(XV[q][j], YV[q][j]);         // the half's two 8x8 sums
         }
       }
+      rr = __vimin3_s16x2(rr, rr_even, __vimin3_s16x2(gmin8(XV) * one + cxv, gmin8(YV) * one + cyv, gmin8(T) * one + ce));
+    }
+    if (b == 3) break;                                // the lower half is voted on together with the whole-MB partitions below
+    const bool lp = vm != 0u && (((rr + mm2) & 0x80008000u) != 0u);
+    if (__any_sync(0xffffffffu, lp)) {                // cold: a candidate of some lane may beat a partition's best
+#ifdef FS_PROFILE
+      ncold++;
+#endif
+      if (lp) pass |= fs_cold_spill(S, ws, X, Y, X0, Y0, E0, 1, dxa, dy0, vm, lanebits, R);
+      __syncwarp();
+    }
+  }
+  {                                                   // whole-MB partitions, vote of the lower half
+    const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
+    const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
+    uint32_t TB[2][K], LR[2][K];
+    int smin = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const uint32_t top = __dp2a_lo(E0[q][j], 0x0101u, 0u), bot = __dp2a_lo(T[q][j], 0x0101u, 0u);
+        TB[q][j] = bot * 65536u + top;
+        LR[q][j] = add2(E0[q][j], T[q][j]);
+        smin = min(smin, (int)(top + bot));
+      }
+    }
+    rr = __vimin3_s16x2(rr, gmin8(TB) * one + ctb, gmin8(LR) * one + clr);
+    const int s16 = smin + c16 + (int)mmin;
+    const bool lp = vm != 0u && ((((rr + mm2) & 0x80008000u) != 0u) || s16 < 0);
+    if (__any_sync(0xffffffffu, lp)) {
+#ifdef FS_PROFILE
+      ncold++;
+#endif
+      if (lp) pass |= fs_cold_spill(S, ws, X, Y, X0, Y0, E0, 3, dxa, dy0, vm, lanebits, R);
+      __syncwarp();
     }
   }
   return pass;
+}
+
+// Exact evaluation of the task's survivor records, one lane per record: mv cost with the partition's own predictor, spiral
+// position, strict (cost, position) order through a 64-bit atomicMin (me_fullsearch.c:83-93), new filter constant.
+template <class SLOT>
+__device__ __noinline__ void fs_process_records(SLOT &S, FsWarp &ws, int n, int t, int R, int g, int lambda_f)
+{
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t w = ws.rec[i];
+    const int sad = w & 0xffff, p = (w >> 16) & 63, qj = (w >> 22) & 7, l = w >> 25;
+    int dxa, dy0;
+    if (t < S.ntaskA) { const int e = S.ttab[t]; dxa = 64 * (e >> 8) + 8 * (l >> 2) + (l & 3); dy0 = e & 255; }
+    else { const int job = (t - S.ntaskA) * 32 + l; const int ii = job / S.ngy, gy = job - ii * S.ngy; dxa = 64 * S.ncbA + 8 * (ii >> 2) + (ii & 3); dy0 = gy * FS_K; }
+    const int dx = dxa + 4 * (qj >> 2), dy = dy0 + (qj & 3);
+    if (S.pgrp[p] != g) continue;
+    const int ox = dx - R - S.pex[p], oy = dy - R - S.pey[p];   // displacement from the partition's own centre
+    if (max(abs(ox), abs(oy)) > S.psr[p]) continue;
+    const int mvx = S.pcx[p] + 4 * ox, mvy = S.pcy[p] + 4 * oy;
+    const long long cost = ((long long)sad << 5) + (long long)lambda_f * (mvbits(mvx - S.ppx[p]) + mvbits(mvy - S.ppy[p]));
+    const unsigned long long bestv = *reinterpret_cast<volatile unsigned long long *>(&S.best[p]);
+    if ((unsigned long long)cost > (bestv >> 20)) continue;
+    const unsigned long long key = ((unsigned long long)cost << 20) | (unsigned)spiral_index(ox, oy);
+    if (key < bestv) {
+      const unsigned long long old = atomicMin(&S.best[p], key);
+      set_threshold(S, p, old < key ? old : key);
+    }
+  }
+}
+
+// Survivors of a task (out of line: rare).  Records: exact evaluation from the recorded SADs; a list that overflowed: per-candidate
+// re-evaluation (fs_exact2) of the candidates whose pass bit is set.  Returns the number of exact evaluations (lane 0).
+template <int PITCH, class SLOT>
+__device__ __noinline__ int fs_survivors(SLOT &S, FsWarp &ws, const uint8_t *win, int copy_bytes, const uint32_t *pgt, uint32_t pass,
+                                         int dxa, int dy0, int t, int R, int g, int lambda_f)
+{
+  constexpr int K = FS_K;
+  const int lane = threadIdx.x & 31;
+  const int nrec = *reinterpret_cast<volatile int *>(&ws.nrec);
+  int nh = 0;
+  if (nrec <= FS_RCAP) {
+    fs_process_records(S, ws, nrec, t, R, g, lambda_f);
+    nh = lane == 0 ? nrec : 0;
+  } else {
+    for (int bb = 0; bb < 2 * K; bb++) {
+      uint32_t m = __ballot_sync(0xffffffffu, (pass >> bb) & 1u);
+      while (m) {
+        const int l0 = __ffs(m) - 1; m &= m - 1;
+        const bool v1 = m != 0;
+        const int l1 = v1 ? __ffs(m) - 1 : l0; m &= m - 1;
+        const int ddx = bb >= K ? 4 : 0, ddy = bb >= K ? bb - K : bb;
+        const int ex0_ = __shfl_sync(0xffffffffu, dxa, l0) + ddx, ey0 = __shfl_sync(0xffffffffu, dy0, l0) + ddy;
+        const int ex1_ = __shfl_sync(0xffffffffu, dxa, l1) + ddx, ey1 = __shfl_sync(0xffffffffu, dy0, l1) + ddy;
+        fs_exact2<PITCH>(S, ws, win, copy_bytes, pgt, ex0_, ey0, ex1_, ey1, v1, R, g, lambda_f);
+        if (lane == 0) nh += v1 ? 2 : 1;
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) *reinterpret_cast<volatile int *>(&ws.nrec) = 0;
+  __syncwarp();
+  return nh;
 }
 
 // ---- mbarrier / TMA (PTX) ------------------------------------------------------------------
@@ -522,7 +667,7 @@ __device__ __forceinline__ void fs_setup_group(SLOT &S, int g, const FsArgs &a)
   }
   {                                                // type-A tasks: row groups from the centre outwards, per column block
     const int gc = min(ngy - 1, (R + (spany >> 1)) / K), lo = gc, hi = ngy - 1 - gc, mn = min(lo, hi);
-    for (int t = lane; t < ncbA * ngy && t < 96; t += 32) {
+    for (int t = lane; t < ncbA * ngy && t < SLOT::NTT; t += 32) {
       const int cb = t / ngy, k = t - cb * ngy;
       const int gy = k <= 2 * mn ? ((k & 1) ? gc + ((k + 1) >> 1) : gc - (k >> 1)) : (lo > hi ? gc - (k - hi) : gc + (k - lo));
       S.ttab[t] = (unsigned short)((gy * K) | (cb << 8));
@@ -705,7 +850,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
     const PartGeom gm = part_geom(tid);
     pgt[tid] = (gm.ox >> 2) | ((gm.oy >> 2) << 4) | (((gm.ox + gm.w) >> 2) << 8) | (((gm.oy + gm.h) >> 2) << 12);
   }
-  for (int i = tid; i < (NWORK + 1) * 2 * 28; i += NT) (&WS[0].sat[0][0])[i] = 0;
+  for (int i = tid; i < (int)((NWORK + 1) * sizeof(FsWarp) / 4); i += NT) reinterpret_cast<uint32_t *>(&WS[0])[i] = 0;
   if (tid == 0) { st.err = 0; st.nhits = 0; st.ngroups = 0; st.nitems = 0; for (int i = 0; i < 9; i++) st.cyc[i] = 0; }
   if (tid < 2) {
     FsCtl &C = CB[tid];
@@ -771,7 +916,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
   } else {
   // ---- worker warps.  They drain ONE buffer at a time (pref) and move to the other only when pref has no task
   //      left to claim, so the two units finish staggered and the producer's work overlaps the other buffer ----
-  int ex0 = 0, ex1 = 0, nh = 0, pref = 0;
+  int ex0 = 0, ex1 = 0, nh = 0, pref = 0, ncold = 0;
   long long c_task = 0, c_exact = 0;
   const long long t_begin = clock64();
   unsigned long long g_begin; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_begin));
@@ -832,31 +977,21 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         const uint8_t *wb = win + cc * G.copy_bytes + (dy0 + cc) * PITCH + (dxa >> 2) * 4;
         const long long tt0 = FS_CLOCK();
         c_dec += tt0 - td0;
-        uint32_t pass = 0;
-#pragma unroll 1
-        for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
-          pass |= K == 4 ? fs_task4<PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one)
-                         : fs_task<5, PITCH>(S, wb, S.mxs[dxa], S.mxs[dxa + 4], S.mys + dy0, (uint32_t)a.one);
         uint32_t vm = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) if (dy0 + j < S.ncy) vm |= (va ? 1u << j : 0u) | (vb ? 1u << (K + j) : 0u);
-        pass &= vm;
+        // lower bound of the mv cost over the lane's eight candidates (columns dxa, dxa+4; rows dy0..dy0+3)
+        const uint32_t mmin = min((uint32_t)S.mxs[dxa], (uint32_t)S.mxs[dxa + 4]) +
+                              min(min((uint32_t)S.mys[dy0], (uint32_t)S.mys[dy0 + 1]), min((uint32_t)S.mys[dy0 + 2], (uint32_t)S.mys[dy0 + 3]));
+        uint32_t pass = 0;
+#pragma unroll 1
+        for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
+          pass |= fs_task4<PITCH>(S, WS[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, R, ncold);
         const long long tt1 = FS_CLOCK();
         c_task += tt1 - tt0;
-        if (__any_sync(0xffffffffu, pass != 0)) {
-          for (int bb = 0; bb < 2 * K; bb++) {
-            uint32_t m = __ballot_sync(0xffffffffu, (pass >> bb) & 1u);
-            while (m) {
-              const int l0 = __ffs(m) - 1; m &= m - 1;
-              const bool v1 = m != 0;
-              const int l1 = v1 ? __ffs(m) - 1 : l0; m &= m - 1;
-              const int ddx = bb >= K ? 4 : 0, ddy = bb >= K ? bb - K : bb;
-              const int ex0_ = __shfl_sync(0xffffffffu, dxa, l0) + ddx, ey0 = __shfl_sync(0xffffffffu, dy0, l0) + ddy;
-              const int ex1_ = __shfl_sync(0xffffffffu, dxa, l1) + ddx, ey1 = __shfl_sync(0xffffffffu, dy0, l1) + ddy;
-              fs_exact2<PITCH>(S, WS[warp], win, G.copy_bytes, pgt, ex0_, ey0, ex1_, ey1, v1, R, g, a.lambda_f);
-              nh += v1 ? 2 : 1;
-            }
-          }
+        __syncwarp();
+        if (*reinterpret_cast<volatile int *>(&WS[warp].nrec)) {        // survivors (rare): out of line
+          nh += fs_survivors<PITCH>(S, WS[warp], win, G.copy_bytes, pgt, pass, dxa, dy0, t, R, g, a.lambda_f);
           c_exact += FS_CLOCK() - tt1;
         }
       }
@@ -884,7 +1019,9 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
     if (nend == 2) break;
     if (!any) { __nanosleep(200); c_idle += FS_CLOCK() - ti0; }
   }
+  nh = __reduce_add_sync(0xffffffffu, nh);
   if (lane == 0 && nh) atomicAdd(&st.nhits, nh);
+  if (lane == 0 && ncold && a.stats) atomicAdd(&a.stats[14], (unsigned long long)ncold);
   if (lane == 0) { atomicAdd(&st.cyc[3], (unsigned long long)c_idle); atomicAdd(&st.cyc[6], (unsigned long long)c_claim); atomicAdd(&st.cyc[7], (unsigned long long)c_dec); atomicAdd(&st.cyc[8], (unsigned long long)c_post); }
   if (lane == 0) {
     atomicAdd(&st.cyc[0], (unsigned long long)c_task); atomicAdd(&st.cyc[1], (unsigned long long)c_exact);
