@@ -121,11 +121,12 @@ struct FsCtl {                    // per window buffer: the pipeline between the
   int epoch, tma_uses;
 };
 
+constexpr int FS_DENSE = 6;      // lanes of a warp in the cold path at once from which the dense collapse runs first
 constexpr int FS_RCAP = 24;      // survivor records per warp and task
 struct FsWarp {
   unsigned short sat[2][28];     // fs_exact2's summed-area tables (row 0 / column 0 stay zero)
   uint32_t rec[FS_RCAP];
-  int nrec;
+  int nrec;                      // records appended since the last flush (may exceed FS_RCAP: overflow)
 };
 
 // partition p -> index into the u16 view of Cw (word*2 + half); p == 0 -> -1 (scalar C16)
@@ -248,6 +249,133 @@ __device__ __forceinline__ void fs_cold_test(FsWarp &ws, uint32_t V, uint32_t c,
   }
 }
 
+// Exact evaluation of the task's survivor records, one lane per record: mv cost with the partition's own predictor, spiral
+// position, strict (cost, position) order through a 64-bit atomicMin (me_fullsearch.c:83-93), new filter constant.
+template <class SLOT>
+__device__ __noinline__ void fs_process_records(SLOT &S, FsWarp &ws, int n, int t, int R, int g, int lambda_f, int first, int stride)
+{
+  for (int i = first; i < n; i += stride) {
+    const uint32_t w = ws.rec[i];
+    const int sad = w & 0xffff, p = (w >> 16) & 63, qj = (w >> 22) & 7, l = w >> 25;
+    int dxa, dy0;
+    if (t < S.ntaskA) { const int e = S.ttab[t]; dxa = 64 * (e >> 8) + 8 * (l >> 2) + (l & 3); dy0 = e & 255; }
+    else { const int job = (t - S.ntaskA) * 32 + l; const int ii = job / S.ngy, gy = job - ii * S.ngy; dxa = 64 * S.ncbA + 8 * (ii >> 2) + (ii & 3); dy0 = gy * FS_K; }
+    const int dx = dxa + 4 * (qj >> 2), dy = dy0 + (qj & 3);
+    if (S.pgrp[p] != g) continue;
+    const int ox = dx - R - S.pex[p], oy = dy - R - S.pey[p];   // displacement from the partition's own centre
+    if (max(abs(ox), abs(oy)) > S.psr[p]) continue;
+    const int mvx = S.pcx[p] + 4 * ox, mvy = S.pcy[p] + 4 * oy;
+    const long long cost = ((long long)sad << 5) + (long long)lambda_f * (mvbits(mvx - S.ppx[p]) + mvbits(mvy - S.ppy[p]));
+    const unsigned long long bestv = *reinterpret_cast<volatile unsigned long long *>(&S.best[p]);
+    if ((unsigned long long)cost > (bestv >> 20)) continue;
+    const unsigned long long key = ((unsigned long long)cost << 20) | (unsigned)spiral_index(ox, oy);
+    if (key < bestv) {
+      const unsigned long long old = atomicMin(&S.best[p], key);
+      set_threshold(S, p, old < key ? old : key);
+    }
+  }
+}
+
+struct FsTaskCtx { int t, R, g, lambda_f; };
+
+__device__ __forceinline__ uint32_t minu2(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+// Dense cold path (many lanes of the warp passed at once: the bounds are still loose, e.g. the first tasks of an item whose
+// predictor is wrong).  Instead of recording every passing (candidate, partition) pair -- hundreds -- the passing lanes find,
+// per partition of this level, the ONE candidate of the task with the smallest SAD + mv-cost bound (a minimum per lane that
+// carries the candidate's index, a warp min-reduction per partition), record it and evaluate those <= 23 records exactly at once.  The bounds drop to about
+// their final values for this task's candidates, and the ordinary per-candidate test that follows finds few survivors.
+// Called by the lanes of `mask` (converged); vmm: the lane's candidates that are valid and outside the pre-pass box.
+template <class SLOT>
+__device__ __noinline__ void fs_dense_collapse(SLOT &S, FsWarp &ws, const uint32_t *buf, int b, int dxa, int dy0, uint32_t vmm, uint32_t lanebits,
+                                               FsTaskCtx tc, uint32_t mask)
+{
+  const int lane = threadIdx.x & 31;
+  const int nk = b == 3 ? 11 : 9;
+  uint32_t M[11]; uint32_t M16 = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < 11; k++) M[k] = 0xffffffffu;
+  // flush what earlier cold entries of this task recorded (keeps the list below its capacity)
+  __syncwarp(mask);
+  {
+    const int n0 = *reinterpret_cast<volatile int *>(&ws.nrec);
+    if (n0 > 0 && n0 <= FS_RCAP) {
+      fs_process_records(S, ws, n0, tc.t, tc.R, tc.g, tc.lambda_f, __popc(mask & ((1u << lane) - 1u)), __popc(mask));
+      __syncwarp(mask);
+      if ((mask & ((1u << lane) - 1u)) == 0u) *reinterpret_cast<volatile int *>(&ws.nrec) = 0;
+      __syncwarp(mask);
+    }
+  }
+  // per lane: minimum over its candidates of ((SAD + mv-cost bound) << 3 | candidate) for every partition of this level
+  uint32_t Mh[11];
+#pragma unroll
+  for (int k = 0; k < 11; k++) Mh[k] = 0xffffffffu;
+#pragma unroll 1
+  for (int c = 0; c < 8; c++) {
+    if (!((vmm >> c) & 1u)) continue;
+    const uint32_t m = (uint32_t)S.mxs[dxa + 4 * (c >> 2)] + (uint32_t)S.mys[dy0 + (c & 3)];
+    const uint32_t X = buf[c], Y = buf[8 + c], X0 = buf[16 + c], Y0 = buf[24 + c], E0 = buf[32 + c];
+    uint32_t Q[11];
+    Q[0] = X0; Q[1] = Y0; Q[2] = X0 + Y0; Q[3] = X; Q[4] = Y; Q[5] = X + Y; Q[6] = X + X0; Q[7] = Y + Y0; Q[8] = Q[6] + Q[7];
+    const uint32_t top = (E0 & 0xffffu) + (E0 >> 16), bot = (Q[8] & 0xffffu) + (Q[8] >> 16);
+    Q[9] = (bot << 16) | top; Q[10] = E0 + Q[8];
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+      if (k < nk) {
+        M[k] = min(M[k], ((((Q[k] & 0xffffu) + m) << 3) | (uint32_t)c));
+        Mh[k] = min(Mh[k], ((((Q[k] >> 16) + m) << 3) | (uint32_t)c));
+      }
+    }
+    if (b == 3) M16 = min(M16, ((top + bot + m) << 3) | (uint32_t)c);
+  }
+  // per partition: the warp's minimum; its owner records the candidate (only partitions whose bound the minimum can reach)
+#pragma unroll
+  for (int k = 0; k < 11; k++) {
+    if (k < nk) {
+      const int a = b - 1, bb = b >> 1;
+      const int cidx = k < 3 ? 3 * a + k : (k < 6 ? 3 * b + (k - 3) : (k < 9 ? 12 + 3 * bb + (k - 6) : 18 + (k - 9)));
+      const int plo = k == 0 ? 25 + 4 * a : k == 1 ? 26 + 4 * a : k == 2 ? 9 + 2 * a : k == 3 ? 25 + 4 * b : k == 4 ? 26 + 4 * b : k == 5 ? 9 + 2 * b
+                    : k == 6 ? 17 + 4 * bb : k == 7 ? 18 + 4 * bb : k == 8 ? 5 + 2 * bb : k == 9 ? 1 : 3;
+      const int phi = (k == 2 || k == 5 || k == 8 || k >= 9) ? plo + 1 : plo + 2;
+      const uint32_t cc = ld_vol(&S.Cw[cidx]);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const uint32_t mine = h ? Mh[k] : M[k];
+        const uint32_t w = __reduce_min_sync(mask, mine > 0x7ffffffu ? 0xffffffffu : ((mine << 5) | (uint32_t)lane));
+        const uint32_t v = w >> 8, th = h ? cc >> 16 : cc & 0xffffu;          // v = SAD + bound;  th = (-B - 1 [- 2]) mod 2^16
+        if (w != 0xffffffffu && (((v + th) & 0x8000u) != 0u) && (w & 31u) == (uint32_t)lane) {
+          const int c = mine & 7;
+          const uint32_t m = (uint32_t)S.mxs[dxa + 4 * (c >> 2)] + (uint32_t)S.mys[dy0 + (c & 3)];
+          fs_rec(ws, ((mine >> 3) - m) | ((uint32_t)(h ? phi : plo) << 16) | lanebits | ((uint32_t)c << 22));
+        }
+      }
+    }
+  }
+  if (b == 3) {
+    const uint32_t w = __reduce_min_sync(mask, M16 > 0x7ffffffu ? 0xffffffffu : ((M16 << 5) | (uint32_t)lane));
+    if (w != 0xffffffffu && (int)(w >> 8) + *reinterpret_cast<const volatile int *>(&S.C16) < 0 && (w & 31u) == (uint32_t)lane) {
+      const int c = M16 & 7;
+      const uint32_t m = (uint32_t)S.mxs[dxa + 4 * (c >> 2)] + (uint32_t)S.mys[dy0 + (c & 3)];
+      fs_rec(ws, ((M16 >> 3) - m) | lanebits | ((uint32_t)c << 22));
+    }
+  }
+  __syncwarp(mask);
+  {
+    const int n1 = *reinterpret_cast<volatile int *>(&ws.nrec);
+    if (n1 > 0 && n1 <= FS_RCAP) {
+      fs_process_records(S, ws, n1, tc.t, tc.R, tc.g, tc.lambda_f, __popc(mask & ((1u << lane) - 1u)), __popc(mask));
+      __syncwarp(mask);
+      if ((mask & ((1u << lane) - 1u)) == 0u) *reinterpret_cast<volatile int *>(&ws.nrec) = 0;
+      __syncwarp(mask);
+    }
+  }
+}
+
 // Records of ONE candidate that passed the quick test of the cold path, at the end of the odd block row b: the partitions
 // inside block rows b - 1 and b (4x4, 8x4), those spanning both (4x8, 8x8) and, at b == 3, the whole-MB ones.  X0, Y0 / X, Y:
 // packed 4x4 SADs ((bx0, bx2), (bx1, bx3)) of rows b - 1 / b; E0: the two 8x8 sums of the upper half; m: the candidate's
@@ -281,9 +409,19 @@ __device__ __noinline__ void fs_cold_detail(const SLOT &S, FsWarp &ws, uint32_t 
 // the minimum over the candidates), the records of those that pass.  buf[5][8]: X, Y, X0, Y0, E0 per candidate q*4+j.
 // Returns the pass bits of the candidates.
 template <class SLOT>
-__device__ __noinline__ uint32_t fs_cold_lane(const SLOT &S, FsWarp &ws, const uint32_t *buf, int b, int dxa, int dy0, uint32_t vm, uint32_t lanebits, int R)
+__device__ __noinline__ uint32_t fs_cold_lane(SLOT &S, FsWarp &ws, const uint32_t *buf, int b, int dxa, int dy0, uint32_t vm, uint32_t lanebits, FsTaskCtx tc)
 {
-  const int a = b - 1, bb = b >> 1;
+  const int a = b - 1, bb = b >> 1, R = tc.R;
+  uint32_t vmm = 0;                                  // valid candidates outside the centres' box (that box was evaluated exactly by the producer's pre-pass)
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int x = dxa + 4 * (c >> 2) - R, y = dy0 + (c & 3) - R;
+    if (((vm >> c) & 1u) && !(x >= -FS_PRE && x <= S.spanx + FS_PRE && y >= -FS_PRE && y <= S.spany + FS_PRE)) vmm |= 1u << c;
+  }
+  {
+    const uint32_t mask = __activemask();
+    if (__popc(mask) >= FS_DENSE) fs_dense_collapse(S, ws, buf, b, dxa, dy0, vmm, lanebits, tc, mask);
+  }
   const uint32_t cx0 = ld_vol(&S.Cw[3 * a]), cy0 = ld_vol(&S.Cw[3 * a + 1]), ch0 = ld_vol(&S.Cw[3 * a + 2]);
   const uint32_t cx = ld_vol(&S.Cw[3 * b]), cy = ld_vol(&S.Cw[3 * b + 1]), ch = ld_vol(&S.Cw[3 * b + 2]);
   const uint32_t cxv = ld_vol(&S.Cw[12 + 3 * bb]), cyv = ld_vol(&S.Cw[13 + 3 * bb]), ce = ld_vol(&S.Cw[14 + 3 * bb]);
@@ -292,11 +430,7 @@ __device__ __noinline__ uint32_t fs_cold_lane(const SLOT &S, FsWarp &ws, const u
   uint32_t pass = 0;
 #pragma unroll 1
   for (int c = 0; c < 8; c++) {
-    if (!((vm >> c) & 1u)) continue;
-    {                                                // the centres' box was evaluated exactly by the producer's pre-pass
-      const int x = dxa + 4 * (c >> 2) - R, y = dy0 + (c & 3) - R;
-      if (x >= -FS_PRE && x <= S.spanx + FS_PRE && y >= -FS_PRE && y <= S.spany + FS_PRE) continue;
-    }
+    if (!((vmm >> c) & 1u)) continue;
     const uint32_t m = (uint32_t)S.mxs[dxa + 4 * (c >> 2)] + (uint32_t)S.mys[dy0 + (c & 3)];
     const uint32_t X = buf[c], Y = buf[8 + c], X0 = buf[16 + c], Y0 = buf[24 + c], E0 = buf[32 + c];
     const uint32_t XV = X + X0, YV = Y + Y0, E = XV + YV;
@@ -336,8 +470,8 @@ __device__ __forceinline__ uint32_t gmin8(const uint32_t (&v)[2][4])
 // The lane's packed sums go to the cold path through local memory: one rolled copy of the per-candidate test, and a small
 // call site (the spill is a handful of STL.128).
 template <class SLOT>
-__device__ __forceinline__ uint32_t fs_cold_spill(const SLOT &S, FsWarp &ws, const uint32_t (&X)[2][4], const uint32_t (&Y)[2][4], const uint32_t (&X0)[2][4],
-                                                  const uint32_t (&Y0)[2][4], const uint32_t (&E0)[2][4], int b, int dxa, int dy0, uint32_t vm, uint32_t lanebits, int R)
+__device__ __forceinline__ uint32_t fs_cold_spill(SLOT &S, FsWarp &ws, const uint32_t (&X)[2][4], const uint32_t (&Y)[2][4], const uint32_t (&X0)[2][4],
+                                                  const uint32_t (&Y0)[2][4], const uint32_t (&E0)[2][4], int b, int dxa, int dy0, uint32_t vm, uint32_t lanebits, FsTaskCtx tc)
 {
   uint32_t buf[5][8];
 #pragma unroll
@@ -348,22 +482,25 @@ __device__ __forceinline__ uint32_t fs_cold_spill(const SLOT &S, FsWarp &ws, con
       buf[2][q * 4 + j] = X0[q][j]; buf[3][q * 4 + j] = Y0[q][j]; buf[4][q * 4 + j] = E0[q][j];
     }
   }
-  return fs_cold_lane(S, ws, &buf[0][0], b, dxa, dy0, vm, lanebits, R);
+  return fs_cold_lane(S, ws, &buf[0][0], b, dxa, dy0, vm, lanebits, tc);
 }
 
 // One lane-job: candidates (dxa, dy0..dy0+3) and (dxa+4, same rows); wb = lane address of window row dy0.  The two 8-row
 // halves of the macroblock run as a rolled loop (the register window slot of reference row i+j is (i+j)&3 in both halves, so
-// the body is the same code: ~8 KB of SASS instead of ~21 KB; 12 desynchronised warps per SM stream through it).
+// the body is the same code; 12 desynchronised warps per SM stream through it).
 //
-// Filter (round 2).  The 41 partition sums of a candidate are still formed per candidate (packed tree sums), but they are no
-// longer tested per candidate: each packed sum is first reduced to its MINIMUM over the lane's eight candidates (7 two-input
-// minima per 8 candidates instead of 8 add + 8 min), and only that minimum meets the threshold  min_c sad_p(c) - B_p - 1 +
-// min_c m(c) < 0  -- a necessary condition for any of the eight to beat partition p's best.  Four warp votes per task (one per
-// block row) decide whether a lane passed; only then do the passing lanes test their candidates one by one (fs_cold_cand)
-// and record the (candidate, partition, SAD) triples that pass.  Returns the pass bits of the lane's candidates (bit q*4+j),
-// used only when the record list overflows.
+// Filter (round 2).  Measured: the task loop is bound by the ALU pipe (VABSDIFF4 occupies it for two cycles; so do VIMNMX3,
+// LOP3, SHF), not by issue slots, so what counts is the ALU work beside the 512 VABSDIFF4 of a task.  The sixteen 4x4 SADs of
+// a candidate are packed two per register on the FMA pipe (IMAD), and the ONLY per-candidate ALU work left is the minimum of
+// each packed 4x4 SAD over the lane's eight candidates (7 two-input minima per 8 candidates and register).  The 41-partition
+// tree is then formed ONCE per lane on those minima:  sum over the 4x4 blocks k of P of min_c sad_k(c)  <=  min_c sad_P(c),
+// so   LB_P - B_P - 1 + min_c m(c) < 0   is a necessary condition for any of the eight candidates to beat partition P's best
+// (B_P = best_P >> 5, m = lower bound of the mv cost >> 5).  Two warp votes per task (after 8 and 16 rows) decide whether some
+// lane passed; only then do the passing lanes test their candidates one by one (fs_cold_lane: exact sums, still in
+// registers) and record the (candidate, partition, SAD) triples that pass.  Returns the pass bits of the lane's candidates
+// (bit q*4+j), used only when the record list overflows.
 template <int PITCH, class SLOT>
-__device__ __forceinline__ uint32_t fs_task4(const SLOT &S, FsWarp &ws, const uint8_t *wb, int dxa, int dy0, uint32_t vm, uint32_t mmin, uint32_t one, int R, int &ncold)
+__device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, const uint8_t *wb, int dxa, int dy0, uint32_t vm, uint32_t mmin, uint32_t one, FsTaskCtx tc, int &ncold)
 {
   constexpr int K = 4;
   const uint4 *cur = reinterpret_cast<const uint4 *>(S.cur);
@@ -371,31 +508,26 @@ __device__ __forceinline__ uint32_t fs_task4(const SLOT &S, FsWarp &ws, const ui
   const uint32_t mm2 = mmin * 0x10001u;
   uint32_t rw[K][6];
   uint32_t acc[2][K][4];
-  uint32_t X[2][K], Y[2][K], T[2][K], X0[2][K], Y0[2][K], E0[2][K];
-  uint32_t pass = 0, rr_even = 0x7fff7fffu, rr = 0x7fff7fffu;
+  uint32_t X0[2][K], Y0[2][K], E0[2][K];
+  uint32_t pass = 0, ME0 = 0, MX0 = 0, MY0 = 0;
 #pragma unroll
-  for (int j = 0; j < K; j++) {
-#pragma unroll
-    for (int q = 0; q < 2; q++) { E0[q][j] = 0; X0[q][j] = 0; Y0[q][j] = 0; X[q][j] = 0; Y[q][j] = 0; T[q][j] = 0; }
-  }
+  for (int j = 0; j < K; j++) { E0[0][j] = E0[1][j] = 0; X0[0][j] = X0[1][j] = 0; Y0[0][j] = Y0[1][j] = 0; }
 #pragma unroll
   for (int j = 0; j < K - 1; j++) ld3(rw[j], wb + j * PITCH);
-  // One block row (4 pixel rows) per iteration: the body (~5 KB of SASS) stays in the scheduler's L0 instruction cache (~6 KB)
-  // for the four iterations of a task; the 12 workers and 3 producer warps of an SM share a 32 KB L1.5 that the kernel's whole
-  // working set does not fit (measured: stall_no_instruction was 25 % of all samples with the 8-row body).
 #pragma unroll 1
-  for (int b = 0; b < 4; b++) {
-    const uint8_t *wr = wb + b * 4 * PITCH;
+  for (int bb = 0; bb < 2; bb++) {
+    const uint8_t *wr = wb + bb * 8 * PITCH;
+    const uint32_t *Cb = S.Cw + 6 * bb;
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
+    for (int r = 0; r < 8; r++) {
       ld3(rw[(r + K - 1) & 3], wr + (r + K - 1) * PITCH);
-      const uint4 c = cur[b * 4 + r];
+      const uint4 c = cur[bb * 8 + r];
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const int sl = (r + j) & 3;
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-          if (r == 0) {
+          if ((r & 3) == 0) {
             acc[q][j][0] = sad4(c.x, rw[sl][q + 0], 0u);
             acc[q][j][1] = sad4(c.y, rw[sl][q + 1], 0u);
             acc[q][j][2] = sad4(c.z, rw[sl][q + 2], 0u);
@@ -408,108 +540,63 @@ __device__ __forceinline__ uint32_t fs_task4(const SLOT &S, FsWarp &ws, const ui
           }
         }
       }
-    }
-    const bool odd = b & 1;
-    if (b == 2) {                                     // T still holds the upper half's 8x8 sums: keep them for the whole-MB partitions
+      if (r == 3) {                                   // even block row 2*bb: pack, minima over the lane's candidates
 #pragma unroll
-      for (int j = 0; j < K; j++) { E0[0][j] = T[0][j]; E0[1][j] = T[1][j]; }
-    }
-    if (odd) {                                        // X, Y still hold the previous (even) block row's packed sums
+        for (int j = 0; j < K; j++) {
 #pragma unroll
-      for (int j = 0; j < K; j++) { X0[0][j] = X[0][j]; X0[1][j] = X[1][j]; Y0[0][j] = Y[0][j]; Y0[1][j] = Y[1][j]; }
-    }
-    const uint32_t cx = ld_vol(&S.Cw[3 * b]), cy = ld_vol(&S.Cw[3 * b + 1]), ch = ld_vol(&S.Cw[3 * b + 2]);
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        X[q][j] = acc[q][j][2] * 65536u + acc[q][j][0];
-        Y[q][j] = acc[q][j][3] * 65536u + acc[q][j][1];
-        T[q][j] = add2(X[q][j], Y[q][j]);
+          for (int q = 0; q < 2; q++) {
+            X0[q][j] = acc[q][j][2] * 65536u + acc[q][j][0];
+            Y0[q][j] = acc[q][j][3] * 65536u + acc[q][j][1];
+          }
+        }
+        MX0 = gmin8(X0); MY0 = gmin8(Y0);
       }
-    }
-    rr = __vimin3_s16x2(gmin8(X) * one + cx, gmin8(Y) * one + cy, gmin8(T) * one + ch);
-    if (!odd) { rr_even = rr; continue; }             // tested with the next block row: one vote per 8 rows
-    {
-      const int bb = b >> 1;
-      const uint32_t cxv = ld_vol(&S.Cw[12 + 3 * bb]), cyv = ld_vol(&S.Cw[13 + 3 * bb]), ce = ld_vol(&S.Cw[14 + 3 * bb]);
-      uint32_t XV[2][K], YV[2][K];
+      if (r == 7) {                                   // odd block row 2*bb+1: the tree on the minima, one vote
+        uint32_t X[2][K], Y[2][K];
 #pragma unroll
-      for (int j = 0; j < K; j++) {
+        for (int j = 0; j < K; j++) {
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-          XV[q][j] = add2(X[q][j], X0[q][j]);
-          YV[q][j] = add2(Y[q][j], Y0[q][j]);
-          T[q][j] = add2(XV[q][j], YV[q][j]);         // the half's two 8x8 sums
+          for (int q = 0; q < 2; q++) {
+            X[q][j] = acc[q][j][2] * 65536u + acc[q][j][0];
+            Y[q][j] = acc[q][j][3] * 65536u + acc[q][j][1];
+          }
+        }
+        const uint32_t MX1 = gmin8(X), MY1 = gmin8(Y);
+        const uint32_t cx0 = ld_vol(&Cb[0]), cy0 = ld_vol(&Cb[1]), ch0 = ld_vol(&Cb[2]);
+        const uint32_t cx1 = ld_vol(&Cb[3]), cy1 = ld_vol(&Cb[4]), ch1 = ld_vol(&Cb[5]);
+        const uint32_t cxv = ld_vol(&S.Cw[12 + 3 * bb]), cyv = ld_vol(&S.Cw[13 + 3 * bb]), ce = ld_vol(&S.Cw[14 + 3 * bb]);
+        const uint32_t MXV = add2(MX0, MX1), MYV = add2(MY0, MY1), ME = add2(MXV, MYV);
+        uint32_t rr = __vimin3_s16x2(MX0 * one + cx0, MY0 * one + cy0, add2(MX0, MY0) * one + ch0);
+        rr = __vimin3_s16x2(rr, MX1 * one + cx1, MY1 * one + cy1);
+        rr = __vimin3_s16x2(rr, add2(MX1, MY1) * one + ch1, MXV * one + cxv);
+        rr = __vimin3_s16x2(rr, MYV * one + cyv, ME * one + ce);
+        int s16 = 0;
+        if (bb) {                                     // whole-MB partitions
+          const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
+          const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
+          const uint32_t top = __dp2a_lo(ME0, 0x0101u, 0u), bot = __dp2a_lo(ME, 0x0101u, 0u);
+          rr = __vimin3_s16x2(rr, (bot * 65536u + top) * one + ctb, add2(ME0, ME) * one + clr);
+          s16 = (int)(top + bot) + c16 + (int)mmin;
+        } else {
+          ME0 = ME;
+#pragma unroll
+          for (int j = 0; j < K; j++) {               // the upper half's two 8x8 sums per candidate: read by the cold path at b == 3
+#pragma unroll
+            for (int q = 0; q < 2; q++) E0[q][j] = add2(add2(X0[q][j], Y0[q][j]), add2(X[q][j], Y[q][j]));
+          }
+        }
+        const bool lp = vm != 0u && ((((rr + mm2) & 0x80008000u) != 0u) || s16 < 0);
+        if (__any_sync(0xffffffffu, lp)) {            // cold: a candidate of some lane may beat a partition's best
+#ifdef FS_PROFILE
+          ncold++;
+#endif
+          if (lp) pass |= fs_cold_spill(S, ws, X, Y, X0, Y0, E0, 2 * bb + 1, dxa, dy0, vm, lanebits, tc);
+          __syncwarp();
         }
       }
-      rr = __vimin3_s16x2(rr, rr_even, __vimin3_s16x2(gmin8(XV) * one + cxv, gmin8(YV) * one + cyv, gmin8(T) * one + ce));
-    }
-    if (b == 3) break;                                // the lower half is voted on together with the whole-MB partitions below
-    const bool lp = vm != 0u && (((rr + mm2) & 0x80008000u) != 0u);
-    if (__any_sync(0xffffffffu, lp)) {                // cold: a candidate of some lane may beat a partition's best
-#ifdef FS_PROFILE
-      ncold++;
-#endif
-      if (lp) pass |= fs_cold_spill(S, ws, X, Y, X0, Y0, E0, 1, dxa, dy0, vm, lanebits, R);
-      __syncwarp();
-    }
-  }
-  {                                                   // whole-MB partitions, vote of the lower half
-    const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
-    const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
-    uint32_t TB[2][K], LR[2][K];
-    int smin = 0x7fffffff;
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const uint32_t top = __dp2a_lo(E0[q][j], 0x0101u, 0u), bot = __dp2a_lo(T[q][j], 0x0101u, 0u);
-        TB[q][j] = bot * 65536u + top;
-        LR[q][j] = add2(E0[q][j], T[q][j]);
-        smin = min(smin, (int)(top + bot));
-      }
-    }
-    rr = __vimin3_s16x2(rr, gmin8(TB) * one + ctb, gmin8(LR) * one + clr);
-    const int s16 = smin + c16 + (int)mmin;
-    const bool lp = vm != 0u && ((((rr + mm2) & 0x80008000u) != 0u) || s16 < 0);
-    if (__any_sync(0xffffffffu, lp)) {
-#ifdef FS_PROFILE
-      ncold++;
-#endif
-      if (lp) pass |= fs_cold_spill(S, ws, X, Y, X0, Y0, E0, 3, dxa, dy0, vm, lanebits, R);
-      __syncwarp();
     }
   }
   return pass;
-}
-
-// Exact evaluation of the task's survivor records, one lane per record: mv cost with the partition's own predictor, spiral
-// position, strict (cost, position) order through a 64-bit atomicMin (me_fullsearch.c:83-93), new filter constant.
-template <class SLOT>
-__device__ __noinline__ void fs_process_records(SLOT &S, FsWarp &ws, int n, int t, int R, int g, int lambda_f)
-{
-  const int lane = threadIdx.x & 31;
-  for (int i = lane; i < n; i += 32) {
-    const uint32_t w = ws.rec[i];
-    const int sad = w & 0xffff, p = (w >> 16) & 63, qj = (w >> 22) & 7, l = w >> 25;
-    int dxa, dy0;
-    if (t < S.ntaskA) { const int e = S.ttab[t]; dxa = 64 * (e >> 8) + 8 * (l >> 2) + (l & 3); dy0 = e & 255; }
-    else { const int job = (t - S.ntaskA) * 32 + l; const int ii = job / S.ngy, gy = job - ii * S.ngy; dxa = 64 * S.ncbA + 8 * (ii >> 2) + (ii & 3); dy0 = gy * FS_K; }
-    const int dx = dxa + 4 * (qj >> 2), dy = dy0 + (qj & 3);
-    if (S.pgrp[p] != g) continue;
-    const int ox = dx - R - S.pex[p], oy = dy - R - S.pey[p];   // displacement from the partition's own centre
-    if (max(abs(ox), abs(oy)) > S.psr[p]) continue;
-    const int mvx = S.pcx[p] + 4 * ox, mvy = S.pcy[p] + 4 * oy;
-    const long long cost = ((long long)sad << 5) + (long long)lambda_f * (mvbits(mvx - S.ppx[p]) + mvbits(mvy - S.ppy[p]));
-    const unsigned long long bestv = *reinterpret_cast<volatile unsigned long long *>(&S.best[p]);
-    if ((unsigned long long)cost > (bestv >> 20)) continue;
-    const unsigned long long key = ((unsigned long long)cost << 20) | (unsigned)spiral_index(ox, oy);
-    if (key < bestv) {
-      const unsigned long long old = atomicMin(&S.best[p], key);
-      set_threshold(S, p, old < key ? old : key);
-    }
-  }
 }
 
 // Survivors of a task (out of line: rare).  Records: exact evaluation from the recorded SADs; a list that overflowed: per-candidate
@@ -523,7 +610,7 @@ __device__ __noinline__ int fs_survivors(SLOT &S, FsWarp &ws, const uint8_t *win
   const int nrec = *reinterpret_cast<volatile int *>(&ws.nrec);
   int nh = 0;
   if (nrec <= FS_RCAP) {
-    fs_process_records(S, ws, nrec, t, R, g, lambda_f);
+    fs_process_records(S, ws, nrec, t, R, g, lambda_f, lane, 32);
     nh = lane == 0 ? nrec : 0;
   } else {
     for (int bb = 0; bb < 2 * K; bb++) {
@@ -986,7 +1073,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         uint32_t pass = 0;
 #pragma unroll 1
         for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
-          pass |= fs_task4<PITCH>(S, WS[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, R, ncold);
+          pass |= fs_task4<PITCH>(S, WS[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, FsTaskCtx{t, R, g, a.lambda_f}, ncold);
         const long long tt1 = FS_CLOCK();
         c_task += tt1 - tt0;
         __syncwarp();
