@@ -228,25 +228,13 @@ __device__ __forceinline__ void ld3(uint32_t (&r)[6], const uint8_t *p)
 }
 
 // ---- survivor records ---------------------------------------------------------------------------------------
-// A (candidate, partition) pair that passes the precise filter is recorded where its SAD is still in a register:
+// Records of the dense collapse (fs_dense_collapse): a (candidate, partition) pair whose SAD is known,
 //   word = sad (16) | partition << 16 | (q * 4 + j) << 22 | lane << 25        (q: column of the lane's pair, j: row of the task)
-// and evaluated exactly (mv cost, spiral position, 64-bit atomicMin) by the warp at the end of the task, one lane per
-// record.  A task that overflows the list falls back to the per-candidate re-evaluation (fs_exact2)
-// through its pass bits.
+// evaluated exactly (mv cost, spiral position, 64-bit atomicMin) by fs_process_records, one lane per record.
 __device__ __noinline__ void fs_rec(FsWarp &ws, uint32_t word)
 {
   const int i = atomicAdd(&ws.nrec, 1);
   if (i < FS_RCAP) ws.rec[i] = word;
-}
-
-__device__ __forceinline__ void fs_cold_test(FsWarp &ws, uint32_t V, uint32_t c, uint32_t mcp, int plo, int phi, uint32_t cb, uint32_t &hit)
-{
-  const uint32_t tt = V + c + mcp;                 // per half: sad - B - 1 + m (the high half up to two lower, see set_threshold)
-  if (tt & 0x80008000u) {
-    hit = 1u;
-    if (tt & 0x8000u) fs_rec(ws, (V & 0xffffu) | ((uint32_t)plo << 16) | cb);
-    if (tt & 0x80000000u) fs_rec(ws, (V >> 16) | ((uint32_t)phi << 16) | cb);
-  }
 }
 
 // Exact evaluation of the task's survivor records, one lane per record: mv cost with the partition's own predictor, spiral
@@ -300,17 +288,6 @@ __device__ __noinline__ void fs_dense_collapse(SLOT &S, FsWarp &ws, const uint32
   uint32_t M[11]; uint32_t M16 = 0xffffffffu;
 #pragma unroll
   for (int k = 0; k < 11; k++) M[k] = 0xffffffffu;
-  // flush what earlier cold entries of this task recorded (keeps the list below its capacity)
-  __syncwarp(mask);
-  {
-    const int n0 = *reinterpret_cast<volatile int *>(&ws.nrec);
-    if (n0 > 0 && n0 <= FS_RCAP) {
-      fs_process_records(S, ws, n0, tc.t, tc.R, tc.g, tc.lambda_f, __popc(mask & ((1u << lane) - 1u)), __popc(mask));
-      __syncwarp(mask);
-      if ((mask & ((1u << lane) - 1u)) == 0u) *reinterpret_cast<volatile int *>(&ws.nrec) = 0;
-      __syncwarp(mask);
-    }
-  }
   // per lane: minimum over its candidates of ((SAD + mv-cost bound) << 3 | candidate) for every partition of this level
   uint32_t Mh[11];
 #pragma unroll
@@ -376,35 +353,6 @@ __device__ __noinline__ void fs_dense_collapse(SLOT &S, FsWarp &ws, const uint32
   }
 }
 
-// Records of ONE candidate that passed the quick test of the cold path, at the end of the odd block row b: the partitions
-// inside block rows b - 1 and b (4x4, 8x4), those spanning both (4x8, 8x8) and, at b == 3, the whole-MB ones.  X0, Y0 / X, Y:
-// packed 4x4 SADs ((bx0, bx2), (bx1, bx3)) of rows b - 1 / b; E0: the two 8x8 sums of the upper half; m: the candidate's
-// mv-cost lower bound.
-template <class SLOT>
-__device__ __noinline__ void fs_cold_detail(const SLOT &S, FsWarp &ws, uint32_t X, uint32_t Y, uint32_t X0, uint32_t Y0, uint32_t E0,
-                                            int b, uint32_t m, uint32_t cb)
-{
-  uint32_t hit = 0;
-  const uint32_t mcp = m * 0x10001u;
-  const int a = b - 1, bb = b >> 1;
-  fs_cold_test(ws, X0, ld_vol(&S.Cw[3 * a]), mcp, 25 + 4 * a, 27 + 4 * a, cb, hit);
-  fs_cold_test(ws, Y0, ld_vol(&S.Cw[3 * a + 1]), mcp, 26 + 4 * a, 28 + 4 * a, cb, hit);
-  fs_cold_test(ws, X0 + Y0, ld_vol(&S.Cw[3 * a + 2]), mcp, 9 + 2 * a, 10 + 2 * a, cb, hit);
-  fs_cold_test(ws, X, ld_vol(&S.Cw[3 * b]), mcp, 25 + 4 * b, 27 + 4 * b, cb, hit);
-  fs_cold_test(ws, Y, ld_vol(&S.Cw[3 * b + 1]), mcp, 26 + 4 * b, 28 + 4 * b, cb, hit);
-  fs_cold_test(ws, X + Y, ld_vol(&S.Cw[3 * b + 2]), mcp, 9 + 2 * b, 10 + 2 * b, cb, hit);
-  const uint32_t XV = X + X0, YV = Y + Y0, E = XV + YV;
-  fs_cold_test(ws, XV, ld_vol(&S.Cw[12 + 3 * bb]), mcp, 17 + 4 * bb, 19 + 4 * bb, cb, hit);
-  fs_cold_test(ws, YV, ld_vol(&S.Cw[13 + 3 * bb]), mcp, 18 + 4 * bb, 20 + 4 * bb, cb, hit);
-  fs_cold_test(ws, E, ld_vol(&S.Cw[14 + 3 * bb]), mcp, 5 + 2 * bb, 6 + 2 * bb, cb, hit);
-  if (b == 3) {
-    const uint32_t top = (E0 & 0xffffu) + (E0 >> 16), bot = (E & 0xffffu) + (E >> 16);
-    fs_cold_test(ws, (bot << 16) | top, ld_vol(&S.Cw[18]), mcp, 1, 2, cb, hit);
-    fs_cold_test(ws, E0 + E, ld_vol(&S.Cw[19]), mcp, 3, 4, cb, hit);
-    if ((int)(top + bot) + *reinterpret_cast<const volatile int *>(&S.C16) + (int)m < 0) fs_rec(ws, (top + bot) | cb);
-  }
-}
-
 // The cold path of one lane at the end of the odd block row b: a quick packed test per candidate (the hot path's filter without
 // the minimum over the candidates), the records of those that pass.  buf[5][8]: X, Y, X0, Y0, E0 per candidate q*4+j.
 // Returns the pass bits of the candidates.
@@ -444,10 +392,7 @@ __device__ __noinline__ uint32_t fs_cold_lane(SLOT &S, FsWarp &ws, const uint32_
       t = __vimin3_s16x2(t, ((bot << 16) | top) + ctb, E0 + E + clr);
       s16 = (int)(top + bot) + c16 + (int)m;
     }
-    if ((((t + m * 0x10001u) & 0x80008000u) != 0u) || s16 < 0) {
-      fs_cold_detail(S, ws, X, Y, X0, Y0, E0, b, m, lanebits | ((uint32_t)c << 22));
-      pass |= 1u << c;
-    }
+    if ((((t + m * 0x10001u) & 0x80008000u) != 0u) || s16 < 0) pass |= 1u << c;
   }
   return pass;
 }
@@ -599,37 +544,29 @@ __device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, const uint8_t 
   return pass;
 }
 
-// Survivors of a task (out of line: rare).  Records: exact evaluation from the recorded SADs; a list that overflowed: per-candidate
-// re-evaluation (fs_exact2) of the candidates whose pass bit is set.  Returns the number of exact evaluations (lane 0).
+// Survivors of a task (out of line: rare): the candidates whose pass bit is set are evaluated exactly for all 41 partitions at once
+// (fs_exact2: 16 lanes per candidate for the 4x4 SADs, one lane per (candidate, partition)).  Returns the number of exact
+// evaluations (lane 0).
 template <int PITCH, class SLOT>
 __device__ __noinline__ int fs_survivors(SLOT &S, FsWarp &ws, const uint8_t *win, int copy_bytes, const uint32_t *pgt, uint32_t pass,
-                                         int dxa, int dy0, int t, int R, int g, int lambda_f)
+                                         int dxa, int dy0, int R, int g, int lambda_f)
 {
   constexpr int K = FS_K;
   const int lane = threadIdx.x & 31;
-  const int nrec = *reinterpret_cast<volatile int *>(&ws.nrec);
   int nh = 0;
-  if (nrec <= FS_RCAP) {
-    fs_process_records(S, ws, nrec, t, R, g, lambda_f, lane, 32);
-    nh = lane == 0 ? nrec : 0;
-  } else {
-    for (int bb = 0; bb < 2 * K; bb++) {
-      uint32_t m = __ballot_sync(0xffffffffu, (pass >> bb) & 1u);
-      while (m) {
-        const int l0 = __ffs(m) - 1; m &= m - 1;
-        const bool v1 = m != 0;
-        const int l1 = v1 ? __ffs(m) - 1 : l0; m &= m - 1;
-        const int ddx = bb >= K ? 4 : 0, ddy = bb >= K ? bb - K : bb;
-        const int ex0_ = __shfl_sync(0xffffffffu, dxa, l0) + ddx, ey0 = __shfl_sync(0xffffffffu, dy0, l0) + ddy;
-        const int ex1_ = __shfl_sync(0xffffffffu, dxa, l1) + ddx, ey1 = __shfl_sync(0xffffffffu, dy0, l1) + ddy;
-        fs_exact2<PITCH>(S, ws, win, copy_bytes, pgt, ex0_, ey0, ex1_, ey1, v1, R, g, lambda_f);
-        if (lane == 0) nh += v1 ? 2 : 1;
-      }
+  for (int bb = 0; bb < 2 * K; bb++) {
+    uint32_t m = __ballot_sync(0xffffffffu, (pass >> bb) & 1u);
+    while (m) {
+      const int l0 = __ffs(m) - 1; m &= m - 1;
+      const bool v1 = m != 0;
+      const int l1 = v1 ? __ffs(m) - 1 : l0; m &= m - 1;
+      const int ddx = bb >= K ? 4 : 0, ddy = bb >= K ? bb - K : bb;
+      const int ex0_ = __shfl_sync(0xffffffffu, dxa, l0) + ddx, ey0 = __shfl_sync(0xffffffffu, dy0, l0) + ddy;
+      const int ex1_ = __shfl_sync(0xffffffffu, dxa, l1) + ddx, ey1 = __shfl_sync(0xffffffffu, dy0, l1) + ddy;
+      fs_exact2<PITCH>(S, ws, win, copy_bytes, pgt, ex0_, ey0, ex1_, ey1, v1, R, g, lambda_f);
+      if (lane == 0) nh += v1 ? 2 : 1;
     }
   }
-  __syncwarp();
-  if (lane == 0) *reinterpret_cast<volatile int *>(&ws.nrec) = 0;
-  __syncwarp();
   return nh;
 }
 
@@ -1076,9 +1013,8 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
           pass |= fs_task4<PITCH>(S, WS[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, FsTaskCtx{t, R, g, a.lambda_f}, ncold);
         const long long tt1 = FS_CLOCK();
         c_task += tt1 - tt0;
-        __syncwarp();
-        if (*reinterpret_cast<volatile int *>(&WS[warp].nrec)) {        // survivors (rare): out of line
-          nh += fs_survivors<PITCH>(S, WS[warp], win, G.copy_bytes, pgt, pass, dxa, dy0, t, R, g, a.lambda_f);
+        if (__any_sync(0xffffffffu, pass != 0u)) {                      // survivors (rare): out of line
+          nh += fs_survivors<PITCH>(S, WS[warp], win, G.copy_bytes, pgt, pass, dxa, dy0, R, g, a.lambda_f);
           c_exact += FS_CLOCK() - tt1;
         }
       }
