@@ -302,6 +302,7 @@ static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
   { const char *e = getenv("B2ME_FS_NOTMA"); f.flags = (e && e[0] == '1') ? 1 : 0;
     const char *r = getenv("B2ME_FS_REP"); if (r) f.flags |= atoi(r) << 8;
     const char *z = getenv("B2ME_FS_SLEEP"); if (z && z[0] == '1') f.flags |= 2;
+    const char *sd = getenv("B2ME_FS_NOSEED"); if (sd && sd[0] == '1') f.flags |= 4;
     const char *k = getenv("B2ME_FS_CLAIM"); f.claim = k ? atoi(k) : 3; if (f.claim < 1) f.claim = 1; }
   f.work_counter = c->d_work;
   B2_CUDA_CHECK(c, cudaMemsetAsync(c->d_work, 0, sizeof(int), s));

@@ -61,9 +61,9 @@ namespace b2 {
 #endif
 constexpr int FS_K = FS_KV;         // candidate rows per task (lock step); fs_task4 is written for 4
 #ifndef FS_PREV
-#define FS_PREV 0
+#define FS_PREV -1
 #endif
-constexpr int FS_PRE = FS_PREV;       // radius of the exact pre-pass around the centres (initial bounds)
+constexpr int FS_PRE = FS_PREV;       // >= 0: radius of the exact pre-pass around the centres' box; -1: one centre only (initial bounds)
 constexpr int FS_SMAX = 7;       // partitions whose centres lie within a 7-pel box share one window pass
 constexpr int FS_BMAX = 12;      // a trailing column block of at most this width is walked row-major (type B)
 constexpr int FS_MCAP = 2047;    // cap of each half of the mv-cost lower bound (keeps packed sums in range)
@@ -102,6 +102,8 @@ struct __align__(16) FsSlotT {    // one unit = (item, centre group): everything
   signed char pgrp[NPART];        // centre group of the partition (-1 inactive)
   signed char pex[NPART], pey[NPART];   // centre of the partition relative to its group's box origin (pel)
   int item, mb, ref, g, ngroups; unsigned base_lo, base_hi;
+  int seedx, seedy;               // window coordinates of the seed candidate the pre-pass evaluated (-1: none)
+  int prex, prey, prew, preh;     // window rectangle the pre-pass evaluated exactly
   int gx0, gy0, spanx, spany;     // the group's centre box (pel)
   int wx0, wy0, inside;           // window origin in the search plane; inside: the TMA path applies
   int ncx, ncy, ngy, gc, ncbA, ntaskA, npb, ntask;
@@ -121,7 +123,7 @@ struct FsCtl {                    // per window buffer: the pipeline between the
   int epoch, tma_uses;
 };
 
-constexpr int FS_DENSE = 6;      // lanes of a warp in the cold path at once from which the dense collapse runs first
+constexpr int FS_DENSE = 12;     // candidates of a warp passing the cold path's test at once from which the dense collapse runs
 constexpr int FS_RCAP = 24;      // survivor records per warp and task
 struct FsWarp {
   unsigned short sat[2][28];     // fs_exact2's summed-area tables (row 0 / column 0 stay zero)
@@ -363,36 +365,42 @@ __device__ __noinline__ uint32_t fs_cold_lane(SLOT &S, FsWarp &ws, const uint32_
   uint32_t vmm = 0;                                  // valid candidates outside the centres' box (that box was evaluated exactly by the producer's pre-pass)
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    const int x = dxa + 4 * (c >> 2) - R, y = dy0 + (c & 3) - R;
-    if (((vm >> c) & 1u) && !(x >= -FS_PRE && x <= S.spanx + FS_PRE && y >= -FS_PRE && y <= S.spany + FS_PRE)) vmm |= 1u << c;
+    const int x = dxa + 4 * (c >> 2), y = dy0 + (c & 3);
+    if (((vm >> c) & 1u) && !(x >= S.prex && x < S.prex + S.prew && y >= S.prey && y < S.prey + S.preh) && !(x == S.seedx && y == S.seedy)) vmm |= 1u << c;
   }
-  {
-    const uint32_t mask = __activemask();
-    if (__popc(mask) >= FS_DENSE) fs_dense_collapse(S, ws, buf, b, dxa, dy0, vmm, lanebits, tc, mask);
-  }
-  const uint32_t cx0 = ld_vol(&S.Cw[3 * a]), cy0 = ld_vol(&S.Cw[3 * a + 1]), ch0 = ld_vol(&S.Cw[3 * a + 2]);
-  const uint32_t cx = ld_vol(&S.Cw[3 * b]), cy = ld_vol(&S.Cw[3 * b + 1]), ch = ld_vol(&S.Cw[3 * b + 2]);
-  const uint32_t cxv = ld_vol(&S.Cw[12 + 3 * bb]), cyv = ld_vol(&S.Cw[13 + 3 * bb]), ce = ld_vol(&S.Cw[14 + 3 * bb]);
-  const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
-  const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
+  const uint32_t mask = __activemask();              // the lanes in the cold path (converged here)
   uint32_t pass = 0;
 #pragma unroll 1
-  for (int c = 0; c < 8; c++) {
-    if (!((vmm >> c) & 1u)) continue;
-    const uint32_t m = (uint32_t)S.mxs[dxa + 4 * (c >> 2)] + (uint32_t)S.mys[dy0 + (c & 3)];
-    const uint32_t X = buf[c], Y = buf[8 + c], X0 = buf[16 + c], Y0 = buf[24 + c], E0 = buf[32 + c];
-    const uint32_t XV = X + X0, YV = Y + Y0, E = XV + YV;
-    uint32_t t = __vimin3_s16x2(X0 + cx0, Y0 + cy0, X0 + Y0 + ch0);
-    t = __vimin3_s16x2(t, X + cx, Y + cy);
-    t = __vimin3_s16x2(t, X + Y + ch, XV + cxv);
-    t = __vimin3_s16x2(t, YV + cyv, E + ce);
-    int s16 = 0;
-    if (b == 3) {
-      const uint32_t top = (E0 & 0xffffu) + (E0 >> 16), bot = (E & 0xffffu) + (E >> 16);
-      t = __vimin3_s16x2(t, ((bot << 16) | top) + ctb, E0 + E + clr);
-      s16 = (int)(top + bot) + c16 + (int)m;
+  for (int round = 0; round < 2; round++) {
+    const uint32_t cx0 = ld_vol(&S.Cw[3 * a]), cy0 = ld_vol(&S.Cw[3 * a + 1]), ch0 = ld_vol(&S.Cw[3 * a + 2]);
+    const uint32_t cx = ld_vol(&S.Cw[3 * b]), cy = ld_vol(&S.Cw[3 * b + 1]), ch = ld_vol(&S.Cw[3 * b + 2]);
+    const uint32_t cxv = ld_vol(&S.Cw[12 + 3 * bb]), cyv = ld_vol(&S.Cw[13 + 3 * bb]), ce = ld_vol(&S.Cw[14 + 3 * bb]);
+    const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
+    const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
+    pass = 0;
+#pragma unroll 1
+    for (int c = 0; c < 8; c++) {
+      if (!((vmm >> c) & 1u)) continue;
+      const uint32_t m = (uint32_t)S.mxs[dxa + 4 * (c >> 2)] + (uint32_t)S.mys[dy0 + (c & 3)];
+      const uint32_t X = buf[c], Y = buf[8 + c], X0 = buf[16 + c], Y0 = buf[24 + c], E0 = buf[32 + c];
+      const uint32_t XV = X + X0, YV = Y + Y0, E = XV + YV;
+      uint32_t t = __vimin3_s16x2(X0 + cx0, Y0 + cy0, X0 + Y0 + ch0);
+      t = __vimin3_s16x2(t, X + cx, Y + cy);
+      t = __vimin3_s16x2(t, X + Y + ch, XV + cxv);
+      t = __vimin3_s16x2(t, YV + cyv, E + ce);
+      int s16 = 0;
+      if (b == 3) {
+        const uint32_t top = (E0 & 0xffffu) + (E0 >> 16), bot = (E & 0xffffu) + (E >> 16);
+        t = __vimin3_s16x2(t, ((bot << 16) | top) + ctb, E0 + E + clr);
+        s16 = (int)(top + bot) + c16 + (int)m;
+      }
+      if ((((t + m * 0x10001u) & 0x80008000u) != 0u) || s16 < 0) pass |= 1u << c;
     }
-    if ((((t + m * 0x10001u) & 0x80008000u) != 0u) || s16 < 0) pass |= 1u << c;
+    __syncwarp(mask);
+    // many candidates of the warp pass at once: the bounds are still loose (the first tasks of an item whose predictor is
+    // wrong).  Collapse them (one exact evaluation per partition), then test again against the new bounds.
+    if (round || (int)__reduce_add_sync(mask, (unsigned)__popc(pass)) < FS_DENSE) break;
+    fs_dense_collapse(S, ws, buf, b, dxa, dy0, vmm, lanebits, tc, mask);
   }
   return pass;
 }
@@ -622,7 +630,7 @@ struct FsCtaStats { int err, nhits, ngroups, nitems; unsigned long long cyc[9]; 
 
 // Results of a finished item (me_fullsearch.c:95-102: mv += spiral[best], return min_mcost).
 template <class SLOT>
-__device__ __forceinline__ void fs_write_results(const SLOT &S, const FsArgs &a, FsCtaStats *st)
+__device__ __forceinline__ void fs_write_results(const SLOT &S, const FsArgs &a, FsCtaStats *st, int *lastmv)
 {
   const int lane = threadIdx.x & 31;
   if (S.item < 0 || S.ngroups <= 0) return;
@@ -634,6 +642,7 @@ __device__ __forceinline__ void fs_write_results(const SLOT &S, const FsArgs &a,
     int sx, sy; spiral_xy(pos, &sx, &sy);
     a.mv_int[(base + p) * 2]     = (int16_t)(S.pcx[p] + 4 * sx);
     a.mv_int[(base + p) * 2 + 1] = (int16_t)(S.pcy[p] + 4 * sy);
+    if (p == 0) lastmv[S.ref & 15] = ((S.pcx[p] + 4 * sx) & 0xffff) | ((S.pcy[p] + 4 * sy) << 16);   // seed of this CTA's next item of that reference
     long long cost = (long long)(key >> 20);
     if (pos == 0 && cost == (1ll << 42) && a.min_mcost > (1ll << 42)) cost = a.min_mcost;   // bound never beaten
     a.cost_int[base + p] = cost;
@@ -789,7 +798,7 @@ __device__ __noinline__ bool fs_prepare(SLOT &S, int &item_io, const FsArgs &a, 
 // task counter second (see the worker loop).
 template <int PITCH, class SLOT>
 __device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWarp &ws, uint8_t *win, const uint32_t *pgt,
-                                         const FsArgs &a, const CUtensorMap *tm, FsCtaStats *st)
+                                         const FsArgs &a, const CUtensorMap *tm, FsCtaStats *st, const int *lastmv)
 {
   constexpr int K = FS_K;
   const FsGeom G = fs_geom(a.R);
@@ -825,16 +834,43 @@ __device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWa
     }
   }
   __syncwarp();
-  // ---- initial bounds: exact pre-pass over the centres' box ----
+  // ---- initial bounds: exact pre-pass over the centres' box, plus ONE seed candidate: the 16x16 vector this CTA's last finished
+  //      item of the same reference ended on.  Any candidate may be evaluated first without changing the result (the argmin
+  //      is exact); when the predictor is wrong but the motion is coherent the seed brings the bounds down before the first
+  //      task instead of after the row group that holds the optimum (measured: 6.6 ms -> see DESIGN 4.1 for predictors off by
+  //      +-8 pel) ----
   {
-    const int xlo = max(0, R - FS_PRE), ylo = max(0, R - FS_PRE);
-    const int pw = min(S.ncx - 1, R + S.spanx + FS_PRE) - xlo + 1, ph = min(S.ncy - 1, R + S.spany + FS_PRE) - ylo + 1;
-    const int total = pw * ph;
+    // FS_PRE < 0 (default): ONE candidate instead of the centres' box -- the centre of the group's first partition.  With one
+    // predictor per partition the box holds up to (1 + span)^2 candidates and their exact evaluation saturated the producer
+    // warp (measured: per-partition predictors 1.84 ms against 1.23 ms with shared ones); the other centres are ordinary
+    // candidates of the hot path.
+    int xlo, ylo, pw, ph;
+    if (FS_PRE >= 0) {
+      xlo = max(0, R - FS_PRE); ylo = max(0, R - FS_PRE);
+      pw = min(S.ncx - 1, R + S.spanx + FS_PRE) - xlo + 1; ph = min(S.ncy - 1, R + S.spany + FS_PRE) - ylo + 1;
+    } else {
+      int p0 = 0;
+      while (p0 < NPART - 1 && S.pgrp[p0] != S.g) p0++;
+      xlo = R + S.pex[p0]; ylo = R + S.pey[p0]; pw = 1; ph = 1;
+    }
+    int total = pw * ph;
+    int sdx = -1, sdy = -1;
+    {
+      const int sm = lastmv[S.ref & 15];
+      if (sm != 0x7fff7fff && !(a.flags & 4)) {
+        const int x = ((int)(short)(sm & 0xffff) >> 2) - S.gx0 + R, y = ((sm >> 16) >> 2) - S.gy0 + R;
+        const bool inbox = x >= xlo && x < xlo + pw && y >= ylo && y < ylo + ph;
+        if (x >= 0 && x < S.ncx && y >= 0 && y < S.ncy && !inbox) { sdx = x; sdy = y; }
+      }
+    }
+    if (lane == 0) { S.seedx = sdx; S.seedy = sdy; S.prex = xlo; S.prey = ylo; S.prew = pw; S.preh = ph; }
+    if (sdx >= 0) total++;
     for (int i0 = 0; i0 < total; i0 += 2) {
       const int i1 = i0 + 1;
       const bool v1 = i1 < total;
-      const int dx0 = xlo + i0 % pw, dy0 = ylo + i0 / pw;
-      const int dx1 = v1 ? xlo + i1 % pw : dx0, dy1 = v1 ? ylo + i1 / pw : dy0;
+      const bool s0 = sdx >= 0 && i0 == total - 1, s1 = sdx >= 0 && i1 == total - 1;
+      const int dx0 = s0 ? sdx : xlo + i0 % pw, dy0 = s0 ? sdy : ylo + i0 / pw;
+      const int dx1 = !v1 ? dx0 : (s1 ? sdx : xlo + i1 % pw), dy1 = !v1 ? dy0 : (s1 ? sdy : ylo + i1 / pw);
       fs_exact2<PITCH>(S, ws, win, G.copy_bytes, pgt, dx0, dy0, dx1, dy1, v1, R, S.g, a.lambda_f);
     }
   }
@@ -865,6 +901,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
   __shared__ FsWarp WS[NWORK + 1];
   __shared__ uint32_t pgt[NPART];
   __shared__ FsCtaStats st;
+  __shared__ int lastmv[16];                       // per reference slot: the 16x16 vector of the CTA's last finished item (0x7fff7fff: none)
   constexpr int K = FS_K;
   const FsGeom G = fs_geom(a.R);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -884,6 +921,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 3) { SS[tid].item = -1; SS[tid].ngroups = 0; SS[tid].g = 0; }
+  if (tid < 16) lastmv[tid] = 0x7fff7fff;
   __syncthreads();
 
   if (warp == NWORK) {
@@ -897,7 +935,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
     bool staged = fs_prepare<PITCH>(SS[0], item, a, &st);
     for (int b = 0; b < 2; b++) {
       if (staged) {
-        fs_activate<PITCH>(CB[b], SS[b], b, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st);
+        fs_activate<PITCH>(CB[b], SS[b], b, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st, lastmv);
         staged = fs_prepare<PITCH>(SS[b == 0 ? 1 : 2], item, a, &st);
       } else if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int *>(&CB[b].ended) = 1; }
     }
@@ -919,22 +957,27 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         SLOT &O = SS[old];
         if (O.g + 1 < O.ngroups) {                   // next centre group of the same item, in place (rare)
           fs_setup_group<PITCH>(O, O.g + 1, a);
-          fs_activate<PITCH>(C, O, old, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st);
+          fs_activate<PITCH>(C, O, old, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st, lastmv);
         } else if (staged) {
-          fs_activate<PITCH>(C, SS[stage], stage, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st);
-          fs_write_results(O, a, &st);
+          fs_activate<PITCH>(C, SS[stage], stage, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st, lastmv);
+          fs_write_results(O, a, &st, lastmv);
           __syncwarp();
           stage = old;
           staged = fs_prepare<PITCH>(SS[stage], item, a, &st);
         } else {
-          fs_write_results(O, a, &st);
+          fs_write_results(O, a, &st, lastmv);
           __syncwarp();
           if (lane == 0) { O.item = -1; __threadfence_block(); *reinterpret_cast<volatile int *>(&C.ended) = 1; }
         }
       }
       if (any) p_busy += FS_CLOCK() - tb0;
       if (nend == 2) break;
-      if (!any && !mbar_try_wait_ns(&evt, evp, 20000u) && (a.flags & 2)) __nanosleep(1000);   // (two completions inside one scan would be seen at the time-out)
+      if (!any) {
+        // sleep on the event barrier; the hardware ends a try_wait after ~0.4 us whatever the hint says, so only every 16th
+        // time-out goes back to the scan (two completions inside one scan flip the parity twice: they are seen at that rescan)
+#pragma unroll 1
+        for (int k = 0; k < 16 && !mbar_try_wait_ns(&evt, evp, 20000u); k++) { if (a.flags & 2) __nanosleep(1000); }
+      }
     }
     if (lane == 0) { atomicAdd(&st.cyc[2], (unsigned long long)(clock64() - t_p0)); atomicAdd(&st.cyc[5], (unsigned long long)p_busy); }
   } else {
