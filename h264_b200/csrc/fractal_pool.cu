@@ -762,8 +762,8 @@ static int fp_launch(b2fp_ctx *c, int probe, int32_t *dom, uint8_t *iso, int16_t
   a.best_dom = dom; a.best_iso = iso; a.aq = aq; a.beta = beta; a.err_num = (long long *)err;
   a.stats = c->d_stats; a.probe = probe;
   const int smem = 2 * 8192 + FP_BSTAGES * 16384 + FP_CSTAGES * FP_CT_BYTES + FP_EPI_WARPS * 4096 + (int)sizeof(FpSmem) + 1024;
-  static int configured = 0;
-  if (!configured) { FP_CHECK(c, cudaFuncSetAttribute(k_frac_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, smem < 160 * 1024 ? 160 * 1024 : smem)); configured = 1; }
+  static int configured[64] = {0};                      // per device ordinal: the attribute belongs to the device's copy of the function
+  if (!configured[c->device & 63]) { FP_CHECK(c, cudaFuncSetAttribute(k_frac_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, smem < 160 * 1024 ? 160 * 1024 : smem)); configured[c->device & 63] = 1; }
   const int grid = c->mtiles < c->sm_count ? c->mtiles : c->sm_count;
   if (timed) cudaEventRecord(c->ev0, s);
   // >= 116 KB of dynamic shared memory keeps ONE CTA per SM: each CTA allocates all 512 TMEM columns

@@ -1116,7 +1116,8 @@ FsGeom fs_geom_host(int R) { return fs_geom(R); }
 cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, cudaStream_t s, int *smem_bytes_out)
 {
   const FsGeom G = fs_geom(a.R);
-  static int configured160 = 0;
+  static int configured160[64] = {0};                   // cudaFuncSetAttribute is per DEVICE: one flag per device ordinal
+  int dev = 0; cudaGetDevice(&dev); dev &= 63;
   cudaError_t e;
   if (smem_bytes_out) *smem_bytes_out = G.total;
   if (G.pitch == 96) {
@@ -1125,17 +1126,19 @@ cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, 
     if (var < 0) { const char *e = getenv("B2ME_FS_VAR"); var = !e ? 0 : (e[0] == '7' ? 1 : (e[0] == '6' ? 2 : (e[0] == '3' ? 3 : 0))); }
 #define FS_LAUNCH96(NW, MB)                                                                                                   \
     {                                                                                                                         \
-      static int configured = 0, occ = -1;                                                                                    \
-      if (configured < G.total) {                                                                                             \
+      static int configured[64] = {0}, occs[64] = {0};                                                                        \
+      if (configured[dev] < G.total) {                                                                                        \
         e = cudaFuncSetAttribute(k_sad_fs<96, NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);                 \
         if (e != cudaSuccess) return e;                                                                                       \
-        configured = G.total;                                                                                                 \
+        configured[dev] = G.total; occs[dev] = 0;                                                                             \
       }                                                                                                                       \
-      if (occ < 0) {                                                                                                          \
+      if (occs[dev] < 1) {                                                                                                    \
+        int occ = 0;                                                                                                          \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sad_fs<96, NW, MB>, (NW + 1) * 32, G.total);                    \
         if (getenv("B2ME_FS_PROFILE")) fprintf(stderr, "[b2me] k_sad_fs<96,%d>: %d CTAs/SM (dyn smem %d)\n", NW, occ, G.total); \
-        if (occ < 1) occ = 1;                                                                                                 \
+        occs[dev] = occ < 1 ? 1 : occ;                                                                                        \
       }                                                                                                                       \
+      const int occ = occs[dev];                                                                                              \
       const int grid = min((a.nitems + 1) / 2, sm_count * occ);                                                               \
       k_sad_fs<96, NW, MB><<<grid, (NW + 1) * 32, G.total, s>>>(tm, a);                                                       \
     }
@@ -1145,10 +1148,10 @@ cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, 
     else FS_LAUNCH96(4, 3)
 #undef FS_LAUNCH96
   } else if (G.pitch == 160) {
-    if (configured160 < G.total) {
+    if (configured160[dev] < G.total) {
       e = cudaFuncSetAttribute(k_sad_fs<160, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G.total);
       if (e != cudaSuccess) return e;
-      configured160 = G.total;
+      configured160[dev] = G.total;
     }
     const int grid = min((a.nitems + 1) / 2, sm_count);
     k_sad_fs<160, 12, 1><<<grid, G.threads, G.total, s>>>(tm, a);
