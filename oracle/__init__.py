@@ -533,6 +533,22 @@ class JMQuantRef:
         return level[:, :m].astype(np.int16), run[:, :m].astype(np.uint8), recon, cost, nz.astype(np.uint8)
 
 
+def have_v1tq():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libv1tq.so"))
+
+
+def v1_dct_luma(qp, slice_type, orig, pred):
+    """The UNMODIFIED version1 dct_luma (V1/src/block.c:836-1045) behind oracle/v1_harness_tq.c on [nblk][16] raster blocks:
+    level, run, recon, cost, nonzero in the layout of tq()."""
+    L = _load(os.path.join(_HERE, "_ref", "libv1tq.so"))
+    orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+    nblk = orig.shape[0]
+    level = np.zeros((nblk, 16), np.int32); run = np.zeros((nblk, 16), np.int32)
+    recon = np.zeros((nblk, 16), np.uint8); cost = np.zeros(nblk, np.int32); nz = np.zeros(nblk, np.int32)
+    L.v1tq_dct_luma(C.c_int(qp), C.c_int(slice_type), C.c_int(nblk), _ptr(orig), _ptr(pred), _ptr(level), _ptr(run), _ptr(recon), _ptr(cost), _ptr(nz))
+    return level.astype(np.int16), run.astype(np.uint8), recon, cost, nz.astype(np.uint8)
+
+
 # ---- fractal pool matching (oracle/b2_oracle_pool.c: DEFINES the pool-mode semantics, see its header) ----
 def pool_positions(dw, dh, nd):
     xy = np.zeros((nd, 2), np.int32)
@@ -562,6 +578,18 @@ def pool_rms_double(r64, d64):
     r = np.ascontiguousarray(r64, np.uint8); d = np.ascontiguousarray(d64, np.uint8)
     rms = L.orc_pool_rms_double(_ptr(r), _ptr(d), C.byref(al), C.byref(be))
     return rms, al.value, be.value
+
+
+def pool_pair(r64, d64):
+    """orc_pool_pair: the exact integer fit of one (range, domain) pair -> (accepted, aq, G, beta, err_num)"""
+    L = orc_lib()
+    r = np.ascontiguousarray(r64, np.uint8).reshape(64); d = np.ascontiguousarray(d64, np.uint8).reshape(64)
+    aq, G = C.c_int(), C.c_int64()
+    ok = L.orc_pool_pair(_ptr(r), _ptr(d), C.byref(aq), C.byref(G))
+    sr = int(r.astype(np.int64).sum()); sr2 = int((r.astype(np.int64) ** 2).sum())
+    beta = int(L.orc_pool_quan_a(C.c_int(sr // 64)))
+    err = 640000 * (sr2 - 2 * beta * sr + 64 * beta * beta) - G.value if ok else -1
+    return bool(ok), aq.value, G.value if ok else None, beta, err
 
 
 def pool_search(range_plane, domain_plane, nd):

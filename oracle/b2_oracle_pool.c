@@ -32,6 +32,8 @@ static int quan_a_pool(int x)
   return c * 10 + b;
 }
 
+int orc_pool_quan_a(int x) { return quan_a_pool(x); }
+
 /* pixel (i row, j col) of isometry `iso` of block src[8][8] */
 static int iso_src_index(int iso, int i, int j)
 {
