@@ -246,6 +246,111 @@ def fractal_leg(device, with_cpu):
     return res
 
 
+def bands_leg(local, rank, world, steps=5):
+    """BASELINE config 4 (secondary line, every rank takes part): ONE 3840x2160 picture, full search +-64, 1 reference, split into
+    `world` MB-row bands (h264_b200/bands.py).  Per picture, inside the timed region: halo exchange of the reconstructed
+    reference rows with the neighbouring bands (NCCL point-to-point), the sub-pel / search planes of the rows the band reads,
+    the search of the band (integer + sub-pel).  Strong scaling: the picture is fixed, the driver compares the N values."""
+    import torch
+    import torch.distributed as dist
+    from h264_b200 import api, bands, synth
+    dev = torch.device("cuda", local)
+    Wb, Hb, Rb = 3840, 2160, 64
+    fr = synth.luma_sequence(Wb, Hb, 2, seed=9)
+    nmb = (Wb // 16) * (Hb // 16)
+    pred, cen = synth.predictors(Wb, Hb, 1, seed=2, spread=0, base=np.tile(np.array([[[[8, 4]]]], np.int64), (nmb, 1, 1, 1)))
+    b = bands.BandSearcher(Wb, Hb, 1, Rb, rank, world, device=local, max_center_pel=16)
+    d_cur = torch.from_numpy(fr[1]).to(dev)
+    own = torch.from_numpy(fr[0][16 * b.first_row:16 * b.last_row]).to(dev).contiguous()
+    d_pred, d_cen = torch.from_numpy(pred).to(dev), torch.from_numpy(cen).to(dev)
+    mvi = torch.zeros((nmb, 1, 41, 2), dtype=torch.int16, device=dev); mvs = torch.zeros_like(mvi)
+    ci = torch.zeros((nmb, 1, 41), dtype=torch.int64, device=dev); cs = torch.zeros_like(ci)
+    params = api.make_params(LAMBDA)
+    stream = torch.cuda.current_stream().cuda_stream
+    b.set_cur_dev(d_cur, stream)
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        b.set_ref_from_band(0, own, stream)          # halo exchange (NCCL p2p) + planes of the rows this band reads
+        e[1].record()
+        b.search(d_pred, d_cen, params, mvi, ci, mvs, cs, stream, check=False)
+        e[2].record()
+        return e
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    b.search(d_pred, d_cen, params, mvi, ci, mvs, cs, stream, check=True)       # validates the centres against the halo once
+    for _ in range(3):
+        step()
+    barrier()
+    evs = []
+    for i in range(steps):
+        flush.fill_(i)
+        evs.append(step())
+    barrier()
+    t = torch.tensor([sum(e[0].elapsed_time(e[2]) for e in evs) / steps, sum(e[0].elapsed_time(e[1]) for e in evs) / steps],
+                     dtype=torch.float64, device=dev)
+    halo = sum((hi - lo) * Wb for s_, d_, lo, hi in bands.exchange_plan(world, Hb // 16, Rb) if d_ == rank)
+    hb = torch.tensor([halo], dtype=torch.int64, device=dev)
+    chk = mvs[b.mb_first:b.mb_first + b.mb_count].to(torch.int64).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(hb); dist.all_reduce(chk)
+    b.s.close()
+    pel = nmb * (2 * Rb + 1) ** 2 * 256
+    return {"workload": f"{Wb}x{Hb} single picture, full search +-{Rb} (SAD) + sub-pel SATD, 1 ref, {world} MB-row band(s), "
+                        f"halo exchange of the reconstructed reference per picture (NCCL point-to-point)",
+            "scaling": "strong", "ms_per_picture": float(t[0]), "value": pel / (float(t[0]) * 1e-3) / 1e6, "unit": UNIT,
+            "ms_halo_exchange_and_planes": float(t[1]), "halo_bytes_all_ranks": int(hb.item()),
+            "limiter": "the band's search; the exchange + plane rebuild share is ms_halo_exchange_and_planes / ms_per_picture",
+            "mv_checksum_all_bands": int(chk.item()), "l2": "192 MB L2 flush between timed pictures"}
+
+
+def pool_multi_leg(local, rank, world, nds=(16384, 65536), steps=4):
+    """BASELINE config 5 across ranks (secondary line, every rank takes part): the 1080p range plane split into `world` bands
+    of range-block rows, the domain plane replicated by ONE NCCL broadcast per picture (inside the timed region), each rank
+    building the pool operands and searching its band (h264_b200/pool_bands.py).  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from h264_b200 import pool_bands, synth
+    dev = torch.device("cuda", local)
+    Wp, Hp = 1920, 1080
+    fr = synth.luma_sequence(Wp, Hp, 2, seed=3)
+    rp = torch.from_numpy(fr[1]).to(dev)
+    dp = torch.from_numpy(fr[0]).to(dev) if rank == 0 else torch.zeros((Hp, Wp), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for nd in nds:
+        b = pool_bands.PoolBandSearcher(Wp, Hp, Wp, Hp, nd, rank, world, device=local)
+        res = (torch.zeros(b.nr, dtype=torch.int32, device=dev), torch.zeros(b.nr, dtype=torch.uint8, device=dev),
+               torch.zeros(b.nr, dtype=torch.int16, device=dev), torch.zeros(b.nr, dtype=torch.int16, device=dev),
+               torch.zeros(b.nr, dtype=torch.int64, device=dev))
+        for _ in range(3):
+            b.search_dev(rp, dp, res, stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        evs = []
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); b.search_dev(rp, dp, res, stream); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(c) for a, c in evs) / steps], dtype=torch.float64, device=dev)
+        chk = res[0].to(torch.int64).sum().reshape(1)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(chk)
+        ops = 2.0 * 8 * (Wp // 8) * (Hp // 8) * nd * 64
+        out[str(nd)] = {"ms_per_picture": float(t[0]), "Tops_useful": ops / (float(t[0]) * 1e-3) / 1e12, "best_dom_checksum": int(chk.item())}
+        b.close()
+    return {"workload": f"{Wp}x{Hp} range plane ({(Wp // 8) * (Hp // 8)} 8x8 ranges x 8 isometries) in {world} band(s) of range rows, domain "
+                        f"plane broadcast ({Wp * Hp} B, NCCL) + pool build + k_frac_pool per picture", "scaling": "strong", "pools": out}
+
+
 def _cpu_worker(job):
     """One process of the CPU reference arm: its own copy of the reference state, its own MB range."""
     first, cnt, trial = job
@@ -493,6 +598,7 @@ def main():
     for st in streams[1:]:
         st.ctx.close()
 
+    multi = {"bands_4k": bands_leg(local, rank, world), "pool_multi": pool_multi_leg(local, rank, world)}     # every rank takes part
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -517,6 +623,7 @@ def main():
     if os.path.exists(tr_path):
         roofline["traffic"] = json.load(open(tr_path)).get("k_sad_fs")
     secondary = {"fractal_pool": pool_leg(local, peaks), "fractal_window": fractal_leg(local, not args.no_cpu)}
+    secondary.update(multi)
     # the integer search alone under less friendly predictors / content (k_sad_fs is data-dependent)
     roofline["robustness"] = robustness_block(local, sad_peak_tpel)
     cpu = None if args.no_cpu else cpu_reference(15.0)

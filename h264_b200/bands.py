@@ -52,7 +52,7 @@ def exchange_plan(world, mbh, R, max_center_pel=16):
 def exchange_halos(own_band, H, W, R, max_center_pel=16, group=None, out=None):
     """own_band: uint8 [band rows, W] reconstructed luma of this rank's band (CUDA tensor with NCCL, CPU tensor with
     gloo).  Returns a [H, W] picture whose rows needed_rows(rank) are valid (the rest is zero)."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)     # one band: nothing to exchange
     mbh = H // 16
     f, l = band_mb_rows(rank, world, mbh)
     assert own_band.shape == (16 * (l - f), W) and own_band.dtype == torch.uint8
@@ -109,6 +109,15 @@ class BandSearcher:
             self.s.set_ref_dev(ref_idx, full, stream)
         return full
 
-    def search(self, pred, center, params, mv_int, cost_int, mv_sub, cost_sub, stream=0):
+    def search(self, pred, center, params, mv_int, cost_int, mv_sub, cost_sub, stream=0, check=True):
+        """check: refuse search centres beyond max_center_pel -- the halo was sized for that bound, a centre beyond it would
+        read rows that were never exchanged (one device reduction + host read per call; pass False once the caller has
+        validated its predictors)."""
+        if check and self.mb_count:
+            c = center[self.mb_first:self.mb_first + self.mb_count]
+            worst = int(c.abs().max().item()) if c.numel() else 0
+            if worst > 4 * self.max_center:
+                raise ValueError(f"BandSearcher: a search centre of {worst / 4:.2f} pel exceeds max_center_pel = {self.max_center}: "
+                                 f"the halo exchange covers R + {self.max_center} + 4 rows only")
         self.s.search_frame_dev(pred, center, params, mv_int, cost_int, mv_sub, cost_sub, stream,
                                 mb_first=self.mb_first, mb_count=self.mb_count)

@@ -64,3 +64,42 @@ def test_halo_exchange_gloo(world, H, R):
     for p in procs:
         p.join(timeout=60)
     assert res == [(r, True) for r in range(world)]
+
+
+# ---- fractal pool matching across ranks (h264_b200/pool_bands.py): range-row bands, replicated domain plane ----
+def test_range_bands_cover_the_picture():
+    from h264_b200 import pool_bands
+    for rows8 in (6, 36, 135, 270):
+        for world in (1, 2, 3, 4, 8):
+            rows = [pool_bands.range_band_rows(r, world, rows8) for r in range(world)]
+            assert rows[0][0] == 0 and rows[-1][1] == rows8
+            assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in rows) - min(b - a for a, b in rows) <= 1
+
+
+def _pool_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from h264_b200 import pool_bands
+        rng = np.random.default_rng(11)
+        plane = torch.from_numpy(rng.integers(0, 256, (48, 64), dtype=np.uint8))
+        mine = plane.clone() if rank == 1 else torch.zeros_like(plane)       # rank 1 owns the reconstructed picture
+        pool_bands.replicate_domain(mine, src=1)
+        q.put((rank, bool((mine == plane).all())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_domain_plane_is_replicated_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_pool_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

@@ -84,3 +84,69 @@ def test_pool_1080p_16k_sample_matches_oracle():
         assert (best[1], best[2], best[3]) == (dom[ri], iso[ri], aq[ri]), int(ri)
         Sr, Sr2 = int(r0.astype(np.int64).sum()), int((r0.astype(np.int64) ** 2).sum())
         assert err[ri] == 640000 * (Sr2 - 2 * int(beta[ri]) * Sr + 64 * int(beta[ri]) ** 2) - best[0]
+
+
+def test_4k_range64_sample_matches_oracle():
+    """BASELINE config 4's shape on one GPU: 3840x2160 (coded x2160), full search +-64, 1 reference.  Sampled macroblocks --
+    picture corners / borders and the first / last MB rows of the 8 bands of an 8-GPU split -- against the oracle, bit for bit;
+    window properties on every macroblock."""
+    from h264_b200 import bands
+    W, H, R = 3840, 2160, 64
+    fr = synth.luma_sequence(W, H, 2, seed=9)
+    nmb = (W // 16) * (H // 16)
+    base = np.tile(np.array([[[[8, 4]]]], np.int64), (nmb, 1, 1, 1))
+    pred, cen = synth.predictors(W, H, 1, seed=2, spread=3, base=base)
+    s = api.Searcher(W, H, 1, R)
+    s.set_cur(fr[1]); s.set_ref(0, fr[0])
+    lam = (187, 187, 187)
+    got = s.search_frame(pred, cen, api.make_params(lam))
+    d = got[0].astype(np.int32) - cen.astype(np.int32)
+    assert (np.abs(d) <= 4 * R).all() and (d % 4 == 0).all() and (got[1] > 0).all()
+    of = oracle.OrcFrame(fr[1], fr[[0]], R)
+    mbw, mbh = W // 16, H // 16
+    rows = sorted({0, mbh - 1} | {bands.band_mb_rows(r, 8, mbh)[0] for r in range(8)} | {bands.band_mb_rows(r, 8, mbh)[1] - 1 for r in range(8)})
+    rng = np.random.default_rng(4)
+    sample = sorted({0, mbw - 1, nmb - mbw, nmb - 1} | {int(r * mbw + rng.integers(0, mbw)) for r in rows})
+    for mb in sample:
+        exp = of.search_frame(pred, cen, lam, mb_first=int(mb), mb_count=1)
+        for a, b, n in zip(got, exp, ("mv_int", "cost_int", "mv_sub", "cost_sub")):
+            assert (a[mb] == b[mb]).all(), (n, int(mb))
+
+
+def test_band_searcher_refuses_centres_beyond_its_halo():
+    import torch
+    from h264_b200 import bands
+    W, H, R = 64, 96, 16
+    b = bands.BandSearcher(W, H, 1, R, 0, 2, max_center_pel=4)
+    nmb = (W // 16) * (H // 16)
+    cen = torch.zeros((nmb, 1, 41, 2), dtype=torch.int16, device="cuda")
+    cen[b.mb_first + 1, 0, 7, 1] = 4 * 5                       # 5 pel > max_center_pel
+    z = torch.zeros_like(cen); c64 = torch.zeros((nmb, 1, 41), dtype=torch.int64, device="cuda")
+    with pytest.raises(ValueError):
+        b.search(cen, cen, api.make_params((187, 187, 187)), z, c64, z.clone(), c64.clone())
+
+
+def test_pool_range_bands_equal_whole_picture():
+    """h264_b200/pool_bands.py's split: the range-row bands of 1, 2, 3 and 8 ranks, searched one after the other on this GPU against
+    the replicated domain plane, give the whole picture's result (the argmin is per range block)."""
+    import torch
+    from h264_b200 import pool_bands
+    W, H, nd = 176, 144, 700
+    (yr, _, _), (yc, _, _) = synth.yuv_pair(W, H, seed=8, shift=(2, -1), gain=0.9, offset=5.0)
+    whole = api.PoolSearcher(W, H, W, H, nd)
+    whole.set_planes(yc, yr)
+    exp = whole.search()
+    rp, dp = torch.from_numpy(yc).cuda(), torch.from_numpy(yr).cuda()
+    for world in (1, 2, 3, 8):
+        parts = []
+        for rank in range(world):
+            b = pool_bands.PoolBandSearcher(W, H, W, H, nd, rank, world)
+            out = (torch.zeros(b.nr, dtype=torch.int32, device="cuda"), torch.zeros(b.nr, dtype=torch.uint8, device="cuda"),
+                   torch.zeros(b.nr, dtype=torch.int16, device="cuda"), torch.zeros(b.nr, dtype=torch.int16, device="cuda"),
+                   torch.zeros(b.nr, dtype=torch.int64, device="cuda"))
+            b.search_dev(rp, dp, out)
+            torch.cuda.synchronize()
+            parts.append([t.cpu().numpy() for t in out])
+            b.close()
+        for k in range(5):
+            assert (np.concatenate([p[k] for p in parts]) == exp[k]).all(), (world, k)
