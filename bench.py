@@ -182,14 +182,18 @@ def pool_leg(device, peaks, nd=16384):
     st = s.stats()
     probe = min(s.probe_ms() for _ in range(3))
     ops = 2.0 * 8 * s.nr * nd * 64
-    peak = 2.0 * peaks["bf16_tflops"]
-    out = {"workload": f"{Wp}x{Hp} range plane: {s.nr} 8x8 ranges x 8 isometries vs {nd} pooled domain blocks (K = 64)",
+    peak = api.ubench_i8(4000, device=device)            # measured: dense tcgen05.mma kind::i8, resident operands, no epilogue
+    t = ms / n * 1e-3
+    out = {"workload": f"{Wp}x{Hp} range plane: {s.nr} 8x8 ranges x 8 isometries vs {nd} pooled domain blocks (K = 64 useful of 160 executed)",
            "kernel": "k_frac_pool (tcgen05.mma kind::i8 + fused least-squares fit / argmin epilogue)",
-           "kernel_ms": ms / n, "pairs_per_s": 8.0 * s.nr * nd / (ms / n * 1e-3),
-           "roofline": {"bound": "tensor", "achieved": ops / (ms / n * 1e-3) / 1e12, "peak": peak, "unit": "Tops (int8 dense)",
-                        "frac": ops / (ms / n * 1e-3) / 1e12 / peak, "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (nominal int8:bf16 ratio)",
+           "kernel_ms": ms / n, "pairs_per_s": 8.0 * s.nr * nd / t,
+           "roofline": {"bound": "tensor", "achieved": ops / t / 1e12, "peak": peak, "unit": "Tops (int8 dense)",
+                        "frac": ops / t / 1e12 / peak, "peak_source": "measured live: b2fp_ubench_i8 (tcgen05.mma kind::i8 M128 N256 K32 back to back on every SM)",
+                        "executed_frac": ops * 160 / 64 / t / 1e12 / peak,
                         "tensor_only_ms": probe, "tensor_only_Tops": ops / (probe * 1e-3) / 1e12,
-                        "note": "K = 64 per output: the per-output epilogue on the FP32/INT pipes, not the MMA, bounds this kernel (DESIGN.md 4)"},
+                        "note": "useful ops = 2*64 per (range-isometry, domain) pair; the contraction executes K = 160 (66 correction columns move the "
+                                "-Sr*Sd/64 term of the fit into the MMA so that the epilogue filters raw accumulators), executed_frac counts those; "
+                                "the per-output epilogue on the ALU pipe (32 three-input min/max per 32 outputs) and the re-examinations, not the MMA, bound the kernel (DESIGN.md 4.2)"},
            "exact_fits_per_row": st["exact_evals"] / (5 * 8 * s.nr), "best_dom_checksum": int(res[0].astype(np.int64).sum())}
     s.close()
     return out

@@ -72,6 +72,15 @@ def ubench(kind, iters=2000, device=0):
     return g.value
 
 
+def ubench_i8(iters=4000, device=0):
+    """measured dense tcgen05.mma kind::i8 rate in Tops (b2fp_ubench_i8)"""
+    t = C.c_double()
+    r = lib().b2fp_ubench_i8(C.c_int(device), C.c_int(iters), C.byref(t))
+    if r:
+        raise B2Error(f"b2fp_ubench_i8 failed: {r}")
+    return t.value
+
+
 class Searcher:
     """One b2me context: a coded picture size, nrefs reference pictures, SearchRange R."""
 

@@ -40,31 +40,40 @@
 namespace b2 {
 
 constexpr int FP_TM = 128;            // range rows (range x isometry) per CTA tile
-constexpr int FP_TN = 256;            // domains per MMA tile
-constexpr int FP_BSTAGES = 4;         // B-tile ring in shared memory
-constexpr int FP_CSTAGES = 4;         // per-tile constants ring: a slot is reused only after the EPILOGUE of its tile
+#ifndef FP_TN_V
+#define FP_TN_V 256
+#endif
+constexpr int FP_TN = FP_TN_V;        // domains per MMA tile
+constexpr int FP_TSTAGES = 512 / FP_TN;   // accumulator stages in TMEM (512 columns).  Measured: 128-column tiles (four stages) halve the MMA rate
+                                          // (tensor-only pass 0.71 ms against 0.36 ms at 16 K domains): two stages of 256 columns
+constexpr int FP_K = 160;             // contraction length: 64 pixels + 66 correction columns (see the header), padded to 5 K steps of 32
+constexpr int FP_KCH = FP_K / 16;     // 16-byte k-chunks per row
+constexpr int FP_KSTEPS = FP_K / 32;  // tcgen05.mma kind::i8 instructions per tile
+constexpr int FP_ABYTES = FP_TM * FP_K;   // 20480: one A tile
+constexpr int FP_BBYTES = FP_TN * FP_K;   // 40960: one B tile
+constexpr int FP_BSTAGES = 3 * 256 / FP_TN;   // B-tile ring in shared memory (120 KB)
 #ifndef FP_SPARSE_V
 #define FP_SPARSE_V 2
 #endif
 constexpr int FP_SPARSE = FP_SPARSE_V;          // rows of a warp passing a chunk's filter: up to this many are re-examined warp-across-columns
 constexpr int FP_CHUNK = 32;          // epilogue column chunk
-constexpr uint32_t FP_MAGIC = 0x4B000000u;   // float 2^23
-constexpr int FP_CT_BYTES = 3104;     // per-tile constants: float Sd[256] | int det[256] | float wcol[256] | float wchunk[8]
+constexpr int FP_SCR_WORDS = 32 * 33; // per-warp scratch: one parked chunk, [column][row] with a pad word per column
 #ifndef FP_GROUPS_V
 #define FP_GROUPS_V 3
 #endif
 constexpr int FP_EPI_GROUPS = FP_GROUPS_V;      // epilogue warp groups (4 warps each, one per TMEM lane quarter); group g takes chunks ch % groups == g
 constexpr int FP_EPI_WARPS = 4 * FP_EPI_GROUPS;
-#ifndef FP_PF_MAXG
-#define FP_PF_MAXG 2                  // largest group count that still double-buffers a chunk in registers (measured: 3 groups without beat 3 with)
+#ifndef FP_PREFETCH_V
+#define FP_PREFETCH_V 0
 #endif
+constexpr bool FP_PREFETCH = FP_PREFETCH_V != 0;   // double-buffer a chunk of accumulators in registers (measured: 127 instead of 106 registers, 1.22 against 1.12 ms at 16 K)
 constexpr int FP_THREADS = 128 + 32 * FP_EPI_WARPS;   // warp 0 producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4.. epilogue
 
 struct FpArgs {
-  const uint8_t *A;       // [mtiles][8192] range rows, core-matrix order
-  const uint8_t *B;       // [ntiles][16384] domains (sorted by det), core-matrix order
-  const uint8_t *ctile;   // [ntiles][FP_CT_BYTES] per-tile constants of the sorted domains: float Sd[256] | int det[256]
-                          //   (padding entries: -1) | float wchunk[8] = 10000*4096/detmin of each 32-column chunk
+  const uint8_t *A;       // [mtiles][FP_ABYTES] range rows, core-matrix order
+  const uint8_t *B;       // [ntiles][FP_BBYTES] domains (sorted by det), core-matrix order
+  const float *wchunk;    // [ntiles*8] 10000*4096/detmin of each 32-column chunk (0: only padding columns)
+  const float *dchunk;    // [ntiles*8] 160000*detmin of each chunk
   const int *sd;          // [ntiles*256] Sd (int)
   const int *det;         // [ntiles*256] det (int); padding entries: -1
   const int *orig;        // [ntiles*256] original pool index; padding: 0x7fffffff
@@ -74,7 +83,7 @@ struct FpArgs {
   int mtiles, ntiles, nranges, nd;
   int *best_dom; unsigned char *best_iso; short *aq; short *beta; long long *err_num;
   unsigned long long *stats;   // [0] exact evaluations, [1] chunk rescans, [2] chunks
-  int probe;              // 1: tensor-only probe (no epilogue math), see b2fp_ubench_i8
+  int probe;              // 1: tensor-only probe (no epilogue math), 2: filter arithmetic only
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -109,11 +118,11 @@ __device__ __forceinline__ void fp_bulk_g2s(void *dst, const void *src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(fp_smem(dst)), "l"(src), "r"(bytes), "r"(fp_smem(bar)) : "memory");
 }
-// K-major, no swizzle: LBO = 128 B between the two 16-byte k-chunks of an instruction, SBO = 512 B between 8-row groups
+// K-major, no swizzle: LBO = 128 B between the two 16-byte k-chunks of an instruction, SBO = FP_KCH * 128 B between 8-row groups
 __device__ __forceinline__ uint64_t fp_smem_desc(const void *p)
 {
   const uint64_t a = (uint64_t)((fp_smem(p) & 0x3ffffu) >> 4);
-  return a | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
+  return a | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((FP_KCH * 128) >> 4) << 32) | (1ull << 46);
 }
 // kind::i8, u8 x u8 -> s32, K-major A and B, M = 128, N = 256
 constexpr uint32_t FP_IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(FP_TN >> 3) << 17) | ((uint32_t)(FP_TM >> 4) << 24);
@@ -147,25 +156,6 @@ __device__ __forceinline__ void fp_tmem_ld32_nowait(uint32_t taddr, uint32_t (&v
                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                : "r"(taddr) : "memory");
 }
-// Re-arms 32 accumulator columns with the magic constant: eight x4 stores from FOUR registers that the caller keeps
-// live (opaque to the compiler, see fp_magic4), instead of one x32 store whose 32 source registers would have to be
-// re-materialised for every chunk (they cannot stay allocated next to the chunk's 64 live values).
-struct FpMagic4 { uint32_t a, b, c, d; };
-__device__ __forceinline__ FpMagic4 fp_magic4()
-{
-  FpMagic4 m;
-  asm volatile("mov.u32 %0, 0x4B000000;\n\tmov.u32 %1, 0x4B000000;\n\tmov.u32 %2, 0x4B000000;\n\tmov.u32 %3, 0x4B000000;"
-               : "=r"(m.a), "=r"(m.b), "=r"(m.c), "=r"(m.d));
-  return m;
-}
-__device__ __forceinline__ void fp_tmem_st32_const(uint32_t taddr, const FpMagic4 &m)
-{
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 ::"r"(taddr + 4 * i), "r"(m.a), "r"(m.b), "r"(m.c), "r"(m.d) : "memory");
-}
-
 __host__ __device__ __forceinline__ int fp_quan_a(int x)
 {
   int b = x % 10, c = x / 10;
@@ -178,8 +168,7 @@ __host__ __device__ __forceinline__ int fp_quan_a(int x)
 struct FpSmem {
   unsigned long long b_full[FP_BSTAGES], b_empty[FP_BSTAGES];
   unsigned long long a_full[2], a_empty[2];
-  unsigned long long t_full[2], t_empty[2];
-  unsigned long long c_empty[FP_CSTAGES];
+  unsigned long long t_full[FP_TSTAGES], t_empty[FP_TSTAGES];
   uint32_t tmem_base;
   long long mG[FP_EPI_GROUPS - 1][FP_TM]; int mIdx[FP_EPI_GROUPS - 1][FP_TM]; short mAq[FP_EPI_GROUPS - 1][FP_TM];   // per-row partial results of epilogue group 1, merged by group 0
   float shareT[FP_EPI_GROUPS][FP_TM];                        // per-row thresholds exchanged between the groups once per tile
@@ -197,24 +186,51 @@ __device__ __forceinline__ void fp_fold(const int *__restrict__ orig, long long 
   if (idx < bestIdx) { bestPos = pos; bestIdx = idx; bestAq = aq; }
 }
 
+// a = trunc(100 * num / det) quantised by QUAN_A, or a value outside [-235, 400] when it cannot fall inside: the quotient is
+// estimated in float (relative error < 2^-22), anything beyond +-1000 is rejected at once, the rest is made exact with one 64-bit
+// multiply and at most two corrections -- no FP64 (the B200's double rate made the division the most expensive step of a fit).
+__device__ __forceinline__ int fp_fit_aq(int num, int det)
+{
+  if (det == 0) return 0;
+  const float qf = (100.0f * (float)num) / (float)det;
+  if (!(fabsf(qf) < 1000.0f)) return 100000;
+  const long long n = 100ll * (long long)(num < 0 ? -num : num);           // |100 num| < 2^35
+  long long q = (long long)fabsf(qf);
+  long long r = n - q * det;
+  while (r < 0) { q--; r += det; }
+  while (r >= det) { q++; r -= det; }
+  return fp_quan_a(num < 0 ? -(int)q : (int)q);                             // C truncation toward zero, like the (int) cast
+}
+
+// upper bound of G for |num| <= 64 x and this det (w = 40960000 / det): the unquantised optimum, or the limit MAX_ALPHA where the optimum lies beyond it
+__device__ __forceinline__ float fp_gbound(float x, float w, int det)
+{
+  return x * w * (1.0f / 6400.0f) <= 400.0f ? (x * x) * w : 5120000.0f * x - 160000.0f * (float)det;
+}
+
+// Exact integer numerator of the fit from a raw accumulator of the extended contraction (see the header):
+//   acc = sum r d + 64 Mr Md' + Mr Fd' + Fr Md',   Mr = Sr >> 6, Fr = Sr & 63, Md' = 255 - (Sd >> 6), Fd' = 63 - (Sd & 63)
+__device__ __forceinline__ int fp_num(uint32_t acc, int sr, int sd)
+{
+  const int Mr = sr >> 6, Fr = sr & 63, Mdp = 255 - (sd >> 6), Fdp = 63 - (sd & 63);
+  const int srd = (int)acc - (64 * Mr * Mdp + Mr * Fdp + Fr * Mdp);
+  return 64 * srd - sr * sd;
+}
+
 __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_constant__ FpArgs a)
 {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // carve: A[2][8192] | B[FP_BSTAGES][16384] | constants[FP_BSTAGES][FP_CT_BYTES] | control
+  // carve: A[2][FP_ABYTES] | B[FP_BSTAGES][FP_BBYTES] | re-examination scratch | control
   uint8_t *sA = smem;
-  uint8_t *sB = smem + 2 * 8192;
-  uint8_t *sCt = sB + FP_BSTAGES * 16384;
-  uint32_t *sScr = reinterpret_cast<uint32_t *>(sCt + FP_CSTAGES * FP_CT_BYTES);     // [FP_EPI_WARPS][32 columns][32 lanes] re-examination scratch
-  FpSmem *S = reinterpret_cast<FpSmem *>(reinterpret_cast<uint8_t *>(sScr) + FP_EPI_WARPS * 4096);
+  uint8_t *sB = smem + 2 * FP_ABYTES;
+  uint32_t *sScr = reinterpret_cast<uint32_t *>(sB + FP_BSTAGES * FP_BBYTES);     // [FP_EPI_WARPS][32 columns][32 lanes]
+  FpSmem *S = reinterpret_cast<FpSmem *>(reinterpret_cast<uint8_t *>(sScr) + FP_EPI_WARPS * FP_SCR_WORDS * 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < FP_BSTAGES; i++) { fp_mbar_init(&S->b_full[i], 1); fp_mbar_init(&S->b_empty[i], 1); }
-    for (int i = 0; i < 2; i++) {
-      fp_mbar_init(&S->a_full[i], 1); fp_mbar_init(&S->a_empty[i], 1);
-      fp_mbar_init(&S->t_full[i], 1); fp_mbar_init(&S->t_empty[i], FP_EPI_WARPS);
-    }
-    for (int i = 0; i < FP_CSTAGES; i++) fp_mbar_init(&S->c_empty[i], FP_EPI_WARPS);
+    for (int i = 0; i < 2; i++) { fp_mbar_init(&S->a_full[i], 1); fp_mbar_init(&S->a_empty[i], 1); }
+    for (int i = 0; i < FP_TSTAGES; i++) { fp_mbar_init(&S->t_full[i], 1); fp_mbar_init(&S->t_empty[i], FP_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {                                  // TMEM: all 512 columns (two 256-column accumulator stages)
@@ -228,40 +244,38 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
 
   const int nmt = (a.mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // M tiles of this CTA
   if (warp == 0) {
-    // ===== producer: A tile per M tile, B tiles (+ their Sd floats) through the ring =====
+    // ===== producer: A tile per M tile, B tiles through the ring (one bulk copy each: the tiles are contiguous in HBM) =====
     if (lane == 0) {
       uint32_t it = 0;
       for (int i = 0; i < nmt; i++) {
         const int mt = (int)blockIdx.x + i * (int)gridDim.x;
         const int ab = i & 1;
         fp_mbar_wait_sleep(&S->a_empty[ab], ((i >> 1) & 1) ^ 1);
-        fp_mbar_expect_tx(&S->a_full[ab], 8192);
-        fp_bulk_g2s(sA + ab * 8192, a.A + (size_t)mt * 8192, 8192, &S->a_full[ab]);
+        fp_mbar_expect_tx(&S->a_full[ab], FP_ABYTES);
+        fp_bulk_g2s(sA + ab * FP_ABYTES, a.A + (size_t)mt * FP_ABYTES, FP_ABYTES, &S->a_full[ab]);
         for (int nt = 0; nt < a.ntiles; nt++, it++) {
-          const int st = it % FP_BSTAGES, cs = it % FP_CSTAGES;
+          const int st = it % FP_BSTAGES;
           fp_mbar_wait_sleep(&S->b_empty[st], ((it / FP_BSTAGES) & 1) ^ 1);
-          fp_mbar_wait_sleep(&S->c_empty[cs], ((it / FP_CSTAGES) & 1) ^ 1);
-          fp_mbar_expect_tx(&S->b_full[st], 16384 + FP_CT_BYTES);
-          fp_bulk_g2s(sB + st * 16384, a.B + (size_t)nt * 16384, 16384, &S->b_full[st]);
-          fp_bulk_g2s(sCt + cs * FP_CT_BYTES, a.ctile + (size_t)nt * FP_CT_BYTES, FP_CT_BYTES, &S->b_full[st]);
+          fp_mbar_expect_tx(&S->b_full[st], FP_BBYTES);
+          fp_bulk_g2s(sB + st * FP_BBYTES, a.B + (size_t)(a.ntiles - 1 - nt) * FP_BBYTES, FP_BBYTES, &S->b_full[st]);   // descending det: see the epilogue
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: D[stage] (pre-loaded with the magic constant) += A x B^T, two K = 32 steps =====
+    // ===== MMA issuer: D[stage] = A x B^T, five K = 32 steps, the first one overwrites the stage =====
     if (lane == 0) {
       uint32_t it = 0;
       for (int i = 0; i < nmt; i++) {
         const int ab = i & 1;
         fp_mbar_wait_sleep(&S->a_full[ab], (i >> 1) & 1);
         for (int nt = 0; nt < a.ntiles; nt++, it++) {
-          const int st = it % FP_BSTAGES, ts = it & 1;
-          fp_mbar_wait_sleep(&S->t_empty[ts], (it >> 1) & 1);      // phase 0 = the epilogue's initial arming of the stage
+          const int st = it % FP_BSTAGES, ts = it % FP_TSTAGES;
+          fp_mbar_wait_sleep(&S->t_empty[ts], (it / FP_TSTAGES) & 1);      // phase 0 = the epilogue's initial release of the stage
           fp_mbar_wait_sleep(&S->b_full[st], (it / FP_BSTAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t ad = fp_smem_desc(sA + ab * 8192), bd = fp_smem_desc(sB + st * 16384);
-          fp_mma_i8(tmem + ts * FP_TN, ad, bd, 1u);
-          fp_mma_i8(tmem + ts * FP_TN, ad + (256 >> 4), bd + (256 >> 4), 1u);
+          const uint64_t ad = fp_smem_desc(sA + ab * FP_ABYTES), bd = fp_smem_desc(sB + st * FP_BBYTES);
+#pragma unroll
+          for (int k = 0; k < FP_KSTEPS; k++) fp_mma_i8(tmem + ts * FP_TN, ad + (uint64_t)(k * (256 >> 4)), bd + (uint64_t)(k * (256 >> 4)), k ? 1u : 0u);
           fp_commit(&S->b_empty[st]);               // the ring slot is free once these MMAs have read it
           fp_commit(&S->t_full[ts]);                // ... and the accumulator stage is complete
         }
@@ -273,21 +287,15 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
     //       group grp = (warp-4)>>2 takes the 32-column chunks with ch % FP_EPI_GROUPS == grp =====
     const int q = warp & 3, grp = (warp - 4) >> 2;
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
-    const FpMagic4 magic = fp_magic4();
-    for (int c0 = grp * 32; c0 < 512; c0 += 32 * FP_EPI_GROUPS) fp_tmem_st32_const(tl + c0, magic);
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) { fp_mbar_arrive(&S->t_empty[0]); fp_mbar_arrive(&S->t_empty[1]); }
+    if (lane == 0) { for (int i = 0; i < FP_TSTAGES; i++) fp_mbar_arrive(&S->t_empty[i]); }
     // thresholds published to the other groups: reset here and between the two barriers that end an M tile, so that no
     // group can read a value of the previous tile's rows
     S->shareT[grp][q * 32 + lane] = -1.0f;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * FP_EPI_WARPS) : "memory");
     unsigned long long n_exact = 0, n_rescan = 0, n_chunk = 0;
     uint32_t it = 0;
-    constexpr int NCHT = FP_TN / FP_CHUNK;                     // chunks per tile; group g takes ch = g, g + groups, ...
+    constexpr int NCHT = FP_TN / FP_CHUNK;                     // chunks per tile; group g takes ch = g', g' + groups, ... (g' rotates with the tile when the chunks do not divide evenly)
     constexpr int NCH = (NCHT + FP_EPI_GROUPS - 1) / FP_EPI_GROUPS;
-    constexpr bool PF = FP_EPI_GROUPS <= FP_PF_MAXG;           // prefetch the next chunk's accumulators into a second register buffer
     for (int i = 0; i < nmt; i++) {
       const int mt = (int)blockIdx.x + i * (int)gridDim.x;
       const int rit = q * 32 + lane;                          // row in tile
@@ -295,177 +303,163 @@ __global__ void __launch_bounds__(FP_THREADS, 1) k_frac_pool(const __grid_consta
       const int rng = row >> 3;
       const bool rvalid = rng < a.nranges;
       const int sr = rvalid ? a.sr[rng] : 0;
-      const float nfr = -(float)sr * (1.0f / 64.0f);          // exact: sr < 2^14
+      // acc - rowc = num/64 + eps, 0 <= eps < 63  (eps = Fr * Fd / 64): the filter bounds |num/64| from the raw accumulators
+      const int rowc = (64 * 255 + 63) * (sr >> 6) + 255 * (sr & 63);
       // running best of the row: position in the (sorted) pool; its ORIGINAL index (the tie-break key) is fetched from
       // global memory only when a tie needs it (-1 = not fetched yet), which keeps that latency out of the re-examinations
       long long bestG = -1; int bestPos = -1, bestIdx = -1, bestAq = 0;
       float Tf = -1.0f;                                        // lower bound of the row's best G (either group's)
-      for (int nt = 0; nt < a.ntiles; nt++, it++) {
-        const int cs = it % FP_CSTAGES, ts = it & 1;
-        fp_mbar_wait(&S->t_full[ts], (it >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float *fdp = reinterpret_cast<const float *>(sCt + cs * FP_CT_BYTES);
-        const float *wcp = reinterpret_cast<const float *>(sCt + cs * FP_CT_BYTES + 2048);
-        const float *wp = reinterpret_cast<const float *>(sCt + cs * FP_CT_BYTES + 3072);
-        uint32_t vbuf[PF ? 2 : 1][32];
-        if (PF) fp_tmem_ld32_nowait(tl + ts * FP_TN + grp * FP_CHUNK, vbuf[0]);
+      // ---- deferred re-examination of ONE parked chunk (scr[column * 33 + row]) ----
+      uint32_t *scr = sScr + (warp - 4) * FP_SCR_WORDS;
+      int dk = -1, dcol = 0, ddet = 0, dsd = 0; uint32_t dpm = 0; float dw = 0.f, dd = 0.f;
+      auto rescan = [&]() {
+        uint32_t pm = dpm;
+        n_rescan++;
+        if (__popc(pm) <= FP_SPARSE) {
+          // few rows passed: one row at a time with the WARP across its 32 columns (rows pass rarely and independently: a lane
+          // walking its own 32 columns would idle the other 31).  Lane j takes column j: its own bound against the row's
+          // threshold, then the exact integer fit of the flagged columns in parallel; the row's owner folds the survivors
+          const int sdj = dsd, det = ddet;
+          const float wcj = det > 0 ? 40960000.0f / (float)det : 3.0e38f;
+          while (pm) {
+            const int r = __ffs(pm) - 1; pm &= pm - 1;
+            const uint32_t vj = scr[lane * 33 + r];
+            const float Tr = __shfl_sync(0xffffffffu, Tf, r);
+            const int srr = __shfl_sync(0xffffffffu, sr, r);
+            const int num = fp_num(vj, srr, sdj);
+            const float xj = fabsf((float)num) * (1.0f / 64.0f) + 1.0f;
+            const bool flag = det >= 0 && fp_gbound(xj, wcj, det) * 1.00001f >= Tr;     // det < 0: padding column
+            uint32_t cm = 0;
+            long long G = -1; int aq = 0;
+            if (__any_sync(0xffffffffu, flag)) {
+              const long long bG = __shfl_sync(0xffffffffu, bestG, r);
+              bool cand = false;
+              if (flag) {
+                n_exact++;
+                aq = fp_fit_aq(num, det);                         // exact integer fit (oracle/b2_oracle_pool.c orc_pool_pair)
+                if (aq >= -235 && aq <= 400) {
+                  G = 200ll * aq * num - (long long)aq * aq * det;
+                  cand = G >= bG;
+                }
+              }
+              cm = __ballot_sync(0xffffffffu, cand);
+            }
+            while (cm) {                                          // usually one column; first maximum in pool-index order
+              const int l = __ffs(cm) - 1; cm &= cm - 1;
+              const long long G2 = __shfl_sync(0xffffffffu, G, l);
+              const int aq2 = __shfl_sync(0xffffffffu, aq, l);
+              if (lane == r) fp_fold(a.orig, G2, dcol + l, aq2, bestG, bestPos, bestIdx, bestAq, Tf);
+            }
+          }
+        } else {
+          // many rows passed (the start of a sweep): every passing lane walks its own 32 columns (rolled: one copy of the fit)
+          const bool pass = (pm >> lane) & 1u;
+#pragma unroll 1
+          for (int j = 0; j < 32; j++) {
+            const int det = __shfl_sync(0xffffffffu, ddet, j), sdj = __shfl_sync(0xffffffffu, dsd, j);
+            if (!pass || det < 0) continue;                       // det < 0: padding column
+            const uint32_t vj = scr[j * 33 + lane];
+            {                                                     // raw-accumulator bound with the chunk's weight first
+              const float xb = (float)max((int)vj - rowc, rowc + 63 - (int)vj) + 1.0f;
+              if ((xb * dw * (1.0f / 6400.0f) <= 400.0f ? (xb * xb) * dw : 5120000.0f * xb - dd) * 1.00001f < Tf) continue;
+            }
+            const int num = fp_num(vj, sr, sdj);
+            const float xj = fabsf((float)num) * (1.0f / 64.0f) + 1.0f;
+            if (fp_gbound(xj, det > 0 ? 40960000.0f / (float)det : 3.0e38f, det) * 1.00001f < Tf) continue;     // against the row's CURRENT threshold
+            n_exact++;
+            const int aq = fp_fit_aq(num, det);
+            if (aq < -235 || aq > 400) continue;
+            const long long G = 200ll * aq * num - (long long)aq * aq * det;
+            if (G < bestG) continue;
+            fp_fold(a.orig, G, dcol + j, aq, bestG, bestPos, bestIdx, bestAq, Tf);
+          }
+        }
+        __syncwarp();
+        // Only the best of a range's 8 isometries is written, so its rows (8 consecutive lanes) share ONE threshold:
+        // a candidate below another isometry's best can never be the range's result (ties stay in: the tests are >=)
+        Tf = fmaxf(Tf, __shfl_xor_sync(0xffffffffu, Tf, 1));
+        Tf = fmaxf(Tf, __shfl_xor_sync(0xffffffffu, Tf, 2));
+        Tf = fmaxf(Tf, __shfl_xor_sync(0xffffffffu, Tf, 4));
+        if (FP_EPI_GROUPS > 1) S->shareT[grp][rit] = Tf;
+      };
+      for (int nti = 0; nti < a.ntiles; nti++, it++) {
+        // N tiles in DESCENDING det order: high-variance domains first.  They hold the good matches of textured ranges, so the
+        // rows' thresholds rise early; the low-variance tail can match only with |alpha| beyond the limits and is cut by the
+        // clamped bound below.
+        const int nt = a.ntiles - 1 - nti;
+        const int ts = it % FP_TSTAGES;
+        float wch[NCH], dch[NCH];                                        // the chunk weights of this tile (global, L1/L2-resident: 32 B per tile)
+        const int grot = NCHT % FP_EPI_GROUPS ? (int)((grp + it) % FP_EPI_GROUPS) : grp;
+#pragma unroll
+        for (int k = 0; k < NCH; k++) { const int ch = k * FP_EPI_GROUPS + grot; wch[k] = ch < NCHT ? __ldg(&a.wchunk[nt * NCHT + ch]) : 0.f; dch[k] = ch < NCHT ? __ldg(&a.dchunk[nt * NCHT + ch]) : 0.f; }
+        // the column constants of the warp's chunks, lane j <-> column j: fetched before the wait on the accumulator stage, so that
+        // a re-examination never waits on global memory (measured: with the loads inside the walk a dense chunk took ~10 k cycles)
+        int detc[NCH], sdc[NCH];
 #pragma unroll
         for (int k = 0; k < NCH; k++) {
-          const int ch = k * FP_EPI_GROUPS + grp;
-          if (NCHT % FP_EPI_GROUPS != 0 && ch >= NCHT) break;
-          uint32_t (&v)[32] = vbuf[PF ? (k & 1) : 0];
-          if (!PF) fp_tmem_ld32_nowait(tl + ts * FP_TN + ch * FP_CHUNK, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (PF && k + 1 < NCH && ch + FP_EPI_GROUPS < NCHT) fp_tmem_ld32_nowait(tl + ts * FP_TN + (ch + FP_EPI_GROUPS) * FP_CHUNK, vbuf[(k + 1) & 1]);   // next chunk in flight
-          fp_tmem_st32_const(tl + ts * FP_TN + ch * FP_CHUNK, magic);   // re-arm the accumulator
-          if (a.probe == 1) continue;
-          float g[32];
+          const int ch = k * FP_EPI_GROUPS + grot;
+          detc[k] = ch < NCHT ? __ldg(&a.det[nt * FP_TN + ch * FP_CHUNK + lane]) : -1;
+          sdc[k] = ch < NCHT ? __ldg(&a.sd[nt * FP_TN + ch * FP_CHUNK + lane]) : 0;
+        }
+        fp_mbar_wait(&S->t_full[ts], (it / FP_TSTAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // the next chunk's accumulators are in flight (tcgen05.ld) while the current chunk is filtered
+        uint32_t vbuf[FP_PREFETCH ? 2 : 1][32];
+        if (FP_PREFETCH) fp_tmem_ld32_nowait(tl + ts * FP_TN + grot * FP_CHUNK, vbuf[0]);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; j4++) {
-            const float4 f = reinterpret_cast<const float4 *>(fdp + ch * FP_CHUNK)[j4];
-            g[4 * j4 + 0] = fmaf(nfr, f.x, __uint_as_float(v[4 * j4 + 0]));
-            g[4 * j4 + 1] = fmaf(nfr, f.y, __uint_as_float(v[4 * j4 + 1]));
-            g[4 * j4 + 2] = fmaf(nfr, f.z, __uint_as_float(v[4 * j4 + 2]));
-            g[4 * j4 + 3] = fmaf(nfr, f.w, __uint_as_float(v[4 * j4 + 3]));
-          }
-          // all g are positive floats (2^23 + num/64, |num/64| < 2^22): their bit patterns order like integers;
-          // four independent max / min chains (one warp per scheduler: latency, not issue, is what counts)
+        for (int k = 0; k < NCH; k++) {
+          const int ch = k * FP_EPI_GROUPS + grot;
+          if (NCHT % FP_EPI_GROUPS != 0 && ch >= NCHT) break;
+          uint32_t (&v)[32] = vbuf[FP_PREFETCH ? (k & 1) : 0];
+          if (!FP_PREFETCH) fp_tmem_ld32_nowait(tl + ts * FP_TN + ch * FP_CHUNK, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (FP_PREFETCH && k + 1 < NCH && ch + FP_EPI_GROUPS < NCHT) fp_tmem_ld32_nowait(tl + ts * FP_TN + (ch + FP_EPI_GROUPS) * FP_CHUNK, vbuf[(k + 1) & 1]);
+          if (a.probe == 1) continue;
+          // raw accumulators are positive (< 2^23): integer 3-input max / min, four independent chains
           int mx[4], mn[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
-            mx[c] = __vimax3_s32(__float_as_int(g[8 * c]), __float_as_int(g[8 * c + 1]), __float_as_int(g[8 * c + 2]));
-            mn[c] = __vimin3_s32(__float_as_int(g[8 * c]), __float_as_int(g[8 * c + 1]), __float_as_int(g[8 * c + 2]));
-            mx[c] = __vimax3_s32(mx[c], __float_as_int(g[8 * c + 3]), __float_as_int(g[8 * c + 4]));
-            mn[c] = __vimin3_s32(mn[c], __float_as_int(g[8 * c + 3]), __float_as_int(g[8 * c + 4]));
-            mx[c] = __vimax3_s32(mx[c], __float_as_int(g[8 * c + 5]), __float_as_int(g[8 * c + 6]));
-            mn[c] = __vimin3_s32(mn[c], __float_as_int(g[8 * c + 5]), __float_as_int(g[8 * c + 6]));
-            mx[c] = max(mx[c], __float_as_int(g[8 * c + 7]));
-            mn[c] = min(mn[c], __float_as_int(g[8 * c + 7]));
+            mx[c] = __vimax3_s32((int)v[8 * c], (int)v[8 * c + 1], (int)v[8 * c + 2]);
+            mn[c] = __vimin3_s32((int)v[8 * c], (int)v[8 * c + 1], (int)v[8 * c + 2]);
+            mx[c] = __vimax3_s32(mx[c], (int)v[8 * c + 3], (int)v[8 * c + 4]);
+            mn[c] = __vimin3_s32(mn[c], (int)v[8 * c + 3], (int)v[8 * c + 4]);
+            mx[c] = __vimax3_s32(mx[c], (int)v[8 * c + 5], (int)v[8 * c + 6]);
+            mn[c] = __vimin3_s32(mn[c], (int)v[8 * c + 5], (int)v[8 * c + 6]);
+            mx[c] = max(mx[c], (int)v[8 * c + 7]);
+            mn[c] = min(mn[c], (int)v[8 * c + 7]);
           }
           const int mxa = max(__vimax3_s32(mx[0], mx[1], mx[2]), mx[3]), mna = min(__vimin3_s32(mn[0], mn[1], mn[2]), mn[3]);
-          const float X = fmaxf(__int_as_float(mxa) - 8388608.0f, 8388608.0f - __int_as_float(mna)) + 0.5f;
+          // |num/64| <= max(mx - rowc, rowc + 63 - mn)   (+1: float rounding of the conversion and of the product below)
+          const float X = (float)max(mxa - rowc, rowc + 63 - mna) + 1.0f;
           if (FP_EPI_GROUPS > 1) {
 #pragma unroll
             for (int o = 1; o < FP_EPI_GROUPS; o++) Tf = fmaxf(Tf, *reinterpret_cast<volatile float *>(&S->shareT[(grp + o) % FP_EPI_GROUPS][rit]));
           }
-          const bool pass = rvalid && a.probe != 2 && (X * X) * wp[ch] * 1.00001f >= Tf;     // probe 2: filter arithmetic only
+          // G = 200 aq num - aq^2 det <= 10000 num^2 / det at the unquantised optimum aq = 100 num / det; where that optimum lies
+          // beyond MAX_ALPHA (400) the best admissible aq is the limit itself: G <= 80000 |num| - 160000 det.  Both forms grow
+          // with |num| and shrink with det, so |num| <= 64 X and det >= detmin(chunk) bound every pair of the chunk.
+          const float gb = X * wch[k] * (1.0f / 6400.0f) <= 400.0f ? (X * X) * wch[k] : 5120000.0f * X - dch[k];
+          const bool pass = rvalid && a.probe != 2 && gb * 1.00001f >= Tf;     // probe 2: filter arithmetic only
           n_chunk++;
           uint32_t pm = __ballot_sync(0xffffffffu, pass);
-          const uint32_t pm0 = pm;
-          if (pm && __popc(pm) <= FP_SPARSE) {
-            // ---- few rows passed: re-examine the chunk one row at a time with the WARP across its 32 columns
-            //      (rows pass rarely and independently: a lane walking its own 32 columns would idle the other 31).
-            //      The row's accumulators cross through shared memory; lane j takes column j: its own bound
-            //      10000*num^2/det against the row's threshold, then the exact integer fit of the flagged columns in
-            //      parallel; the row's owner folds the survivors into its running best ----
-            n_rescan++;
-            uint32_t *scr = sScr + (warp - 4) * 1024;
-            const int *detp = reinterpret_cast<const int *>(sCt + cs * FP_CT_BYTES + 1024);
-            const int col = ch * FP_CHUNK + lane;
-            const float sdf = fdp[col], wcj = wcp[col];
-            const int det = detp[col];
-            while (pm) {
-              const int r = __ffs(pm) - 1; pm &= pm - 1;
-              if (lane == r) {
+          if (pm) {
+            // The chunk may hold a winner: its accumulators go to the warp's scratch ([column][row], padded) and are re-examined
+            // at once -- FP_DEFER: after the warp has released the accumulator stage instead (measured: no gain, the thresholds
+            // then rise one tile later and the two-stage TMEM pipeline absorbs only one tile of delay either way).
+            if (dk >= 0) { rescan(); dk = -1; }
 #pragma unroll
-                for (int j4 = 0; j4 < 8; j4++) reinterpret_cast<uint4 *>(scr)[j4] = make_uint4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-              }
-              __syncwarp();
-              const uint32_t vj = scr[lane];
-              const float Tr = __shfl_sync(0xffffffffu, Tf, r);
-              const int srr = __shfl_sync(0xffffffffu, sr, r);
-              const float gj = fmaf(-(float)srr * (1.0f / 64.0f), sdf, __uint_as_float(vj));
-              const float xj = fabsf(gj - 8388608.0f) + 0.5f;
-              const bool flag = det >= 0 && (xj * xj) * wcj * 1.00001f >= Tr;     // det < 0: padding column
-              uint32_t cm = 0;
-              long long G = -1; int aq = 0;
-              if (__any_sync(0xffffffffu, flag)) {
-                const long long bG = __shfl_sync(0xffffffffu, bestG, r);
-                bool cand = false;
-                if (flag) {
-                  n_exact++;
-                  // exact integer fit (oracle/b2_oracle_pool.c orc_pool_pair); the double quotient truncates like the
-                  // exact rational: a non-integer p/q with q < 2^29 is further than 2^-53 (relative) from an integer
-                  const int num = 64 * (int)(vj - FP_MAGIC) - srr * (int)sdf;
-                  const int qa = det == 0 ? 0 : (int)((100.0 * (double)num) / (double)det);
-                  aq = fp_quan_a(qa);
-                  if (aq >= -235 && aq <= 400) {
-                    G = 200ll * aq * num - (long long)aq * aq * det;
-                    cand = G >= bG;
-                  }
-                }
-                cm = __ballot_sync(0xffffffffu, cand);
-              }
-              while (cm) {                                        // usually one column; first maximum in pool-index order
-                const int l = __ffs(cm) - 1; cm &= cm - 1;
-                const long long G2 = __shfl_sync(0xffffffffu, G, l);
-                const int aq2 = __shfl_sync(0xffffffffu, aq, l);
-                if (lane == r) fp_fold(a.orig, G2, nt * FP_TN + ch * FP_CHUNK + l, aq2, bestG, bestPos, bestIdx, bestAq, Tf);
-              }
-              __syncwarp();
-            }
-          } else if (pm) {
-            // ---- re-examine the 32 columns.  Phase 1 (registers, branch-free): mask of the columns whose own
-            //      bound 10000*num^2/det reaches the row's threshold ----
-            n_rescan++;
-            uint32_t m = 0;
-            if (pass) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; j4++) {
-                const float4 wc = reinterpret_cast<const float4 *>(wcp + ch * FP_CHUNK)[j4];
-                const float x0 = fabsf(g[4 * j4 + 0] - 8388608.0f) + 0.5f, x1 = fabsf(g[4 * j4 + 1] - 8388608.0f) + 0.5f;
-                const float x2 = fabsf(g[4 * j4 + 2] - 8388608.0f) + 0.5f, x3 = fabsf(g[4 * j4 + 3] - 8388608.0f) + 0.5f;
-                m |= ((x0 * x0) * wc.x * 1.00001f >= Tf ? 1u : 0u) << (4 * j4 + 0);
-                m |= ((x1 * x1) * wc.y * 1.00001f >= Tf ? 1u : 0u) << (4 * j4 + 1);
-                m |= ((x2 * x2) * wc.z * 1.00001f >= Tf ? 1u : 0u) << (4 * j4 + 2);
-                m |= ((x3 * x3) * wc.w * 1.00001f >= Tf ? 1u : 0u) << (4 * j4 + 3);
-              }
-            }
-            if (__any_sync(0xffffffffu, m != 0)) {
-              // ---- phase 2: exact integer fit of the flagged columns; the accumulators go through shared memory so
-              //      that the loop is rolled (one copy of the fit) without dynamic register indexing ----
-              uint32_t *scr = sScr + (warp - 4) * 1024 + lane;
-#pragma unroll
-              for (int j = 0; j < 32; j++) scr[j * 32] = v[j];
-              __syncwarp();
-              const int *detp = reinterpret_cast<const int *>(sCt + cs * FP_CT_BYTES + 1024);
-              while (m) {
-                const int j = __ffs(m) - 1; m &= m - 1;
-                const int det = detp[ch * FP_CHUNK + j];
-                if (det < 0) continue;                            // padding column
-                const uint32_t vj = scr[j * 32];
-                const float sdf = fdp[ch * FP_CHUNK + j];
-                {                                                  // the row's threshold may have risen since the mask was formed
-                  const float xj = fabsf(fmaf(nfr, sdf, __uint_as_float(vj)) - 8388608.0f) + 0.5f;
-                  if ((xj * xj) * wcp[ch * FP_CHUNK + j] * 1.00001f < Tf) continue;
-                }
-                n_exact++;
-                // exact integer fit (oracle/b2_oracle_pool.c orc_pool_pair); the double quotient truncates like the
-                // exact rational: a non-integer p/q with q < 2^29 is further than 2^-53 (relative) from an integer
-                const int num = 64 * (int)(vj - FP_MAGIC) - sr * (int)sdf;
-                const int qa = det == 0 ? 0 : (int)((100.0 * (double)num) / (double)det);
-                const int aq = fp_quan_a(qa);
-                if (aq < -235 || aq > 400) continue;
-                const long long G = 200ll * aq * num - (long long)aq * aq * det;
-                if (G < bestG) continue;
-                fp_fold(a.orig, G, nt * FP_TN + ch * FP_CHUNK + j, aq, bestG, bestPos, bestIdx, bestAq, Tf);
-              }
-              __syncwarp();
-            }
-          }
-          if (pm0) {
-            // Only the best of a range's 8 isometries is written, so its rows (8 consecutive lanes) share ONE threshold:
-            // a candidate below another isometry's best can never be the range's result (ties stay in: the tests are >=)
-            Tf = fmaxf(Tf, __shfl_xor_sync(0xffffffffu, Tf, 1));
-            Tf = fmaxf(Tf, __shfl_xor_sync(0xffffffffu, Tf, 2));
-            Tf = fmaxf(Tf, __shfl_xor_sync(0xffffffffu, Tf, 4));
-            if (FP_EPI_GROUPS > 1) S->shareT[grp][rit] = Tf;
+            for (int j = 0; j < 32; j++) scr[j * 33 + lane] = v[j];
+            __syncwarp();
+            dk = k; dpm = pm; dcol = nt * FP_TN + ch * FP_CHUNK; dw = wch[k]; dd = dch[k]; ddet = detc[k]; dsd = sdc[k];
+#ifndef FP_DEFER
+            rescan(); dk = -1;
+#endif
           }
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) { fp_mbar_arrive(&S->t_empty[ts]); fp_mbar_arrive(&S->c_empty[cs]); }
+        if (lane == 0) fp_mbar_arrive(&S->t_empty[ts]);
+        if (dk >= 0) { rescan(); dk = -1; }
       }
       if (a.probe != 1) {
         if (bestIdx < 0) bestIdx = bestPos < 0 ? 0x7fffffff : a.orig[bestPos];
@@ -522,20 +516,40 @@ __device__ __forceinline__ int fp_iso_src(int iso, int i, int j)
     default: return (7 - j) * 8 + (7 - i);
   }
 }
-// byte offset of element (row, k) inside the core-matrix layout (rows counted from the start of the operand)
-__device__ __forceinline__ size_t fp_blk_off(int row, int k) { return (size_t)(row >> 3) * 512 + (size_t)(k >> 4) * 128 + (row & 7) * 16 + (k & 15); }
+// byte offset of element (row, k) inside the core-matrix layout (rows counted from the start of the operand): a tile of T rows
+// is [T/8 row groups][FP_KCH k-chunks][8 rows][16 bytes], tiles follow one another
+__device__ __forceinline__ size_t fp_blk_off(int row, int k) { return (size_t)(row >> 3) * (FP_KCH * 128) + (size_t)(k >> 4) * 128 + (row & 7) * 16 + (k & 15); }
 
-// one thread per (range, isometry) row: writes the 64 bytes of its A row; iso 0 also writes Sr, err base, beta
+// Extended rows (the -Sr*Sd/64 correction of the fit moved into the contraction, tests/test_pool_kext_model.py):
+//   A row = r[64] | Mr x 64 | Mr | Fr | 0...      B row = d[64] | Md' x 64 | Fd' | Md' | 0...
+//   Mr = Sr >> 6, Fr = Sr & 63, Md' = 255 - (Sd >> 6), Fd' = 63 - (Sd & 63)   (all u8)
+// so that  acc = sum r d + 64 Mr Md' + Mr Fd' + Fr Md' = num/64 + RowConst(r) + Fr Fd / 64,  RowConst = (64*255+63) Mr + 255 Fr.
+__device__ __forceinline__ void fp_write_row(uint8_t *base, int row, const uint8_t *px, int m, int f0, int f1)
+{
+  for (int k4 = 0; k4 < FP_K; k4 += 4) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int k = k4 + e;
+      const int v = k < 64 ? px[k] : (k < 128 ? m : (k == 128 ? f0 : (k == 129 ? f1 : 0)));
+      w |= (uint32_t)v << (8 * e);
+    }
+    *reinterpret_cast<uint32_t *>(base + fp_blk_off(row, k4)) = w;
+  }
+}
+
+// one thread per (range, isometry) row: writes the FP_K bytes of its A row; iso 0 also writes Sr, err base, beta
 __global__ void __launch_bounds__(256) k_fp_ranges(const uint8_t *__restrict__ plane, int stride, int rw, int nranges, int mrows,
                                                    uint8_t *__restrict__ A, int *__restrict__ sr, long long *__restrict__ ar, short *__restrict__ betaq)
 {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= mrows) return;
   const int rng = row >> 3, iso = row & 7;
-  uint8_t px[64];
+  uint8_t px[64], t[64];
+  int s = 0;
   if (rng < nranges) {
     const int bx = rng % (rw / 8), by = rng / (rw / 8);
-    int s = 0; long long s2 = 0;
+    long long s2 = 0;
     for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) { const int v = plane[(size_t)(by * 8 + i) * stride + bx * 8 + j]; px[i * 8 + j] = (uint8_t)v; s += v; s2 += v * v; }
     if (iso == 0) {
       const int beta = fp_quan_a(s / 64);
@@ -546,7 +560,8 @@ __global__ void __launch_bounds__(256) k_fp_ranges(const uint8_t *__restrict__ p
     for (int k = 0; k < 64; k++) px[k] = 0;
   }
   for (int i = 0; i < 8; i++)
-    for (int j = 0; j < 8; j++) A[fp_blk_off(row, i * 8 + j)] = px[fp_iso_src(iso, i, j)];
+    for (int j = 0; j < 8; j++) t[i * 8 + j] = px[fp_iso_src(iso, i, j)];
+  fp_write_row(A, row, t, s >> 6, s >> 6, s & 63);
 }
 
 // one thread per pool entry: 2x2-averaged 8x8 block -> tmp[p][64], det key
@@ -567,32 +582,79 @@ __global__ void __launch_bounds__(256) k_fp_domains(const uint8_t *__restrict__ 
   val[p] = p; sdv[p] = s;
 }
 
-// one thread per sorted column: core-matrix B rows + per-column constants; padding columns are inert
+// one thread per sorted column: core-matrix B row + per-column constants; padding columns are inert (Sd = 0: their
+// accumulators equal the row constant exactly, so they never raise a chunk's bound)
 __global__ void __launch_bounds__(256) k_fp_pack(const uint8_t *__restrict__ tmp, const unsigned *__restrict__ key_sorted, const int *__restrict__ val_sorted,
-                                                 const int *__restrict__ sdv, int nd, int ncols, uint8_t *__restrict__ B, uint8_t *__restrict__ ctile,
+                                                 const int *__restrict__ sdv, int nd, int ncols, uint8_t *__restrict__ B,
                                                  int *__restrict__ sd, int *__restrict__ det, int *__restrict__ orig)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncols) return;
-  float *fd = reinterpret_cast<float *>(ctile + (size_t)(c >> 8) * FP_CT_BYTES) + (c & 255);
-  int *dt = reinterpret_cast<int *>(ctile + (size_t)(c >> 8) * FP_CT_BYTES + 1024) + (c & 255);
-  float *wc = reinterpret_cast<float *>(ctile + (size_t)(c >> 8) * FP_CT_BYTES + 2048) + (c & 255);
+  uint8_t px[64];
+  int s = 0;
   if (c < nd) {
     const int p = val_sorted[c];
-    for (int k = 0; k < 64; k++) B[fp_blk_off(c, k)] = tmp[(size_t)p * 64 + k];
-    *fd = (float)sdv[p]; *dt = (int)key_sorted[c]; *wc = key_sorted[c] ? 40960000.0f / (float)key_sorted[c] : 3.0e38f; sd[c] = sdv[p]; det[c] = (int)key_sorted[c]; orig[c] = p;
+    for (int k = 0; k < 64; k++) px[k] = tmp[(size_t)p * 64 + k];
+    s = sdv[p];
+    sd[c] = s; det[c] = (int)key_sorted[c]; orig[c] = p;
   } else {
-    for (int k = 0; k < 64; k++) B[fp_blk_off(c, k)] = 0;
-    *fd = 0.f; *dt = -1; *wc = -1.0f; sd[c] = 0; det[c] = -1; orig[c] = 0x7fffffff;
+    for (int k = 0; k < 64; k++) px[k] = 0;
+    sd[c] = 0; det[c] = -1; orig[c] = 0x7fffffff;
   }
+  fp_write_row(B, c, px, 255 - (s >> 6), 63 - (s & 63), 255 - (s >> 6));
 }
-__global__ void __launch_bounds__(256) k_fp_wchunk(const int *__restrict__ det, int nchunks, uint8_t *__restrict__ ctile)
+__global__ void __launch_bounds__(256) k_fp_wchunk(const int *__restrict__ det, int nchunks, float *__restrict__ wchunk, float *__restrict__ dchunk)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nchunks) return;
   int mn = 0x7fffffff; bool any = false;
   for (int j = 0; j < FP_CHUNK; j++) { const int d = det[c * FP_CHUNK + j]; if (d >= 0) { any = true; mn = min(mn, d); } }
-  reinterpret_cast<float *>(ctile + (size_t)(c >> 3) * FP_CT_BYTES + 3072)[c & 7] = !any ? 0.f : (mn == 0 ? 3.0e38f : 40960000.0f / (float)mn);
+  wchunk[c] = !any ? 0.f : (mn == 0 ? 3.0e38f : 40960000.0f / (float)mn);
+  dchunk[c] = !any ? 3.0e38f : 160000.0f * (float)mn * 0.99999f;            // rounded down: the bound must not shrink
+}
+
+// ---- dense kind::i8 rate of the tensor pipe (the roofline denominator of k_frac_pool, measured live) ----------------------
+// One CTA per SM; one thread issues `iters` x 8 back-to-back tcgen05.mma kind::i8 (M 128, N 256, K 32, u8 x u8 -> s32) on
+// operands that stay in shared memory, accumulating into the two 256-column TMEM stages alternately; no loads, no epilogue.
+__global__ void __launch_bounds__(128, 1) k_i8_peak(int iters, uint32_t *out)
+{
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *sA = smem, *sB = smem + 4096;            // A: 128 rows x 32 B, B: 256 rows x 32 B, core-matrix order (2 k-chunks per row)
+  __shared__ unsigned long long bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (4096 + 8192) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01020304u * (uint32_t)(i & 63);
+  if (tid == 0) { fp_mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(fp_smem(&tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    // K-major, no swizzle, two 16-byte k-chunks per row: LBO 128 B, SBO 256 B
+    const uint64_t da = (uint64_t)((fp_smem(sA) & 0x3ffffu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+    const uint64_t db = (uint64_t)((fp_smem(sB) & 0x3ffffu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) fp_mma_i8(tmem + (u & 1) * 256, da, db, (it | u) > 1 ? 1u : 0u);
+    }
+    fp_commit(&bar);
+    fp_mbar_wait(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v[32];
+    fp_tmem_ld32(tmem, v);
+    if (out) out[blockIdx.x * 32 + (tid & 31)] = v[0] ^ v[31];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 }  // namespace b2
@@ -605,7 +667,7 @@ struct b2fp_ctx {
   uint8_t *d_rplane, *d_dplane, *d_A, *d_B, *d_tmp;
   int *d_xy, *d_val, *d_val_s, *d_sdv, *d_sd, *d_det, *d_orig, *d_sr;
   unsigned *d_key, *d_key_s;
-  uint8_t *d_ctile;
+  float *d_wchunk, *d_dchunk;
   long long *d_ar, *d_err; short *d_betaq, *d_aq, *d_beta; int *d_dom; unsigned char *d_iso;
   unsigned long long *d_stats;
   void *d_sort_tmp; size_t sort_bytes;
@@ -662,8 +724,8 @@ extern "C" int b2fp_create(b2fp_ctx **out, int device, int range_w, int range_h,
   FP_CHECK(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   FP_CHECK(c, cudaMalloc(&c->d_rplane, (size_t)range_w * range_h));
   FP_CHECK(c, cudaMalloc(&c->d_dplane, (size_t)domain_w * domain_h));
-  FP_CHECK(c, cudaMalloc(&c->d_A, (size_t)c->mtiles * 8192));
-  FP_CHECK(c, cudaMalloc(&c->d_B, (size_t)c->ntiles * 16384));
+  FP_CHECK(c, cudaMalloc(&c->d_A, (size_t)c->mtiles * FP_ABYTES));
+  FP_CHECK(c, cudaMalloc(&c->d_B, (size_t)c->ntiles * FP_BBYTES));
   FP_CHECK(c, cudaMalloc(&c->d_tmp, (size_t)pool_size * 64));
   FP_CHECK(c, cudaMalloc(&c->d_xy, (size_t)pool_size * 2 * sizeof(int)));
   FP_CHECK(c, cudaMalloc(&c->d_val, (size_t)pool_size * sizeof(int)));
@@ -671,8 +733,9 @@ extern "C" int b2fp_create(b2fp_ctx **out, int device, int range_w, int range_h,
   FP_CHECK(c, cudaMalloc(&c->d_key, (size_t)pool_size * sizeof(unsigned)));
   FP_CHECK(c, cudaMalloc(&c->d_key_s, (size_t)pool_size * sizeof(unsigned)));
   FP_CHECK(c, cudaMalloc(&c->d_sdv, (size_t)pool_size * sizeof(int)));
-  FP_CHECK(c, cudaMalloc(&c->d_ctile, (size_t)c->ntiles * FP_CT_BYTES));
-  FP_CHECK(c, cudaMemset(c->d_ctile, 0, (size_t)c->ntiles * FP_CT_BYTES));
+  FP_CHECK(c, cudaMalloc(&c->d_wchunk, (size_t)c->ntiles * 8 * sizeof(float)));
+  FP_CHECK(c, cudaMemset(c->d_wchunk, 0, (size_t)c->ntiles * 8 * sizeof(float)));
+  FP_CHECK(c, cudaMalloc(&c->d_dchunk, (size_t)c->ntiles * 8 * sizeof(float)));
   FP_CHECK(c, cudaMalloc(&c->d_sd, (size_t)c->ncols * sizeof(int)));
   FP_CHECK(c, cudaMalloc(&c->d_det, (size_t)c->ncols * sizeof(int)));
   FP_CHECK(c, cudaMalloc(&c->d_orig, (size_t)c->ncols * sizeof(int)));
@@ -704,7 +767,7 @@ extern "C" void b2fp_destroy(b2fp_ctx *c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->d_rplane); cudaFree(c->d_dplane); cudaFree(c->d_A); cudaFree(c->d_B); cudaFree(c->d_tmp); cudaFree(c->d_xy);
-  cudaFree(c->d_val); cudaFree(c->d_val_s); cudaFree(c->d_key); cudaFree(c->d_key_s); cudaFree(c->d_sdv); cudaFree(c->d_ctile);
+  cudaFree(c->d_val); cudaFree(c->d_val_s); cudaFree(c->d_key); cudaFree(c->d_key_s); cudaFree(c->d_sdv); cudaFree(c->d_wchunk); cudaFree(c->d_dchunk);
   cudaFree(c->d_sd); cudaFree(c->d_det); cudaFree(c->d_orig); cudaFree(c->d_sr); cudaFree(c->d_ar);
   cudaFree(c->d_betaq); cudaFree(c->d_dom); cudaFree(c->d_iso); cudaFree(c->d_aq); cudaFree(c->d_beta); cudaFree(c->d_err);
   cudaFree(c->d_stats); cudaFree(c->d_sort_tmp);
@@ -728,8 +791,8 @@ static int fp_prepare(b2fp_ctx *c, const uint8_t *rplane_dev, int rstride, const
   k_fp_domains<<<(c->nd + 255) / 256, 256, 0, s>>>(dplane_dev, dstride, c->d_xy, c->nd, c->d_tmp, c->d_key, c->d_val, c->d_sdv);
   FP_CHECK(c, cudaGetLastError());
   FP_CHECK(c, cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, c->sort_bytes, c->d_key, c->d_key_s, c->d_val, c->d_val_s, c->nd, 0, 32, s));
-  k_fp_pack<<<(c->ncols + 255) / 256, 256, 0, s>>>(c->d_tmp, c->d_key_s, c->d_val_s, c->d_sdv, c->nd, c->ncols, c->d_B, c->d_ctile, c->d_sd, c->d_det, c->d_orig);
-  k_fp_wchunk<<<(c->ncols / FP_CHUNK + 255) / 256, 256, 0, s>>>(c->d_det, c->ncols / FP_CHUNK, c->d_ctile);
+  k_fp_pack<<<(c->ncols + 255) / 256, 256, 0, s>>>(c->d_tmp, c->d_key_s, c->d_val_s, c->d_sdv, c->nd, c->ncols, c->d_B, c->d_sd, c->d_det, c->d_orig);
+  k_fp_wchunk<<<(c->ncols / FP_CHUNK + 255) / 256, 256, 0, s>>>(c->d_det, c->ncols / FP_CHUNK, c->d_wchunk, c->d_dchunk);
   FP_CHECK(c, cudaGetLastError());
   c->launches += 4;
   return B2ME_OK;
@@ -756,18 +819,18 @@ extern "C" int b2fp_set_planes(b2fp_ctx *c, const uint8_t *range_plane, int rstr
 static int fp_launch(b2fp_ctx *c, int probe, int32_t *dom, uint8_t *iso, int16_t *aq, int16_t *beta, int64_t *err, cudaStream_t s, int timed)
 {
   FpArgs a;
-  a.A = c->d_A; a.B = c->d_B; a.ctile = c->d_ctile; a.sd = c->d_sd; a.det = c->d_det; a.orig = c->d_orig;
+  a.A = c->d_A; a.B = c->d_B; a.wchunk = c->d_wchunk; a.dchunk = c->d_dchunk; a.sd = c->d_sd; a.det = c->d_det; a.orig = c->d_orig;
   a.sr = c->d_sr; a.ar = c->d_ar; a.betaq = c->d_betaq;
   a.mtiles = c->mtiles; a.ntiles = c->ntiles; a.nranges = c->nranges; a.nd = c->nd;
   a.best_dom = dom; a.best_iso = iso; a.aq = aq; a.beta = beta; a.err_num = (long long *)err;
   a.stats = c->d_stats; a.probe = probe;
-  const int smem = 2 * 8192 + FP_BSTAGES * 16384 + FP_CSTAGES * FP_CT_BYTES + FP_EPI_WARPS * 4096 + (int)sizeof(FpSmem) + 1024;
+  const int smem = 2 * FP_ABYTES + FP_BSTAGES * FP_BBYTES + FP_EPI_WARPS * FP_SCR_WORDS * 4 + (int)sizeof(FpSmem) + 1024;
   static int configured[64] = {0};                      // per device ordinal: the attribute belongs to the device's copy of the function
-  if (!configured[c->device & 63]) { FP_CHECK(c, cudaFuncSetAttribute(k_frac_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, smem < 160 * 1024 ? 160 * 1024 : smem)); configured[c->device & 63] = 1; }
+  if (!configured[c->device & 63]) { FP_CHECK(c, cudaFuncSetAttribute(k_frac_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured[c->device & 63] = 1; }
   const int grid = c->mtiles < c->sm_count ? c->mtiles : c->sm_count;
   if (timed) cudaEventRecord(c->ev0, s);
   // >= 116 KB of dynamic shared memory keeps ONE CTA per SM: each CTA allocates all 512 TMEM columns
-  k_frac_pool<<<grid, FP_THREADS, smem < 120 * 1024 ? 120 * 1024 : smem, s>>>(a);
+  k_frac_pool<<<grid, FP_THREADS, smem, s>>>(a);
   FP_CHECK(c, cudaGetLastError());
   if (timed) {
     cudaEventRecord(c->ev1, s); FP_CHECK(c, cudaEventSynchronize(c->ev1));
@@ -833,3 +896,32 @@ extern "C" int b2fp_stats(b2fp_ctx *c, int64_t out[3], int reset)
   return B2ME_OK;
 }
 extern "C" int64_t b2fp_launch_count(b2fp_ctx *c) { return c ? c->launches : 0; }
+
+// Measured dense tcgen05.mma kind::i8 rate of the whole chip in Tops (2 ops per multiply-accumulate): best of four launches.
+extern "C" int b2fp_ubench_i8(int device, int iters, double *tops)
+{
+  if (!tops || iters <= 0) return B2ME_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return B2ME_ECUDA;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  uint32_t *out = nullptr;
+  if (cudaMalloc(&out, (size_t)sms * 32 * sizeof(uint32_t)) != cudaSuccess) return B2ME_ENOMEM;
+  // 120 KB of dynamic shared memory: one CTA per SM (each allocates all 512 TMEM columns)
+  cudaError_t e = cudaFuncSetAttribute(k_i8_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4 && e == cudaSuccess; rep++) {
+    cudaEventRecord(e0);
+    k_i8_peak<<<sms, 128, 120 * 1024>>>(iters, out);
+    cudaEventRecord(e1);
+    e = cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  if (e != cudaSuccess) { snprintf(g_fperr, sizeof(g_fperr), "b2fp_ubench_i8: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
+  *tops = (double)sms * iters * 8.0 * 2.0 * 128.0 * 256.0 * 32.0 / (best * 1e-3) / 1e12;
+  return B2ME_OK;
+}

@@ -315,6 +315,10 @@ int b2fp_kernel_time_ms(b2fp_ctx *ctx, double *ms, int64_t *launches, int reset)
 int b2fp_probe(b2fp_ctx *ctx, double *ms);
 int b2fp_stats(b2fp_ctx *ctx, int64_t out[3], int reset);
 int64_t b2fp_launch_count(b2fp_ctx *ctx);
+/* Micro-benchmark: dense tcgen05.mma kind::i8 (u8 x u8 -> s32, M 128 x N 256 x K 32 per instruction) issued back to back on every
+ * SM from resident shared-memory operands, no epilogue: the measured int8 rate of the chip in Tops (2 ops per MAC) -- the
+ * roofline denominator bench.py uses for k_frac_pool (BASELINE.md section 4 asks for a measured figure). */
+int b2fp_ubench_i8(int device, int iters, double *tops);
 
 /* ==== residual transform + quantisation + reconstruction ================================= */
 /* Parameter block = the reference's per-(plane, intra, qp) LevelQuantParams table
