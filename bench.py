@@ -11,7 +11,7 @@ SAD-tree-algorithmic unit); MB/s is reported beside it.
 
   value : inputs already resident in HBM (device pointers through the C ABI's *_dev calls)
   e2e   : the same step through the host-pointer C ABI (b2me_set_cur / b2me_set_ref /
-          b2me_search_frame) with pinned HOST buffers, H2D + D2H inside the timed region; two independent
+          b2me_search_frame_best) with pinned HOST buffers, H2D + D2H inside the timed region; two independent
           segment streams per GPU (own context + host thread each), the single-stream figure beside it.
 
 Multi-GPU (torchrun, one rank per GPU): independent closed-GOP segments, i.e. every rank runs the
@@ -523,8 +523,9 @@ def main():
     k_ms_launch = k_ms / max(k_n, 1)
 
     # ---- e2e: host buffers through the host-pointer C ABI -----------------------------------
-    # Every step: b2me_set_cur + b2me_set_ref + b2me_search_frame on pinned HOST buffers, the refined vectors / costs back
-    # on the host on return (synchronous calls).  Measured twice: ONE frame stream per GPU, and E2E_STREAMS independent
+    # Every step: b2me_set_cur + b2me_set_ref + b2me_search_frame_best on pinned HOST buffers: the current picture, the newest
+    # reference and one predictor per (MB, ref) go up; what the mode decision consumes -- best reference and cost per (mode, block),
+    # the chosen refined vector of every partition -- is on the host on return (synchronous calls).  Measured twice: ONE frame stream per GPU, and E2E_STREAMS independent
     # closed-GOP segment streams per GPU (the north star's own partitioning: segments share no state), each with its own
     # context and host thread, so that one stream's copies run under the other's kernels.  The headline is the latter.
     import ctypes as C
@@ -534,22 +535,25 @@ def main():
     # this box would then outnumber its host cores (one synchronising host thread per stream)
     E2E_STREAMS = int(os.environ.get("B2ME_E2E_STREAMS", "3" if (os.cpu_count() or 1) >= 3 * world + 2 else "2"))
 
+    pred_mb_np = np.ascontiguousarray(pred_np[:, :, 0, :])         # the headline's predictors ARE one per (MB, ref)
+
     class Stream:
         def __init__(self, ctx):
             self.ctx = ctx
             self.h_cur = torch.from_numpy(fr[NREFS]).pin_memory()
             self.h_ref = [torch.from_numpy(fr[j]).pin_memory() for j in range(NREFS)]
-            self.h_pred = torch.from_numpy(pred_np).pin_memory(); self.h_cen = torch.from_numpy(cen_np).pin_memory()
-            self.h_mvs = torch.zeros((nmb, NREFS, 41, 2), dtype=torch.int16).pin_memory()
-            self.h_cs = torch.zeros((nmb, NREFS, 41), dtype=torch.int64).pin_memory()
+            self.h_pred = torch.from_numpy(pred_mb_np).pin_memory()
+            self.h_br = torch.zeros((nmb, 21), dtype=torch.int8).pin_memory()
+            self.h_bc = torch.zeros((nmb, 21), dtype=torch.int32).pin_memory()
+            self.h_mvs = torch.zeros((nmb, 41, 2), dtype=torch.int16).pin_memory()
 
         def step(self, i):
             h = self.ctx.h
             r = L.b2me_set_cur(h, C.c_void_p(self.h_cur.data_ptr()), C.c_int(W))
             r |= L.b2me_set_ref(h, C.c_int(i % NREFS), C.c_void_p(self.h_ref[NREFS - 1 - (i % NREFS)].data_ptr()), C.c_int(W))
-            r |= L.b2me_search_frame(h, C.c_void_p(self.h_pred.data_ptr()), C.c_void_p(self.h_cen.data_ptr()), C.byref(params),
-                                     None, None,                 # the caller consumes the refined vectors / costs only
-                                     C.c_void_p(self.h_mvs.data_ptr()), C.c_void_p(self.h_cs.data_ptr()))
+            # one predictor per (MB, ref) up; best reference / cost per (mode, block) and the chosen vectors down
+            r |= L.b2me_search_frame_best(h, C.c_void_p(self.h_pred.data_ptr()), C.byref(params), C.c_int(LAMBDA[2]),
+                                          C.c_void_p(self.h_br.data_ptr()), C.c_void_p(self.h_bc.data_ptr()), C.c_void_p(self.h_mvs.data_ptr()))
             if r:
                 raise RuntimeError(f"C ABI call failed: {L.b2me_last_error(h)}")
 
@@ -595,8 +599,8 @@ def main():
     dt1 = timed(streams[:1])
     dtS = timed(streams)
     e2e_value = world * pel_sp(nmb) / dtS / 1e6
-    h2d = 2 * W * H + 2 * n * 2 * 2
-    d2h = n * 2 * 2 + n * 8
+    h2d = 2 * W * H + nmb * NREFS * 2 * 2
+    d2h = nmb * 21 * (1 + 4) + nmb * 41 * 2 * 2
     checksum = int(streams[0].h_mvs.to(torch.int64).sum().item())           # the result really is on the host
     assert all(int(st.h_mvs.to(torch.int64).sum().item()) == checksum for st in streams)
     for st in streams[1:]:

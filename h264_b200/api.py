@@ -163,6 +163,15 @@ class Searcher:
                                            _p(mv_sub), _p(cost_sub)), "b2me_search_frame")
         return mv_int, cost_int, mv_sub, cost_sub
 
+    def search_frame_best(self, pred_mb, params, ref_lambda):
+        """b2me_search_frame_best: pred_mb [nmb][nrefs][2] -> best_ref [nmb][21] i8, best_cost [nmb][21] i32, best_mv [nmb][41][2] i16"""
+        pred_mb = np.ascontiguousarray(pred_mb, np.int16)
+        assert pred_mb.shape == (self.nmb, self.nrefs, 2)
+        br = np.zeros((self.nmb, 21), np.int8); bc = np.zeros((self.nmb, 21), np.int32); bm = np.zeros((self.nmb, NPART, 2), np.int16)
+        self._chk(self.L.b2me_search_frame_best(self.h, _p(pred_mb), C.byref(params), C.c_int(int(ref_lambda)), _p(br), _p(bc), _p(bm)),
+                  "b2me_search_frame_best")
+        return br, bc, bm
+
     def search_frame_dev(self, pred, center, params, mv_int, cost_int, mv_sub, cost_sub, stream=0,
                          mb_first=0, mb_count=None):
         """torch CUDA tensors in/out (device pointers), asynchronous on `stream`."""

@@ -108,6 +108,7 @@ extern "C" void b2me_destroy(b2me_ctx *c)
   cudaFree(c->d_cur); cudaFree(c->d_stage); cudaFree(c->d_planes); cudaFree(c->d_spl); cudaFree(c->d_tmap_spl);
   cudaFree(c->d_pred); cudaFree(c->d_center); cudaFree(c->d_mv_int); cudaFree(c->d_mv_sub);
   cudaFree(c->d_cost_int); cudaFree(c->d_cost_sub); cudaFree(c->d_io16); cudaFree(c->d_io64);
+  cudaFree(c->d_pred_mb); cudaFree(c->d_best_ref); cudaFree(c->d_best_cost); cudaFree(c->d_best_cost32); cudaFree(c->d_best_mv);
   cudaFreeHost(c->h_io16); cudaFreeHost(c->h_io64); cudaFree(c->d_errflag); cudaFree(c->d_work); cudaFree(c->d_stats);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
@@ -394,6 +395,39 @@ extern "C" int b2me_search_frame(b2me_ctx *c, const int16_t *pred, const int16_t
     }
   }
   B2_CUDA_CHECK(c, cudaStreamSynchronize(c->stream_d2h));
+  return check_errflag(c, s);
+}
+
+// Compact whole-frame search: ONE predictor per (MB, ref) up, the mode decision's view down (see include/b2me.h).  Everything in
+// between stays on the device; one synchronisation.
+extern "C" int b2me_search_frame_best(b2me_ctx *c, const int16_t *pred_mb, const b2me_search_params *p, int ref_lambda,
+                                      int8_t *best_ref, int32_t *best_cost, int16_t *best_mv)
+{
+  if (!c || !pred_mb || !best_ref || !best_cost || !best_mv) return B2ME_EINVAL;
+  int r = check_params(c, p);
+  if (r) return r;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const size_t nitem = (size_t)c->nmb * c->nrefs;
+  if (!c->d_pred_mb) {
+    B2_CUDA_CHECK(c, cudaMalloc(&c->d_pred_mb, nitem * 2 * sizeof(int16_t)));
+    B2_CUDA_CHECK(c, cudaMalloc(&c->d_best_ref, (size_t)c->nmb * 21));
+    B2_CUDA_CHECK(c, cudaMalloc(&c->d_best_cost, (size_t)c->nmb * 21 * sizeof(long long)));
+    B2_CUDA_CHECK(c, cudaMalloc(&c->d_best_cost32, (size_t)c->nmb * 21 * sizeof(int32_t)));
+    B2_CUDA_CHECK(c, cudaMalloc(&c->d_best_mv, (size_t)c->nmb * NPART * 2 * sizeof(int16_t)));
+  }
+  cudaStream_t s = c->stream;
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(c->d_pred_mb, pred_mb, nitem * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  B2_CUDA_CHECK(c, launch_expand_pred((int)(nitem * NPART), c->d_pred_mb, c->d_pred, c->d_center, s));
+  c->launches++;
+  r = run_search(c, 0, c->nmb, 0, c->nrefs, 1, (1ull << NPART) - 1, -1, c->d_pred, c->d_center, p,
+                 c->d_mv_int, c->d_cost_int, c->d_mv_sub, c->d_cost_sub, s);
+  if (r) return r;
+  B2_CUDA_CHECK(c, launch_select_gather(c->nmb, c->nrefs, p->do_subpel ? c->d_cost_sub : c->d_cost_int, ref_lambda,
+                                        p->do_subpel ? c->d_mv_sub : c->d_mv_int, c->d_best_ref, c->d_best_cost, c->d_best_mv, c->d_best_cost32, s));
+  c->launches += 2;
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(best_ref, c->d_best_ref, (size_t)c->nmb * 21, cudaMemcpyDeviceToHost, s));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(best_cost, c->d_best_cost32, (size_t)c->nmb * 21 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(best_mv, c->d_best_mv, (size_t)c->nmb * NPART * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
   return check_errflag(c, s);
 }
 

@@ -25,6 +25,8 @@ struct b2me_ctx {
   int16_t *d_io16;
   long long *d_io64;
   int *d_errflag;
+  // compact frame search (b2me_search_frame_best), allocated at the first call
+  int16_t *d_pred_mb, *d_best_mv; int8_t *d_best_ref; long long *d_best_cost; int32_t *d_best_cost32;
   int *d_work;                  // k_sad_fs item counter
   int wp_apply[16], wp_weight[16], wp_offset[16], wp_denom[16];   // explicit weighted prediction per reference slot
   unsigned long long *d_stats;
@@ -100,6 +102,9 @@ struct McArgs {
   uint8_t *orig_blk, *pred_blk;
 };
 cudaError_t launch_mc_luma(const McArgs &a, cudaStream_t s);
+cudaError_t launch_expand_pred(int n, const int16_t *pred_mb, int16_t *pred, int16_t *center, cudaStream_t s);
+cudaError_t launch_select_gather(int nmb, int nrefs, const long long *cost, int ref_lambda, const int16_t *mv, int8_t *best_ref, long long *best_cost,
+                                 int16_t *best_mv, int32_t *cost32, cudaStream_t s);
 cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, int row_lo, int row_hi, cudaStream_t s);
 cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, cudaStream_t s, int *smem_bytes_out);
 FsGeom fs_geom_host(int R);

@@ -302,6 +302,49 @@ __global__ void __launch_bounds__(256) k_select_refs(int nmb, int nrefs, const l
   best_ref[i] = (int8_t)br; best_cost[i] = bm;
 }
 
+// ---- compact frame search (b2me_search_frame_best): one predictor per (MB, ref) in, the mode decision's view out -------------
+// pred_mb [nmb][nrefs][2] -> pred / centre [nmb][nrefs][41][2]: the 41 partitions share the predictor, the integer search centre
+// is ((p + 2) >> 2) * 4 (JM_INT_DIVIDE, mv_search.c:931-932)
+__global__ void __launch_bounds__(256) k_expand_pred(int n, const int16_t *__restrict__ pred_mb, int16_t *__restrict__ pred, int16_t *__restrict__ center)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (mb * nrefs + ref) * 41 + p
+  if (i >= n) return;
+  const int item = i / NPART;
+  const int px = pred_mb[2 * item], py = pred_mb[2 * item + 1];
+  pred[2 * i] = (int16_t)px; pred[2 * i + 1] = (int16_t)py;
+  center[2 * i] = (int16_t)(((px + 2) >> 2) * 4); center[2 * i + 1] = (int16_t)(((py + 2) >> 2) * 4);
+}
+
+// the vector of every partition for the reference its (mode, block) entry chose; costs saturated to int32
+__global__ void __launch_bounds__(256) k_gather_best(int nmb, int nrefs, const int16_t *__restrict__ mv, const int8_t *__restrict__ best_ref,
+                                                     const long long *__restrict__ best_cost, int16_t *__restrict__ best_mv, int32_t *__restrict__ cost32)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nmb * 21) { const long long c = best_cost[i]; cost32[i] = c > 0x7fffffffll ? 0x7fffffff : (int32_t)c; }
+  if (i >= nmb * NPART) return;
+  const int mb = i / NPART, p = i - mb * NPART;
+  int e = 0;
+#pragma unroll 1
+  for (int k = 0; k < 21; k++)
+    for (int j = 0; j < 4; j++) if (c_entry_parts[k][j] == p) e = k;
+  const int r = best_ref[mb * 21 + e];
+  const size_t src = (((size_t)mb * nrefs + r) * NPART + p) * 2;
+  best_mv[2 * i] = mv[src]; best_mv[2 * i + 1] = mv[src + 1];
+}
+
+cudaError_t launch_expand_pred(int n, const int16_t *pred_mb, int16_t *pred, int16_t *center, cudaStream_t s)
+{
+  k_expand_pred<<<(n + 255) / 256, 256, 0, s>>>(n, pred_mb, pred, center);
+  return cudaGetLastError();
+}
+cudaError_t launch_select_gather(int nmb, int nrefs, const long long *cost, int ref_lambda, const int16_t *mv, int8_t *best_ref, long long *best_cost,
+                                 int16_t *best_mv, int32_t *cost32, cudaStream_t s)
+{
+  k_select_refs<<<(nmb * 21 + 255) / 256, 256, 0, s>>>(nmb, nrefs, cost, ref_lambda, best_ref, best_cost);
+  k_gather_best<<<(nmb * NPART + 255) / 256, 256, 0, s>>>(nmb, nrefs, mv, best_ref, best_cost, best_mv, cost32);
+  return cudaGetLastError();
+}
+
 }  // namespace b2
 
 using namespace b2;

@@ -119,6 +119,17 @@ int b2me_search_mbs_dev(b2me_ctx *ctx, int mb_first, int mb_count,
                         int16_t *mv_int_dev, int64_t *cost_int_dev,
                         int16_t *mv_sub_dev, int64_t *cost_sub_dev, void *stream);
 
+/* Compact whole-frame search (the end-to-end path of bench.py): what the reference's BlockMotionSearch receives and what its mode
+ * decision consumes, nothing else crossing the bus.
+ *   pred_mb   [nmb][nrefs][2] int16: ONE quarter-pel predictor per (MB, ref), shared by its 41 partitions; the integer search
+ *             centre is derived on the device, ((p + 2) >> 2) * 4 (JM_INT_DIVIDE, mv_search.c:931-932)
+ *   best_ref  [nmb][21] int8, best_cost [nmb][21] int32: list_prediction_cost (mode_decision.c:275-300) per (mode, block) entry as
+ *             b2me_select_refs_dev defines them (costs above INT32_MAX -- a bound that was never beaten -- saturate)
+ *   best_mv   [nmb][41][2] int16: the refined vector of every partition for the reference its entry chose
+ * Host pointers (pinned for speed); one synchronisation; 4.3 + 2.2 MB per 1080p x 4 refs picture instead of 14.9 + 16.1. */
+int b2me_search_frame_best(b2me_ctx *ctx, const int16_t *pred_mb, const b2me_search_params *params, int ref_lambda,
+                           int8_t *best_ref, int32_t *best_cost, int16_t *best_mv);
+
 /* Drop-in for ONE call of full_search_motion_estimation (+ sub_pel_motion_estimation): block
  * at luma (pos_x,pos_y), JM blocktype 1..7, reference ref_idx.  search_range_pel is the
  * block's own range (min(max_x,max_y)>>2 after get_search_range). */

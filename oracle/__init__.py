@@ -80,6 +80,11 @@ def partition_geometry():
 SELECT_ENTRIES = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1)] + [(m, b) for m in (4, 5, 6, 7) for b in range(4)]   # (mode, block) of the 21 entries
 
 
+# (mode, block) entries of list_prediction_cost -> the partitions whose motion costs they sum (include/b2me.h, b2me_select_refs_dev)
+ENTRY_PARTS = [(0,), (1,), (2,), (3,), (4,), (5,), (6,), (7,), (8,), (9, 11), (10, 12), (13, 15), (14, 16),
+               (17, 18), (19, 20), (21, 22), (23, 24), (25, 26, 29, 30), (27, 28, 31, 32), (33, 34, 37, 38), (35, 36, 39, 40)]
+
+
 def select_refs(cost, ref_lambda):
     """list_prediction_cost (list 0) for every macroblock: cost [nmb][nrefs][41] -> (best_ref int8 [nmb][21], best_cost int64 [nmb][21])"""
     cost = np.ascontiguousarray(cost, np.int64)

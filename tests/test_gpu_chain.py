@@ -79,3 +79,29 @@ def test_reference_selection_on_the_device_matches_oracle():
         ebr, ebc = oracle.select_refs(cs.cpu().numpy(), lam)
         assert (br.cpu().numpy() == ebr).all() and (bc.cpu().numpy() == ebc).all(), lam
     assert len(np.unique(br.cpu().numpy())) > 1
+
+
+def test_compact_frame_search_equals_full_arrays_plus_selection():
+    """b2me_search_frame_best (one predictor per (MB, ref) up; best reference, cost and vector per entry / partition down) ==
+    b2me_search_frame on the expanded predictors followed by the oracle's list_prediction_cost and the gather of the chosen vectors."""
+    W, H, R, NR = 96, 64, 16, 3
+    fr = synth.luma_sequence(W, H, NR + 1, seed=5)
+    cur, refs = fr[NR], fr[[NR - 1 - r for r in range(NR)]]
+    s = api.Searcher(W, H, NR, R)
+    s.set_cur(cur)
+    for r in range(NR):
+        s.set_ref(r, refs[r])
+    rng = np.random.default_rng(3)
+    nmb = (W // 16) * (H // 16)
+    pred_mb = rng.integers(-30, 31, (nmb, NR, 2)).astype(np.int16)
+    lam = 187
+    p = api.make_params((lam, lam, lam))
+    br, bc, bm = s.search_frame_best(pred_mb, p, lam)
+    pred = np.broadcast_to(pred_mb[:, :, None, :], (nmb, NR, 41, 2)).copy()
+    cen = (((pred.astype(np.int32) + 2) >> 2) * 4).astype(np.int16)
+    _, _, mv_sub, cost_sub = s.search_frame(pred, cen, p)
+    ebr, ebc = oracle.select_refs(cost_sub, lam)
+    assert (br == ebr).all() and (bc == np.minimum(ebc, 0x7fffffff)).all()
+    for e, parts in enumerate(oracle.ENTRY_PARTS):
+        for q in parts:
+            assert (bm[:, q] == mv_sub[np.arange(nmb), ebr[:, e], q]).all(), (e, q)
