@@ -422,6 +422,21 @@ class PoolSearcher:
         return self.L.b2fp_launch_count(self.h)
 
 
+def tq16x16(params, orig, pred, device=0):
+    """b2tq_16x16 (Intra16x16 luma): orig / pred [nmb][256] raster -> dc_level, dc_run, ac_level, ac_run, recon, ac_coef"""
+    orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+    nmb = orig.shape[0]
+    dl = np.zeros((nmb, 16), np.int16); dr = np.zeros((nmb, 16), np.uint8)
+    al = np.zeros((nmb, 16, 16), np.int16); ar = np.zeros((nmb, 16, 16), np.uint8)
+    rec = np.zeros((nmb, 256), np.uint8); ac = np.zeros(nmb, np.uint8)
+    L = lib()
+    L.b2tq_last_error.restype = C.c_char_p
+    r = L.b2tq_16x16(C.c_int(device), C.byref(params), C.c_int(nmb), _p(orig), _p(pred), _p(dl), _p(dr), _p(al), _p(ar), _p(rec), _p(ac))
+    if r:
+        raise B2Error(f"b2tq_16x16 failed ({r}): {L.b2tq_last_error().decode()}")
+    return dl, dr, al, ar, rec, ac
+
+
 def tq_dev(params, orig, pred, n, level, run, recon, cost, nonzero, stream=0):
     """b2tq_4x4_dev / b2tq_8x8_dev on torch CUDA tensors (orig, pred [nblk][n*n] u8; outputs preallocated)."""
     L = lib()

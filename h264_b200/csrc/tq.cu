@@ -221,6 +221,123 @@ __global__ void __launch_bounds__(64) k_tq8x8(const __grid_constant__ b2tq_param
   cost[k] = cst; nonzero[k] = (uint8_t)nz;
 }
 
+// ---- Intra16x16 luma: residual_transform_quant_luma_16x16 (JM/lencod/src/block.c:207-345) -----------------------------------------
+// 16 threads per macroblock (one per 4x4 block, raster), two macroblocks per warp.  forward4x4 per thread; the sixteen DC
+// coefficients form a 4x4 matrix across the threads: hadamard4x4 / ihadamard4x4 (JM/lcommon/src/transform.c:121-214) take each
+// thread's row and column through shuffles; quant_dc4x4_normal (quant4x4_normal.c:200-270) and its run/level list come from a
+// ballot over the scan order; quant_ac4x4_normal (:117-190, scan positions 1..15), inverse4x4 and sample_reconstruct stay in the
+// thread.  orig / pred / recon: [nmb][256] raster 16x16.
+template <bool FIELD>
+__global__ void __launch_bounds__(128) k_tq16x16(const __grid_constant__ b2tq_params c_tq, int nmb, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ pred,
+                                                 short *__restrict__ dc_level, uint8_t *__restrict__ dc_run, short *__restrict__ ac_level, uint8_t *__restrict__ ac_run,
+                                                 uint8_t *__restrict__ recon, uint8_t *__restrict__ ac_coef)
+{
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int mb = gid >> 4, b = gid & 15, lane = threadIdx.x & 31, hb = lane & 16;      // hb: first lane of this macroblock's half warp
+  const bool live = mb < nmb;
+  const int jj = b >> 2, ii = b & 3;
+  const int qp_per = c_tq.qp / 6, q_bits = 15 + qp_per;
+  int x[16], pr[16];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const size_t o = (size_t)mb * 256 + (4 * jj + r) * 16 + 4 * ii;
+    const uint32_t ow = live ? *reinterpret_cast<const uint32_t *>(orig + o) : 0u, pw = live ? *reinterpret_cast<const uint32_t *>(pred + o) : 0u;
+#pragma unroll
+    for (int c = 0; c < 4; c++) { pr[4 * r + c] = (pw >> (8 * c)) & 255; x[4 * r + c] = (int)((ow >> (8 * c)) & 255) - pr[4 * r + c]; }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) fwd4(x[4 * r], x[4 * r + 1], x[4 * r + 2], x[4 * r + 3]);
+#pragma unroll
+  for (int c = 0; c < 4; c++) fwd4(x[c], x[4 + c], x[8 + c], x[12 + c]);
+  // ---- hadamard4x4 of the DC matrix: thread (jj, ii) ends with tblock[jj][ii] ----
+  int dcv;
+  {
+    int p[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) p[k] = __shfl_sync(0xffffffffu, x[0], hb + 4 * jj + k);
+    const int t0 = p[0] + p[3], t1 = p[1] + p[2], t2 = p[1] - p[2], t3 = p[0] - p[3];
+    const int h = ii == 0 ? t0 + t1 : ii == 1 ? t3 + t2 : ii == 2 ? t0 - t1 : t3 - t2;
+#pragma unroll
+    for (int k = 0; k < 4; k++) p[k] = __shfl_sync(0xffffffffu, h, hb + 4 * k + ii);
+    const int u0 = p[0] + p[3], u1 = p[1] + p[2], u2 = p[1] - p[2], u3 = p[0] - p[3];
+    dcv = (jj == 0 ? u0 + u1 : jj == 1 ? u2 + u3 : jj == 2 ? u0 - u1 : u3 - u2) >> 1;
+  }
+  // ---- quant_dc4x4_normal: every thread quantises its own coefficient; the lists follow the scan order ----
+  int dlev = 0;
+  if (dcv != 0) {
+    int lv = ((dcv < 0 ? -dcv : dcv) * c_tq.scale[0] + (c_tq.offset[0] << 1)) >> (q_bits + 1);
+    if (lv != 0) { if (c_tq.cavlc && lv > 2063) lv = 2063; dlev = dcv < 0 ? -lv : lv; }
+  }
+  {
+    const int si = FIELD ? FS4[b][0] : ZZ4[b][0], sj = FIELD ? FS4[b][1] : ZZ4[b][1];          // thread b doubles as scan position b
+    const int slev = __shfl_sync(0xffffffffu, dlev, hb + sj * 4 + si);
+    const uint32_t mask = (__ballot_sync(0xffffffffu, slev != 0) >> hb) & 0xffffu;
+    if (live) { dc_level[(size_t)mb * 16 + b] = 0; dc_run[(size_t)mb * 16 + b] = 0; }
+    __syncwarp();
+    if (live && slev != 0) {
+      const uint32_t below = mask & ((1u << b) - 1u);
+      const int idx = __popc(below), run = below ? b - 1 - (31 - __clz(below)) : b;
+      dc_level[(size_t)mb * 16 + idx] = (short)slev; dc_run[(size_t)mb * 16 + idx] = (uint8_t)run;
+    }
+    // ---- inverse DC transform + DC dequantisation (only when a DC level is nonzero) ----
+    int dcr = 0;
+    if (mask) {                                     // uniform per half warp; the shuffles below run for the whole warp
+    }
+    {
+      int p[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) p[k] = __shfl_sync(0xffffffffu, dlev, hb + 4 * jj + k);
+      const int a0 = p[0] + p[2], a1 = p[0] - p[2], a2 = p[1] - p[3], a3 = p[1] + p[3];
+      const int h = ii == 0 ? a0 + a3 : ii == 1 ? a1 + a2 : ii == 2 ? a1 - a2 : a0 - a3;
+#pragma unroll
+      for (int k = 0; k < 4; k++) p[k] = __shfl_sync(0xffffffffu, h, hb + 4 * k + ii);
+      const int c0 = p[0] + p[2], c1 = p[0] - p[2], c2 = p[1] - p[3], c3 = p[1] + p[3];
+      const int v = jj == 0 ? c0 + c3 : jj == 1 ? c1 + c2 : jj == 2 ? c1 - c2 : c0 - c3;
+      dcr = mask ? (((v * c_tq.invscale[0]) << qp_per) + 32) >> 6 : 0;
+    }
+    x[0] = dcr;
+  }
+  // ---- quant_ac4x4_normal of this thread's block ----
+  __align__(16) short lev[16]; __align__(16) unsigned char rn[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { lev[i] = 0; rn[i] = 0; }
+  int nz = 0, n = 0, runc = 0;
+#pragma unroll
+  for (int s = 1; s < 16; s++) {
+    const int i = FIELD ? FS4[s][0] : ZZ4[s][0], j = FIELD ? FS4[s][1] : ZZ4[s][1], idx = j * 4 + i;
+    const int m7 = x[idx];
+    int lv = 0;
+    if (m7 != 0) lv = ((m7 < 0 ? -m7 : m7) * c_tq.scale[idx] + c_tq.offset[idx]) >> q_bits;
+    if (lv != 0) {
+      if (c_tq.cavlc && lv > 2063) lv = 2063;
+      const int sl = m7 < 0 ? -lv : lv;
+      x[idx] = (((sl * c_tq.invscale[idx]) << qp_per) + 8) >> 4;
+      lev[n] = (short)sl; rn[n] = (unsigned char)runc; n++;
+      runc = 0; nz = 1;
+    } else { x[idx] = 0; runc++; }
+  }
+  if (x[0] != 0 || nz) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) inv4(x[4 * r], x[4 * r + 1], x[4 * r + 2], x[4 * r + 3]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) inv4(x[c], x[4 + c], x[8 + c], x[12 + c]);
+  }
+  const uint32_t anyac = (__ballot_sync(0xffffffffu, nz != 0) >> hb) & 0xffffu;
+  if (!live) return;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) v |= (uint32_t)clip255(((x[4 * r + c] + 32) >> 6) + pr[4 * r + c]) << (8 * c);
+    *reinterpret_cast<uint32_t *>(recon + (size_t)mb * 256 + (4 * jj + r) * 16 + 4 * ii) = v;
+  }
+  const uint4 *lv4 = reinterpret_cast<const uint4 *>(lev);
+  uint4 *lo = reinterpret_cast<uint4 *>(ac_level + ((size_t)mb * 16 + b) * 16);
+  lo[0] = lv4[0]; lo[1] = lv4[1];
+  *reinterpret_cast<uint4 *>(ac_run + ((size_t)mb * 16 + b) * 16) = *reinterpret_cast<const uint4 *>(rn);
+  if (b == 0) ac_coef[mb] = anyac ? 15 : 0;
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -329,6 +446,50 @@ extern "C" int b2tq_4x4(int device, const b2tq_params *p, int nblk, const uint8_
 extern "C" int b2tq_8x8(int device, const b2tq_params *p, int nblk, const uint8_t *orig, const uint8_t *pred, int16_t *level, uint8_t *run,
                         uint8_t *recon, int32_t *coeff_cost, uint8_t *nonzero)
 { return tq_host(1, device, p, nblk, orig, pred, level, run, recon, coeff_cost, nonzero); }
+
+// Intra16x16 luma macroblocks (see include/b2me.h)
+extern "C" int b2tq_16x16_dev(const b2tq_params *p, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+                              int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *ac_coef, void *stream)
+{
+  int r = check_tq(p, 0);
+  if (r) return r;
+  if (p->mode != 0) { snprintf(g_tqerr, sizeof(g_tqerr), "b2tq_16x16: version1 has no Intra16x16 DC path (mode must be 0)"); return B2ME_EUNSUPPORTED; }
+  if (nmb < 0 || !orig || !pred || !dc_level || !dc_run || !ac_level || !ac_run || !recon || !ac_coef) return B2ME_EINVAL;
+  if (nmb == 0) return B2ME_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = (nmb * 16 + 127) / 128;
+  if (p->field_scan) k_tq16x16<true><<<grid, 128, 0, s>>>(*p, nmb, orig, pred, dc_level, dc_run, ac_level, ac_run, recon, ac_coef);
+  else k_tq16x16<false><<<grid, 128, 0, s>>>(*p, nmb, orig, pred, dc_level, dc_run, ac_level, ac_run, recon, ac_coef);
+  TQ_CHECK(cudaGetLastError());
+  return B2ME_OK;
+}
+extern "C" int b2tq_16x16(int device, const b2tq_params *p, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+                          int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *ac_coef)
+{
+  if (nmb < 0 || !orig || !pred || !dc_level || !dc_run || !ac_level || !ac_run || !recon || !ac_coef) return B2ME_EINVAL;
+  if (nmb == 0) return B2ME_OK;
+  TQ_CHECK(cudaSetDevice(device));
+  const size_t N = (size_t)nmb;
+  // layout: orig 256 | pred 256 | recon 256 | ac_run 256 | ac_level 512 | dc_level 32 | dc_run 16 | ac_coef 1 (+ pad) per macroblock
+  uint8_t *d = nullptr;
+  const size_t o_pred = N * 256, o_rec = N * 512, o_arun = N * 768, o_alev = N * 1024, o_dlev = N * 1536, o_drun = N * 1568, o_ac = N * 1584, total = N * 1585 + 16;
+  TQ_CHECK(cudaMalloc(&d, total));
+  cudaError_t e = cudaMemcpy(d, orig, N * 256, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + o_pred, pred, N * 256, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); TQ_CHECK(e); }
+  int r = b2tq_16x16_dev(p, nmb, d, d + o_pred, (int16_t *)(d + o_dlev), d + o_drun, (int16_t *)(d + o_alev), d + o_arun, d + o_rec, d + o_ac, 0);
+  if (r == B2ME_OK) {
+    e = cudaMemcpy(recon, d + o_rec, N * 256, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ac_run, d + o_arun, N * 256, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ac_level, d + o_alev, N * 512, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dc_level, d + o_dlev, N * 32, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dc_run, d + o_drun, N * 16, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ac_coef, d + o_ac, N, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { snprintf(g_tqerr, sizeof(g_tqerr), "b2tq_16x16: %s", cudaGetErrorString(e)); r = B2ME_ECUDA; }
+  }
+  cudaFree(d);
+  return r;
+}
 
 // intra: 0 inter block, 1 intra block of a P/B slice, 2 intra block of an I slice (the reference's
 // default offset lists give 682 only to the last: q_offsets.c:426-470, CalculateOffset4x4Param :487-561).

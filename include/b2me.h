@@ -364,6 +364,17 @@ int b2tq_4x4_dev(const b2tq_params *p, int nblk, const uint8_t *orig, const uint
                  int16_t *level, uint8_t *run, uint8_t *recon, int32_t *coeff_cost, uint8_t *nonzero, void *stream);
 int b2tq_8x8_dev(const b2tq_params *p, int nblk, const uint8_t *orig, const uint8_t *pred,
                  int16_t *level, uint8_t *run, uint8_t *recon, int32_t *coeff_cost, uint8_t *nonzero, void *stream);
+/* Intra16x16 luma macroblocks:  <- residual_transform_quant_luma_16x16  JM/lencod/src/block.c:207-345
+ *    hadamard4x4 / ihadamard4x4 of the sixteen DC coefficients   JM/lcommon/src/transform.c:121-214
+ *    quant_dc4x4_normal / quant_ac4x4_normal                     JM/lencod/src/quant4x4_normal.c:200-270, 117-190
+ * p = the INTRA 4x4 table of the plane (b2tq_default_params intra 1 or 2), mode 0.  orig / pred / recon [nmb][256] raster 16x16;
+ * dc_level [nmb][16] int16 + dc_run [nmb][16] u8 = cofDC (zero-terminated, zero-padded); ac_level / ac_run [nmb][16][16]: the
+ * ACLevel / ACRun lists of the sixteen 4x4 blocks in RASTER block order (the reference files them under cofAC[b8][b4]);
+ * ac_coef [nmb] = the return value (15 when any AC level is nonzero). */
+int b2tq_16x16(int device, const b2tq_params *p, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+               int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *ac_coef);
+int b2tq_16x16_dev(const b2tq_params *p, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+                   int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *ac_coef, void *stream);
 const char *b2tq_last_error(void);
 
 #ifdef __cplusplus

@@ -515,6 +515,18 @@ def tq(params, orig, pred, n):
     return level, run, recon, cost, nz
 
 
+def tq16x16(params, orig, pred):
+    """restated residual_transform_quant_luma_16x16: orig / pred [nmb][256] raster -> dc_level [nmb][16] i16, dc_run [nmb][16] u8,
+    ac_level [nmb][16][16] i16, ac_run [nmb][16][16] u8, recon [nmb][256] u8, ac_coef [nmb] u8"""
+    orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+    nmb = orig.shape[0]
+    dl = np.zeros((nmb, 16), np.int16); dr = np.zeros((nmb, 16), np.uint8)
+    al = np.zeros((nmb, 16, 16), np.int16); ar = np.zeros((nmb, 16, 16), np.uint8)
+    rec = np.zeros((nmb, 256), np.uint8); ac = np.zeros(nmb, np.uint8)
+    orc_lib().orc_tq16x16(C.byref(params), C.c_int(nmb), _ptr(orig), _ptr(pred), _ptr(dl), _ptr(dr), _ptr(al), _ptr(ar), _ptr(rec), _ptr(ac))
+    return dl, dr, al, ar, rec, ac
+
+
 class JMQuantRef:
     """The unmodified JM residual_transform_quant_luma_4x4/_8x8 behind oracle/jm_harness_tq.c."""
 
@@ -536,6 +548,16 @@ class JMQuantRef:
         f = self.L.jmq_tq4x4 if n == 4 else self.L.jmq_tq8x8
         f(self.h, C.c_int(qp), C.c_int(intra), C.c_int(nblk), _ptr(orig), _ptr(pred), _ptr(level), _ptr(run), _ptr(recon), _ptr(cost), _ptr(nz))
         return level[:, :m].astype(np.int16), run[:, :m].astype(np.uint8), recon, cost, nz.astype(np.uint8)
+
+    def tq16x16(self, qp, orig, pred):
+        """the unmodified residual_transform_quant_luma_16x16 (Intra16x16 luma) on [nmb][256] raster macroblocks"""
+        orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+        nmb = orig.shape[0]
+        dl = np.zeros((nmb, 17), np.int32); dr = np.zeros((nmb, 17), np.int32)
+        al = np.zeros((nmb, 16, 16), np.int32); ar = np.zeros((nmb, 16, 16), np.int32)
+        rec = np.zeros((nmb, 256), np.uint8); ac = np.zeros(nmb, np.int32)
+        self.L.jmq_tq16x16(self.h, C.c_int(qp), C.c_int(nmb), _ptr(orig), _ptr(pred), _ptr(dl), _ptr(dr), _ptr(al), _ptr(ar), _ptr(rec), _ptr(ac))
+        return dl[:, :16].astype(np.int16), dr[:, :16].astype(np.uint8), al.astype(np.int16), ar.astype(np.uint8), rec, ac.astype(np.uint8)
 
 
 def have_v1tq():

@@ -174,3 +174,93 @@ void orc_tq8x8(const orc_tq_params *P, int nblk, const uint8_t *orig, const uint
   }
 }
 void orc_scan8(int field, uint8_t *out) { if (!scans_ready) build_scans(); memcpy(out, field ? FIELD8 : SNGL8, 128); }
+
+/* ---- Intra16x16 luma (restated): residual_transform_quant_luma_16x16 JM/lencod/src/block.c:207-345 with hadamard4x4 /
+ * ihadamard4x4 (JM/lcommon/src/transform.c:121-214), quant_dc4x4_normal (quant4x4_normal.c:200-270: q_bits + 1, offset << 1,
+ * the level itself goes back into the block) and quant_ac4x4_normal (:117-190: scan positions 1..15).  P = the intra 4x4
+ * table of the plane.  orig / pred / recon [nmb][256] raster; dc lists [nmb][16]; ac lists [nmb][16 blocks raster][16]. */
+void orc_hadamard4x4_dc(const int *in, int *out)
+{
+  int tmp[16], i;
+  for (i = 0; i < 4; i++) {
+    int p0 = in[4*i], p1 = in[4*i+1], p2 = in[4*i+2], p3 = in[4*i+3];
+    int t0 = p0 + p3, t1 = p1 + p2, t2 = p1 - p2, t3 = p0 - p3;
+    tmp[4*i] = t0 + t1; tmp[4*i+1] = t3 + t2; tmp[4*i+2] = t0 - t1; tmp[4*i+3] = t3 - t2;
+  }
+  for (i = 0; i < 4; i++) {
+    int p0 = tmp[i], p1 = tmp[4+i], p2 = tmp[8+i], p3 = tmp[12+i];
+    int t0 = p0 + p3, t1 = p1 + p2, t2 = p1 - p2, t3 = p0 - p3;
+    out[i] = (t0 + t1) >> 1; out[4+i] = (t2 + t3) >> 1; out[8+i] = (t0 - t1) >> 1; out[12+i] = (t3 - t2) >> 1;
+  }
+}
+void orc_ihadamard4x4_dc(const int *in, int *out)
+{
+  int tmp[16], i;
+  for (i = 0; i < 4; i++) {
+    int t0 = in[4*i], t1 = in[4*i+1], t2 = in[4*i+2], t3 = in[4*i+3];
+    int p0 = t0 + t2, p1 = t0 - t2, p2 = t1 - t3, p3 = t1 + t3;
+    tmp[4*i] = p0 + p3; tmp[4*i+1] = p1 + p2; tmp[4*i+2] = p1 - p2; tmp[4*i+3] = p0 - p3;
+  }
+  for (i = 0; i < 4; i++) {
+    int t0 = tmp[i], t1 = tmp[4+i], t2 = tmp[8+i], t3 = tmp[12+i];
+    int p0 = t0 + t2, p1 = t0 - t2, p2 = t1 - t3, p3 = t1 + t3;
+    out[i] = p0 + p3; out[4+i] = p1 + p2; out[8+i] = p1 - p2; out[12+i] = p0 - p3;
+  }
+}
+void orc_tq16x16(const orc_tq_params *P, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+                 int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *ac_coef)
+{
+  int k, b, i, j, s;
+  const int qp_per = P->qp / 6, q_bits = 15 + qp_per;
+  const uint8_t (*scan)[2] = P->field_scan ? FIELD4 : SNGL4;
+  for (k = 0; k < nmb; k++) {
+    int t[16][16], dc[16], hd[16], n = 0, runc = 0, nzdc = 0, ac = 0;
+    memset(dc_level + 16 * k, 0, 32); memset(dc_run + 16 * k, 0, 16);
+    memset(ac_level + 256 * k, 0, 512); memset(ac_run + 256 * k, 0, 256);
+    for (b = 0; b < 16; b++) {
+      int res[16];
+      for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) { int o = 256 * k + (4 * (b >> 2) + j) * 16 + 4 * (b & 3) + i; res[4 * j + i] = (int)orig[o] - (int)pred[o]; }
+      orc_forward4x4(res, t[b]);
+      dc[b] = t[b][0];
+    }
+    orc_hadamard4x4_dc(dc, hd);
+    for (s = 0; s < 16; s++) {                       /* quant_dc4x4_normal */
+      int idx = scan[s][1] * 4 + scan[s][0], m7 = hd[idx];
+      if (m7 != 0) {
+        int lv = (abs(m7) * P->scale[0] + (P->offset[0] << 1)) >> (q_bits + 1);
+        if (lv != 0) {
+          if (P->cavlc && lv > 2063) lv = 2063;
+          lv = m7 < 0 ? -lv : lv;
+          hd[idx] = lv; dc_level[16 * k + n] = (int16_t)lv; dc_run[16 * k + n] = (uint8_t)runc; n++; runc = 0; nzdc = 1;
+        } else { runc++; hd[idx] = 0; }
+      } else runc++;
+    }
+    if (nzdc) {
+      orc_ihadamard4x4_dc(hd, dc);
+      for (b = 0; b < 16; b++) t[b][0] = (((dc[b] * P->invscale[0]) << qp_per) + 32) >> 6;
+    } else for (b = 0; b < 16; b++) t[b][0] = 0;
+    for (b = 0; b < 16; b++) {                       /* quant_ac4x4_normal + inverse4x4 */
+      int r[16], nz = 0;
+      n = 0; runc = 0;
+      for (s = 1; s < 16; s++) {
+        int idx = scan[s][1] * 4 + scan[s][0], m7 = t[b][idx];
+        if (m7 != 0) {
+          int lv = (abs(m7) * P->scale[idx] + P->offset[idx]) >> q_bits;
+          if (lv != 0) {
+            if (P->cavlc && lv > 2063) lv = 2063;
+            lv = m7 < 0 ? -lv : lv;
+            t[b][idx] = (((lv * P->invscale[idx]) << qp_per) + 8) >> 4;
+            ac_level[(16 * k + b) * 16 + n] = (int16_t)lv; ac_run[(16 * k + b) * 16 + n] = (uint8_t)runc; n++; runc = 0; nz = 1;
+          } else { t[b][idx] = 0; runc++; }
+        } else runc++;
+      }
+      if (nz) ac = 15;
+      if (t[b][0] != 0 || nz) orc_inverse4x4(t[b], r); else memcpy(r, t[b], sizeof(r));
+      for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) {
+        int o = 256 * k + (4 * (b >> 2) + j) * 16 + 4 * (b & 3) + i;
+        recon[o] = (uint8_t)clip255(((r[4 * j + i] + 32) >> 6) + pred[o]);
+      }
+    }
+    ac_coef[k] = (uint8_t)ac;
+  }
+}

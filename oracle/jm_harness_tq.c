@@ -134,3 +134,36 @@ void jmq_params(void *hh, int is8x8, int qp, int intra, int *out)
       out[2 * n * n + j * n + i] = q[j][i].InvScaleComp;
     }
 }
+
+/* ---- Intra16x16 luma: residual_transform_quant_luma_16x16 (JM/lencod/src/block.c:207-345) -> forward4x4 x 16, hadamard4x4 /
+ * ihadamard4x4 (JM/lcommon/src/transform.c:121-214), quant_dc4x4_normal / quant_ac4x4_normal (quant4x4_normal.c:200, 117),
+ * inverse4x4, sample_reconstruct.  nmb macroblocks; orig / pred / recon [nmb][256] raster 16x16;
+ * dc_level / dc_run [nmb][17]; ac_level / ac_run [nmb][16 blocks, raster][16]; ac_coef [nmb] = the return value. */
+void jmq_tq16x16(void *hh, int qp, int nmb, const unsigned char *orig, const unsigned char *pred,
+                 int *dc_level, int *dc_run, int *ac_level, int *ac_run, unsigned char *recon, int *ac_coef)
+{
+  JMQ *h = (JMQ *)hh; Slice *s = h->slice; VideoParameters *p_Vid = h->p_Vid; int k, i, j, n, b;
+  static imgpel **cur;
+  if (!s->cofDC) { get_mem3Dint(&s->cofDC, 3, 2, 18); get_mem2Dint(&s->tblk4x4, 4, 4); get_mem4Dpel(&s->mpr_16x16, 3, 5, 16, 16); get_mem2Dpel(&cur, 16, 16); }
+  p_Vid->pCurImg = cur;
+  h->mb.qp_scaled[0] = qp; h->mb.i16mode = 2; h->mb.opix_y = 0; h->mb.pix_x = 0; h->mb.pix_y = 0; h->mb.is_field_mode = 0;
+  for (k = 0; k < nmb; k++) {
+    for (j = 0; j < 16; j++)
+      for (i = 0; i < 16; i++) { cur[j][i] = orig[k * 256 + j * 16 + i]; s->mpr_16x16[0][2][j][i] = pred[k * 256 + j * 16 + i]; }
+    for (b = 0; b < 4; b++) for (n = 0; n < 4; n++) { memset(s->cofAC[b][n][0], 0, 65 * sizeof(int)); memset(s->cofAC[b][n][1], 0, 65 * sizeof(int)); }
+    memset(s->cofDC[0][0], 0, 18 * sizeof(int)); memset(s->cofDC[0][1], 0, 18 * sizeof(int));
+    ac_coef[k] = residual_transform_quant_luma_16x16(&h->mb, PLANE_Y);
+    for (n = 0; n < 17; n++) { dc_level[k * 17 + n] = s->cofDC[0][0][n]; dc_run[k * 17 + n] = s->cofDC[0][1][n]; }
+    for (n = 0; n < 16 && dc_level[k * 17 + n] != 0; n++) ;
+    for (; n < 17; n++) { dc_level[k * 17 + n] = 0; dc_run[k * 17 + n] = 0; }
+    for (b = 0; b < 16; b++) {
+      int jj = b >> 2, ii = b & 3, b8 = 2 * (jj >> 1) + (ii >> 1), b4 = 2 * (jj & 1) + (ii & 1);
+      int *L = ac_level + (k * 16 + b) * 16, *R = ac_run + (k * 16 + b) * 16;
+      for (n = 0; n < 16; n++) { L[n] = s->cofAC[b8][b4][0][n]; R[n] = s->cofAC[b8][b4][1][n]; }
+      for (n = 0; n < 15 && L[n] != 0; n++) ;
+      for (; n < 16; n++) { L[n] = 0; R[n] = 0; }
+    }
+    for (j = 0; j < 16; j++)
+      for (i = 0; i < 16; i++) recon[k * 256 + j * 16 + i] = (unsigned char)h->enc->imgY[j][i];
+  }
+}

@@ -52,3 +52,16 @@ def test_empty_and_bad_arguments():
         api.tq(p, np.zeros((1, 16), np.uint8), np.zeros((1, 16), np.uint8), 4)
     with pytest.raises(api.B2Error):
         api.tq_default_params(8, 28, 0, mode=1)        # version1 has no 8x8 transform
+
+
+@pytest.mark.parametrize("qp,cavlc,field,seed", [(0, 1, 0, 41), (28, 1, 0, 42), (28, 0, 1, 43), (45, 1, 0, 44)])
+def test_intra16x16_matches_oracle(qp, cavlc, field, seed):
+    """b2tq_16x16 (k_tq16x16: DC Hadamard across the threads, DC / AC quantisers) vs the restated oracle, itself pinned to the
+    unmodified residual_transform_quant_luma_16x16 (tests/test_oracle_tq.py)"""
+    from oracle.gen_golden_tq16 import macroblocks
+    orig, pred = macroblocks(1001, seed)
+    p = api.tq_default_params(4, qp, 2, cavlc=cavlc, field_scan=field)
+    q = oracle.tq_params(api.tq_params_table(p, 4), qp, mode=0, cavlc=cavlc, field_scan=field)
+    got, exp = api.tq16x16(p, orig, pred), oracle.tq16x16(q, orig, pred)
+    for a, b, name in zip(got, exp, ("dc_level", "dc_run", "ac_level", "ac_run", "recon", "ac_coef")):
+        assert (a == b).all(), (name, int((a != b).sum()))

@@ -55,3 +55,16 @@ def test_restated_matches_reference_live():
         b = oracle.tq(oracle.tq_params(r.params(n, qp, intra), qp), orig, pred, n)
         for x, y in zip(a, b):
             assert (x == y).all(), (n, qp, intra)
+
+
+def test_restated_intra16x16_matches_reference_golden(golden_dir):
+    """residual_transform_quant_luma_16x16 (DC Hadamard, quant_dc4x4 / quant_ac4x4) restated vs the unmodified JM objects"""
+    from oracle.gen_golden_tq16 import CASES, NMB, macroblocks
+    g = np.load(os.path.join(golden_dir, "jm_tq16.npz"))
+    for ci, (qp, sm, seed) in enumerate(CASES):
+        orig, pred = macroblocks(NMB, seed)
+        p = oracle.tq_params(g[f"c{ci}_params"], qp, mode=0, cavlc=int(sm == 0))
+        got = oracle.tq16x16(p, orig, pred)
+        for a, name in zip(got, ("dc_level", "dc_run", "ac_level", "ac_run", "recon", "ac_coef")):
+            assert (a == g[f"c{ci}_{name}"]).all(), (qp, sm, name)
+        assert (api.tq_params_table(api.tq_default_params(4, qp, 2), 4) == g[f"c{ci}_params"]).all()   # the product's default intra table
