@@ -108,7 +108,7 @@ extern "C" void b2me_destroy(b2me_ctx *c)
   cudaFree(c->d_cur); cudaFree(c->d_stage); cudaFree(c->d_planes); cudaFree(c->d_spl); cudaFree(c->d_tmap_spl);
   cudaFree(c->d_pred); cudaFree(c->d_center); cudaFree(c->d_mv_int); cudaFree(c->d_mv_sub);
   cudaFree(c->d_cost_int); cudaFree(c->d_cost_sub); cudaFree(c->d_io16); cudaFree(c->d_io64);
-  cudaFree(c->d_pred_mb); cudaFree(c->d_best_ref); cudaFree(c->d_best_cost); cudaFree(c->d_best_cost32); cudaFree(c->d_best_mv);
+  cudaFree(c->d_sadtab); cudaFree(c->d_pred_mb); cudaFree(c->d_best_ref); cudaFree(c->d_best_cost); cudaFree(c->d_best_cost32); cudaFree(c->d_best_mv);
   cudaFreeHost(c->h_io16); cudaFreeHost(c->h_io64); cudaFree(c->d_errflag); cudaFree(c->d_work); cudaFree(c->d_stats);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);

@@ -25,6 +25,7 @@ struct b2me_ctx {
   int16_t *d_io16;
   long long *d_io64;
   int *d_errflag;
+  uint16_t *d_sadtab; size_t sadtab_bytes;   // b2me_sad_table's device buffer
   // compact frame search (b2me_search_frame_best), allocated at the first call
   int16_t *d_pred_mb, *d_best_mv; int8_t *d_best_ref; long long *d_best_cost; int32_t *d_best_cost32;
   int *d_work;                  // k_sad_fs item counter

@@ -138,6 +138,14 @@ int b2me_block_search(b2me_ctx *ctx, int pos_x, int pos_y, int blocktype, int re
                       const b2me_search_params *params, int search_range_pel,
                       int16_t mv_int[2], int64_t *cost_int, int16_t mv_sub[2], int64_t *cost_sub);
 
+/* Drop-in service of JM's FAST full search (SearchMode 0): the SAD tables setup_fast_full_search builds for one macroblock and
+ * reference (JM/lencod/src/me_fullfast.c:269-608 luma unweighted branch, update_full_search_large_blocks :195-260): for every
+ * position pos of the spiral around center_mv (relative MV, multiple of 4; the reference centres on the rounded 16x16 predictor)
+ * and every partition p:  table[p * npos + pos] = SAD of partition p at center + spiral[pos],  npos = (2 * search_range_pel + 1)^2,
+ * uint16.  The 41 table scans of fast_full_search_motion_estimation (:618-689), whose motion costs need predictors that exist only
+ * one partition after the other, stay with the caller (integration/jm/b2me_jm_shim.c).  Host pointer, synchronous. */
+int b2me_sad_table(b2me_ctx *ctx, int mb_x, int mb_y, int ref_idx, const int16_t center_mv[2], int search_range_pel, uint16_t *table);
+
 /* Drop-in for ONE call of sub_pel_motion_estimation: mv_in = the block's current MV (relative,
  * quarter-pel), min_mcost = the bound exactly as the caller hands it over (BlockMotionSearch passes
  * DISTBLK_MAX when the metric changes between levels, mv_search.c:971-974). */

@@ -305,3 +305,111 @@ distblk computeSSE(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, 
 distblk computeSATD(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
 { (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 2); }
 #endif
+
+#ifdef B2ME_SHIM_FULLFAST
+/* ---- SearchMode 0 (fast full search): every symbol of JM's me_fullfast.o (JM/lencod/inc/me_fullfast.h:29-35), that object
+ * left out of the link.  setup_fast_full_search -- the 4x4-SAD tables of one (macroblock, list, reference) around the rounded
+ * 16x16 predictor and their tree sums -- is ONE GPU call (b2me_sad_table); the 41 calls of fast_full_search_motion_estimation
+ * that follow scan that table with the caller's own predictor, the max_mvd guard included, exactly as
+ * JM/lencod/src/me_fullfast.c:618-689 does.  The reference's BlockSAD arrays become one uint16 [41][max_pos] table per
+ * (list, reference). ---- */
+#include "me_fullfast.h"
+#include "mv_prediction.h"
+
+typedef struct {
+  uint16_t *tab[2][B2_MAX_SLOTS];      /* [list][ref] -> [41][max_pos] */
+  int done[2][B2_MAX_SLOTS];
+  int range[2][B2_MAX_SLOTS];          /* max_search_range[list][ref] (pel) */
+  MotionVector center[2][B2_MAX_SLOTS];
+  int nref, max_pos;
+} B2FF;
+static B2FF g_ff;
+static long g_calls_ff, g_setups_ff;
+
+void initialize_fast_full_search(VideoParameters *p_Vid, InputParameters *p_Inp)
+{
+  int list, i, sr = p_Inp->search_range[p_Vid->view_id];
+  memset(&g_ff, 0, sizeof(g_ff));
+  g_ff.nref = imin(B2_MAX_SLOTS, p_Vid->max_num_references);
+  g_ff.max_pos = (2 * sr + 1) * (2 * sr + 1);
+  for (list = 0; list < 2; list++)
+    for (i = 0; i < g_ff.nref; i++) {
+      g_ff.tab[list][i] = (uint16_t *)calloc((size_t)B2ME_NPART * g_ff.max_pos, sizeof(uint16_t));
+      if (!g_ff.tab[list][i]) no_mem_exit("b2me shim: fast full search tables");
+      g_ff.range[list][i] = (p_Inp->full_search == 2 || i == 0) ? sr : sr / 2;       /* me_fullfast.c:113-128 */
+    }
+}
+void clear_fast_full_search(VideoParameters *p_Vid)
+{
+  int list, i;
+  (void)p_Vid;
+  for (list = 0; list < 2; list++) for (i = 0; i < g_ff.nref; i++) { free(g_ff.tab[list][i]); g_ff.tab[list][i] = NULL; }
+  if (getenv("B2ME_SHIM_VERBOSE")) fprintf(stderr, "b2me shim: %ld fast-full-search set-ups (GPU), %ld table scans\n", g_setups_ff, g_calls_ff);
+}
+void reset_fast_full_search(VideoParameters *p_Vid) { (void)p_Vid; memset(g_ff.done, 0, sizeof(g_ff.done)); }
+void update_full_search_large_blocks(MEFullFast *p, int list, int refindex, int max_pos) { (void)p; (void)list; (void)refindex; (void)max_pos; }
+
+void setup_fast_full_search(Macroblock *currMB, MEBlock *mv_block, int list)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  InputParameters *p_Inp = currMB->p_Inp;
+  Slice *currSlice = currMB->p_Slice;
+  short ref = mv_block->ref_idx;
+  int range = g_ff.range[list][ref], rq = range << 2, slot;
+  MotionVector pmv, *c = &g_ff.center[list][ref];
+  PixelPos block[4];
+  int16_t cm[2];
+
+  b2_ensure_ctx(currMB);
+  b2_check_config(currMB, mv_block);
+  if (ref >= g_ff.nref) b2_fail("reference index beyond the fast-full-search tables");
+  b2_ensure_cur(p_Vid);
+  slot = b2_ref_slot(currSlice->listX[list + currMB->list_offset][ref]);
+  /* search centre: the rounded predictor of the 16x16 block, clipped (me_fullfast.c:309-330) */
+  get_neighbors(currMB, block, 0, 0, 16);
+  currMB->GetMVPredictor(currMB, block, &pmv, ref, p_Vid->enc_picture->mv_info, list, 0, 0, 16, 16);
+  c->mv_x = (short)(((pmv.mv_x + 2) >> 2) * 4);
+  c->mv_y = (short)(((pmv.mv_y + 2) >> 2) * 4);
+  if (!p_Inp->rdopt) { c->mv_x = (short)iClip3(-rq, rq, c->mv_x); c->mv_y = (short)iClip3(-rq, rq, c->mv_y); }
+  c->mv_x = (short)iClip3(p_Vid->MaxHmvR[4] + rq, p_Vid->MaxHmvR[5] - rq, c->mv_x);
+  c->mv_y = (short)iClip3(p_Vid->MaxVmvR[4] + rq, p_Vid->MaxVmvR[5] - rq, c->mv_y);
+  cm[0] = c->mv_x; cm[1] = c->mv_y;
+  if (b2me_sad_table(g_ctx, currMB->pix_x >> 4, currMB->opix_y >> 4, slot, cm, range, g_ff.tab[list][ref]) != B2ME_OK) b2_fail("b2me_sad_table failed");
+  g_ff.done[list][ref] = 1; g_setups_ff++;
+}
+
+distblk fast_full_search_motion_estimation(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  int search_range = imax(mv_block->searchRange.max_x, mv_block->searchRange.max_y) >> 2;
+  int max_pos = (2 * search_range + 1) * (2 * search_range + 1), best_pos = 0, pos, part, q;
+  int list = mv_block->list;
+  short ref = mv_block->ref_idx;
+  MotionVector cand = {0, 0}, *offset;
+  int max_mvd = p_Vid->max_mvd - 1, tab_pos;
+  const uint16_t *block_sad;
+  static const int first[8] = {0, 0, 1, 3, 5, 9, 17, 25};
+  static const int bw[8] = {0, 16, 16, 8, 8, 8, 4, 4}, bh[8] = {0, 16, 8, 16, 8, 4, 8, 4};
+
+  if (!g_ff.done[list][ref]) currMB->p_SetupFastFullPelSearch(currMB, mv_block, list);
+  offset = &g_ff.center[list][ref];
+  tab_pos = (2 * g_ff.range[list][ref] + 1) * (2 * g_ff.range[list][ref] + 1);
+  if (max_pos > tab_pos) b2_fail("fast full search: the block's range exceeds the table of its reference (the reference reads unwritten memory there; use RestrictSearchRange 2)");
+  /* this library's partition number of (blocktype, block_x, block_y): raster order inside the blocktype */
+  q = mv_block->blocktype;
+  part = first[q] + (mv_block->block_y * 4 / bh[q]) * (16 / bw[q]) + mv_block->block_x * 4 / bw[q];
+  block_sad = g_ff.tab[list][ref] + (size_t)part * tab_pos;
+  g_calls_ff++;
+  /* (the non-RDO (0,0) pre-check of :652-659 is unreachable: b2_check_config refuses RDOptimization 0) */
+  for (pos = 0; pos < max_pos; pos++) {
+    distblk mcost = dist_scale((distblk)block_sad[pos]);
+    cand = add_MVs(p_Vid->spiral_qpel_search[pos], offset);
+    if (mcost < min_mcost && GetMaxMVD(&cand, pred_mv) < max_mvd) {
+      mcost += mv_cost(p_Vid, lambda_factor, &cand, pred_mv);
+      if (mcost < min_mcost) { min_mcost = mcost; best_pos = pos; }
+    }
+  }
+  mv_block->mv[list] = add_MVs(p_Vid->spiral_qpel_search[best_pos], offset);
+  return min_mcost;
+}
+#endif

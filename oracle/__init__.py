@@ -66,6 +66,20 @@ def mvbits(d):
     return orc_lib().orc_mvbits(C.c_int(int(d)))
 
 
+def spiral_xy(pos):
+    """integer displacement of position pos of the JM spiral (mv_search.c:406-442)"""
+    if pos == 0:
+        return 0, 0
+    l = 1
+    while (2 * l + 1) ** 2 <= pos:
+        l += 1
+    k = pos - (2 * l - 1) ** 2
+    if k < 2 * (2 * l - 1):
+        return (k >> 1) - l + 1, (l if k & 1 else -l)
+    k -= 2 * (2 * l - 1)
+    return (l if k & 1 else -l), (k >> 1) - l
+
+
 def partition_geometry():
     """[(blocktype, ox, oy, w, h)] for the 41 partitions of an MB."""
     L = orc_lib()

@@ -139,3 +139,28 @@ def test_dropin_fails_loudly_without_a_gpu():
         open(yuv, "wb").write(synth.yuv420_sequence(W, H, 2, seed=1))
         with pytest.raises(RuntimeError, match="b2me"):
             jm_run.run_lencod(yuv, W, H, 2, os.path.join(d, "b2"), exe="lencod_b2")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (have and os.path.exists(os.path.join(REF, "lencod_b2f"))), reason="oracle/_ref/lencod_b2f not built")
+@pytest.mark.parametrize("frames,nrefs,sr,qp,bframes", [(6, 2, 16, 28, 0), (5, 2, 8, 30, 1)])
+def test_fast_full_search_with_gpu_sad_tables_is_bit_identical(frames, nrefs, sr, qp, bframes):
+    """lencod_b2f, SearchMode 0: me_fullfast.o AND me_fullsearch.o out of the link; setup_fast_full_search's SAD tables come from
+    b2me_sad_table (one GPU call per macroblock and reference), fast_full_search_motion_estimation scans them in the shim with the
+    max_mvd guard (JM/lencod/src/me_fullfast.c:618-689)."""
+    W, H = 176, 144
+    extra = ("RestrictSearchRange=2",)
+    if bframes:
+        extra += ("NumberBFrames=1", "HierarchicalCoding=0", "BReferencePictures=0", "QPBSlice=30", "BList1References=1")
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(W, H, frames, seed=21))
+        a = _encode("lencod", yuv, W, H, frames, os.path.join(d, "stock"), nrefs=nrefs, search_range=sr, qp=qp, search_mode=0, extra=extra)
+        b = _encode("lencod_b2f", yuv, W, H, frames, os.path.join(d, "b2"), nrefs=nrefs, search_range=sr, qp=qp, search_mode=0, extra=extra,
+                    env={"B2ME_SHIM_VERBOSE": "1"})
+        assert len(a[0]) > 1000
+        assert a[0] == b[0], "bitstreams differ"
+        assert a[1] == b[1], "reconstructions differ"
+        import re
+        m = re.search(r"(\d+) fast-full-search set-ups \(GPU\), (\d+) table scans", b[2])
+        assert m and int(m.group(1)) > 100 and int(m.group(2)) > 30 * int(m.group(1)), b[2][-400:]

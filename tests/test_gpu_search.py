@@ -303,3 +303,36 @@ def test_refined_results_only_and_upload_ordering():
     import ctypes as C
     assert s.L.b2me_search_frame(s.h, pred.ctypes.data_as(C.c_void_p), cen.ctypes.data_as(C.c_void_p),
                                  C.byref(api.make_params(lam, do_subpel=False)), None, None, None, None) == -1
+
+
+def test_sad_table_matches_oracle_distortions():
+    """b2me_sad_table (setup_fast_full_search's BlockSAD tables): sampled (partition, position) entries against the oracle's
+    computeSAD at that candidate, border macroblocks and a centre that pushes the window outside the picture included."""
+    import ctypes as C
+    W, H, R, NR = 96, 64, 16, 2
+    fr = synth.luma_sequence(W, H, NR + 1, seed=12)
+    cur, refs = fr[NR], fr[[1, 0]]
+    s = api.Searcher(W, H, NR, R)
+    s.set_cur(cur)
+    for r in range(NR):
+        s.set_ref(r, refs[r])
+    of = oracle.OrcFrame(cur, refs, R)
+    geo = oracle.partition_geometry()
+    rng = np.random.default_rng(5)
+    for (mbx, mby, ref, cen, sr) in ((0, 0, 0, (-40, -28), 16), (5, 3, 1, (36, 44), 16), (2, 1, 0, (0, 4), 7)):
+        npos = (2 * sr + 1) ** 2
+        tab = np.zeros((41, npos), np.uint16)
+        cm = (C.c_int16 * 2)(*cen)
+        r = s.L.b2me_sad_table(s.h, mbx, mby, ref, cm, sr, tab.ctypes.data_as(C.c_void_p))
+        assert r == 0
+        cands = np.zeros(0, synth.CANDIDATE)
+        picks = [(int(p), int(pos)) for p, pos in zip(rng.integers(0, 41, 300), rng.integers(0, npos, 300))] + [(0, 0), (40, npos - 1)]
+        cands = np.zeros(len(picks), synth.CANDIDATE)
+        for k, (p, pos) in enumerate(picks):
+            bt, ox, oy, bw, bh = geo[p]
+            sx, sy = oracle.spiral_xy(pos)
+            cands[k]["pos_x"], cands[k]["pos_y"], cands[k]["blocktype"], cands[k]["ref"] = mbx * 16 + ox, mby * 16 + oy, bt, ref
+            cands[k]["mv"] = (cen[0] + 4 * sx, cen[1] + 4 * sy)
+        exp = of.distortion_candidates(cands, 0) >> 5
+        got = np.array([tab[p, pos] for p, pos in picks], np.int64)
+        assert (got == exp).all(), np.flatnonzero(got != exp)[:5]
