@@ -355,6 +355,40 @@ def pool_multi_leg(local, rank, world, nds=(16384, 65536), steps=4):
                         f"plane broadcast ({Wp * Hp} B, NCCL) + pool build + k_frac_pool per picture", "scaling": "strong", "pools": out}
 
 
+def dropin_leg(frames=10):
+    """The drop-in on the reference's own clock (part of the cpu_baseline leg: it runs the prebuilt reference binaries of oracle/_ref):
+    BASELINE config 1 (QCIF 176x144 IPPP, +-16, 1 reference, QP 28) encoded by the stock JM lencod and by the same objects with the
+    motion search served by libb2me.so -- lencod_b2 (SearchMode -1: one GPU call per full_search / sub_pel call) and lencod_b2f
+    (SearchMode 0: one GPU call per (macroblock, reference) for the SAD tables).  JM's own `Total ME time` is quoted; the
+    bitstreams must be identical.  The per-call drop-in is a CORRECTNESS boundary: every call is a host round trip to the GPU."""
+    import re
+    import tempfile
+    from h264_b200 import synth
+    from oracle import jm_run
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not all(os.path.exists(os.path.join(ref, f)) for f in ("lencod", "lencod_b2", "lencod_b2f", "encoder.cfg")):
+        return {"unavailable": "oracle/_ref/lencod{,_b2,_b2f} not built"}
+    Wq, Hq = 176, 144
+    out = {"workload": f"JM 18.5 lencod, synthetic QCIF {Wq}x{Hq}, {frames} frames IPPP, +-16, 1 ref, QP 28 (BASELINE config 1)"}
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(Wq, Hq, frames, seed=20261018))
+        for mode, exes in ((-1, ("lencod", "lencod_b2")), (0, ("lencod", "lencod_b2f"))):
+            res = {}
+            for exe in exes:
+                od = os.path.join(d, f"{exe}_{mode}")
+                log = jm_run.run_lencod(yuv, Wq, Hq, frames, od, exe=exe, nrefs=1, search_range=16, qp=28, search_mode=mode)
+                m = re.search(r"Total ME time for sequence\s*:\s*([0-9.]+) sec", log)
+                t = re.search(r"Total encoding time for the seq\.\s*:\s*([0-9.]+) sec", log)
+                res[exe] = {"me_time_s": float(m.group(1)) if m else None, "total_s": float(t.group(1)) if t else None,
+                            "bitstream": open(os.path.join(od, "out.264"), "rb").read()}
+            a, b = res[exes[0]], res[exes[1]]
+            out["full_search" if mode == -1 else "fast_full_search"] = {
+                "stock_me_time_s": a["me_time_s"], "dropin_me_time_s": b["me_time_s"], "stock_total_s": a["total_s"], "dropin_total_s": b["total_s"],
+                "dropin": exes[1], "bitstreams_identical": a["bitstream"] == b["bitstream"]}
+    return out
+
+
 def _cpu_worker(job):
     """One process of the CPU reference arm: its own copy of the reference state, its own MB range."""
     first, cnt, trial = job
@@ -635,6 +669,8 @@ def main():
     # the integer search alone under less friendly predictors / content (k_sad_fs is data-dependent)
     roofline["robustness"] = robustness_block(local, sad_peak_tpel)
     cpu = None if args.no_cpu else cpu_reference(15.0)
+    if cpu is not None:
+        cpu["dropin_jm"] = dropin_leg()
     line = {"metric": UNIT, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
