@@ -125,11 +125,12 @@ struct FsCtl {                    // per window buffer: the pipeline between the
 
 constexpr int FS_DENSE = 12;     // candidates of a warp passing the cold path's test at once from which the dense collapse runs
 constexpr int FS_RCAP = 24;      // survivor records per warp and task
-struct FsWarp {
+struct __align__(16) FsWarp {
   unsigned short sat[2][28];     // fs_exact2's summed-area tables (row 0 / column 0 stay zero)
-  uint32_t rec[FS_RCAP];
+  uint32_t rec[FS_RCAP];         // records of the dense collapse; ALSO words 0..23 of the sparse cold path's staging (X, Y, X0 of one lane)
   int nrec;                      // records appended since the last flush (may exceed FS_RCAP: overflow)
 };
+constexpr int FS_SPARSE = 3;     // at most this many lanes of a warp pass the group filter at once: their packed sums cross through shared memory
 
 // partition p -> index into the u16 view of Cw (word*2 + half); p == 0 -> -1 (scalar C16)
 __device__ __forceinline__ int cmap(int p)
@@ -405,6 +406,37 @@ __device__ __noinline__ uint32_t fs_cold_lane(SLOT &S, FsWarp &ws, const uint32_
   return pass;
 }
 
+// Sparse cold path (the usual one: one to FS_SPARSE lanes of the warp passed the group filter).  The passing lane's packed sums
+// (X, Y, X0, Y0, E0 of its eight candidates) were staged in shared memory (ws.rec: 24 words, stg: 16 words); lane c of every
+// group of eight tests candidate c -- the hot path's filter without the minimum over the candidates -- so the eight tests run
+// side by side instead of one after the other (measured: the serial version read its operands back from LOCAL memory, which
+// with 229 KB of the SM carved out as shared memory misses L1: 8 260 warp-cycles per entry, 11 % of the kernel's warp time).
+// dxa, dy0, vm: the passing lane's (uniform).  Returns the pass bits of its candidates (uniform).
+template <class SLOT>
+__device__ __noinline__ uint32_t fs_cold_test8(SLOT &S, const FsWarp &ws, const uint32_t *stg, int b, int dxa, int dy0, uint32_t vm, int R)
+{
+  const int c = threadIdx.x & 7;
+  const int a = b - 1, bb = b >> 1;
+  const int x = dxa + 4 * (c >> 2), y = dy0 + (c & 3);
+  // valid candidates outside the rectangle / seed the producer's pre-pass evaluated exactly
+  const bool v = ((vm >> c) & 1u) && !(x >= S.prex && x < S.prex + S.prew && y >= S.prey && y < S.prey + S.preh) && !(x == S.seedx && y == S.seedy);
+  const uint32_t X = ld_vol(&ws.rec[c]), Y = ld_vol(&ws.rec[8 + c]), X0 = ld_vol(&ws.rec[16 + c]), Y0 = ld_vol(&stg[c]), E0 = ld_vol(&stg[8 + c]);
+  const uint32_t m = (uint32_t)S.mxs[x] + (uint32_t)S.mys[y];
+  const uint32_t XV = X + X0, YV = Y + Y0, E = XV + YV;
+  uint32_t t = __vimin3_s16x2(X0 + ld_vol(&S.Cw[3 * a]), Y0 + ld_vol(&S.Cw[3 * a + 1]), X0 + Y0 + ld_vol(&S.Cw[3 * a + 2]));
+  t = __vimin3_s16x2(t, X + ld_vol(&S.Cw[3 * b]), Y + ld_vol(&S.Cw[3 * b + 1]));
+  t = __vimin3_s16x2(t, X + Y + ld_vol(&S.Cw[3 * b + 2]), XV + ld_vol(&S.Cw[12 + 3 * bb]));
+  t = __vimin3_s16x2(t, YV + ld_vol(&S.Cw[13 + 3 * bb]), E + ld_vol(&S.Cw[14 + 3 * bb]));
+  int s16 = 0;
+  if (b == 3) {
+    const uint32_t top = (E0 & 0xffffu) + (E0 >> 16), bot = (E & 0xffffu) + (E >> 16);
+    t = __vimin3_s16x2(t, ((bot << 16) | top) + ld_vol(&S.Cw[18]), E0 + E + ld_vol(&S.Cw[19]));
+    s16 = (int)(top + bot) + *reinterpret_cast<const volatile int *>(&S.C16) + (int)m;
+  }
+  const bool ps = v && ((((t + m * 0x10001u) & 0x80008000u) != 0u) || s16 < 0);
+  return __ballot_sync(0xffffffffu, ps) & 0xffu;
+}
+
 __device__ __forceinline__ uint32_t min2s(uint32_t a, uint32_t b)
 {
   uint32_t r;
@@ -453,7 +485,7 @@ __device__ __forceinline__ uint32_t fs_cold_spill(SLOT &S, FsWarp &ws, const uin
 // registers) and record the (candidate, partition, SAD) triples that pass.  Returns the pass bits of the lane's candidates
 // (bit q*4+j), used only when the record list overflows.
 template <int PITCH, class SLOT>
-__device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, const uint8_t *wb, int dxa, int dy0, uint32_t vm, uint32_t mmin, uint32_t one, FsTaskCtx tc, int &ncold)
+__device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, uint32_t *stg, const uint8_t *wb, int dxa, int dy0, uint32_t vm, uint32_t mmin, uint32_t one, FsTaskCtx tc, int &ncold)
 {
   constexpr int K = 4;
   const uint4 *cur = reinterpret_cast<const uint4 *>(S.cur);
@@ -539,12 +571,34 @@ __device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, const uint8_t 
           }
         }
         const bool lp = vm != 0u && ((((rr + mm2) & 0x80008000u) != 0u) || s16 < 0);
-        if (__any_sync(0xffffffffu, lp)) {            // cold: a candidate of some lane may beat a partition's best
+        uint32_t bal = __ballot_sync(0xffffffffu, lp);
+        if (bal) {                                    // cold: a candidate of some lane may beat a partition's best
 #ifdef FS_PROFILE
           ncold++;
 #endif
-          if (lp) pass |= fs_cold_spill(S, ws, X, Y, X0, Y0, E0, 2 * bb + 1, dxa, dy0, vm, lanebits, tc);
-          __syncwarp();
+          if (__popc(bal) <= FS_SPARSE) {             // the usual case: the passing lanes one at a time, eight candidates side by side
+            const int lane = threadIdx.x & 31;
+#pragma unroll 1
+            while (bal) {
+              const int L = __ffs(bal) - 1; bal &= bal - 1;
+              if (lane == L) {
+                uint4 *d = reinterpret_cast<uint4 *>(ws.rec), *e = reinterpret_cast<uint4 *>(stg);
+                d[0] = make_uint4(X[0][0], X[0][1], X[0][2], X[0][3]); d[1] = make_uint4(X[1][0], X[1][1], X[1][2], X[1][3]);
+                d[2] = make_uint4(Y[0][0], Y[0][1], Y[0][2], Y[0][3]); d[3] = make_uint4(Y[1][0], Y[1][1], Y[1][2], Y[1][3]);
+                d[4] = make_uint4(X0[0][0], X0[0][1], X0[0][2], X0[0][3]); d[5] = make_uint4(X0[1][0], X0[1][1], X0[1][2], X0[1][3]);
+                e[0] = make_uint4(Y0[0][0], Y0[0][1], Y0[0][2], Y0[0][3]); e[1] = make_uint4(Y0[1][0], Y0[1][1], Y0[1][2], Y0[1][3]);
+                e[2] = make_uint4(E0[0][0], E0[0][1], E0[0][2], E0[0][3]); e[3] = make_uint4(E0[1][0], E0[1][1], E0[1][2], E0[1][3]);
+              }
+              __syncwarp();
+              const uint32_t bits = fs_cold_test8(S, ws, stg, 2 * bb + 1, __shfl_sync(0xffffffffu, dxa, L), __shfl_sync(0xffffffffu, dy0, L),
+                                                  __shfl_sync(0xffffffffu, vm, L), tc.R);
+              if (lane == L) pass |= bits;
+              __syncwarp();
+            }
+          } else {
+            if (lp) pass |= fs_cold_spill(S, ws, X, Y, X0, Y0, E0, 2 * bb + 1, dxa, dy0, vm, lanebits, tc);
+            __syncwarp();
+          }
         }
       }
     }
@@ -899,6 +953,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
   __shared__ unsigned long long evt;               // completes a phase whenever a worker finishes a unit: the producer sleeps on it
   constexpr int NT = (NWORK + 1) * 32;
   __shared__ FsWarp WS[NWORK + 1];
+  __shared__ __align__(16) uint32_t STG[NWORK][16];   // words 24..39 of the sparse cold path's staging (Y0, E0), per worker warp
   __shared__ uint32_t pgt[NPART];
   __shared__ FsCtaStats st;
   __shared__ int lastmv[16];                       // per reference slot: the 16x16 vector of the CTA's last finished item (0x7fff7fff: none)
@@ -1053,7 +1108,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         uint32_t pass = 0;
 #pragma unroll 1
         for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
-          pass |= fs_task4<PITCH>(S, WS[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, FsTaskCtx{t, R, g, a.lambda_f}, ncold);
+          pass |= fs_task4<PITCH>(S, WS[warp], STG[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, FsTaskCtx{t, R, g, a.lambda_f}, ncold);
         const long long tt1 = FS_CLOCK();
         c_task += tt1 - tt0;
         if (__any_sync(0xffffffffu, pass != 0u)) {                      // survivors (rare): out of line
