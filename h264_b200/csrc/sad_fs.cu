@@ -130,7 +130,10 @@ struct __align__(16) FsWarp {
   uint32_t rec[FS_RCAP];         // records of the dense collapse; ALSO words 0..23 of the sparse cold path's staging (X, Y, X0 of one lane)
   int nrec;                      // records appended since the last flush (may exceed FS_RCAP: overflow)
 };
-constexpr int FS_SPARSE = 3;     // at most this many lanes of a warp pass the group filter at once: their packed sums cross through shared memory
+#ifndef FS_SPARSEV
+#define FS_SPARSEV 3
+#endif
+constexpr int FS_SPARSE = FS_SPARSEV;     // at most this many lanes of a warp pass the group filter at once: their packed sums cross through shared memory
 
 // partition p -> index into the u16 view of Cw (word*2 + half); p == 0 -> -1 (scalar C16)
 __device__ __forceinline__ int cmap(int p)
@@ -183,16 +186,27 @@ __device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterp
 // for every partition of group g.  Called by a whole warp.
 template <int PITCH, class SLOT>
 __device__ __noinline__ void fs_exact2(SLOT &S, FsWarp &ws, const uint8_t *win, int copy_bytes, const uint32_t *pgt,
-                                       int dx0, int dy0, int dx1, int dy1, bool valid1, int R, int g, int lambda_f)
+                                       int dx0, int dy0, int dx1, int dy1, bool valid1, int R, int g, int lambda_f, const FsArgs *ga = nullptr)
 {
   const int lane = threadIdx.x & 31, half = lane >> 4, k = lane & 15, bx = k & 3, by = k >> 2;
   {
     const int col = (half ? dx1 : dx0) + 4 * bx, row = (half ? dy1 : dy0) + 4 * by;
-    const int c = col & 3;
-    const uint8_t *p = win + c * copy_bytes + (row + c) * PITCH + (col >> 2) * 4;
     uint32_t v = 0;
+    if (ga) {                                        // straight from the search planes (the producer's pre-pass, before the window exists):
+      const int X = S.wx0 + col, Y = S.wy0 + row;    // plane X & 3 holds the four bytes from column X as one aligned word
+      const int c = X & 3;
+      const uint8_t *p = ga->spl + ((size_t)(S.ref * 16 + c) * ga->Hq + Y) * ga->Wq + (X - c);
+      uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) v = sad4(S.cur[(by * 4 + i) * 4 + bx], *reinterpret_cast<const uint32_t *>(p + i * PITCH), v);
+      for (int i = 0; i < 4; i++) w[i] = __ldg(reinterpret_cast<const uint32_t *>(p + (size_t)i * ga->Wq));
+#pragma unroll
+      for (int i = 0; i < 4; i++) v = sad4(S.cur[(by * 4 + i) * 4 + bx], w[i], v);
+    } else {
+      const int c = col & 3;
+      const uint8_t *p = win + c * copy_bytes + (row + c) * PITCH + (col >> 2) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; i++) v = sad4(S.cur[(by * 4 + i) * 4 + bx], *reinterpret_cast<const uint32_t *>(p + i * PITCH), v);
+    }
     uint32_t t;
     t = __shfl_up_sync(0xffffffffu, v, 1, 16); if (bx >= 1) v += t;
     t = __shfl_up_sync(0xffffffffu, v, 2, 16); if (bx >= 2) v += t;
@@ -770,11 +784,63 @@ __device__ __forceinline__ void fs_setup_group(SLOT &S, int g, const FsArgs &a)
   __syncwarp();
 }
 
+// Initial bounds of a unit (exact evaluation of the first centre and of the seed candidate).  global: read the candidates from
+// the search planes in global memory -- the producer does that while the unit is still STAGED (fs_prepare), so that attaching
+// it to a window buffer later is only the window copy: the pre-pass is off the buffer's turn-around path.  Windows that leave
+// the search plane (clamped staging) keep the pre-pass on the staged window (fs_activate).
+template <int PITCH, class SLOT>
+__device__ __forceinline__ void fs_prepass(SLOT &S, FsWarp &ws, const uint8_t *win, const uint32_t *pgt, const FsArgs &a, const int *lastmv, bool global)
+{
+  const FsGeom G = fs_geom(a.R);
+  const int lane = threadIdx.x & 31, R = a.R;
+  // ---- initial bounds: exact pre-pass over the centres' box, plus ONE seed candidate: the 16x16 vector this CTA's last finished
+  //      item of the same reference ended on.  Any candidate may be evaluated first without changing the result (the argmin
+  //      is exact); when the predictor is wrong but the motion is coherent the seed brings the bounds down before the first
+  //      task instead of after the row group that holds the optimum (measured: 6.6 ms -> see DESIGN 4.1 for predictors off by
+  //      +-8 pel) ----
+  {
+    // FS_PRE < 0 (default): ONE candidate instead of the centres' box -- the centre of the group's first partition.  With one
+    // predictor per partition the box holds up to (1 + span)^2 candidates and their exact evaluation saturated the producer
+    // warp (measured: per-partition predictors 1.84 ms against 1.23 ms with shared ones); the other centres are ordinary
+    // candidates of the hot path.
+    int xlo, ylo, pw, ph;
+    if (FS_PRE >= 0) {
+      xlo = max(0, R - FS_PRE); ylo = max(0, R - FS_PRE);
+      pw = min(S.ncx - 1, R + S.spanx + FS_PRE) - xlo + 1; ph = min(S.ncy - 1, R + S.spany + FS_PRE) - ylo + 1;
+    } else {
+      int p0 = 0;
+      while (p0 < NPART - 1 && S.pgrp[p0] != S.g) p0++;
+      xlo = R + S.pex[p0]; ylo = R + S.pey[p0]; pw = 1; ph = 1;
+    }
+    int total = pw * ph;
+    int sdx = -1, sdy = -1;
+    {
+      const int sm = lastmv[S.ref & 15];
+      if (sm != 0x7fff7fff && !(a.flags & 4)) {
+        const int x = ((int)(short)(sm & 0xffff) >> 2) - S.gx0 + R, y = ((sm >> 16) >> 2) - S.gy0 + R;
+        const bool inbox = x >= xlo && x < xlo + pw && y >= ylo && y < ylo + ph;
+        if (x >= 0 && x < S.ncx && y >= 0 && y < S.ncy && !inbox) { sdx = x; sdy = y; }
+      }
+    }
+    if (lane == 0) { S.seedx = sdx; S.seedy = sdy; S.prex = xlo; S.prey = ylo; S.prew = pw; S.preh = ph; }
+    if (sdx >= 0) total++;
+    for (int i0 = 0; i0 < total; i0 += 2) {
+      const int i1 = i0 + 1;
+      const bool v1 = i1 < total;
+      const bool s0 = sdx >= 0 && i0 == total - 1, s1 = sdx >= 0 && i1 == total - 1;
+      const int dx0 = s0 ? sdx : xlo + i0 % pw, dy0 = s0 ? sdy : ylo + i0 / pw;
+      const int dx1 = !v1 ? dx0 : (s1 ? sdx : xlo + i1 % pw), dy1 = !v1 ? dy0 : (s1 ? sdy : ylo + i1 / pw);
+      fs_exact2<PITCH>(S, ws, win, G.copy_bytes, pgt, dx0, dy0, dx1, dy1, v1, R, S.g, a.lambda_f, global ? &a : nullptr);
+    }
+  }
+  __syncwarp();
+}
+
 // Loads item `item` (handed out in order by a global counter: load balance) into slot S and prepares its first
 // centre group; fetches the index of the following item into `item` while the loads are in flight.  Returns false
 // when the items are exhausted.  Touches no window: runs while the workers are busy.
 template <int PITCH, class SLOT>
-__device__ __noinline__ bool fs_prepare(SLOT &S, int &item_io, const FsArgs &a, FsCtaStats *st)
+__device__ __noinline__ bool fs_prepare(SLOT &S, int &item_io, const FsArgs &a, FsCtaStats *st, FsWarp &ws, const uint32_t *pgt, const int *lastmv)
 {
   const int lane = threadIdx.x & 31, R = a.R;
   for (;;) {
@@ -843,6 +909,11 @@ __device__ __noinline__ bool fs_prepare(SLOT &S, int &item_io, const FsArgs &a, 
     __syncwarp();
     if (ng == 0) continue;                         // no active partition: nothing to search, nothing to write
     fs_setup_group<PITCH>(S, 0, a);
+    if (S.inside) {                                // initial bounds now, from global memory: attaching the unit later is only the window copy
+      fs_prepass<PITCH>(S, ws, nullptr, pgt, a, lastmv, true);
+      if (lane == 0) S.inside = 2;
+      __syncwarp();
+    }
     return true;
   }
 }
@@ -852,7 +923,7 @@ __device__ __noinline__ bool fs_prepare(SLOT &S, int &item_io, const FsArgs &a, 
 // task counter second (see the worker loop).
 template <int PITCH, class SLOT>
 __device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWarp &ws, uint8_t *win, const uint32_t *pgt,
-                                         const FsArgs &a, const CUtensorMap *tm, FsCtaStats *st, const int *lastmv)
+                                         const FsArgs &a, const CUtensorMap *tm, FsCtaStats *st, int *lastmv, const SLOT *O = nullptr)
 {
   constexpr int K = FS_K;
   const FsGeom G = fs_geom(a.R);
@@ -868,11 +939,13 @@ __device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWa
         tma_load_3d(win + c * G.copy_bytes, tm, &C.mbar, (x0 + c) & ~15, y0 - c, S.ref * 16 + ((x0 + c) & 15));
     }
     __syncwarp();
+    if (O) { fs_write_results(*O, a, st, lastmv); __syncwarp(); }     // the finished unit's results, under the window copy
     const uint32_t parity = (uint32_t)C.tma_uses & 1u;
     while (!mbar_try_wait_ns(&C.mbar, parity, 2000u)) { if (a.flags & 2) __nanosleep(400); }
     __syncwarp();
     if (lane == 0) C.tma_uses++;
   } else {                                         // window leaves the search plane: per-pixel coordinate clamp
+    if (O) { fs_write_results(*O, a, st, lastmv); __syncwarp(); }
     const uint8_t *plane = a.spl + (size_t)S.ref * 16 * a.Wq * a.Hq;     // shift-0 plane
     const int nrows = min(K * S.ngy + 15, G.rows - 3), wpw = PITCH >> 2;
     for (int r = 0; r < nrows; r++) {
@@ -888,46 +961,7 @@ __device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWa
     }
   }
   __syncwarp();
-  // ---- initial bounds: exact pre-pass over the centres' box, plus ONE seed candidate: the 16x16 vector this CTA's last finished
-  //      item of the same reference ended on.  Any candidate may be evaluated first without changing the result (the argmin
-  //      is exact); when the predictor is wrong but the motion is coherent the seed brings the bounds down before the first
-  //      task instead of after the row group that holds the optimum (measured: 6.6 ms -> see DESIGN 4.1 for predictors off by
-  //      +-8 pel) ----
-  {
-    // FS_PRE < 0 (default): ONE candidate instead of the centres' box -- the centre of the group's first partition.  With one
-    // predictor per partition the box holds up to (1 + span)^2 candidates and their exact evaluation saturated the producer
-    // warp (measured: per-partition predictors 1.84 ms against 1.23 ms with shared ones); the other centres are ordinary
-    // candidates of the hot path.
-    int xlo, ylo, pw, ph;
-    if (FS_PRE >= 0) {
-      xlo = max(0, R - FS_PRE); ylo = max(0, R - FS_PRE);
-      pw = min(S.ncx - 1, R + S.spanx + FS_PRE) - xlo + 1; ph = min(S.ncy - 1, R + S.spany + FS_PRE) - ylo + 1;
-    } else {
-      int p0 = 0;
-      while (p0 < NPART - 1 && S.pgrp[p0] != S.g) p0++;
-      xlo = R + S.pex[p0]; ylo = R + S.pey[p0]; pw = 1; ph = 1;
-    }
-    int total = pw * ph;
-    int sdx = -1, sdy = -1;
-    {
-      const int sm = lastmv[S.ref & 15];
-      if (sm != 0x7fff7fff && !(a.flags & 4)) {
-        const int x = ((int)(short)(sm & 0xffff) >> 2) - S.gx0 + R, y = ((sm >> 16) >> 2) - S.gy0 + R;
-        const bool inbox = x >= xlo && x < xlo + pw && y >= ylo && y < ylo + ph;
-        if (x >= 0 && x < S.ncx && y >= 0 && y < S.ncy && !inbox) { sdx = x; sdy = y; }
-      }
-    }
-    if (lane == 0) { S.seedx = sdx; S.seedy = sdy; S.prex = xlo; S.prey = ylo; S.prew = pw; S.preh = ph; }
-    if (sdx >= 0) total++;
-    for (int i0 = 0; i0 < total; i0 += 2) {
-      const int i1 = i0 + 1;
-      const bool v1 = i1 < total;
-      const bool s0 = sdx >= 0 && i0 == total - 1, s1 = sdx >= 0 && i1 == total - 1;
-      const int dx0 = s0 ? sdx : xlo + i0 % pw, dy0 = s0 ? sdy : ylo + i0 / pw;
-      const int dx1 = !v1 ? dx0 : (s1 ? sdx : xlo + i1 % pw), dy1 = !v1 ? dy0 : (s1 ? sdy : ylo + i1 / pw);
-      fs_exact2<PITCH>(S, ws, win, G.copy_bytes, pgt, dx0, dy0, dx1, dy1, v1, R, S.g, a.lambda_f);
-    }
-  }
+  if (S.inside != 2) fs_prepass<PITCH>(S, ws, win, pgt, a, lastmv, false);
   __syncwarp();
   if (lane == 0) {
     // seqlock: the negative epoch marks "being re-armed" BEFORE any field changes, so that a worker that still holds
@@ -987,11 +1021,11 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
     long long p_busy = 0;                            // cycles spent attaching / writing / preparing (FS_PROFILE)
     if (lane == 0) item = atomicAdd(a.work_counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
-    bool staged = fs_prepare<PITCH>(SS[0], item, a, &st);
+    bool staged = fs_prepare<PITCH>(SS[0], item, a, &st, WS[warp], pgt, lastmv);
     for (int b = 0; b < 2; b++) {
       if (staged) {
         fs_activate<PITCH>(CB[b], SS[b], b, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st, lastmv);
-        staged = fs_prepare<PITCH>(SS[b == 0 ? 1 : 2], item, a, &st);
+        staged = fs_prepare<PITCH>(SS[b == 0 ? 1 : 2], item, a, &st, WS[warp], pgt, lastmv);
       } else if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int *>(&CB[b].ended) = 1; }
     }
     for (;;) {
@@ -1012,13 +1046,12 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         SLOT &O = SS[old];
         if (O.g + 1 < O.ngroups) {                   // next centre group of the same item, in place (rare)
           fs_setup_group<PITCH>(O, O.g + 1, a);
+          if (O.inside) { fs_prepass<PITCH>(O, WS[warp], nullptr, pgt, a, lastmv, true); if (lane == 0) O.inside = 2; __syncwarp(); }
           fs_activate<PITCH>(C, O, old, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st, lastmv);
         } else if (staged) {
-          fs_activate<PITCH>(C, SS[stage], stage, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st, lastmv);
-          fs_write_results(O, a, &st, lastmv);
-          __syncwarp();
+          fs_activate<PITCH>(C, SS[stage], stage, WS[warp], smem + b * G.slot_bytes, pgt, a, tmap, &st, lastmv, &O);
           stage = old;
-          staged = fs_prepare<PITCH>(SS[stage], item, a, &st);
+          staged = fs_prepare<PITCH>(SS[stage], item, a, &st, WS[warp], pgt, lastmv);
         } else {
           fs_write_results(O, a, &st, lastmv);
           __syncwarp();
