@@ -304,7 +304,8 @@ static int run_search(b2me_ctx *c, int mb_first, int mb_count, int ref_first, in
     const char *r = getenv("B2ME_FS_REP"); if (r) f.flags |= atoi(r) << 8;
     const char *z = getenv("B2ME_FS_SLEEP"); if (z && z[0] == '1') f.flags |= 2;
     const char *sd = getenv("B2ME_FS_NOSEED"); if (sd && sd[0] == '1') f.flags |= 4;
-    const char *k = getenv("B2ME_FS_CLAIM"); f.claim = k ? atoi(k) : 3; if (f.claim < 1) f.claim = 1; }
+    const char *nb = getenv("B2ME_FS_NOB"); if (nb && nb[0] == '1') f.flags |= 8;      /* timing probe: drops the type-B tasks (WRONG results) */
+    const char *k = getenv("B2ME_FS_CLAIM"); f.claim = k ? atoi(k) : (fs_geom_host(f.R).pitch == 96 ? 1 : 3); if (f.claim < 1) f.claim = 1; }   // measured: 18 tasks per unit and 4 workers want single claims (the tail), 68 tasks and 12 workers claims of 3
   f.work_counter = c->d_work;
   B2_CUDA_CHECK(c, cudaMemsetAsync(c->d_work, 0, sizeof(int), s));
   {

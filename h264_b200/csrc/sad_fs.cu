@@ -779,7 +779,7 @@ __device__ __forceinline__ void fs_setup_group(SLOT &S, int g, const FsArgs &a)
     S.wx0 = x0; S.wy0 = y0;
     S.inside = (x0 >= 0 && y0 >= 0 && x0 + ncx + 15 <= a.Wq && y0 + ncy + 15 <= a.Hq && !(a.flags & 1)) ? 1 : 0;
     S.ncx = ncx; S.ncy = ncy; S.ngy = ngy; S.gc = min(ngy - 1, (R + (spany >> 1)) / K);
-    S.ncbA = ncbA; S.ntaskA = ncbA * ngy; S.npb = npb; S.ntask = ncbA * ngy + (npb * ngy + 31) / 32;
+    S.ncbA = ncbA; S.ntaskA = ncbA * ngy; S.npb = npb; S.ntask = ncbA * ngy + ((a.flags & 8) ? 0 : (npb * ngy + 31) / 32);
   }
   __syncwarp();
 }
