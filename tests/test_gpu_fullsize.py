@@ -48,9 +48,10 @@ def test_1080p_4refs_sample_matches_oracle():
             assert (a[mb] == b[mb]).all(), (n, int(mb))
 
 
-def test_pool_1080p_16k_sample_matches_oracle():
-    """BASELINE config 5: 1080p range plane against a 16 K pool: sampled range blocks re-derived by brute force."""
-    W, H, nd = 1920, 1080, 16384
+@pytest.mark.parametrize("nd", [16384, 65536])
+def test_pool_1080p_sample_matches_oracle(nd):
+    """BASELINE config 5: 1080p range plane against a 16 K / 64 K pool: sampled range blocks re-derived by brute force."""
+    W, H = 1920, 1080
     fr = synth.luma_sequence(W, H, 2, seed=3)
     rp, dp = fr[1], fr[0]
     s = api.PoolSearcher(W, H, W, H, nd)
@@ -68,7 +69,7 @@ def test_pool_1080p_16k_sample_matches_oracle():
         c = np.trunc(a / 10).astype(np.int64); b = a - c * 10
         return np.where((b > 2) & (b < 8), c * 10 + 5, np.where(b > 7, (c + 1) * 10, c * 10))
 
-    for ri in rng.integers(0, s.nr, 24):
+    for ri in rng.integers(0, s.nr, 24 if nd <= 16384 else 10):
         bx, by = ri % (W // 8), ri // (W // 8)
         r0 = rp[by * 8:by * 8 + 8, bx * 8:bx * 8 + 8].reshape(64)
         best = (-1, 0, 0, 0)
