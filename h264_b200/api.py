@@ -209,6 +209,16 @@ class Searcher:
                   "b2me_distortion_candidates")
         return out
 
+    def epzs_search(self, jobs, preds, patterns):
+        """b2me_epzs_search: synth.EPZS_JOB records, preds [n][2] int16, synth.EPZS_PATTERN records -> synth.EPZS_RESULT records"""
+        from . import synth
+        jobs = np.ascontiguousarray(jobs, synth.EPZS_JOB); patterns = np.ascontiguousarray(patterns, synth.EPZS_PATTERN)
+        preds = np.ascontiguousarray(preds, np.int16).reshape(-1, 2)
+        out = np.zeros(len(jobs), synth.EPZS_RESULT)
+        self._chk(self.L.b2me_epzs_search(self.h, C.c_int(len(jobs)), _p(jobs), C.c_int(len(preds)), _p(preds), C.c_int(len(patterns)), _p(patterns), _p(out)),
+                  "b2me_epzs_search")
+        return out
+
     def block_search(self, pos_x, pos_y, blocktype, ref, pred_mv, center_mv, params, search_range):
         pm = (C.c_int16 * 2)(int(pred_mv[0]), int(pred_mv[1]))
         cm = (C.c_int16 * 2)(int(center_mv[0]), int(center_mv[1]))

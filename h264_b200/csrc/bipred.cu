@@ -272,6 +272,159 @@ __global__ void __launch_bounds__(128) k_cand_dist(const CandArgs a)
   if (lane == 0) a.out[i] = (long long)s << 5;
 }
 
+// ---- EPZS integer-pel search (JM/lencod/src/me_epzs.c:54-407 macroblock variant, :417-750 sub-macroblock variant) -------
+// One warp per job.  The control flow is scalar (every lane runs the same state machine); a search point's SAD is computed
+// by the 32 lanes together.  The reference's EPZSMap (one uint16 per window position, "visited in this call" = BlkCount) is a
+// per-warp list of the visited vectors here: a call visits tens of points, and membership is one strided compare.
+struct EpzsArgs {
+  const uint8_t *cur; int cur_pitch;
+  const uint8_t *planes; size_t plane_size;
+  int W, H, Wp, nrefs, njobs, npats;
+  const b2me_epzs_job *jobs; const int16_t *preds; const b2me_epzs_pattern *pats; b2me_epzs_result *out; int *errflag;
+};
+constexpr int EPZS_VCAP = 768;        // visited vectors per job (overflow: the job fails loudly)
+
+__device__ __forceinline__ bool epzs_visit(uint32_t *vis, int &nvis, int x, int y, bool &ovf)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t key = ((uint32_t)(x & 0xffff) << 16) | (uint32_t)(y & 0xffff);
+  bool hit = false;
+  for (int i = lane; i < nvis; i += 32) hit |= vis[i] == key;
+  if (__any_sync(0xffffffffu, hit)) return false;
+  if (nvis >= EPZS_VCAP) { ovf = true; return true; }
+  if (lane == 0) vis[nvis] = key;
+  nvis++;
+  __syncwarp();
+  return true;
+}
+
+__global__ void __launch_bounds__(128) k_epzs(const EpzsArgs a)
+{
+  __shared__ uint32_t s_vis[4][EPZS_VCAP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, ji = blockIdx.x * 4 + w;
+  if (ji >= a.njobs) return;
+  const b2me_epzs_job J = a.jobs[ji];
+  uint32_t *vis = s_vis[w];
+  int nvis = 0; bool ovf = false;
+  bool bad = J.blocktype < 1 || J.blocktype > 7 || J.ref < 0 || J.ref >= a.nrefs || J.pos_x < 0 || J.pos_y < 0;
+  const PartGeom gm = part_geom(part_first(bad ? 1 : J.blocktype));
+  const int bsx = gm.w, bsy = gm.h;
+  bad = bad || J.pos_x + bsx > a.W || J.pos_y + bsy > a.H;
+  const int pidx[5] = {J.pat_init, J.pat_sd, J.pat_sq, J.pat_else, J.pat_dual};
+  for (int i = 0; i < 5; i++) bad = bad || pidx[i] < 0 || pidx[i] >= a.npats;
+  if (bad) { if (lane == 0) { *a.errflag = 1; a.out[ji].cost = -1; a.out[ji].mv[0] = a.out[ji].mv[1] = 0; a.out[ji].early = 1; a.out[ji].npoints = 0; } return; }
+  const uint8_t *cur = a.cur + (size_t)J.pos_y * a.cur_pitch + J.pos_x;
+  BiArgs u; u.planes = a.planes; u.plane_size = a.plane_size; u.W = a.W; u.H = a.H; u.Wp = a.Wp;
+  int npts = 0;
+  auto sad = [&](int tx, int ty) -> long long {                  // computeSAD << 5 (me_distortion.c:349-426), no early exit
+    const uint8_t *r = bi_umv(u, J.ref, (J.pos_x << 2) + tx, (J.pos_y << 2) + ty);
+    int s = 0;
+    for (int k = lane; k < bsx * bsy; k += 32) {
+      const int x = k % bsx, y = k / bsx;
+      s += abs((int)cur[(size_t)y * a.cur_pitch + x] - (int)r[(size_t)y * a.Wp + x]);
+    }
+    npts++;
+    return (long long)__reduce_add_sync(0xffffffffu, s) << 5;
+  };
+  auto mvc = [&](int tx, int ty) -> long long { return (long long)J.lambda_factor * (mvbits(tx - J.pred[0]) + mvbits(ty - J.pred[1])); };
+  auto inrange = [&](int tx, int ty) -> bool { return abs(tx - J.mv[0]) <= J.range[0] && abs(ty - J.mv[1]) <= J.range[1]; };
+  const int mvx = J.mv[0], mvy = J.mv[1];
+  int tx = mvx, ty = mvy, t2x = 0, t2y = 0;                       // tmp (best), tmp2 (second best)
+  int early = 1;
+  const bool pgate = (J.flags & B2ME_EPZS_REFGT0_FRAME) != 0;
+  epzs_visit(vis, nvis, mvx, mvy, ovf);
+  long long minc = mvc(mvx, mvy);
+  minc += sad(mvx, mvy);
+  bool done = pgate && J.prev_sad < (J.stop0 < minc ? J.stop0 : minc);            // :118
+  if (!done && minc > J.stop0) {
+    const long long stop = J.stop;
+    if (minc < (stop >> 1)) done = true;                                          // :145
+    if (!done) {
+      bool checkMedian = false;
+      long long second = BI_DISTBLK_MAX;
+      const bool use[4] = {true, J.cond_host[1] && minc > stop, J.fixed_edge || (J.cond_host[2] && minc > 3 * stop),
+                           (J.cond_host[3] & 1) && ((J.cond_host[3] & 2) || minc > 2 * stop)};
+      int pi = J.pred_first;
+      for (int g = 0; g < 4; g++) {
+        for (int k = 0; k < J.npred[g]; k++, pi++) {
+          if (!use[g]) continue;
+          const int px = (int)(short)(a.preds[2 * pi] & (short)0xFFFC), py = (int)(short)(a.preds[2 * pi + 1] & (short)0xFFFC);   // set_integer_mv
+          if (!inrange(px, py)) continue;
+          if (!epzs_visit(vis, nvis, px, py, ovf)) continue;
+          long long mc = mvc(px, py);
+          if (mc < second) {
+            mc += sad(px, py);
+            if (mc < minc) { t2x = tx; t2y = ty; tx = px; ty = py; second = minc; minc = mc; checkMedian = true; }
+            else if (mc < second) { t2x = px; t2y = py; second = mc; checkMedian = true; }
+          }
+        }
+      }
+      if ((J.flags & B2ME_EPZS_EARLY34) && minc < ((3 * stop) >> 2)) done = true;  // :586 (sub-macroblock variant)
+      if (!done && minc > stop) {
+        int pat = J.pat_init;
+        if (J.flags & B2ME_EPZS_ADAPT) {
+          if (minc < stop + ((3 * J.medthres) >> 1))
+            pat = ((tx == 0 && ty == 0) || (abs(tx - mvx) < J.mv_range && abs(ty - mvy) < J.mv_range)) ? J.pat_sd : J.pat_sq;
+          else pat = J.pat_else;
+        }
+        int cx = tx, cy = ty;
+        int patternStop = 0, pointNumber = 0, nextLast = 0, motionDirection = 0;
+        for (int guard = 0; guard < 4 && !ovf; guard++) {
+          const b2me_epzs_pattern *P = &a.pats[pat];
+          int totalCheckPts = P->npoints;
+          int iter = 0;
+          do {
+            int checkPts = totalCheckPts;
+            do {
+              const int qx = cx + P->pt[pointNumber].dx, qy = cy + P->pt[pointNumber].dy;
+              if (inrange(qx, qy) && epzs_visit(vis, nvis, qx, qy, ovf)) {
+                long long mc = mvc(qx, qy);
+                if (mc < minc) {
+                  mc += sad(qx, qy);
+                  if (mc < minc) { tx = qx; ty = qy; minc = mc; motionDirection = pointNumber; }
+                }
+              }
+              ++pointNumber;
+              if (pointNumber >= P->npoints) pointNumber -= P->npoints;
+              checkPts--;
+            } while (checkPts > 0);
+            if (nextLast || (tx == cx && ty == cy)) {
+              patternStop = P->stop_search;
+              const int np = P->next_pattern;
+              if (np < 0 || np >= a.npats) { ovf = true; break; }
+              P = &a.pats[np];
+              totalCheckPts = P->npoints;
+              nextLast = P->next_last;
+              motionDirection = 0;
+              pointNumber = 0;
+            } else {
+              totalCheckPts = P->pt[motionDirection].next_points;
+              pointNumber = P->pt[motionDirection].start_nmbr;
+              cx = tx; cy = ty;
+            }
+            if (++iter > 4096) { ovf = true; break; }
+          } while (patternStop != 1);
+          if (ovf) break;
+          if (pgate && ((4 * J.prev_sad < minc) || ((3 * J.prev_sad < minc) && (J.prev_sad <= stop)))) { done = true; break; }   // :351
+          if (!(checkMedian && (J.flags & B2ME_EPZS_DUAL) && minc > stop)) break;
+          pointNumber = 0; patternStop = 0; motionDirection = 0; nextLast = 0;
+          if ((tx == 0 && ty == 0) || (tx == mvx && ty == mvy))
+            pat = (abs(tx - mvx) < J.mv_range && abs(ty - mvy) < J.mv_range) ? J.pat_sd : J.pat_sq;
+          else pat = J.pat_dual;
+          cx = t2x; cy = t2y;
+          checkMedian = false;
+        }
+      }
+    }
+  }
+  if (!done) early = 0;
+  if (lane == 0) {
+    if (ovf) { *a.errflag = 2; a.out[ji].cost = -1; }
+    else a.out[ji].cost = minc;
+    a.out[ji].mv[0] = (int16_t)tx; a.out[ji].mv[1] = (int16_t)ty; a.out[ji].early = (int16_t)early; a.out[ji].npoints = (int16_t)npts;
+  }
+}
+
 // ---- list_prediction_cost, list 0 (JM/lencod/src/mode_decision.c:275-300; update_mcost :256-267; ref_cost mv_search.h:114) ---
 // For the 21 (mode, block) entries of every macroblock: the reference minimising motion cost + lambda * refbits(ref),
 // first minimum in reference order; the motion cost of an 8x8 quadrant in modes 5..7 is the sum over its sub-partitions
@@ -402,6 +555,60 @@ extern "C" int b2me_distortion_candidates(b2me_ctx *c, int metric, int test8x8, 
     }
   }
   cudaFreeAsync(dc, c->stream); cudaFreeAsync(dout, c->stream);
+  return r;
+}
+
+extern "C" int b2me_epzs_search_dev(b2me_ctx *c, int njobs, const b2me_epzs_job *jobs_dev, const int16_t *preds_dev,
+                                    int npatterns, const b2me_epzs_pattern *patterns_dev, b2me_epzs_result *out_dev, void *stream)
+{
+  if (!c || njobs < 0 || npatterns < 1 || (njobs && (!jobs_dev || !patterns_dev || !out_dev))) return B2ME_EINVAL;
+  if (!njobs) return B2ME_OK;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->planes_pending && s != c->stream) B2_CUDA_CHECK(c, cudaStreamWaitEvent(s, c->ev_planes, 0));
+  EpzsArgs a;
+  a.cur = c->d_cur; a.cur_pitch = c->W; a.planes = c->d_planes; a.plane_size = c->plane_size;
+  a.W = c->W; a.H = c->H; a.Wp = c->Wp; a.nrefs = c->nrefs; a.njobs = njobs; a.npats = npatterns;
+  a.jobs = jobs_dev; a.preds = preds_dev; a.pats = patterns_dev; a.out = out_dev; a.errflag = c->d_errflag;
+  k_epzs<<<(njobs + 3) / 4, 128, 0, s>>>(a);
+  B2_CUDA_CHECK(c, cudaGetLastError());
+  c->launches++;
+  return B2ME_OK;
+}
+
+extern "C" int b2me_epzs_search(b2me_ctx *c, int njobs, const b2me_epzs_job *jobs, int npreds_total, const int16_t *preds,
+                                int npatterns, const b2me_epzs_pattern *patterns, b2me_epzs_result *out)
+{
+  if (!c || njobs < 0 || npreds_total < 0 || npatterns < 1 || (njobs && (!jobs || !patterns || !out)) || (npreds_total && !preds)) return B2ME_EINVAL;
+  if (!njobs) return B2ME_OK;
+  for (int i = 0; i < njobs; i++) {                   // every job's predictors lie inside the array handed over
+    const int n = jobs[i].npred[0] + jobs[i].npred[1] + jobs[i].npred[2] + jobs[i].npred[3];
+    if (jobs[i].pred_first < 0 || n < 0 || jobs[i].pred_first + n > npreds_total) return B2ME_EINVAL;
+  }
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const size_t bj = sizeof(b2me_epzs_job) * njobs, bp = ((sizeof(int16_t) * 2 * (size_t)npreds_total + 15) & ~(size_t)15) + 16;
+  const size_t bt = sizeof(b2me_epzs_pattern) * npatterns, bo = sizeof(b2me_epzs_result) * njobs;
+  uint8_t *d = nullptr;
+  B2_CUDA_CHECK(c, cudaMallocAsync(&d, bj + bp + bt + bo, c->stream));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(d, jobs, bj, cudaMemcpyHostToDevice, c->stream));
+  if (npreds_total) B2_CUDA_CHECK(c, cudaMemcpyAsync(d + bj, preds, sizeof(int16_t) * 2 * (size_t)npreds_total, cudaMemcpyHostToDevice, c->stream));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(d + bj + bp, patterns, bt, cudaMemcpyHostToDevice, c->stream));
+  int r = b2me_epzs_search_dev(c, njobs, reinterpret_cast<const b2me_epzs_job *>(d), reinterpret_cast<const int16_t *>(d + bj), npatterns,
+                               reinterpret_cast<const b2me_epzs_pattern *>(d + bj + bp), reinterpret_cast<b2me_epzs_result *>(d + bj + bp + bt), c->stream);
+  if (!r) {
+    int flag = 0;
+    cudaError_t e = cudaMemcpyAsync(out, d + bj + bp + bt, bo, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "b2me_epzs_search: %s", cudaGetErrorString(e)); r = B2ME_ECUDA; }
+    else if (flag) {
+      cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream);
+      snprintf(c->err, sizeof(c->err), flag == 2 ? "b2me_epzs_search: a job visited more search points than the device list holds, or names a pattern out of range"
+                                                 : "b2me_epzs_search: a job is out of range (blocktype, reference slot, position or pattern index)");
+      r = flag == 2 ? B2ME_EUNSUPPORTED : B2ME_EINVAL;
+    }
+  }
+  cudaFreeAsync(d, c->stream);
   return r;
 }
 

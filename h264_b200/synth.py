@@ -108,6 +108,15 @@ BIPRED_JOB = np.dtype([("min_mcost", np.int64), ("pos_x", np.int16), ("pos_y", n
                        ("pred1", np.int16, 2), ("pred2", np.int16, 2), ("mv1", np.int16, 2), ("mv2", np.int16, 2),
                        ("weight1", np.int16), ("weight2", np.int16), ("offset_bi", np.int16), ("reserved", np.int16)], align=True)
 BIPRED_RESULT = np.dtype([("cost_int", np.int64), ("cost_sub", np.int64), ("mv_int", np.int16, 2), ("mv_sub", np.int16, 2)], align=True)
+# include/b2me.h b2me_epzs_job / b2me_epzs_result / b2me_epzs_pattern (C layout, 104 / 16 / 112 bytes)
+EPZS_JOB = np.dtype([("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.int16), ("ref", np.int16), ("mv", np.int16, 2),
+                     ("pred", np.int16, 2), ("range", np.int16, 2), ("mv_range", np.int16), ("flags", np.int16), ("lambda_factor", np.int32),
+                     ("stop0", np.int64), ("stop", np.int64), ("medthres", np.int64), ("prev_sad", np.int64), ("pred_first", np.int32),
+                     ("npred", np.int16, 4), ("cond_host", np.int16, 4), ("fixed_edge", np.int16), ("pat_init", np.int16), ("pat_sd", np.int16),
+                     ("pat_sq", np.int16), ("pat_else", np.int16), ("pat_dual", np.int16), ("pad_", np.int16)], align=True)
+EPZS_RESULT = np.dtype([("cost", np.int64), ("mv", np.int16, 2), ("early", np.int16), ("npoints", np.int16)], align=True)
+EPZS_PATTERN = np.dtype([("npoints", np.int32), ("stop_search", np.int32), ("next_last", np.int32), ("next_pattern", np.int32),
+                         ("pt", np.int16, (12, 4))], align=True)
 CANDIDATE = np.dtype([("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.int16), ("ref", np.int16), ("mv", np.int16, 2)])
 _BS = {1: (16, 16), 2: (16, 8), 3: (8, 16), 4: (8, 8), 5: (8, 4), 6: (4, 8), 7: (4, 4)}
 

@@ -203,6 +203,61 @@ int b2me_distortion_candidates(b2me_ctx *ctx, int metric, int test8x8, int n, co
 int b2me_distortion_candidates_dev(b2me_ctx *ctx, int metric, int test8x8, int n, const b2me_candidate *cands_dev,
                                    int64_t *out_dev, void *stream);
 
+/* ---- EPZS integer-pel search on the device --------------------------------------------------------- */
+/* One job = one call of EPZS_motion_estimation (JM/lencod/src/me_epzs.c:54-407) or EPZS_subMB_motion_estimation (:417-750):
+ * the median check and its early exits, the predictor scan with best / second-best bookkeeping, the pattern refinement
+ * (small diamond / square / configured pattern, pattern chaining through nextpattern, the second-best "dual" round) and the
+ * prevSad exits run on the GPU, one warp per job, every distortion = computeSAD at an integer position (<< 5), every
+ * vector cost = lambda_factor * (mvbits(dx) + mvbits(dy)).  What stays with the caller is its STATE: the predictor values
+ * (spatial / memory / temporal / window / block-type predictors are functions of the neighbouring blocks' final vectors and of
+ * per-line memories), the stop criterion of EPZSDetermineStopCriterion (me_epzs_common.c:1764-1780) and prevSad; the pattern
+ * tables are handed over as data (the caller serialises its EPZSStructure objects, me_epzs_common.c:46-145).
+ * Predictor groups, in scan order: 0 always; 1 (temporal neighbours, me_epzs_common.c:1551) when cond_host[1] and
+ * min_mcost > stop; 2 (window predictors, me_epzs.c:141-150) when fixed_edge or (cond_host[2] and min_mcost > 3 * stop);
+ * 3 (block-type predictors, :156-159) when cond_host[3] & 1 and (cond_host[3] & 2 [ref == 0] or min_mcost > 2 * stop) --
+ * min_mcost = the median candidate's cost, as in the reference. */
+typedef struct b2me_epzs_point { int16_t dx, dy, start_nmbr, next_points; } b2me_epzs_point;
+typedef struct b2me_epzs_pattern {
+  int32_t npoints, stop_search, next_last, next_pattern;   /* next_pattern: index into the patterns array */
+  b2me_epzs_point pt[12];
+} b2me_epzs_pattern;                                        /* 112 bytes */
+#define B2ME_EPZS_REFGT0_FRAME 1    /* ref > 0 && structure == FRAME: the prevSad exits (me_epzs.c:118, 351) apply */
+#define B2ME_EPZS_EARLY34      2    /* sub-macroblock variant: stop after the predictors when min_mcost < 3 * stop >> 2 (:586) */
+#define B2ME_EPZS_ADAPT        4    /* EPZSPattern != 0: choose the refinement pattern from the cost (:268-284) */
+#define B2ME_EPZS_DUAL         8    /* the second-best round is allowed (EPZSDual > 0 and the slice / block-type condition, :366-368) */
+typedef struct b2me_epzs_job {
+  int16_t pos_x, pos_y;       /* luma position of the block */
+  int16_t blocktype;          /* 1..7 */
+  int16_t ref;                /* reference slot */
+  int16_t mv[2];              /* search centre at entry (quarter-pel) */
+  int16_t pred[2];            /* motion vector predictor (quarter-pel) */
+  int16_t range[2];           /* searchRange.max_x / max_y (quarter-pel) */
+  int16_t mv_range;           /* 10 (macroblock variant) / 12 (sub-macroblock variant) */
+  int16_t flags;              /* B2ME_EPZS_* */
+  int32_t lambda_factor;
+  int64_t stop0;              /* medthres[blocktype] + lambda_dist */
+  int64_t stop;               /* EPZSDetermineStopCriterion */
+  int64_t medthres;
+  int64_t prev_sad;           /* *prevSad at entry */
+  int32_t pred_first;         /* first predictor of this job in the predictor array */
+  int16_t npred[4];           /* predictors per group */
+  int16_t cond_host[4];
+  int16_t fixed_edge;
+  int16_t pat_init, pat_sd, pat_sq, pat_else, pat_dual;   /* pattern indices: configured, small diamond, square, the else branch of :281-284, searchPatternD */
+  int16_t pad_;
+} b2me_epzs_job;
+typedef struct b2me_epzs_result {
+  int64_t cost;               /* the function's return value */
+  int16_t mv[2];              /* *mv at return */
+  int16_t early;              /* 1: returned through an early exit (prevSad is not updated), 0: the final return */
+  int16_t npoints;            /* search points evaluated (distortion calls) */
+} b2me_epzs_result;
+/* preds: [npreds_total][2] int16 (the raw predictor vectors; set_integer_mv is applied on the device). */
+int b2me_epzs_search(b2me_ctx *ctx, int njobs, const b2me_epzs_job *jobs, int npreds_total, const int16_t *preds,
+                     int npatterns, const b2me_epzs_pattern *patterns, b2me_epzs_result *out);
+int b2me_epzs_search_dev(b2me_ctx *ctx, int njobs, const b2me_epzs_job *jobs_dev, const int16_t *preds_dev,
+                         int npatterns, const b2me_epzs_pattern *patterns_dev, b2me_epzs_result *out_dev, void *stream);
+
 /* ---- reference selection per (mode, block) (the first step of the mode decision) ------------------- */
 /* list_prediction_cost for list 0 (JM/lencod/src/mode_decision.c:275-300, update_mcost :256-267, ref_cost mv_search.h:114,
  * refbits mv_search.c:377-385) from the search's cost array, for every macroblock of the picture:

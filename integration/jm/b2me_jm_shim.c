@@ -46,7 +46,7 @@ static long g_clock;
 static StorablePicture *g_cur_pic;
 static int g_cur_poc = -0x7fffffff;
 static unsigned char *g_stage;
-static long g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_uploads;
+static long g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_uploads, g_calls_epzs, g_points_epzs;
 static int g_in_bipred;
 
 static void b2_fail(const char *what)
@@ -59,8 +59,8 @@ static void b2_fail(const char *what)
 static void b2_report(void)
 {
   if (getenv("B2ME_SHIM_VERBOSE"))
-    fprintf(stderr, "b2me shim: %ld integer searches, %ld sub-pel refinements, %ld bi-predictive calls, %ld distortion calls, %ld picture uploads, %lld kernel launches\n",
-            g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_uploads, g_ctx ? (long long)b2me_launch_count(g_ctx) : 0LL);
+    fprintf(stderr, "b2me shim: %ld integer searches, %ld sub-pel refinements, %ld bi-predictive calls, %ld distortion calls, %ld EPZS searches (%ld search points), %ld picture uploads, %lld kernel launches\n",
+            g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_calls_epzs, g_points_epzs, g_uploads, g_ctx ? (long long)b2me_launch_count(g_ctx) : 0LL);
   if (g_ctx) b2me_destroy(g_ctx);
   g_ctx = NULL;
 }
@@ -412,4 +412,64 @@ distblk fast_full_search_motion_estimation(Macroblock *currMB, MotionVector *pre
   mv_block->mv[list] = add_MVs(p_Vid->spiral_qpel_search[best_pos], offset);
   return min_mcost;
 }
+#endif
+
+#ifdef B2ME_SHIM_EPZS
+/* ---- SearchMode 3 (EPZS): the integer-pel stage on the GPU.  EPZS_motion_estimation (JM/lencod/src/me_epzs.c:54-407) and
+ * EPZS_subMB_motion_estimation (:417-750) are made weak in the reference's me_epzs.o (objcopy on the object compiled from the
+ * unmodified source) and defined here.  What stays on the host is the encoder's STATE, gathered with the reference's own helper
+ * functions of me_epzs_common.o (declared in me_epzs_common.h:101-107): the predictor vectors, the stop criterion, prevSad,
+ * the pattern tables (serialised from the live EPZSStructure objects).  The reference generates some predictor groups only
+ * when the median candidate's cost exceeds a multiple of the stop criterion; here every group is generated, with the host part
+ * of its condition, and the device applies the cost part (include/b2me.h b2me_epzs_job).  One launch per call (the median check,
+ * the predictor scan and the whole pattern refinement) instead of one per search point. ---- */
+#include "b2me_jm_epzs_job.h"
+
+static distblk b2_epzs(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, int lambda_factor, int submb)
+{
+  Slice *currSlice = currMB->p_Slice;
+  VideoParameters *p_Vid = currMB->p_Vid;
+  InputParameters *p_Inp = currMB->p_Inp;
+  EPZSParameters *p_EPZS = currSlice->p_EPZS;
+  const int blocktype = mv_block->blocktype, list = mv_block->list, cur_list = list + currMB->list_offset;
+  const short ref = mv_block->ref_idx;
+  MotionVector *mv = &mv_block->mv[list];
+  StorablePicture *ref_picture = currSlice->listX[cur_list][ref];
+  distblk *prevSad = &p_EPZS->distortion[cur_list][blocktype - 1][mv_block->pos_x2];
+  MotionVector *p_motion = NULL;
+  b2me_epzs_job J;
+  b2me_epzs_result R;
+  int16_t pv[2 * B2_EPZS_MAXPRED];
+  int ntot;
+
+  b2_ensure_ctx(currMB);
+  b2_check_config(currMB, mv_block);
+  if (mv_block->apply_weights) b2_fail("weighted-prediction ME is not supported by the EPZS shim");
+  b2_ensure_cur(p_Vid);
+  if (p_Inp->EPZSSpatialMem) {
+#if EPZSREF
+    p_motion = &p_EPZS->p_motion[cur_list][ref][blocktype - 1][mv_block->block_y][mv_block->pos_x2];
+#else
+    p_motion = &p_EPZS->p_motion[cur_list][blocktype - 1][mv_block->block_y][mv_block->pos_x2];
+#endif
+  }
+  ntot = b2_epzs_build_job(currMB, pred_mv, mv_block, lambda_factor, submb, b2_ref_slot(ref_picture), &J, pv);
+  ++p_EPZS->BlkCount;
+  if (p_EPZS->BlkCount == 0) ++p_EPZS->BlkCount;
+  if (b2me_epzs_search(g_ctx, 1, &J, ntot, pv, g_npat, g_pat, &R) != B2ME_OK) b2_fail("b2me_epzs_search failed");
+  g_calls_epzs++; g_points_epzs += R.npoints;
+  if (!R.early && ((ref == 0) || (*prevSad > (distblk)R.cost))) *prevSad = (distblk)R.cost;
+#if EPZSREF
+  if (p_Inp->EPZSSpatialMem)
+#else
+  if (p_Inp->EPZSSpatialMem && ref == 0)
+#endif
+  { p_motion->mv_x = R.mv[0]; p_motion->mv_y = R.mv[1]; }
+  mv->mv_x = R.mv[0]; mv->mv_y = R.mv[1];
+  return (distblk)R.cost;
+}
+distblk EPZS_motion_estimation(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor)
+{ (void)min_mcost; return b2_epzs(currMB, pred_mv, mv_block, lambda_factor, 0); }
+distblk EPZS_subMB_motion_estimation(Macroblock *currMB, MotionVector *pred_mv, MEBlock *mv_block, distblk min_mcost, int lambda_factor)
+{ (void)min_mcost; return b2_epzs(currMB, pred_mv, mv_block, lambda_factor, 1); }
 #endif

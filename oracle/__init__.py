@@ -193,6 +193,15 @@ class OrcFrame:
         self.L.orc_distortion_candidates(self.h, C.c_int(metric), C.c_int(int(test8x8)), C.c_int(len(cands)), _ptr(cands), _ptr(out))
         return out
 
+    def epzs_search(self, jobs, preds, patterns):
+        """orc_epzs_search (EPZS_motion_estimation / EPZS_subMB_motion_estimation restated over include/b2me.h's job records)"""
+        from h264_b200 import synth
+        jobs = np.ascontiguousarray(jobs, synth.EPZS_JOB); patterns = np.ascontiguousarray(patterns, synth.EPZS_PATTERN)
+        preds = np.ascontiguousarray(preds, np.int16).reshape(-1, 2)
+        out = np.zeros(len(jobs), synth.EPZS_RESULT)
+        self.L.orc_epzs_search(self.h, C.c_int(len(jobs)), _ptr(jobs), _ptr(preds), C.c_int(len(patterns)), _ptr(patterns), _ptr(out))
+        return out
+
     def planes(self, r):
         Hp, Wp = self.H + 2 * PAD_Y, self.W + 2 * PAD_X
         p = self.L.orc_frame_planes(self.h, C.c_int(r))

@@ -648,3 +648,116 @@ void orc_select_refs(int nmb, int nrefs, const int64_t *cost, int ref_lambda, in
       best_ref[(size_t)mb * 21 + e] = (int8_t)br; best_cost[(size_t)mb * 21 + e] = bm;
     }
 }
+
+/* ------------------------------------------------------------------------------------
+ * EPZS integer-pel search: EPZS_motion_estimation JM/lencod/src/me_epzs.c:54-407 and its sub-macroblock twin
+ * EPZS_subMB_motion_estimation :417-750, restated over the job the C ABI defines (include/b2me.h b2me_epzs_job): what the two
+ * functions read from encoder state -- predictor vectors, EPZSDetermineStopCriterion (me_epzs_common.c:1764-1780), prevSad,
+ * the EPZSStructure pattern tables (:46-145) -- arrives as data; everything they compute is here:
+ *   median candidate (:104-110), prevSad exit (:118), stop test and half-threshold exit (:133-156), predictor scan with the
+ *   EPZSMap test, best / second-best bookkeeping (:213-252), [sub-MB: three-quarter exit :586], pattern choice (:262-285),
+ *   refinement loop with pattern chaining (:290-345), prevSad exit (:351), the second-best round (:366-390).
+ * The EPZSMap (visited in this call) is a byte map over the window here.
+ * ---------------------------------------------------------------------------------- */
+typedef struct { int16_t dx, dy, start_nmbr, next_points; } OrcEpzsPoint;
+typedef struct { int32_t npoints, stop_search, next_last, next_pattern; OrcEpzsPoint pt[12]; } OrcEpzsPattern;
+typedef struct {
+  int16_t pos_x, pos_y, blocktype, ref, mv[2], pred[2], range[2], mv_range, flags;
+  int32_t lambda_factor;
+  int64_t stop0, stop, medthres, prev_sad;
+  int32_t pred_first;
+  int16_t npred[4], cond_host[4], fixed_edge, pat_init, pat_sd, pat_sq, pat_else, pat_dual, pad_;
+} OrcEpzsJob;
+typedef struct { int64_t cost; int16_t mv[2], early, npoints; } OrcEpzsResult;
+
+typedef struct { const OrcFrame *f; const uint8_t *pl; const uint8_t *cur; const OrcEpzsJob *J; int bsx, bsy, npts; uint8_t *map; int mw, mh; } OrcEpzsCtx;
+static int64_t oe_sad(OrcEpzsCtx *c, int tx, int ty)
+{
+  c->npts++;
+  return ((int64_t)orc_sad(c->pl, c->f->W, c->f->H, c->cur, c->f->W, c->bsx, c->bsy, (c->J->pos_x << 2) + tx, (c->J->pos_y << 2) + ty)) << 5;
+}
+static int64_t oe_mvc(const OrcEpzsJob *J, int tx, int ty) { return (int64_t)J->lambda_factor * (orc_mvbits(tx - J->pred[0]) + orc_mvbits(ty - J->pred[1])); }
+static int oe_in(const OrcEpzsJob *J, int tx, int ty) { return abs(tx - J->mv[0]) <= J->range[0] && abs(ty - J->mv[1]) <= J->range[1]; }
+static int oe_visit(OrcEpzsCtx *c, int tx, int ty)       /* 1: first visit (now marked) */
+{
+  uint8_t *m = &c->map[(size_t)(ty - c->J->mv[1] + c->J->range[1]) * c->mw + (tx - c->J->mv[0] + c->J->range[0])];
+  if (*m) return 0;
+  *m = 1; return 1;
+}
+void orc_epzs_search(void *h, int njobs, const OrcEpzsJob *jobs, const int16_t *preds, int npats, const OrcEpzsPattern *pats, OrcEpzsResult *out)
+{
+  const OrcFrame *f = (const OrcFrame *)h; int ji;
+  for (ji = 0; ji < njobs; ji++) {
+    const OrcEpzsJob *J = &jobs[ji];
+    OrcEpzsCtx c;
+    int tx = J->mv[0], ty = J->mv[1], t2x = 0, t2y = 0, done = 0;
+    int64_t minc;
+    const int pgate = (J->flags & 1) != 0;
+    c.f = f; c.J = J; c.pl = orc_frame_planes(h, J->ref); c.cur = f->cur + (size_t)J->pos_y * f->W + J->pos_x;
+    c.bsx = ORC_BS[J->blocktype][0]; c.bsy = ORC_BS[J->blocktype][1]; c.npts = 0;
+    c.mw = 2 * J->range[0] + 1; c.mh = 2 * J->range[1] + 1;
+    c.map = (uint8_t *)calloc((size_t)c.mw * c.mh, 1);
+    oe_visit(&c, tx, ty);
+    minc = oe_mvc(J, tx, ty) + oe_sad(&c, tx, ty);
+    if (pgate && J->prev_sad < (J->stop0 < minc ? J->stop0 : minc)) done = 1;
+    if (!done && minc > J->stop0) {
+      const int64_t stop = J->stop;
+      if (minc < (stop >> 1)) done = 1;
+      if (!done) {
+        int checkMedian = 0, g, k, pi = J->pred_first;
+        int64_t second = DISTBLK_MAX_ORC;
+        int use[4];
+        use[0] = 1; use[1] = J->cond_host[1] && minc > stop; use[2] = J->fixed_edge || (J->cond_host[2] && minc > 3 * stop);
+        use[3] = (J->cond_host[3] & 1) && ((J->cond_host[3] & 2) || minc > 2 * stop);
+        for (g = 0; g < 4; g++)
+          for (k = 0; k < J->npred[g]; k++, pi++) {
+            int px, py; int64_t mc;
+            if (!use[g]) continue;
+            px = (int16_t)(preds[2 * pi] & 0xFFFC); py = (int16_t)(preds[2 * pi + 1] & 0xFFFC);     /* set_integer_mv :40-44 */
+            if (!oe_in(J, px, py) || !oe_visit(&c, px, py)) continue;
+            mc = oe_mvc(J, px, py);
+            if (mc >= second) continue;
+            mc += oe_sad(&c, px, py);
+            if (mc < minc) { t2x = tx; t2y = ty; tx = px; ty = py; second = minc; minc = mc; checkMedian = 1; }
+            else if (mc < second) { t2x = px; t2y = py; second = mc; checkMedian = 1; }
+          }
+        if ((J->flags & 2) && minc < ((3 * stop) >> 2)) done = 1;
+        if (!done && minc > stop) {
+          int pat = J->pat_init, cx, cy, round;
+          if (J->flags & 4) {
+            if (minc < stop + ((3 * J->medthres) >> 1))
+              pat = ((tx == 0 && ty == 0) || (abs(tx - J->mv[0]) < J->mv_range && abs(ty - J->mv[1]) < J->mv_range)) ? J->pat_sd : J->pat_sq;
+            else pat = J->pat_else;
+          }
+          cx = tx; cy = ty;
+          for (round = 0; round < 2; round++) {
+            const OrcEpzsPattern *P = &pats[pat];
+            int total = P->npoints, point = 0, pstop = 0, last = 0, dir = 0;
+            do {
+              int n = total;
+              while (n-- > 0) {
+                const int qx = cx + P->pt[point].dx, qy = cy + P->pt[point].dy;
+                if (oe_in(J, qx, qy) && oe_visit(&c, qx, qy)) {
+                  int64_t mc = oe_mvc(J, qx, qy);
+                  if (mc < minc) { mc += oe_sad(&c, qx, qy); if (mc < minc) { tx = qx; ty = qy; minc = mc; dir = point; } }
+                }
+                if (++point >= P->npoints) point -= P->npoints;
+              }
+              if (last || (tx == cx && ty == cy)) { pstop = P->stop_search; P = &pats[P->next_pattern]; total = P->npoints; last = P->next_last; dir = 0; point = 0; }
+              else { total = P->pt[dir].next_points; point = P->pt[dir].start_nmbr; cx = tx; cy = ty; }
+            } while (pstop != 1);
+            if (pgate && ((4 * J->prev_sad < minc) || ((3 * J->prev_sad < minc) && (J->prev_sad <= stop)))) { done = 1; break; }
+            if (!(checkMedian && (J->flags & 8) && minc > stop)) break;
+            if ((tx == 0 && ty == 0) || (tx == J->mv[0] && ty == J->mv[1]))
+              pat = (abs(tx - J->mv[0]) < J->mv_range && abs(ty - J->mv[1]) < J->mv_range) ? J->pat_sd : J->pat_sq;
+            else pat = J->pat_dual;
+            cx = t2x; cy = t2y; checkMedian = 0;
+          }
+        }
+      }
+    }
+    free(c.map);
+    out[ji].cost = minc; out[ji].mv[0] = (int16_t)tx; out[ji].mv[1] = (int16_t)ty; out[ji].early = (int16_t)done; out[ji].npoints = (int16_t)c.npts;
+  }
+  (void)npats;
+}

@@ -107,6 +107,33 @@ def test_epzs_with_every_distortion_on_the_gpu_is_bit_identical():
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(not (have and os.path.exists(os.path.join(REF, "lencod_b2e"))), reason="oracle/_ref/lencod_b2e not built")
+@pytest.mark.parametrize("frames,nrefs,sr,extra", [
+    (6, 2, 16, ("EPZSSubPelME=2", "EPZSSubPelGrid=0")),                                              # P slices, two references (the prevSad exits of ref > 0)
+    (4, 1, 32, ("EPZSSubPelME=2", "EPZSSubPelGrid=0", "EPZSPattern=5", "EPZSDualRefinement=6")),     # PMVFAST pattern chain, dual refinement with the large diamond
+    (5, 2, 8, ("EPZSSubPelME=2", "EPZSSubPelMEBiPred=2", "EPZSSubPelGrid=0", "NumberBFrames=1", "HierarchicalCoding=0", "BReferencePictures=0",
+               "QPBSlice=30", "BList1References=1", "EPZSFixedPredictors=3", "EPZSTemporal=1", "EPZSSpatialMem=1", "EPZSBlockType=1")),   # B slices: list 1, temporal + memory predictors
+])
+def test_epzs_integer_search_on_the_gpu_is_bit_identical(frames, nrefs, sr, extra):
+    """lencod_b2e: EPZS_motion_estimation / EPZS_subMB_motion_estimation (JM/lencod/src/me_epzs.c:54-407, :417-750)
+    served by b2me_epzs_search -- median check, predictor scan, pattern refinement and the dual round on the device, one call per
+    block; predictors, thresholds and pattern tables are the reference's own (me_epzs_common.o)."""
+    W, H = 176, 144
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(W, H, frames, seed=31))
+        a = _encode("lencod", yuv, W, H, frames, os.path.join(d, "stock"), nrefs=nrefs, search_range=sr, qp=28, search_mode=3, extra=extra)
+        b = _encode("lencod_b2e", yuv, W, H, frames, os.path.join(d, "b2"), nrefs=nrefs, search_range=sr, qp=28, search_mode=3, extra=extra,
+                    env={"B2ME_SHIM_VERBOSE": "1"})
+        assert len(a[0]) > 1000
+        assert a[0] == b[0], "bitstreams differ"
+        assert a[1] == b[1], "reconstructions differ"
+        import re
+        m = re.search(r"(\d+) EPZS searches \((\d+) search points\)", b[2])
+        assert m and int(m.group(1)) > 1000 and int(m.group(2)) > int(m.group(1)), b[2][-400:]
+
+
+@pytest.mark.gpu
 @pytest.mark.skipif(not (have and os.path.exists(os.path.join(REF, "lencod_b2t"))), reason="oracle/_ref/lencod_b2t not built")
 @pytest.mark.parametrize("qp", [32])
 def test_lencod_with_cuda_transform_quant_is_bit_identical(qp):

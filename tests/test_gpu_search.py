@@ -336,3 +336,79 @@ def test_sad_table_matches_oracle_distortions():
         exp = of.distortion_candidates(cands, 0) >> 5
         got = np.array([tab[p, pos] for p, pos in picks], np.int64)
         assert (got == exp).all(), np.flatnonzero(got != exp)[:5]
+
+
+def test_epzs_search_matches_oracle_and_reference_golden():
+    """b2me_epzs_search (k_epzs, one warp per job) against the oracle on the jobs captured from stock lencod runs, and against what
+    the unmodified EPZS_motion_estimation / EPZS_subMB_motion_estimation returned for them (tests/golden/jm_epzs.npz):
+    cost, vector, exit path and the number of search points, bit for bit."""
+    from test_oracle_jm import _epzs_golden
+    n = 0
+    for tag, poc, cur, refs, R, jobs, preds, pats, res in _epzs_golden():
+        H, W = cur.shape
+        s = api.Searcher(W, H, len(refs), R)
+        s.set_cur(cur)
+        for r, rf in enumerate(refs):
+            s.set_ref(r, rf)
+        out = s.epzs_search(jobs, preds, pats)
+        exp = oracle.OrcFrame(cur, refs, R).epzs_search(jobs, preds, pats)
+        for k in ("cost", "mv", "early", "npoints"):
+            assert (out[k] == exp[k]).all(), (tag, poc, k)
+        assert (out["cost"] == res[:, 0]).all() and (out["mv"][:, 0] == res[:, 1]).all() and (out["mv"][:, 1] == res[:, 2]).all()
+        n += len(jobs)
+    assert n > 5000
+
+
+def test_epzs_search_synthetic_jobs_and_errors():
+    """Jobs the captures do not hold: blocks at the picture border with vectors far outside (the padded planes' clamp), every block
+    type, search windows of +-64, a pattern that chains to another one; then the error codes (pattern index out of range,
+    predictor range outside the array)."""
+    rng = np.random.default_rng(11)
+    W, H, R = 128, 96, 64
+    fr = synth.luma_sequence(W, H, 3, seed=4)
+    s = api.Searcher(W, H, 2, R)
+    s.set_cur(fr[2]); s.set_ref(0, fr[1]); s.set_ref(1, fr[0])
+    o = oracle.OrcFrame(fr[2], [fr[1], fr[0]], R)
+    pats = np.zeros(3, synth.EPZS_PATTERN)
+    sd = [(0, 4, 3, 3), (4, 0, 0, 3), (0, -4, 1, 3), (-4, 0, 2, 3)]
+    sq = [(0, 4, 7, 3), (4, 4, 7, 5), (4, 0, 1, 3), (4, -4, 1, 5), (0, -4, 3, 3), (-4, -4, 3, 5), (-4, 0, 5, 3), (-4, 4, 5, 5)]
+    ld = [(0, 8, 6, 5), (4, 4, 0, 3), (8, 0, 0, 5), (4, -4, 2, 3), (0, -8, 2, 5), (-4, -4, 4, 3), (-8, 0, 4, 5), (-4, 4, 6, 3)]
+    for i, (pts, stop, nxt) in enumerate(((sd, 1, 0), (sq, 1, 1), (ld, 0, 0))):       # the third chains to the small diamond
+        pats[i]["npoints"] = len(pts); pats[i]["stop_search"] = stop; pats[i]["next_last"] = 1; pats[i]["next_pattern"] = nxt
+        pats[i]["pt"][:len(pts)] = pts
+    sizes = {1: (16, 16), 2: (16, 8), 3: (8, 16), 4: (8, 8), 5: (8, 4), 6: (4, 8), 7: (4, 4)}
+    n = 600
+    jobs = np.zeros(n, synth.EPZS_JOB)
+    preds = rng.integers(-4 * 70, 4 * 70, (n * 12, 2)).astype(np.int16)
+    for i in range(n):
+        bt = 1 + i % 7
+        bw, bh = sizes[bt]
+        j = jobs[i]
+        j["blocktype"] = bt; j["ref"] = i % 2
+        j["pos_x"] = rng.integers(0, (W - bw) // 4 + 1) * 4 if i % 5 else (0 if i % 2 else W - bw)
+        j["pos_y"] = rng.integers(0, (H - bh) // 4 + 1) * 4 if i % 3 else (0 if i % 2 else H - bh)
+        j["mv"] = rng.integers(-40, 41, 2) * 4
+        j["pred"] = j["mv"] + rng.integers(-3, 4, 2)
+        j["range"] = (4 * R, 4 * R) if i % 4 else (4 * 8, 4 * 16)
+        j["mv_range"] = 10 if bt < 5 else 12
+        j["flags"] = (1 if j["ref"] else 0) | (2 if bt > 4 else 0) | (4 if i % 6 else 0) | (8 if i % 3 else 0)
+        j["lambda_factor"] = int(rng.integers(1, 2000))
+        j["medthres"] = int(rng.integers(0, 3000)) << 5
+        j["stop0"] = j["medthres"] + 2 * j["lambda_factor"]
+        j["stop"] = int(rng.integers(0, 20000)) << 5 if i % 7 else 0
+        j["prev_sad"] = int(rng.integers(0, 30000)) << 5
+        j["pred_first"] = 12 * i
+        j["npred"] = (5, 2, 3, 2); j["cond_host"] = (1, i % 2, (i >> 1) % 2, i % 4); j["fixed_edge"] = 1 if i % 11 == 0 else 0
+        j["pat_init"] = 2 if i % 2 else 1; j["pat_sd"] = 0; j["pat_sq"] = 1; j["pat_else"] = 1 if i % 3 else 2; j["pat_dual"] = 2 if i % 5 else 0
+    out = s.epzs_search(jobs, preds, pats)
+    exp = o.epzs_search(jobs, preds, pats)
+    for k in ("cost", "mv", "early", "npoints"):
+        assert (out[k] == exp[k]).all(), k
+    assert out["npoints"].max() > 30 and (out["early"] == 0).any() and (out["early"] == 1).any()
+    bad = jobs[:4].copy(); bad["pat_dual"] = 3
+    with pytest.raises(RuntimeError, match="out of range"):
+        s.epzs_search(bad, preds, pats)
+    bad = jobs[:4].copy(); bad["pred_first"] = len(preds) - 3
+    with pytest.raises(RuntimeError):
+        s.epzs_search(bad, preds, pats)
+    assert (s.epzs_search(jobs[:8], preds, pats)["cost"] == exp["cost"][:8]).all()      # the context still works afterwards

@@ -256,3 +256,31 @@ def test_reference_selection_equals_live_reference():
             for e, (mode, blk) in enumerate(oracle.SELECT_ENTRIES):
                 c = [int(cost[mb, r, parts[e]].sum()) for r in range(nrefs)]
                 assert jm.list_prediction_cost(mode, blk, c, 187) == (int(br[mb, e]), int(bc[mb, e])), (nrefs, mb, e)
+
+
+def _epzs_golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "jm_epzs.npz"))
+    for tag in ("a", "b"):
+        W, H, R, nrefs = int(g[f"{tag}_W"]), int(g[f"{tag}_H"]), int(g[f"{tag}_R"]), int(g[f"{tag}_nrefs"])
+        jobs, preds, res, jpoc, pats = g[f"{tag}_jobs"], g[f"{tag}_preds"], g[f"{tag}_results"], g[f"{tag}_job_poc"], g[f"{tag}_patterns"]
+        for poc in g[f"{tag}_pocs"]:
+            refs = [g[f"{tag}_ref_{poc}_{r}"] for r in range(nrefs) if f"{tag}_ref_{poc}_{r}" in g]
+            sel = np.nonzero(jpoc == poc)[0]
+            yield tag, int(poc), g[f"{tag}_cur_{poc}"], refs, R, jobs[sel], preds, pats, res[sel]
+
+
+def test_epzs_restatement_matches_reference_golden():
+    """orc_epzs_search against what the UNMODIFIED EPZS_motion_estimation / EPZS_subMB_motion_estimation returned for the same
+    jobs in stock lencod runs (tests/golden/jm_epzs.npz, oracle/gen_golden_epzs.py): cost and vector of 5 684 calls -- two
+    references with the prevSad exits, every predictor group, the extended-diamond and the PMVFAST pattern chains, the dual round."""
+    n = 0
+    kinds = set()
+    for tag, poc, cur, refs, R, jobs, preds, pats, res in _epzs_golden():
+        fr = oracle.OrcFrame(cur, refs, R)
+        out = fr.epzs_search(jobs, preds, pats)
+        assert (out["cost"] == res[:, 0]).all(), (tag, poc)
+        assert (out["mv"][:, 0] == res[:, 1]).all() and (out["mv"][:, 1] == res[:, 2]).all(), (tag, poc)
+        n += len(jobs)
+        kinds |= {(int(e), int(f) & 2) for e, f in zip(out["early"], jobs["flags"])}
+    assert n > 5000 and len(kinds) == 4          # early and final returns of both variants occur
