@@ -299,6 +299,52 @@ def bands_leg(local, rank, world, steps=5):
     barrier()
     t = torch.tensor([sum(e[0].elapsed_time(e[2]) for e in evs) / steps, sum(e[0].elapsed_time(e[1]) for e in evs) / steps],
                      dtype=torch.float64, device=dev)
+    # ---- config 4's EPZS half: the EPZS integer search (b2me_epzs_search_dev, one warp per block) of every partition of the
+    #      band's macroblocks on the same planes.  Predictors = the encoder's usual sources taken from the motion field the full
+    #      search above left (zero, the block's own predictor, the left / top / top-right macroblocks' vectors); extended-diamond
+    #      refinement with the dual round.  Reported: time per picture, search points per block, agreement with the full search. ----
+    mvi_h = mvi[:, 0].cpu().numpy()
+    mbw = Wb // 16
+    mbs = np.arange(b.mb_first, b.mb_first + b.mb_count)
+    geom = np.array(synth.PART_GEOM, np.int64)
+    nj = len(mbs) * 41
+    jobs = np.zeros(nj, synth.EPZS_JOB)
+    mbx, mby = np.repeat(mbs % mbw, 41), np.repeat(mbs // mbw, 41)
+    pp = np.tile(np.arange(41), len(mbs))
+    jobs["pos_x"] = 16 * mbx + geom[pp, 1]; jobs["pos_y"] = 16 * mby + geom[pp, 2]; jobs["blocktype"] = geom[pp, 0]
+    jobs["mv"] = (8, 4); jobs["pred"] = (8, 4); jobs["range"] = (4 * Rb, 4 * Rb)
+    jobs["mv_range"] = np.where(geom[pp, 0] < 5, 10, 12)
+    jobs["flags"] = 4 | 8 | np.where(geom[pp, 0] > 4, 2, 0)
+    jobs["lambda_factor"] = LAMBDA[0]
+    jobs["medthres"] = (geom[pp, 3] * geom[pp, 4]) << 5
+    jobs["stop0"] = jobs["medthres"] + 2 * LAMBDA[0]; jobs["stop"] = 2 * jobs["medthres"] + 2 * LAMBDA[0]
+    jobs["pred_first"] = 5 * np.arange(nj); jobs["npred"][:, 0] = 5; jobs["cond_host"][:, 0] = 1
+    jobs["pat_init"] = 2; jobs["pat_sd"] = 0; jobs["pat_sq"] = 1; jobs["pat_else"] = 2; jobs["pat_dual"] = 2
+    nb = lambda dx, dy: mvi_h[np.clip(mby + dy, 0, Hb // 16 - 1) * mbw + np.clip(mbx + dx, 0, mbw - 1), pp]
+    preds = np.stack([np.zeros((nj, 2), np.int16), np.tile(np.array([8, 4], np.int16), (nj, 1)), nb(-1, 0), nb(0, -1), nb(1, -1)], axis=1).astype(np.int16)
+    d_jobs = torch.from_numpy(jobs.view(np.uint8)).to(dev); d_preds = torch.from_numpy(preds.reshape(-1, 2)).to(dev)
+    d_pats = torch.from_numpy(synth.epzs_patterns().view(np.uint8)).to(dev)
+    d_out = torch.zeros(nj * synth.EPZS_RESULT.itemsize, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        b.s.epzs_search_dev(nj, d_jobs, d_preds, 3, d_pats, d_out, stream)
+    barrier()
+    ee = []
+    for i in range(steps):
+        flush.fill_(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); b.s.epzs_search_dev(nj, d_jobs, d_preds, 3, d_pats, d_out, stream); e1.record()
+        ee.append((e0, e1))
+    barrier()
+    res = d_out.cpu().numpy().view(synth.EPZS_RESULT)
+    same = int((res["mv"] == mvi_h[mbs].reshape(-1, 2)).all(axis=1).sum())
+    et = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in ee) / steps], dtype=torch.float64, device=dev)
+    ec = torch.tensor([nj, int(res["npoints"].sum()), same], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX); dist.all_reduce(ec)
+    epzs = {"kernel": "k_epzs (b2me_epzs_search_dev: EPZS_motion_estimation / EPZS_subMB_motion_estimation on the device, one warp per block)",
+            "blocks_per_picture": int(ec[0]), "ms_per_picture": float(et[0]), "search_points_per_block": float(ec[1]) / float(ec[0]),
+            "blocks_per_s": float(ec[0]) / (float(et[0]) * 1e-3), "same_vector_as_full_search": float(ec[2]) / float(ec[0]),
+            "predictors": "zero, the block's predictor, left / top / top-right macroblocks' vectors; extended diamond + dual refinement"}
     halo = sum((hi - lo) * Wb for s_, d_, lo, hi in bands.exchange_plan(world, Hb // 16, Rb) if d_ == rank)
     hb = torch.tensor([halo], dtype=torch.int64, device=dev)
     chk = mvs[b.mb_first:b.mb_first + b.mb_count].to(torch.int64).sum().reshape(1)
@@ -311,7 +357,7 @@ def bands_leg(local, rank, world, steps=5):
             "scaling": "strong", "ms_per_picture": float(t[0]), "value": pel / (float(t[0]) * 1e-3) / 1e6, "unit": UNIT,
             "ms_halo_exchange_and_planes": float(t[1]), "halo_bytes_all_ranks": int(hb.item()),
             "limiter": "the band's search; the exchange + plane rebuild share is ms_halo_exchange_and_planes / ms_per_picture",
-            "mv_checksum_all_bands": int(chk.item()), "l2": "192 MB L2 flush between timed pictures"}
+            "mv_checksum_all_bands": int(chk.item()), "l2": "192 MB L2 flush between timed pictures", "epzs": epzs}
 
 
 def pool_multi_leg(local, rank, world, nds=(16384, 65536), steps=4):

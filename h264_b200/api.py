@@ -219,6 +219,11 @@ class Searcher:
                   "b2me_epzs_search")
         return out
 
+    def epzs_search_dev(self, njobs, jobs_t, preds_t, npatterns, patterns_t, out_t, stream=0):
+        """device buffers (torch uint8 / int16 tensors holding the C records); asynchronous on `stream`"""
+        self._chk(self.L.b2me_epzs_search_dev(self.h, C.c_int(njobs), C.c_void_p(jobs_t.data_ptr()), C.c_void_p(preds_t.data_ptr()), C.c_int(npatterns),
+                                              C.c_void_p(patterns_t.data_ptr()), C.c_void_p(out_t.data_ptr()), C.c_void_p(stream)), "b2me_epzs_search_dev")
+
     def block_search(self, pos_x, pos_y, blocktype, ref, pred_mv, center_mv, params, search_range):
         pm = (C.c_int16 * 2)(int(pred_mv[0]), int(pred_mv[1]))
         cm = (C.c_int16 * 2)(int(center_mv[0]), int(center_mv[1]))

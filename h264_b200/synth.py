@@ -108,6 +108,17 @@ BIPRED_JOB = np.dtype([("min_mcost", np.int64), ("pos_x", np.int16), ("pos_y", n
                        ("pred1", np.int16, 2), ("pred2", np.int16, 2), ("mv1", np.int16, 2), ("mv2", np.int16, 2),
                        ("weight1", np.int16), ("weight2", np.int16), ("offset_bi", np.int16), ("reserved", np.int16)], align=True)
 BIPRED_RESULT = np.dtype([("cost_int", np.int64), ("cost_sub", np.int64), ("mv_int", np.int16, 2), ("mv_sub", np.int16, 2)], align=True)
+# (blocktype, ox, oy, w, h) of the 41 partitions in include/b2me.h's order
+PART_GEOM = ([(1, 0, 0, 16, 16), (2, 0, 0, 16, 8), (2, 0, 8, 16, 8), (3, 0, 0, 8, 16), (3, 8, 0, 8, 16)] +
+             [(4, x, y, 8, 8) for y in (0, 8) for x in (0, 8)] + [(5, x, y, 8, 4) for y in (0, 4, 8, 12) for x in (0, 8)] +
+             [(6, x, y, 4, 8) for y in (0, 8) for x in (0, 4, 8, 12)] + [(7, x, y, 4, 4) for y in (0, 4, 8, 12) for x in (0, 4, 8, 12)])
+# the refinement patterns of JM's EPZS as b2me_epzs_pattern records: (points (dx, dy, start_nmbr, next_points), stop_search, next_last, next_pattern)
+EPZS_SDIAMOND = [(0, 4, 3, 3), (4, 0, 0, 3), (0, -4, 1, 3), (-4, 0, 2, 3)]
+EPZS_SQUARE = [(0, 4, 7, 3), (4, 4, 7, 5), (4, 0, 1, 3), (4, -4, 1, 5), (0, -4, 3, 3), (-4, -4, 3, 5), (-4, 0, 5, 3), (-4, 4, 5, 5)]
+EPZS_EDIAMOND = [(-4, 4, 10, 5), (0, 8, 10, 8), (0, 4, 10, 7), (4, 4, 1, 5), (8, 0, 1, 8), (4, 0, 1, 7), (4, -4, 4, 5), (0, -8, 4, 8),
+                 (0, -4, 4, 7), (-4, -4, 7, 5), (-8, 0, 7, 8), (-4, 0, 7, 7)]
+
+
 # include/b2me.h b2me_epzs_job / b2me_epzs_result / b2me_epzs_pattern (C layout, 104 / 16 / 112 bytes)
 EPZS_JOB = np.dtype([("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.int16), ("ref", np.int16), ("mv", np.int16, 2),
                      ("pred", np.int16, 2), ("range", np.int16, 2), ("mv_range", np.int16), ("flags", np.int16), ("lambda_factor", np.int32),
@@ -117,6 +128,15 @@ EPZS_JOB = np.dtype([("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.
 EPZS_RESULT = np.dtype([("cost", np.int64), ("mv", np.int16, 2), ("early", np.int16), ("npoints", np.int16)], align=True)
 EPZS_PATTERN = np.dtype([("npoints", np.int32), ("stop_search", np.int32), ("next_last", np.int32), ("next_pattern", np.int32),
                          ("pt", np.int16, (12, 4))], align=True)
+def epzs_patterns():
+    """[small diamond, square, extended diamond], each ending in itself (stop_search = next_last = 1)"""
+    pats = np.zeros(3, EPZS_PATTERN)
+    for i, pts in enumerate((EPZS_SDIAMOND, EPZS_SQUARE, EPZS_EDIAMOND)):
+        pats[i]["npoints"] = len(pts); pats[i]["stop_search"] = 1; pats[i]["next_last"] = 1; pats[i]["next_pattern"] = i
+        pats[i]["pt"][:len(pts)] = pts
+    return pats
+
+
 CANDIDATE = np.dtype([("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.int16), ("ref", np.int16), ("mv", np.int16, 2)])
 _BS = {1: (16, 16), 2: (16, 8), 3: (8, 16), 4: (8, 8), 5: (8, 4), 6: (4, 8), 7: (4, 4)}
 
