@@ -191,6 +191,11 @@ class Searcher:
         self._chk(self.L.b2me_select_refs_dev(self.h, _dp(cost), C.c_int(int(ref_lambda)), _dp(best_ref), _dp(best_cost), _vp(stream)),
                   "b2me_select_refs_dev")
 
+    def select_refs_list_dev(self, cost, list_size, ref_lambda, best_ref, best_cost, stream=0):
+        """list_prediction_cost for one list of a B slice: only the first list_size references of `cost` take part"""
+        self._chk(self.L.b2me_select_refs_list_dev(self.h, _dp(cost), C.c_int(int(list_size)), C.c_int(int(ref_lambda)), _dp(best_ref), _dp(best_cost), _vp(stream)),
+                  "b2me_select_refs_list_dev")
+
     def bipred_search(self, jobs, params, apply_weights=False, log_denom=0, test8x8=False):
         """full_search_bipred (+ sub_pel_bipred) for an array of synth.BIPRED_JOB records; returns BIPRED_RESULT records"""
         from . import synth
@@ -507,3 +512,30 @@ def tq(params, orig, pred, n, device=0):
     if r:
         raise B2Error(f"b2tq_{n}x{n} failed ({r}): {L.b2tq_last_error().decode()}")
     return level, run, recon, cost, nz
+
+
+def deblock_frame(y, u, v, mbs, blks, device=0):
+    """b2dbk_frame: DeblockFrame on the GPU; host planes (packed uint8), synth.DBK_MB / DBK_BLK records; returns filtered copies"""
+    from . import synth
+    y, u, v = (np.ascontiguousarray(a, np.uint8).copy() for a in (y, u, v))
+    H, W = y.shape
+    mbs = np.ascontiguousarray(mbs, synth.DBK_MB); blks = np.ascontiguousarray(blks, synth.DBK_BLK)
+    if mbs.size != (W // 16) * (H // 16) or blks.size != (W // 4) * (H // 4):
+        raise ValueError("deblock_frame: record arrays do not match the picture size")
+    L = lib()
+    r = L.b2dbk_frame(C.c_int(device), C.c_int(W), C.c_int(H), _p(y), _p(u), _p(v), _p(mbs), _p(blks))
+    if r != 0:
+        L.b2dbk_last_error.restype = C.c_char_p
+        raise RuntimeError(f"b2dbk_frame failed ({r}): {L.b2dbk_last_error().decode()}")
+    return y, u, v
+
+
+def deblock_frame_dev(y, u, v, mbs, blks, progress, stream=0):
+    """b2dbk_frame_dev on torch CUDA tensors (uint8 planes in place; mbs / blks uint8 views of the records; progress int32 [H / 16])"""
+    L = lib()
+    H, W = y.shape
+    r = L.b2dbk_frame_dev(C.c_int(W), C.c_int(H), C.c_void_p(y.data_ptr()), C.c_int(y.stride(0)), C.c_void_p(u.data_ptr()), C.c_void_p(v.data_ptr()),
+                          C.c_int(u.stride(0)), C.c_void_p(mbs.data_ptr()), C.c_void_p(blks.data_ptr()), C.c_void_p(progress.data_ptr()), C.c_void_p(stream))
+    if r != 0:
+        L.b2dbk_last_error.restype = C.c_char_p
+        raise RuntimeError(f"b2dbk_frame_dev failed ({r}): {L.b2dbk_last_error().decode()}")

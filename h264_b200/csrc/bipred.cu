@@ -436,19 +436,21 @@ __constant__ signed char c_entry_parts[21][4] = {
   {17, 18, -1, -1}, {19, 20, -1, -1}, {21, 22, -1, -1}, {23, 24, -1, -1},
   {25, 26, 29, 30}, {27, 28, 31, 32}, {33, 34, 37, 38}, {35, 36, 39, 40}};
 
-__global__ void __launch_bounds__(256) k_select_refs(int nmb, int nrefs, const long long *__restrict__ cost, int ref_lambda,
+// nrefs: references per macroblock in the cost array; lsize: listXsize of the list the costs belong to (the loop bound of
+// list_prediction_cost and the "<= 1 reference: no reference bits" rule of ref_cost) -- list 1 of a B slice usually holds fewer.
+__global__ void __launch_bounds__(256) k_select_refs(int nmb, int nrefs, int lsize, const long long *__restrict__ cost, int ref_lambda,
                                                       int8_t *__restrict__ best_ref, long long *__restrict__ best_cost)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nmb * 21) return;
   const int mb = i / 21, e = i - mb * 21;
   long long bm = BI_DISTBLK_MAX; int br = 0;
-  for (int r = 0; r < nrefs; r++) {
+  for (int r = 0; r < lsize; r++) {
     long long mc = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) { const int p = c_entry_parts[e][k]; if (p >= 0) mc += cost[((size_t)mb * nrefs + r) * NPART + p]; }
     if (mc < bm) {
-      mc += nrefs <= 1 ? 0 : (long long)ref_lambda * (65 - 2 * __clz(r + 1) - 2);    // refbits = 2 * floor(log2(ref + 1)) + 1
+      mc += lsize <= 1 ? 0 : (long long)ref_lambda * (65 - 2 * __clz(r + 1) - 2);    // refbits = 2 * floor(log2(ref + 1)) + 1
       if (mc < bm) { bm = mc; br = r; }
     }
   }
@@ -493,7 +495,7 @@ cudaError_t launch_expand_pred(int n, const int16_t *pred_mb, int16_t *pred, int
 cudaError_t launch_select_gather(int nmb, int nrefs, const long long *cost, int ref_lambda, const int16_t *mv, int8_t *best_ref, long long *best_cost,
                                  int16_t *best_mv, int32_t *cost32, cudaStream_t s)
 {
-  k_select_refs<<<(nmb * 21 + 255) / 256, 256, 0, s>>>(nmb, nrefs, cost, ref_lambda, best_ref, best_cost);
+  k_select_refs<<<(nmb * 21 + 255) / 256, 256, 0, s>>>(nmb, nrefs, nrefs, cost, ref_lambda, best_ref, best_cost);
   k_gather_best<<<(nmb * NPART + 255) / 256, 256, 0, s>>>(nmb, nrefs, mv, best_ref, best_cost, best_mv, cost32);
   return cudaGetLastError();
 }
@@ -502,12 +504,24 @@ cudaError_t launch_select_gather(int nmb, int nrefs, const long long *cost, int 
 
 using namespace b2;
 
+extern "C" int b2me_select_refs_list_dev(b2me_ctx *c, const int64_t *cost_dev, int list_size, int ref_lambda, int8_t *best_ref_dev, int64_t *best_cost_dev, void *stream)
+{
+  if (!c || !cost_dev || !best_ref_dev || !best_cost_dev || list_size < 1 || list_size > c->nrefs) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const int n = c->nmb * 21;
+  k_select_refs<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->nmb, c->nrefs, list_size, reinterpret_cast<const long long *>(cost_dev), ref_lambda,
+                                                                  best_ref_dev, reinterpret_cast<long long *>(best_cost_dev));
+  B2_CUDA_CHECK(c, cudaGetLastError());
+  c->launches++;
+  return B2ME_OK;
+}
+
 extern "C" int b2me_select_refs_dev(b2me_ctx *c, const int64_t *cost_dev, int ref_lambda, int8_t *best_ref_dev, int64_t *best_cost_dev, void *stream)
 {
   if (!c || !cost_dev || !best_ref_dev || !best_cost_dev) return B2ME_EINVAL;
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
   const int n = c->nmb * 21;
-  k_select_refs<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->nmb, c->nrefs, reinterpret_cast<const long long *>(cost_dev), ref_lambda,
+  k_select_refs<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->nmb, c->nrefs, c->nrefs, reinterpret_cast<const long long *>(cost_dev), ref_lambda,
                                                                   best_ref_dev, reinterpret_cast<long long *>(best_cost_dev));
   B2_CUDA_CHECK(c, cudaGetLastError());
   c->launches++;

@@ -137,6 +137,10 @@ def epzs_patterns():
     return pats
 
 
+# include/b2me.h b2dbk_mb / b2dbk_blk (12 bytes each)
+DBK_MB = np.dtype([("intra", np.uint8), ("qp", np.uint8), ("qpc_u", np.uint8), ("qpc_v", np.uint8), ("transform8x8", np.uint8), ("disable", np.uint8),
+                   ("alpha_off", np.int8), ("beta_off", np.int8), ("cbp_blk", np.uint16), ("pad_", np.uint16)], align=True)
+DBK_BLK = np.dtype([("mv", np.int16, (2, 2)), ("ref", np.int16, 2)], align=True)
 CANDIDATE = np.dtype([("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.int16), ("ref", np.int16), ("mv", np.int16, 2)])
 _BS = {1: (16, 16), 2: (16, 8), 3: (8, 16), 4: (8, 8), 5: (8, 4), 6: (4, 8), 7: (4, 4)}
 

@@ -258,6 +258,29 @@ int b2me_epzs_search(b2me_ctx *ctx, int njobs, const b2me_epzs_job *jobs, int np
 int b2me_epzs_search_dev(b2me_ctx *ctx, int njobs, const b2me_epzs_job *jobs_dev, const int16_t *preds_dev,
                          int npatterns, const b2me_epzs_pattern *patterns_dev, b2me_epzs_result *out_dev, void *stream);
 
+/* ---- in-loop deblocking filter of a frame picture ------------------------------------------------------ */
+/* DeblockFrame (JM/lencod/src/loopFilter.c:63-111, DeblockMb :196-377) with the non-MBAFF functions of
+ * JM/lencod/src/loop_filter_normal.c (GetStrengthVer / Hor :52-283, EdgeLoopLuma / Chroma Ver / Hor :285-758), 8-bit 4:2:0 frame
+ * pictures, every macroblock of one slice type P / B / I (not SP / SI), DFDisableIdc 0 or 1 per macroblock.  The reconstructed
+ * planes are filtered IN PLACE on the device, so that a band's reconstruction can stay on the GPU for the halo exchange and the
+ * plane build of the next picture.  What the filter reads from encoder state arrives as two arrays:
+ *   mbs  [mbh * mbw]   : intra, qp, chroma qp (qpc[0], qpc[1]), luma_transform_size_8x8_flag, DFDisableIdc == 1,
+ *                        DFAlphaC0Offset, DFBetaOffset, cbp_blk bits 0..15 (bit 4 * by + bx: the 4x4 luma block holds coefficients)
+ *   blks [H / 4][W / 4]: both lists' vectors (quarter-pel) and reference PICTURE identity per 4x4 block (any id that is equal
+ *                        exactly when the pictures are the same; -1: the list is unused) -- enc_picture->mv_info.
+ * Macroblock order is the reference's (raster; the kernel runs the 2:1 wavefront of JM_PARALLEL_DEBLOCK, loopFilter.c:92-109,
+ * one CTA per macroblock row): the result is bit-identical to the serial filter. */
+typedef struct b2dbk_mb {
+  uint8_t intra, qp, qpc_u, qpc_v, transform8x8, disable;
+  int8_t alpha_off, beta_off;
+  uint16_t cbp_blk, pad_;
+} b2dbk_mb;                     /* 12 bytes */
+typedef struct b2dbk_blk { int16_t mv[2][2]; int16_t ref[2]; } b2dbk_blk;   /* 12 bytes; mv[list][x, y] */
+int b2dbk_frame(int device, int W, int H, uint8_t *y, uint8_t *u, uint8_t *v, const b2dbk_mb *mbs, const b2dbk_blk *blks);   /* host planes, packed */
+int b2dbk_frame_dev(int W, int H, uint8_t *y_dev, int y_pitch, uint8_t *u_dev, uint8_t *v_dev, int c_pitch,
+                    const b2dbk_mb *mbs_dev, const b2dbk_blk *blks_dev, int *progress_dev /* [H / 16] ints, any content */, void *stream);
+const char *b2dbk_last_error(void);
+
 /* ---- reference selection per (mode, block) (the first step of the mode decision) ------------------- */
 /* list_prediction_cost for list 0 (JM/lencod/src/mode_decision.c:275-300, update_mcost :256-267, ref_cost mv_search.h:114,
  * refbits mv_search.c:377-385) from the search's cost array, for every macroblock of the picture:
@@ -267,6 +290,10 @@ int b2me_epzs_search_dev(b2me_ctx *ctx, int njobs, const b2me_epzs_job *jobs_dev
  *   (the motion cost of a quadrant in modes 5..7 is the sum over its sub-partitions, as PartitionMotionSearch accumulates it).
  * Device pointers; keeps the 41 x nrefs candidates on the device and hands 21 (reference, cost) pairs per macroblock on. */
 int b2me_select_refs_dev(b2me_ctx *ctx, const int64_t *cost_dev, int ref_lambda, int8_t *best_ref_dev, int64_t *best_cost_dev, void *stream);
+/* The same for either list of a B slice (list < BI_PRED, mode_decision.c:286-300): cost holds the searches of ONE list
+ * ([nmb][nrefs][41], nrefs = the context's), list_size = listXsize[cur_list] <= nrefs bounds the loop and decides whether
+ * reference bits are charged (ref_cost: none when the list holds a single picture). */
+int b2me_select_refs_list_dev(b2me_ctx *ctx, const int64_t *cost_dev, int list_size, int ref_lambda, int8_t *best_ref_dev, int64_t *best_cost_dev, void *stream);
 
 /* ---- motion-compensated prediction (keeps the vectors on the device between search and transform) ---- */
 /* luma_prediction with p_dir == 0 (list 0), no weighting (JM/lencod/src/mc_prediction.c:144-236;

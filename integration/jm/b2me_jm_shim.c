@@ -36,6 +36,7 @@
 typedef struct {
   StorablePicture *pic;
   int poc;
+  unsigned sig;          /* samples of the picture: JM re-uses StorablePicture addresses, and POC restarts at every IDR */
   long stamp;
 } B2Slot;
 
@@ -45,6 +46,7 @@ static B2Slot g_slot[B2_MAX_SLOTS];
 static long g_clock;
 static StorablePicture *g_cur_pic;
 static int g_cur_poc = -0x7fffffff;
+static unsigned g_cur_sig;
 static unsigned char *g_stage;
 static long g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_uploads, g_calls_epzs, g_points_epzs;
 static int g_in_bipred;
@@ -80,6 +82,15 @@ static void b2_check_config(Macroblock *currMB, MEBlock *mv_block)
   if (p_Inp->OnTheFlyFractMCP) b2_fail("OnTheFlyFractMCP must be 0");
 }
 
+/* Transform8x8Mode sets mv_block->test8x8 for 8x8 and larger blocks (mv_search.c:1630, 1770) and computeSATD then takes the 8x8
+ * Hadamard (me_distortion.c:762).  The single-list sub-pel kernel has the 4x4 Hadamard only: stop instead of diverging. */
+static void b2_check_test8x8(Macroblock *currMB, MEBlock *mv_block)
+{
+  InputParameters *p_Inp = currMB->p_Inp;
+  if (mv_block->test8x8 && (p_Inp->MEErrorMetric[H_PEL] == ERROR_SATD || p_Inp->MEErrorMetric[Q_PEL] == ERROR_SATD))
+    b2_fail("Transform8x8Mode with SATD sub-pel refinement (8x8 Hadamard, test8x8) is not supported by the single-list sub-pel search");
+}
+
 static void b2_ensure_ctx2(VideoParameters *p_Vid, InputParameters *p_Inp);
 static void b2_ensure_ctx(Macroblock *currMB) { b2_ensure_ctx2(currMB->p_Vid, currMB->p_Inp); }
 static void b2_ensure_ctx2(VideoParameters *p_Vid, InputParameters *p_Inp)
@@ -108,10 +119,24 @@ static void b2_narrow(imgpel **src)
   }
 }
 
+/* 256 samples spread over the picture: with (address, poc) a key that a re-allocated picture of another GOP does not repeat */
+static unsigned b2_signature(imgpel **img)
+{
+  unsigned h = 2166136261u;
+  int k;
+  for (k = 0; k < 256; k++) {
+    const int y = (int)(((long)k * 2654435761u) % (unsigned)g_H), x = (int)(((long)k * 40503u + 17) % (unsigned)g_W);
+    h = (h ^ (unsigned)img[y][x]) * 16777619u;
+  }
+  return h;
+}
+
 static void b2_ensure_cur(VideoParameters *p_Vid)
 {
   StorablePicture *enc = p_Vid->enc_picture;
-  if (enc == g_cur_pic && enc->poc == g_cur_poc) return;
+  const unsigned sig = b2_signature(p_Vid->pCurImg);
+  if (enc == g_cur_pic && enc->poc == g_cur_poc && sig == g_cur_sig) return;
+  g_cur_sig = sig;
   b2_narrow(p_Vid->pCurImg);
   if (b2me_set_cur(g_ctx, g_stage, g_W) != B2ME_OK) b2_fail("b2me_set_cur failed");
   g_cur_pic = enc; g_cur_poc = enc->poc; g_uploads++;
@@ -121,13 +146,14 @@ static void b2_ensure_cur(VideoParameters *p_Vid)
 static int b2_ref_slot(StorablePicture *ref)
 {
   int i, victim = 0;
+  const unsigned sig = b2_signature(ref->imgY);
   for (i = 0; i < g_nslots; i++)
-    if (g_slot[i].pic == ref && g_slot[i].poc == ref->poc && g_slot[i].stamp) { g_slot[i].stamp = ++g_clock; return i; }
+    if (g_slot[i].pic == ref && g_slot[i].poc == ref->poc && g_slot[i].sig == sig && g_slot[i].stamp) { g_slot[i].stamp = ++g_clock; return i; }
   for (i = 1; i < g_nslots; i++)
     if (g_slot[i].stamp < g_slot[victim].stamp) victim = i;
   b2_narrow(ref->imgY);                 /* reconstructed (deblocked) luma; the GPU rebuilds getSubImagesLuma's planes */
   if (b2me_set_ref(g_ctx, victim, g_stage, g_W) != B2ME_OK) b2_fail("b2me_set_ref failed");
-  g_slot[victim].pic = ref; g_slot[victim].poc = ref->poc; g_slot[victim].stamp = ++g_clock; g_uploads++;
+  g_slot[victim].pic = ref; g_slot[victim].poc = ref->poc; g_slot[victim].sig = sig; g_slot[victim].stamp = ++g_clock; g_uploads++;
   return victim;
 }
 
@@ -180,6 +206,7 @@ distblk sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, MEBloc
   b2_ensure_ctx(currMB);
   b2_check_config(currMB, mv_block);
   if (mv_block->search_pos2 != 9 || mv_block->search_pos4 != 9) b2_fail("SubPelSearch position counts other than 9/9 are not supported");
+  b2_check_test8x8(currMB, mv_block);
   b2_ensure_cur(currMB->p_Vid);
   slot = b2_ref_slot(ref_picture);
   b2_params(currMB->p_Inp, &P, lambda[F_PEL], lambda[H_PEL], lambda[Q_PEL], min_mcost);
@@ -207,6 +234,7 @@ distblk full_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, M
 
   b2_ensure_ctx(currMB);
   b2_check_config(currMB, mv_block);
+  b2_check_test8x8(currMB, mv_block);
   b2_ensure_cur(currMB->p_Vid);
   slot = b2_ref_slot(ref_picture);
   b2_params(currMB->p_Inp, &P, lambda[F_PEL], lambda[H_PEL], lambda[Q_PEL], min_mcost);
@@ -268,6 +296,7 @@ distblk sub_pel_bipred_motion_estimation(Macroblock *currMB, MEBlock *mv_block, 
                                          MotionVector *mv1, MotionVector *mv2, distblk min_mcost, int *lambda)
 {
   if (mv_block->search_pos2 != 9 || mv_block->search_pos4 != 9) b2_fail("SubPelSearch position counts other than 9/9 are not supported");
+  b2_check_test8x8(currMB, mv_block);
   return b2_bipred(currMB, list, pred_mv1, pred_mv2, mv1, mv2, mv_block, -1, min_mcost, lambda, 1);
 }
 

@@ -99,13 +99,25 @@ ENTRY_PARTS = [(0,), (1,), (2,), (3,), (4,), (5,), (6,), (7,), (8,), (9, 11), (1
                (17, 18), (19, 20), (21, 22), (23, 24), (25, 26, 29, 30), (27, 28, 31, 32), (33, 34, 37, 38), (35, 36, 39, 40)]
 
 
-def select_refs(cost, ref_lambda):
-    """list_prediction_cost (list 0) for every macroblock: cost [nmb][nrefs][41] -> (best_ref int8 [nmb][21], best_cost int64 [nmb][21])"""
+def select_refs(cost, ref_lambda, list_size=None):
+    """list_prediction_cost (list < BI_PRED) for every macroblock: cost [nmb][nrefs][41] -> (best_ref int8 [nmb][21], best_cost int64 [nmb][21]);
+    list_size: listXsize of the list the costs belong to (default: all nrefs)"""
     cost = np.ascontiguousarray(cost, np.int64)
     nmb, nrefs = cost.shape[:2]
     br = np.zeros((nmb, 21), np.int8); bc = np.zeros((nmb, 21), np.int64)
-    orc_lib().orc_select_refs(C.c_int(nmb), C.c_int(nrefs), _ptr(cost), C.c_int(int(ref_lambda)), _ptr(br), _ptr(bc))
+    orc_lib().orc_select_refs_list(C.c_int(nmb), C.c_int(nrefs), C.c_int(nrefs if list_size is None else int(list_size)), _ptr(cost), C.c_int(int(ref_lambda)), _ptr(br), _ptr(bc))
     return br, bc
+
+
+def deblock_frame(y, u, v, mbs, blks):
+    """orc_deblock_frame (DeblockFrame of JM restated): returns filtered copies of the planes"""
+    from h264_b200 import synth
+    y, u, v = (np.ascontiguousarray(a, np.uint8).copy() for a in (y, u, v))
+    H, W = y.shape
+    mbs = np.ascontiguousarray(mbs, synth.DBK_MB); blks = np.ascontiguousarray(blks, synth.DBK_BLK)
+    assert mbs.size == (W // 16) * (H // 16) and blks.size == (W // 4) * (H // 4)
+    orc_lib().orc_deblock_frame(C.c_int(W), C.c_int(H), _ptr(y), _ptr(u), _ptr(v), _ptr(mbs), _ptr(blks))
+    return y, u, v
 
 
 def subpel_planes(luma):
@@ -316,11 +328,11 @@ class JMRef:
                                  C.c_int(int(wp)), C.c_int(log_denom), _ptr(out))
         return out
 
-    def list_prediction_cost(self, mode, block, costs, ref_lambda):
-        """the reference's list_prediction_cost (list 0) for one (mode, block): (best_ref, bmcost)"""
+    def list_prediction_cost(self, mode, block, costs, ref_lambda, list=0):
+        """the reference's list_prediction_cost (list 0 or 1) for one (mode, block): (best_ref, bmcost)"""
         c = np.ascontiguousarray(costs, np.int64)
         br = C.c_int(); bm = C.c_longlong()
-        self.L.jmh_list_prediction_cost(self.h, C.c_int(mode), C.c_int(block), C.c_int(len(c)), _ptr(c), C.c_int(int(ref_lambda)), C.byref(br), C.byref(bm))
+        self.L.jmh_list_prediction_cost(self.h, C.c_int(list), C.c_int(mode), C.c_int(block), C.c_int(len(c)), _ptr(c), C.c_int(int(ref_lambda)), C.byref(br), C.byref(bm))
         return br.value, bm.value
 
     def search_frame(self, pred, center, lambda_factor, do_subpel=True, mb_first=0, mb_count=None):

@@ -631,17 +631,21 @@ static const signed char ORC_ENTRY_PARTS[21][4] = {
   {17, 18, -1, -1}, {19, 20, -1, -1}, {21, 22, -1, -1}, {23, 24, -1, -1},          /* 4x8: two columns */
   {25, 26, 29, 30}, {27, 28, 31, 32}, {33, 34, 37, 38}, {35, 36, 39, 40}};         /* 4x4 */
 int orc_refbits(int ref) { int b = 1, v = ref + 1; while (v > 1) { v >>= 1; b += 2; } return b; }
+void orc_select_refs_list(int nmb, int nrefs, int lsize, const int64_t *cost, int ref_lambda, int8_t *best_ref, int64_t *best_cost);
 void orc_select_refs(int nmb, int nrefs, const int64_t *cost, int ref_lambda, int8_t *best_ref, int64_t *best_cost)
+{ orc_select_refs_list(nmb, nrefs, nrefs, cost, ref_lambda, best_ref, best_cost); }
+/* either list of a B slice: lsize = listXsize[cur_list] bounds the loop (mode_decision.c:290) and ref_cost (mv_search.h:116) */
+void orc_select_refs_list(int nmb, int nrefs, int lsize, const int64_t *cost, int ref_lambda, int8_t *best_ref, int64_t *best_cost)
 {
   int mb, e, r, k;
   for (mb = 0; mb < nmb; mb++)
     for (e = 0; e < 21; e++) {
       int64_t bm = DISTBLK_MAX_ORC; int br = 0;
-      for (r = 0; r < nrefs; r++) {
+      for (r = 0; r < lsize; r++) {
         int64_t mc = 0;
         for (k = 0; k < 4 && ORC_ENTRY_PARTS[e][k] >= 0; k++) mc += cost[((size_t)mb * nrefs + r) * 41 + ORC_ENTRY_PARTS[e][k]];
         if (mc < bm) {                                   /* update_mcost */
-          mc += nrefs <= 1 ? 0 : (int64_t)ref_lambda * orc_refbits(r);
+          mc += lsize <= 1 ? 0 : (int64_t)ref_lambda * orc_refbits(r);
           if (mc < bm) { bm = mc; br = r; }
         }
       }

@@ -333,19 +333,19 @@ void jmh_bipred_search(void *hh, int njobs, const JmhBiJob *jobs, const int *lam
 
 /* list_prediction_cost (mode_decision.c:275) for one (mode, block): p_Vid->motion_cost[mode][LIST_0][ref][block] = costs[ref] */
 #include "mode_decision.h"
-void jmh_list_prediction_cost(void *hh, int mode, int block, int nrefs, const long long *costs, int ref_lambda, int *best_ref, long long *bmcost_out)
+void jmh_list_prediction_cost(void *hh, int list, int mode, int block, int nrefs, const long long *costs, int ref_lambda, int *best_ref, long long *bmcost_out)
 {
   JMH *h = (JMH *)hh; RD_PARAMS enc_mb; distblk bmcost[5]; char bref[2] = {0, 0}; int r;
-  char save = h->slice->listXsize[0];
+  char save = h->slice->listXsize[list];
   memset(&enc_mb, 0, sizeof(enc_mb));
   enc_mb.lambda_mf[Q_PEL] = ref_lambda;
   if (!h->p_Vid->motion_cost) get_mem4Ddistblk(&h->p_Vid->motion_cost, 8, 2, h->p_Vid->max_num_references, 4);
-  for (r = 0; r < nrefs; r++) h->p_Vid->motion_cost[mode][0][r][block] = (distblk)costs[r];
-  h->slice->listXsize[0] = (char)nrefs;
+  for (r = 0; r < nrefs; r++) h->p_Vid->motion_cost[mode][list][r][block] = (distblk)costs[r];
+  h->slice->listXsize[list] = (char)nrefs;
   h->p_Vid->checkref = 0;
-  bmcost[0] = DISTBLK_MAX;
-  list_prediction_cost(&h->mb, LIST_0, block, mode, &enc_mb, bmcost, bref);
-  h->slice->listXsize[0] = save;
-  *best_ref = bref[0]; *bmcost_out = (long long)bmcost[0];
+  bmcost[list] = DISTBLK_MAX;
+  list_prediction_cost(&h->mb, list, block, mode, &enc_mb, bmcost, bref);
+  h->slice->listXsize[list] = save;
+  *best_ref = bref[list]; *bmcost_out = (long long)bmcost[list];
 }
 int jmh_refbits(void *hh, int r) { return ((JMH *)hh)->p_Vid->refbits[r]; }

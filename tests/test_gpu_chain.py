@@ -74,6 +74,11 @@ def test_reference_selection_on_the_device_matches_oracle():
     s.search_frame_dev(dp, dc, api.make_params((187, 187, 187)), mvi, ci, mvs, cs)
     br = torch.zeros((s.nmb, 21), dtype=torch.int8, device=dev); bc = torch.zeros((s.nmb, 21), dtype=torch.int64, device=dev)
     for lam in (187, 4000):
+        for ls in range(1, cs.shape[1] + 1):            # list 1 of a B slice: the loop stops at listXsize
+            s.select_refs_list_dev(cs, ls, lam, br, bc)
+            torch.cuda.synchronize()
+            ebr, ebc = oracle.select_refs(cs.cpu().numpy(), lam, list_size=ls)
+            assert (br.cpu().numpy() == ebr).all() and (bc.cpu().numpy() == ebc).all(), ls
         s.select_refs_dev(cs, lam, br, bc)
         torch.cuda.synchronize()
         ebr, ebc = oracle.select_refs(cs.cpu().numpy(), lam)

@@ -256,6 +256,13 @@ def test_reference_selection_equals_live_reference():
             for e, (mode, blk) in enumerate(oracle.SELECT_ENTRIES):
                 c = [int(cost[mb, r, parts[e]].sum()) for r in range(nrefs)]
                 assert jm.list_prediction_cost(mode, blk, c, 187) == (int(br[mb, e]), int(bc[mb, e])), (nrefs, mb, e)
+        # list 1 of a B slice with fewer pictures than the cost array holds: the loop stops at listXsize[1]
+        for ls in range(1, nrefs + 1):
+            br1, bc1 = oracle.select_refs(cost, 187, list_size=ls)
+            for mb in (1, 3):
+                for e, (mode, blk) in enumerate(oracle.SELECT_ENTRIES):
+                    c = [int(cost[mb, r, parts[e]].sum()) for r in range(ls)]
+                    assert jm.list_prediction_cost(mode, blk, c, 187, list=1) == (int(br1[mb, e]), int(bc1[mb, e])), (nrefs, ls, mb, e)
 
 
 def _epzs_golden():
@@ -284,3 +291,18 @@ def test_epzs_restatement_matches_reference_golden():
         n += len(jobs)
         kinds |= {(int(e), int(f) & 2) for e, f in zip(out["early"], jobs["flags"])}
     assert n > 5000 and len(kinds) == 4          # early and final returns of both variants occur
+
+
+def test_deblock_restatement_matches_reference_golden():
+    """orc_deblock_frame against the planes the UNMODIFIED DeblockFrame (JM/lencod/src/loopFilter.c:63, loop_filter_normal.c) left
+    on the pictures of stock lencod runs (tests/golden/jm_deblock.npz): I / P / B pictures, two lists, 8x8 transform, filter offsets."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "jm_deblock.npz"))
+    n = 0
+    for tag in "pbt":
+        for i in range(int(g[f"{tag}_n"])):
+            got = oracle.deblock_frame(*[g[f"{tag}{i}_{p}0"] for p in "yuv"], g[f"{tag}{i}_mbs"], g[f"{tag}{i}_blks"])
+            for a, p in zip(got, "yuv"):
+                assert (a == g[f"{tag}{i}_{p}1"]).all(), (tag, i, p)
+            n += 1
+    assert n == 12
