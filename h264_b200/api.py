@@ -191,6 +191,19 @@ class Searcher:
         self._chk(self.L.b2me_select_refs_dev(self.h, _dp(cost), C.c_int(int(ref_lambda)), _dp(best_ref), _dp(best_cost), _vp(stream)),
                   "b2me_select_refs_dev")
 
+    def set_cur_chroma(self, u, v):
+        u = np.ascontiguousarray(u, np.uint8); v = np.ascontiguousarray(v, np.uint8)
+        self._chk(self.L.b2me_set_cur_chroma(self.h, _p(u), _p(v), C.c_int(u.shape[1])), "b2me_set_cur_chroma")
+
+    def set_ref_chroma(self, ref, u, v):
+        u = np.ascontiguousarray(u, np.uint8); v = np.ascontiguousarray(v, np.uint8)
+        self._chk(self.L.b2me_set_ref_chroma(self.h, C.c_int(ref), _p(u), _p(v), C.c_int(u.shape[1])), "b2me_set_ref_chroma")
+
+    def mc_mb_dev(self, mb_mode, b8mode, pdir, ref8, mv_l0, mv_l1, orig_y, pred_y, orig_c, pred_c, stream=0):
+        """luma + chroma prediction from either list or both on torch CUDA tensors (see include/b2me.h b2me_mc_mb_dev)"""
+        self._chk(self.L.b2me_mc_mb_dev(self.h, _dp(mb_mode), _dp(b8mode), _dp(pdir), _dp(ref8), _dp(mv_l0), _dp(mv_l1), _dp(orig_y), _dp(pred_y),
+                                        _dp(orig_c), _dp(pred_c), _vp(stream)), "b2me_mc_mb_dev")
+
     def select_refs_list_dev(self, cost, list_size, ref_lambda, best_ref, best_cost, stream=0):
         """list_prediction_cost for one list of a B slice: only the first list_size references of `cost` take part"""
         self._chk(self.L.b2me_select_refs_list_dev(self.h, _dp(cost), C.c_int(int(list_size)), C.c_int(int(ref_lambda)), _dp(best_ref), _dp(best_cost), _vp(stream)),

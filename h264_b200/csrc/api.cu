@@ -105,7 +105,7 @@ extern "C" void b2me_destroy(b2me_ctx *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_cur); cudaFree(c->d_stage); cudaFree(c->d_planes); cudaFree(c->d_spl); cudaFree(c->d_tmap_spl);
+  cudaFree(c->d_cur); cudaFree(c->d_curc); cudaFree(c->d_refc); cudaFree(c->d_stage); cudaFree(c->d_planes); cudaFree(c->d_spl); cudaFree(c->d_tmap_spl);
   cudaFree(c->d_pred); cudaFree(c->d_center); cudaFree(c->d_mv_int); cudaFree(c->d_mv_sub);
   cudaFree(c->d_cost_int); cudaFree(c->d_cost_sub); cudaFree(c->d_io16); cudaFree(c->d_io64);
   cudaFree(c->d_sadtab); cudaFree(c->d_pred_mb); cudaFree(c->d_best_ref); cudaFree(c->d_best_cost); cudaFree(c->d_best_cost32); cudaFree(c->d_best_mv);
@@ -522,6 +522,70 @@ extern "C" int b2me_mc_luma_dev(b2me_ctx *c, const uint8_t *mb_mode, const uint8
   m.W = c->W; m.H = c->H; m.Wp = c->Wp; m.mbw = c->mbw; m.nmb = c->nmb; m.nrefs = c->nrefs;
   m.mb_mode = mb_mode; m.b8mode = b8mode; m.ref8 = ref8; m.mv = mv; m.orig_blk = orig_blk; m.pred_blk = pred_blk;
   B2_CUDA_CHECK(c, launch_mc_luma(m, (cudaStream_t)stream));
+  c->launches++;
+  return B2ME_OK;
+}
+
+// ---- chroma planes (4:2:0) for the prediction of whole macroblocks, b2me_mc_mb_dev ----
+static int ensure_chroma(b2me_ctx *c)
+{
+  const size_t n = (size_t)(c->W / 2) * (c->H / 2) * 2;
+  if (!c->d_curc) B2_CUDA_CHECK(c, cudaMalloc(&c->d_curc, n));
+  if (!c->d_refc) B2_CUDA_CHECK(c, cudaMalloc(&c->d_refc, n * c->nrefs));
+  return B2ME_OK;
+}
+static int set_chroma(b2me_ctx *c, uint8_t *dst, const uint8_t *u, const uint8_t *v, int stride, cudaMemcpyKind kind, cudaStream_t s)
+{
+  const int Wc = c->W / 2, Hc = c->H / 2;
+  B2_CUDA_CHECK(c, cudaMemcpy2DAsync(dst, Wc, u, stride, Wc, Hc, kind, s));
+  B2_CUDA_CHECK(c, cudaMemcpy2DAsync(dst + (size_t)Wc * Hc, Wc, v, stride, Wc, Hc, kind, s));
+  return B2ME_OK;
+}
+extern "C" int b2me_set_cur_chroma_dev(b2me_ctx *c, const uint8_t *u_dev, const uint8_t *v_dev, int stride, void *stream)
+{
+  if (!c || !u_dev || !v_dev || stride < c->W / 2) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  { int r = ensure_chroma(c); if (r) return r; }
+  return set_chroma(c, c->d_curc, u_dev, v_dev, stride, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+}
+extern "C" int b2me_set_ref_chroma_dev(b2me_ctx *c, int ref, const uint8_t *u_dev, const uint8_t *v_dev, int stride, void *stream)
+{
+  if (!c || !u_dev || !v_dev || ref < 0 || ref >= c->nrefs || stride < c->W / 2) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  { int r = ensure_chroma(c); if (r) return r; }
+  return set_chroma(c, c->d_refc + (size_t)ref * (c->W / 2) * (c->H / 2) * 2, u_dev, v_dev, stride, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+}
+extern "C" int b2me_set_cur_chroma(b2me_ctx *c, const uint8_t *u, const uint8_t *v, int stride)
+{
+  if (!c || !u || !v || stride < c->W / 2) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  { int r = ensure_chroma(c); if (r) return r; }
+  { int r = set_chroma(c, c->d_curc, u, v, stride, cudaMemcpyHostToDevice, c->stream); if (r) return r; }
+  B2_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return B2ME_OK;
+}
+extern "C" int b2me_set_ref_chroma(b2me_ctx *c, int ref, const uint8_t *u, const uint8_t *v, int stride)
+{
+  if (!c || !u || !v || ref < 0 || ref >= c->nrefs || stride < c->W / 2) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  { int r = ensure_chroma(c); if (r) return r; }
+  { int r = set_chroma(c, c->d_refc + (size_t)ref * (c->W / 2) * (c->H / 2) * 2, u, v, stride, cudaMemcpyHostToDevice, c->stream); if (r) return r; }
+  B2_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return B2ME_OK;
+}
+extern "C" int b2me_mc_mb_dev(b2me_ctx *c, const uint8_t *mb_mode, const uint8_t *b8mode, const uint8_t *pdir, const int8_t *ref8, const int16_t *mv_l0,
+                              const int16_t *mv_l1, uint8_t *orig_y, uint8_t *pred_y, uint8_t *orig_c, uint8_t *pred_c, void *stream)
+{
+  if (!c || !mb_mode || !b8mode || !pdir || !ref8 || !mv_l0 || !mv_l1 || !orig_y || !pred_y || !orig_c || !pred_c) return B2ME_EINVAL;
+  if (!c->d_curc || !c->d_refc) { snprintf(c->err, sizeof(c->err), "b2me_mc_mb_dev: no chroma planes (b2me_set_cur_chroma / b2me_set_ref_chroma)"); return B2ME_EINVAL; }
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  { int r0 = after_uploads(c, (cudaStream_t)stream); if (r0) return r0; }
+  McMbArgs m;
+  m.cur = c->d_cur; m.cur_pitch = c->W; m.curc = c->d_curc; m.refc = c->d_refc; m.planes = c->d_planes; m.plane_size = c->plane_size;
+  m.W = c->W; m.H = c->H; m.Wp = c->Wp; m.mbw = c->mbw; m.nmb = c->nmb; m.nrefs = c->nrefs;
+  m.mb_mode = mb_mode; m.b8mode = b8mode; m.pdir = pdir; m.ref8 = ref8; m.mv0 = mv_l0; m.mv1 = mv_l1;
+  m.orig_y = orig_y; m.pred_y = pred_y; m.orig_c = orig_c; m.pred_c = pred_c;
+  B2_CUDA_CHECK(c, launch_mc_mb(m, (cudaStream_t)stream));
   c->launches++;
   return B2ME_OK;
 }

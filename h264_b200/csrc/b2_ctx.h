@@ -10,6 +10,8 @@ struct b2me_ctx {
   int W, H, Wp, Hp, mbw, mbh, nmb, nrefs, R;
   size_t plane_size;            // Wp*Hp
   uint8_t *d_cur;               // [H][W]
+  uint8_t *d_curc;              // [2][H/2][W/2] current chroma (b2me_set_cur_chroma; allocated on first use)
+  uint8_t *d_refc;              // [nrefs][2][H/2][W/2] reference chroma (b2me_set_ref_chroma)
   uint8_t *d_planes;            // [nrefs][16][Hp][Wp]  index [yy*4+xx]
   uint8_t *d_stage;             // [H][W] staging for host uploads
   uint8_t *d_spl;               // [nrefs][16][Hq][Wq] search planes: integer picture with an edge-replicated pad of spad, 16 byte shifts
@@ -103,6 +105,14 @@ struct McArgs {
   uint8_t *orig_blk, *pred_blk;
 };
 cudaError_t launch_mc_luma(const McArgs &a, cudaStream_t s);
+struct McMbArgs {                // luma + chroma, either list or both (k_mc_mb)
+  const uint8_t *cur; int cur_pitch; const uint8_t *curc; const uint8_t *refc;
+  const uint8_t *planes; size_t plane_size;
+  int W, H, Wp, mbw, nmb, nrefs;
+  const uint8_t *mb_mode, *b8mode, *pdir; const int8_t *ref8; const int16_t *mv0, *mv1;
+  uint8_t *orig_y, *pred_y, *orig_c, *pred_c;
+};
+cudaError_t launch_mc_mb(const McMbArgs &a, cudaStream_t s);
 cudaError_t launch_expand_pred(int n, const int16_t *pred_mb, int16_t *pred, int16_t *center, cudaStream_t s);
 cudaError_t launch_select_gather(int nmb, int nrefs, const long long *cost, int ref_lambda, const int16_t *mv, int8_t *best_ref, long long *best_cost,
                                  int16_t *best_mv, int32_t *cost32, cudaStream_t s);

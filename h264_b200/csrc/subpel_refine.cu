@@ -421,6 +421,85 @@ __global__ void __launch_bounds__(256) k_mc_luma(const McArgs a)
   reinterpret_cast<uint4 *>(a.orig_blk)[t] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
 }
 
+// ---- luma + chroma prediction of 4:2:0 macroblocks from either list or both: luma_prediction (JM/lencod/src/mc_prediction.c:
+//      144-236: p_dir 0 / 1 / 2, bi_prediction :82-99 = (l0 + l1 + 1) >> 1), chroma_prediction (:469-566) with the bilinear
+//      eighth-sample interpolation of OneComponentChromaPrediction4x4_regenerate (:292-353: every chroma sample takes the vector
+//      of the luma 4x4 block above it, coordinates clipped to the chroma plane per tap).  Unweighted.  24 threads per macroblock:
+//      16 luma 4x4 blocks, 2 x 4 chroma 4x4 blocks; outputs in the block-packed layout of the transform entries. ----
+__device__ __forceinline__ void mc_partition(int mode, const uint8_t *b8, int bx, int by, int &p, int &ox, int &oy)
+{
+  const int qd = (by >> 1) * 2 + (bx >> 1);
+  if (mode == 1) { p = 0; ox = 0; oy = 0; }
+  else if (mode == 2) { p = 1 + (by >> 1); ox = 0; oy = 8 * (by >> 1); }
+  else if (mode == 3) { p = 3 + (bx >> 1); ox = 8 * (bx >> 1); oy = 0; }
+  else {
+    const int sub = b8[qd];
+    if (sub == 4) { p = 5 + qd; ox = 8 * (bx >> 1); oy = 8 * (by >> 1); }
+    else if (sub == 5) { p = 9 + by * 2 + (bx >> 1); ox = 8 * (bx >> 1); oy = 4 * by; }
+    else if (sub == 6) { p = 17 + (by >> 1) * 4 + bx; ox = 4 * bx; oy = 8 * (by >> 1); }
+    else { p = 25 + by * 4 + bx; ox = 4 * bx; oy = 4 * by; }
+  }
+}
+
+__global__ void __launch_bounds__(192) k_mc_mb(const McMbArgs a)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.nmb * 24) return;
+  const int m = t / 24, k = t - 24 * m;
+  const int mbx = m % a.mbw, mby = m / a.mbw, mode = a.mb_mode[m];
+  const int Wc = a.W >> 1, Hc = a.H >> 1;
+  if (k < 16) {
+    const int bx = k & 3, by = k >> 2, qd = (by >> 1) * 2 + (bx >> 1), dir = a.pdir[m * 4 + qd];
+    int p, ox, oy;
+    mc_partition(mode, a.b8mode + m * 4, bx, by, p, ox, oy);
+    int acc[16];
+    for (int i = 0; i < 16; i++) acc[i] = 0;
+    for (int L = 0; L < 2; L++) {
+      if (!(dir == 2 || dir == L)) continue;
+      const int r = a.ref8[(m * 2 + L) * 4 + qd];
+      const int16_t *v = (L ? a.mv1 : a.mv0) + (((size_t)m * a.nrefs + r) * NPART + p) * 2;
+      const int qx = 4 * (mbx * 16 + ox) + v[0], qy = 4 * (mby * 16 + oy) + v[1];
+      const int x = iclamp(qx >> 2, -PADX, a.W + 15) + PADX + (4 * bx - ox), y = iclamp(qy >> 2, -PADY, a.H + 3) + PADY + (4 * by - oy);
+      const uint8_t *rp = a.planes + ((size_t)r * 16 + (qy & 3) * 4 + (qx & 3)) * a.plane_size + (size_t)y * a.Wp + x;
+      for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) acc[i * 4 + j] += rp[(size_t)i * a.Wp + j];
+    }
+    uint8_t *po = a.pred_y + ((size_t)m * 16 + k) * 16, *oo = a.orig_y + ((size_t)m * 16 + k) * 16;
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) {
+        po[i * 4 + j] = (uint8_t)(dir == 2 ? (acc[i * 4 + j] + 1) >> 1 : acc[i * 4 + j]);
+        oo[i * 4 + j] = a.cur[(size_t)(mby * 16 + 4 * by + i) * a.cur_pitch + mbx * 16 + 4 * bx + j];
+      }
+  } else {
+    const int c = k - 16, pl = c >> 2, cb = c & 3, cbx = cb & 1, cby = cb >> 1, qd = cb, dir = a.pdir[m * 4 + qd];
+    uint8_t *po = a.pred_c + (((size_t)m * 2 + pl) * 4 + cb) * 16, *oo = a.orig_c + (((size_t)m * 2 + pl) * 4 + cb) * 16;
+    for (int j = 0; j < 4; j++)
+      for (int i = 0; i < 4; i++) {
+        const int ci = 4 * cbx + i, cj = 4 * cby + j;             // chroma sample inside the macroblock's 8x8 block
+        int p, ox, oy, acc = 0;
+        mc_partition(mode, a.b8mode + m * 4, ci >> 1, cj >> 1, p, ox, oy);
+        for (int L = 0; L < 2; L++) {
+          if (!(dir == 2 || dir == L)) continue;
+          const int r = a.ref8[(m * 2 + L) * 4 + qd];
+          const int16_t *v = (L ? a.mv1 : a.mv0) + (((size_t)m * a.nrefs + r) * NPART + p) * 2;
+          const uint8_t *rc = a.refc + ((size_t)r * 2 + pl) * Wc * Hc;
+          const int ii = 8 * (mbx * 8 + ci) + v[0], jj = 8 * (mby * 8 + cj) + v[1];
+          const int x0 = iclamp(ii >> 3, 0, Wc - 1), x1 = iclamp((ii + 7) >> 3, 0, Wc - 1), y0 = iclamp(jj >> 3, 0, Hc - 1), y1 = iclamp((jj + 7) >> 3, 0, Hc - 1);
+          const int fx = ii & 7, fy = jj & 7;
+          acc += ((8 - fx) * (8 - fy) * rc[(size_t)y0 * Wc + x0] + fx * (8 - fy) * rc[(size_t)y0 * Wc + x1] +
+                  (8 - fx) * fy * rc[(size_t)y1 * Wc + x0] + fx * fy * rc[(size_t)y1 * Wc + x1] + 32) >> 6;
+        }
+        po[j * 4 + i] = (uint8_t)(dir == 2 ? (acc + 1) >> 1 : acc);
+        oo[j * 4 + i] = a.curc[(size_t)pl * Wc * Hc + (size_t)(mby * 8 + cj) * Wc + mbx * 8 + ci];
+      }
+  }
+}
+
+cudaError_t launch_mc_mb(const McMbArgs &a, cudaStream_t s)
+{
+  k_mc_mb<<<(a.nmb * 24 + 191) / 192, 192, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mc_luma(const McArgs &a, cudaStream_t s)
 {
   k_mc_luma<<<(a.nmb * 16 + 255) / 256, 256, 0, s>>>(a);

@@ -306,6 +306,21 @@ int b2me_select_refs_list_dev(b2me_ctx *ctx, const int64_t *cost_dev, int list_s
 int b2me_mc_luma_dev(b2me_ctx *ctx, const uint8_t *mb_mode, const uint8_t *b8mode, const int8_t *ref8, const int16_t *mv,
                      uint8_t *orig_blk, uint8_t *pred_blk, void *stream);
 
+/* Luma AND chroma prediction of 4:2:0 macroblocks from list 0, list 1 or both (SURVEY 8f-1, B slices and chroma):
+ *   luma_prediction (JM/lencod/src/mc_prediction.c:144-236) with p_dir 0 / 1 / 2 -- bi_prediction (:82-99) = (l0 + l1 + 1) >> 1 --
+ *   and chroma_prediction (:469-566) with the bilinear eighth-sample interpolation of
+ *   OneComponentChromaPrediction4x4_regenerate (:292-353).  Unweighted prediction.
+ *   pdir [nmb][4] uint8: per 8x8 quadrant 0 list 0, 1 list 1, 2 bi-predictive;  ref8 [nmb][2][4] int8: reference SLOT per list and
+ *   quadrant (both lists' pictures live in the context's slots);  mv_l0 / mv_l1 [nmb][nrefs][41][2]: the vectors of either list,
+ *   indexed by slot (the two may be the same array);  chroma planes: b2me_set_cur_chroma / b2me_set_ref_chroma.
+ *   orig_y / pred_y [nmb*16][16] as b2me_mc_luma_dev;  orig_c / pred_c [nmb][2][4][16]: the four 4x4 blocks (raster) of Cb, then Cr. */
+int b2me_set_cur_chroma(b2me_ctx *ctx, const uint8_t *u, const uint8_t *v, int stride);
+int b2me_set_cur_chroma_dev(b2me_ctx *ctx, const uint8_t *u_dev, const uint8_t *v_dev, int stride, void *stream);
+int b2me_set_ref_chroma(b2me_ctx *ctx, int ref, const uint8_t *u, const uint8_t *v, int stride);
+int b2me_set_ref_chroma_dev(b2me_ctx *ctx, int ref, const uint8_t *u_dev, const uint8_t *v_dev, int stride, void *stream);
+int b2me_mc_mb_dev(b2me_ctx *ctx, const uint8_t *mb_mode, const uint8_t *b8mode, const uint8_t *pdir, const int8_t *ref8,
+                   const int16_t *mv_l0, const int16_t *mv_l1, uint8_t *orig_y, uint8_t *pred_y, uint8_t *orig_c, uint8_t *pred_c, void *stream);
+
 /* ---- mode-decision distortions on precomputed difference blocks ------------------------ */
 /* distortion4x4/8x8{SAD,SSE,SATD} (JM/lencod/src/me_distortion.c:38-134; p_Vid->distortion4x4/8x8 as bound by
  * select_distortion :136-158): diff [nblk][n*n] int16 raster, n = 4 or 8, kind 0 SAD, 1 SSE, 2 SATD

@@ -188,6 +188,17 @@ class OrcFrame:
         self.L.orc_mc_luma(self.h, _ptr(mb_mode), _ptr(b8mode), _ptr(ref8), _ptr(mv), _ptr(orig), _ptr(pred))
         return orig, pred
 
+    def mc_mb(self, mb_mode, b8mode, pdir, ref8, mv0, mv1, curc, refc):
+        """orc_mc_mb: luma + chroma prediction from either list or both; returns (orig_y, pred_y, orig_c, pred_c)"""
+        nmb = (self.W // 16) * (self.H // 16)
+        mb_mode = np.ascontiguousarray(mb_mode, np.uint8); b8mode = np.ascontiguousarray(b8mode, np.uint8); pdir = np.ascontiguousarray(pdir, np.uint8)
+        ref8 = np.ascontiguousarray(ref8, np.int8); mv0 = np.ascontiguousarray(mv0, np.int16); mv1 = np.ascontiguousarray(mv1, np.int16)
+        curc = np.ascontiguousarray(curc, np.uint8); refc = np.ascontiguousarray(refc, np.uint8)
+        oy = np.zeros((nmb * 16, 16), np.uint8); py = np.zeros_like(oy); oc = np.zeros((nmb, 2, 4, 16), np.uint8); pc = np.zeros_like(oc)
+        self.L.orc_mc_mb(self.h, _ptr(mb_mode), _ptr(b8mode), _ptr(pdir), _ptr(ref8), _ptr(mv0), _ptr(mv1), _ptr(curc), _ptr(refc),
+                         _ptr(oy), _ptr(py), _ptr(oc), _ptr(pc))
+        return oy, py, oc, pc
+
     def bipred_search(self, jobs, lam, metric_h=2, metric_q=2, do_subpel=True, test8x8=False, wp=False, log_denom=0):
         """full_search_bipred (+ sub_pel_bipred) for an array of BIPRED_JOB; returns BIPRED_RESULT array"""
         jobs = np.ascontiguousarray(jobs, BIPRED_JOB)
@@ -327,6 +338,14 @@ class JMRef:
         self.L.jmh_bipred_search(self.h, C.c_int(len(jobs)), _ptr(jobs), _ptr(lam), C.c_int(int(do_subpel)), C.c_int(int(test8x8)),
                                  C.c_int(int(wp)), C.c_int(log_denom), _ptr(out))
         return out
+
+    def chroma_pred4x4(self, plane, pix_c_x, opix_c_y, block_c_x, block_c_y, mv16):
+        """one chroma 4x4 block through the unmodified OneComponentChromaPrediction4x4_regenerate; mv16 [4][4][2]"""
+        plane = np.ascontiguousarray(plane, np.uint8); mv16 = np.ascontiguousarray(mv16, np.int16)
+        out = np.zeros(16, np.uint8)
+        self.L.jmh_chroma_pred4x4(self.h, C.c_int(plane.shape[1]), C.c_int(plane.shape[0]), _ptr(plane), C.c_int(pix_c_x), C.c_int(opix_c_y),
+                                  C.c_int(block_c_x), C.c_int(block_c_y), _ptr(mv16), _ptr(out))
+        return out.reshape(4, 4)
 
     def list_prediction_cost(self, mode, block, costs, ref_lambda, list=0):
         """the reference's list_prediction_cost (list 0 or 1) for one (mode, block): (best_ref, bmcost)"""

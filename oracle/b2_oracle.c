@@ -765,3 +765,68 @@ void orc_epzs_search(void *h, int njobs, const OrcEpzsJob *jobs, const int16_t *
   }
   (void)npats;
 }
+
+/* ------------------------------------------------------------------------------------
+ * Luma + chroma prediction of 4:2:0 macroblocks from list 0, list 1 or both (mirrors b2me_mc_mb_dev):
+ * luma_prediction JM/lencod/src/mc_prediction.c:144-236 (bi_prediction :82-99), chroma_prediction :469-566 with
+ * OneComponentChromaPrediction4x4_regenerate :292-353 -- restated below as orc_chroma_sample: the reference's own arithmetic,
+ * C division of the (possibly negative) eighth-sample coordinate included.
+ * ---------------------------------------------------------------------------------- */
+int orc_chroma_sample(const uint8_t *plane, int Wc, int Hc, int ii, int jj)
+{
+  const int x0 = ii / 8, x1 = (ii + 7) / 8, y0 = jj / 8, y1 = (jj + 7) / 8;        /* C division, as the reference (:338-341) */
+  const int cx0 = x0 < 0 ? 0 : (x0 > Wc - 1 ? Wc - 1 : x0), cx1 = x1 < 0 ? 0 : (x1 > Wc - 1 ? Wc - 1 : x1);
+  const int cy0 = y0 < 0 ? 0 : (y0 > Hc - 1 ? Hc - 1 : y0), cy1 = y1 < 0 ? 0 : (y1 > Hc - 1 ? Hc - 1 : y1);
+  const int f1 = ii & 7, f0 = 8 - f1, g1 = jj & 7, g0 = 8 - g1;
+  return (f0 * g0 * plane[(size_t)cy0 * Wc + cx0] + f1 * g0 * plane[(size_t)cy0 * Wc + cx1] +
+          f0 * g1 * plane[(size_t)cy1 * Wc + cx0] + f1 * g1 * plane[(size_t)cy1 * Wc + cx1] + 32) / 64;
+}
+void orc_mc_mb(void *h, const uint8_t *mb_mode, const uint8_t *b8mode, const uint8_t *pdir, const int8_t *ref8, const int16_t *mv0, const int16_t *mv1,
+               const uint8_t *curc /* [2][Hc][Wc] */, const uint8_t *refc /* [nrefs][2][Hc][Wc] */,
+               uint8_t *orig_y, uint8_t *pred_y, uint8_t *orig_c, uint8_t *pred_c)
+{
+  OrcFrame *f = (OrcFrame *)h;
+  const int mbw = f->W / 16, nmb = mbw * (f->H / 16), Wp = f->W + 2 * PAD_X, Wc = f->W / 2, Hc = f->H / 2;
+  int m, k, i, j, L;
+  for (m = 0; m < nmb; m++) {
+    const int mbx = m % mbw, mby = m / mbw;
+    for (k = 0; k < 16; k++) {
+      const int bx = k & 3, by = k >> 2, qd = (by >> 1) * 2 + (bx >> 1), dir = pdir[m * 4 + qd];
+      int p, ox, oy, acc[16] = {0};
+      orc_block_partition(mb_mode[m], b8mode + m * 4, bx, by, &p, &ox, &oy);
+      for (L = 0; L < 2; L++) {
+        if (!(dir == 2 || dir == L)) continue;
+        {
+          const int r = ref8[(m * 2 + L) * 4 + qd];
+          const int16_t *v = (L ? mv1 : mv0) + (((size_t)m * f->nrefs + r) * 41 + p) * 2;
+          const uint8_t *ref = orc_umv_line4x(orc_frame_planes(h, r), f->W, f->H, 4 * (mby * 16 + oy) + v[1], 4 * (mbx * 16 + ox) + v[0]);
+          for (i = 0; i < 4; i++) for (j = 0; j < 4; j++) acc[i * 4 + j] += ref[(size_t)(4 * by - oy + i) * Wp + (4 * bx - ox + j)];
+        }
+      }
+      for (i = 0; i < 4; i++)
+        for (j = 0; j < 4; j++) {
+          pred_y[((size_t)m * 16 + k) * 16 + i * 4 + j] = (uint8_t)(dir == 2 ? (acc[i * 4 + j] + 1) >> 1 : acc[i * 4 + j]);
+          orig_y[((size_t)m * 16 + k) * 16 + i * 4 + j] = f->cur[(size_t)(mby * 16 + 4 * by + i) * f->W + mbx * 16 + 4 * bx + j];
+        }
+    }
+    for (k = 0; k < 8; k++) {
+      const int pl = k >> 2, cb = k & 3, cbx = cb & 1, cby = cb >> 1, dir = pdir[m * 4 + cb];
+      for (j = 0; j < 4; j++)
+        for (i = 0; i < 4; i++) {
+          const int ci = 4 * cbx + i, cj = 4 * cby + j;
+          int p, ox, oy, acc = 0;
+          orc_block_partition(mb_mode[m], b8mode + m * 4, ci >> 1, cj >> 1, &p, &ox, &oy);
+          for (L = 0; L < 2; L++) {
+            if (!(dir == 2 || dir == L)) continue;
+            {
+              const int r = ref8[(m * 2 + L) * 4 + cb];
+              const int16_t *v = (L ? mv1 : mv0) + (((size_t)m * f->nrefs + r) * 41 + p) * 2;
+              acc += orc_chroma_sample(refc + ((size_t)r * 2 + pl) * Wc * Hc, Wc, Hc, 8 * (mbx * 8 + ci) + v[0], 8 * (mby * 8 + cj) + v[1]);
+            }
+          }
+          pred_c[(((size_t)m * 2 + pl) * 4 + cb) * 16 + j * 4 + i] = (uint8_t)(dir == 2 ? (acc + 1) >> 1 : acc);
+          orig_c[(((size_t)m * 2 + pl) * 4 + cb) * 16 + j * 4 + i] = curc[(size_t)pl * Wc * Hc + (size_t)(mby * 8 + cj) * Wc + mbx * 8 + ci];
+        }
+    }
+  }
+}

@@ -349,3 +349,31 @@ void jmh_list_prediction_cost(void *hh, int list, int mode, int block, int nrefs
   *best_ref = bref[list]; *bmcost_out = (long long)bmcost[list];
 }
 int jmh_refbits(void *hh, int r) { return ((JMH *)hh)->p_Vid->refbits[r]; }
+
+/* One chroma 4x4 block through the UNMODIFIED OneComponentChromaPrediction4x4_regenerate (mc_prediction.c:292-353):
+ * plane [Hc][Wc] = one chroma component of the reference picture, (pix_c_x, opix_c_y) = the macroblock's chroma origin,
+ * (block_c_x, block_c_y) in {0, 4}^2, mv16 [4][4][2] = the vectors of the macroblock's sixteen luma 4x4 blocks. */
+#include "mc_prediction.h"
+void jmh_chroma_pred4x4(void *hh, int Wc, int Hc, const unsigned char *plane, int pix_c_x, int opix_c_y, int block_c_x, int block_c_y,
+                        const short *mv16, unsigned char *out16)
+{
+  JMH *h = (JMH *)hh; VideoParameters *p_Vid = h->p_Vid;
+  StorablePicture pic; Macroblock mb = h->mb; Macroblock mbd; seq_parameter_set_rbsp_t sps;
+  MotionVector mvs[4][4], *rows[4]; imgpel mpred[16]; imgpel **uv2[2]; int x, y, i;
+  memset(&pic, 0, sizeof(pic)); memset(&mbd, 0, sizeof(mbd)); memset(&sps, 0, sizeof(sps));
+  sps.chroma_format_idc = 1;
+  get_mem2Dpel(&uv2[0], Hc, Wc); uv2[1] = uv2[0];
+  for (y = 0; y < Hc; y++) for (x = 0; x < Wc; x++) uv2[0][y][x] = plane[(size_t)y * Wc + x];
+  pic.imgUV = uv2; pic.chroma_vector_adjustment = 0;
+  for (y = 0; y < 4; y++) { rows[y] = mvs[y]; for (x = 0; x < 4; x++) { mvs[y][x].mv_x = mv16[(y * 4 + x) * 2]; mvs[y][x].mv_y = mv16[(y * 4 + x) * 2 + 1]; } }
+  {
+    seq_parameter_set_rbsp_t *save_sps = p_Vid->active_sps; Macroblock *save_md = p_Vid->mb_data;
+    const int sx = p_Vid->mb_cr_size_x, sy = p_Vid->mb_cr_size_y, wc = p_Vid->width_cr, hc = p_Vid->height_cr;
+    p_Vid->active_sps = &sps; p_Vid->mb_data = &mbd; p_Vid->mb_cr_size_x = p_Vid->mb_cr_size_y = 8; p_Vid->width_cr = Wc; p_Vid->height_cr = Hc;
+    mb.mbAddrX = 0; mb.pix_c_x = (short)pix_c_x; mb.opix_c_y = (short)opix_c_y;
+    OneComponentChromaPrediction4x4_regenerate(&mb, mpred, block_c_x, block_c_y, rows, &pic, 0);
+    p_Vid->active_sps = save_sps; p_Vid->mb_data = save_md; p_Vid->mb_cr_size_x = sx; p_Vid->mb_cr_size_y = sy; p_Vid->width_cr = wc; p_Vid->height_cr = hc;
+  }
+  for (i = 0; i < 16; i++) out16[i] = (unsigned char)mpred[i];
+  free_mem2Dpel(uv2[0]);
+}

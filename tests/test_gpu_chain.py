@@ -110,3 +110,43 @@ def test_compact_frame_search_equals_full_arrays_plus_selection():
     for e, parts in enumerate(oracle.ENTRY_PARTS):
         for q in parts:
             assert (bm[:, q] == mv_sub[np.arange(nmb), ebr[:, e], q]).all(), (e, q)
+
+
+def test_luma_and_chroma_prediction_of_both_lists_matches_oracle():
+    """b2me_mc_mb_dev: luma + chroma prediction of 4:2:0 macroblocks from list 0, list 1 or both (bi_prediction), every macroblock
+    mode and 8x8 sub-mode, vectors that leave the picture; the luma of list-0 macroblocks equals b2me_mc_luma_dev's."""
+    W, H, R, NR = 96, 64, 12, 3
+    rng = np.random.default_rng(14)
+    yuv = [np.frombuffer(synth.yuv420_sequence(W, H, 1, seed=60 + i), np.uint8) for i in range(NR + 1)]
+    Y = [f[:W * H].reshape(H, W) for f in yuv]
+    U = [f[W * H:W * H * 5 // 4].reshape(H // 2, W // 2) for f in yuv]
+    V = [f[W * H * 5 // 4:].reshape(H // 2, W // 2) for f in yuv]
+    nmb = (W // 16) * (H // 16)
+    mb_mode = rng.choice([1, 2, 3, 8], nmb).astype(np.uint8)
+    b8mode = rng.integers(4, 8, (nmb, 4)).astype(np.uint8)
+    pdir = rng.integers(0, 3, (nmb, 4)).astype(np.uint8)
+    ref8 = rng.integers(0, NR, (nmb, 2, 4)).astype(np.int8)
+    mv0 = rng.integers(-60, 61, (nmb, NR, 41, 2)).astype(np.int16); mv1 = rng.integers(-60, 61, (nmb, NR, 41, 2)).astype(np.int16)
+    mv0[:3] = rng.integers(-500, 501, (3, NR, 41, 2)); mv1[-3:] = rng.integers(-500, 501, (3, NR, 41, 2))      # far outside the picture
+    dev = torch.device("cuda", 0)
+    s = api.Searcher(W, H, NR, R)
+    s.set_cur(Y[NR]); s.set_cur_chroma(U[NR], V[NR])
+    for r in range(NR):
+        s.set_ref(r, Y[r]); s.set_ref_chroma(r, U[r], V[r])
+    t = lambda a: torch.from_numpy(a).to(dev)
+    oy = torch.zeros((nmb * 16, 16), dtype=torch.uint8, device=dev); py = torch.zeros_like(oy)
+    oc = torch.zeros((nmb, 2, 4, 16), dtype=torch.uint8, device=dev); pc = torch.zeros_like(oc)
+    s.mc_mb_dev(t(mb_mode), t(b8mode), t(pdir), t(ref8), t(mv0), t(mv1), oy, py, oc, pc)
+    torch.cuda.synchronize()
+    of = oracle.OrcFrame(Y[NR], [Y[r] for r in range(NR)], R)
+    curc = np.stack([U[NR], V[NR]]); refc = np.stack([np.stack([U[r], V[r]]) for r in range(NR)])
+    e = of.mc_mb(mb_mode, b8mode, pdir, ref8, mv0, mv1, curc, refc)
+    for g, x, n in zip((oy, py, oc, pc), e, ("orig_y", "pred_y", "orig_c", "pred_c")):
+        assert (g.cpu().numpy() == x).all(), n
+    # list-0 only: the luma equals the single-list entry's
+    pd0 = np.zeros_like(pdir)
+    s.mc_mb_dev(t(mb_mode), t(b8mode), t(pd0), t(ref8), t(mv0), t(mv1), oy, py, oc, pc)
+    o2 = torch.zeros_like(oy); p2 = torch.zeros_like(py)
+    s.mc_luma_dev(t(mb_mode), t(b8mode), t(np.ascontiguousarray(ref8[:, 0])), t(mv0), o2, p2)
+    torch.cuda.synchronize()
+    assert (py == p2).all() and (oy == o2).all()

@@ -306,3 +306,33 @@ def test_deblock_restatement_matches_reference_golden():
                 assert (a == g[f"{tag}{i}_{p}1"]).all(), (tag, i, p)
             n += 1
     assert n == 12
+
+
+def test_chroma_prediction_restatement_matches_reference():
+    """orc_chroma_sample (the eighth-sample bilinear interpolation of chroma prediction) against the UNMODIFIED
+    OneComponentChromaPrediction4x4_regenerate (JM/lencod/src/mc_prediction.c:292-353) through the harness: random planes,
+    vectors that leave the picture on every side (negative coordinates: the reference divides with C truncation), different
+    vectors for the four 2x2 groups of a block."""
+    import ctypes as C
+    rng = np.random.default_rng(8)
+    jm = oracle.JMRef(64, 48, 4, 1)
+    L = oracle.orc_lib()
+    Wc, Hc = 32, 24
+    plane = rng.integers(0, 256, (Hc, Wc)).astype(np.uint8)
+    n = 0
+    for trial in range(300):
+        mbx, mby = int(rng.integers(0, Wc // 8)), int(rng.integers(0, Hc // 8))
+        span = 40 if trial % 3 else 400
+        mv16 = rng.integers(-span, span + 1, (4, 4, 2)).astype(np.int16)
+        for bcx in (0, 4):
+            for bcy in (0, 4):
+                ref = jm.chroma_pred4x4(plane, mbx * 8, mby * 8, bcx, bcy, mv16)
+                for j in range(4):
+                    for i in range(4):
+                        ci, cj = bcx + i, bcy + j
+                        v = mv16[cj >> 1, ci >> 1]
+                        got = L.orc_chroma_sample(plane.ctypes.data_as(C.c_void_p), C.c_int(Wc), C.c_int(Hc), C.c_int(8 * (mbx * 8 + ci) + int(v[0])),
+                                                  C.c_int(8 * (mby * 8 + cj) + int(v[1])))
+                        assert got == int(ref[j, i]), (trial, bcx, bcy, i, j)
+                        n += 1
+    assert n == 300 * 64
