@@ -455,6 +455,21 @@ class PoolSearcher:
         return self.L.b2fp_launch_count(self.h)
 
 
+def tq_chroma(params, orig, pred, device=0):
+    """b2tq_chroma (4:2:0 chroma, one plane): orig / pred [nmb][64] raster -> dc_level, dc_run, ac_level, ac_run, recon, cr_cbp"""
+    orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+    nmb = orig.shape[0]
+    dl = np.zeros((nmb, 4), np.int16); dr = np.zeros((nmb, 4), np.uint8)
+    al = np.zeros((nmb, 4, 16), np.int16); ar = np.zeros((nmb, 4, 16), np.uint8)
+    rec = np.zeros((nmb, 64), np.uint8); cbp = np.zeros(nmb, np.uint8)
+    L = lib()
+    L.b2tq_last_error.restype = C.c_char_p
+    r = L.b2tq_chroma(C.c_int(device), C.byref(params), C.c_int(nmb), _p(orig), _p(pred), _p(dl), _p(dr), _p(al), _p(ar), _p(rec), _p(cbp))
+    if r:
+        raise B2Error(f"b2tq_chroma failed ({r}): {L.b2tq_last_error().decode()}")
+    return dl, dr, al, ar, rec, cbp
+
+
 def tq16x16(params, orig, pred, device=0):
     """b2tq_16x16 (Intra16x16 luma): orig / pred [nmb][256] raster -> dc_level, dc_run, ac_level, ac_run, recon, ac_coef"""
     orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)

@@ -338,6 +338,112 @@ __global__ void __launch_bounds__(128) k_tq16x16(const __grid_constant__ b2tq_pa
   if (b == 0) ac_coef[mb] = anyac ? 15 : 0;
 }
 
+// ---- chroma of 4:2:0 macroblocks, one plane: residual_transform_quant_chroma_4x4 (JM/lencod/src/block.c:953-1200) -------------------
+// Four threads per 8x8 chroma block (one per 4x4 block, raster), eight blocks per warp.  forward4x4 per thread; the four DC
+// coefficients go through hadamard2x2 (JM/lcommon/src/transform.c:302-315), quant_dc2x2_normal (quantChroma_normal.c:37-96: natural
+// order, offset << 1, q_bits + 1, levels de-quantised in place), ihadamard2x2 (:317-331) and >> 5 with shuffles; quant_ac4x4_normal
+// (quant4x4_normal.c:117-190) per thread with its coefficient cost, summed over the four threads for the _CHROMA_COEFF_COST_ rule
+// (block.c:1137-1168: fewer / smaller AC levels than that are all dropped); inverse4x4 and sample_reconstruct stay in the thread.
+template <bool FIELD>
+__global__ void __launch_bounds__(128) k_tq_chroma(const __grid_constant__ b2tq_params c_tq, int nmb, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ pred,
+                                                   short *__restrict__ dc_level, uint8_t *__restrict__ dc_run, short *__restrict__ ac_level, uint8_t *__restrict__ ac_run,
+                                                   uint8_t *__restrict__ recon, uint8_t *__restrict__ cr_cbp)
+{
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int mb = gid >> 2, b = gid & 3, lane = threadIdx.x & 31, q0 = lane & ~3;        // q0: first lane of this block's quad
+  const bool live = mb < nmb;
+  const int jj = b >> 1, ii = b & 1;
+  const int qp_per = c_tq.qp / 6, q_bits = 15 + qp_per;
+  int x[16], pr[16];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const size_t o = (size_t)mb * 64 + (4 * jj + r) * 8 + 4 * ii;
+    const uint32_t ow = live ? *reinterpret_cast<const uint32_t *>(orig + o) : 0u, pw = live ? *reinterpret_cast<const uint32_t *>(pred + o) : 0u;
+#pragma unroll
+    for (int c = 0; c < 4; c++) { pr[4 * r + c] = (pw >> (8 * c)) & 255; x[4 * r + c] = (int)((ow >> (8 * c)) & 255) - pr[4 * r + c]; }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) fwd4(x[4 * r], x[4 * r + 1], x[4 * r + 2], x[4 * r + 3]);
+#pragma unroll
+  for (int c = 0; c < 4; c++) fwd4(x[c], x[4 + c], x[8 + c], x[12 + c]);
+  // ---- hadamard2x2: thread b ends with coefficient b of the 2x2 DC block ----
+  int d[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) d[k] = __shfl_sync(0xffffffffu, x[0], q0 + k);
+  int m = b == 0 ? d[0] + d[1] + d[2] + d[3] : b == 1 ? d[0] - d[1] + d[2] - d[3] : b == 2 ? d[0] + d[1] - d[2] - d[3] : d[0] - d[1] - d[2] + d[3];
+  // ---- quant_dc2x2_normal (natural order); the level list through a ballot ----
+  int dlev = 0;
+  if (m != 0) {
+    int lv = ((m < 0 ? -m : m) * c_tq.scale[0] + (c_tq.offset[0] << 1)) >> (q_bits + 1);
+    if (lv != 0) { if (c_tq.cavlc && lv > 2063) lv = 2063; dlev = m < 0 ? -lv : lv; }
+  }
+  m = (dlev * c_tq.invscale[0]) << qp_per;
+  const uint32_t dmask = (__ballot_sync(0xffffffffu, dlev != 0) >> q0) & 0xfu;
+  if (live) { dc_level[(size_t)mb * 4 + b] = 0; dc_run[(size_t)mb * 4 + b] = 0; }
+  __syncwarp();
+  if (live && dlev != 0) {
+    const uint32_t below = dmask & ((1u << b) - 1u);
+    const int idx = __popc(below), run = below ? b - 1 - (31 - __clz(below)) : b;
+    dc_level[(size_t)mb * 4 + idx] = (short)dlev; dc_run[(size_t)mb * 4 + idx] = (uint8_t)run;
+  }
+  // ---- ihadamard2x2, >> 5 ----
+#pragma unroll
+  for (int k = 0; k < 4; k++) d[k] = __shfl_sync(0xffffffffu, m, q0 + k);
+  x[0] = (b == 0 ? d[0] + d[1] + d[2] + d[3] : b == 1 ? d[0] - d[1] + d[2] - d[3] : b == 2 ? d[0] + d[1] - d[2] - d[3] : d[0] - d[1] - d[2] + d[3]) >> 5;
+  // ---- quant_ac4x4_normal of this thread's block ----
+  __align__(16) short lev[16]; __align__(16) unsigned char rn[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { lev[i] = 0; rn[i] = 0; }
+  int nz = 0, n = 0, runc = 0, cost = 0;
+#pragma unroll
+  for (int s = 1; s < 16; s++) {
+    const int i = FIELD ? FS4[s][0] : ZZ4[s][0], j = FIELD ? FS4[s][1] : ZZ4[s][1], idx = j * 4 + i;
+    const int m7 = x[idx];
+    int lv = 0;
+    if (m7 != 0) lv = ((m7 < 0 ? -m7 : m7) * c_tq.scale[idx] + c_tq.offset[idx]) >> q_bits;
+    if (lv != 0) {
+      if (c_tq.cavlc && lv > 2063) lv = 2063;
+      cost += lv > 1 ? 999999 : cost4(runc, c_tq.disthres);      // COEFF_COST4x4 (block.c:72-76)
+      const int sl = m7 < 0 ? -lv : lv;
+      x[idx] = (((sl * c_tq.invscale[idx]) << qp_per) + 8) >> 4;
+      lev[n] = (short)sl; rn[n] = (unsigned char)runc; n++;
+      runc = 0; nz = 1;
+    } else { x[idx] = 0; runc++; }
+  }
+  // ---- _CHROMA_COEFF_COST_: the four blocks' cost together ----
+  int tot = cost > 999999 ? 999999 : cost;
+  tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+  tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+  const uint32_t anynz = (__ballot_sync(0xffffffffu, nz != 0) >> q0) & 0xfu;
+  const bool drop = anynz && tot < 4;
+  if (drop && nz) {
+    nz = 0;
+#pragma unroll
+    for (int i = 1; i < 16; i++) x[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) lev[i] = 0;
+  }
+  if (x[0] != 0 || nz) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) inv4(x[4 * r], x[4 * r + 1], x[4 * r + 2], x[4 * r + 3]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) inv4(x[c], x[4 + c], x[8 + c], x[12 + c]);
+  }
+  if (!live) return;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) v |= (uint32_t)clip255(((x[4 * r + c] + 32) >> 6) + pr[4 * r + c]) << (8 * c);
+    *reinterpret_cast<uint32_t *>(recon + (size_t)mb * 64 + (4 * jj + r) * 8 + 4 * ii) = v;
+  }
+  const uint4 *lv4 = reinterpret_cast<const uint4 *>(lev);
+  uint4 *lo = reinterpret_cast<uint4 *>(ac_level + ((size_t)mb * 4 + b) * 16);
+  lo[0] = lv4[0]; lo[1] = lv4[1];
+  *reinterpret_cast<uint4 *>(ac_run + ((size_t)mb * 4 + b) * 16) = *reinterpret_cast<const uint4 *>(rn);
+  if (b == 0) cr_cbp[mb] = (uint8_t)((anynz && !drop) ? 2 : (dmask ? 1 : 0));
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -537,4 +643,46 @@ extern "C" int b2tq_default_params(b2tq_params *p, int is8x8, int qp, int intra,
       }
   }
   return B2ME_OK;
+}
+
+// chroma (4:2:0) blocks of one plane (see include/b2me.h)
+extern "C" int b2tq_chroma_dev(const b2tq_params *p, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+                               int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *cr_cbp, void *stream)
+{
+  if (!p || nmb < 0 || !orig || !pred || !dc_level || !dc_run || !ac_level || !ac_run || !recon || !cr_cbp) { snprintf(g_tqerr, sizeof(g_tqerr), "b2tq_chroma: bad arguments"); return B2ME_EINVAL; }
+  if (p->mode != 0) { snprintf(g_tqerr, sizeof(g_tqerr), "b2tq_chroma: version1 has no chroma DC path (mode must be 0)"); return B2ME_EUNSUPPORTED; }
+  { int r = check_tq(p, 0); if (r) return r; }
+  if (nmb == 0) return B2ME_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = (nmb * 4 + 127) / 128;
+  if (p->field_scan) k_tq_chroma<true><<<grid, 128, 0, s>>>(*p, nmb, orig, pred, dc_level, dc_run, ac_level, ac_run, recon, cr_cbp);
+  else k_tq_chroma<false><<<grid, 128, 0, s>>>(*p, nmb, orig, pred, dc_level, dc_run, ac_level, ac_run, recon, cr_cbp);
+  TQ_CHECK(cudaGetLastError());
+  return B2ME_OK;
+}
+extern "C" int b2tq_chroma(int device, const b2tq_params *p, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+                           int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *cr_cbp)
+{
+  if (!p || nmb < 0 || !orig || !pred || !dc_level || !dc_run || !ac_level || !ac_run || !recon || !cr_cbp) { snprintf(g_tqerr, sizeof(g_tqerr), "b2tq_chroma: bad arguments"); return B2ME_EINVAL; }
+  if (nmb == 0) return B2ME_OK;
+  TQ_CHECK(cudaSetDevice(device));
+  const size_t n = (size_t)nmb;
+  const size_t o_pred = n * 64, o_rec = o_pred + n * 64, o_dlev = o_rec + n * 64, o_drun = o_dlev + n * 8, o_alev = (o_drun + n * 4 + 15) & ~(size_t)15,
+               o_arun = o_alev + n * 128, o_cbp = o_arun + n * 64, total = o_cbp + n;
+  uint8_t *d = nullptr;
+  TQ_CHECK(cudaMalloc(&d, total));
+  cudaMemcpy(d, orig, n * 64, cudaMemcpyHostToDevice); cudaMemcpy(d + o_pred, pred, n * 64, cudaMemcpyHostToDevice);
+  int r = b2tq_chroma_dev(p, nmb, d, d + o_pred, (int16_t *)(d + o_dlev), d + o_drun, (int16_t *)(d + o_alev), d + o_arun, d + o_rec, d + o_cbp, 0);
+  if (!r) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(recon, d + o_rec, n * 64, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dc_level, d + o_dlev, n * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dc_run, d + o_drun, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ac_level, d + o_alev, n * 128, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ac_run, d + o_arun, n * 64, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(cr_cbp, d + o_cbp, n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { snprintf(g_tqerr, sizeof(g_tqerr), "b2tq_chroma: %s", cudaGetErrorString(e)); r = B2ME_ECUDA; }
+  }
+  cudaFree(d);
+  return r;
 }

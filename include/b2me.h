@@ -480,6 +480,17 @@ int b2tq_16x16(int device, const b2tq_params *p, int nmb, const uint8_t *orig, c
                int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *ac_coef);
 int b2tq_16x16_dev(const b2tq_params *p, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
                    int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *ac_coef, void *stream);
+/* Chroma of 4:2:0 macroblocks, one plane at a time:  <- residual_transform_quant_chroma_4x4  JM/lencod/src/block.c:953-1200
+ *    hadamard2x2 / ihadamard2x2 of the four DC coefficients       JM/lcommon/src/transform.c:302-331
+ *    quant_dc2x2_normal                                            JM/lencod/src/quantChroma_normal.c:37-96
+ *    quant_ac4x4_normal + the _CHROMA_COEFF_COST_ rule             JM/lencod/src/quant4x4_normal.c:117-190, block.c:1137-1168
+ * p->qp = the CHROMA qp (qpc[uv]) and p's tables the chroma plane's quantiser (4x4).  (hadamard4x2 belongs to 4:2:2: out of scope.)
+ * orig / pred / recon [nmb][64] raster 8x8; dc_level [nmb][4] int16 + dc_run [nmb][4] u8 = cofDC (zero-terminated, zero-padded);
+ * ac_level / ac_run [nmb][4][16]: the four 4x4 blocks in raster order; cr_cbp [nmb]: 0 no coefficient, 1 DC only, 2 AC. */
+int b2tq_chroma(int device, const b2tq_params *p, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+                int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *cr_cbp);
+int b2tq_chroma_dev(const b2tq_params *p, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+                    int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *cr_cbp, void *stream);
 const char *b2tq_last_error(void);
 
 #ifdef __cplusplus

@@ -581,6 +581,18 @@ def tq16x16(params, orig, pred):
     return dl, dr, al, ar, rec, ac
 
 
+def tq_chroma(params, orig, pred):
+    """restated residual_transform_quant_chroma_4x4 (4:2:0, one plane): orig / pred [nmb][64] raster 8x8 -> dc_level [nmb][4] i16,
+    dc_run [nmb][4] u8, ac_level [nmb][4][16] i16, ac_run [nmb][4][16] u8, recon [nmb][64] u8, cr_cbp [nmb] u8"""
+    orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+    nmb = orig.shape[0]
+    dl = np.zeros((nmb, 4), np.int16); dr = np.zeros((nmb, 4), np.uint8)
+    al = np.zeros((nmb, 4, 16), np.int16); ar = np.zeros((nmb, 4, 16), np.uint8)
+    rec = np.zeros((nmb, 64), np.uint8); cbp = np.zeros(nmb, np.uint8)
+    orc_lib().orc_tq_chroma(C.byref(params), C.c_int(nmb), _ptr(orig), _ptr(pred), _ptr(dl), _ptr(dr), _ptr(al), _ptr(ar), _ptr(rec), _ptr(cbp))
+    return dl, dr, al, ar, rec, cbp
+
+
 class JMQuantRef:
     """The unmodified JM residual_transform_quant_luma_4x4/_8x8 behind oracle/jm_harness_tq.c."""
 
@@ -602,6 +614,23 @@ class JMQuantRef:
         f = self.L.jmq_tq4x4 if n == 4 else self.L.jmq_tq8x8
         f(self.h, C.c_int(qp), C.c_int(intra), C.c_int(nblk), _ptr(orig), _ptr(pred), _ptr(level), _ptr(run), _ptr(recon), _ptr(cost), _ptr(nz))
         return level[:, :m].astype(np.int16), run[:, :m].astype(np.uint8), recon, cost, nz.astype(np.uint8)
+
+    def tq_chroma(self, qpc, intra, uv, orig, pred):
+        """the unmodified residual_transform_quant_chroma_4x4 on [nmb][64] raster 8x8 chroma blocks of plane uv"""
+        orig = np.ascontiguousarray(orig, np.uint8); pred = np.ascontiguousarray(pred, np.uint8)
+        nmb = orig.shape[0]
+        dl = np.zeros((nmb, 5), np.int32); dr = np.zeros((nmb, 5), np.int32)
+        al = np.zeros((nmb, 4, 16), np.int32); ar = np.zeros((nmb, 4, 16), np.int32)
+        rec = np.zeros((nmb, 64), np.uint8); cbp = np.zeros(nmb, np.int32)
+        self.L.jmq_tq_chroma(self.h, C.c_int(qpc), C.c_int(intra), C.c_int(uv), C.c_int(nmb), _ptr(orig), _ptr(pred), _ptr(dl), _ptr(dr), _ptr(al), _ptr(ar),
+                             _ptr(rec), _ptr(cbp))
+        return dl[:, :4].astype(np.int16), dr[:, :4].astype(np.uint8), al.astype(np.int16), ar.astype(np.uint8), rec, cbp.astype(np.uint8)
+
+    def params_chroma(self, plane, qp, intra):
+        """[3][16] table (ScaleComp, OffsetComp, InvScaleComp) of a chroma plane's 4x4 quantiser, for tq_params()"""
+        out = np.zeros((3, 16), np.int32)
+        self.L.jmq_params_chroma(self.h, C.c_int(plane), C.c_int(qp), C.c_int(intra), _ptr(out))
+        return out
 
     def tq16x16(self, qp, orig, pred):
         """the unmodified residual_transform_quant_luma_16x16 (Intra16x16 luma) on [nmb][256] raster macroblocks"""

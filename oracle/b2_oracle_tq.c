@@ -264,3 +264,78 @@ void orc_tq16x16(const orc_tq_params *P, int nmb, const uint8_t *orig, const uin
     ac_coef[k] = (uint8_t)ac;
   }
 }
+
+/* ---- chroma of a 4:2:0 macroblock, one plane: residual_transform_quant_chroma_4x4 (JM/lencod/src/block.c:953-1200) -----------
+ * forward4x4 of the four 4x4 blocks, hadamard2x2 of their DC coefficients (lcommon/src/transform.c:302-315), quant_dc2x2_normal
+ * (quantChroma_normal.c:37-96: natural order, offset << 1, q_bits + 1, levels de-quantised in place), ihadamard2x2 (:317-331)
+ * and >> 5, quant_ac4x4_normal per block (quant4x4_normal.c:117-190) with its coefficient cost, the rule that throws ALL AC
+ * levels away when that cost stays below _CHROMA_COEFF_COST_ = 4 (block.c:1137-1168), inverse4x4 of the blocks that hold
+ * anything, sample_reconstruct.  P->qp = the chroma qp (qpc[uv]), P's tables = the chroma plane's.
+ * dc_level / dc_run [nmb][4]; ac_level / ac_run [nmb][4][16] (blocks in raster order); cr_cbp: 0 nothing, 1 DC only, 2 AC. */
+void orc_tq_chroma(const orc_tq_params *P, int nmb, const uint8_t *orig, const uint8_t *pred, int16_t *dc_level, uint8_t *dc_run,
+                   int16_t *ac_level, uint8_t *ac_run, uint8_t *recon, uint8_t *cr_cbp)
+{
+  int k, b, i, j, s;
+  const int qp_per = P->qp / 6, q_bits = 15 + qp_per;
+  const uint8_t (*scan)[2] = P->field_scan ? FIELD4 : SNGL4;
+  for (k = 0; k < nmb; k++) {
+    int t[4][16], m[4], d[4], n = 0, runc = 0, dcnz = 0, cost = 0, nzb[4] = {0, 0, 0, 0}, anynz = 0, cbp = 0;
+    memset(dc_level + 4 * k, 0, 8); memset(dc_run + 4 * k, 0, 4);
+    memset(ac_level + 64 * k, 0, 128); memset(ac_run + 64 * k, 0, 64);
+    for (b = 0; b < 4; b++) {
+      int res[16];
+      for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) { int o = 64 * k + (4 * (b >> 1) + j) * 8 + 4 * (b & 1) + i; res[4 * j + i] = (int)orig[o] - (int)pred[o]; }
+      orc_forward4x4(res, t[b]);
+    }
+    m[0] = t[0][0] + t[1][0] + t[2][0] + t[3][0]; m[1] = t[0][0] - t[1][0] + t[2][0] - t[3][0];
+    m[2] = t[0][0] + t[1][0] - t[2][0] - t[3][0]; m[3] = t[0][0] - t[1][0] - t[2][0] + t[3][0];
+    for (s = 0; s < 4; s++) {
+      if (m[s] != 0) {
+        int lv = (abs(m[s]) * P->scale[0] + (P->offset[0] << 1)) >> (q_bits + 1);
+        if (lv != 0) {
+          if (P->cavlc && lv > 2063) lv = 2063;
+          lv = m[s] < 0 ? -lv : lv;
+          m[s] = (lv * P->invscale[0]) << qp_per;
+          dc_level[4 * k + n] = (int16_t)lv; dc_run[4 * k + n] = (uint8_t)runc; n++; runc = 0; dcnz = 1;
+        } else { runc++; m[s] = 0; }
+      } else runc++;
+    }
+    if (dcnz) cbp = 1;
+    d[0] = m[0] + m[1] + m[2] + m[3]; d[1] = m[0] - m[1] + m[2] - m[3]; d[2] = m[0] + m[1] - m[2] - m[3]; d[3] = m[0] - m[1] - m[2] + m[3];
+    for (b = 0; b < 4; b++) t[b][0] = d[b] >> 5;
+    for (b = 0; b < 4; b++) {
+      n = 0; runc = 0;
+      for (s = 1; s < 16; s++) {
+        int idx = scan[s][1] * 4 + scan[s][0], m7 = t[b][idx];
+        if (m7 != 0) {
+          int lv = (abs(m7) * P->scale[idx] + P->offset[idx]) >> q_bits;
+          if (lv != 0) {
+            if (P->cavlc && lv > 2063) lv = 2063;
+            cost += (lv > 1) ? 999999 : COST4[P->disthres][runc];
+            lv = m7 < 0 ? -lv : lv;
+            t[b][idx] = (((lv * P->invscale[idx]) << qp_per) + 8) >> 4;
+            ac_level[(4 * k + b) * 16 + n] = (int16_t)lv; ac_run[(4 * k + b) * 16 + n] = (uint8_t)runc; n++; runc = 0; nzb[b] = 1;
+          } else { t[b][idx] = 0; runc++; }
+        } else runc++;
+      }
+      if (nzb[b]) anynz = 1;
+    }
+    if (anynz && cost < 4) {                         /* _CHROMA_COEFF_COST_: too few, too small AC levels -- drop them all */
+      for (b = 0; b < 4; b++)
+        if (nzb[b]) {
+          nzb[b] = 0;
+          for (s = 1; s < 16; s++) t[b][s] = 0;
+          memset(ac_level + (4 * k + b) * 16, 0, 32);       /* ACRun keeps its values, as in the reference (only the levels are cleared) */
+        }
+    } else if (anynz) cbp = 2;
+    for (b = 0; b < 4; b++) {
+      int r[16];
+      if (t[b][0] != 0 || nzb[b]) orc_inverse4x4(t[b], r); else memcpy(r, t[b], sizeof(r));
+      for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) {
+        int o = 64 * k + (4 * (b >> 1) + j) * 8 + 4 * (b & 1) + i;
+        recon[o] = (uint8_t)clip255(((r[4 * j + i] + 32) >> 6) + pred[o]);
+      }
+    }
+    cr_cbp[k] = (uint8_t)cbp;
+  }
+}

@@ -167,3 +167,53 @@ void jmq_tq16x16(void *hh, int qp, int nmb, const unsigned char *orig, const uns
       for (i = 0; i < 16; i++) recon[k * 256 + j * 16 + i] = (unsigned char)h->enc->imgY[j][i];
   }
 }
+
+/* ---- chroma (4:2:0): residual_transform_quant_chroma_4x4 (JM/lencod/src/block.c:953-1200) -> forward4x4 x 4, hadamard2x2 /
+ * ihadamard2x2 (lcommon/src/transform.c:302-331), quant_dc2x2_normal (quantChroma_normal.c:37-96), quant_ac4x4_normal
+ * (quant4x4_normal.c:117-190) with the _CHROMA_COEFF_COST_ rule, inverse4x4, sample_reconstruct.
+ * nmb chroma blocks of one plane; orig / pred / recon [nmb][64] raster 8x8; dc_level / dc_run [nmb][5]; ac_level / ac_run
+ * [nmb][4 blocks, raster][16]; cr_cbp [nmb] = the return value (called with cr_cbp = 0); plane = uv + 1 selects the quantiser set. */
+#include "quantChroma.h"
+void jmq_tq_chroma(void *hh, int qpc, int intra, int uv, int nmb, const unsigned char *orig, const unsigned char *pred,
+                   int *dc_level, int *dc_run, int *ac_level, int *ac_run, unsigned char *recon, int *cr_cbp)
+{
+  JMQ *h = (JMQ *)hh; Slice *s = h->slice; VideoParameters *p_Vid = h->p_Vid; int k, i, j, n, b;
+  if (!s->cofDC) { get_mem3Dint(&s->cofDC, 3, 2, 18); get_mem2Dint(&s->tblk4x4, 4, 4); }
+  if (!h->enc->imgUV) get_mem3Dpel(&h->enc->imgUV, 2, 8, 8);
+  p_Vid->mb_cr_size_x = p_Vid->mb_cr_size_y = 8; p_Vid->num_blk8x8_uv = 2; p_Vid->yuv_format = YUV420; p_Vid->AdaptiveRounding = 0;
+  s->bitdepth_chroma_qp_scale = 0;
+  init_quant_Chroma(s);
+  h->mb.qpc[uv] = qpc; h->mb.mb_type = intra ? I16MB : P16x16; h->mb.pix_c_x = 0; h->mb.pix_c_y = 0; h->mb.is_field_mode = 0;
+  h->mb.luma_transform_size_8x8_flag = 0;
+  p_Vid->max_pel_value_comp[1] = p_Vid->max_pel_value_comp[2] = 255;
+  for (k = 0; k < nmb; k++) {
+    for (j = 0; j < 8; j++)
+      for (i = 0; i < 8; i++) {
+        s->mb_pred[uv + 1][j][i] = pred[k * 64 + j * 8 + i];
+        s->mb_ores[uv + 1][j][i] = (int)orig[k * 64 + j * 8 + i] - (int)pred[k * 64 + j * 8 + i];
+      }
+    for (b = 0; b < 4; b++) { memset(s->cofAC[4 + uv][b][0], 0, 65 * sizeof(int)); memset(s->cofAC[4 + uv][b][1], 0, 65 * sizeof(int)); }
+    memset(s->cofDC[uv + 1][0], 0, 18 * sizeof(int)); memset(s->cofDC[uv + 1][1], 0, 18 * sizeof(int));
+    h->mb.cbp_blk = 0;
+    cr_cbp[k] = residual_transform_quant_chroma_4x4(&h->mb, uv, 0);
+    for (n = 0; n < 5; n++) { dc_level[k * 5 + n] = s->cofDC[uv + 1][0][n]; dc_run[k * 5 + n] = s->cofDC[uv + 1][1][n]; }
+    for (n = 0; n < 4 && dc_level[k * 5 + n] != 0; n++) ;
+    for (; n < 5; n++) { dc_level[k * 5 + n] = 0; dc_run[k * 5 + n] = 0; }
+    for (b = 0; b < 4; b++) {                      /* cofAC[4 + uv][b4]: b4 = 2 * (y / 4) + (x / 4) in 4:2:0 (hor_offset / ver_offset) */
+      int *L = ac_level + (k * 4 + b) * 16, *R = ac_run + (k * 4 + b) * 16;
+      for (n = 0; n < 16; n++) { L[n] = s->cofAC[4 + uv][b][0][n]; R[n] = s->cofAC[4 + uv][b][1][n]; }
+      for (n = 0; n < 15 && L[n] != 0; n++) ;
+      for (; n < 16; n++) { L[n] = 0; R[n] = 0; }
+    }
+    for (j = 0; j < 8; j++)
+      for (i = 0; i < 8; i++) recon[k * 64 + j * 8 + i] = (unsigned char)h->enc->imgUV[uv][j][i];
+  }
+}
+/* LevelQuantParams of a chroma plane (plane = uv + 1): out[3][16] = ScaleComp, OffsetComp, InvScaleComp */
+void jmq_params_chroma(void *hh, int plane, int qp, int intra, int *out)
+{
+  JMQ *h = (JMQ *)hh; int i, j;
+  LevelQuantParams **q = h->p_Vid->p_Quant->q_params_4x4[plane][intra][qp];
+  for (j = 0; j < 4; j++)
+    for (i = 0; i < 4; i++) { out[j * 4 + i] = q[j][i].ScaleComp; out[16 + j * 4 + i] = q[j][i].OffsetComp; out[32 + j * 4 + i] = q[j][i].InvScaleComp; }
+}

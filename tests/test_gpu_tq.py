@@ -65,3 +65,17 @@ def test_intra16x16_matches_oracle(qp, cavlc, field, seed):
     got, exp = api.tq16x16(p, orig, pred), oracle.tq16x16(q, orig, pred)
     for a, b, name in zip(got, exp, ("dc_level", "dc_run", "ac_level", "ac_run", "recon", "ac_coef")):
         assert (a == b).all(), (name, int((a != b).sum()))
+
+
+@pytest.mark.parametrize("qp,cavlc,field,intra,seed", [(0, 1, 0, 1, 1), (14, 1, 1, 0, 2), (26, 0, 0, 1, 3), (33, 1, 0, 0, 4), (39, 1, 1, 1, 5)])
+def test_chroma_matches_oracle(qp, cavlc, field, intra, seed):
+    """b2tq_chroma (k_tq_chroma: hadamard2x2 through shuffles, DC / AC quantisers, the chroma coefficient-cost rule) vs the restated
+    oracle, itself pinned to the unmodified residual_transform_quant_chroma_4x4 (tests/test_oracle_tq.py)"""
+    from oracle.gen_golden_tqc import chroma_blocks
+    orig, pred = chroma_blocks(2003, seed)
+    p = api.tq_default_params(4, qp, intra, cavlc=cavlc, field_scan=field)
+    q = oracle.tq_params(api.tq_params_table(p, 4), qp, mode=0, cavlc=cavlc, field_scan=field)
+    got, exp = api.tq_chroma(p, orig, pred), oracle.tq_chroma(q, orig, pred)
+    for a, b, name in zip(got, exp, ("dc_level", "dc_run", "ac_level", "ac_run", "recon", "cr_cbp")):
+        assert (a == b).all(), (name, int((a != b).sum()))
+    assert set(got[5].tolist()) == {0, 1, 2} or qp == 0

@@ -68,3 +68,39 @@ def test_restated_intra16x16_matches_reference_golden(golden_dir):
         for a, name in zip(got, ("dc_level", "dc_run", "ac_level", "ac_run", "recon", "ac_coef")):
             assert (a == g[f"c{ci}_{name}"]).all(), (qp, sm, name)
         assert (api.tq_params_table(api.tq_default_params(4, qp, 2), 4) == g[f"c{ci}_params"]).all()   # the product's default intra table
+
+
+def _chroma_cmp(got, exp, tag):
+    dl, dr, al, ar, rec, cbp = got
+    for a, b, name in zip(got, exp, ("dc_level", "dc_run", "ac_level", "ac_run", "recon", "cr_cbp")):
+        if name == "ac_run":            # the reference leaves the runs of dropped AC levels behind: compare where a level stands
+            assert (a[al != 0] == b[al != 0]).all(), (tag, name)
+        elif name == "dc_run":
+            assert (a[dl != 0] == b[dl != 0]).all(), (tag, name)
+        else:
+            assert (a == b).all(), (tag, name, int((a != b).sum()))
+
+
+def test_restated_chroma_matches_reference_golden(golden_dir):
+    """residual_transform_quant_chroma_4x4 (hadamard2x2, quant_dc2x2_normal, quant_ac4x4_normal, the chroma coefficient-cost rule)
+    restated vs the unmodified JM objects (tests/golden/jm_tqc.npz, oracle/gen_golden_tqc.py)"""
+    from oracle.gen_golden_tqc import CASES, NMB, chroma_blocks
+    g = np.load(os.path.join(golden_dir, "jm_tqc.npz"))
+    seen = set()
+    for ci, (qp, sm, intra, uv, seed) in enumerate(CASES):
+        orig, pred = chroma_blocks(NMB, seed)
+        p = oracle.tq_params(g[f"c{ci}_params"], qp, mode=0, cavlc=int(sm == 0))
+        got = oracle.tq_chroma(p, orig, pred)
+        _chroma_cmp(got, [g[f"c{ci}_{n}"] for n in ("dc_level", "dc_run", "ac_level", "ac_run", "recon", "cr_cbp")], (qp, sm, intra, uv))
+        seen |= set(got[5].tolist())
+    assert seen == {0, 1, 2}
+
+
+@pytest.mark.skipif(not oracle.have_jmref(), reason="oracle/_ref/libjmref.so not built")
+def test_restated_chroma_matches_reference_live():
+    from oracle.gen_golden_tqc import chroma_blocks
+    for qp, sm, intra, uv, seed in ((5, 0, 0, 0, 71), (20, 1, 1, 1, 72), (30, 0, 0, 1, 73), (38, 0, 1, 0, 74)):
+        r = oracle.JMQuantRef(2 if intra else 0, sm)
+        orig, pred = chroma_blocks(250, seed)
+        p = oracle.tq_params(r.params_chroma(uv + 1, qp, intra), qp, cavlc=int(sm == 0))
+        _chroma_cmp(oracle.tq_chroma(p, orig, pred), r.tq_chroma(qp, intra, uv, orig, pred), (qp, sm, intra, uv))
