@@ -23,7 +23,7 @@
 #include "quant_params.h"
 #include "b2me.h"
 
-static long g_tq_calls;
+static long g_tq_calls, g_tq8_calls, g_tq16_calls, g_tqc_calls;
 static int g_tq_dev = -1;
 
 static void b2tq_fail(const char *what)
@@ -34,7 +34,7 @@ static void b2tq_fail(const char *what)
 }
 static void b2tq_report(void)
 {
-  if (getenv("B2ME_SHIM_VERBOSE")) fprintf(stderr, "b2tq shim: %ld transform/quant calls\n", g_tq_calls);
+  if (getenv("B2ME_SHIM_VERBOSE")) fprintf(stderr, "b2tq shim: %ld transform/quant calls, %ld 8x8, %ld Intra16x16, %ld chroma\n", g_tq_calls, g_tq8_calls, g_tq16_calls, g_tqc_calls);
 }
 
 int residual_transform_quant_luma_4x4(Macroblock *currMB, ColorPlane pl, int block_x, int block_y, int *coeff_cost, int intra)
@@ -87,4 +87,118 @@ int residual_transform_quant_luma_4x4(Macroblock *currMB, ColorPlane pl, int blo
   for (j = 0; j < 4; j++)
     for (i = 0; i < 4; i++) img_enc[currMB->pix_y + block_y + j][currMB->pix_x + block_x + i] = recon[4 * j + i];
   return nz;
+}
+
+/* ---- the other residual paths of a 4:2:0 macroblock, same scheme (weak definition in the reference's object, strong one here):
+ *   residual_transform_quant_luma_8x8    JM/lencod/src/transform8x8.c:522-578 (CABAC's 64-coefficient list)  -> b2tq_8x8
+ *   residual_transform_quant_luma_16x16  JM/lencod/src/block.c:207-345 (Intra16x16: DC Hadamard)            -> b2tq_16x16
+ *   residual_transform_quant_chroma_4x4  JM/lencod/src/block.c:953-1200 (2x2 DC Hadamard, cost rule)        -> b2tq_chroma ---- */
+#include "transform8x8.h"
+#include "quant8x8.h"
+#include "quantChroma.h"
+static void b2tq_common(Macroblock *currMB)
+{
+  Slice *currSlice = currMB->p_Slice; VideoParameters *p_Vid = currSlice->p_Vid;
+  if (g_tq_dev < 0) { const char *e = getenv("B2ME_DEVICE"); g_tq_dev = e ? atoi(e) : 0; atexit(b2tq_report); }
+  if (p_Vid->yuv_format != YUV420) b2tq_fail("only 4:2:0 is supported");
+  if (p_Vid->bitdepth_luma != 8 || p_Vid->bitdepth_chroma != 8) b2tq_fail("only 8-bit samples are supported");
+  if (p_Vid->AdaptiveRounding) b2tq_fail("AdaptiveRounding is not supported");
+  if (currSlice->slice_type == SP_SLICE || currSlice->slice_type == SI_SLICE) b2tq_fail("SP / SI slices are not supported");
+}
+static void b2tq_fill(b2tq_params *P, Macroblock *currMB, int qp, LevelQuantParams **q, int n)
+{
+  Slice *currSlice = currMB->p_Slice; int i, j;
+  memset(P, 0, sizeof(*P));
+  P->qp = qp; P->mode = 0; P->cavlc = currSlice->symbol_mode == CAVLC; P->field_scan = currMB->is_field_mode ? 1 : 0; P->disthres = currSlice->disthres;
+  for (j = 0; j < n; j++)
+    for (i = 0; i < n; i++) { P->scale[n * j + i] = q[j][i].ScaleComp; P->offset[n * j + i] = q[j][i].OffsetComp; P->invscale[n * j + i] = q[j][i].InvScaleComp; }
+}
+
+int residual_transform_quant_luma_8x8(Macroblock *currMB, ColorPlane pl, int b8, int *coeff_cost, int intra)
+{
+  Slice *currSlice = currMB->p_Slice; VideoParameters *p_Vid = currSlice->p_Vid;
+  const int block_x = 8 * (b8 & 1), block_y = 8 * (b8 >> 1), qp = currMB->qp_scaled[pl];
+  imgpel **img_enc = p_Vid->enc_picture->p_curr_img, **mb_pred = currSlice->mb_pred[pl];
+  int **mb_ores = currSlice->mb_ores[pl];
+  int *ACLevel = currSlice->cofAC[b8][0][0], *ACRun = currSlice->cofAC[b8][0][1];
+  b2tq_params P; uint8_t orig[64], pred[64], recon[64], run[64], nz = 0; int16_t level[64]; int32_t cost = 0; int i, j, any = 0;
+  b2tq_common(currMB);
+  if (pl != PLANE_Y) b2tq_fail("only the luma plane is supported");
+  if (currSlice->quant_8x8 != quant_8x8_normal) b2tq_fail("only quant_8x8_normal (no RDOQ, no adaptive rounding) is supported");
+  for (j = 0; j < 8; j++)
+    for (i = 0; i < 8; i++) {
+      const int p = mb_pred[block_y + j][block_x + i], r = mb_ores[block_y + j][block_x + i];
+      pred[8 * j + i] = (uint8_t)p; orig[8 * j + i] = (uint8_t)(p + r); any |= r;
+    }
+  b2tq_fill(&P, currMB, qp, p_Vid->p_Quant->q_params_8x8[pl][intra][qp], 8);
+  if (b2tq_8x8(g_tq_dev, &P, 1, orig, pred, level, run, recon, &cost, &nz) != B2ME_OK) b2tq_fail("b2tq_8x8 failed");
+  g_tq8_calls++;
+  if (any) {
+    for (i = 0; i < 64 && level[i] != 0; i++) { ACLevel[i] = level[i]; ACRun[i] = run[i]; }
+    ACLevel[i] = 0;
+    *coeff_cost += cost;
+  } else ACLevel[0] = 0;
+  for (j = 0; j < 8; j++)
+    for (i = 0; i < 8; i++) img_enc[currMB->pix_y + block_y + j][currMB->pix_x + block_x + i] = recon[8 * j + i];
+  return nz;
+}
+
+int residual_transform_quant_luma_16x16(Macroblock *currMB, ColorPlane pl)
+{
+  Slice *currSlice = currMB->p_Slice; VideoParameters *p_Vid = currSlice->p_Vid;
+  const int qp = currMB->qp_scaled[pl];
+  imgpel **img_enc = p_Vid->enc_picture->p_curr_img, **predm = currSlice->mpr_16x16[pl][currMB->i16mode];
+  int *DCLevel = currSlice->cofDC[pl][0], *DCRun = currSlice->cofDC[pl][1];
+  b2tq_params P; uint8_t orig[256], pred[256], recon[256], dr[16], ar[256], ac = 0; int16_t dl[16], al[256]; int i, j, b, n;
+  b2tq_common(currMB);
+  if (pl != PLANE_Y) b2tq_fail("only the luma plane is supported");
+  if (currSlice->quant_dc4x4 != quant_dc4x4_normal || currSlice->quant_ac4x4 != quant_ac4x4_normal) b2tq_fail("only the normal DC / AC quantisers are supported");
+  for (j = 0; j < 16; j++)
+    for (i = 0; i < 16; i++) { orig[16 * j + i] = (uint8_t)p_Vid->pCurImg[currMB->opix_y + j][currMB->pix_x + i]; pred[16 * j + i] = (uint8_t)predm[j][i]; }
+  b2tq_fill(&P, currMB, qp, p_Vid->p_Quant->q_params_4x4[pl][1][qp], 4);
+  if (b2tq_16x16(g_tq_dev, &P, 1, orig, pred, dl, dr, al, ar, recon, &ac) != B2ME_OK) b2tq_fail("b2tq_16x16 failed");
+  g_tq16_calls++;
+  for (n = 0; n < 16 && dl[n] != 0; n++) { DCLevel[n] = dl[n]; DCRun[n] = dr[n]; }
+  DCLevel[n] = 0;
+  for (b = 0; b < 16; b++) {
+    const int jj = b >> 2, ii = b & 3, b8 = 2 * (jj >> 1) + (ii >> 1), b4 = 2 * (jj & 1) + (ii & 1);
+    int *L = currSlice->cofAC[b8][b4][0], *R = currSlice->cofAC[b8][b4][1];
+    for (n = 0; n < 15 && al[b * 16 + n] != 0; n++) { L[n] = al[b * 16 + n]; R[n] = ar[b * 16 + n]; }
+    L[n] = 0;
+  }
+  currMB->subblock_y = 12; currMB->subblock_x = 12;              /* what the reference's block loop leaves */
+  for (j = 0; j < 16; j++)
+    for (i = 0; i < 16; i++) img_enc[currMB->pix_y + j][currMB->pix_x + i] = recon[16 * j + i];
+  return ac;
+}
+
+int residual_transform_quant_chroma_4x4(Macroblock *currMB, int uv, int cr_cbp)
+{
+  Slice *currSlice = currMB->p_Slice; VideoParameters *p_Vid = currSlice->p_Vid;
+  const int intra = is_intra(currMB), qp = currMB->qpc[uv] + currSlice->bitdepth_chroma_qp_scale;
+  imgpel **mb_pred = currSlice->mb_pred[uv + 1];
+  int **mb_ores = currSlice->mb_ores[uv + 1];
+  int *DCLevel = currSlice->cofDC[uv + 1][0], *DCRun = currSlice->cofDC[uv + 1][1];
+  b2tq_params P; uint8_t orig[64], pred[64], recon[64], dr[4], ar[64], cbp = 0; int16_t dl[4], al[64]; int i, j, b, n, anyac = 0;
+  b2tq_common(currMB);
+  if (currSlice->quant_dc_cr != quant_dc2x2_normal || currSlice->quant_ac4x4cr != quant_ac4x4_normal) b2tq_fail("only the normal chroma quantisers are supported");
+  for (j = 0; j < 8; j++)
+    for (i = 0; i < 8; i++) { const int p = mb_pred[j][i]; pred[8 * j + i] = (uint8_t)p; orig[8 * j + i] = (uint8_t)(p + mb_ores[j][i]); }
+  b2tq_fill(&P, currMB, qp, p_Vid->p_Quant->q_params_4x4[uv + 1][intra][qp], 4);
+  if (b2tq_chroma(g_tq_dev, &P, 1, orig, pred, dl, dr, al, ar, recon, &cbp) != B2ME_OK) b2tq_fail("b2tq_chroma failed");
+  g_tqc_calls++;
+  p_Vid->is_v_block = uv;
+  for (n = 0; n < 4 && dl[n] != 0; n++) { DCLevel[n] = dl[n]; DCRun[n] = dr[n]; }
+  DCLevel[n] = 0;
+  if (n) currMB->cbp_blk |= (int64)0xf0000 << (uv << 2);         /* a DC level: the coded bits of all four blocks (block.c:1064-1068) */
+  for (b = 0; b < 4; b++) {                                      /* cofAC[4 + uv][b4], b4 = 2 * (y / 4) + (x / 4) in 4:2:0 */
+    int *L = currSlice->cofAC[4 + uv][b][0], *R = currSlice->cofAC[4 + uv][b][1];
+    for (i = 0; i < 15 && al[b * 16 + i] != 0; i++) { L[i] = al[b * 16 + i]; R[i] = ar[b * 16 + i]; }
+    L[i] = 0;
+    if (i) { anyac = 1; currMB->cbp_blk |= (int64)1 << (16 + 4 * uv + b); }
+  }
+  (void)anyac;
+  for (j = 0; j < 8; j++)
+    for (i = 0; i < 8; i++) p_Vid->enc_picture->imgUV[uv][currMB->pix_c_y + j][currMB->pix_c_x + i] = recon[8 * j + i];
+  return cbp == 2 ? 2 : (cbp == 1 ? imax(1, cr_cbp) : cr_cbp);
 }

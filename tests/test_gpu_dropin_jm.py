@@ -154,6 +154,32 @@ def test_lencod_with_cuda_transform_quant_is_bit_identical(qp):
         assert m and int(m.group(1)) > 10000, b[2][-400:]
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not (have and os.path.exists(os.path.join(REF, "lencod_b2q"))), reason="oracle/_ref/lencod_b2q not built")
+@pytest.mark.parametrize("extra,what", [
+    (("SymbolMode=1", "Transform8x8Mode=1"), "8x8"),               # CABAC: residual_transform_quant_luma_8x8's 64-coefficient list
+    ((), "chroma"),                                                 # CAVLC, 4x4 transform: luma 4x4, Intra16x16 and chroma paths
+])
+def test_lencod_with_every_residual_path_on_the_gpu_is_bit_identical(extra, what):
+    """lencod_b2q: residual_transform_quant_luma_4x4 / _8x8 / _16x16 and residual_transform_quant_chroma_4x4 (block.c:660, 207, 953;
+    transform8x8.c:522) served by b2tq_4x4 / b2tq_8x8 / b2tq_16x16 / b2tq_chroma under the stock motion search and mode decision."""
+    W, H, frames = 176, 144, 2
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(synth.yuv420_sequence(W, H, frames, seed=17))
+        a = _encode("lencod", yuv, W, H, frames, os.path.join(d, "stock"), nrefs=1, search_range=8, qp=30, search_mode=3, extra=extra)
+        b = _encode("lencod_b2q", yuv, W, H, frames, os.path.join(d, "b2"), nrefs=1, search_range=8, qp=30, search_mode=3, extra=extra,
+                    env={"B2ME_SHIM_VERBOSE": "1"})
+        assert len(a[0]) > 500
+        assert a[0] == b[0], "bitstreams differ"
+        assert a[1] == b[1], "reconstructions differ"
+        import re
+        m = re.search(r"(\d+) transform/quant calls, (\d+) 8x8, (\d+) Intra16x16, (\d+) chroma", b[2])
+        assert m, b[2][-400:]
+        n4, n8, n16, nc = (int(x) for x in m.groups())
+        assert n16 > 100 and nc > 1000 and (n8 > 1000 if what == "8x8" else n4 > 10000), m.group(0)
+
+
 @pytest.mark.skipif(not have, reason="oracle/_ref/lencod_b2 not built")
 def test_dropin_fails_loudly_without_a_gpu():
     """No CPU fallback behind the boundary: without a CUDA device the shim stops the encoder."""
