@@ -210,6 +210,33 @@ __global__ void __launch_bounds__(128) k_bipred(const BiArgs a)
   if (tid == 0) { O->mv_sub[0] = (int16_t)mv1[0]; O->mv_sub[1] = (int16_t)mv1[1]; O->cost_sub = bound; }
 }
 
+// ---- bi-predictive distortion at explicit candidate pairs: computeBiPredSAD1 / SAD2, SSE1 / SSE2, SATD1 / SATD2
+//      (me_distortion.c:525-737, 943-1182, 1353-1549) at their own boundary (mv_block->computeBiPred1[] / computeBiPred2[]):
+//      the record is b2me_bipred_job (position, block type, two slots, mv1 = candidate of list A, mv2 = candidate of list B,
+//      weights); out = distortion << 5.  One warp per record, the serial distortion routine of k_bipred by lane 0. ----
+__global__ void __launch_bounds__(32) k_bicand(const BiArgs a, int metric, long long *out)
+{
+  __shared__ uint8_t cur[256];
+  const int tid = threadIdx.x;
+  const b2me_bipred_job J = a.jobs[blockIdx.x];
+  const int bt = J.blocktype;
+  const bool bad = bt < 1 || bt > 7 || J.ref1 < 0 || J.ref1 >= a.nrefs || J.ref2 < 0 || J.ref2 >= a.nrefs || J.pos_x < 0 || J.pos_y < 0 ||
+                   J.pos_x + part_geom(part_first(bt < 1 || bt > 7 ? 7 : bt)).w > a.W || J.pos_y + part_geom(part_first(bt < 1 || bt > 7 ? 7 : bt)).h > a.H;
+  if (bad) { if (tid == 0) { *a.errflag = 1; out[blockIdx.x] = -1; } return; }
+  const PartGeom gm = part_geom(part_first(bt));
+  for (int i = tid; i < 256; i += 32) {
+    const int x = i & 15, y = i >> 4;
+    cur[i] = (x < gm.w && y < gm.h) ? a.cur[(size_t)(J.pos_y + y) * a.cur_pitch + J.pos_x + x] : 0;
+  }
+  __syncwarp();
+  if (tid == 0) {
+    BiWp w; w.wp = a.wp; w.w1 = J.weight1; w.w2 = J.weight2; w.off = J.offset_bi; w.shift = a.denom + 1;
+    w.lround = 2 * (a.denom ? 1 << (a.denom - 1) : 0);
+    const int ox = J.pos_x << 2, oy = J.pos_y << 2;
+    out[blockIdx.x] = (long long)bi_dist(a, cur, gm.w, gm.h, J.ref1, J.ref2, ox + J.mv1[0], oy + J.mv1[1], ox + J.mv2[0], oy + J.mv2[1], metric, w) << 5;
+  }
+}
+
 // ---- distortion of a list of (block, reference, candidate) triples ---------------------------------------------
 // computeSAD / computeSSE / computeSATD (me_distortion.c:349-426, 1190-1255, 745-825) at their own boundary
 // (mv_block->computePredFPel / HPel / QPel): what a search whose control flow stays on the host (EPZS, UMHex) asks
@@ -623,6 +650,43 @@ extern "C" int b2me_epzs_search(b2me_ctx *c, int njobs, const b2me_epzs_job *job
     }
   }
   cudaFreeAsync(d, c->stream);
+  return r;
+}
+
+extern "C" int b2me_bipred_distortion_candidates(b2me_ctx *c, int metric, int test8x8, int apply_weights, int luma_log_weight_denom, int n,
+                                                 const b2me_bipred_job *cands, int64_t *out)
+{
+  if (!c || n < 0 || (n && (!cands || !out)) || metric < 0 || metric > 2 || luma_log_weight_denom < 0 || luma_log_weight_denom > 7) return B2ME_EINVAL;
+  if (apply_weights && test8x8 && metric == 2) {
+    snprintf(c->err, sizeof(c->err), "weighted bi-predictive SATD with the 8x8 Hadamard is not implemented (the reference's computeBiPredSATD2 8x8 branch "
+                                     "reads past its source row, me_distortion.c:1167)");
+    return B2ME_EUNSUPPORTED;
+  }
+  if (!n) return B2ME_OK;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  b2me_bipred_job *dj = nullptr; long long *dout = nullptr;
+  B2_CUDA_CHECK(c, cudaMallocAsync(&dj, sizeof(b2me_bipred_job) * n, c->stream));
+  B2_CUDA_CHECK(c, cudaMallocAsync(&dout, sizeof(long long) * n, c->stream));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(dj, cands, sizeof(b2me_bipred_job) * n, cudaMemcpyHostToDevice, c->stream));
+  BiArgs a;
+  memset(&a, 0, sizeof(a));
+  a.cur = c->d_cur; a.cur_pitch = c->W; a.planes = c->d_planes; a.plane_size = c->plane_size;
+  a.W = c->W; a.H = c->H; a.Wp = c->Wp; a.nrefs = c->nrefs; a.R = c->R; a.test8x8 = test8x8; a.wp = apply_weights; a.denom = luma_log_weight_denom;
+  a.jobs = dj; a.njobs = n; a.errflag = c->d_errflag;
+  k_bicand<<<n, 32, 0, c->stream>>>(a, metric, dout);
+  int r = B2ME_OK, flag = 0;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, sizeof(long long) * n, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "b2me_bipred_distortion_candidates: %s", cudaGetErrorString(e)); r = B2ME_ECUDA; }
+  else if (flag) {
+    cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream);
+    snprintf(c->err, sizeof(c->err), "b2me_bipred_distortion_candidates: a record is out of range (blocktype, reference slot or position)");
+    r = B2ME_EINVAL;
+  }
+  c->launches++;
+  cudaFreeAsync(dj, c->stream); cudaFreeAsync(dout, c->stream);
   return r;
 }
 

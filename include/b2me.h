@@ -186,6 +186,14 @@ int b2me_bipred_search(b2me_ctx *ctx, int njobs, const b2me_bipred_job *jobs, co
 int b2me_bipred_search_dev(b2me_ctx *ctx, int njobs, const b2me_bipred_job *jobs_dev, const b2me_search_params *params,
                            int apply_weights, int luma_log_weight_denom, int test8x8, b2me_bipred_result *out_dev, void *stream);
 
+/* The bi-predictive distortions at their own boundary (mv_block->computeBiPred1[] / computeBiPred2[]): computeBiPredSAD1 / SSE1 /
+ * SATD1 (unweighted average) and computeBiPredSAD2 / SSE2 / SATD2 (apply_weights: weight1, weight2, offset_bi of the record)
+ * (JM/lencod/src/me_distortion.c:525-737, 943-1182, 1353-1549) for n records: position, block type, the two reference slots,
+ * mv1 = candidate of the first picture, mv2 = candidate of the second (quarter-pel, relative); the other fields are ignored.
+ * out = distortion << 5.  metric 0 SAD, 1 SSE, 2 SATD. */
+int b2me_bipred_distortion_candidates(b2me_ctx *ctx, int metric, int test8x8, int apply_weights, int luma_log_weight_denom, int n,
+                                      const b2me_bipred_job *cands, int64_t *out);
+
 /* ---- distortion at explicit candidates (the computeSAD family at its own boundary) ---------------------------- */
 /* computeSAD / computeSSE / computeSATD (JM/lencod/src/me_distortion.c:349-426, 1190-1255, 745-825; the WP variants
  * when the slot was uploaded with b2me_set_ref_weights) for n independent (block, reference slot, vector) triples:

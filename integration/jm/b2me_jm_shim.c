@@ -37,6 +37,7 @@ typedef struct {
   StorablePicture *pic;
   int poc;
   unsigned sig;          /* samples of the picture: JM re-uses StorablePicture addresses, and POC restarts at every IDR */
+  int wp, weight, offset, denom;   /* planes stored weighted (UseWeightedReferenceME: computeSADWP & co read weighted samples) */
   long stamp;
 } B2Slot;
 
@@ -48,7 +49,7 @@ static StorablePicture *g_cur_pic;
 static int g_cur_poc = -0x7fffffff;
 static unsigned g_cur_sig;
 static unsigned char *g_stage;
-static long g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_uploads, g_calls_epzs, g_points_epzs;
+static long g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_uploads, g_calls_epzs, g_points_epzs, g_calls_bidist, g_calls_blk;
 static int g_in_bipred;
 
 static void b2_fail(const char *what)
@@ -61,8 +62,8 @@ static void b2_fail(const char *what)
 static void b2_report(void)
 {
   if (getenv("B2ME_SHIM_VERBOSE"))
-    fprintf(stderr, "b2me shim: %ld integer searches, %ld sub-pel refinements, %ld bi-predictive calls, %ld distortion calls, %ld EPZS searches (%ld search points), %ld picture uploads, %lld kernel launches\n",
-            g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_calls_epzs, g_points_epzs, g_uploads, g_ctx ? (long long)b2me_launch_count(g_ctx) : 0LL);
+    fprintf(stderr, "b2me shim: %ld integer searches, %ld sub-pel refinements, %ld bi-predictive calls, %ld distortion calls, %ld bi-predictive distortion calls, %ld block distortions, %ld EPZS searches (%ld search points), %ld picture uploads, %lld kernel launches\n",
+            g_calls_int, g_calls_sub, g_calls_bi, g_calls_dist, g_calls_bidist, g_calls_blk, g_calls_epzs, g_points_epzs, g_uploads, g_ctx ? (long long)b2me_launch_count(g_ctx) : 0LL);
   if (g_ctx) b2me_destroy(g_ctx);
   g_ctx = NULL;
 }
@@ -76,7 +77,6 @@ static void b2_check_config(Macroblock *currMB, MEBlock *mv_block)
   if (currSlice->structure != FRAME || currMB->list_offset != 0) b2_fail("field / MBAFF pictures are not supported");
   if (mv_block->list != 0 && mv_block->list != 1) b2_fail("only list 0 / list 1 frame references are supported");
   if (p_Inp->ChromaMEEnable || mv_block->ChromaMEEnable) b2_fail("ChromaMEEnable is not supported");
-  if (mv_block->apply_weights && !g_in_bipred) b2_fail("weighted-prediction ME of the single-list search is not supported by the shim");
   if (!p_Inp->rdopt) b2_fail("RDOptimization=0 ((0,0)-bias path) is not supported");
   if (p_Inp->MEErrorMetric[F_PEL] != ERROR_SAD) b2_fail("MEDistortionFPel must be SAD");
   if (p_Inp->OnTheFlyFractMCP) b2_fail("OnTheFlyFractMCP must be 0");
@@ -100,7 +100,7 @@ static void b2_ensure_ctx2(VideoParameters *p_Vid, InputParameters *p_Inp)
   if (g_ctx) return;
   if (e) dev = atoi(e);
   g_W = p_Vid->width; g_H = p_Vid->height;
-  g_nslots = imin(B2_MAX_SLOTS, imax(2, p_Vid->max_num_references + 1));
+  g_nslots = imin(B2_MAX_SLOTS, imax(2, 2 * (p_Vid->max_num_references + 1)));
   if (b2me_create(&g_ctx, dev, g_W, g_H, g_nslots, R) != B2ME_OK) b2_fail("b2me_create failed");
   g_stage = (unsigned char *)malloc((size_t)g_W * g_H);
   if (!g_stage) no_mem_exit("b2me shim: staging plane");
@@ -143,18 +143,29 @@ static void b2_ensure_cur(VideoParameters *p_Vid)
   /* a new coded picture: reference slots whose picture is gone are simply aged out by the LRU */
 }
 
-static int b2_ref_slot(StorablePicture *ref)
+static int b2_ref_slot_wp(StorablePicture *ref, int wp, int weight, int offset, int denom)
 {
   int i, victim = 0;
   const unsigned sig = b2_signature(ref->imgY);
+  if (!wp) weight = offset = denom = 0;
   for (i = 0; i < g_nslots; i++)
-    if (g_slot[i].pic == ref && g_slot[i].poc == ref->poc && g_slot[i].sig == sig && g_slot[i].stamp) { g_slot[i].stamp = ++g_clock; return i; }
+    if (g_slot[i].pic == ref && g_slot[i].poc == ref->poc && g_slot[i].sig == sig && g_slot[i].stamp && g_slot[i].wp == wp &&
+        g_slot[i].weight == weight && g_slot[i].offset == offset && g_slot[i].denom == denom) { g_slot[i].stamp = ++g_clock; return i; }
   for (i = 1; i < g_nslots; i++)
     if (g_slot[i].stamp < g_slot[victim].stamp) victim = i;
   b2_narrow(ref->imgY);                 /* reconstructed (deblocked) luma; the GPU rebuilds getSubImagesLuma's planes */
+  if (b2me_set_ref_weights(g_ctx, victim, wp, weight, offset, denom) != B2ME_OK) b2_fail("b2me_set_ref_weights failed");
   if (b2me_set_ref(g_ctx, victim, g_stage, g_W) != B2ME_OK) b2_fail("b2me_set_ref failed");
   g_slot[victim].pic = ref; g_slot[victim].poc = ref->poc; g_slot[victim].sig = sig; g_slot[victim].stamp = ++g_clock; g_uploads++;
+  g_slot[victim].wp = wp; g_slot[victim].weight = weight; g_slot[victim].offset = offset; g_slot[victim].denom = denom;
   return victim;
+}
+static int b2_ref_slot(StorablePicture *ref) { return b2_ref_slot_wp(ref, 0, 0, 0, 0); }
+/* the slot of a single-list search / distortion: weighted planes when the block asks for them (PrepareMEParams, mv_search.c:183-188) */
+static int b2_ref_slot_for(Macroblock *currMB, MEBlock *mv_block, StorablePicture *ref)
+{
+  if (!mv_block->apply_weights) return b2_ref_slot(ref);
+  return b2_ref_slot_wp(ref, 1, mv_block->weight_luma, mv_block->offset_luma, currMB->p_Slice->luma_log_weight_denom);
 }
 
 static void b2_params(InputParameters *p_Inp, b2me_search_params *P, int lam_f, int lam_h, int lam_q, distblk min_mcost)
@@ -181,7 +192,7 @@ distblk full_search_motion_estimation(Macroblock *currMB, MotionVector *pred_mv,
   b2_ensure_ctx(currMB);
   b2_check_config(currMB, mv_block);
   b2_ensure_cur(currMB->p_Vid);
-  slot = b2_ref_slot(ref_picture);
+  slot = b2_ref_slot_for(currMB, mv_block, ref_picture);
   b2_params(currMB->p_Inp, &P, lambda_factor, lambda_factor, lambda_factor, min_mcost);
   pm[0] = pred_mv->mv_x; pm[1] = pred_mv->mv_y; cm[0] = mv->mv_x; cm[1] = mv->mv_y;
   if (b2me_block_search(g_ctx, mv_block->pos_x, mv_block->pos_y, mv_block->blocktype, slot, pm, cm, &P, search_range,
@@ -208,7 +219,7 @@ distblk sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, MEBloc
   if (mv_block->search_pos2 != 9 || mv_block->search_pos4 != 9) b2_fail("SubPelSearch position counts other than 9/9 are not supported");
   b2_check_test8x8(currMB, mv_block);
   b2_ensure_cur(currMB->p_Vid);
-  slot = b2_ref_slot(ref_picture);
+  slot = b2_ref_slot_for(currMB, mv_block, ref_picture);
   b2_params(currMB->p_Inp, &P, lambda[F_PEL], lambda[H_PEL], lambda[Q_PEL], min_mcost);
   P.do_subpel = 1;
   pm[0] = pred->mv_x; pm[1] = pred->mv_y; in[0] = mv->mv_x; in[1] = mv->mv_y;
@@ -236,7 +247,7 @@ distblk full_sub_pel_motion_estimation(Macroblock *currMB, MotionVector *pred, M
   b2_check_config(currMB, mv_block);
   b2_check_test8x8(currMB, mv_block);
   b2_ensure_cur(currMB->p_Vid);
-  slot = b2_ref_slot(ref_picture);
+  slot = b2_ref_slot_for(currMB, mv_block, ref_picture);
   b2_params(currMB->p_Inp, &P, lambda[F_PEL], lambda[H_PEL], lambda[Q_PEL], min_mcost);
   P.do_subpel = 1; P.subpel_full = 1;
   pm[0] = pred->mv_x; pm[1] = pred->mv_y; in[0] = mv->mv_x; in[1] = mv->mv_y;
@@ -307,12 +318,18 @@ distblk full_sub_pel_bipred_motion_estimation(Macroblock *currMB, MEBlock *mv_bl
 }
 
 #ifdef B2ME_SHIM_DISTORTION
-/* ---- the computeSAD family at its own boundary (JM/lencod/inc/me_distortion.h:60-62): the distortion pointers
- * mv_block->computePredFPel / HPel / QPel of EVERY search mode (EPZS, UMHex, ...) then evaluate on the GPU, one candidate per
- * call -- a functional demonstration of the boundary (lencod_b2d in oracle/Makefile.jm), not a fast path: a search that wants
- * throughput hands whole predictor sets to b2me_distortion_candidates.  The early exits of the reference return a value above
- * the caller's bound; the full distortion returned here is above it too, so every comparison falls the same way. ---- */
-static distblk b2_distortion(StorablePicture *ref1, MEBlock *mv_block, MotionVector *cand, int metric)
+/* ---- every symbol of JM's me_distortion.o (JM/lencod/inc/me_distortion.h:21-91), that object left out of the link (lencod_b2d).
+ * The computeSAD family at its own boundary -- the distortion pointers mv_block->computePredFPel / HPel / QPel,
+ * computeBiPred1[] / computeBiPred2[] of EVERY search mode (EPZS, UMHex, ...) -- evaluates on the GPU, one candidate per call: a
+ * functional demonstration of the boundary, not a fast path (a search that wants throughput hands whole predictor sets to
+ * b2me_distortion_candidates or runs on the device altogether, b2me_epzs_search).  The weighted variants read planes that were
+ * uploaded weighted (b2me_set_ref_weights); the bi-predictive ones go through b2me_bipred_distortion_candidates; the
+ * mode decision's block distortions (distortion4x4 / 8x8 SAD / SSE / SATD, HadamardSAD4x4 / 8x8) through b2me_distortion_blocks.
+ * The early exits of the reference return a value above the caller's bound; the full distortion returned here is above it too,
+ * so every comparison falls the same way.  select_distortion and calcDifference are the reference's glue (function-pointer
+ * selection, a subtraction loop) and are restated here because their object is gone. ---- */
+#include "me_distortion.h"
+static distblk b2_distortion(StorablePicture *ref1, MEBlock *mv_block, MotionVector *cand, int metric, int wp)
 {
   b2me_candidate c;
   int64_t out = 0;
@@ -321,18 +338,82 @@ static distblk b2_distortion(StorablePicture *ref1, MEBlock *mv_block, MotionVec
   if (mv_block->p_Vid->bitdepth_luma != 8) b2_fail("only 8-bit luma is supported");
   b2_ensure_cur(mv_block->p_Vid);
   c.pos_x = mv_block->pos_x; c.pos_y = mv_block->pos_y; c.blocktype = mv_block->blocktype;
-  c.ref = (int16_t)b2_ref_slot(ref1);
+  c.ref = (int16_t)(wp ? b2_ref_slot_wp(ref1, 1, mv_block->weight_luma, mv_block->offset_luma, mv_block->p_Slice->luma_log_weight_denom) : b2_ref_slot(ref1));
   c.mv[0] = (int16_t)(cand->mv_x - mv_block->pos_x_padded); c.mv[1] = (int16_t)(cand->mv_y - mv_block->pos_y_padded);
   if (b2me_distortion_candidates(g_ctx, metric, mv_block->test8x8, 1, &c, &out) != B2ME_OK) b2_fail("b2me_distortion_candidates failed");
   g_calls_dist++;
   return (distblk)out;
 }
 distblk computeSAD(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
-{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 0); }
+{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 0, 0); }
 distblk computeSSE(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
-{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 1); }
+{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 1, 0); }
 distblk computeSATD(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
-{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 2); }
+{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 2, 0); }
+distblk computeSADWP(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 0, 1); }
+distblk computeSSEWP(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 1, 1); }
+distblk computeSATDWP(StorablePicture *ref1, MEBlock *mv_block, distblk min_mcost, MotionVector *cand)
+{ (void)min_mcost; return b2_distortion(ref1, mv_block, cand, 2, 1); }
+
+static distblk b2_bidistortion(StorablePicture *ref1, StorablePicture *ref2, MEBlock *mv_block, MotionVector *cand1, MotionVector *cand2, int metric, int wp)
+{
+  b2me_bipred_job J;
+  int64_t out = 0;
+  b2_ensure_ctx2(mv_block->p_Vid, mv_block->p_Vid->p_Inp);
+  if (mv_block->ChromaMEEnable) b2_fail("ChromaMEEnable is not supported");
+  b2_ensure_cur(mv_block->p_Vid);
+  memset(&J, 0, sizeof(J));
+  J.pos_x = mv_block->pos_x; J.pos_y = mv_block->pos_y; J.blocktype = mv_block->blocktype;
+  J.ref1 = (int16_t)b2_ref_slot(ref1); J.ref2 = (int16_t)b2_ref_slot(ref2);
+  if (g_slot[J.ref1].pic != ref1 || g_slot[J.ref1].wp) J.ref1 = (int16_t)b2_ref_slot(ref1);
+  if (J.ref1 == J.ref2 && ref1 != ref2) b2_fail("reference slots exhausted");
+  J.mv1[0] = (int16_t)(cand1->mv_x - mv_block->pos_x_padded); J.mv1[1] = (int16_t)(cand1->mv_y - mv_block->pos_y_padded);
+  J.mv2[0] = (int16_t)(cand2->mv_x - mv_block->pos_x_padded); J.mv2[1] = (int16_t)(cand2->mv_y - mv_block->pos_y_padded);
+  J.weight1 = mv_block->weight1; J.weight2 = mv_block->weight2; J.offset_bi = mv_block->offsetBi;
+  if (b2me_bipred_distortion_candidates(g_ctx, metric, mv_block->test8x8, wp, wp ? mv_block->p_Slice->luma_log_weight_denom : 0, 1, &J, &out) != B2ME_OK)
+    b2_fail("b2me_bipred_distortion_candidates failed");
+  g_calls_bidist++;
+  return (distblk)out;
+}
+distblk computeBiPredSAD1(StorablePicture *r1, StorablePicture *r2, MEBlock *b, distblk m, MotionVector *c1, MotionVector *c2) { (void)m; return b2_bidistortion(r1, r2, b, c1, c2, 0, 0); }
+distblk computeBiPredSAD2(StorablePicture *r1, StorablePicture *r2, MEBlock *b, distblk m, MotionVector *c1, MotionVector *c2) { (void)m; return b2_bidistortion(r1, r2, b, c1, c2, 0, 1); }
+distblk computeBiPredSSE1(StorablePicture *r1, StorablePicture *r2, MEBlock *b, distblk m, MotionVector *c1, MotionVector *c2) { (void)m; return b2_bidistortion(r1, r2, b, c1, c2, 1, 0); }
+distblk computeBiPredSSE2(StorablePicture *r1, StorablePicture *r2, MEBlock *b, distblk m, MotionVector *c1, MotionVector *c2) { (void)m; return b2_bidistortion(r1, r2, b, c1, c2, 1, 1); }
+distblk computeBiPredSATD1(StorablePicture *r1, StorablePicture *r2, MEBlock *b, distblk m, MotionVector *c1, MotionVector *c2) { (void)m; return b2_bidistortion(r1, r2, b, c1, c2, 2, 0); }
+distblk computeBiPredSATD2(StorablePicture *r1, StorablePicture *r2, MEBlock *b, distblk m, MotionVector *c1, MotionVector *c2) { (void)m; return b2_bidistortion(r1, r2, b, c1, c2, 2, 1); }
+
+/* the mode decision's distortions of one difference block (me_distortion.c:38-134) and the two Hadamards (:175-341) */
+static int64_t b2_blockdist(short *diff, int kind, int n)
+{
+  int64_t out = 0;
+  static int dev = -1;
+  if (dev < 0) { const char *e = getenv("B2ME_DEVICE"); dev = e ? atoi(e) : 0; }
+  if (b2me_distortion_blocks(dev, kind, n, 1, diff, &out) != B2ME_OK) b2_fail("b2me_distortion_blocks failed");
+  g_calls_blk++;
+  return out;
+}
+distblk distortion4x4SAD(short *diff, distblk m) { (void)m; return (distblk)b2_blockdist(diff, 0, 4); }
+distblk distortion4x4SSE(short *diff, distblk m) { (void)m; return (distblk)b2_blockdist(diff, 1, 4); }
+distblk distortion4x4SATD(short *diff, distblk m) { (void)m; return (distblk)b2_blockdist(diff, 2, 4); }
+distblk distortion8x8SAD(short *diff, distblk m) { (void)m; return (distblk)b2_blockdist(diff, 0, 8); }
+distblk distortion8x8SADthres(short *diff, distblk m) { (void)m; return (distblk)b2_blockdist(diff, 0, 8); }
+distblk distortion8x8SSE(short *diff, distblk m) { (void)m; return (distblk)b2_blockdist(diff, 1, 8); }
+distblk distortion8x8SATD(short *diff, distblk m) { (void)m; return (distblk)b2_blockdist(diff, 2, 8); }
+int HadamardSAD4x4(short *diff) { return (int)(b2_blockdist(diff, 2, 4) >> 5); }      /* dist_scale = << 5 */
+int HadamardSAD8x8(short *diff) { return (int)(b2_blockdist(diff, 2, 8) >> 5); }
+void select_distortion(VideoParameters *p_Vid, InputParameters *p_Inp)
+{
+  const int m = p_Inp->ModeDecisionMetric;
+  p_Vid->distortion4x4 = m == ERROR_SAD ? distortion4x4SAD : (m == ERROR_SSE ? distortion4x4SSE : distortion4x4SATD);
+  p_Vid->distortion8x8 = m == ERROR_SAD ? distortion8x8SAD : (m == ERROR_SSE ? distortion8x8SSE : distortion8x8SATD);
+}
+void calcDifference(imgpel **origImg, int ox, int oy, imgpel **predImg, int px, int py, int width, int height, short *diff)
+{
+  int i, j;
+  for (j = 0; j < height; j++) for (i = 0; i < width; i++) *diff++ = (short)(origImg[oy + j][ox + i] - predImg[py + j][px + i]);
+}
 #endif
 
 #ifdef B2ME_SHIM_FULLFAST

@@ -106,6 +106,45 @@ def test_epzs_with_every_distortion_on_the_gpu_is_bit_identical():
         assert m and int(m.group(1)) > 10000, b[2][-400:]
 
 
+def _fading_clip(W, H, frames, seed):
+    """a clip whose luma fades from frame to frame, so that explicit weighted prediction finds weights other than the default"""
+    import numpy as np
+    raw = np.frombuffer(synth.yuv420_sequence(W, H, frames, seed=seed), np.uint8).reshape(frames, W * H * 3 // 2).copy()
+    for i in range(frames):
+        y = raw[i, :W * H].astype(np.float64)
+        raw[i, :W * H] = np.clip(y * (1.0 - 0.09 * i) + 3 * i, 0, 255).astype(np.uint8)
+    return raw.tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (have and os.path.exists(os.path.join(REF, "lencod_b2d"))), reason="oracle/_ref/lencod_b2d not built")
+@pytest.mark.parametrize("exe,mode,extra,counter", [
+    # B slices under EPZS with its own bi-predictive search: computeBiPredSAD1 / SATD1 per candidate pair, the block distortions of BIDPartitionCost
+    ("lencod_b2d", 3, ("EPZSSubPelME=1", "EPZSSubPelMEBiPred=1", "EPZSSubPelGrid=0", "NumberBFrames=1", "BiPredMotionEstimation=1", "HierarchicalCoding=0",
+                       "BReferencePictures=0", "QPBSlice=30", "BList1References=1", "BiPredMESearchRange=8", "BiPredMERefinements=1"), r"(\d+) bi-predictive distortion calls"),
+    # explicit weighted prediction on a fading clip, weighted reference ME: computeSADWP / SATDWP through weighted planes (EPZS)
+    ("lencod_b2d", 3, ("EPZSSubPelME=1", "EPZSSubPelGrid=0", "WeightedPrediction=1", "UseWeightedReferenceME=1"), r"(\d+) distortion calls"),
+    # the same configuration under the full search: full_search / sub_pel of me_fullsearch.o on weighted planes
+    ("lencod_b2", -1, ("WeightedPrediction=1", "UseWeightedReferenceME=1"), r"(\d+) integer searches"),
+])
+def test_weighted_and_bipredictive_distortions_on_the_gpu_are_bit_identical(exe, mode, extra, counter):
+    """The rest of me_distortion.o in the drop-in (lencod_b2d: that object is out of the link, all 22 symbols come from the shim) and
+    weighted single-list motion estimation of the full search (b2me_set_ref_weights)."""
+    W, H, frames = 176, 144, 4
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        open(yuv, "wb").write(_fading_clip(W, H, frames, 23))
+        a = _encode("lencod", yuv, W, H, frames, os.path.join(d, "stock"), nrefs=2, search_range=8, qp=30, search_mode=mode, extra=extra)
+        b = _encode(exe, yuv, W, H, frames, os.path.join(d, "b2"), nrefs=2, search_range=8, qp=30, search_mode=mode, extra=extra,
+                    env={"B2ME_SHIM_VERBOSE": "1"})
+        assert len(a[0]) > 1000
+        assert a[0] == b[0], "bitstreams differ"
+        assert a[1] == b[1], "reconstructions differ"
+        import re
+        m = re.search(counter, b[2])
+        assert m and int(m.group(1)) > 500, b[2][-500:]
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not (have and os.path.exists(os.path.join(REF, "lencod_b2e"))), reason="oracle/_ref/lencod_b2e not built")
 @pytest.mark.parametrize("frames,nrefs,sr,extra", [
