@@ -250,6 +250,73 @@ def fractal_leg(device, with_cpu):
     return res
 
 
+def recon_leg(device, steps=10):
+    """The reconstruction side of a 1080p 4:2:0 picture on the device (secondary line): prediction of every macroblock from
+    two lists (k_mc_mb), residual transform + quantisation of all luma 4x4 blocks and of both chroma planes (k_tq4x4, k_tq_chroma),
+    the in-loop deblocking filter (k_deblock, 2:1 macroblock wavefront).  Device-resident synthetic inputs; CUDA events."""
+    import torch
+    from h264_b200 import api, synth
+    dev = torch.device("cuda", device)
+    Wr, Hr, NRr = 1920, 1088, 2
+    rng = np.random.default_rng(21)
+    fr = synth.luma_sequence(Wr, Hr, NRr + 1, seed=5)
+    s = api.Searcher(Wr, Hr, NRr, 16)
+    s.set_cur(fr[NRr])
+    cu = rng.integers(90, 160, (Hr // 2, Wr // 2)).astype(np.uint8)
+    s.set_cur_chroma(cu, cu)
+    for r in range(NRr):
+        s.set_ref(r, fr[NRr - 1 - r]); s.set_ref_chroma(r, np.roll(cu, r + 1, axis=1), np.roll(cu, r + 1, axis=0))
+    nmb = s.nmb
+    t = lambda a: torch.from_numpy(a).to(dev)
+    mb_mode = t(rng.choice([1, 2, 3, 8], nmb).astype(np.uint8)); b8mode = t(rng.integers(4, 8, (nmb, 4)).astype(np.uint8))
+    pdir = t(rng.integers(0, 3, (nmb, 4)).astype(np.uint8)); ref8 = t(rng.integers(0, NRr, (nmb, 2, 4)).astype(np.int8))
+    mv = t(rng.integers(-24, 25, (nmb, NRr, 41, 2)).astype(np.int16))
+    oy = torch.zeros((nmb * 16, 16), dtype=torch.uint8, device=dev); py = torch.zeros_like(oy)
+    oc = torch.zeros((nmb, 2, 4, 16), dtype=torch.uint8, device=dev); pc = torch.zeros_like(oc)
+    p4 = api.tq_default_params(4, 28, 0)
+    lv = torch.zeros((nmb * 16, 16), dtype=torch.int16, device=dev); rn = torch.zeros((nmb * 16, 16), dtype=torch.uint8, device=dev)
+    rec = torch.zeros_like(oy); cst = torch.zeros(nmb * 16, dtype=torch.int32, device=dev); nz = torch.zeros(nmb * 16, dtype=torch.uint8, device=dev)
+    L = api.lib()
+    c_o = torch.zeros((nmb * 2, 64), dtype=torch.uint8, device=dev); c_p = torch.zeros_like(c_o); c_r = torch.zeros_like(c_o)
+    c_dl = torch.zeros((nmb * 2, 4), dtype=torch.int16, device=dev); c_dr = torch.zeros((nmb * 2, 4), dtype=torch.uint8, device=dev)
+    c_al = torch.zeros((nmb * 2, 4, 16), dtype=torch.int16, device=dev); c_ar = torch.zeros((nmb * 2, 4, 16), dtype=torch.uint8, device=dev)
+    c_cbp = torch.zeros(nmb * 2, dtype=torch.uint8, device=dev)
+    yd = t(fr[NRr].copy()); ud = t(cu.copy()); vd = t(cu.copy())
+    mbs = np.zeros(nmb, synth.DBK_MB); mbs["qp"] = rng.integers(24, 40, nmb); mbs["qpc_u"] = mbs["qpc_v"] = 30; mbs["intra"] = rng.random(nmb) < 0.1
+    mbs["cbp_blk"] = np.where(rng.random(nmb) < 0.5, rng.integers(0, 65536, nmb), 0)
+    blks = np.zeros((Wr // 4) * (Hr // 4), synth.DBK_BLK); blks["mv"] = rng.integers(-6, 7, (len(blks), 2, 2)); blks["ref"] = rng.integers(-1, 2, (len(blks), 2))
+    d_mbs = t(mbs.view(np.uint8)); d_blks = t(blks.view(np.uint8)); prog = torch.zeros(Hr // 16, dtype=torch.int32, device=dev)
+    import ctypes as C
+
+    def run():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        s.mc_mb_dev(mb_mode, b8mode, pdir, ref8, mv, mv, oy, py, oc, pc)
+        ev[1].record()
+        api.tq_dev(p4, oy, py, 4, lv, rn, rec, cst, nz)
+        r = L.b2tq_chroma_dev(C.byref(p4), C.c_int(nmb * 2), C.c_void_p(oc.data_ptr()), C.c_void_p(pc.data_ptr()), C.c_void_p(c_dl.data_ptr()), C.c_void_p(c_dr.data_ptr()),
+                              C.c_void_p(c_al.data_ptr()), C.c_void_p(c_ar.data_ptr()), C.c_void_p(c_r.data_ptr()), C.c_void_p(c_cbp.data_ptr()), C.c_void_p(0))
+        assert r == 0
+        ev[2].record()
+        api.deblock_frame_dev(yd, ud, vd, d_mbs, d_blks, prog)
+        ev[3].record()
+        return ev
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    evs = [run() for _ in range(steps)]
+    torch.cuda.synchronize()
+    ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / steps for i in range(3)]
+    s.close()
+    px = Wr * Hr * 3 // 2
+    return {"workload": "1920x1088 4:2:0: prediction of every macroblock from two lists (luma + chroma), transform / quantisation of all luma 4x4 blocks and both chroma "
+                        "planes, in-loop deblocking; synthetic modes / vectors, inputs resident",
+            "ms_prediction": ms[0], "ms_transform_quant": ms[1], "ms_deblock": ms[2],
+            "prediction_gbs": 4 * px / (ms[0] * 1e-3) / 1e9, "transform_quant_gbs": 3.3 * px / (ms[1] * 1e-3) / 1e9,
+            "deblock_note": "k_deblock is latency-bound by construction: one warp per macroblock row, rows chained 2:1 (120 + 2 x 67 wavefront steps at 1080p)",
+            "kernels": "k_mc_mb, k_tq4x4, k_tq_chroma, k_deblock"}
+
+
 def bands_leg(local, rank, world, steps=5):
     """BASELINE config 4 (secondary line, every rank takes part): ONE 3840x2160 picture, full search +-64, 1 reference, split into
     `world` MB-row bands (h264_b200/bands.py).  Per picture, inside the timed region: halo exchange of the reconstructed
@@ -710,7 +777,7 @@ def main():
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tr_path):
         roofline["traffic"] = json.load(open(tr_path)).get("k_sad_fs")
-    secondary = {"fractal_pool": pool_leg(local, peaks), "fractal_window": fractal_leg(local, not args.no_cpu)}
+    secondary = {"fractal_pool": pool_leg(local, peaks), "fractal_window": fractal_leg(local, not args.no_cpu), "reconstruction_1080p": recon_leg(local)}
     secondary.update(multi)
     # the integer search alone under less friendly predictors / content (k_sad_fs is data-dependent)
     roofline["robustness"] = robustness_block(local, sad_peak_tpel)
