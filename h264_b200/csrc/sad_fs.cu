@@ -64,7 +64,18 @@ constexpr int FS_K = FS_KV;         // candidate rows per task (lock step); fs_t
 #define FS_PREV -1
 #endif
 constexpr int FS_PRE = FS_PREV;       // >= 0: radius of the exact pre-pass around the centres' box; -1: one centre only (initial bounds)
-constexpr int FS_SMAX = 7;       // partitions whose centres lie within a 7-pel box share one window pass
+#ifndef FS_SMAXV
+#define FS_SMAXV 7
+#endif
+constexpr int FS_SMAX = FS_SMAXV;       // partitions whose centres lie within a box of this many pel share one window pass
+#ifndef FS_ROLL4V
+#define FS_ROLL4V 0
+#endif
+constexpr bool FS_ROLL4 = FS_ROLL4V != 0;       // fs_task4's loop rolled over 4-row block rows (instruction-cache footprint)
+#ifndef FS_REDUCEDV
+#define FS_REDUCEDV 0
+#endif
+constexpr bool FS_REDUCED = FS_REDUCEDV != 0;   // reduced task routines for the odd column / odd row of a +-R window (fs_task4<1, 4>, <2, 1>)
 constexpr int FS_BMAX = 12;      // a trailing column block of at most this width is walked row-major (type B)
 constexpr int FS_MCAP = 2047;    // cap of each half of the mv-cost lower bound (keeps packed sums in range)
 
@@ -498,10 +509,17 @@ __device__ __forceinline__ uint32_t fs_cold_spill(SLOT &S, FsWarp &ws, const uin
 // lane passed; only then do the passing lanes test their candidates one by one (fs_cold_lane: exact sums, still in
 // registers) and record the (candidate, partition, SAD) triples that pass.  Returns the pass bits of the lane's candidates
 // (bit q*4+j), used only when the record list overflows.
-template <int PITCH, class SLOT>
+//
+// QN, JN: the candidates the routine computes -- columns q < QN of the pair, rows j < JN of the four.  <2, 4> is the full job;
+// <1, 4> serves the trailing column block when it is at most 4 columns wide (the second column of every pair lies outside the
+// window: the +-R window has an odd number of columns) and <2, 1> the last row group when only its first row exists (an odd
+// number of rows): half / a quarter of the VABSDIFF4 of a full job.  The packed sums of the other candidates are a constant that
+// never wins a minimum; their vm bits are clear, so the cold paths never look at them.
+template <int PITCH, int QN, int JN, class SLOT>
 __device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, uint32_t *stg, const uint8_t *wb, int dxa, int dy0, uint32_t vm, uint32_t mmin, uint32_t one, FsTaskCtx tc, int &ncold)
 {
   constexpr int K = 4;
+  constexpr uint32_t BIG = 0x1fff1fffu;            // packed sums of a candidate that is not computed
   const uint4 *cur = reinterpret_cast<const uint4 *>(S.cur);
   const uint32_t lanebits = (uint32_t)(threadIdx.x & 31) << 25;
   const uint32_t mm2 = mmin * 0x10001u;
@@ -513,19 +531,25 @@ __device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, uint32_t *stg,
   for (int j = 0; j < K; j++) { E0[0][j] = E0[1][j] = 0; X0[0][j] = X0[1][j] = 0; Y0[0][j] = Y0[1][j] = 0; }
 #pragma unroll
   for (int j = 0; j < K - 1; j++) ld3(rw[j], wb + j * PITCH);
+  // FS_ROLL4: the loop is rolled over the four block rows (even / odd block rows take a warp-uniform branch after their four
+  // rows) instead of over the two 8-row halves: the body is ~4.5 KB of SASS instead of ~7 KB.  The instruction caches are small
+  // (L0 ~6 KB per scheduler, L1.5 32 KB per SM) and the SM's warps walk the loop desynchronised.
+  constexpr int RPI = FS_ROLL4 ? 4 : 8;           // rows per rolled iteration
 #pragma unroll 1
-  for (int bb = 0; bb < 2; bb++) {
-    const uint8_t *wr = wb + bb * 8 * PITCH;
+  for (int it = 0; it < 16 / RPI; it++) {
+    const int bb = FS_ROLL4 ? it >> 1 : it;
+    const uint8_t *wr = wb + it * RPI * PITCH;
     const uint32_t *Cb = S.Cw + 6 * bb;
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < RPI; r++) {
       ld3(rw[(r + K - 1) & 3], wr + (r + K - 1) * PITCH);
-      const uint4 c = cur[bb * 8 + r];
+      const uint4 c = cur[it * RPI + r];
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const int sl = (r + j) & 3;
 #pragma unroll
         for (int q = 0; q < 2; q++) {
+          if (q >= QN || j >= JN) continue;
           if ((r & 3) == 0) {
             acc[q][j][0] = sad4(c.x, rw[sl][q + 0], 0u);
             acc[q][j][1] = sad4(c.y, rw[sl][q + 1], 0u);
@@ -539,25 +563,25 @@ __device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, uint32_t *stg,
           }
         }
       }
-      if (r == 3) {                                   // even block row 2*bb: pack, minima over the lane's candidates
+      if (FS_ROLL4 ? (r == 3 && !(it & 1)) : r == 3) {   // even block row 2*bb: pack, minima over the lane's candidates
 #pragma unroll
         for (int j = 0; j < K; j++) {
 #pragma unroll
           for (int q = 0; q < 2; q++) {
-            X0[q][j] = acc[q][j][2] * 65536u + acc[q][j][0];
-            Y0[q][j] = acc[q][j][3] * 65536u + acc[q][j][1];
+            X0[q][j] = (q < QN && j < JN) ? acc[q][j][2] * 65536u + acc[q][j][0] : BIG;
+            Y0[q][j] = (q < QN && j < JN) ? acc[q][j][3] * 65536u + acc[q][j][1] : BIG;
           }
         }
         MX0 = gmin8(X0); MY0 = gmin8(Y0);
       }
-      if (r == 7) {                                   // odd block row 2*bb+1: the tree on the minima, one vote
+      if (FS_ROLL4 ? (r == 3 && (it & 1)) : r == 7) {    // odd block row 2*bb+1: the tree on the minima, one vote
         uint32_t X[2][K], Y[2][K];
 #pragma unroll
         for (int j = 0; j < K; j++) {
 #pragma unroll
           for (int q = 0; q < 2; q++) {
-            X[q][j] = acc[q][j][2] * 65536u + acc[q][j][0];
-            Y[q][j] = acc[q][j][3] * 65536u + acc[q][j][1];
+            X[q][j] = (q < QN && j < JN) ? acc[q][j][2] * 65536u + acc[q][j][0] : BIG;
+            Y[q][j] = (q < QN && j < JN) ? acc[q][j][3] * 65536u + acc[q][j][1] : BIG;
           }
         }
         const uint32_t MX1 = gmin8(X), MY1 = gmin8(Y);
@@ -581,7 +605,7 @@ __device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, uint32_t *stg,
 #pragma unroll
           for (int j = 0; j < K; j++) {               // the upper half's two 8x8 sums per candidate: read by the cold path at b == 3
 #pragma unroll
-            for (int q = 0; q < 2; q++) E0[q][j] = add2(add2(X0[q][j], Y0[q][j]), add2(X[q][j], Y[q][j]));
+            for (int q = 0; q < 2; q++) E0[q][j] = (q < QN && j < JN) ? add2(add2(X0[q][j], Y0[q][j]), add2(X[q][j], Y[q][j])) : BIG;
           }
         }
         const bool lp = vm != 0u && ((((rr + mm2) & 0x80008000u) != 0u) || s16 < 0);
@@ -978,7 +1002,12 @@ __device__ __noinline__ void fs_activate(FsCtl &C, SLOT &S, int slot_index, FsWa
 }
 
 template <int PITCH, int NWORK, int MINB>
-__global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtensorMap *__restrict__ tmap, const __grid_constant__ FsArgs a)
+#ifdef FS_MAXNREG
+__global__ void __maxnreg__(FS_MAXNREG) k_sad_fs(
+#else
+__global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(
+#endif
+    const CUtensorMap *__restrict__ tmap, const __grid_constant__ FsArgs a)
 {
   using SLOT = FsSlotT<PITCH>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -1141,7 +1170,12 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(const CUtenso
         uint32_t pass = 0;
 #pragma unroll 1
         for (int rep = 0; rep <= (a.flags >> 8); rep++)      // flags >> 8: extra repetitions of the task (throughput probe, B2ME_FS_REP)
-          pass |= fs_task4<PITCH>(S, WS[warp], STG[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, FsTaskCtx{t, R, g, a.lambda_f}, ncold);
+          if (FS_REDUCED && t >= S.ntaskA && S.npb <= 4)         // trailing column block of <= 4 columns: first column of the pairs only
+            pass |= fs_task4<PITCH, 1, 4>(S, WS[warp], STG[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, FsTaskCtx{t, R, g, a.lambda_f}, ncold);
+          else if (FS_REDUCED && t < S.ntaskA && dy0 + 1 >= S.ncy)  // last row group, one row
+            pass |= fs_task4<PITCH, 2, 1>(S, WS[warp], STG[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, FsTaskCtx{t, R, g, a.lambda_f}, ncold);
+          else
+            pass |= fs_task4<PITCH, 2, 4>(S, WS[warp], STG[warp], wb, dxa, dy0, vm, mmin, (uint32_t)a.one, FsTaskCtx{t, R, g, a.lambda_f}, ncold);
         const long long tt1 = FS_CLOCK();
         c_task += tt1 - tt0;
         if (__any_sync(0xffffffffu, pass != 0u)) {                      // survivors (rare): out of line
@@ -1209,9 +1243,9 @@ cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, 
   cudaError_t e;
   if (smem_bytes_out) *smem_bytes_out = G.total;
   if (G.pitch == 96) {
-    // CTA shape: workers x resident CTAs per SM (B2ME_FS_VAR = "4x3" default, "3x3", "7x2", "6x2": development probes)
+    // CTA shape: workers x resident CTAs per SM (B2ME_FS_VAR = "4x3" default; "3x3", "5x3", "6x3", "7x2", "6x2": development probes)
     static int var = -1;
-    if (var < 0) { const char *e = getenv("B2ME_FS_VAR"); var = !e ? 0 : (e[0] == '7' ? 1 : (e[0] == '6' ? 2 : (e[0] == '3' ? 3 : 0))); }
+    if (var < 0) { const char *e = getenv("B2ME_FS_VAR"); var = (e && e[0] && e[1] == 'x' && e[2]) ? (e[0] - '0') * 10 + (e[2] - '0') : 43; }
 #define FS_LAUNCH96(NW, MB)                                                                                                   \
     {                                                                                                                         \
       static int configured[64] = {0}, occs[64] = {0};                                                                        \
@@ -1230,9 +1264,11 @@ cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, 
       const int grid = min((a.nitems + 1) / 2, sm_count * occ);                                                               \
       k_sad_fs<96, NW, MB><<<grid, (NW + 1) * 32, G.total, s>>>(tm, a);                                                       \
     }
-    if (var == 1) FS_LAUNCH96(7, 2)
-    else if (var == 2) FS_LAUNCH96(6, 2)
-    else if (var == 3) FS_LAUNCH96(3, 3)
+    if (var == 72) FS_LAUNCH96(7, 2)
+    else if (var == 62) FS_LAUNCH96(6, 2)
+    else if (var == 33) FS_LAUNCH96(3, 3)
+    else if (var == 53) FS_LAUNCH96(5, 3)
+    else if (var == 63) FS_LAUNCH96(6, 3)
     else FS_LAUNCH96(4, 3)
 #undef FS_LAUNCH96
   } else if (G.pitch == 160) {

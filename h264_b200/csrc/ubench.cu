@@ -23,7 +23,10 @@ __global__ void __launch_bounds__(256) k_ubench(uint32_t *out, int iters, uint32
     for (int u = 0; u < 4; u++) {
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        if (KIND == 0 || KIND == 1 || KIND == 2 || KIND == 3 || KIND == 7 || (KIND >= 8 && KIND != 19)) a[i] = sad4(x[i], b, a[i]);
+        if (KIND == 0 || KIND == 1 || KIND == 2 || KIND == 3 || KIND == 7 || (KIND >= 8 && KIND != 19 && KIND != 24 && KIND != 25)) a[i] = sad4(x[i], b, a[i]);
+        // 24: VABSDIFF4 predicated OFF at run time (does a nullified instruction hold the ALU pipe?); 25: one live + one nullified
+        if (KIND == 24 || KIND == 25) asm volatile("{.reg .pred p; setp.eq.u32 p, %3, 0x7fffffff; @p vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;}" : "+r"(y[i]) : "r"(x[i]), "r"(b), "r"(iters));
+        if (KIND == 25) a[i] = sad4(x[i], b, a[i]);
         if (KIND == 8) asm volatile("shf.r.clamp.b32 %0, %0, %1, %2;" : "+r"(y[i]) : "r"(b), "r"(8));          // SHF (funnel shift)
         if (KIND == 9) asm volatile("prmt.b32 %0, %0, %1, 0x4321;" : "+r"(y[i]) : "r"(b));                      // PRMT
         if (KIND == 10) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(b), "r"(seed));        // LOP3, independent chain
@@ -91,7 +94,9 @@ cudaError_t ubench(int kind, int iters, double *gops)
       case 20: k_ubench<20><<<grid, block>>>(out, iters, rep); break;
       case 21: k_ubench<21><<<grid, block>>>(out, iters, rep); break;
       case 22: k_ubench<22><<<grid, block>>>(out, iters, rep); break;
-      default: k_ubench<23><<<grid, block>>>(out, iters, rep); break;
+      case 23: k_ubench<23><<<grid, block>>>(out, iters, rep); break;
+      case 24: k_ubench<24><<<grid, block>>>(out, iters, rep); break;
+      default: k_ubench<25><<<grid, block>>>(out, iters, rep); break;
     }
     cudaEventRecord(e1);
     e = cudaEventSynchronize(e1);

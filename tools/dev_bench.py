@@ -5,8 +5,10 @@ import numpy as np
 from h264_b200 import api, synth
 
 out = {}
-names = ["vabsdiff4", "vabsdiff4+imad", "vabsdiff4+iadd3", "vabsdiff4+lop3", "iadd3", "imad", "vimnmx16x2", "vabsdiff4+lds", "v+shf", "v+prmt", "v+lop3i", "v+vimnmx", "v+lds32", "v+iadd", "v+imad", "v+viaddmnmx", "v+idp2a", "v+lds64", "v+imadpack", "viaddmnmx", "v+vimnmx3_16x2", "v+viadd16x2", "v+mad1", "v+vimnmx_s16x2"]
+names = ["vabsdiff4", "vabsdiff4+imad", "vabsdiff4+iadd3", "vabsdiff4+lop3", "iadd3", "imad", "vimnmx16x2", "vabsdiff4+lds", "v+shf", "v+prmt", "v+lop3i", "v+vimnmx", "v+lds32", "v+iadd", "v+imad", "v+viaddmnmx", "v+idp2a", "v+lds64", "v+imadpack", "viaddmnmx", "v+vimnmx3_16x2", "v+viadd16x2", "v+mad1", "v+vimnmx_s16x2", "vabsdiff4_nullified", "vabsdiff4+nullified"]
 for k, n in (enumerate(names) if os.environ.get("UBENCH") else []):
+    if os.environ.get("UBENCH") != "1" and n not in os.environ["UBENCH"].split(","):
+        continue
     out[n] = api.ubench(k, 4000)
     print(f"ubench {n}: {out[n]:.1f} G lane-ops/s", flush=True)
 
