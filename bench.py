@@ -313,8 +313,8 @@ def recon_leg(device, steps=10):
                         "planes, in-loop deblocking; synthetic modes / vectors, inputs resident",
             "ms_prediction": ms[0], "ms_transform_quant": ms[1], "ms_deblock": ms[2],
             "prediction_gbs": 4 * px / (ms[0] * 1e-3) / 1e9, "transform_quant_gbs": 3.3 * px / (ms[1] * 1e-3) / 1e9,
-            "deblock_note": "k_deblock is latency-bound by construction: one warp per macroblock row, rows chained 2:1 (120 + 2 x 67 wavefront steps at 1080p)",
-            "kernels": "k_mc_mb, k_tq4x4, k_tq_chroma, k_deblock"}
+            "deblock_note": "k_deblock is latency-bound by construction: the macroblock order is a 2:1 wavefront (120 + 67 dependent steps at 1080p); one CTA per macroblock row (luma warp + chroma warp), boundary strengths by a picture-wide pre-pass (k_dbk_prep)",
+            "kernels": "k_mc_mb, k_tq4x4, k_tq_chroma, k_dbk_prep, k_deblock"}
 
 
 def bands_leg(local, rank, world, steps=5):

@@ -6,13 +6,19 @@
 //
 // The filter is sequential in macroblock order: macroblock (x, y) modifies three sample columns of (x - 1, y) and three rows of
 // (x, y - 1), and (x + 1, y - 1) modifies three columns of (x, y - 1) -- including the 3 x 3 corner that (x, y)'s top edge touches
-// afterwards.  So (x, y) may start once (x - 1, y) and (x + 1, y - 1) are done: the 2:1 wavefront the reference itself describes
-// under JM_PARALLEL_DEBLOCK (loopFilter.c:92-109).  One CTA (one warp) per macroblock ROW walks its row left to right and waits on
-// the progress counter of the row above; all rows are resident at once (a row CTA is one warp and 1.3 KB of shared memory), so
-// the wait cannot deadlock.  A macroblock is staged in shared memory with the four columns / rows of its left / top neighbours
-// (one pass over global memory in, one out), its 32 boundary strengths are computed by the 32 lanes, and the eight edge steps run
-// on the staged tile: lanes 0-15 the 16 luma lines of an edge, lanes 16-31 the 2 x 8 chroma lines.
+// afterwards.  So the top edge of (x, y) may run once (x - 1, y) is done and the LEFT edge of (x + 1, y - 1) has been filtered: the
+// 2:1 wavefront the reference itself describes under JM_PARALLEL_DEBLOCK (loopFilter.c:92-109), one left edge tighter.
+//   k_dbk_prep   everything that does not depend on samples, for the whole picture at once (one warp per macroblock): the 32
+//                boundary strengths, alpha / beta / clip values per (neighbour kind, plane) -> one 96-byte DbkRec per macroblock
+//   k_deblock    the wavefront: one CTA per macroblock ROW, warp 0 the luma plane, warp 1 both chroma planes (independent chains,
+//                each with its own half of the row's progress counter); all rows are resident at once, so the waits cannot deadlock.
+// Per macroblock the serial chain holds sample work only: vertical edges on the staged tile (a lane keeps one row through all four
+// edges; the left neighbour's four columns stay in the tile from the previous step; own samples and record were fetched one step
+// ahead) -> after the left edge the neighbour's last columns are written and the row's counter released -> wait for the row above ->
+// its four rows over this macroblock (one L2 round trip) -> horizontal edges (a lane keeps one column) -> write-back.
 // Sample loads bypass L1 (ld.global.cg): a line fetched for one macroblock also holds samples that the row above rewrites later.
+// Measured (1080p, B200): 2.55 ms for the one-warp-per-row kernel of the first version, 1.31 ms now; per macroblock of a middle row
+// (-DDBK_PROF): vertical edges 2 700 cycles + 1 020 for the write + release, wait 4 700, rows above 770, horizontal edges 2 480.
 #include <cstdio>
 #include "b2_common.cuh"
 #include "../../include/b2me.h"
@@ -31,7 +37,7 @@ __constant__ uint8_t c_dbk_clip[52][5] = {
 struct DbkArgs {
   int W, H, mbw, mbh;
   uint8_t *y; int yp; uint8_t *u, *v; int cp;
-  const b2dbk_mb *mbs; const b2dbk_blk *blks; int *progress;
+  const b2dbk_mb *mbs; const b2dbk_blk *blks; int *progress;     // progress: one counter per macroblock row, DBK_PSTRIDE ints apart
 };
 
 __device__ __forceinline__ int dbk_mvne(const b2dbk_blk &a, int la, const b2dbk_blk &b, int lb)
@@ -73,122 +79,255 @@ __device__ __forceinline__ void dbk_chroma_line(uint8_t *q, int st, int bs, int 
 }
 
 __device__ __forceinline__ uint32_t ld_cg32(const uint8_t *p) { return __ldcg(reinterpret_cast<const uint32_t *>(p)); }
+__device__ __forceinline__ int ld_acquire(const int *p)
+{ int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{ int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void red_release_add(int *p, int v)
+{ asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-constexpr int DBK_YP = 32, DBK_CP = 16;      // tile pitches
+// Everything of a macroblock's filter that does not depend on samples, computed for the whole picture at once (k_dbk_prep, one
+// warp per macroblock) so that the wavefront kernel's serial chain holds sample work only: the 32 boundary strengths
+// (GetStrengthVer / GetStrengthHor) and alpha / beta / the clip-table row per (neighbour kind, plane).
+struct __align__(16) DbkRec {
+  uint8_t bs[2][4][4];                         // [direction][edge][segment]
+  uint8_t alpha[3][3], beta[3][3];             // [0 left edge, 1 top edge, 2 internal edges][Y, U, V]
+  uint8_t c0[3][3][4];                         // clip-table entry per strength (index bs: 1..3 used; bs == 4 takes the strong filter)
+  uint8_t t8, pad_[9];
+};
+constexpr int DBK_RECW = 24;                   // words per record
+static_assert(sizeof(DbkRec) == 4 * DBK_RECW, "DbkRec is one 96-byte record per macroblock");
 
-__global__ void __launch_bounds__(32) k_deblock(const DbkArgs a)
+__global__ void __launch_bounds__(128) k_dbk_prep(const DbkArgs a, DbkRec *rec)
 {
-  __shared__ __align__(16) uint8_t ty[20 * DBK_YP];          // luma rows -4..15, columns -4..15
-  __shared__ __align__(16) uint8_t tc[2][12 * DBK_CP];       // chroma rows -4..7, columns -4..7, per plane
-  __shared__ uint8_t sbs[2][4][4];
-  const int row = blockIdx.x, lane = threadIdx.x;
-  const int bw = a.W >> 2;
-  for (int mbx = 0; mbx < a.mbw; mbx++) {
-    if (row > 0) {                                           // (mbx + 1, row - 1) must be done
-      const int need = min(mbx + 2, a.mbw);
-      if (lane == 0) {
-        const volatile int *pr = a.progress + row - 1;
-        while (*pr < need) __nanosleep(40);
-      }
-      __syncwarp();
-      __threadfence();
-    }
-    const int mb = row * a.mbw + mbx;
-    const b2dbk_mb mq = a.mbs[mb];
-    if (!mq.disable) {
-      const b2dbk_mb ml = mbx ? a.mbs[mb - 1] : mq, mt = row ? a.mbs[mb - a.mbw] : mq;
-      // ---- stage the macroblock with four columns / rows of its left / top neighbours ----
-      if (lane < 20) {
-        const int gy = row * 16 - 4 + lane;
-        if (gy >= 0) {
-          const uint8_t *src = a.y + (size_t)gy * a.yp + mbx * 16 - 4;
-          uint32_t *dst = reinterpret_cast<uint32_t *>(ty + lane * DBK_YP);
-#pragma unroll
-          for (int k = 0; k < 5; k++) if (k || mbx) dst[k] = ld_cg32(src + 4 * k);
-        }
-      }
-      if (lane < 24) {
-        const int pl = lane / 12, r = lane - 12 * pl, gy = row * 8 - 4 + r;
-        if (gy >= 0) {
-          const uint8_t *src = (pl ? a.v : a.u) + (size_t)gy * a.cp + mbx * 8 - 4;
-          uint32_t *dst = reinterpret_cast<uint32_t *>(tc[pl] + r * DBK_CP);
-#pragma unroll
-          for (int k = 0; k < 3; k++) if (k || mbx) dst[k] = ld_cg32(src + 4 * k);
-        }
-      }
-      // ---- boundary strengths: lane = (direction, edge, segment) ----
-      {
-        const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
-        const int qx = dir ? k : e, qy = dir ? e : k, px = dir ? qx : (qx + 3) & 3, py = dir ? (qy + 3) & 3 : qy;
-        int s = 0;
-        if (!(e == 0 && (dir ? row : mbx) == 0)) {
-          const b2dbk_mb &mp = e ? mq : (dir ? mt : ml);
-          if (mp.intra || mq.intra) s = e ? 3 : 4;
-          else if (((mp.cbp_blk >> (py * 4 + px)) & 1) || ((mq.cbp_blk >> (qy * 4 + qx)) & 1)) s = 2;
-          else {
-            const b2dbk_blk *pq = a.blks + (size_t)(row * 4 + qy) * bw + mbx * 4 + qx;
-            const b2dbk_blk bq = *pq, bp = *(dir ? pq - bw : pq - 1);
-            const int p0 = bp.ref[0], p1 = bp.ref[1], q0 = bq.ref[0], q1 = bq.ref[1];
-            if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) s = 1;
-            else if (p0 != p1) s = p0 == q0 ? (dbk_mvne(bp, 0, bq, 0) | dbk_mvne(bp, 1, bq, 1)) : (dbk_mvne(bp, 0, bq, 1) | dbk_mvne(bp, 1, bq, 0));
-            else s = (dbk_mvne(bp, 0, bq, 0) | dbk_mvne(bp, 1, bq, 1)) && (dbk_mvne(bp, 0, bq, 1) | dbk_mvne(bp, 1, bq, 0));
-          }
-        }
-        sbs[dir][e][k] = (uint8_t)s;
-      }
-      __syncwarp();
-      // ---- the eight edge steps ----
-#pragma unroll 1
-      for (int dir = 0; dir < 2; dir++) {
-#pragma unroll 1
-        for (int e = 0; e < 4; e++) {
-          const uint32_t b4 = *reinterpret_cast<const uint32_t *>(sbs[dir][e]);
-          if (b4 == 0u) continue;
-          const b2dbk_mb &mp = e ? mq : (dir ? mt : ml);
-          if (lane < 16) {
-            if (!((e & 1) && mq.transform8x8)) {
-              const int bs = (b4 >> (8 * (lane >> 2))) & 0xff;
-              const int qp = (mp.qp + mq.qp + 1) >> 1, ia = iclamp(qp + mq.alpha_off, 0, 51), ib = iclamp(qp + mq.beta_off, 0, 51);
-              const int alpha = c_dbk_alpha[ia], beta = c_dbk_beta[ib];
-              if (bs && (alpha | beta))
-                dbk_luma_line(dir ? ty + (4 + 4 * e) * DBK_YP + 4 + lane : ty + (4 + lane) * DBK_YP + 4 + 4 * e, dir ? DBK_YP : 1, bs, alpha, beta, c_dbk_clip[ia][bs]);
-            }
-          } else if (!(e & 1)) {
-            const int pl = (lane - 16) >> 3, i = lane & 7;
-            const int bs = (b4 >> (8 * (i >> 1))) & 0xff;
-            const int qp = ((pl ? mp.qpc_v : mp.qpc_u) + (pl ? mq.qpc_v : mq.qpc_u) + 1) >> 1;
-            const int ia = iclamp(qp + mq.alpha_off, 0, 51), ib = iclamp(qp + mq.beta_off, 0, 51);
-            const int alpha = c_dbk_alpha[ia], beta = c_dbk_beta[ib];
-            if (bs && (alpha | beta))
-              dbk_chroma_line(dir ? tc[pl] + (4 + 2 * e) * DBK_CP + 4 + i : tc[pl] + (4 + i) * DBK_CP + 4 + 2 * e, dir ? DBK_CP : 1, bs, alpha, beta, c_dbk_clip[ia][bs]);
-          }
-          __syncwarp();
-        }
-      }
-      // ---- write back: own rows with the left neighbour's four columns, the top neighbour's rows without the corner ----
-      if (lane < 20) {
-        const int gy = row * 16 - 4 + lane;
-        if (gy >= 0) {
-          uint8_t *dstp = a.y + (size_t)gy * a.yp + mbx * 16 - 4;
-          const uint32_t *src = reinterpret_cast<const uint32_t *>(ty + lane * DBK_YP);
-#pragma unroll
-          for (int k = 0; k < 5; k++) if (k || (mbx && lane >= 4)) reinterpret_cast<uint32_t *>(dstp)[k] = src[k];
-        }
-      }
-      if (lane < 24) {
-        const int pl = lane / 12, r = lane - 12 * pl, gy = row * 8 - 4 + r;
-        if (gy >= 0) {
-          uint8_t *dstp = (pl ? a.v : a.u) + (size_t)gy * a.cp + mbx * 8 - 4;
-          const uint32_t *src = reinterpret_cast<const uint32_t *>(tc[pl] + r * DBK_CP);
-#pragma unroll
-          for (int k = 0; k < 3; k++) if (k || (mbx && r >= 4)) reinterpret_cast<uint32_t *>(dstp)[k] = src[k];
-        }
+  const int mb = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (mb >= a.mbw * a.mbh) return;
+  const int row = mb / a.mbw, mbx = mb - row * a.mbw, bw = a.W >> 2;
+  const b2dbk_mb mq = a.mbs[mb];
+  const b2dbk_mb ml = mbx ? a.mbs[mb - 1] : mq, mt = row ? a.mbs[mb - a.mbw] : mq;
+  {
+    const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
+    const int qx = dir ? k : e, qy = dir ? e : k, px = dir ? qx : (qx + 3) & 3, py = dir ? (qy + 3) & 3 : qy;
+    int s = 0;
+    if (!mq.disable && !(e == 0 && (dir ? row : mbx) == 0)) {
+      const b2dbk_mb &mp = e ? mq : (dir ? mt : ml);
+      if (mp.intra || mq.intra) s = e ? 3 : 4;
+      else if (((mp.cbp_blk >> (py * 4 + px)) & 1) || ((mq.cbp_blk >> (qy * 4 + qx)) & 1)) s = 2;
+      else {
+        const b2dbk_blk *pq = a.blks + (size_t)(row * 4 + qy) * bw + mbx * 4 + qx;
+        const b2dbk_blk bq = *pq, bp = *(dir ? pq - bw : pq - 1);
+        const int p0 = bp.ref[0], p1 = bp.ref[1], q0 = bq.ref[0], q1 = bq.ref[1];
+        if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) s = 1;
+        else if (p0 != p1) s = p0 == q0 ? (dbk_mvne(bp, 0, bq, 0) | dbk_mvne(bp, 1, bq, 1)) : (dbk_mvne(bp, 0, bq, 1) | dbk_mvne(bp, 1, bq, 0));
+        else s = (dbk_mvne(bp, 0, bq, 0) | dbk_mvne(bp, 1, bq, 1)) && (dbk_mvne(bp, 0, bq, 1) | dbk_mvne(bp, 1, bq, 0));
       }
     }
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) *reinterpret_cast<volatile int *>(a.progress + row) = mbx + 1;
+    rec[mb].bs[dir][e][k] = (uint8_t)s;
   }
+  if (lane < 9) {
+    const int t = lane / 3, pl = lane - 3 * t;
+    const b2dbk_mb &mp = t == 0 ? ml : (t == 1 ? mt : mq);
+    const int qp = pl == 0 ? (mp.qp + mq.qp + 1) >> 1 : (pl == 1 ? (mp.qpc_u + mq.qpc_u + 1) >> 1 : (mp.qpc_v + mq.qpc_v + 1) >> 1);
+    const int ia = iclamp(qp + mq.alpha_off, 0, 51), ib = iclamp(qp + mq.beta_off, 0, 51);
+    rec[mb].alpha[t][pl] = c_dbk_alpha[ia]; rec[mb].beta[t][pl] = c_dbk_beta[ib];
+#pragma unroll
+    for (int b = 0; b < 4; b++) rec[mb].c0[t][pl][b] = c_dbk_clip[ia][b];
+  }
+  if (lane == 9) rec[mb].t8 = mq.transform8x8;
+}
+
+constexpr int DBK_PSTRIDE = 32;                // a row's progress counter has a 128-byte line to itself (67 rows poll and add concurrently)
+constexpr int DBK_YP = 36, DBK_CP = 20;      // tile pitches (bytes): rows of a tile start 9 / 5 banks apart
+
+// The wavefront.  One CTA per macroblock row, two warps: warp 0 filters the luma plane, warp 1 both chroma planes (independent
+// of each other, each with its own half of the row's progress counter).  Per macroblock the serial chain is: vertical edges (need
+// only the row's own samples: the left neighbour's four columns stay in the tile from the previous step, the macroblock's own
+// samples and its DbkRec were fetched one step ahead) -> wait for (x + 1, row - 1) -> the four rows above (one L2 round trip) ->
+// horizontal edges -> write-back.  Columns 12..15 (chroma 4..7) of a macroblock are written by the NEXT step, right after its left
+// edge -- the last thing that modifies them -- and that write is followed by the release the row below waits for: release k of a
+// row says that its macroblocks 0 .. k-1 are final, so the rows run one left edge (not one macroblock) behind each other.
+__global__ void __launch_bounds__(64) k_deblock(const DbkArgs a, const DbkRec *__restrict__ recs)
+{
+  __shared__ __align__(16) uint8_t ty[20 * DBK_YP];          // luma rows -4..15, columns -4..15 (+ pad)
+  __shared__ __align__(16) uint8_t tc[2][12 * DBK_CP];       // chroma rows -4..7, columns -4..7, per plane
+  __shared__ __align__(16) uint32_t srec[2][DBK_RECW];             // the macroblock's DbkRec, one copy per warp
+  const int row = blockIdx.x, lane = threadIdx.x & 31, chroma = threadIdx.x >> 5;
+  const DbkRec &R = *reinterpret_cast<const DbkRec *>(srec[chroma]);
+  const DbkRec *rrow = recs + (size_t)row * a.mbw;
+  uint32_t pf[4] = {0, 0, 0, 0}, prec = 0;
+#ifdef DBK_PROF
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
+#define DBK_T(i) { const long long t_ = clock64(); pc[i] += t_ - pt; pt = t_; }
+#else
+#define DBK_T(i)
+#endif
+  // ---- first macroblock: samples and record straight into the tile ----
+  if (!chroma) {
+    if (lane < 16) {
+      const uint8_t *src = a.y + (size_t)(row * 16 + lane) * a.yp;
+#pragma unroll
+      for (int k = 0; k < 4; k++) reinterpret_cast<uint32_t *>(ty + (4 + lane) * DBK_YP + 4)[k] = ld_cg32(src + 4 * k);
+    }
+  } else if (lane < 16) {
+    const int pl = lane >> 3, r = lane & 7;
+    const uint8_t *src = (pl ? a.v : a.u) + (size_t)(row * 8 + r) * a.cp;
+#pragma unroll
+    for (int k = 0; k < 2; k++) reinterpret_cast<uint32_t *>(tc[pl] + (4 + r) * DBK_CP + 4)[k] = ld_cg32(src + 4 * k);
+  }
+  if (lane < DBK_RECW) srec[chroma][lane] = reinterpret_cast<const uint32_t *>(rrow)[lane];
+  __syncwarp();
+  for (int mbx = 0; mbx < a.mbw; mbx++) {
+    const bool more = mbx + 1 < a.mbw;
+    const bool t8 = R.t8 != 0;
+    DBK_T(0)
+    // ---- vertical edges ----
+    if (!chroma) {
+      // a lane filters the same row at all four edges: no exchange between the lanes until the horizontal edges.  After the
+      // LEFT edge the left neighbour's last four columns are final -- and with them everything of that macroblock the row
+      // below reads: written and released at once, so the row below follows one left edge behind instead of one macroblock
+#pragma unroll 1
+      for (int e = 0; e < 4; e++) {
+        const uint32_t b4 = *reinterpret_cast<const uint32_t *>(R.bs[0][e]);
+        if (b4 != 0u && !((e & 1) && t8) && lane < 16) {
+          const int bs = (b4 >> (8 * (lane >> 2))) & 0xff, t = e ? 2 : 0;
+          const int alpha = R.alpha[t][0], beta = R.beta[t][0];
+          if (bs && (alpha | beta)) dbk_luma_line(ty + (4 + lane) * DBK_YP + 4 + 4 * e, 1, bs, alpha, beta, R.c0[t][0][bs & 3]);
+        }
+        if (e == 0 && mbx) {
+          DBK_T(1)
+          if (lane < 16) reinterpret_cast<uint32_t *>(a.y + (size_t)(row * 16 + lane) * a.yp + mbx * 16)[-1] = reinterpret_cast<const uint32_t *>(ty + (4 + lane) * DBK_YP)[0];
+          __syncwarp();
+          if (lane == 0) red_release_add(a.progress + row * DBK_PSTRIDE, 1);
+          __syncwarp();
+          DBK_T(7)
+        }
+      }
+      __syncwarp();
+    } else {
+      const int pl = lane >> 4, ed = (lane >> 3) & 1, i = lane & 7, t = ed ? 2 : 0;
+      const int bs = R.bs[0][2 * ed][i >> 1];
+      const int alpha = R.alpha[t][1 + pl], beta = R.beta[t][1 + pl];
+      if (bs && (alpha | beta)) dbk_chroma_line(tc[pl] + (4 + i) * DBK_CP + 4 + 4 * ed, 1, bs, alpha, beta, R.c0[t][1 + pl][bs & 3]);
+      __syncwarp();
+      if (mbx) {
+        if (lane < 16) reinterpret_cast<uint32_t *>((lane >> 3 ? a.v : a.u) + (size_t)(row * 8 + (lane & 7)) * a.cp + mbx * 8)[-1] =
+                         reinterpret_cast<const uint32_t *>(tc[lane >> 3] + (4 + (lane & 7)) * DBK_CP)[0];
+        __syncwarp();
+        if (lane == 0) red_release_add(a.progress + row * DBK_PSTRIDE, 0x10000);
+      }
+    }
+    // ---- one step ahead: the next macroblock's own samples (nobody modifies them before this row does) and its record; issued
+    //      after the release above (a fence waits for the loads in flight) and consumed at the end of the step ----
+    if (more) {
+      if (!chroma) {
+        if (lane < 16) {
+          const uint8_t *src = a.y + (size_t)(row * 16 + lane) * a.yp + (mbx + 1) * 16;
+#pragma unroll
+          for (int k = 0; k < 4; k++) pf[k] = ld_cg32(src + 4 * k);
+        }
+      } else if (lane < 16) {
+        const int pl = lane >> 3, r = lane & 7;
+        const uint8_t *src = (pl ? a.v : a.u) + (size_t)(row * 8 + r) * a.cp + (mbx + 1) * 8;
+#pragma unroll
+        for (int k = 0; k < 2; k++) pf[k] = ld_cg32(src + 4 * k);
+      }
+      if (lane < DBK_RECW) prec = reinterpret_cast<const uint32_t *>(rrow + mbx + 1)[lane];
+    }
+    DBK_T(1)
+    // ---- the row above: (mbx + 1, row - 1) must be done; then its last four (chroma: two) rows over this macroblock ----
+    if (row > 0) {
+      const int need = mbx + 1;                       // release k of the row above: its macroblocks 0 .. k-1 are final
+      if (lane == 0) {
+        const int *pr = a.progress + (row - 1) * DBK_PSTRIDE;
+        while (((ld_relaxed(pr) >> (16 * chroma)) & 0xffff) < need) { }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire: one fence after the spin instead of one per poll
+      }
+      __syncwarp();
+      DBK_T(2)
+      if (!chroma) {
+        if (lane < 16) {
+          const int r = lane >> 2, k = lane & 3;
+          reinterpret_cast<uint32_t *>(ty + r * DBK_YP + 4)[k] = ld_cg32(a.y + (size_t)(row * 16 - 4 + r) * a.yp + mbx * 16 + 4 * k);
+        }
+      } else if (lane < 8) {
+        const int pl = lane >> 2, r = 2 + ((lane >> 1) & 1), k = lane & 1;
+        reinterpret_cast<uint32_t *>(tc[pl] + r * DBK_CP + 4)[k] = ld_cg32((pl ? a.v : a.u) + (size_t)(row * 8 - 4 + r) * a.cp + mbx * 8 + 4 * k);
+      }
+      __syncwarp();
+    }
+    DBK_T(3)
+    // ---- horizontal edges ----
+    if (!chroma) {
+#pragma unroll 1
+      for (int e = 0; e < 4; e++) {
+        const uint32_t b4 = *reinterpret_cast<const uint32_t *>(R.bs[1][e]);
+        if (b4 == 0u || ((e & 1) && t8)) continue;
+        if (lane < 16) {
+          const int bs = (b4 >> (8 * (lane >> 2))) & 0xff, t = e ? 2 : 1;
+          const int alpha = R.alpha[t][0], beta = R.beta[t][0];
+          if (bs && (alpha | beta)) dbk_luma_line(ty + (4 + 4 * e) * DBK_YP + 4 + lane, DBK_YP, bs, alpha, beta, R.c0[t][0][bs & 3]);
+        }
+      }
+      __syncwarp();
+    } else {
+      const int pl = lane >> 4, ed = (lane >> 3) & 1, i = lane & 7, t = ed ? 2 : 1;
+      const int bs = R.bs[1][2 * ed][i >> 1];
+      const int alpha = R.alpha[t][1 + pl], beta = R.beta[t][1 + pl];
+      if (bs && (alpha | beta)) dbk_chroma_line(tc[pl] + (4 + 4 * ed) * DBK_CP + 4 + i, DBK_CP, bs, alpha, beta, R.c0[t][1 + pl][bs & 3]);
+      __syncwarp();
+    }
+    DBK_T(4)
+    // ---- write-back: the three (one) rows above that the top edge may have changed; own rows from the left neighbour's
+    //      four columns up to column 11 (3), the last four columns only at the end of the row ----
+    if (!chroma) {
+      if (lane < 16) {
+        uint8_t *dst = a.y + (size_t)(row * 16 + lane) * a.yp + mbx * 16;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(ty + (4 + lane) * DBK_YP + 4);
+#pragma unroll
+        for (int k = 0; k < 3; k++) reinterpret_cast<uint32_t *>(dst)[k] = src[k];
+        if (!more) reinterpret_cast<uint32_t *>(dst)[3] = src[3];
+      } else if (row > 0 && lane < 28) {
+        const int r = 1 + (lane - 16) / 4, k = lane & 3;
+        reinterpret_cast<uint32_t *>(a.y + (size_t)(row * 16 - 4 + r) * a.yp + mbx * 16)[k] = reinterpret_cast<const uint32_t *>(ty + r * DBK_YP + 4)[k];
+      }
+    } else {
+      if (lane < 16) {
+        const int pl = lane >> 3, r = lane & 7;
+        uint8_t *dst = (pl ? a.v : a.u) + (size_t)(row * 8 + r) * a.cp + mbx * 8;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(tc[pl] + (4 + r) * DBK_CP + 4);
+        reinterpret_cast<uint32_t *>(dst)[0] = src[0];
+        if (!more) reinterpret_cast<uint32_t *>(dst)[1] = src[1];
+      } else if (row > 0 && lane < 20) {
+        const int pl = (lane >> 1) & 1, k = lane & 1;
+        reinterpret_cast<uint32_t *>((pl ? a.v : a.u) + (size_t)(row * 8 - 1) * a.cp + mbx * 8)[k] = reinterpret_cast<const uint32_t *>(tc[pl] + 3 * DBK_CP + 4)[k];
+      }
+    }
+    __syncwarp();
+    if (!more && lane == 0) red_release_add(a.progress + row * DBK_PSTRIDE, chroma ? 0x10000 : 1);       // the row's last release: everything is final
+    DBK_T(5)
+    // ---- next macroblock: its left neighbour's columns are this tile's last four; own samples and record from the registers ----
+    if (more) {
+      if (!chroma) {
+        if (lane < 16) {
+          uint32_t *t = reinterpret_cast<uint32_t *>(ty + (4 + lane) * DBK_YP);
+          t[0] = t[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) t[1 + k] = pf[k];
+        }
+      } else if (lane < 16) {
+        uint32_t *t = reinterpret_cast<uint32_t *>(tc[lane >> 3] + (4 + (lane & 7)) * DBK_CP);
+        t[0] = t[2]; t[1] = pf[0]; t[2] = pf[1];
+      }
+      if (lane < DBK_RECW) srec[chroma][lane] = prec;
+      __syncwarp();
+    }
+    DBK_T(6)
+  }
+#ifdef DBK_PROF
+  if (lane == 0 && (row == 0 || row == a.mbh / 2))
+    printf("[dbk] row %d %s: cycles per macroblock: prefetch issue %lld, vertical edges (+ release) %lld, wait %lld, rows above %lld, horizontal edges %lld, write-back %lld, carry %lld; write + release of the left columns %lld\n",
+           row, chroma ? "chroma" : "luma", pc[0] / a.mbw, pc[1] / a.mbw, pc[2] / a.mbw, pc[3] / a.mbw, pc[4] / a.mbw, pc[5] / a.mbw, pc[6] / a.mbw, pc[7] / a.mbw);
+#endif
 }
 
 }  // namespace b2
@@ -201,7 +340,7 @@ extern "C" const char *b2dbk_last_error(void) { return g_dbkerr; }
 extern "C" int b2dbk_frame_dev(int W, int H, uint8_t *y, int y_pitch, uint8_t *u, uint8_t *v, int c_pitch,
                                const b2dbk_mb *mbs, const b2dbk_blk *blks, int *progress, void *stream)
 {
-  if (W <= 0 || H <= 0 || (W & 15) || (H & 15) || !y || !u || !v || !mbs || !blks || !progress || y_pitch < W || c_pitch < W / 2 || (y_pitch & 3) || (c_pitch & 3) ||
+  if (W <= 0 || H <= 0 || (W & 15) || (H & 15) || !y || !u || !v || !mbs || !blks || y_pitch < W || c_pitch < W / 2 || (y_pitch & 3) || (c_pitch & 3) ||
       ((uintptr_t)y & 3) || ((uintptr_t)u & 3) || ((uintptr_t)v & 3)) {
     snprintf(g_dbkerr, sizeof(g_dbkerr), "b2dbk_frame: picture size must be a multiple of 16, planes and pitches 4-byte aligned");
     return B2ME_EINVAL;
@@ -210,7 +349,7 @@ extern "C" int b2dbk_frame_dev(int W, int H, uint8_t *y, int y_pitch, uint8_t *u
   int dev = 0, sms = 0, occ = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_deblock, 32, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_deblock, 64, 0);
   if (e != cudaSuccess) { snprintf(g_dbkerr, sizeof(g_dbkerr), "b2dbk_frame: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
   if (H / 16 > occ * sms) {                         // every macroblock row must be resident: a row waits on the row above
     snprintf(g_dbkerr, sizeof(g_dbkerr), "b2dbk_frame: %d macroblock rows exceed the %d resident row CTAs of this device", H / 16, occ * sms);
@@ -218,8 +357,17 @@ extern "C" int b2dbk_frame_dev(int W, int H, uint8_t *y, int y_pitch, uint8_t *u
   }
   DbkArgs a;
   a.W = W; a.H = H; a.mbw = W / 16; a.mbh = H / 16; a.y = y; a.yp = y_pitch; a.u = u; a.v = v; a.cp = c_pitch; a.mbs = mbs; a.blks = blks; a.progress = progress;
-  e = cudaMemsetAsync(progress, 0, sizeof(int) * a.mbh, s);
-  if (e == cudaSuccess) { k_deblock<<<a.mbh, 32, 0, s>>>(a); e = cudaGetLastError(); }
+  DbkRec *rec = nullptr;
+  const int nmb = a.mbw * a.mbh;
+  const size_t cnt_bytes = sizeof(int) * DBK_PSTRIDE * (size_t)a.mbh;
+  // stream-ordered scratch: the rows' progress counters (one 128-byte line each; the caller's `progress` array is too dense
+  // for 67 rows polling and adding at once and is left untouched) + one DbkRec per macroblock
+  e = cudaMallocAsync(reinterpret_cast<void **>(&rec), cnt_bytes + sizeof(DbkRec) * (size_t)nmb, s);
+  if (e == cudaSuccess) { a.progress = reinterpret_cast<int *>(rec); rec = reinterpret_cast<DbkRec *>(reinterpret_cast<uint8_t *>(rec) + cnt_bytes); }
+  if (e == cudaSuccess) e = cudaMemsetAsync(a.progress, 0, cnt_bytes, s);
+  if (e == cudaSuccess) { k_dbk_prep<<<(nmb + 3) / 4, 128, 0, s>>>(a, rec); e = cudaGetLastError(); }
+  if (e == cudaSuccess) { k_deblock<<<a.mbh, 64, 0, s>>>(a, rec); e = cudaGetLastError(); }
+  if (rec) { const cudaError_t e2 = cudaFreeAsync(a.progress, s); if (e == cudaSuccess) e = e2; }
   if (e != cudaSuccess) { snprintf(g_dbkerr, sizeof(g_dbkerr), "b2dbk_frame: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
   return B2ME_OK;
 }

@@ -277,7 +277,8 @@ int b2me_epzs_search_dev(b2me_ctx *ctx, int njobs, const b2me_epzs_job *jobs_dev
  *   blks [H / 4][W / 4]: both lists' vectors (quarter-pel) and reference PICTURE identity per 4x4 block (any id that is equal
  *                        exactly when the pictures are the same; -1: the list is unused) -- enc_picture->mv_info.
  * Macroblock order is the reference's (raster; the kernel runs the 2:1 wavefront of JM_PARALLEL_DEBLOCK, loopFilter.c:92-109,
- * one CTA per macroblock row): the result is bit-identical to the serial filter. */
+ * one CTA per macroblock row, one warp for luma and one for chroma; boundary strengths by a picture-wide pre-pass): the result is
+ * bit-identical to the serial filter. */
 typedef struct b2dbk_mb {
   uint8_t intra, qp, qpc_u, qpc_v, transform8x8, disable;
   int8_t alpha_off, beta_off;
@@ -286,7 +287,7 @@ typedef struct b2dbk_mb {
 typedef struct b2dbk_blk { int16_t mv[2][2]; int16_t ref[2]; } b2dbk_blk;   /* 12 bytes; mv[list][x, y] */
 int b2dbk_frame(int device, int W, int H, uint8_t *y, uint8_t *u, uint8_t *v, const b2dbk_mb *mbs, const b2dbk_blk *blks);   /* host planes, packed */
 int b2dbk_frame_dev(int W, int H, uint8_t *y_dev, int y_pitch, uint8_t *u_dev, uint8_t *v_dev, int c_pitch,
-                    const b2dbk_mb *mbs_dev, const b2dbk_blk *blks_dev, int *progress_dev /* [H / 16] ints, any content */, void *stream);
+                    const b2dbk_mb *mbs_dev, const b2dbk_blk *blks_dev, int *progress_dev /* unused (kept for the ABI; may be NULL): the rows' counters live in stream-ordered scratch */, void *stream);
 const char *b2dbk_last_error(void);
 
 /* ---- reference selection per (mode, block) (the first step of the mode decision) ------------------- */
