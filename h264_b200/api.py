@@ -133,6 +133,10 @@ class Searcher:
     def set_ref_dev(self, r, t, stream=0):
         self._chk(self.L.b2me_set_ref_dev(self.h, C.c_int(r), _dp(t), C.c_int(t.stride(0)), _vp(stream)), "b2me_set_ref_dev")
 
+    def check_errors(self, stream=0):
+        """b2me_check_errors: synchronises `stream`; raises if a _dev search since the last check saw a quarter-pel centre"""
+        self._chk(self.L.b2me_check_errors(self.h, _vp(stream)), "b2me_check_errors")
+
     def set_ref_rows_dev(self, r, t, row_first, row_count, stream=0):
         """planes of luma rows [row_first, row_first + row_count) only (MB-row bands), from a full-geometry CUDA picture"""
         self._chk(self.L.b2me_set_ref_rows_dev(self.h, C.c_int(r), _dp(t), C.c_int(t.stride(0)), C.c_int(row_first), C.c_int(row_count),
@@ -225,6 +229,15 @@ class Searcher:
         out = np.zeros(len(cands), np.int64)
         self._chk(self.L.b2me_distortion_candidates(self.h, C.c_int(metric), C.c_int(int(test8x8)), C.c_int(len(cands)), _p(cands), _p(out)),
                   "b2me_distortion_candidates")
+        return out
+
+    def bid_partition_cost(self, jobs, metric, transform8x8=False, apply_weights=False, log_denom=0):
+        """b2me_bid_partition_cost: BIDPartitionCost of synth.BID_JOB records; int64 array"""
+        from . import synth
+        jobs = np.ascontiguousarray(jobs, synth.BID_JOB)
+        out = np.zeros(len(jobs), np.int64)
+        self._chk(self.L.b2me_bid_partition_cost(self.h, C.c_int(metric), C.c_int(int(transform8x8)), C.c_int(int(apply_weights)), C.c_int(log_denom),
+                                                 C.c_int(len(jobs)), _p(jobs), _p(out)), "b2me_bid_partition_cost")
         return out
 
     def epzs_search(self, jobs, preds, patterns):

@@ -220,6 +220,11 @@ extern "C" int b2me_set_ref_rows_dev(b2me_ctx *c, int ref_idx, const uint8_t *lu
 {
   if (!c || !luma_dev || stride < c->W || ref_idx < 0 || ref_idx >= c->nrefs || row_first < 0 || row_count < 0 || row_first + row_count > c->H) return B2ME_EINVAL;
   B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  if (c->wp_apply[ref_idx] && !(row_first == 0 && row_count == c->H)) {
+    // k_apply_wp maps the slot's whole plane set in place: a partial rebuild would weight the untouched rows a second time
+    snprintf(c->err, sizeof(c->err), "b2me_set_ref_rows_dev: reference slot %d is weighted (b2me_set_ref_weights); upload it whole", ref_idx);
+    return B2ME_EUNSUPPORTED;
+  }
   { int r0 = after_uploads(c, (cudaStream_t)stream); if (r0) return r0; }
   return build_planes(c, ref_idx, luma_dev, stride, (cudaStream_t)stream, row_first, row_first + row_count);
 }
@@ -339,6 +344,15 @@ extern "C" int b2me_search_frame_dev(b2me_ctx *c, const int16_t *pred, const int
 {
   if (!c) return B2ME_EINVAL;
   return b2me_search_mbs_dev(c, 0, c->nmb, pred, center, p, mv_int, cost_int, mv_sub, cost_sub, stream);
+}
+
+static int check_errflag(b2me_ctx *c, cudaStream_t s);
+// The _dev searches never synchronise, so the device-side input check (a search centre that is not integer-pel) is read here.
+extern "C" int b2me_check_errors(b2me_ctx *c, void *stream)
+{
+  if (!c) return B2ME_EINVAL;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  return check_errflag(c, (cudaStream_t)stream);
 }
 
 static int check_errflag(b2me_ctx *c, cudaStream_t s)

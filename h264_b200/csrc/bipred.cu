@@ -237,6 +237,109 @@ __global__ void __launch_bounds__(32) k_bicand(const BiArgs a, int metric, long 
   }
 }
 
+// ---- BIDPartitionCost (mv_search.c:1159-1250): the bi-predictive direction's motion cost in the mode decision.  One warp per
+//      partition.  The region (<= 16x16) is predicted sub-block by sub-block -- each with its own vector pair and ONE origin clamp
+//      per list (OneComponentLumaPrediction -> UMVLine4X, mc_prediction.c:117-136), bi_prediction / weighted_bi_prediction -- into a
+//      shared residual tile; then a lane per 4x4 block (per 8x8 block with the 8x8 transform on and blocktype <= 4) takes the mode
+//      decision's distortion (distortion4x4 / 8x8 of select_distortion: SAD, SSE or the Hadamard sums) and the warp adds them up:
+//      cost = lambda_factor * mvd_bits + (sum << 5). ----
+struct BidArgs {
+  const uint8_t *cur; int cur_pitch;
+  const uint8_t *planes; size_t plane_size;
+  int W, H, Wp, nrefs, metric, t8, wp, denom, n;
+  const b2me_bid_job *jobs; long long *out; int *errflag;
+};
+__constant__ uint8_t c_bid_bx0[5][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 2, 0, 0}, {0, 2, 0, 2}};     // mv_search.c:57-58
+__constant__ uint8_t c_bid_by0[5][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 2, 0, 0}, {0, 0, 0, 0}, {0, 0, 2, 2}};
+__constant__ uint8_t c_bid_bs[8][2] = {{16, 16}, {16, 16}, {16, 8}, {8, 16}, {8, 8}, {8, 4}, {4, 8}, {4, 4}};      // block_size[][]
+
+__global__ void __launch_bounds__(128) k_bid_cost(const BidArgs a)
+{
+  __shared__ short sdiff[4][256];                    // residual of the region, pitch 16, per warp
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, job = blockIdx.x * 4 + w;
+  if (job >= a.n) return;
+  const b2me_bid_job J = a.jobs[job];
+  const int bt = J.blocktype;
+  const bool bad = bt < 1 || bt > 7 || J.block8x8 < 0 || J.block8x8 > 3 || J.ref_l0 < 0 || J.ref_l0 >= a.nrefs || J.ref_l1 < 0 || J.ref_l1 >= a.nrefs ||
+                   J.mb_x < 0 || J.mb_y < 0 || J.mb_x + 16 > a.W || J.mb_y + 16 > a.H;
+  if (bad) { if (lane == 0) { *a.errflag = 1; a.out[job] = -1; } return; }
+  const int pt = bt < 4 ? bt : 4;
+  const int bx = c_bid_bx0[pt][J.block8x8] << 2, by = c_bid_by0[pt][J.block8x8] << 2;
+  const int w0 = c_bid_bs[pt][0], h0 = c_bid_bs[pt][1], sw = c_bid_bs[bt][0], sh = c_bid_bs[bt][1];
+  const int nsx = w0 / sw;
+  BiArgs ba; ba.planes = a.planes; ba.plane_size = a.plane_size; ba.W = a.W; ba.H = a.H; ba.Wp = a.Wp;     // what bi_umv reads
+  BiWp wp; wp.wp = a.wp; wp.w1 = J.weight_l0; wp.w2 = J.weight_l1; wp.off = J.offset_bi; wp.shift = a.denom + 1;
+  wp.lround = 2 * (a.denom ? 1 << (a.denom - 1) : 0);
+  short *d = sdiff[w];
+  for (int i = lane; i < w0 * h0; i += 32) {
+    const int x = i % w0, y = i / w0;
+    const int sb = (y / sh) * nsx + x / sw, ox = (x / sw) * sw, oy = (y / sh) * sh;     // sub-block and its origin inside the region
+    const int qx = (J.mb_x + bx + ox) << 2, qy = (J.mb_y + by + oy) << 2;
+    const uint8_t *r0 = bi_umv(ba, J.ref_l0, qx + J.mv_l0[sb][0], qy + J.mv_l0[sb][1]);
+    const uint8_t *r1 = bi_umv(ba, J.ref_l1, qx + J.mv_l1[sb][0], qy + J.mv_l1[sb][1]);
+    const size_t o = (size_t)(y - oy) * a.Wp + (x - ox);
+    d[y * 16 + x] = (short)((int)a.cur[(size_t)(J.mb_y + by + y) * a.cur_pitch + J.mb_x + bx + x] - bi_pel(r0[o], r1[o], wp));
+  }
+  __syncwarp();
+  const bool use8 = a.t8 && bt <= 4;
+  const int bsz = use8 ? 8 : 4, nbx = w0 / bsz, nb = nbx * (h0 / bsz);
+  int sum = 0;
+  if (lane < nb) {
+    const short *p = d + (lane / nbx) * bsz * 16 + (lane % nbx) * bsz;
+    if (use8) {
+      short t[64];
+      for (int j = 0; j < 8; j++) for (int i = 0; i < 8; i++) t[j * 8 + i] = p[j * 16 + i];
+      if (a.metric == 2) sum = bi_had8(t);
+      else for (int i = 0; i < 64; i++) sum += a.metric == 0 ? abs((int)t[i]) : (int)t[i] * t[i];
+    } else {
+      int t[16];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) t[j * 4 + i] = p[j * 16 + i];
+      if (a.metric == 2) sum = bi_had4(t);
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) sum += a.metric == 0 ? abs(t[i]) : t[i] * t[i];
+      }
+    }
+  }
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  if (lane == 0) a.out[job] = (long long)J.lambda_factor * J.mvd_bits + ((long long)sum << 5);
+}
+
+extern "C" int b2me_bid_partition_cost(b2me_ctx *c, int metric, int transform8x8, int apply_weights, int luma_log_weight_denom, int n,
+                                       const b2me_bid_job *jobs, int64_t *out)
+{
+  if (!c || n < 0 || (n && (!jobs || !out)) || metric < 0 || metric > 2 || luma_log_weight_denom < 0 || luma_log_weight_denom > 7) return B2ME_EINVAL;
+  if (!n) return B2ME_OK;
+  B2_CUDA_CHECK(c, cudaSetDevice(c->device));
+  uint8_t *d = nullptr;
+  const size_t bj = (sizeof(b2me_bid_job) * (size_t)n + 15) & ~(size_t)15;
+  B2_CUDA_CHECK(c, cudaMallocAsync(&d, bj + sizeof(long long) * (size_t)n, c->stream));
+  B2_CUDA_CHECK(c, cudaMemcpyAsync(d, jobs, sizeof(b2me_bid_job) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  BidArgs a;
+  a.cur = c->d_cur; a.cur_pitch = c->W; a.planes = c->d_planes; a.plane_size = c->plane_size;
+  a.W = c->W; a.H = c->H; a.Wp = c->Wp; a.nrefs = c->nrefs; a.metric = metric; a.t8 = transform8x8 ? 1 : 0; a.wp = apply_weights ? 1 : 0;
+  a.denom = luma_log_weight_denom; a.n = n; a.jobs = reinterpret_cast<const b2me_bid_job *>(d); a.out = reinterpret_cast<long long *>(d + bj);
+  a.errflag = c->d_errflag;
+  k_bid_cost<<<(n + 3) / 4, 128, 0, c->stream>>>(a);
+  int r = B2ME_OK, flag = 0;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + bj, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, c->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "b2me_bid_partition_cost: %s", cudaGetErrorString(e)); r = B2ME_ECUDA; }
+  else if (flag) {
+    cudaMemsetAsync(c->d_errflag, 0, sizeof(int), c->stream);
+    snprintf(c->err, sizeof(c->err), "b2me_bid_partition_cost: a record is out of range (blocktype, partition index, reference slot or position)");
+    r = B2ME_EINVAL;
+  }
+  c->launches++;
+  cudaFreeAsync(d, c->stream);
+  return r;
+}
+
 // ---- distortion of a list of (block, reference, candidate) triples ---------------------------------------------
 // computeSAD / computeSSE / computeSATD (me_distortion.c:349-426, 1190-1255, 745-825) at their own boundary
 // (mv_block->computePredFPel / HPel / QPel): what a search whose control flow stays on the host (EPZS, UMHex) asks

@@ -107,6 +107,11 @@ BIPRED_JOB = np.dtype([("min_mcost", np.int64), ("pos_x", np.int16), ("pos_y", n
                        ("ref1", np.int16), ("ref2", np.int16), ("search_range", np.int16),
                        ("pred1", np.int16, 2), ("pred2", np.int16, 2), ("mv1", np.int16, 2), ("mv2", np.int16, 2),
                        ("weight1", np.int16), ("weight2", np.int16), ("offset_bi", np.int16), ("reserved", np.int16)], align=True)
+# b2me_bid_job (include/b2me.h): one BIDPartitionCost call
+BID_JOB = np.dtype([("mb_x", np.int16), ("mb_y", np.int16), ("blocktype", np.int16), ("block8x8", np.int16), ("ref_l0", np.int16), ("ref_l1", np.int16),
+                    ("mv_l0", np.int16, (4, 2)), ("mv_l1", np.int16, (4, 2)), ("weight_l0", np.int16), ("weight_l1", np.int16), ("offset_bi", np.int16),
+                    ("reserved", np.int16), ("mvd_bits", np.int32), ("lambda_factor", np.int32)], align=True)
+assert BID_JOB.itemsize == 60
 BIPRED_RESULT = np.dtype([("cost_int", np.int64), ("cost_sub", np.int64), ("mv_int", np.int16, 2), ("mv_sub", np.int16, 2)], align=True)
 # (blocktype, ox, oy, w, h) of the 41 partitions in include/b2me.h's order
 PART_GEOM = ([(1, 0, 0, 16, 16), (2, 0, 0, 16, 8), (2, 0, 8, 16, 8), (3, 0, 0, 8, 16), (3, 8, 0, 8, 16)] +
@@ -143,6 +148,23 @@ DBK_MB = np.dtype([("intra", np.uint8), ("qp", np.uint8), ("qpc_u", np.uint8), (
 DBK_BLK = np.dtype([("mv", np.int16, (2, 2)), ("ref", np.int16, 2)], align=True)
 CANDIDATE = np.dtype([("pos_x", np.int16), ("pos_y", np.int16), ("blocktype", np.int16), ("ref", np.int16), ("mv", np.int16, 2)])
 _BS = {1: (16, 16), 2: (16, 8), 3: (8, 16), 4: (8, 8), 5: (8, 4), 6: (4, 8), 7: (4, 4)}
+
+
+def bid_jobs(W, H, nrefs, n, seed=1, weighted=False, rmax=9):
+    """n seeded BIDPartitionCost calls: any macroblock (picture borders included), any blocktype and partition index, vectors at any
+    quarter-pel (far enough to leave the picture at the borders), plausible mvd bit counts"""
+    rng = np.random.default_rng(seed)
+    j = np.zeros(n, BID_JOB)
+    j["mb_x"] = 16 * rng.integers(0, W // 16, n); j["mb_y"] = 16 * rng.integers(0, H // 16, n)
+    j["blocktype"] = rng.integers(1, 8, n)
+    nblk = np.where(j["blocktype"] == 1, 1, np.where(j["blocktype"] < 4, 2, 4))
+    j["block8x8"] = rng.integers(0, 4, n) % nblk
+    j["ref_l0"] = rng.integers(0, nrefs, n); j["ref_l1"] = rng.integers(0, nrefs, n)
+    j["mv_l0"] = rng.integers(-4 * rmax, 4 * rmax + 1, (n, 4, 2)); j["mv_l1"] = rng.integers(-4 * rmax, 4 * rmax + 1, (n, 4, 2))
+    j["mvd_bits"] = rng.integers(2, 60, n); j["lambda_factor"] = rng.integers(20, 600, n)
+    if weighted:
+        j["weight_l0"] = rng.integers(10, 60, n); j["weight_l1"] = rng.integers(10, 60, n); j["offset_bi"] = rng.integers(-8, 9, n)
+    return j
 
 
 def bipred_jobs(W, H, nrefs, R, n, seed=1, weighted=False, blocktypes=(1, 2, 3, 4, 5, 6, 7), rmax=5):

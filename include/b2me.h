@@ -84,7 +84,9 @@ int b2me_set_ref(b2me_ctx *ctx, int ref_idx, const uint8_t *luma, int stride);
 int b2me_set_ref_dev(b2me_ctx *ctx, int ref_idx, const uint8_t *luma_dev, int stride, void *stream);
 /* MB-row bands (one picture across several GPUs): rebuild the planes of luma rows [row_first, row_first + row_count)
  * only -- the rows this GPU's band reads (its own rows plus the halo it received) -- from a full-geometry picture
- * buffer; the pad above / below goes with the first / last picture row, everything else keeps its old content. */
+ * buffer; the pad above / below goes with the first / last picture row, everything else keeps its old content.
+ * A slot with weights applied (b2me_set_ref_weights) is stored weighted as a whole: a partial range returns
+ * B2ME_EUNSUPPORTED for it. */
 int b2me_set_ref_rows_dev(b2me_ctx *ctx, int ref_idx, const uint8_t *luma_dev, int stride, int row_first, int row_count, void *stream);
 /* Explicit weighted prediction for the single-list search (UseWeightedReferenceME: computeSADWP / SATDWP / SSEWP,
  * JM/lencod/src/me_distortion.c:434-517, 833-935, 1262-1345; weights from PrepareMEParams, mv_search.c:183-188):
@@ -111,6 +113,14 @@ int b2me_search_frame_dev(b2me_ctx *ctx, const int16_t *pred_dev, const int16_t 
                           const b2me_search_params *params,
                           int16_t *mv_int_dev, int64_t *cost_int_dev,
                           int16_t *mv_sub_dev, int64_t *cost_sub_dev, void *stream);
+/* Streams and the _dev entry points.  A context owns ONE work-item counter and ONE error flag: at most one search of a
+ * context may be in flight at a time, whatever the stream (use one context per concurrent stream -- contexts are cheap next
+ * to their plane sets -- as bench.py's end-to-end leg does).  Uploads (b2me_set_cur_dev / b2me_set_ref[_rows]_dev) and the
+ * searches that read them must be issued on the same stream or be ordered by the caller; a host-pointer b2me_set_ref is
+ * ordered before later work on any stream by the library.  The _dev searches never synchronise, so their device-side
+ * input check (a search centre that is not a multiple of 4) is not reported by the call itself: b2me_check_errors
+ * synchronises `stream`, returns B2ME_EINVAL if a search since the last check saw such a centre, and clears the flag. */
+int b2me_check_errors(b2me_ctx *ctx, void *stream);
 /* MB sub-range variant (MB-row bands / bounded samples): MBs [mb_first, mb_first+mb_count);
  * arrays are still indexed by absolute MB number. */
 int b2me_search_mbs_dev(b2me_ctx *ctx, int mb_first, int mb_count,
@@ -193,6 +203,31 @@ int b2me_bipred_search_dev(b2me_ctx *ctx, int njobs, const b2me_bipred_job *jobs
  * out = distortion << 5.  metric 0 SAD, 1 SSE, 2 SATD. */
 int b2me_bipred_distortion_candidates(b2me_ctx *ctx, int metric, int test8x8, int apply_weights, int luma_log_weight_denom, int n,
                                       const b2me_bipred_job *cands, int64_t *out);
+
+/* ---- motion cost of the bi-predictive direction in the mode decision ------------------------------- */
+/* BIDPartitionCost (JM/lencod/src/mv_search.c:1159-1250; called from list_prediction_cost's BI_PRED branch, mode_decision.c:
+ * 765, 774): for one partition of a B macroblock, weighted_cost(lambda_factor, mvd_bits) + the mode decision's distortion
+ * (p_Vid->distortion4x4 / distortion8x8: select_distortion, me_distortion.c:148-166) of the residual against luma_prediction
+ * with p_dir == 2 (mc_prediction.c:144-236: every sub-block of the partition fetched with ITS vector from both lists through
+ * UMVLine4X, then bi_prediction, or weighted_bi_prediction with the record's weights when apply_weights).
+ *   region     : parttype = blocktype < 4 ? blocktype : 4; origin (bx0, by0)[parttype][block8x8] * 4 inside the macroblock,
+ *                size block_size[parttype]; sub-blocks of block_size[blocktype] in raster order inside the region (1, 1, 1, 1, 2, 2, 4)
+ *   mv_l0/l1   : all_mv[LIST][ref][blocktype][by][bx] of those sub-blocks (quarter-pel, relative), at most four
+ *   mvd_bits   : what mv_bit_cost (mv_search.c:559-581) adds up for both lists -- the caller's motion-vector predictors
+ *                (GetMVPredictor on the encoder's motion field) stay on the host
+ *   metric     : ModeDecisionMetric 0 SAD, 1 SSE, 2 SATD; transform8x8: Transform8x8Mode != 0 (8x8 blocks for blocktype <= 4)
+ * out = the returned distblk.  One launch for n partitions (one warp each). */
+typedef struct b2me_bid_job {
+  int16_t mb_x, mb_y;         /* luma position of the macroblock (pix_x, opix_y) */
+  int16_t blocktype;          /* 1..7 */
+  int16_t block8x8;           /* 0..3 */
+  int16_t ref_l0, ref_l1;     /* reference slots of the context holding listX[0][cur_ref[0]] / listX[1][cur_ref[1]] */
+  int16_t mv_l0[4][2], mv_l1[4][2];
+  int16_t weight_l0, weight_l1, offset_bi, reserved;   /* wbp_weight[0/1][ref0][ref1][0], (wp_offset0 + wp_offset1 + 1) >> 1; read only with apply_weights */
+  int32_t mvd_bits, lambda_factor;
+} b2me_bid_job;               /* 60 bytes */
+int b2me_bid_partition_cost(b2me_ctx *ctx, int metric, int transform8x8, int apply_weights, int luma_log_weight_denom, int n,
+                            const b2me_bid_job *jobs, int64_t *out);
 
 /* ---- distortion at explicit candidates (the computeSAD family at its own boundary) ---------------------------- */
 /* computeSAD / computeSSE / computeSATD (JM/lencod/src/me_distortion.c:349-426, 1190-1255, 745-825; the WP variants

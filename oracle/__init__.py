@@ -216,6 +216,15 @@ class OrcFrame:
         self.L.orc_distortion_candidates(self.h, C.c_int(metric), C.c_int(int(test8x8)), C.c_int(len(cands)), _ptr(cands), _ptr(out))
         return out
 
+    def bid_partition_cost(self, jobs, metric, transform8x8=False, apply_weights=False, log_denom=0):
+        """orc_bid_partition_cost (BIDPartitionCost, mv_search.c:1159-1250) over h264_b200.synth.BID_JOB records"""
+        jobs = np.ascontiguousarray(jobs)
+        assert jobs.dtype.itemsize == 60
+        out = np.zeros(len(jobs), np.int64)
+        self.L.orc_bid_partition_cost(self.h, C.c_int(metric), C.c_int(int(transform8x8)), C.c_int(int(apply_weights)), C.c_int(log_denom),
+                                      C.c_int(len(jobs)), _ptr(jobs), _ptr(out))
+        return out
+
     def epzs_search(self, jobs, preds, patterns):
         """orc_epzs_search (EPZS_motion_estimation / EPZS_subMB_motion_estimation restated over include/b2me.h's job records)"""
         from h264_b200 import synth

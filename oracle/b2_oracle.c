@@ -617,6 +617,56 @@ void orc_distortion_candidates(void *h, int metric, int test8x8, int n, const Or
 }
 
 /* ------------------------------------------------------------------------------------
+ * BIDPartitionCost (JM/lencod/src/mv_search.c:1159-1250): motion cost of the bi-predictive direction of one partition.
+ *   mcost  = weighted_cost(lambda_factor, mvd_bits)              (lcommon/inc/ifunctions.h:224: factor * bits, JCOST_CALC_SCALEUP)
+ *   mb_pred: for every sub-block (h, v) of the region, luma_prediction(.., p_dir = 2, ..) (mc_prediction.c:144-236): both lists'
+ *            blocks through OneComponentLumaPrediction (:117-136, ONE UMVLine4X origin clamp per sub-block and list), then
+ *            bi_prediction ((a + b + 1) >> 1) or weighted_bi_prediction with wbp_weight / offsets (:207-213)
+ *   mcost += distortion4x4 of every 4x4 block of the region, or distortion8x8 of every 8x8 block when Transform8x8Mode is on and
+ *            blocktype <= 4 (select_distortion, me_distortion.c:148-166; each returns dist_scale(.) = . << 5)
+ * mvd_bits (mv_bit_cost, mv_search.c:559-581) needs the encoder's motion field: it is an input here, as at the device boundary.
+ * Job layout = b2me_bid_job of include/b2me.h.
+ * ---------------------------------------------------------------------------------- */
+typedef struct { int16_t mb_x, mb_y, blocktype, block8x8, ref_l0, ref_l1, mv_l0[4][2], mv_l1[4][2], weight_l0, weight_l1, offset_bi, reserved;
+                 int32_t mvd_bits, lambda_factor; } OrcBidJob;
+static const short ORC_BX0[5][4] = {{0,0,0,0}, {0,0,0,0}, {0,0,0,0}, {0,2,0,0}, {0,2,0,2}};
+static const short ORC_BY0[5][4] = {{0,0,0,0}, {0,0,0,0}, {0,2,0,0}, {0,0,0,0}, {0,0,2,2}};
+void orc_bid_partition_cost(void *h, int metric, int transform8x8, int wp, int denom, int n, const OrcBidJob *jobs, int64_t *out)
+{
+  const OrcFrame *f = (const OrcFrame *)h;
+  const int Wp = f->W + 2 * PAD_X;
+  int k;
+  for (k = 0; k < n; k++) {
+    const OrcBidJob *J = &jobs[k];
+    const int bt = J->blocktype, pt = bt < 4 ? bt : 4;
+    const int bx = ORC_BX0[pt][J->block8x8] << 2, by = ORC_BY0[pt][J->block8x8] << 2;
+    const int w0 = ORC_BS[pt][0], h0 = ORC_BS[pt][1], sw = ORC_BS[bt][0], sh = ORC_BS[bt][1];
+    const uint8_t *pl0 = orc_frame_planes(h, J->ref_l0), *pl1 = orc_frame_planes(h, J->ref_l1);
+    uint8_t pred[16][16];
+    int v, hh, x, y, sb = 0;
+    int64_t mcost = (int64_t)J->lambda_factor * J->mvd_bits;
+    for (v = 0; v < h0; v += sh)
+      for (hh = 0; hh < w0; hh += sw, sb++) {
+        const int qx = (J->mb_x + bx + hh) << 2, qy = (J->mb_y + by + v) << 2;
+        const uint8_t *r0 = orc_umv_line4x(pl0, f->W, f->H, qy + J->mv_l0[sb][1], qx + J->mv_l0[sb][0]);
+        const uint8_t *r1 = orc_umv_line4x(pl1, f->W, f->H, qy + J->mv_l1[sb][1], qx + J->mv_l1[sb][0]);
+        for (y = 0; y < sh; y++)
+          for (x = 0; x < sw; x++)
+            pred[v + y][hh + x] = (uint8_t)orc_bi_pel(r0[(size_t)y * Wp + x], r1[(size_t)y * Wp + x], wp, J->weight_l0, J->weight_l1, J->offset_bi, denom);
+      }
+    { const int T = (transform8x8 && bt <= 4) ? 8 : 4; int16_t diff[64]; int i, j;
+      for (v = 0; v < h0; v += T)
+        for (hh = 0; hh < w0; hh += T) {
+          for (j = 0; j < T; j++)
+            for (i = 0; i < T; i++)
+              diff[j * T + i] = (int16_t)((int)f->cur[(size_t)(J->mb_y + by + v + j) * f->W + J->mb_x + bx + hh + i] - (int)pred[v + j][hh + i]);
+          mcost += orc_distortion(metric, T, diff);
+        } }
+    out[k] = mcost;
+  }
+}
+
+/* ------------------------------------------------------------------------------------
  * list_prediction_cost, list 0 (JM/lencod/src/mode_decision.c:275-300) with update_mcost (:256-267) and ref_cost
  * (JM/lencod/inc/mv_search.h:114-131, refbits of mv_search.c:377-385 = the ue(v) length 2*floor(log2(ref+1))+1):
  * for the 21 (mode, block) entries of a macroblock -- mode 1 (1 block), 2 and 3 (2 blocks), 4..7 (the four 8x8 quadrants;

@@ -16,7 +16,7 @@ def declared_symbols():
             continue
         txt = open(os.path.join(ROOT, "include", h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-        names |= set(re.findall(r"\b(b2(?:me|fr|fp|tq)_\w+)\s*\(", txt))
+        names |= set(re.findall(r"\b(b2(?:me|fr|fp|tq|dbk)_\w+)\s*\(", txt))
     return sorted(names)
 
 

@@ -116,3 +116,31 @@ def test_candidate_distortions_match_oracle():
     bad = c[:8].copy(); bad[3]["blocktype"] = 9
     with pytest.raises(api.B2Error):
         s.distortion_candidates(bad, 0)
+
+
+def test_bid_partition_cost_matches_reference_golden_and_oracle():
+    """b2me_bid_partition_cost (k_bid_cost, one warp per partition) against the costs the UNMODIFIED BIDPartitionCost returned in
+    stock lencod runs (tests/golden/jm_bid.npz) and against the oracle on seeded records: SAD / SSE / SATD, 4x4 and 8x8 blocks,
+    weighted, macroblocks at the picture borders with vectors that leave the picture."""
+    from test_oracle_jm import _bid_golden
+    n = 0
+    for tag, cur, refs, jobs, cost, par in _bid_golden():
+        s = _searcher(cur, refs, 8)
+        for p in np.unique(par, axis=0):
+            m = (par == p).all(axis=1)
+            got = s.bid_partition_cost(jobs[m], int(p[0]), bool(p[1]), bool(p[2]), int(p[3]))
+            assert (got == cost[m]).all(), (tag, p, jobs[m][got != cost[m]][:2])
+            n += int(m.sum())
+        s.close()
+    assert n > 1000
+    W, H, NR = 96, 64, 3
+    fr = synth.luma_sequence(W, H, NR + 1, seed=31)
+    cur, refs = fr[NR], fr[[2, 1, 0]]
+    s, of = _searcher(cur, refs, 8), oracle.OrcFrame(cur, refs, 8)
+    for k, (metric, t8, wp, denom) in enumerate([(0, 0, 0, 0), (1, 0, 0, 0), (2, 0, 0, 0), (2, 1, 0, 0), (0, 1, 1, 5), (1, 1, 0, 0), (2, 0, 1, 6), (2, 1, 1, 3)]):
+        jobs = synth.bid_jobs(W, H, NR, 600, seed=40 + k, weighted=bool(wp), rmax=14)
+        got, exp = s.bid_partition_cost(jobs, metric, bool(t8), bool(wp), denom), of.bid_partition_cost(jobs, metric, bool(t8), bool(wp), denom)
+        assert (got == exp).all(), ((metric, t8, wp, denom), jobs[got != exp][:2], got[got != exp][:2], exp[got != exp][:2])
+    bad = synth.bid_jobs(W, H, NR, 4, seed=1); bad[2]["ref_l1"] = NR
+    with pytest.raises(api.B2Error):
+        s.bid_partition_cost(bad, 2)

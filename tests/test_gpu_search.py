@@ -164,6 +164,33 @@ def test_error_codes():
         s.search_frame(pred, cen, api.make_params(100))
 
 
+def test_device_entry_error_flag_and_weighted_row_ranges():
+    """The _dev searches never synchronise: a quarter-pel centre is reported by b2me_check_errors (once, then cleared).  A weighted
+    reference slot refuses a partial row range (its plane set is stored weighted as a whole)."""
+    import torch
+    W, H = 64, 48
+    s = api.Searcher(W, H, 1, 7)
+    dev = torch.device("cuda", 0)
+    z = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    s.set_cur_dev(z); s.set_ref_dev(0, z)
+    pred, cen = synth.predictors(W, H, 1)
+    bad = cen.copy(); bad[0, 0, 0, 0] = 2
+    nmb = s.nmb
+    mvi = torch.zeros((nmb, 1, 41, 2), dtype=torch.int16, device=dev); mvs = torch.zeros_like(mvi)
+    ci = torch.zeros((nmb, 1, 41), dtype=torch.int64, device=dev); cs = torch.zeros_like(ci)
+    p = api.make_params(100)
+    s.search_frame_dev(torch.from_numpy(pred).to(dev), torch.from_numpy(bad).to(dev), p, mvi, ci, mvs, cs)
+    assert s.L.b2me_check_errors(s.h, None) == -1        # B2ME_EINVAL
+    assert s.L.b2me_check_errors(s.h, None) == 0         # cleared
+    s.search_frame_dev(torch.from_numpy(pred).to(dev), torch.from_numpy(cen).to(dev), p, mvi, ci, mvs, cs)
+    assert s.L.b2me_check_errors(s.h, None) == 0
+    s.set_ref_weights(0, 40, -3, 5)
+    with pytest.raises(api.B2Error):
+        s.set_ref_rows_dev(0, z, 16, 16)
+    s.set_ref_rows_dev(0, z, 0, H)                       # the whole picture is fine
+    torch.cuda.synchronize()
+
+
 def test_search_range_64_kernel():
     """+-64 takes the other k_sad_fs instantiation (window pitch 160, 12 worker warps)."""
     W, H, R = 64, 48, 64

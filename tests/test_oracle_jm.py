@@ -308,6 +308,30 @@ def test_deblock_restatement_matches_reference_golden():
     assert n == 12
 
 
+def _bid_golden():
+    """(tag, cur, refs, jobs, cost, par) per captured B picture of tests/golden/jm_bid.npz"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "jm_bid.npz"))
+    for tag in "stw":
+        for i in range(int(g[f"{tag}_n"])):
+            yield tag, g[f"{tag}{i}_cur"], g[f"{tag}{i}_refs"], g[f"{tag}{i}_jobs"], g[f"{tag}{i}_cost"], g[f"{tag}{i}_par"]
+
+
+def test_bid_partition_cost_restatement_matches_reference_golden():
+    """orc_bid_partition_cost against what the UNMODIFIED BIDPartitionCost (JM/lencod/src/mv_search.c:1159-1250) returned for the
+    calls of stock lencod runs (tests/golden/jm_bid.npz, oracle/gen_golden_bid.py): every block type, two references per list,
+    8x8 transform on, implicit weighted bi-prediction on a fading clip."""
+    n = 0
+    for tag, cur, refs, jobs, cost, par in _bid_golden():
+        of = oracle.OrcFrame(cur, refs, 8)
+        for p in np.unique(par, axis=0):
+            m = (par == p).all(axis=1)
+            got = of.bid_partition_cost(jobs[m], int(p[0]), bool(p[1]), bool(p[2]), int(p[3]))
+            assert (got == cost[m]).all(), (tag, p, jobs[m][got != cost[m]][:2])
+            n += int(m.sum())
+    assert n > 1000
+
+
 def test_chroma_prediction_restatement_matches_reference():
     """orc_chroma_sample (the eighth-sample bilinear interpolation of chroma prediction) against the UNMODIFIED
     OneComponentChromaPrediction4x4_regenerate (JM/lencod/src/mc_prediction.c:292-353) through the harness: random planes,
