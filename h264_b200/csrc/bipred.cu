@@ -410,9 +410,14 @@ struct EpzsArgs {
   const uint8_t *cur; int cur_pitch;
   const uint8_t *planes; size_t plane_size;
   int W, H, Wp, nrefs, njobs, npats;
+  const uint8_t *spl; int Wq, Hq, spad;          // the references' byte-shifted search planes (k_search_plane): aligned words at any column
   const b2me_epzs_job *jobs; const int16_t *preds; const b2me_epzs_pattern *pats; b2me_epzs_result *out; int *errflag;
 };
 constexpr int EPZS_VCAP = 768;        // visited vectors per job (overflow: the job fails loudly)
+#ifndef EPZS_MINBV
+#define EPZS_MINBV 5
+#endif
+constexpr int EPZS_MINB = EPZS_MINBV;   // resident CTAs per SM asked of ptxas.  Measured: 8 / 12 / 16 (64 / 40 / 32 registers, spills) give 0.89 / 1.49 / 2.01 ms against 0.89 at 5: the kernel is bound by its own instruction count (1 900 per job, 66 % issue), not by latency
 
 __device__ __forceinline__ bool epzs_visit(uint32_t *vis, int &nvis, int x, int y, bool &ovf)
 {
@@ -428,7 +433,7 @@ __device__ __forceinline__ bool epzs_visit(uint32_t *vis, int &nvis, int x, int 
   return true;
 }
 
-__global__ void __launch_bounds__(128) k_epzs(const EpzsArgs a)
+__global__ void __launch_bounds__(128, EPZS_MINB) k_epzs(const EpzsArgs a)
 {
   __shared__ uint32_t s_vis[4][EPZS_VCAP];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, ji = blockIdx.x * 4 + w;
@@ -446,7 +451,34 @@ __global__ void __launch_bounds__(128) k_epzs(const EpzsArgs a)
   const uint8_t *cur = a.cur + (size_t)J.pos_y * a.cur_pitch + J.pos_x;
   BiArgs u; u.planes = a.planes; u.plane_size = a.plane_size; u.W = a.W; u.H = a.H; u.Wp = a.Wp;
   int npts = 0;
+  // The block's current samples stay in registers as packed words (a lane owns word `lane` and `lane + 32` of the block's
+  // bsx / 4 x bsy words); an integer-pel candidate inside the search plane is read as ALIGNED words of the byte-shifted plane
+  // (column & 3) -- one VABSDIFF4 per four samples instead of two byte loads per sample.  The search plane is the
+  // edge-replicated integer picture, i.e. exactly what UMVLine4X's origin clamp delivers (sad_fs.cu, exactness note).
+  const int wpr = bsx >> 2, nw = wpr * bsy;
+  uint32_t cw[2] = {0u, 0u};
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int k = lane + 32 * h;
+    if (k < nw) cw[h] = *reinterpret_cast<const uint32_t *>(cur + (size_t)(k / wpr) * a.cur_pitch + 4 * (k % wpr));
+  }
+  const bool cur_aligned = ((J.pos_x | a.cur_pitch) & 3) == 0;
   auto sad = [&](int tx, int ty) -> long long {                  // computeSAD << 5 (me_distortion.c:349-426), no early exit
+    if (cur_aligned && !((tx | ty) & 3)) {
+      const int X = J.pos_x + (tx >> 2) + a.spad, Y = J.pos_y + (ty >> 2) + a.spad;
+      if (X >= 0 && Y >= 0 && X + bsx <= a.Wq && Y + bsy <= a.Hq) {
+        const int c = X & 3;
+        const uint8_t *pl = a.spl + ((size_t)(J.ref * 16 + c) * a.Hq + Y) * a.Wq + (X - c);
+        uint32_t s = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int k = lane + 32 * h;
+          if (k < nw) s = sad4(cw[h], __ldg(reinterpret_cast<const uint32_t *>(pl + (size_t)(k / wpr) * a.Wq + 4 * (k % wpr))), s);
+        }
+        npts++;
+        return (long long)__reduce_add_sync(0xffffffffu, s) << 5;
+      }
+    }
     const uint8_t *r = bi_umv(u, J.ref, (J.pos_x << 2) + tx, (J.pos_y << 2) + ty);
     int s = 0;
     for (int k = lane; k < bsx * bsy; k += 32) {
@@ -714,6 +746,7 @@ extern "C" int b2me_epzs_search_dev(b2me_ctx *c, int njobs, const b2me_epzs_job 
   a.cur = c->d_cur; a.cur_pitch = c->W; a.planes = c->d_planes; a.plane_size = c->plane_size;
   a.W = c->W; a.H = c->H; a.Wp = c->Wp; a.nrefs = c->nrefs; a.njobs = njobs; a.npats = npatterns;
   a.jobs = jobs_dev; a.preds = preds_dev; a.pats = patterns_dev; a.out = out_dev; a.errflag = c->d_errflag;
+  a.spl = c->d_spl; a.Wq = c->Wq; a.Hq = c->Hq; a.spad = c->spad;
   k_epzs<<<(njobs + 3) / 4, 128, 0, s>>>(a);
   B2_CUDA_CHECK(c, cudaGetLastError());
   c->launches++;

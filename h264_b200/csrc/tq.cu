@@ -140,85 +140,125 @@ __global__ void __launch_bounds__(128) k_tq4x4(const __grid_constant__ b2tq_para
   cost[k] = cst; nonzero[k] = (uint8_t)nz;
 }
 
-template <bool FIELD>
-__global__ void __launch_bounds__(64) k_tq8x8(const __grid_constant__ b2tq_params c_tq, int nblk, const uint4 *__restrict__ orig, const uint4 *__restrict__ pred,
-                                              short *__restrict__ level, uint8_t *__restrict__ run, uint4 *__restrict__ recon,
-                                              int *__restrict__ cost, uint8_t *__restrict__ nonzero)
+// 8x8 transpose across the eight lanes of a block's group (lane t holds row t -> lane t holds column t): three exchange rounds,
+// every register index is a compile-time constant.
+__device__ __forceinline__ void transpose8(int (&x)[8], int t)
 {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nblk) return;
-  int x[64];
-  uint32_t pw[16];
+#pragma unroll
+  for (int s = 4; s >= 1; s >>= 1) {
+    const bool up = (t & s) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (i & s) continue;
+      const int a = x[i], b = x[i | s];
+      const int recv = __shfl_xor_sync(0xffffffffu, up ? a : b, s);
+      if (up) x[i] = recv; else x[i | s] = recv;
+    }
+  }
+}
+
+// residual_transform_quant_luma_8x8: EIGHT threads per block (round 1 ran one thread per block on a 64-entry register array: 186
+// registers, 18.6 % issue, 3 x the time of k_tq4x4 per byte).  Thread t of a group loads row t (8 bytes of orig and pred), runs the
+// horizontal pass in registers, the group transposes through shuffles, the vertical pass and the quantiser run on column t.  The
+// run / level list comes from a 64-bit mask of the nonzero levels in scan order (OR over the group): a level's slot in the list
+// is the number of set bits below its scan position, its run the distance to the set bit before it; the lists are staged in
+// shared memory and leave as 16-byte / 8-byte stores.  inverse8x8 is horizontal first (JM/lcommon/src/transform.c:450): back to
+// rows, to columns, and to rows again for the reconstruction.  16 blocks per 128-thread CTA.
+template <bool FIELD>
+__global__ void __launch_bounds__(128) k_tq8x8(const __grid_constant__ b2tq_params c_tq, int nblk, const uint2 *__restrict__ orig, const uint2 *__restrict__ pred,
+                                               uint4 *__restrict__ level, uint2 *__restrict__ run, uint2 *__restrict__ recon,
+                                               int *__restrict__ cost, uint8_t *__restrict__ nonzero)
+{
+  __shared__ int s_scale[64], s_offset[64], s_inv[64];
+  __shared__ uint8_t s_pos[64];                        // raster index j*8+i -> scan position
+  __shared__ __align__(16) short s_lev[16][64];
+  __shared__ __align__(8) uint8_t s_run[16][64];
+  const int tid = threadIdx.x, t = tid & 7, g = tid >> 3;
+  if (tid < 64) {
+    s_scale[tid] = c_tq.scale[tid]; s_offset[tid] = c_tq.offset[tid]; s_inv[tid] = c_tq.invscale[tid];
+    const int i = FIELD ? FS8[tid][0] : ZZ8[tid][0], j = FIELD ? FS8[tid][1] : ZZ8[tid][1];
+    s_pos[j * 8 + i] = (uint8_t)tid;
+  }
+  reinterpret_cast<uint4 *>(s_lev[g])[t] = make_uint4(0u, 0u, 0u, 0u);
+  reinterpret_cast<uint2 *>(s_run[g])[t] = make_uint2(0u, 0u);
+  __syncthreads();
+  const int k = blockIdx.x * 16 + g;
+  const bool live = k < nblk;
+  const int kk = live ? k : nblk - 1;                  // idle groups shadow the last block (the shuffles want every lane)
+  const uint2 o2 = orig[(size_t)kk * 8 + t], p2 = pred[(size_t)kk * 8 + t];
+  int x[8];
   int any = 0;
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const uint4 o4 = orig[4 * k + q], p4 = pred[4 * k + q];
-    const uint32_t ow[4] = {o4.x, o4.y, o4.z, o4.w};
-    pw[4 * q] = p4.x; pw[4 * q + 1] = p4.y; pw[4 * q + 2] = p4.z; pw[4 * q + 3] = p4.w;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const int idx = 16 * q + i;
-      x[idx] = (int)((ow[i >> 2] >> (8 * (i & 3))) & 255) - (int)((pw[4 * q + (i >> 2)] >> (8 * (i & 3))) & 255);
-      any |= x[idx];
-    }
+  for (int i = 0; i < 8; i++) {
+    const uint32_t ow = i < 4 ? o2.x : o2.y, pw = i < 4 ? p2.x : p2.y;
+    x[i] = (int)((ow >> (8 * (i & 3))) & 255) - (int)((pw >> (8 * (i & 3))) & 255);
+    any |= x[i];
   }
+  const uint32_t gmask = 0xffu << (8 * ((tid >> 3) & 3));      // this group's lanes of the warp
+  any = (__ballot_sync(0xffffffffu, any != 0) & gmask) != 0u;
   const int qp_per = c_tq.qp / 6, q_bits = 16 + qp_per;
-  // run/level lists are compacted into thread-local arrays (L1) and leave as 16-byte stores: scattered 2- and 1-byte
-  // stores to the thread's own 128 + 64 output bytes made this kernel 4.5x slower than k_tq4x4 per byte
-  __align__(16) short lv_out[64];
-  __align__(16) uint8_t rn_out[64];
-  int nz = 0, cst = 0, n = 0;
-  if (any != 0) {
+  unsigned long long M = 0ull;
+  int cst = 0;
+  if (__any_sync(0xffffffffu, any)) {                  // warp-uniform: some block of the warp has a residual
+    fwd8(x, 1);                                        // row t
+    transpose8(x, t);
+    fwd8(x, 1);                                        // column t: x[j] = coefficient (i = t, j)
+    int lv[8];
+    uint32_t mlo = 0u, mhi = 0u;
 #pragma unroll
-    for (int r = 0; r < 8; r++) fwd8(x + 8 * r, 1);
+    for (int j = 0; j < 8; j++) {
+      const int idx = j * 8 + t, m7 = x[j], am = m7 < 0 ? -m7 : m7;
+      int l = any ? (am * s_scale[idx] + s_offset[idx]) >> q_bits : 0;      // a block without residual is skipped (mode 0)
+      lv[j] = m7 < 0 ? -l : l;
+      const int p = s_pos[idx];
+      if (l) { if (p < 32) mlo |= 1u << p; else mhi |= 1u << (p - 32); }
+    }
 #pragma unroll
-    for (int c = 0; c < 8; c++) fwd8(x + c, 8);
-    int runc = 0;
+    for (int s2 = 1; s2 < 8; s2 <<= 1) { mlo |= __shfl_xor_sync(0xffffffffu, mlo, s2); mhi |= __shfl_xor_sync(0xffffffffu, mhi, s2); }
+    M = ((unsigned long long)mhi << 32) | mlo;
 #pragma unroll
-    for (int s = 0; s < 64; s++) {
-      const int i = FIELD ? FS8[s][0] : ZZ8[s][0], j = FIELD ? FS8[s][1] : ZZ8[s][1], idx = j * 8 + i;
-      const int m7 = x[idx];
-      int lv = 0;
-      if (m7 != 0) {
-        const int am = m7 < 0 ? -m7 : m7;
-        lv = (am * c_tq.scale[idx] + c_tq.offset[idx]) >> q_bits;
+    for (int j = 0; j < 8; j++) {
+      const int idx = j * 8 + t;
+      if (lv[j]) {
+        const int p = s_pos[idx];
+        const unsigned long long below = M & ((1ull << p) - 1ull);
+        const int rank = __popcll(below), prev = below ? 63 - __clzll((long long)below) : -1, r = p - prev - 1;
+        const int al = lv[j] < 0 ? -lv[j] : lv[j];
+        cst += al > 1 ? 999999 : cost8(r, c_tq.disthres);
+        s_lev[g][rank] = (short)lv[j]; s_run[g][rank] = (uint8_t)r;
+        x[j] = (((lv[j] * s_inv[idx]) << qp_per) + 32) >> 6;
+      } else x[j] = 0;
+    }
+#pragma unroll
+    for (int s2 = 1; s2 < 8; s2 <<= 1) cst += __shfl_xor_sync(0xffffffffu, cst, s2);
+  }
+  __syncwarp();
+  if (live) {
+    level[(size_t)k * 8 + t] = reinterpret_cast<const uint4 *>(s_lev[g])[t];
+    run[(size_t)k * 8 + t] = reinterpret_cast<const uint2 *>(s_run[g])[t];
+  }
+  const bool nz = M != 0ull;
+  uint2 rec = p2;
+  if (__any_sync(0xffffffffu, nz)) {
+    transpose8(x, t);                                  // row t
+    inv8(x, 1);
+    transpose8(x, t);                                  // column t
+    inv8(x, 1);
+    transpose8(x, t);                                  // row t again
+    if (nz) {
+      uint32_t w[2] = {0u, 0u};
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const uint32_t pw = i < 4 ? p2.x : p2.y;
+        w[i >> 2] |= (uint32_t)clip255(((x[i] + 32) >> 6) + (int)((pw >> (8 * (i & 3))) & 255)) << (8 * (i & 3));
       }
-      if (lv != 0) {
-        cst += (lv > 1) ? 999999 : cost8(runc, c_tq.disthres);
-        const int sl = m7 < 0 ? -lv : lv;
-        x[idx] = (((sl * c_tq.invscale[idx]) << qp_per) + 32) >> 6;
-        lv_out[n] = (short)sl; rn_out[n] = (uint8_t)runc; n++;
-        runc = 0; nz = 1;
-      } else { x[idx] = 0; runc++; }
+      rec = make_uint2(w[0], w[1]);
     }
   }
-  for (int i = n; i < 64; i++) { lv_out[i] = 0; rn_out[i] = 0; }
-  {
-    uint4 *lo = reinterpret_cast<uint4 *>(level + (size_t)k * 64), *ro = reinterpret_cast<uint4 *>(run + (size_t)k * 64);
-#pragma unroll
-    for (int i = 0; i < 8; i++) lo[i] = reinterpret_cast<const uint4 *>(lv_out)[i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) ro[i] = reinterpret_cast<const uint4 *>(rn_out)[i];
+  if (live) {
+    recon[(size_t)k * 8 + t] = rec;
+    if (t == 0) { cost[k] = cst; nonzero[k] = (uint8_t)nz; }
   }
-  if (nz) {
-#pragma unroll
-    for (int r = 0; r < 8; r++) inv8(x + 8 * r, 1);
-#pragma unroll
-    for (int c = 0; c < 8; c++) inv8(x + c, 8);
-#pragma unroll
-    for (int w = 0; w < 16; w++) {
-      uint32_t v = 0;
-#pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const int i = 4 * w + b;
-        v |= (uint32_t)clip255(((x[i] + 32) >> 6) + (int)((pw[w] >> (8 * b)) & 255)) << (8 * b);
-      }
-      pw[w] = v;
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 4; q++) recon[4 * k + q] = make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
-  cost[k] = cst; nonzero[k] = (uint8_t)nz;
 }
 
 // ---- Intra16x16 luma: residual_transform_quant_luma_16x16 (JM/lencod/src/block.c:207-345) -----------------------------------------
@@ -484,9 +524,9 @@ extern "C" int b2tq_8x8_dev(const b2tq_params *p, int nblk, const uint8_t *orig,
   if (nblk < 0 || !orig || !pred || !level || !run || !recon || !coeff_cost || !nonzero) return B2ME_EINVAL;
   if (nblk == 0) return B2ME_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = (nblk + 63) / 64;
-  if (p->field_scan) k_tq8x8<true><<<grid, 64, 0, s>>>(*p, nblk, (const uint4 *)orig, (const uint4 *)pred, level, run, (uint4 *)recon, coeff_cost, nonzero);
-  else k_tq8x8<false><<<grid, 64, 0, s>>>(*p, nblk, (const uint4 *)orig, (const uint4 *)pred, level, run, (uint4 *)recon, coeff_cost, nonzero);
+  const int grid = (nblk + 15) / 16;          // eight threads per block, 16 blocks per CTA
+  if (p->field_scan) k_tq8x8<true><<<grid, 128, 0, s>>>(*p, nblk, (const uint2 *)orig, (const uint2 *)pred, (uint4 *)level, (uint2 *)run, (uint2 *)recon, coeff_cost, nonzero);
+  else k_tq8x8<false><<<grid, 128, 0, s>>>(*p, nblk, (const uint2 *)orig, (const uint2 *)pred, (uint4 *)level, (uint2 *)run, (uint2 *)recon, coeff_cost, nonzero);
   TQ_CHECK(cudaGetLastError());
   return B2ME_OK;
 }

@@ -11,8 +11,9 @@ B2ME_BANDS=1 ITERS=1 timeout 600 ncu --set full --import-source on --clock-contr
 ND=16384 timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_frac_pool|k_fp_' -c 5 -f -o $O/${TAG}_pool python tools/prof_pool.py > $O/${TAG}_ncu3.log 2>&1
 timeout 300 python tools/pool_bench.py > $O/${TAG}_pool_bench.log 2>&1
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_half|k_quarter|k_apply_wp|k_mc_luma|k_tq|k_distortion|k_bipred|k_cand_dist|k_frac_domain|k_frac_range|k_frac_window|k_frac_decide|k_frac_predict' -c 48 -f -o $O/${TAG}_rest python tools/prof_rest.py > $O/${TAG}_ncu4.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:'k_mc_mb|k_tq16x16|k_tq_chroma|k_dbk_prep|k_deblock|k_epzs|k_sad_table|k_bicand|k_bid_cost|k_expand_pred|k_select_refs|k_gather_best' -c 48 -f -o $O/${TAG}_rest2 python tools/prof_rest2.py > $O/${TAG}_ncu5.log 2>&1
 tail -n 2 $O/${TAG}_ncu1.log; tail -n 2 $O/${TAG}_ncu2.log
 # summaries are made on the box; only the k_sad_fs report itself travels back (gpurun merges at most 64 MiB)
-for n in sad_fs other pool rest; do [ -f $O/${TAG}_$n.ncu-rep ] && python tools/ncu_summary.py $O/${TAG}_$n.ncu-rep $O/${TAG}_$n.ncu.txt > /dev/null 2>&1; done
-rm -f $O/${TAG}_other.ncu-rep $O/${TAG}_pool.ncu-rep $O/${TAG}_rest.ncu-rep
+for n in sad_fs other pool rest rest2; do [ -f $O/${TAG}_$n.ncu-rep ] && python tools/ncu_summary.py $O/${TAG}_$n.ncu-rep $O/${TAG}_$n.ncu.txt > /dev/null 2>&1; done
+rm -f $O/${TAG}_other.ncu-rep $O/${TAG}_pool.ncu-rep $O/${TAG}_rest.ncu-rep $O/${TAG}_rest2.ncu-rep $O/${TAG}_sad_fs.ncu-rep
 ls -la $O | tail -20

@@ -1,6 +1,6 @@
 """Profiling target for the kernels added in round 2 (tools/prof_rest.py covers round 1's): one launch each at 1080p so that one
-`ncu --set full` pass captures k_mc_mb, k_tq16x16, k_tq_chroma, k_deblock, k_epzs, k_sad_table, k_bicand, k_expand_pred,
-k_select_refs, k_gather_best."""
+`ncu --set full` pass captures k_mc_mb, k_tq16x16, k_tq_chroma, k_dbk_prep, k_deblock, k_epzs, k_sad_table, k_bicand, k_bid_cost,
+k_expand_pred, k_select_refs, k_gather_best."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -53,4 +53,7 @@ for mbx, mby in ((3, 2), (60, 30), (119, 67)):
 bj = synth.bipred_jobs(W, H, NR, 16, 4096, seed=2)
 outb = np.zeros(len(bj), np.int64)
 assert s.L.b2me_bipred_distortion_candidates(s.h, 2, 0, 0, 0, len(bj), bj.ctypes.data_as(C.c_void_p), outb.ctypes.data_as(C.c_void_p)) == 0
-print("ok", int(res["npoints"].sum()), int(tab.sum()), int(outb.sum() & 0xffff))
+# k_bid_cost: BIDPartitionCost of 16 K partitions
+bid = synth.bid_jobs(W, H, NR, 16384, seed=4)
+cb = s.bid_partition_cost(bid, 2)
+print("ok", int(cb.sum() & 0xffff), int(res["npoints"].sum()), int(tab.sum()), int(outb.sum() & 0xffff))
