@@ -157,14 +157,18 @@ __device__ __forceinline__ double v1_rms(int n, int ids1, int ids2, int irs1, in
   double alpha = 0.0;
   if (det != 0.0) alpha = __ddiv_rn(__dsub_rn(__dmul_rn(no, rdsum), __dmul_rn(rsum1, dsum1)), det);
   int a = x86_d2i(__dmul_rn(alpha, 100.0));
-  double beta = __ddiv_rn(rsum1, no);
+  // n is a power of two for every partition (16 .. 256): x / n == x * 2^-k bit for bit, and an FP64 division is ~30 instructions
+  const bool p2 = (n & (n - 1)) == 0;
+  const double inv_no = 1.0 / no;                 // folded at compile time where n is (the partition loop is unrolled); exact for a power of two
+  double beta = p2 ? __dmul_rn(rsum1, inv_no) : __ddiv_rn(rsum1, no);
   a = quan_a(a);
   beta = (double)quan_a(x86_d2i(beta));
   alpha = __ddiv_rn((double)a, 100.0);
   *alpha_o = alpha; *beta_o = beta;
   if (alpha < -2.35 || alpha > 4.0) return 1e30;
   if (beta < -60.0 || beta > 255.0) return 1e30;
-  const double t = __dsub_rn(beta, __ddiv_rn(__dmul_rn(alpha, dsum1), no));
+  const double ad = __dmul_rn(alpha, dsum1);
+  const double t = __dsub_rn(beta, p2 ? __dmul_rn(ad, inv_no) : __ddiv_rn(ad, no));
   const double in1 = __dadd_rn(__dsub_rn(__dmul_rn(alpha, dsum2), __dmul_rn(2.0, rdsum)), __dmul_rn(__dmul_rn(2.0, t), dsum1));
   const double in2 = __dsub_rn(__dmul_rn(t, no), __dmul_rn(2.0, rsum1));
   return __dadd_rn(__dadd_rn(rsum2, __dmul_rn(alpha, in1)), __dmul_rn(t, in2));
@@ -253,17 +257,15 @@ __global__ void __launch_bounds__(FR_NT) k_frac_window(const FrArgs a)
       double al = 0.0, be = 0.0, rms = 2e30;
       int o = 0x7fffffff;
       if (ok) { rms = v1_rms(g.w * g.h, ds, dq, rs[p], rq[p], rd, &al, &be); o = ord; }
-      int ij = (di & 0xffff) | (dj << 16);
-      // lexicographic (rms, visit order) minimum over the warp
+      const int ij = (di & 0xffff) | (dj << 16);
+      // lexicographic (rms, visit order) minimum over the warp: the minimum rms through shuffles, the visit order among the
+      // lanes that hold it through one integer reduction (orders are distinct); the winning LANE then compares with the warp's
+      // running best and writes its own scale / offset / displacement -- nothing but the rms ever crosses lanes
+      double rmin = rms;
 #pragma unroll
-      for (int s = 16; s > 0; s >>= 1) {
-        const double r2 = __shfl_xor_sync(0xffffffffu, rms, s);
-        const int o2 = __shfl_xor_sync(0xffffffffu, o, s);
-        const double a2 = __shfl_xor_sync(0xffffffffu, al, s), b2v = __shfl_xor_sync(0xffffffffu, be, s);
-        const int ij2 = __shfl_xor_sync(0xffffffffu, ij, s);
-        if (r2 < rms || (r2 == rms && o2 < o)) { rms = r2; o = o2; al = a2; be = b2v; ij = ij2; }
-      }
-      if (lane == 0 && (rms < wb_rms[warp][p] || (rms == wb_rms[warp][p] && o < wb_ord[warp][p]))) {
+      for (int s = 16; s > 0; s >>= 1) { const double r2 = __shfl_xor_sync(0xffffffffu, rmin, s); rmin = r2 < rmin ? r2 : rmin; }
+      const int omin = __reduce_min_sync(0xffffffffu, rms == rmin ? o : 0x7fffffff);
+      if (rms == rmin && o == omin && o != 0x7fffffff && (rms < wb_rms[warp][p] || (rms == wb_rms[warp][p] && o < wb_ord[warp][p]))) {
         wb_rms[warp][p] = rms; wb_ord[warp][p] = o; wb_al[warp][p] = al; wb_be[warp][p] = be; wb_ij[warp][p] = ij;
       }
     }
