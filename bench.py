@@ -553,7 +553,7 @@ def cpu_reference(seconds_budget=20.0, procs=None):
             "mb_per_s": procs * cnt / wall, "one_core_value": cnt * NREFS * (2 * R + 1) ** 2 * 256 / (sum(r[1] for r in res) / len(res)) / 1e6}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -573,7 +573,7 @@ def run_reference(args):
                        "note": "reference CPU path: unmodified JM objects, one process per host core (the reference is single-threaded), bounded MB sample per step"},
             "cpu_baseline": res, "gpu_launches": 0,
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -584,8 +584,17 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 on their own (NCCL prints its
+    # version line there at the first communicator) go to stderr for the duration of the run
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -799,7 +808,7 @@ def main():
                     "single_stream": {"value": world * pel_sp(nmb) / dt1 / 1e6, "ms_per_step": dt1 * 1e3},
                     "result_checksum": checksum},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -67,6 +67,27 @@ __device__ __forceinline__ void dbk_luma_line(uint8_t *q, int st, int bs, int al
     if (aq) q[st] = (uint8_t)(q1 + iclamp((q2 + avg - (q1 << 1)) >> 1, -c0, c0));
   }
 }
+// the same filter on a line held in registers (p3 .. q3 by reference; p3 / q3 are only read)
+__device__ __forceinline__ void dbk_luma_regs(int p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int q3, int bs, int alpha, int beta, int c0)
+{
+  if (abs(q0 - p0) >= alpha || abs(q0 - q1) >= beta || abs(p0 - p1) >= beta) return;
+  if (bs == 4) {
+    const int small_gap = abs(q0 - p0) < ((alpha >> 2) + 2);
+    const int ap = (abs(p0 - p2) < beta) & small_gap, aq = (abs(q0 - q2) < beta) & small_gap, s = p0 + q0;
+    const int P0 = p0, P1 = p1, P2 = p2, Q0 = q0, Q1 = q1, Q2 = q2;
+    if (ap) { p0 = (Q1 + ((P1 + s) << 1) + P2 + 4) >> 3; p1 = (P2 + P1 + s + 2) >> 2; p2 = (((p3 + P2) << 1) + P2 + P1 + s + 4) >> 3; }
+    else p0 = ((P1 << 1) + P0 + Q1 + 2) >> 2;
+    if (aq) { q0 = (P1 + ((Q1 + s) << 1) + Q2 + 4) >> 3; q1 = (Q2 + Q0 + P0 + Q1 + 2) >> 2; q2 = (((q3 + Q2) << 1) + Q2 + Q1 + s + 4) >> 3; }
+    else q0 = ((Q1 << 1) + Q0 + P1 + 2) >> 2;
+  } else {
+    const int avg = (p0 + q0 + 1) >> 1, ap = abs(p0 - p2) < beta, aq = abs(q0 - q2) < beta, tc = c0 + ap + aq;
+    const int dif = iclamp((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
+    const int P1 = p1, Q1 = q1;
+    if (ap) p1 = P1 + iclamp((p2 + avg - (P1 << 1)) >> 1, -c0, c0);
+    if (aq) q1 = Q1 + iclamp((q2 + avg - (Q1 << 1)) >> 1, -c0, c0);
+    if (dif) { p0 = iclamp(p0 + dif, 0, 255); q0 = iclamp(q0 - dif, 0, 255); }
+  }
+}
 __device__ __forceinline__ void dbk_chroma_line(uint8_t *q, int st, int bs, int alpha, int beta, int c0)
 {
   const int p0 = q[-st], p1 = q[-2 * st], q0 = q[0], q1 = q[st];
@@ -185,22 +206,37 @@ __global__ void __launch_bounds__(64) k_deblock(const DbkArgs a, const DbkRec *_
       // a lane filters the same row at all four edges: no exchange between the lanes until the horizontal edges.  After the
       // LEFT edge the left neighbour's last four columns are final -- and with them everything of that macroblock the row
       // below reads: written and released at once, so the row below follows one left edge behind instead of one macroblock
-#pragma unroll 1
+      // the row lives in registers through all four edges (20 samples unpacked once, packed once)
+      uint32_t *trow = reinterpret_cast<uint32_t *>(ty + (4 + (lane & 15)) * DBK_YP);
+      int px[20];
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const uint32_t wv = trow[k];
+#pragma unroll
+        for (int b = 0; b < 4; b++) px[4 * k + b] = (int)((wv >> (8 * b)) & 255u);
+      }
+#pragma unroll
       for (int e = 0; e < 4; e++) {
         const uint32_t b4 = *reinterpret_cast<const uint32_t *>(R.bs[0][e]);
         if (b4 != 0u && !((e & 1) && t8) && lane < 16) {
           const int bs = (b4 >> (8 * (lane >> 2))) & 0xff, t = e ? 2 : 0;
           const int alpha = R.alpha[t][0], beta = R.beta[t][0];
-          if (bs && (alpha | beta)) dbk_luma_line(ty + (4 + lane) * DBK_YP + 4 + 4 * e, 1, bs, alpha, beta, R.c0[t][0][bs & 3]);
+          if (bs && (alpha | beta))
+            dbk_luma_regs(px[4 * e], px[4 * e + 1], px[4 * e + 2], px[4 * e + 3], px[4 * e + 4], px[4 * e + 5], px[4 * e + 6], px[4 * e + 7], bs, alpha, beta, R.c0[t][0][bs & 3]);
         }
         if (e == 0 && mbx) {
           DBK_T(1)
-          if (lane < 16) reinterpret_cast<uint32_t *>(a.y + (size_t)(row * 16 + lane) * a.yp + mbx * 16)[-1] = reinterpret_cast<const uint32_t *>(ty + (4 + lane) * DBK_YP)[0];
+          if (lane < 16)
+            reinterpret_cast<uint32_t *>(a.y + (size_t)(row * 16 + lane) * a.yp + mbx * 16)[-1] = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16) | ((uint32_t)px[3] << 24);
           __syncwarp();
           if (lane == 0) red_release_add(a.progress + row * DBK_PSTRIDE, 1);
           __syncwarp();
           DBK_T(7)
         }
+      }
+      if (lane < 16) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) trow[k] = (uint32_t)px[4 * k] | ((uint32_t)px[4 * k + 1] << 8) | ((uint32_t)px[4 * k + 2] << 16) | ((uint32_t)px[4 * k + 3] << 24);
       }
       __syncwarp();
     } else {
@@ -258,15 +294,24 @@ __global__ void __launch_bounds__(64) k_deblock(const DbkArgs a, const DbkRec *_
     DBK_T(3)
     // ---- horizontal edges ----
     if (!chroma) {
-#pragma unroll 1
+      // a lane keeps one COLUMN (rows -4 .. 15) in registers through the four horizontal edges
+      uint8_t *tcol = ty + 4 + (lane & 15);
+      int px[20];
+#pragma unroll
+      for (int k = 0; k < 20; k++) px[k] = tcol[k * DBK_YP];
+#pragma unroll
       for (int e = 0; e < 4; e++) {
         const uint32_t b4 = *reinterpret_cast<const uint32_t *>(R.bs[1][e]);
-        if (b4 == 0u || ((e & 1) && t8)) continue;
-        if (lane < 16) {
+        if (b4 != 0u && !((e & 1) && t8) && lane < 16) {
           const int bs = (b4 >> (8 * (lane >> 2))) & 0xff, t = e ? 2 : 1;
           const int alpha = R.alpha[t][0], beta = R.beta[t][0];
-          if (bs && (alpha | beta)) dbk_luma_line(ty + (4 + 4 * e) * DBK_YP + 4 + lane, DBK_YP, bs, alpha, beta, R.c0[t][0][bs & 3]);
+          if (bs && (alpha | beta))
+            dbk_luma_regs(px[4 * e], px[4 * e + 1], px[4 * e + 2], px[4 * e + 3], px[4 * e + 4], px[4 * e + 5], px[4 * e + 6], px[4 * e + 7], bs, alpha, beta, R.c0[t][0][bs & 3]);
         }
+      }
+      if (lane < 16) {
+#pragma unroll
+        for (int k = 1; k < 19; k++) tcol[k * DBK_YP] = (uint8_t)px[k];      // rows -3 .. 14: what an edge can change
       }
       __syncwarp();
     } else {
