@@ -157,7 +157,7 @@ extern "C" int b2me_search_stats(b2me_ctx *c, int64_t out[3], int reset)
   B2_CUDA_CHECK(c, cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
   out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = (int64_t)h[2];
   if (getenv("B2ME_FS_PROFILE"))
-    fprintf(stderr, "[b2me] k_sad_fs warp-cycles: task %llu exact %llu idle %llu total %llu | producer %llu (busy %llu); claim %llu decode %llu post %llu; CTA0 warp0: %llu cycles in %llu ns = %.0f MHz; cold entries %llu\n", h[3], h[4], h[6], h[7], h[5], h[8], h[11], h[12], h[13], h[9], h[10], h[10] ? 1e3 * (double)h[9] / (double)h[10] : 0.0, h[14]);
+    fprintf(stderr, "[b2me] k_sad_fs warp-cycles: task %llu exact %llu idle %llu total %llu | producer %llu (busy %llu); claim %llu decode %llu post %llu; CTA0 warp0: %llu cycles in %llu ns = %.0f MHz; cold entries %llu, %llu warp-cycles in them\n", h[3], h[4], h[6], h[7], h[5], h[8], h[11], h[12], h[13], h[9], h[10], h[10] ? 1e3 * (double)h[9] / (double)h[10] : 0.0, h[14], h[15]);
   if (reset) B2_CUDA_CHECK(c, cudaMemset(c->d_stats, 0, sizeof(h)));
   return B2ME_OK;
 }

@@ -68,6 +68,10 @@ constexpr int FS_PRE = FS_PREV;       // >= 0: radius of the exact pre-pass arou
 #define FS_SMAXV 7
 #endif
 constexpr int FS_SMAX = FS_SMAXV;       // partitions whose centres lie within a box of this many pel share one window pass
+#ifndef FS_COLDPFV
+#define FS_COLDPFV 1
+#endif
+constexpr bool FS_COLDPF = FS_COLDPFV != 0;     // fs_cold_lane: software prefetch of the next candidate's packed sums
 #ifndef FS_ROLL4V
 #define FS_ROLL4V 0
 #endif
@@ -320,11 +324,14 @@ __device__ __noinline__ void fs_dense_collapse(SLOT &S, FsWarp &ws, const uint32
   uint32_t Mh[11];
 #pragma unroll
   for (int k = 0; k < 11; k++) Mh[k] = 0xffffffffu;
+  uint32_t nX = buf[0], nY = buf[8], nX0 = buf[16], nY0 = buf[24], nE0 = buf[32];      // next candidate's words, requested one iteration ahead (see fs_cold_lane)
 #pragma unroll 1
   for (int c = 0; c < 8; c++) {
+    uint32_t X = nX, Y = nY, X0 = nX0, Y0 = nY0, E0 = nE0;
+    if (FS_COLDPF) { if (c < 7) { nX = buf[c + 1]; nY = buf[9 + c]; nX0 = buf[17 + c]; nY0 = buf[25 + c]; nE0 = buf[33 + c]; } }
+    else { X = buf[c]; Y = buf[8 + c]; X0 = buf[16 + c]; Y0 = buf[24 + c]; E0 = buf[32 + c]; }
     if (!((vmm >> c) & 1u)) continue;
     const uint32_t m = (uint32_t)S.mxs[dxa + 4 * (c >> 2)] + (uint32_t)S.mys[dy0 + (c & 3)];
-    const uint32_t X = buf[c], Y = buf[8 + c], X0 = buf[16 + c], Y0 = buf[24 + c], E0 = buf[32 + c];
     uint32_t Q[11];
     Q[0] = X0; Q[1] = Y0; Q[2] = X0 + Y0; Q[3] = X; Q[4] = Y; Q[5] = X + Y; Q[6] = X + X0; Q[7] = Y + Y0; Q[8] = Q[6] + Q[7];
     const uint32_t top = (E0 & 0xffffu) + (E0 >> 16), bot = (Q[8] & 0xffffu) + (Q[8] >> 16);
@@ -404,11 +411,16 @@ __device__ __noinline__ uint32_t fs_cold_lane(SLOT &S, FsWarp &ws, const uint32_
     const uint32_t ctb = ld_vol(&S.Cw[18]), clr = ld_vol(&S.Cw[19]);
     const int c16 = *reinterpret_cast<const volatile int *>(&S.C16);
     pass = 0;
+    // buf is local memory, and with the SM's shared-memory carve-out local lines miss L1: every read is an L2 round trip.  The five
+    // words of candidate c + 1 are requested before candidate c is tested (FS_COLDPF), so the loop pays the latency once, not 8 times.
+    uint32_t nX = buf[0], nY = buf[8], nX0 = buf[16], nY0 = buf[24], nE0 = buf[32];
 #pragma unroll 1
     for (int c = 0; c < 8; c++) {
+      uint32_t X = nX, Y = nY, X0 = nX0, Y0 = nY0, E0 = nE0;
+      if (FS_COLDPF) { if (c < 7) { nX = buf[c + 1]; nY = buf[9 + c]; nX0 = buf[17 + c]; nY0 = buf[25 + c]; nE0 = buf[33 + c]; } }
+      else { X = buf[c]; Y = buf[8 + c]; X0 = buf[16 + c]; Y0 = buf[24 + c]; E0 = buf[32 + c]; }
       if (!((vmm >> c) & 1u)) continue;
       const uint32_t m = (uint32_t)S.mxs[dxa + 4 * (c >> 2)] + (uint32_t)S.mys[dy0 + (c & 3)];
-      const uint32_t X = buf[c], Y = buf[8 + c], X0 = buf[16 + c], Y0 = buf[24 + c], E0 = buf[32 + c];
       const uint32_t XV = X + X0, YV = Y + Y0, E = XV + YV;
       uint32_t t = __vimin3_s16x2(X0 + cx0, Y0 + cy0, X0 + Y0 + ch0);
       t = __vimin3_s16x2(t, X + cx, Y + cy);
@@ -516,7 +528,7 @@ __device__ __forceinline__ uint32_t fs_cold_spill(SLOT &S, FsWarp &ws, const uin
 // number of rows): half / a quarter of the VABSDIFF4 of a full job.  The packed sums of the other candidates are a constant that
 // never wins a minimum; their vm bits are clear, so the cold paths never look at them.
 template <int PITCH, int QN, int JN, class SLOT>
-__device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, uint32_t *stg, const uint8_t *wb, int dxa, int dy0, uint32_t vm, uint32_t mmin, uint32_t one, FsTaskCtx tc, int &ncold)
+__device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, uint32_t *stg, const uint8_t *wb, int dxa, int dy0, uint32_t vm, uint32_t mmin, uint32_t one, FsTaskCtx tc, long long &ncold)
 {
   constexpr int K = 4;
   constexpr uint32_t BIG = 0x1fff1fffu;            // packed sums of a candidate that is not computed
@@ -612,7 +624,7 @@ __device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, uint32_t *stg,
         uint32_t bal = __ballot_sync(0xffffffffu, lp);
         if (bal) {                                    // cold: a candidate of some lane may beat a partition's best
 #ifdef FS_PROFILE
-          ncold++;
+          const long long tc0_ = clock64();
 #endif
           if (__popc(bal) <= FS_SPARSE) {             // the usual case: the passing lanes one at a time, eight candidates side by side
             const int lane = threadIdx.x & 31;
@@ -637,6 +649,9 @@ __device__ __forceinline__ uint32_t fs_task4(SLOT &S, FsWarp &ws, uint32_t *stg,
             if (lp) pass |= fs_cold_spill(S, ws, X, Y, X0, Y0, E0, 2 * bb + 1, dxa, dy0, vm, lanebits, tc);
             __syncwarp();
           }
+#ifdef FS_PROFILE
+          ncold += (1ll << 40) + (clock64() - tc0_);           // entries in the high bits, warp cycles in the low 40
+#endif
         }
       }
     }
@@ -1100,7 +1115,8 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(
   } else {
   // ---- worker warps.  They drain ONE buffer at a time (pref) and move to the other only when pref has no task
   //      left to claim, so the two units finish staggered and the producer's work overlaps the other buffer ----
-  int ex0 = 0, ex1 = 0, nh = 0, pref = 0, ncold = 0;
+  int ex0 = 0, ex1 = 0, nh = 0, pref = 0;
+  long long ncold = 0;
   long long c_task = 0, c_exact = 0;
   const long long t_begin = clock64();
   unsigned long long g_begin; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_begin));
@@ -1209,7 +1225,7 @@ __global__ void __launch_bounds__((NWORK + 1) * 32, MINB) k_sad_fs(
   }
   nh = __reduce_add_sync(0xffffffffu, nh);
   if (lane == 0 && nh) atomicAdd(&st.nhits, nh);
-  if (lane == 0 && ncold && a.stats) atomicAdd(&a.stats[14], (unsigned long long)ncold);
+  if (lane == 0 && ncold && a.stats) { atomicAdd(&a.stats[14], (unsigned long long)(ncold >> 40)); atomicAdd(&a.stats[15], (unsigned long long)(ncold & ((1ll << 40) - 1))); }
   if (lane == 0) { atomicAdd(&st.cyc[3], (unsigned long long)c_idle); atomicAdd(&st.cyc[6], (unsigned long long)c_claim); atomicAdd(&st.cyc[7], (unsigned long long)c_dec); atomicAdd(&st.cyc[8], (unsigned long long)c_post); }
   if (lane == 0) {
     atomicAdd(&st.cyc[0], (unsigned long long)c_task); atomicAdd(&st.cyc[1], (unsigned long long)c_exact);

@@ -19,4 +19,4 @@ p = api.make_params(bench.LAMBDA, do_subpel=False)
 for it in range(int(os.environ.get("ITERS", 1))):
     s.search_frame_dev(torch.from_numpy(pred).to(dev), torch.from_numpy(cen).to(dev), p, mvi, ci, mvs, cs)
 torch.cuda.synchronize()
-print("ok", int(mvi.to(torch.int64).sum().item()))
+print("ok", int(mvi.to(torch.int64).sum().item()), s.search_stats())
