@@ -301,9 +301,12 @@ def recon_leg(device, steps=10):
         api.deblock_frame_dev(yd, ud, vd, d_mbs, d_blks, prog)
         ev[3].record()
         return ev
-    for _ in range(3):
+    # warm-up by TIME, not by count: k_deblock is latency-bound, i.e. proportional to the SM clock, and this leg may follow a host-only
+    # phase (the CPU halves of other legs) during which the GPU has clocked down; 3 passes of ~1 ms do not bring it back
+    t_w = time.time()
+    while time.time() - t_w < 0.25:
         run()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
     evs = [run() for _ in range(steps)]
     torch.cuda.synchronize()
     ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / steps for i in range(3)]
@@ -786,7 +789,7 @@ def main():
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tr_path):
         roofline["traffic"] = json.load(open(tr_path)).get("k_sad_fs")
-    secondary = {"fractal_pool": pool_leg(local, peaks), "fractal_window": fractal_leg(local, not args.no_cpu), "reconstruction_1080p": recon_leg(local)}
+    secondary = {"fractal_pool": pool_leg(local, peaks), "reconstruction_1080p": recon_leg(local), "fractal_window": fractal_leg(local, not args.no_cpu)}
     secondary.update(multi)
     # the integer search alone under less friendly predictors / content (k_sad_fs is data-dependent)
     roofline["robustness"] = robustness_block(local, sad_peak_tpel)

@@ -11,14 +11,20 @@
 //   k_dbk_prep   everything that does not depend on samples, for the whole picture at once (one warp per macroblock): the 32
 //                boundary strengths, alpha / beta / clip values per (neighbour kind, plane) -> one 96-byte DbkRec per macroblock
 //   k_deblock    the wavefront: one CTA per macroblock ROW, warp 0 the luma plane, warp 1 both chroma planes (independent chains,
-//                each with its own half of the row's progress counter); all rows are resident at once, so the waits cannot deadlock.
+//                each with its own half of the row's progress counter), warps 2 / 3 the luma chain's fetcher / publisher; all rows are
+//                resident at once, so the waits cannot deadlock.
 // Per macroblock the serial chain holds sample work only: vertical edges on the staged tile (a lane keeps one row through all four
 // edges; the left neighbour's four columns stay in the tile from the previous step; own samples and record were fetched one step
 // ahead) -> after the left edge the neighbour's last columns are written and the row's counter released -> wait for the row above ->
 // its four rows over this macroblock (one L2 round trip) -> horizontal edges (a lane keeps one column) -> write-back.
 // Sample loads bypass L1 (ld.global.cg): a line fetched for one macroblock also holds samples that the row above rewrites later.
-// Measured (1080p, B200): 2.55 ms for the one-warp-per-row kernel of the first version, 1.31 ms now; per macroblock of a middle row
-// (-DDBK_PROF): vertical edges 2 700 cycles + 1 020 for the write + release, wait 4 700, rows above 770, horizontal edges 2 480.
+// The luma chain's two global round trips run on helper warps of the row's CTA: warp 2 waits for the row above and stages its last
+// four rows (s_top), warp 3 writes the left neighbour's final columns and releases the counter (s_left); the luma warp's own chain per
+// macroblock holds neither a fence nor a global wait.  The luma edges run on registers (a row through the four vertical edges, a
+// column through the four horizontal ones).
+// Measured (1080p, B200): 2.55 ms for the one-warp-per-row kernel of the first version; 1.31 ms with the pre-pass / two warps / early
+// release (per macroblock of a middle row, -DDBK_PROF: vertical edges 2 700 cycles + 1 020 for the write + release, wait 4 700, rows
+// above 770, horizontal edges 2 480); 1.01 ms with the edges on registers; 0.72 ms with the helper warps.
 #include <cstdio>
 #include "b2_common.cuh"
 #include "../../include/b2me.h"
@@ -167,12 +173,45 @@ constexpr int DBK_YP = 36, DBK_CP = 20;      // tile pitches (bytes): rows of a 
 // horizontal edges -> write-back.  Columns 12..15 (chroma 4..7) of a macroblock are written by the NEXT step, right after its left
 // edge -- the last thing that modifies them -- and that write is followed by the release the row below waits for: release k of a
 // row says that its macroblocks 0 .. k-1 are final, so the rows run one left edge (not one macroblock) behind each other.
-__global__ void __launch_bounds__(64) k_deblock(const DbkArgs a, const DbkRec *__restrict__ recs)
+__global__ void __launch_bounds__(128) k_deblock(const DbkArgs a, const DbkRec *__restrict__ recs)
 {
   __shared__ __align__(16) uint8_t ty[20 * DBK_YP];          // luma rows -4..15, columns -4..15 (+ pad)
   __shared__ __align__(16) uint8_t tc[2][12 * DBK_CP];       // chroma rows -4..7, columns -4..7, per plane
   __shared__ __align__(16) uint32_t srec[2][DBK_RECW];             // the macroblock's DbkRec, one copy per warp
-  const int row = blockIdx.x, lane = threadIdx.x & 31, chroma = threadIdx.x >> 5;
+  // The luma chain's two global round trips run on helper warps (warp 2 fetches, warp 3 publishes), so that the luma warp's own
+  // per-macroblock chain holds no fence and no global wait: mailboxes of two slots each, hand-over through shared counters.
+  __shared__ uint32_t s_left[2][16];                         // left-neighbour columns after the left edge of step x (slot x & 1): luma warp -> publisher
+  __shared__ uint32_t s_top[2][16];                          // the four rows above macroblock x (slot x & 1): fetcher -> luma warp
+  __shared__ volatile int s_left_ready, s_published, s_top_ready, s_top_taken;
+  const int row = blockIdx.x, lane = threadIdx.x & 31, role = threadIdx.x >> 5, chroma = role & 1;
+  if (threadIdx.x == 0) { s_left_ready = 0; s_published = 0; s_top_ready = 0; s_top_taken = 0; }
+  __syncthreads();
+  if (role == 2) {                                           // ---- fetcher: waits for the row above, stages its last four rows ----
+    if (row == 0) return;
+    for (int x = 0; x < a.mbw; x++) {
+      if (lane == 0) {
+        const int *pr = a.progress + (row - 1) * DBK_PSTRIDE;
+        while ((ld_relaxed(pr) & 0xffff) < x + 1) { }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        while (s_top_taken < x - 1) { }                      // the slot's previous content (macroblock x - 2) has been taken
+      }
+      __syncwarp();
+      if (lane < 16) s_top[x & 1][lane] = ld_cg32(a.y + (size_t)(row * 16 - 4 + (lane >> 2)) * a.yp + x * 16 + 4 * (lane & 3));
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); s_top_ready = x + 1; }
+    }
+    return;
+  }
+  if (role == 3) {                                           // ---- publisher: writes the left columns, releases the row's counter ----
+    for (int x = 1; x < a.mbw; x++) {
+      if (lane == 0) { while (s_left_ready < x) { } __threadfence_block(); }
+      __syncwarp();
+      if (lane < 16) reinterpret_cast<uint32_t *>(a.y + (size_t)(row * 16 + lane) * a.yp + x * 16)[-1] = s_left[x & 1][lane];
+      __syncwarp();
+      if (lane == 0) { red_release_add(a.progress + row * DBK_PSTRIDE, 1); __threadfence_block(); s_published = x; }
+    }
+    return;
+  }
   const DbkRec &R = *reinterpret_cast<const DbkRec *>(srec[chroma]);
   const DbkRec *rrow = recs + (size_t)row * a.mbw;
   uint32_t pf[4] = {0, 0, 0, 0}, prec = 0;
@@ -226,11 +265,11 @@ __global__ void __launch_bounds__(64) k_deblock(const DbkArgs a, const DbkRec *_
         }
         if (e == 0 && mbx) {
           DBK_T(1)
-          if (lane < 16)
-            reinterpret_cast<uint32_t *>(a.y + (size_t)(row * 16 + lane) * a.yp + mbx * 16)[-1] = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16) | ((uint32_t)px[3] << 24);
+          if (lane == 0) while (s_published < mbx - 2) { }   // the slot's previous content (step mbx - 2) has been published
           __syncwarp();
-          if (lane == 0) red_release_add(a.progress + row * DBK_PSTRIDE, 1);
+          if (lane < 16) s_left[mbx & 1][lane] = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16) | ((uint32_t)px[3] << 24);
           __syncwarp();
+          if (lane == 0) { __threadfence_block(); s_left_ready = mbx; }
           DBK_T(7)
         }
       }
@@ -271,21 +310,24 @@ __global__ void __launch_bounds__(64) k_deblock(const DbkArgs a, const DbkRec *_
     }
     DBK_T(1)
     // ---- the row above: (mbx + 1, row - 1) must be done; then its last four (chroma: two) rows over this macroblock ----
-    if (row > 0) {
+    if (row > 0 && !chroma) {
+      if (lane == 0) { while (s_top_ready < mbx + 1) { } __threadfence_block(); }
+      __syncwarp();
+      DBK_T(2)
+      if (lane < 16) reinterpret_cast<uint32_t *>(ty + (lane >> 2) * DBK_YP + 4)[lane & 3] = s_top[mbx & 1][lane];
+      __syncwarp();
+      if (lane == 0) s_top_taken = mbx + 1;
+    }
+    if (row > 0 && chroma) {
       const int need = mbx + 1;                       // release k of the row above: its macroblocks 0 .. k-1 are final
       if (lane == 0) {
         const int *pr = a.progress + (row - 1) * DBK_PSTRIDE;
-        while (((ld_relaxed(pr) >> (16 * chroma)) & 0xffff) < need) { }
+        while (((ld_relaxed(pr) >> 16) & 0xffff) < need) { }
         asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire: one fence after the spin instead of one per poll
       }
       __syncwarp();
       DBK_T(2)
-      if (!chroma) {
-        if (lane < 16) {
-          const int r = lane >> 2, k = lane & 3;
-          reinterpret_cast<uint32_t *>(ty + r * DBK_YP + 4)[k] = ld_cg32(a.y + (size_t)(row * 16 - 4 + r) * a.yp + mbx * 16 + 4 * k);
-        }
-      } else if (lane < 8) {
+      if (lane < 8) {
         const int pl = lane >> 2, r = 2 + ((lane >> 1) & 1), k = lane & 1;
         reinterpret_cast<uint32_t *>(tc[pl] + r * DBK_CP + 4)[k] = ld_cg32((pl ? a.v : a.u) + (size_t)(row * 8 - 4 + r) * a.cp + mbx * 8 + 4 * k);
       }
@@ -348,7 +390,10 @@ __global__ void __launch_bounds__(64) k_deblock(const DbkArgs a, const DbkRec *_
       }
     }
     __syncwarp();
-    if (!more && lane == 0) red_release_add(a.progress + row * DBK_PSTRIDE, chroma ? 0x10000 : 1);       // the row's last release: everything is final
+    if (!more && lane == 0) {                              // the row's last release: everything is final
+      if (!chroma) { while (s_published < a.mbw - 1) { } __threadfence_block(); }   // after the publisher's last one (the counter only counts)
+      red_release_add(a.progress + row * DBK_PSTRIDE, chroma ? 0x10000 : 1);
+    }
     DBK_T(5)
     // ---- next macroblock: its left neighbour's columns are this tile's last four; own samples and record from the registers ----
     if (more) {
@@ -394,7 +439,7 @@ extern "C" int b2dbk_frame_dev(int W, int H, uint8_t *y, int y_pitch, uint8_t *u
   int dev = 0, sms = 0, occ = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_deblock, 64, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_deblock, 128, 0);
   if (e != cudaSuccess) { snprintf(g_dbkerr, sizeof(g_dbkerr), "b2dbk_frame: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
   if (H / 16 > occ * sms) {                         // every macroblock row must be resident: a row waits on the row above
     snprintf(g_dbkerr, sizeof(g_dbkerr), "b2dbk_frame: %d macroblock rows exceed the %d resident row CTAs of this device", H / 16, occ * sms);
@@ -411,7 +456,7 @@ extern "C" int b2dbk_frame_dev(int W, int H, uint8_t *y, int y_pitch, uint8_t *u
   if (e == cudaSuccess) { a.progress = reinterpret_cast<int *>(rec); rec = reinterpret_cast<DbkRec *>(reinterpret_cast<uint8_t *>(rec) + cnt_bytes); }
   if (e == cudaSuccess) e = cudaMemsetAsync(a.progress, 0, cnt_bytes, s);
   if (e == cudaSuccess) { k_dbk_prep<<<(nmb + 3) / 4, 128, 0, s>>>(a, rec); e = cudaGetLastError(); }
-  if (e == cudaSuccess) { k_deblock<<<a.mbh, 64, 0, s>>>(a, rec); e = cudaGetLastError(); }
+  if (e == cudaSuccess) { k_deblock<<<a.mbh, 128, 0, s>>>(a, rec); e = cudaGetLastError(); }
   if (rec) { const cudaError_t e2 = cudaFreeAsync(a.progress, s); if (e == cudaSuccess) e = e2; }
   if (e != cudaSuccess) { snprintf(g_dbkerr, sizeof(g_dbkerr), "b2dbk_frame: %s", cudaGetErrorString(e)); return B2ME_ECUDA; }
   return B2ME_OK;
