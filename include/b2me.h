@@ -216,6 +216,8 @@ int b2me_bipred_distortion_candidates(b2me_ctx *ctx, int metric, int test8x8, in
  *   mvd_bits   : what mv_bit_cost (mv_search.c:559-581) adds up for both lists -- the caller's motion-vector predictors
  *                (GetMVPredictor on the encoder's motion field) stay on the host
  *   metric     : ModeDecisionMetric 0 SAD, 1 SSE, 2 SATD; transform8x8: Transform8x8Mode != 0 (8x8 blocks for blocktype <= 4)
+ * The twin BPredPartitionCost (mv_search.c:589-700; mode_decision.c:366, 372) is the same computation on the vectors of the
+ * bi-predictive motion search (bipred_mv[list] instead of all_mv; luma_prediction_bi mc_prediction.c:244-284): same record.
  * out = the returned distblk.  One launch for n partitions (one warp each). */
 typedef struct b2me_bid_job {
   int16_t mb_x, mb_y;         /* luma position of the macroblock (pix_x, opix_y) */

@@ -1,4 +1,4 @@
-/* b2me_jm_bid_job.h -- reference-side half of the BIDPartitionCost boundary (JM/lencod/src/mv_search.c:1159-1250): builds the
+/* b2me_jm_bid_job.h -- reference-side half of the BIDPartitionCost / BPredPartitionCost boundary (JM/lencod/src/mv_search.c:1159-1250, 589-700): builds the
  * b2me_bid_job record of include/b2me.h from the encoder's own state.  What stays on the host is what needs the encoder's
  * motion field: mvd_bits, added up exactly as mv_bit_cost does (mv_search.c:559-581: get_neighbors + currMB->GetMVPredictor per
  * sub-block and list, p_Vid->mvbits[]).  Included by a drop-in shim (the call becomes one record of a batched
@@ -16,9 +16,20 @@ static const short b2_bid_bs[8][2] = {{16,16}, {16,16}, {16,8}, {8,16}, {8,8}, {
 static const short b2_bid_bx0[5][4] = {{0,0,0,0}, {0,0,0,0}, {0,0,0,0}, {0,2,0,0}, {0,2,0,2}};
 static const short b2_bid_by0[5][4] = {{0,0,0,0}, {0,0,0,0}, {0,2,0,0}, {0,0,0,0}, {0,0,2,2}};
 
-/* returns 1 when weighted_bi_prediction applies (luma_prediction's apply_weights for p_dir == 2) */
+/* returns 1 when weighted_bi_prediction applies (luma_prediction's apply_weights for p_dir == 2).
+ * mv_array: currSlice->all_mv for BIDPartitionCost; currSlice->bipred_mv[list] for its twin BPredPartitionCost
+ * (mv_search.c:589-700: the same cost on the vectors of the bi-predictive motion search, luma_prediction_bi mc_prediction.c:244-284) */
+static int b2_bipart_build_job(Macroblock *currMB, MotionVector *****mv_array, int blocktype, int block8x8, char cur_ref[2], int lambda_factor,
+                               int slot_l0, int slot_l1, b2me_bid_job *J);
 static int b2_bid_build_job(Macroblock *currMB, int blocktype, int block8x8, char cur_ref[2], int lambda_factor,
                             int slot_l0, int slot_l1, b2me_bid_job *J)
+{ return b2_bipart_build_job(currMB, currMB->p_Slice->all_mv, blocktype, block8x8, cur_ref, lambda_factor, slot_l0, slot_l1, J); }
+static int b2_bpred_build_job(Macroblock *currMB, int blocktype, int block8x8, short ref_l0, short ref_l1, int lambda_factor, int list,
+                              int slot_l0, int slot_l1, b2me_bid_job *J)
+{ char cur_ref[2]; cur_ref[0] = (char)ref_l0; cur_ref[1] = (char)ref_l1;
+  return b2_bipart_build_job(currMB, currMB->p_Slice->bipred_mv[list], blocktype, block8x8, cur_ref, lambda_factor, slot_l0, slot_l1, J); }
+static int b2_bipart_build_job(Macroblock *currMB, MotionVector *****mv_array, int blocktype, int block8x8, char cur_ref[2], int lambda_factor,
+                               int slot_l0, int slot_l1, b2me_bid_job *J)
 {
   VideoParameters *p_Vid = currMB->p_Vid;
   Slice *currSlice = currMB->p_Slice;
@@ -32,7 +43,7 @@ static int b2_bid_build_job(Macroblock *currMB, int blocktype, int block8x8, cha
   J->blocktype = (int16_t)blocktype; J->block8x8 = (int16_t)block8x8;
   J->ref_l0 = (int16_t)slot_l0; J->ref_l1 = (int16_t)slot_l1;
   for (list = 0; list < 2; list++) {
-    MotionVector **all_mv = currSlice->all_mv[list][(int)cur_ref[list]][blocktype];
+    MotionVector **all_mv = mv_array[list][(int)cur_ref[list]][blocktype];
     n = 0;
     for (v = by; v < by + step_v0; v += step_v)
       for (h = bx; h < bx + step_h0; h += step_h, n++) {

@@ -3,8 +3,8 @@
   tests/golden/jm_bid.npz : calls of stock `lencod` runs (oracle/_ref/lencod_wrap_bid = all reference objects + the logger
       oracle/jm_wrap_bid.c): per coded B picture the current luma and the reference lumas it read, the b2me_bid_job records
       built by integration/jm/b2me_jm_bid_job.h and the costs the real function returned.  Runs: SATD metric (default) with two
-      references per list; SAD metric with the 8x8 transform on; implicit weighted bi-prediction (WeightedBiprediction=2) on a
-      fading clip.
+      references per list; the 8x8 transform on; implicit weighted bi-prediction (WeightedBiprediction=2) on a fading clip;
+      bi-predictive motion estimation on (the twin BPredPartitionCost on the bipred_mv vectors, same record).
 The oracle restatement (orc_bid_partition_cost) is checked against every kept call before the file is written.
 Needs /root/reference (build container only)."""
 import os, struct, sys, tempfile
@@ -37,7 +37,7 @@ def parse(path):
             _, metric, t8, wp, denom = struct.unpack_from("<5i", data, o); o += 20
             pics[-1]["jobs"].append(np.frombuffer(data, synth.BID_JOB, 1, o)[0].copy()); o += synth.BID_JOB.itemsize
             pics[-1]["cost"].append(struct.unpack_from("<q", data, o)[0]); o += 8
-            pics[-1]["par"].append((metric, t8, wp, denom))
+            pics[-1]["par"].append((metric, t8, wp & 1, denom, wp >> 1))       # last: 1 = the call was BPredPartitionCost
         else:
             raise ValueError(hex(tag))
     return pics
@@ -62,9 +62,11 @@ def run(tag, frames, extra, seed, stride, fade=False):
         for i in range(frames):
             seq[i, :W * H] = np.clip(seq[i, :W * H].astype(np.int32) * (100 - 9 * i) // 100 + 3 * i, 0, 255).astype(np.uint8)
     open(yuv, "wb").write(seq.tobytes())
+    base = ("NumberBFrames=1", "HierarchicalCoding=0", "BReferencePictures=0", "QPBSlice=32", "DirectModeType=1")
+    if not any(e.startswith("BiPredMotionEstimation") for e in extra):
+        base += ("BiPredMotionEstimation=0",)
     jm_run.run_lencod(yuv, W, H, frames, tmp, exe="lencod_wrap_bid", search_mode=-1, search_range=8, nrefs=2, qp=30,
-                      extra=("NumberBFrames=1", "HierarchicalCoding=0", "BReferencePictures=0", "QPBSlice=32", "DirectModeType=1",
-                             "BiPredMotionEstimation=0") + tuple(extra), env={"B2_WRAP_LOG": log, "B2_WRAP_STRIDE": str(stride)})
+                      extra=base + tuple(extra), env={"B2_WRAP_LOG": log, "B2_WRAP_STRIDE": str(stride)})
     out, n = {}, 0
     for i, pic in enumerate(parse(log)):
         if not pic["jobs"]:
@@ -72,7 +74,7 @@ def run(tag, frames, extra, seed, stride, fade=False):
         jobs, cost, par, got = check(pic)
         bad = int((got != cost).sum())
         print(tag, "poc", pic["poc"], "calls", len(cost), "refs", len(pic["refs"]), "blocktypes", sorted(set(jobs["blocktype"].tolist())),
-              "params", np.unique(par, axis=0).tolist(), "oracle mismatches", bad)
+              "params", np.unique(par, axis=0).tolist(), "BPredPartitionCost calls", int(par[:, 4].sum()), "oracle mismatches", bad)
         assert bad == 0, (jobs[got != cost][:3], cost[got != cost][:3], got[got != cost][:3])
         out[f"{tag}{n}_cur"] = pic["cur"]; out[f"{tag}{n}_refs"] = np.stack(pic["refs"])
         out[f"{tag}{n}_jobs"] = jobs; out[f"{tag}{n}_cost"] = cost; out[f"{tag}{n}_par"] = par
@@ -86,6 +88,9 @@ def main():
     d.update(run("s", 3, ("BList0References=2", "BList1References=1"), 51, 7))
     d.update(run("t", 3, ("Transform8x8Mode=1", "ModeDecisionMetric=0"), 52, 7))
     d.update(run("w", 5, ("WeightedBiprediction=2",), 53, 9, fade=True))
+    # bi-predictive motion estimation on: the mode decision also calls the twin BPredPartitionCost (mv_search.c:589-700) on the
+    # vectors of the bi-predictive search (bipred_mv[list]); same record, same device function
+    d.update(run("p", 3, ("BiPredMotionEstimation=1", "BiPredMERefinements=1", "BiPredMESearchRange=8", "BiPredMESubPel=2"), 54, 5))
     np.savez_compressed(os.path.join(GOLD, "jm_bid.npz"), **d)
     print("written", os.path.getsize(os.path.join(GOLD, "jm_bid.npz")), "bytes")
 

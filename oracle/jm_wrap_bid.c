@@ -1,12 +1,12 @@
 /* jm_wrap_bid.c -- TEST INFRASTRUCTURE ONLY.  Boundary logger for the stock JM 18.5 encoder's BIDPartitionCost
- * (JM/lencod/src/mv_search.c:1159-1250): linked with  -Wl,--wrap=BIDPartitionCost  it records, for the calls the mode decision
+ * (JM/lencod/src/mv_search.c:1159-1250) and its twin BPredPartitionCost (:589-700): linked with  -Wl,--wrap=BIDPartitionCost,--wrap=BPredPartitionCost  it records, for the calls the mode decision
  * makes (mode_decision.c), the b2me_bid_job record a drop-in shim would hand to the GPU -- built by the SAME code,
  * integration/jm/b2me_jm_bid_job.h -- and what the unmodified function returned, plus the luma pictures it read, into the
  * binary file named by $B2_WRAP_LOG.  The encoder's behaviour is unchanged: the real function runs.
  * Records (little endian):
  *   'C': int32 0x43, poc, W, H; W*H bytes: the current picture (pCurImg) -- whenever the coded picture changes; resets the slots
  *   'R': int32 0x52, slot, W, H; W*H bytes: integer luma of a reference picture -- first time the picture is met under this poc
- *   'B': int32 0x42, metric (ModeDecisionMetric), transform8x8, apply_weights, luma_log_weight_denom; sizeof(b2me_bid_job) bytes; int64 cost
+ *   'B': int32 0x42, metric (ModeDecisionMetric), transform8x8, apply_weights | twin << 1 (twin: the call was BPredPartitionCost), luma_log_weight_denom; sizeof(b2me_bid_job) bytes; int64 cost
  * Every $B2_WRAP_STRIDE-th call is kept (default 1). */
 #include <stdio.h>
 #include <stdlib.h>
@@ -42,6 +42,38 @@ static int slot_of(VideoParameters *p_Vid, StorablePicture *p)
   return g_nslot++;
 }
 
+static void log_call(Macroblock *currMB, StorablePicture *p0, StorablePicture *p1, const b2me_bid_job *Jin, int wp, int twin, distblk c)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  Slice *currSlice = currMB->p_Slice;
+  b2me_bid_job J = *Jin;
+  if (p_Vid->enc_picture->poc != g_poc) {
+    g_poc = p_Vid->enc_picture->poc; g_nslot = 0;
+    w32(0x43); w32(g_poc); w32(p_Vid->width); w32(p_Vid->height);
+    plane(p_Vid->pCurImg, p_Vid->width, p_Vid->height);
+  }
+  J.ref_l0 = (int16_t)slot_of(p_Vid, p0); J.ref_l1 = (int16_t)slot_of(p_Vid, p1);
+  w32(0x42); w32(currSlice->p_Inp->ModeDecisionMetric); w32(currSlice->p_Inp->Transform8x8Mode != 0); w32(wp | (twin << 1)); w32(currSlice->luma_log_weight_denom);
+  fwrite(&J, sizeof(J), 1, logf_());
+  { long long v = (long long)c; fwrite(&v, 8, 1, logf_()); }
+}
+
+/* the twin: the same cost on the vectors of the bi-predictive motion search (mode_decision.c:366, 372) */
+distblk __real_BPredPartitionCost(Macroblock *currMB, int blocktype, int block8x8, short ref_l0, short ref_l1, int lambda_factor, int list);
+distblk __wrap_BPredPartitionCost(Macroblock *currMB, int blocktype, int block8x8, short ref_l0, short ref_l1, int lambda_factor, int list)
+{
+  VideoParameters *p_Vid = currMB->p_Vid;
+  Slice *currSlice = currMB->p_Slice;
+  const distblk c = __real_BPredPartitionCost(currMB, blocktype, block8x8, ref_l0, ref_l1, lambda_factor, list);
+  b2me_bid_job J;
+  int wp;
+  logf_();
+  if (p_Vid->mb_aff_frame_flag || p_Vid->structure != FRAME || (g_calls++ % g_stride)) return c;
+  wp = b2_bpred_build_job(currMB, blocktype, block8x8, ref_l0, ref_l1, lambda_factor, list, 0, 0, &J);
+  log_call(currMB, currSlice->listX[LIST_0 + currMB->list_offset][ref_l0], currSlice->listX[LIST_1 + currMB->list_offset][ref_l1], &J, wp, 1, c);
+  return c;
+}
+
 distblk __real_BIDPartitionCost(Macroblock *currMB, int blocktype, int block8x8, char cur_ref[2], int lambda_factor);
 distblk __wrap_BIDPartitionCost(Macroblock *currMB, int blocktype, int block8x8, char cur_ref[2], int lambda_factor)
 {
@@ -49,19 +81,10 @@ distblk __wrap_BIDPartitionCost(Macroblock *currMB, int blocktype, int block8x8,
   Slice *currSlice = currMB->p_Slice;
   const distblk c = __real_BIDPartitionCost(currMB, blocktype, block8x8, cur_ref, lambda_factor);
   b2me_bid_job J;
-  int wp, s0, s1;
+  int wp;
   logf_();
   if (p_Vid->mb_aff_frame_flag || p_Vid->structure != FRAME || (g_calls++ % g_stride)) return c;
-  if (p_Vid->enc_picture->poc != g_poc) {
-    g_poc = p_Vid->enc_picture->poc; g_nslot = 0;
-    w32(0x43); w32(g_poc); w32(p_Vid->width); w32(p_Vid->height);
-    plane(p_Vid->pCurImg, p_Vid->width, p_Vid->height);
-  }
-  s0 = slot_of(p_Vid, currSlice->listX[LIST_0 + currMB->list_offset][(int)cur_ref[LIST_0]]);
-  s1 = slot_of(p_Vid, currSlice->listX[LIST_1 + currMB->list_offset][(int)cur_ref[LIST_1]]);
-  wp = b2_bid_build_job(currMB, blocktype, block8x8, cur_ref, lambda_factor, s0, s1, &J);
-  w32(0x42); w32(currSlice->p_Inp->ModeDecisionMetric); w32(currSlice->p_Inp->Transform8x8Mode != 0); w32(wp); w32(currSlice->luma_log_weight_denom);
-  fwrite(&J, sizeof(J), 1, logf_());
-  { long long v = (long long)c; fwrite(&v, 8, 1, logf_()); }
+  wp = b2_bid_build_job(currMB, blocktype, block8x8, cur_ref, lambda_factor, 0, 0, &J);
+  log_call(currMB, currSlice->listX[LIST_0 + currMB->list_offset][(int)cur_ref[LIST_0]], currSlice->listX[LIST_1 + currMB->list_offset][(int)cur_ref[LIST_1]], &J, wp, 0, c);
   return c;
 }

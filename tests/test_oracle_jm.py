@@ -312,7 +312,7 @@ def _bid_golden():
     """(tag, cur, refs, jobs, cost, par) per captured B picture of tests/golden/jm_bid.npz"""
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "jm_bid.npz"))
-    for tag in "stw":
+    for tag in "stwp":
         for i in range(int(g[f"{tag}_n"])):
             yield tag, g[f"{tag}{i}_cur"], g[f"{tag}{i}_refs"], g[f"{tag}{i}_jobs"], g[f"{tag}{i}_cost"], g[f"{tag}{i}_par"]
 
@@ -320,16 +320,17 @@ def _bid_golden():
 def test_bid_partition_cost_restatement_matches_reference_golden():
     """orc_bid_partition_cost against what the UNMODIFIED BIDPartitionCost (JM/lencod/src/mv_search.c:1159-1250) returned for the
     calls of stock lencod runs (tests/golden/jm_bid.npz, oracle/gen_golden_bid.py): every block type, two references per list,
-    8x8 transform on, implicit weighted bi-prediction on a fading clip."""
-    n = 0
+    8x8 transform on, implicit weighted bi-prediction on a fading clip; with bi-predictive motion estimation on, also the calls of its
+    twin BPredPartitionCost (:589-700, the same cost on the bipred_mv vectors; last column of `par`)."""
+    n = twin = 0
     for tag, cur, refs, jobs, cost, par in _bid_golden():
         of = oracle.OrcFrame(cur, refs, 8)
         for p in np.unique(par, axis=0):
             m = (par == p).all(axis=1)
             got = of.bid_partition_cost(jobs[m], int(p[0]), bool(p[1]), bool(p[2]), int(p[3]))
             assert (got == cost[m]).all(), (tag, p, jobs[m][got != cost[m]][:2])
-            n += int(m.sum())
-    assert n > 1000
+            n += int(m.sum()); twin += int(m.sum()) * int(p[4])
+    assert n > 1600 and twin > 50
 
 
 def test_chroma_prediction_restatement_matches_reference():
