@@ -419,17 +419,21 @@ constexpr int EPZS_VCAP = 768;        // visited vectors per job (overflow: the 
 #endif
 constexpr int EPZS_MINB = EPZS_MINBV;   // resident CTAs per SM asked of ptxas.  Measured: 8 / 12 / 16 (64 / 40 / 32 registers, spills) give 0.89 / 1.49 / 2.01 ms against 0.89 at 5: the kernel is bound by its own instruction count (1 900 per job, 66 % issue), not by latency
 
-__device__ __forceinline__ bool epzs_visit(uint32_t *vis, int &nvis, int x, int y, bool &ovf)
+// The visited set: vectors 0..63 live in two registers per lane (lane l holds vectors l and l + 32: a membership test is one
+// compare per register and a vote, an insertion a predicated move), later ones in the shared-memory list.
+struct EpzsVis { uint32_t v0, v1; uint32_t *list; int n; bool ovf; };
+__device__ __forceinline__ bool epzs_visit(EpzsVis &V, int x, int y)
 {
   const int lane = threadIdx.x & 31;
   const uint32_t key = ((uint32_t)(x & 0xffff) << 16) | (uint32_t)(y & 0xffff);
-  bool hit = false;
-  for (int i = lane; i < nvis; i += 32) hit |= vis[i] == key;
+  bool hit = (lane < V.n && V.v0 == key) || (lane + 32 < V.n && V.v1 == key);
+  for (int i = 64 + lane; i < V.n; i += 32) hit |= V.list[i] == key;
   if (__any_sync(0xffffffffu, hit)) return false;
-  if (nvis >= EPZS_VCAP) { ovf = true; return true; }
-  if (lane == 0) vis[nvis] = key;
-  nvis++;
-  __syncwarp();
+  if (V.n >= EPZS_VCAP) { V.ovf = true; return true; }
+  if (V.n < 32) { if (lane == V.n) V.v0 = key; }
+  else if (V.n < 64) { if (lane == V.n - 32) V.v1 = key; }
+  else { if (lane == 0) V.list[V.n] = key; __syncwarp(); }
+  V.n++;
   return true;
 }
 
@@ -439,8 +443,8 @@ __global__ void __launch_bounds__(128, EPZS_MINB) k_epzs(const EpzsArgs a)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, ji = blockIdx.x * 4 + w;
   if (ji >= a.njobs) return;
   const b2me_epzs_job J = a.jobs[ji];
-  uint32_t *vis = s_vis[w];
-  int nvis = 0; bool ovf = false;
+  EpzsVis V; V.v0 = V.v1 = 0u; V.list = s_vis[w]; V.n = 0; V.ovf = false;
+  bool &ovf = V.ovf;
   bool bad = J.blocktype < 1 || J.blocktype > 7 || J.ref < 0 || J.ref >= a.nrefs || J.pos_x < 0 || J.pos_y < 0;
   const PartGeom gm = part_geom(part_first(bad ? 1 : J.blocktype));
   const int bsx = gm.w, bsy = gm.h;
@@ -455,12 +459,12 @@ __global__ void __launch_bounds__(128, EPZS_MINB) k_epzs(const EpzsArgs a)
   // bsx / 4 x bsy words); an integer-pel candidate inside the search plane is read as ALIGNED words of the byte-shifted plane
   // (column & 3) -- one VABSDIFF4 per four samples instead of two byte loads per sample.  The search plane is the
   // edge-replicated integer picture, i.e. exactly what UMVLine4X's origin clamp delivers (sad_fs.cu, exactness note).
-  const int wpr = bsx >> 2, nw = wpr * bsy;
+  const int wpr = bsx >> 2, nw = wpr * bsy, lw = bsx == 16 ? 2 : (bsx == 8 ? 1 : 0);      // words per row (1, 2 or 4: a shift), words per block
   uint32_t cw[2] = {0u, 0u};
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const int k = lane + 32 * h;
-    if (k < nw) cw[h] = *reinterpret_cast<const uint32_t *>(cur + (size_t)(k / wpr) * a.cur_pitch + 4 * (k % wpr));
+    if (k < nw) cw[h] = *reinterpret_cast<const uint32_t *>(cur + (size_t)(k >> lw) * a.cur_pitch + 4 * (k & (wpr - 1)));
   }
   const bool cur_aligned = ((J.pos_x | a.cur_pitch) & 3) == 0;
   auto sad = [&](int tx, int ty) -> long long {                  // computeSAD << 5 (me_distortion.c:349-426), no early exit
@@ -473,7 +477,7 @@ __global__ void __launch_bounds__(128, EPZS_MINB) k_epzs(const EpzsArgs a)
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const int k = lane + 32 * h;
-          if (k < nw) s = sad4(cw[h], __ldg(reinterpret_cast<const uint32_t *>(pl + (size_t)(k / wpr) * a.Wq + 4 * (k % wpr))), s);
+          if (k < nw) s = sad4(cw[h], __ldg(reinterpret_cast<const uint32_t *>(pl + (size_t)(k >> lw) * a.Wq + 4 * (k & (wpr - 1)))), s);
         }
         npts++;
         return (long long)__reduce_add_sync(0xffffffffu, s) << 5;
@@ -494,7 +498,7 @@ __global__ void __launch_bounds__(128, EPZS_MINB) k_epzs(const EpzsArgs a)
   int tx = mvx, ty = mvy, t2x = 0, t2y = 0;                       // tmp (best), tmp2 (second best)
   int early = 1;
   const bool pgate = (J.flags & B2ME_EPZS_REFGT0_FRAME) != 0;
-  epzs_visit(vis, nvis, mvx, mvy, ovf);
+  epzs_visit(V, mvx, mvy);
   long long minc = mvc(mvx, mvy);
   minc += sad(mvx, mvy);
   bool done = pgate && J.prev_sad < (J.stop0 < minc ? J.stop0 : minc);            // :118
@@ -506,19 +510,85 @@ __global__ void __launch_bounds__(128, EPZS_MINB) k_epzs(const EpzsArgs a)
       long long second = BI_DISTBLK_MAX;
       const bool use[4] = {true, J.cond_host[1] && minc > stop, J.fixed_edge || (J.cond_host[2] && minc > 3 * stop),
                            (J.cond_host[3] & 1) && ((J.cond_host[3] & 2) || minc > 2 * stop)};
-      int pi = J.pred_first;
-      for (int g = 0; g < 4; g++) {
-        for (int k = 0; k < J.npred[g]; k++, pi++) {
-          if (!use[g]) continue;
-          const int px = (int)(short)(a.preds[2 * pi] & (short)0xFFFC), py = (int)(short)(a.preds[2 * pi + 1] & (short)0xFFFC);   // set_integer_mv
-          if (!inrange(px, py)) continue;
-          if (!epzs_visit(vis, nvis, px, py, ovf)) continue;
-          long long mc = mvc(px, py);
-          if (mc < second) {
-            mc += sad(px, py);
-            if (mc < minc) { t2x = tx; t2y = ty; tx = px; ty = py; second = minc; minc = mc; checkMedian = true; }
-            else if (mc < second) { t2x = px; t2y = py; second = mc; checkMedian = true; }
+      // Predictor scan.  The raw predictors are fetched 32 at a time, one per lane, and handed round by shuffles.
+      // EPZS_NBV > 0 (measured, not the default): which predictors are looked at (group enabled, in range, not visited yet) does
+      // not depend on any distortion, so the scan can run in batches -- up to EPZS_NB admitted predictors collected, the
+      // reference words of ALL of them requested before the first SAD is formed, the reference's decisions replayed in order on
+      // the finished sums (a predictor whose vector cost is not below `second` at its turn is skipped as the reference skips
+      // it).  1080p, 41 partitions, five predictors: 0.80 ms one at a time, 0.86 ms in batches of 4, 1.08 ms in batches of 8
+      // (128 registers): the kernel is bound by its instruction count, the batches' bookkeeping costs more than the latency.
+#ifndef EPZS_NBV
+#define EPZS_NBV 0
+#endif
+      constexpr int EPZS_NB = EPZS_NBV > 0 ? EPZS_NBV : 1;      // EPZS_NBV == 0: no batches, one predictor at a time (still prefetched 32 at a time)
+      const int ntot = J.npred[0] + J.npred[1] + J.npred[2] + J.npred[3];
+      uint32_t pword = 0;
+      int bx_[EPZS_NB], by_[EPZS_NB], nb = 0;
+      for (int idx = 0; idx <= ntot; idx++) {
+        bool admit = false; int px = 0, py = 0;
+        if (idx < ntot) {
+          if ((idx & 31) == 0) pword = (idx + lane < ntot) ? reinterpret_cast<const uint32_t *>(a.preds)[J.pred_first + idx + lane] : 0u;
+          const uint32_t wv = __shfl_sync(0xffffffffu, pword, idx & 31);
+          const int g = idx < J.npred[0] ? 0 : (idx < J.npred[0] + J.npred[1] ? 1 : (idx < J.npred[0] + J.npred[1] + J.npred[2] ? 2 : 3));
+          px = (int)(short)((wv & 0xffffu) & 0xFFFCu); py = (int)(short)((wv >> 16) & 0xFFFCu);                       // set_integer_mv
+          admit = use[g] && inrange(px, py) && epzs_visit(V, px, py);
+          if (EPZS_NBV == 0) {
+            if (admit) {
+              long long mc = mvc(px, py);
+              if (mc < second) {
+                mc += sad(px, py);
+                if (mc < minc) { t2x = tx; t2y = ty; tx = px; ty = py; second = minc; minc = mc; checkMedian = true; }
+                else if (mc < second) { t2x = px; t2y = py; second = mc; checkMedian = true; }
+              }
+            }
+            continue;
           }
+          if (admit) {
+#pragma unroll
+            for (int e = 0; e < EPZS_NB; e++) if (e == nb) { bx_[e] = px; by_[e] = py; }
+            nb++;
+          }
+        }
+        if (nb == EPZS_NB || (idx == ntot && nb > 0)) {
+          // ---- all reference words of the batch, then the sums ----
+          long long bs_[EPZS_NB];
+          uint32_t rw0[EPZS_NB], rw1[EPZS_NB];
+          bool fast[EPZS_NB];
+#pragma unroll
+          for (int e = 0; e < EPZS_NB; e++) {
+            fast[e] = false; rw0[e] = rw1[e] = 0u;
+            if (e < nb && cur_aligned) {
+              const int X = J.pos_x + (bx_[e] >> 2) + a.spad, Y = J.pos_y + (by_[e] >> 2) + a.spad;
+              if (X >= 0 && Y >= 0 && X + bsx <= a.Wq && Y + bsy <= a.Hq) {
+                fast[e] = true;
+                const int c = X & 3;
+                const uint8_t *pl = a.spl + ((size_t)(J.ref * 16 + c) * a.Hq + Y) * a.Wq + (X - c);
+                if (lane < nw) rw0[e] = __ldg(reinterpret_cast<const uint32_t *>(pl + (size_t)(lane >> lw) * a.Wq + 4 * (lane & (wpr - 1))));
+                if (lane + 32 < nw) rw1[e] = __ldg(reinterpret_cast<const uint32_t *>(pl + (size_t)((lane + 32) >> lw) * a.Wq + 4 * ((lane + 32) & (wpr - 1))));
+              }
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < EPZS_NB; e++) {
+            bs_[e] = 0;
+            if (e < nb && fast[e]) {
+              uint32_t sv = lane < nw ? sad4(cw[0], rw0[e], 0u) : 0u;
+              if (lane + 32 < nw) sv = sad4(cw[1], rw1[e], sv);
+              bs_[e] = (long long)__reduce_add_sync(0xffffffffu, sv) << 5;
+            }
+          }
+          // ---- the reference's decisions, in order ----
+#pragma unroll
+          for (int e = 0; e < EPZS_NB; e++) {
+            if (e >= nb) continue;
+            long long mc = mvc(bx_[e], by_[e]);
+            if (mc < second) {
+              if (fast[e]) { mc += bs_[e]; npts++; } else mc += sad(bx_[e], by_[e]);
+              if (mc < minc) { t2x = tx; t2y = ty; tx = bx_[e]; ty = by_[e]; second = minc; minc = mc; checkMedian = true; }
+              else if (mc < second) { t2x = bx_[e]; t2y = by_[e]; second = mc; checkMedian = true; }
+            }
+          }
+          nb = 0;
         }
       }
       if ((J.flags & B2ME_EPZS_EARLY34) && minc < ((3 * stop) >> 2)) done = true;  // :586 (sub-macroblock variant)
@@ -539,7 +609,7 @@ __global__ void __launch_bounds__(128, EPZS_MINB) k_epzs(const EpzsArgs a)
             int checkPts = totalCheckPts;
             do {
               const int qx = cx + P->pt[pointNumber].dx, qy = cy + P->pt[pointNumber].dy;
-              if (inrange(qx, qy) && epzs_visit(vis, nvis, qx, qy, ovf)) {
+              if (inrange(qx, qy) && epzs_visit(V, qx, qy)) {
                 long long mc = mvc(qx, qy);
                 if (mc < minc) {
                   mc += sad(qx, qy);
