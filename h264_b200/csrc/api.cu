@@ -15,6 +15,21 @@ extern "C" int b2me_version(void) { return 100; }
 
 extern "C" const char *b2me_last_error(b2me_ctx *ctx) { return ctx ? ctx->err : g_err; }
 
+namespace b2 {
+void b2_pool_retain(int device)
+{
+  static unsigned char done[64] = {0};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done[device] = 1;
+}
+}  // namespace b2
+
 extern "C" int b2me_create(b2me_ctx **out, int device, int width, int height, int nrefs, int search_range)
 {
   if (!out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || nrefs < 1 || nrefs > 16 ||
@@ -37,6 +52,7 @@ extern "C" int b2me_create(b2me_ctx **out, int device, int width, int height, in
   c->plane_size = (size_t)c->Wp * c->Hp;
   *out = c;
   B2_CUDA_CHECK(c, cudaSetDevice(device));
+  b2_pool_retain(device);
   B2_CUDA_CHECK(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   const size_t n = (size_t)c->nmb * nrefs * NPART;
   B2_CUDA_CHECK(c, cudaMalloc(&c->d_cur, (size_t)width * height));

@@ -119,6 +119,10 @@ cudaError_t launch_select_gather(int nmb, int nrefs, const long long *cost, int 
 cudaError_t launch_subpel_planes(const uint8_t *luma, int pitch, int W, int H, uint8_t *planes16, int row_lo, int row_hi, cudaStream_t s);
 cudaError_t launch_sad_fs(const FsArgs &a, const CUtensorMap *tm, int sm_count, cudaStream_t s, int *smem_bytes_out);
 FsGeom fs_geom_host(int R);
+// Stream-ordered scratch (cudaMallocAsync) is used by the host-pointer entries and by b2dbk_frame_dev.  By default the device's
+// memory pool hands freed memory back to the driver at every synchronisation, which turns the next cudaMallocAsync into a real
+// allocation on the host -- milliseconds, inside whatever the caller is timing.  Keep it in the pool (once per device).
+void b2_pool_retain(int device);
 cudaError_t launch_apply_wp(uint8_t *buf, size_t bytes, int weight, int offset, int log_denom, cudaStream_t s);
 cudaError_t launch_search_plane(const uint8_t *luma, int pitch, int W, int H, uint8_t *out, int Wq, int Hq, int spad, int row_lo, int row_hi, cudaStream_t s);
 cudaError_t launch_subpel_refine(const SubArgs &a, cudaStream_t s);

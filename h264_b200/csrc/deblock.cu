@@ -28,6 +28,7 @@
 #include <cstdio>
 #include "b2_common.cuh"
 #include "../../include/b2me.h"
+#include "b2_ctx.h"
 
 namespace b2 {
 
@@ -447,6 +448,7 @@ extern "C" int b2dbk_frame_dev(int W, int H, uint8_t *y, int y_pitch, uint8_t *u
   }
   DbkArgs a;
   a.W = W; a.H = H; a.mbw = W / 16; a.mbh = H / 16; a.y = y; a.yp = y_pitch; a.u = u; a.v = v; a.cp = c_pitch; a.mbs = mbs; a.blks = blks; a.progress = progress;
+  b2_pool_retain(dev);
   DbkRec *rec = nullptr;
   const int nmb = a.mbw * a.mbh;
   const size_t cnt_bytes = sizeof(int) * DBK_PSTRIDE * (size_t)a.mbh;
