@@ -146,7 +146,7 @@ struct __align__(16) FsWarp {
   int nrec;                      // records appended since the last flush (may exceed FS_RCAP: overflow)
 };
 #ifndef FS_SPARSEV
-#define FS_SPARSEV 3
+#define FS_SPARSEV 8
 #endif
 constexpr int FS_SPARSE = FS_SPARSEV;     // at most this many lanes of a warp pass the group filter at once: their packed sums cross through shared memory
 
