@@ -138,7 +138,10 @@ struct FsCtl {                    // per window buffer: the pipeline between the
   int epoch, tma_uses;
 };
 
-constexpr int FS_DENSE = 12;     // candidates of a warp passing the cold path's test at once from which the dense collapse runs
+#ifndef FS_DENSEV
+#define FS_DENSEV 32
+#endif
+constexpr int FS_DENSE = FS_DENSEV;     // candidates of a warp passing the cold path's test at once from which the dense collapse runs
 constexpr int FS_RCAP = 24;      // survivor records per warp and task
 struct __align__(16) FsWarp {
   unsigned short sat[2][28];     // fs_exact2's summed-area tables (row 0 / column 0 stay zero)
