@@ -182,9 +182,13 @@ struct FrArgs {
 };
 
 constexpr int FR_NT = 256;
+#ifndef FR_MINBV
+#define FR_MINBV 2
+#endif
+constexpr int FR_MINB = FR_MINBV;      // resident CTAs per SM asked of ptxas (164 registers left one CTA of 8 warps per SM: 11 % issue)
 
 // One CTA per macroblock: all displacements x 41 partitions.
-__global__ void __launch_bounds__(FR_NT) k_frac_window(const FrArgs a)
+__global__ void __launch_bounds__(FR_NT, FR_MINB) k_frac_window(const FrArgs a)
 {
   extern __shared__ __align__(16) uint8_t sm[];
   const int R = a.R, ww = 16 + 2 * R;
