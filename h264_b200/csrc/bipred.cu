@@ -116,7 +116,7 @@ __device__ int bi_dist(const BiArgs &a, const uint8_t *cur /* smem, pitch 16 */,
 
 constexpr long long BI_DISTBLK_MAX = ((long long)0x7fffffff) << 5;
 
-__global__ void __launch_bounds__(128) k_bipred(const BiArgs a)
+__global__ void __launch_bounds__(128, 8) k_bipred(const BiArgs a)   // 8 CTAs per SM: 64 registers (127 left four CTAs = 16 warps per SM for a latency-bound kernel)
 {
   __shared__ uint8_t cur[256];
   __shared__ unsigned long long key;
